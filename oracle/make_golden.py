@@ -1,0 +1,261 @@
+"""TEST INFRASTRUCTURE ONLY — writes tests/golden/*.npz by running the UNMODIFIED reference.
+
+Run in the build container (needs /root/reference):   python -m oracle.make_golden
+
+Every golden is produced by the reference's own modules (imported through oracle/ref_shim.py):
+`PlanningModel.forward`, the four `LightningTrainer._compute_objectives`, the reference
+`configure_optimizers()` parameter grouping + torch AdamW + clip_grad_norm_(0.5) (Lightning's
+step order), numpy's mean/std for the group advantage, and the source text of
+`get_advantages_GAE` / `compute_return` exec'd from the reference files.  Inputs and parameters
+are NOT stored: they are regenerated from seeds by rift_b200/synth.py (numpy PCG64, portable).
+
+Deterministic parity mode: trunk in eval() (dropout/droppath identity, BatchNorm
+running statistics), parameters randomised by synth_state_dict (seed 7).
+"""
+import ast
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+from oracle import ref_shim  # noqa: E402
+from oracle.pluto_oracle import to_torch  # noqa: E402
+from rift_b200.config import MODEL_ZOO, param_spec, is_buffer  # noqa: E402
+from rift_b200.synth import synth_state_dict, synth_features, synth_rl_extras  # noqa: E402
+
+GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+CASES = {
+    # name: model, model kwargs, batch shape, ragged
+    "cfg1_small": dict(model="small", kw=dict(future_steps=40), bs=1, A=8, Mp=20, R=1, ragged=False),
+    "ragged_small": dict(model="small", kw={}, bs=3, A=9, Mp=11, R=3, ragged=True),
+    "medium_tiny": dict(model="medium", kw={}, bs=2, A=6, Mp=7, R=2, ragged=True),
+}
+TRAINER_KW = dict(lr=1e-4, cl_lr_decay=0.9, weight_decay=1e-5, epochs=16, warmup_epochs=3, frame_rate=10)
+
+
+def _ref_function(relpath: str, name: str, extra_globals=None):
+    """exec one top-level function of a reference file without importing the file."""
+    src = open(os.path.join(ref_shim.REF, relpath)).read()
+    for node in ast.parse(src).body:
+        if isinstance(node, ast.FunctionDef) and node.name == name:
+            g = {"torch": torch, "np": np}
+            g.update(extra_globals or {})
+            exec(compile(ast.Module([node], []), relpath, "exec"), g)
+            return g[name]
+    raise KeyError(name)
+
+
+def build_batch(cfg, case, algo):
+    PlutoFeature = ref_shim.pluto_feature_cls()
+    feats = synth_features(cfg, case["bs"], case["A"], case["Mp"], case["R"], seed=1, ragged=case["ragged"])
+    ex = synth_rl_extras(cfg, feats, seed=2)
+    batch = {"cur_pluto_feature_torch": PlutoFeature(data=to_torch(feats))}
+    for k in ("group_advantage", "group_advantage_mask", "old_group_logits", "ref_group_logits",
+              "state", "advantage", "reward_sum", "old_log_prob", "action_mode", "return"):
+        batch[k + "_torch"] = torch.from_numpy(ex[k].copy())
+    return batch
+
+
+def build_model(cfg, algo):
+    if algo == "ppo":
+        Model = ref_shim.ppo_pluto_model_cls()
+        m = Model(radius=cfg.radius, state_dim=cfg.dim, action_dim=1, hidden_dim=list(cfg.value_hidden),
+                  dim=cfg.dim, num_heads=cfg.num_heads, encoder_depth=cfg.encoder_depth,
+                  decoder_depth=cfg.decoder_depth, future_steps=cfg.future_steps)
+    else:
+        m = ref_shim.planning_model_cls()(
+            radius=cfg.radius, dim=cfg.dim, num_heads=cfg.num_heads, encoder_depth=cfg.encoder_depth,
+            decoder_depth=cfg.decoder_depth, future_steps=cfg.future_steps)
+    sd = {k: torch.from_numpy(v) for k, v in synth_state_dict(cfg, seed=7).items()}
+    m.load_state_dict(sd, strict=True)
+    return m
+
+
+class _Store(dict):
+    """Large tensors are stored as an every-7th-element sample plus (sum, l2) so the fixtures stay small."""
+
+    def put(self, key, arr):
+        arr = np.asarray(arr)
+        if arr.size > 20000:
+            flat = arr.reshape(-1)
+            self[key + "@s7"] = flat[::7].copy()
+            self[key + "@stats"] = np.array([flat.astype(np.float64).sum(),
+                                             np.sqrt((flat.astype(np.float64) ** 2).sum())])
+        else:
+            self[key] = arr.copy()
+
+
+def run_case(name, case):
+    out = _Store()
+    for algo in ("rift", "grpo", "ppo", "reinforce"):
+        kw = dict(case["kw"])
+        if algo == "ppo":
+            kw["value_hidden"] = (256, 256)
+        cfg = MODEL_ZOO[case["model"]](**kw)
+        for mode in ("pi_head", "full"):
+            if mode == "full" and algo in ("reinforce",):
+                continue
+            model = build_model(cfg, algo)
+            layers = ["planning_decoder.pi_head"] if mode == "pi_head" else \
+                [n for n, _ in model.named_children()]
+            if algo == "ppo" and mode == "pi_head":
+                layers = layers + ["value_net"]
+            Trainer = ref_shim.trainer_cls(algo)
+            tr = Trainer(model=model, trainable_layers=layers, **TRAINER_KW)
+            tr.train()
+            tr.model.eval()                       # deterministic parity mode
+            batch = build_batch(cfg, case, algo)
+            data = batch["cur_pluto_feature_torch"].data
+            res = tr.forward(data)
+            if algo == "rift" and mode == "pi_head":
+                for k in ("probability", "trajectory", "prediction", "hidden", "ref_free_trajectory",
+                          "output_trajectory", "candidate_trajectories"):
+                    out.put("out_" + k, res[k].detach().numpy())
+                out["out_best_index"] = res["probability"].detach().reshape(case["bs"], -1).argmax(-1).numpy()
+            prob = res["probability"]
+            prob.retain_grad()
+            losses = tr._compute_objectives(res, data, batch)
+            loss = losses["loss"]
+            out[f"loss_{algo}"] = np.asarray(loss.detach().double().numpy())
+            loss.backward()
+            if mode == "pi_head":
+                out[f"dlogits_{algo}"] = prob.grad.numpy().copy()
+            named = dict(tr.model.named_parameters())
+            if mode == "pi_head" and algo in ("rift", "grpo", "ppo"):
+                for n, p in named.items():
+                    if p.grad is not None and n.startswith("planning_decoder.pi_head"):
+                        out.put(f"grad_{algo}/{n}", p.grad.numpy())
+                if algo == "ppo":
+                    for n, p in named.items():
+                        if n.startswith("value_net") and p.grad is not None:
+                            out.put(f"grad_{algo}/{n}", p.grad.numpy())
+            if mode == "full" and algo in ("rift", "grpo", "ppo"):
+                names = [n for n, _, _ in param_spec(cfg) if not is_buffer(n)]
+                stats = np.zeros((len(names), 3), np.float64)
+                for i, n in enumerate(names):
+                    g = named[n].grad
+                    if g is not None:
+                        g = g.double()
+                        stats[i] = (g.sum(), g.pow(2).sum().sqrt(), g.flatten()[g.numel() // 2])
+                out[f"fullgrad_{algo}_stats"] = stats
+                # a few complete tensors from different corners of the graph
+                for n in ("pos_emb.freqs.weight", "agent_encoder.history_encoder.embed.proj.weight",
+                          "agent_encoder.history_encoder.levels.1.blocks.0.attn.rpb",
+                          "agent_encoder.ego_state_emb.query", "agent_encoder.type_emb.weight",
+                          "map_encoder.polygon_encoder.first_mlp.0.weight",
+                          "map_encoder.speed_limit_emb.mlps.0.3.bias", "encoder_blocks.0.attn.in_proj_bias",
+                          "planning_decoder.m_pos", "planning_decoder.m_emb",
+                          "planning_decoder.r_encoder.second_mlp.1.weight",
+                          "planning_decoder.decoder_blocks.1.norm2.weight",
+                          "planning_decoder.cat_x_proj.bias"):
+                    g = named[n].grad
+                    out.put(f"fullgrad_{algo}/{n}", (torch.zeros_like(named[n]) if g is None else g).numpy())
+            # optimizer: the reference grouping, torch AdamW, Lightning's clip -> step order
+            if algo in ("grpo", "ppo") and mode == "pi_head":
+                mod = sys.modules[Trainer.__module__]
+                saved = mod.WarmupCosLR
+                mod.WarmupCosLR = lambda **k: None      # ctor is incompatible with torch>=2.2
+                try:
+                    (opt,), _ = tr.configure_optimizers()
+                finally:
+                    mod.WarmupCosLR = saved
+                if algo == "grpo":
+                    pd = dict(tr.named_parameters())
+                    inv = {id(p): n for n, p in pd.items()}
+                    out["optim_groups"] = np.array(json.dumps(
+                        [sorted(inv[id(p)][len("model."):] for p in g["params"]) for g in opt.param_groups]))
+                for step in range(3):
+                    if step > 0:
+                        tr.zero_grad()
+                        b2 = build_batch(cfg, case, algo)
+                        r2 = tr.forward(b2["cur_pluto_feature_torch"].data)
+                        l2 = tr._compute_objectives(r2, b2["cur_pluto_feature_torch"].data, b2)["loss"]
+                        l2.backward()
+                        out[f"loss_{algo}_step{step}"] = np.asarray(l2.detach().double().numpy())
+                    tn = torch.nn.utils.clip_grad_norm_(
+                        [p for p in tr.parameters() if p.requires_grad], 0.5)
+                    out[f"gradnorm_{algo}_step{step}"] = np.asarray(tn.double().numpy())
+                    opt.step()
+                    if step in (0, 2):
+                        for n, p in named.items():
+                            if p.requires_grad:
+                                out.put(f"param_{algo}_step{step + 1}/{n}", p.detach().numpy())
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)
+    print(name, len(out), "arrays", sum(v.nbytes for v in out.values()) // 1024, "KiB")
+
+
+def advantage_goldens():
+    """traj_evaluator.py:466-469 evaluated literally by numpy, per group."""
+    rng = np.random.Generator(np.random.PCG64(11))
+    out = {}
+    for G in (2, 7, 8, 12, 24, 72, 96, 128, 129, 144, 300, 1000):
+        ret = rng.normal(-5.0, 20.0, (6, G))
+        ret[1] = ret[1, 0]                      # constant group -> std 0 -> divides by 1e-5
+        ret[2, : G // 2] = -200.0               # collision-dominated group
+        adv = np.empty_like(ret)
+        for i in range(ret.shape[0]):
+            returns = ret[i]
+            mean_return = np.mean(returns)
+            std_return = np.std(returns) + 1e-5
+            adv[i] = (returns - mean_return) / std_return
+        out[f"ret_{G}"] = ret
+        out[f"adv_{G}"] = adv
+    np.savez_compressed(os.path.join(GOLDEN, "advantage.npz"), **out)
+    print("advantage", len(out))
+
+
+def buffer_pass_goldens():
+    gae = _ref_function("rift/cbv/planning/fine_tuner/rlft/ppo_pluto/ppo_datamodule.py", "get_advantages_GAE")
+    ret = _ref_function("rift/cbv/planning/fine_tuner/rlft/reinforce_pluto/reinforce_datamodule.py", "compute_return")
+    rng = np.random.Generator(np.random.PCG64(12))
+    n = 4096
+    rewards = torch.from_numpy(rng.normal(-0.5, 2.0, n).astype(np.float32))
+    dones = torch.from_numpy((rng.uniform(size=n) < 0.02).astype(np.float32))
+    term = torch.from_numpy(((rng.uniform(size=n) < 0.5) & (dones.numpy() > 0)).astype(np.float32))
+    values = torch.from_numpy(rng.normal(0, 3.0, n).astype(np.float32))
+    next_values = torch.from_numpy(rng.normal(0, 3.0, n).astype(np.float32))
+    adv = gae(rewards, 1 - dones, values, next_values, 1 - term)
+    reward_sum = adv + values
+    adv_n = (adv - adv.mean()) / (adv.std(dim=0) + 1e-5)      # ppo_datamodule.py:163
+    out = dict(rewards=rewards.numpy(), dones=dones.numpy(), terminated=term.numpy(), values=values.numpy(),
+               next_values=next_values.numpy(), gae=adv.numpy(), reward_sum=reward_sum.numpy(),
+               gae_normalised=adv_n.numpy())
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")          # its trailing "normalise" takes std of a 0-d tensor
+        r = ret(rewards.clone(), dones.clone())
+    out["discounted_return"] = r.numpy()
+    np.savez_compressed(os.path.join(GOLDEN, "buffer_pass.npz"), **out)
+    print("buffer_pass ok")
+
+
+def state_dict_spec():
+    spec = {}
+    for mname, kw in (("small", {}), ("medium", {})):
+        cfg = MODEL_ZOO[mname](**kw)
+        m = ref_shim.planning_model_cls()(radius=cfg.radius, dim=cfg.dim, num_heads=cfg.num_heads,
+                                          encoder_depth=cfg.encoder_depth, decoder_depth=cfg.decoder_depth)
+        spec[mname] = [[k, list(v.shape), str(v.dtype)] for k, v in m.state_dict().items()]
+    json.dump(spec, open(os.path.join(GOLDEN, "state_dict_spec.json"), "w"))
+    print("state_dict_spec", {k: len(v) for k, v in spec.items()})
+
+
+if __name__ == "__main__":
+    torch.manual_seed(0)
+    torch.set_num_threads(8)
+    os.makedirs(GOLDEN, exist_ok=True)
+    only = sys.argv[1:]
+    if not only or "spec" in only:
+        state_dict_spec()
+    if not only or "adv" in only:
+        advantage_goldens()
+    if not only or "buf" in only:
+        buffer_pass_goldens()
+    for name, case in CASES.items():
+        if not only or name in only:
+            run_case(name, case)

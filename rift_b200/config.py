@@ -229,6 +229,8 @@ def numel(shape) -> int:
 
 
 def is_buffer(name: str) -> bool:
-    """BatchNorm buffers and CriticPPO normalisation constants never receive gradients."""
-    return name.endswith((".running_mean", ".running_var", ".num_batches_tracked")) or \
-        name.startswith("value_net.state_") or name.startswith("value_net.value_")
+    """BatchNorm buffers never receive gradients.  CriticPPO's state_avg/state_std/value_avg/
+    value_std are nn.Parameters (rift/gym_carla/utils/net.py:360-363) which the reference's
+    freeze_parameters() switches to requires_grad=True whenever 'value_net' is trainable
+    (ppo_training.yaml:26-28, ppo_trainer.py:85-96), so they are parameters here too."""
+    return name.endswith((".running_mean", ".running_var", ".num_batches_tracked"))
