@@ -1,0 +1,176 @@
+/* rift_b200 — C ABI of the B200-native RIFT policy-update hot path.
+ *
+ * Drop-in boundary for the reference's fine-tuning inner loop (paths relative to the reference
+ * tree, CurryChen77/RIFT @ 49d643c):
+ *   PlanningModel.forward                   rift/cbv/planning/pluto/model/pluto_model.py:122-225
+ *   LightningTrainer.get_{rift,grpo,ppo,reinforce}_loss
+ *                                           rift/cbv/planning/fine_tuner/rlft/<algo>_pluto/<algo>_trainer.py
+ *   loss.backward / clip_grad_norm_ / AdamW rift/cbv/planning/fine_tuner/rlft/config/lightning/custom_lightning.yaml:40-41,
+ *                                           rift/cbv/planning/fine_tuner/rlft/rift_pluto/rift_trainer.py:279-362
+ *   group-relative advantage                rift/cbv/planning/fine_tuner/rlft/traj_eval/traj_evaluator.py:466-470
+ *   GAE / discounted return                 rift/cbv/planning/fine_tuner/rlft/ppo_pluto/ppo_datamodule.py:22-37,163
+ *                                           rift/cbv/planning/fine_tuner/rlft/reinforce_pluto/reinforce_datamodule.py:19-38
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch allocates; pass tensor.data_ptr())
+ *     unless the parameter is documented as host memory;
+ *   - every call is asynchronous on the `stream` argument (a cudaStream_t passed as void*; use
+ *     torch.cuda.current_stream().cuda_stream);
+ *   - return value 0 = ok, -1 = invalid argument, -2 = CUDA error; rift_b200_last_error() gives the text;
+ *   - no internal threads, no hidden allocations after rift_b200_create; a handle is not thread-safe;
+ *   - bool tensors are passed as uint8 (torch.bool storage), int8 categorical tensors as int8.
+ */
+#ifndef RIFT_B200_H
+#define RIFT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rift_b200_engine rift_b200_engine;
+
+const char* rift_b200_last_error(void);
+int rift_b200_version(void);
+/* number of CUDA kernels this library has launched so far in this process (bench.py: gpu_launches) */
+long long rift_b200_launch_count(void);
+
+/* ---- model description (PlanningModel.__init__, pluto_model.py:23-44) ---- */
+typedef struct {
+    int dim, num_heads, encoder_depth, decoder_depth, num_modes;
+    int history_steps, future_steps, state_channel, ref_points;
+    int value_hidden0, value_hidden1;      /* CriticPPO hidden widths, 0 = no value net */
+} rift_b200_model_config;
+
+/* one state-dict entry of the flat fp32 parameter arena (name = the reference's state_dict key) */
+typedef struct {
+    const char* name;        /* host string */
+    long long offset;        /* element offset into the arena */
+    long long numel;
+    int trainable;           /* LightningTrainer.freeze_parameters outcome (rift_trainer.py:78-90) */
+} rift_b200_param_entry;
+
+/* A collated PlutoFeature.data (pluto_feature.py:25-96) as raw device pointers. */
+typedef struct {
+    int bs, A, Mp, P, R, Pr;
+    int agent_T;                             /* stored time length of agent tensors (>= history_steps) */
+    const float* agent_position;             /* (bs, A, agent_T, 2) */
+    const float* agent_heading;              /* (bs, A, agent_T)    */
+    const float* agent_velocity;             /* (bs, A, agent_T, 2) */
+    const float* agent_shape;                /* (bs, A, agent_T, 2) */
+    const int8_t* agent_category;            /* (bs, A)             */
+    const uint8_t* agent_valid_mask;         /* (bs, A, agent_T)    */
+    const float* map_point_position;         /* (bs, Mp, 3, P, 2)   */
+    const float* map_point_vector;           /* (bs, Mp, 3, P, 2)   */
+    const float* map_point_orientation;      /* (bs, Mp, 3, P)      */
+    const float* map_polygon_center;         /* (bs, Mp, 3)         */
+    const int8_t* map_polygon_type;          /* (bs, Mp)            */
+    const uint8_t* map_polygon_on_route;     /* (bs, Mp)            */
+    const int8_t* map_polygon_tl_status;     /* (bs, Mp)            */
+    const uint8_t* map_polygon_has_speed_limit; /* (bs, Mp)         */
+    const float* map_polygon_speed_limit;    /* (bs, Mp)            */
+    const uint8_t* map_valid_mask;           /* (bs, Mp, P)         */
+    const float* ref_position;               /* (bs, R, Pr, 2)      */
+    const float* ref_vector;                 /* (bs, R, Pr, 2)      */
+    const float* ref_orientation;            /* (bs, R, Pr)         */
+    const uint8_t* ref_valid_mask;           /* (bs, R, Pr)         */
+    const float* current_state;              /* (bs, cs_stride), first state_channel columns used */
+    int cs_stride;
+} rift_b200_batch;
+
+/* Outputs of PlanningModel.forward; any pointer may be NULL to skip materialising that tensor. */
+typedef struct {
+    float* probability;          /* (bs, R, Mo) logits, padded reference lines filled with -1e6 */
+    float* trajectory;           /* (bs, R, Mo, T, 6) */
+    float* prediction;           /* (bs, A-1, T, 6)   */
+    float* hidden;               /* (bs, dim)         */
+    float* ref_free_trajectory;  /* (bs, T, 4)        */
+    float* candidate_trajectories; /* (bs, R, Mo, T, 3), needs trajectory */
+    uint8_t* r_padding_mask;     /* (bs, R) 1 = padded reference line */
+} rift_b200_outputs;
+
+/* ---- engine lifecycle ---- */
+int rift_b200_create(const rift_b200_model_config* cfg, const rift_b200_param_entry* entries, int n_entries,
+                     rift_b200_engine** out);
+void rift_b200_destroy(rift_b200_engine* e);
+/* params / grads: flat fp32 arenas laid out by `entries` (grads may be NULL for inference) */
+int rift_b200_bind_arena(rift_b200_engine* e, float* params, float* grads, long long numel);
+/* bytes of workspace rift_b200_forward/backward need for a batch of this shape */
+size_t rift_b200_workspace_bytes(const rift_b200_engine* e, const rift_b200_batch* shape);
+
+/* flags */
+#define RIFT_B200_FWD_SAVE_FOR_BACKWARD 1   /* keep activations needed by rift_b200_backward in the workspace */
+#define RIFT_B200_GEMM_SIMT 2               /* force the exact-fp32 SIMT GEMM (validation path) */
+
+int rift_b200_forward(rift_b200_engine* e, const rift_b200_batch* batch, const rift_b200_outputs* out,
+                      void* workspace, size_t workspace_bytes, int flags, void* stream);
+/* d(loss)/d(probability) -> gradient arena (accumulated with `=` semantics after an internal zero of the
+ * trainable range).  Must follow a forward with RIFT_B200_FWD_SAVE_FOR_BACKWARD on the same workspace. */
+int rift_b200_backward(rift_b200_engine* e, const rift_b200_batch* batch, const float* dlogits,
+                       void* workspace, size_t workspace_bytes, int flags, void* stream);
+
+/* ---- RL objectives (standalone operators; usable without an engine) ---- */
+/* RIFT (algo 0: clip [lo,hi] + dual clip) and GRPO (algo 1: clip + kl_weight * KL(ref || new)).
+ * logits/old/ref (bs,R,Mo) f32, advantage (bs,R,Mo) f64, valid (bs,R,Mo) u8, r_pad (bs,R) u8 or NULL.
+ * scratch: bs doubles + bs ints (use rift_b200_objective_scratch_bytes).
+ * out3 (device, 3 doubles) = { loss, sum of objectives over valid, valid count }.
+ * dlogits (may be NULL): d loss / d logits; if scale_by_count == 0 it is left multiplied by the valid
+ * count (data-parallel use: all-reduce gradients and counts first, rift_b200_clip_adamw divides). */
+size_t rift_b200_objective_scratch_bytes(int bs);
+int rift_b200_group_objective(int algo, const float* logits, const float* old_logits, const float* ref_logits,
+                              const double* advantage, const uint8_t* valid, const uint8_t* r_pad,
+                              int bs, int R, int Mo, float clip_lo, float clip_hi, float dual_clip, float kl_weight,
+                              void* scratch, double* out3, float* dlogits, int scale_by_count, void* stream);
+/* PPO (mode 0) / REINFORCE (mode 1).  inv_n = 1 / global batch size.  extra_loss (device float, may be
+ * NULL) is added to the scalar (PPO value loss).  loss_out: device float.  scratch: bs floats. */
+int rift_b200_action_objective(int mode, const float* logits, const uint8_t* r_pad, const long long* action_mode,
+                               const float* weight, const float* old_log_prob, int bs, int R, int Mo,
+                               float clip_epsilon, float lambda_entropy, float inv_n, const float* extra_loss,
+                               float* scratch, float* loss_out, float* dlogits, int* chosen, void* stream);
+int rift_b200_smooth_l1(const float* value, const float* target, int n, float inv_n, float* loss_out, float* dvalue,
+                        void* stream);
+
+/* ---- advantage / buffer passes ---- */
+/* (ret - mean) / (std + 1e-5) per group in float64, bit-identical to numpy (population std).
+ * offsets == NULL: n_groups contiguous groups of size G; else offsets[n_groups + 1] (int64 element offsets). */
+int rift_b200_group_advantage(const double* returns, const long long* offsets, long long n_groups, int G,
+                              double* advantage, void* stream);
+int rift_b200_gae(const float* rewards, const float* undones, const float* values, const float* next_values,
+                  const float* unterminated, int n, float gamma, float lambda_, float* advantage, float* reward_sum,
+                  float* advantage_normalised, void* stream);
+int rift_b200_discounted_return(const float* rewards, const float* dones, int n, float gamma, float* returns,
+                                void* stream);
+
+/* ---- optimizer: clip_grad_norm_(max_norm) + AdamW over the flat trainable range ---- */
+/* p/g/m/v: n elements each, 16-byte aligned; the first n_decay elements get weight_decay.
+ * count (device double, may be NULL): gradients are divided by it first (see group_objective).
+ * scratch: rift_b200_optim_scratch_bytes() bytes.  scal_out (device, 2 floats) = { grad norm, applied scale }. */
+size_t rift_b200_optim_scratch_bytes(void);
+int rift_b200_clip_adamw(float* p, const float* g, float* m, float* v, long long n, long long n_decay,
+                         const double* count, float max_norm, float lr, float beta1, float beta2, float eps,
+                         float weight_decay, int step, void* scratch, float* scal_out, void* stream);
+
+/* ---- primitive operators exported for the kernel-level parity tests (tests/test_ops_gpu.py) ---- */
+int rift_b200_op_linear(const float* x, int rows, int K, const float* w, const float* bias, int N, int act,
+                        const float* res, float* y, int simt, void* stream);
+int rift_b200_op_gemm(const float* A, long long sam, long long sak, const float* B, long long sbn, long long sbk,
+                      float* C, long long ldc, int M, int N, int K, float beta, int split_k, float* split_ws,
+                      int simt, void* stream);
+int rift_b200_op_layernorm(const float* x, int rows, int C, const float* gamma, const float* beta, int relu, float* y,
+                           float* mean, float* rstd, void* stream);
+int rift_b200_op_layernorm_bwd(const float* x, const float* dy, int rows, int C, const float* gamma, const float* mean,
+                               const float* rstd, const float* y_relu, float* dx, float* dgamma, float* dbeta,
+                               float* scratch, void* stream);
+int rift_b200_op_attention(const float* qkv, int B, int S, int H, int hd, const uint8_t* key_padding, float* out,
+                           void* stream);
+int rift_b200_op_nat_attention(const float* qkv, int n_seq, int L, int heads, int hd, int ksize, const float* rpb,
+                               float* out, void* stream);
+int rift_b200_op_masked_maxpool(const float* x, const uint8_t* mask, int groups, int n, int C, float* out, int* argmax,
+                                void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RIFT_B200_H */

@@ -1,0 +1,208 @@
+// extern "C" surface declared in include/rift_b200.h.
+#include <mutex>
+#include <new>
+
+#include "engine.h"
+
+namespace rift {
+static thread_local std::string g_last_error;
+long long g_kernel_launches = 0;
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+const char* get_last_error() { return g_last_error.c_str(); }
+}  // namespace rift
+
+using namespace rift;
+
+static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+extern "C" {
+
+const char* rift_b200_last_error(void) { return get_last_error(); }
+int rift_b200_version(void) { return 100; }
+long long rift_b200_launch_count(void) { return g_kernel_launches; }
+
+int rift_b200_create(const rift_b200_model_config* cfg, const rift_b200_param_entry* entries, int n_entries,
+                     rift_b200_engine** out) {
+    RIFT_REQUIRE(cfg && entries && out && n_entries > 0, "create: null argument");
+    RIFT_REQUIRE(cfg->dim % 32 == 0 && cfg->dim / 4 >= 32 / 2, "create: dim must be a multiple of 32");
+    RIFT_REQUIRE(cfg->dim / cfg->num_heads == 32, "create: dim / num_heads must be 32");
+    RIFT_REQUIRE(cfg->state_channel <= 8, "create: state_channel <= 8");
+    rift_b200_engine* e = new (std::nothrow) rift_b200_engine();
+    RIFT_REQUIRE(e != nullptr, "create: out of host memory");
+    e->cfg = *cfg;
+    long long lo = -1, hi = -1;
+    for (int i = 0; i < n_entries; ++i) {
+        RIFT_REQUIRE(entries[i].name != nullptr && entries[i].offset >= 0 && entries[i].numel >= 0, "create: bad entry");
+        e->table[entries[i].name] = ParamRef{entries[i].offset, entries[i].numel, entries[i].trainable != 0};
+        if (entries[i].trainable) {
+            if (lo < 0 || entries[i].offset < lo) lo = entries[i].offset;
+            if (entries[i].offset + entries[i].numel > hi) hi = entries[i].offset + entries[i].numel;
+        }
+    }
+    e->train_lo = lo < 0 ? 0 : lo;
+    e->train_hi = hi < 0 ? 0 : hi;
+    *out = e;
+    return 0;
+}
+
+void rift_b200_destroy(rift_b200_engine* e) { delete e; }
+
+int rift_b200_bind_arena(rift_b200_engine* e, float* params, float* grads, long long numel) {
+    RIFT_REQUIRE(e && params, "bind_arena: null argument");
+    for (auto& kv : e->table)
+        RIFT_REQUIRE(kv.second.offset + kv.second.numel <= numel, "bind_arena: entry beyond the arena: " + kv.first);
+    e->params = params; e->grads = grads; e->numel = numel;
+    int r = e->build_model();
+    e->bound = (r == 0);
+    return r;
+}
+
+size_t rift_b200_workspace_bytes(const rift_b200_engine* e_, const rift_b200_batch* shape) {
+    if (!e_ || !shape || !e_->bound) return 0;
+    rift_b200_engine* e = const_cast<rift_b200_engine*>(e_);
+    Ctx c; c.dry = true; c.save = true;
+    rift_b200_outputs out;
+    float* dummy = reinterpret_cast<float*>(0x100);
+    out.probability = dummy; out.trajectory = dummy; out.prediction = dummy; out.hidden = dummy;
+    out.ref_free_trajectory = dummy; out.candidate_trajectories = dummy; out.r_padding_mask = nullptr;
+    if (e->forward(*shape, out, c) != 0) return 0;
+    if (e->grads && !e->m.any_trainable_outside_pi_head) {
+        if (e->backward(*shape, nullptr, c) != 0) return 0;
+    }
+    return c.off + 4096;
+}
+
+int rift_b200_forward(rift_b200_engine* e, const rift_b200_batch* batch, const rift_b200_outputs* out, void* workspace,
+                      size_t workspace_bytes, int flags, void* stream) {
+    RIFT_REQUIRE(e && batch && out && workspace, "forward: null argument");
+    RIFT_REQUIRE(e->bound, "forward: bind_arena first");
+    RIFT_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "forward: workspace must be 256-byte aligned");
+    Ctx c; c.st = S(stream); c.base = static_cast<char*>(workspace); c.cap = workspace_bytes;
+    c.save = (flags & RIFT_B200_FWD_SAVE_FOR_BACKWARD) != 0;
+    c.simt = true;
+    return e->forward(*batch, *out, c);
+}
+
+int rift_b200_backward(rift_b200_engine* e, const rift_b200_batch* batch, const float* dlogits, void* workspace,
+                       size_t workspace_bytes, int flags, void* stream) {
+    RIFT_REQUIRE(e && batch && dlogits && workspace, "backward: null argument");
+    RIFT_REQUIRE(e->bound, "backward: bind_arena first");
+    Ctx c; c.st = S(stream); c.base = static_cast<char*>(workspace); c.cap = workspace_bytes;
+    c.off = e->fwd_ws_end;          // scratch goes after the activations saved by forward
+    (void)flags;
+    return e->backward(*batch, dlogits, c);
+}
+
+// ---------------------------------------------------------------- objectives
+size_t rift_b200_objective_scratch_bytes(int bs) { return (size_t)bs * (sizeof(double) + sizeof(int)) + 64; }
+
+int rift_b200_group_objective(int algo, const float* logits, const float* old_logits, const float* ref_logits,
+                              const double* advantage, const uint8_t* valid, const uint8_t* r_pad, int bs, int R, int Mo,
+                              float clip_lo, float clip_hi, float dual_clip, float kl_weight, void* scratch, double* out3,
+                              float* dlogits, int scale_by_count, void* stream) {
+    RIFT_REQUIRE(logits && old_logits && advantage && valid && scratch && out3, "group_objective: null argument");
+    RIFT_REQUIRE(algo == 0 || algo == 1, "group_objective: algo must be 0 (rift) or 1 (grpo)");
+    double* part_sum = static_cast<double*>(scratch);
+    int* part_cnt = reinterpret_cast<int*>(part_sum + bs);
+    return launch_group_objective(algo, logits, old_logits, ref_logits, advantage, valid, r_pad, bs, R, Mo, clip_lo, clip_hi,
+                                  dual_clip, kl_weight, part_sum, part_cnt, out3, dlogits, scale_by_count, S(stream));
+}
+
+int rift_b200_action_objective(int mode, const float* logits, const uint8_t* r_pad, const long long* action_mode,
+                               const float* weight, const float* old_log_prob, int bs, int R, int Mo, float clip_epsilon,
+                               float lambda_entropy, float inv_n, const float* extra_loss, float* scratch, float* loss_out,
+                               float* dlogits, int* chosen, void* stream) {
+    RIFT_REQUIRE(logits && r_pad && weight && scratch && loss_out, "action_objective: null argument");
+    RIFT_REQUIRE(mode == 1 || (action_mode && old_log_prob), "action_objective: PPO needs action_mode and old_log_prob");
+    return launch_action_objective(mode, logits, r_pad, action_mode, weight, old_log_prob, bs, R, Mo, clip_epsilon,
+                                   lambda_entropy, inv_n, extra_loss, scratch, loss_out, dlogits, chosen, S(stream));
+}
+
+int rift_b200_smooth_l1(const float* value, const float* target, int n, float inv_n, float* loss_out, float* dvalue,
+                        void* stream) {
+    RIFT_REQUIRE(value && target && loss_out, "smooth_l1: null argument");
+    return launch_smooth_l1(value, target, n, inv_n, loss_out, dvalue, S(stream));
+}
+
+int rift_b200_group_advantage(const double* returns, const long long* offsets, long long n_groups, int G, double* advantage,
+                              void* stream) {
+    RIFT_REQUIRE(returns && advantage, "group_advantage: null argument");
+    return launch_group_advantage(returns, offsets, n_groups, G, advantage, S(stream));
+}
+
+int rift_b200_gae(const float* rewards, const float* undones, const float* values, const float* next_values,
+                  const float* unterminated, int n, float gamma, float lambda_, float* advantage, float* reward_sum,
+                  float* advantage_normalised, void* stream) {
+    RIFT_REQUIRE(rewards && undones && values && next_values && unterminated && advantage, "gae: null argument");
+    return launch_gae(rewards, undones, values, next_values, unterminated, n, gamma, lambda_, advantage, reward_sum,
+                      advantage_normalised, S(stream));
+}
+
+int rift_b200_discounted_return(const float* rewards, const float* dones, int n, float gamma, float* returns, void* stream) {
+    RIFT_REQUIRE(rewards && dones && returns, "discounted_return: null argument");
+    return launch_discounted_return(rewards, dones, n, gamma, returns, S(stream));
+}
+
+size_t rift_b200_optim_scratch_bytes(void) { return (size_t)optim_scratch_doubles() * sizeof(double); }
+
+int rift_b200_clip_adamw(float* p, const float* g, float* m, float* v, long long n, long long n_decay, const double* count,
+                         float max_norm, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                         void* scratch, float* scal_out, void* stream) {
+    RIFT_REQUIRE(p && g && m && v && scratch && scal_out, "clip_adamw: null argument");
+    return launch_clip_adamw(p, g, m, v, n, n_decay, count, max_norm, lr, beta1, beta2, eps, weight_decay, step,
+                             static_cast<double*>(scratch), scal_out, S(stream));
+}
+
+// ---------------------------------------------------------------- primitive operators (tests)
+int rift_b200_op_linear(const float* x, int rows, int K, const float* w, const float* bias, int N, int act, const float* res,
+                        float* y, int simt, void* stream) {
+    GemmArgs a;
+    a.A = x; a.sam = K; a.B = w; a.sbn = K; a.C = y; a.ldc = N; a.M = rows; a.N = N; a.K = K;
+    a.bias = bias; a.act = act; a.res = res; a.ldres = N;
+    (void)simt;
+    return launch_gemm_simt(a, S(stream));
+}
+
+int rift_b200_op_gemm(const float* A, long long sam, long long sak, const float* B, long long sbn, long long sbk, float* C,
+                      long long ldc, int M, int N, int K, float beta, int split_k, float* split_ws, int simt, void* stream) {
+    GemmArgs a;
+    a.A = A; a.sam = sam; a.sak = sak; a.B = B; a.sbn = sbn; a.sbk = sbk; a.C = C; a.ldc = ldc; a.M = M; a.N = N; a.K = K;
+    a.beta = beta; a.split_k = split_k; a.split_ws = split_ws;
+    (void)simt;
+    return launch_gemm_simt(a, S(stream));
+}
+
+int rift_b200_op_layernorm(const float* x, int rows, int C, const float* gamma, const float* beta, int relu, float* y,
+                           float* mean, float* rstd, void* stream) {
+    return launch_layernorm(x, C, rows, C, gamma, beta, y, C, relu, nullptr, 0, nullptr, mean, rstd, S(stream));
+}
+
+int rift_b200_op_layernorm_bwd(const float* x, const float* dy, int rows, int C, const float* gamma, const float* mean,
+                               const float* rstd, const float* y_relu, float* dx, float* dgamma, float* dbeta, float* scratch,
+                               void* stream) {
+    return launch_layernorm_bwd(x, C, dy, C, rows, C, gamma, mean, rstd, y_relu, C, dx, C, 0, dgamma, dbeta, scratch, S(stream));
+}
+
+int rift_b200_op_attention(const float* qkv, int B, int Sq, int H, int hd, const uint8_t* key_padding, float* out,
+                           void* stream) {
+    const int D = H * hd;
+    AttnArgs a;
+    a.q = qkv; a.k = qkv + D; a.v = qkv + 2 * D; a.o = out;
+    a.ldq = a.ldk = a.ldv = 3 * D; a.ldo = D;
+    a.B = B; a.H = H; a.Sq = Sq; a.Sk = Sq; a.hd = hd;
+    a.q_outer = Sq; a.k_outer = Sq;
+    a.kpm = key_padding; a.scale = 1.f / sqrtf((float)hd);
+    return launch_attention(a, S(stream));
+}
+
+int rift_b200_op_nat_attention(const float* qkv, int n_seq, int L, int heads, int hd, int ksize, const float* rpb, float* out,
+                               void* stream) {
+    return launch_nat_attention(qkv, n_seq, L, heads, hd, ksize, rpb, out, S(stream));
+}
+
+int rift_b200_op_masked_maxpool(const float* x, const uint8_t* mask, int groups, int n, int C, float* out, int* argmax,
+                                void* stream) {
+    return launch_masked_maxpool(x, mask, groups, n, C, out, argmax, S(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,75 @@
+// Shared device/host helpers for the rift_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+namespace rift {
+
+// ---- error plumbing: every C-ABI entry returns 0 / negative and leaves a message here
+void set_last_error(const std::string& msg);
+const char* get_last_error();
+
+#define RIFT_CUDA_OK(expr)                                                                        \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess) {                                                                  \
+            ::rift::set_last_error(std::string(#expr) + ": " + cudaGetErrorString(_e) + " @ " +  \
+                                   __FILE__ + ":" + std::to_string(__LINE__));                   \
+            return -2;                                                                            \
+        }                                                                                         \
+    } while (0)
+
+#define RIFT_REQUIRE(cond, msg)                                                  \
+    do {                                                                         \
+        if (!(cond)) {                                                           \
+            ::rift::set_last_error(std::string("invalid argument: ") + (msg));   \
+            return -1;                                                           \
+        }                                                                        \
+    } while (0)
+
+extern long long g_kernel_launches;    // every kernel launch of this library passes through RIFT_LAUNCH_OK
+
+#define RIFT_LAUNCH_OK()                                                                          \
+    do {                                                                                          \
+        ++::rift::g_kernel_launches;                                                              \
+        cudaError_t _e = cudaGetLastError();                                                      \
+        if (_e != cudaSuccess) {                                                                  \
+            ::rift::set_last_error(std::string("kernel launch: ") + cudaGetErrorString(_e) +      \
+                                   " @ " + __FILE__ + ":" + std::to_string(__LINE__));           \
+            return -2;                                                                            \
+        }                                                                                         \
+    } while (0)
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+#ifdef __CUDACC__
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float gelu_erf(float x) {       // nn.GELU() default: exact erf form
+    return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+    const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+    const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
+    return cdf + x * pdf;
+}
+#endif
+
+enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2 };
+
+}  // namespace rift

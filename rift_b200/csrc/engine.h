@@ -1,0 +1,110 @@
+// Host-side executor of the Pluto policy: parameter views over the flat arena, the forward
+// schedule, the saved-activation tape and the backward schedule.
+#pragma once
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/rift_b200.h"
+#include "common.cuh"
+#include "ops.h"
+
+namespace rift {
+
+struct Lin {            // nn.Linear / flattened Conv1d: W [N, K] row-major, b [N]
+    const float* W = nullptr; const float* b = nullptr;
+    float* dW = nullptr; float* db = nullptr;
+    int N = 0, K = 0;
+    bool train = false;
+};
+struct Norm {           // LayerNorm
+    const float* g = nullptr; const float* b = nullptr;
+    float* dg = nullptr; float* db = nullptr;
+    int C = 0;
+    bool train = false;
+};
+struct BNorm {          // BatchNorm1d (eval: running statistics)
+    Norm affine;
+    const float* mean = nullptr; const float* var = nullptr;
+};
+struct Vec {            // bare nn.Parameter / nn.Embedding table
+    const float* p = nullptr; float* d = nullptr; long long n = 0; bool train = false;
+};
+struct MLPLayerP { Lin l0; Norm n; Lin l3; };
+struct FourierP { Vec freqs; int d = 0; std::vector<MLPLayerP> mlps; Norm out_n; Lin out_l; };
+struct PointsEncP { Lin f0; BNorm fbn; Lin f3; Lin s0; BNorm sbn; Lin s3; };
+struct MHAP { Lin in; Lin out; };                 // in = packed in_proj (3D x D)
+struct NatBlockP { Norm n1; Vec rpb; Lin qkv, proj; Norm n2; Lin fc1, fc2; };
+struct NatLevelP { std::vector<NatBlockP> blocks; Lin down; Norm down_n; bool has_down = false; int dim = 0, heads = 0, ksize = 0; };
+struct NatEncP { Lin embed; std::vector<NatLevelP> levels; Norm norms[3]; Lin lateral[3]; Lin fpn; };
+struct StateAttnP { Vec pos_embed, query; Lin lin[8]; MHAP attn; };
+struct EncBlockP { Norm n1; MHAP attn; Norm n2; Lin fc1, fc2; };
+struct DecBlockP { MHAP r2r, m2m, cross; Lin ffn0, ffn3; Norm n1, n2, n3, n4; };
+
+struct Model {
+    FourierP pos_emb;
+    NatEncP hist;
+    StateAttnP ego;
+    Vec agent_type_emb;
+    PointsEncP poly_enc;
+    FourierP speed_emb;
+    Vec map_type_emb, map_route_emb, map_tl_emb, map_unknown_emb;
+    std::vector<EncBlockP> enc;
+    Norm final_norm;
+    MLPLayerP pred_loc, pred_yaw, pred_vel;
+    Vec m_emb, m_pos;
+    std::vector<DecBlockP> dec;
+    FourierP r_pos_emb;
+    PointsEncP r_enc;
+    Lin q_proj, cat_x_proj;
+    MLPLayerP loc_head, yaw_head, vel_head, pi_head;
+    Lin hidden0, hidden2;
+    MLPLayerP ref_free;
+    bool any_trainable_outside_pi_head = false;
+};
+
+struct Ctx {            // per-call state: stream + bump allocator over the caller's workspace
+    cudaStream_t st = nullptr;
+    char* base = nullptr;
+    size_t cap = 0, off = 0;
+    bool dry = false;      // measure only: advance the allocator, launch nothing
+    bool simt = true;      // force the exact-fp32 GEMM
+    bool save = false;
+    template <class T> T* alloc(size_t n) {
+        const size_t bytes = (n * sizeof(T) + 255) & ~(size_t)255;
+        const size_t at = off;
+        off += bytes;
+        if (dry) return reinterpret_cast<T*>((char*)nullptr + 256 + at);   // non-null placeholder
+        if (off > cap) return nullptr;
+        return reinterpret_cast<T*>(base + at);
+    }
+};
+
+// Activations kept between forward and backward (pointers into the workspace).
+struct PiHeadTape {
+    const float* q = nullptr;      // (rows, D) input of pi_head
+    float* h = nullptr;            // (rows, D) l0 output
+    float* a = nullptr;            // (rows, D) relu(LN(h))
+    float* mean = nullptr; float* rstd = nullptr;
+    long long rows = 0;
+    bool valid = false;
+};
+
+struct ParamRef { long long offset, numel; bool trainable; };
+
+}  // namespace rift
+
+struct rift_b200_engine {
+    rift_b200_model_config cfg;
+    std::unordered_map<std::string, rift::ParamRef> table;
+    float* params = nullptr; float* grads = nullptr; long long numel = 0;
+    long long train_lo = 0, train_hi = 0;     // element span covering every trainable entry
+    rift::Model m;
+    bool bound = false;
+    rift::PiHeadTape pi_tape;
+    size_t fwd_ws_end = 0;                    // workspace offset where backward scratch may start
+
+    int build_model();
+    int forward(const rift_b200_batch& bt, const rift_b200_outputs& out, rift::Ctx& c);
+    int backward(const rift_b200_batch& bt, const float* dlogits, rift::Ctx& c);
+};

@@ -1,0 +1,835 @@
+// Row-wise / gather / attention kernels of the Pluto policy (everything that is not a GEMM).
+// Reference semantics are cited per kernel (paths relative to
+// /root/reference/rift/cbv/planning/pluto/model/).
+#include "common.cuh"
+#include "ops.h"
+
+namespace rift {
+
+#define GRID1D(n, t) (int)min((long long)148 * 16, ((long long)(n) + (t) - 1) / (t))
+#define FOR_GRID(i, n) \
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)(n); i += (long long)gridDim.x * blockDim.x)
+
+// =====================================================================================
+// LayerNorm (eps 1e-5, affine), optional fused ReLU (MLPLayer / FourierEmbedding: Linear->LN->ReLU)
+// and optional second output y2 = y + add[row % rowmod] (decoder m2m attention: q = k = LN(x) + m_pos).
+// =====================================================================================
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ x, long long ldx, int rows, int C, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, float* __restrict__ y, long long ldy, int relu,
+                 const float* __restrict__ add_rowmod, int rowmod, float* __restrict__ y2, float* __restrict__ mean_out,
+                 float* __restrict__ rstd_out) {
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += gridDim.x * wpb) {
+        const float* xr = x + (long long)row * ldx;
+        float s = 0.f;
+        for (int c = lane; c < C; c += 32) s += xr[c];
+        const float mean = warp_sum(s) / C;
+        float q = 0.f;
+        for (int c = lane; c < C; c += 32) { const float d = xr[c] - mean; q += d * d; }
+        const float rstd = rsqrtf(warp_sum(q) / C + 1e-5f);
+        if (lane == 0) {
+            if (mean_out) mean_out[row] = mean;
+            if (rstd_out) rstd_out[row] = rstd;
+        }
+        float* yr = y + (long long)row * ldy;
+        for (int c = lane; c < C; c += 32) {
+            float v = (xr[c] - mean) * rstd * gamma[c] + beta[c];
+            if (relu) v = fmaxf(v, 0.f);
+            yr[c] = v;
+            if (y2) y2[(long long)row * ldy + c] = v + add_rowmod[(long long)(row % rowmod) * C + c];
+        }
+    }
+}
+
+int launch_layernorm(const float* x, long long ldx, int rows, int C, const float* gamma, const float* beta, float* y,
+                     long long ldy, int relu, const float* add_rowmod, int rowmod, float* y2, float* mean, float* rstd,
+                     cudaStream_t st) {
+    if (rows <= 0) return 0;
+    RIFT_REQUIRE(y2 == nullptr || (add_rowmod != nullptr && rowmod > 0), "layernorm: y2 needs add_rowmod");
+    layernorm_kernel<<<min(cdiv(rows, 8), 148 * 8), 256, 0, st>>>(x, ldx, rows, C, gamma, beta, y, ldy, relu, add_rowmod,
+                                                                  rowmod, y2, mean, rstd);
+    RIFT_LAUNCH_OK();
+    return 0;
+}
+
+// ---- LayerNorm backward.  dy_eff = dy * (y > 0) when the ReLU was fused.
+// dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy_eff * gamma
+// dgamma += sum_rows dy_eff * xhat ; dbeta += sum_rows dy_eff   (two-stage, fixed order -> deterministic)
+constexpr int LNB_MAXC = 1024;
+constexpr int LNB_BLOCKS = 148;
+
+__global__ void __launch_bounds__(256)
+layernorm_bwd_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ dy, long long lddy, int rows,
+                     int C, const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
+                     const float* __restrict__ y_relu, long long ldy, float* __restrict__ dx, long long lddx,
+                     int dx_accumulate, float* __restrict__ partial /*[grid][2][C]*/) {
+    extern __shared__ float sm[];      // [8 warps][2][C]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float dg[LNB_MAXC / 32], db[LNB_MAXC / 32];
+#pragma unroll
+    for (int i = 0; i < LNB_MAXC / 32; ++i) { dg[i] = 0.f; db[i] = 0.f; }
+    for (int row = blockIdx.x * 8 + warp; row < rows; row += gridDim.x * 8) {
+        const float* xr = x + (long long)row * ldx;
+        const float* dyr = dy + (long long)row * lddy;
+        const float mu = mean[row], rs = rstd[row];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < LNB_MAXC / 32; ++i) {
+            const int c = lane + 32 * i;
+            if (c < C) {
+                float d = dyr[c];
+                if (y_relu && !(y_relu[(long long)row * ldy + c] > 0.f)) d = 0.f;
+                const float xh = (xr[c] - mu) * rs;
+                const float g = d * gamma[c];
+                s1 += g; s2 += g * xh;
+                dg[i] += d * xh; db[i] += d;
+            }
+        }
+        s1 = warp_sum(s1) / C; s2 = warp_sum(s2) / C;
+        if (dx) {
+#pragma unroll
+            for (int i = 0; i < LNB_MAXC / 32; ++i) {
+                const int c = lane + 32 * i;
+                if (c < C) {
+                    float d = dyr[c];
+                    if (y_relu && !(y_relu[(long long)row * ldy + c] > 0.f)) d = 0.f;
+                    const float xh = (xr[c] - mu) * rs;
+                    const float v = rs * (d * gamma[c] - s1 - xh * s2);
+                    float* o = dx + (long long)row * lddx + c;
+                    *o = dx_accumulate ? *o + v : v;
+                }
+            }
+        }
+    }
+    if (partial == nullptr) return;
+#pragma unroll
+    for (int i = 0; i < LNB_MAXC / 32; ++i) {
+        const int c = lane + 32 * i;
+        if (c < C) { sm[(warp * 2 + 0) * C + c] = dg[i]; sm[(warp * 2 + 1) * C + c] = db[i]; }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < 2 * C; c += 256) {
+        const int which = c / C, cc = c - which * C;
+        float a = 0.f;
+        for (int w = 0; w < 8; ++w) a += sm[(w * 2 + which) * C + cc];
+        partial[((long long)blockIdx.x * 2 + which) * C + cc] = a;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+partial_reduce_accumulate_kernel(const float* __restrict__ partial, int nb, long long stride, int C, float* __restrict__ out,
+                                 int accumulate) {
+    FOR_GRID(c, C) {
+        float a = 0.f;
+        for (int b = 0; b < nb; ++b) a += partial[(long long)b * stride + c];
+        out[c] = accumulate ? out[c] + a : a;
+    }
+}
+
+int layernorm_bwd_scratch_floats(int C) { return LNB_BLOCKS * 2 * C; }
+
+int launch_layernorm_bwd(const float* x, long long ldx, const float* dy, long long lddy, int rows, int C,
+                         const float* gamma, const float* mean, const float* rstd, const float* y_for_relu, long long ldy,
+                         float* dx, long long lddx, int dx_accumulate, float* dgamma, float* dbeta, float* scratch,
+                         cudaStream_t st) {
+    if (rows <= 0) return 0;
+    RIFT_REQUIRE(C <= LNB_MAXC, "layernorm_bwd: C too large");
+    RIFT_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "layernorm_bwd: dgamma/dbeta go together");
+    RIFT_REQUIRE(dgamma == nullptr || scratch != nullptr, "layernorm_bwd: scratch required for parameter gradients");
+    const int nb = min(cdiv(rows, 8), LNB_BLOCKS);
+    const size_t smem = (size_t)8 * 2 * C * sizeof(float);
+    static bool attr = false;
+    if (!attr) {
+        RIFT_CUDA_OK(cudaFuncSetAttribute(layernorm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * LNB_MAXC * 4));
+        attr = true;
+    }
+    layernorm_bwd_kernel<<<nb, 256, smem, st>>>(x, ldx, dy, lddy, rows, C, gamma, mean, rstd, y_for_relu, ldy, dx, lddx,
+                                                dx_accumulate, dgamma ? scratch : nullptr);
+    RIFT_LAUNCH_OK();
+    if (dgamma) {
+        partial_reduce_accumulate_kernel<<<cdiv(C, 256), 256, 0, st>>>(scratch, nb, 2LL * C, C, dgamma, 1);
+        RIFT_LAUNCH_OK();
+        partial_reduce_accumulate_kernel<<<cdiv(C, 256), 256, 0, st>>>(scratch + C, nb, 2LL * C, C, dbeta, 1);
+        RIFT_LAUNCH_OK();
+    }
+    return 0;
+}
+
+// ---- column sum (bias gradients): out[c] (+)= sum_r x[r, c], two-stage deterministic
+constexpr int COLSUM_BLOCKS = 148;
+__global__ void __launch_bounds__(256)
+colsum_partial_kernel(const float* __restrict__ x, long long ldx, int rows, int C, float* __restrict__ partial) {
+    // block b owns rows b, b+grid, ...; thread t owns columns t, t+256, ...
+    for (int c = threadIdx.x; c < C; c += 256) {
+        float a = 0.f;
+        for (int r = blockIdx.x; r < rows; r += gridDim.x) a += x[(long long)r * ldx + c];
+        partial[(long long)blockIdx.x * C + c] = a;
+    }
+}
+int launch_colsum(const float* x, long long ldx, int rows, int C, float* out, int accumulate, float* scratch,
+                  cudaStream_t st) {
+    if (C <= 0) return 0;
+    const int nb = max(1, min(rows, COLSUM_BLOCKS));
+    colsum_partial_kernel<<<nb, 256, 0, st>>>(x, ldx, rows, C, scratch);
+    RIFT_LAUNCH_OK();
+    partial_reduce_accumulate_kernel<<<cdiv(C, 256), 256, 0, st>>>(scratch, nb, C, C, out, accumulate);
+    RIFT_LAUNCH_OK();
+    return 0;
+}
+
+// =====================================================================================
+// Multi-head attention for short sequences (S <= ~256, head_dim 32/64): one CTA per (batch, head),
+// K and V of that head staged in shared memory, one query per thread with an online softmax.
+// nn.MultiheadAttention semantics (layers/transformer.py:73-94, modules/planning_decoder.py:42-86):
+// scores = (q * hd^-0.5) k^T, key_padding_mask -> -inf, softmax, @ v.  A fully masked row yields 0.
+// =====================================================================================
+__device__ __forceinline__ long long attn_row(int b, int inner_n, long long outer, long long inner) {
+    return (long long)(b / inner_n) * outer + (long long)(b % inner_n) * inner;
+}
+
+template <int HD>
+__global__ void __launch_bounds__(128)
+attention_kernel(AttnArgs a) {
+    extern __shared__ float sm[];
+    float* Ks = sm;
+    float* Vs = sm + (size_t)a.Sk * HD;
+    const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
+    const long long krow0 = attn_row(b, a.k_inner_n, a.k_outer, a.k_inner);
+    for (int e = threadIdx.x; e < a.Sk * HD; e += blockDim.x) {
+        const int j = e / HD, d = e - j * HD;
+        const long long r = krow0 + (long long)j * a.k_seq;
+        Ks[e] = a.k[r * a.ldk + h * HD + d];
+        Vs[e] = a.v[r * a.ldv + h * HD + d];
+    }
+    __syncthreads();
+    const uint8_t* kpm = a.kpm ? a.kpm + (long long)(b / a.kpm_div) * a.Sk : nullptr;
+    const long long qrow0 = attn_row(b, a.q_inner_n, a.q_outer, a.q_inner);
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < a.Sq; i += gridDim.y * blockDim.x) {
+        const long long qr = qrow0 + (long long)i * a.q_seq;
+        float q[HD], acc[HD];
+#pragma unroll
+        for (int d = 0; d < HD; ++d) { q[d] = a.q[qr * a.ldq + h * HD + d] * a.scale; acc[d] = 0.f; }
+        float m = -INFINITY, l = 0.f;
+        for (int j = 0; j < a.Sk; ++j) {
+            if (kpm && kpm[j]) continue;
+            float s = 0.f;
+#pragma unroll
+            for (int d = 0; d < HD; ++d) s = fmaf(q[d], Ks[j * HD + d], s);
+            const float mn = fmaxf(m, s);
+            const float corr = __expf(m - mn);      // m = -inf on the first key: exp(-inf) = 0
+            const float p = __expf(s - mn);
+            l = l * corr + p;
+#pragma unroll
+            for (int d = 0; d < HD; ++d) acc[d] = acc[d] * corr + p * Vs[j * HD + d];
+            m = mn;
+        }
+        const float inv = l > 0.f ? 1.f / l : 0.f;
+#pragma unroll
+        const long long orow = a.o_custom ? attn_row(b, a.o_inner_n, a.o_outer, a.o_inner) + (long long)i * a.o_seq : qr;
+#pragma unroll
+        for (int d = 0; d < HD; ++d) a.o[orow * a.ldo + h * HD + d] = acc[d] * inv;
+        if (a.lse) a.lse[((long long)b * a.H + h) * a.Sq + i] = l > 0.f ? m + logf(l) : INFINITY;
+    }
+}
+
+int launch_attention(const AttnArgs& a, cudaStream_t st) {
+    if (a.B <= 0 || a.Sq <= 0) return 0;
+    RIFT_REQUIRE(a.hd == 32 || a.hd == 64, "attention: head_dim must be 32 or 64");
+    RIFT_REQUIRE(a.Sk > 0, "attention: empty key sequence");
+    const size_t smem = (size_t)2 * a.Sk * a.hd * sizeof(float);
+    RIFT_REQUIRE(smem <= 200 * 1024, "attention: key sequence too long for the shared-memory kernel");
+    const int threads = min(128, (a.Sq + 31) / 32 * 32);
+    dim3 grid(a.B * a.H, cdiv(a.Sq, 128));
+    static bool attr = false;
+    if (!attr) {
+        RIFT_CUDA_OK(cudaFuncSetAttribute(attention_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        RIFT_CUDA_OK(cudaFuncSetAttribute(attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr = true;
+    }
+    if (a.hd == 32) attention_kernel<32><<<grid, threads, smem, st>>>(a);
+    else attention_kernel<64><<<grid, threads, smem, st>>>(a);
+    RIFT_LAUNCH_OK();
+    return 0;
+}
+
+// =====================================================================================
+// 1-D neighbourhood attention (NATTEN 0.14 NeighborhoodAttention1D, dilation 1; call site
+// layers/embedding.py:169-178).  One warp per (sequence, head); lane = channel.
+// window(i) = [clamp(i - k/2, 0, L - k), +k) ; logit = (q_i * hd^-0.5) . k_j + rpb[h, j - i + k - 1]
+// qkv row layout: [3][heads][hd]  (qkv.reshape(B, L, 3, heads, hd))
+// =====================================================================================
+constexpr int NAT_MAXL = 32, NAT_MAXK = 7;
+
+__global__ void __launch_bounds__(128)
+nat_attention_kernel(const float* __restrict__ qkv, int n_seq, int L, int heads, int hd, int ksize,
+                     const float* __restrict__ rpb, float* __restrict__ out) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n_seq * heads) return;
+    const int n = warp / heads, h = warp % heads;
+    const int dim = heads * hd;
+    const float scale = rsqrtf((float)hd);
+    const float* base = qkv + (long long)n * L * 3 * dim + h * hd;
+    const bool on = lane < hd;
+    for (int i = 0; i < L; ++i) {
+        const int start = min(max(i - ksize / 2, 0), L - ksize);
+        const float q = on ? base[(long long)i * 3 * dim + lane] * scale : 0.f;
+        float logit[NAT_MAXK];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int kk = 0; kk < NAT_MAXK; ++kk) {
+            if (kk < ksize) {
+                const int j = start + kk;
+                const float kv = on ? base[(long long)j * 3 * dim + dim + lane] : 0.f;
+                logit[kk] = warp_sum(q * kv) + rpb[h * (2 * ksize - 1) + (j - i + ksize - 1)];
+                mx = fmaxf(mx, logit[kk]);
+            }
+        }
+        float den = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < NAT_MAXK; ++kk)
+            if (kk < ksize) { logit[kk] = __expf(logit[kk] - mx); den += logit[kk]; }
+        float o = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < NAT_MAXK; ++kk)
+            if (kk < ksize && on) o += logit[kk] * base[(long long)(start + kk) * 3 * dim + 2 * dim + lane];
+        if (on) out[((long long)n * L + i) * dim + h * hd + lane] = o / den;
+    }
+}
+
+int launch_nat_attention(const float* qkv, int n_seq, int L, int heads, int hd, int ksize, const float* rpb, float* out,
+                         cudaStream_t st) {
+    if (n_seq <= 0) return 0;
+    RIFT_REQUIRE(hd <= 32 && ksize <= NAT_MAXK && L >= ksize && L <= NAT_MAXL, "nat_attention: unsupported shape");
+    nat_attention_kernel<<<cdiv((long long)n_seq * heads * 32, 128), 128, 0, st>>>(qkv, n_seq, L, heads, hd, ksize, rpb, out);
+    RIFT_LAUNCH_OK();
+    return 0;
+}
+
+// =====================================================================================
+// Conv1d(k=3, pad=1) as GEMM: im2col in the weight's own (C_in, 3) flattening so that
+// weight.view(C_out, C_in*3) is the GEMM B operand unchanged (layers/embedding.py:90-106,109-120,33-60).
+// x is channel-last (n_seq, L, C).
+// =====================================================================================
+__global__ void im2col_k3_kernel(const float* __restrict__ x, int n_seq, int L, int Lout, int C, int stride,
+                                 float* __restrict__ out) {
+    const long long total = (long long)n_seq * Lout * C * 3;
+    FOR_GRID(e, total) {
+        const int k = (int)(e % 3);
+        const long long r = e / 3;
+        const int c = (int)(r % C);
+        const long long row = r / C;               // n * Lout + t
+        const int t = (int)(row % Lout);
+        const long long n = row / Lout;
+        const int ts = t * stride - 1 + k;
+        out[e] = (ts >= 0 && ts < L) ? x[(n * L + ts) * C + c] : 0.f;
+    }
+}
+int launch_im2col_k3(const float* x, int n_seq, int L, int C, int stride, float* out, cudaStream_t st) {
+    const int Lout = (L + 2 - 3) / stride + 1;
+    const long long total = (long long)n_seq * Lout * C * 3;
+    if (total <= 0) return 0;
+    im2col_k3_kernel<<<GRID1D(total, 256), 256, 0, st>>>(x, n_seq, L, Lout, C, stride, out);
+    RIFT_LAUNCH_OK();
+    return 0;
+}
+// only the last output position (the encoder keeps out[:, :, -1], layers/embedding.py:87)
+__global__ void im2col_k3_last_kernel(const float* __restrict__ x, int n_seq, int L, int C, float* __restrict__ out) {
+    const long long total = (long long)n_seq * C * 3;
+    FOR_GRID(e, total) {
+        const int k = (int)(e % 3);
+        const long long r = e / 3;
+        const int c = (int)(r % C);
+        const long long n = r / C;
+        const int ts = L - 2 + k;
+        out[e] = (ts >= 0 && ts < L) ? x[(n * L + ts) * C + c] : 0.f;
+    }
+}
+int launch_im2col_k3_last(const float* x, int n_seq, int L, int C, float* out, cudaStream_t st) {
+    const long long total = (long long)n_seq * C * 3;
+    if (total <= 0) return 0;
+    im2col_k3_last_kernel<<<GRID1D(total, 256), 256, 0, st>>>(x, n_seq, L, C, out);
+    RIFT_LAUNCH_OK();
+    return 0;
+}
+
+// FPN top-down: dst += F.interpolate(src, scale_factor=Ld/Ls, mode='linear', align_corners=False)
+__global__ void fpn_upsample_add_kernel(float* __restrict__ dst, const float* __restrict__ src, int n_seq, int Ld, int Ls,
+                                        int C) {
+    const long long total = (long long)n_seq * Ld * C;
+    const float rscale = (float)Ls / (float)Ld;
+    FOR_GRID(e, total) {
+        const int c = (int)(e % C);
+        const long long r = e / C;
+        const int j = (int)(r % Ld);
+        const long long n = r / Ld;
+        float sp = ((float)j + 0.5f) * rscale - 0.5f;
+        sp = fmaxf(sp, 0.f);
+        const int i0 = min((int)sp, Ls - 1);
+        const int i1 = min(i0 + 1, Ls - 1);
+        const float w1 = sp - (float)i0, w0 = 1.f - w1;
+        dst[e] += w0 * src[(n * Ls + i0) * C + c] + w1 * src[(n * Ls + i1) * C + c];
+    }
+}
+int launch_fpn_upsample_add(float* dst, const float* src, int n_seq, int Ld, int Ls, int C, cudaStream_t st) {
+    const long long total = (long long)n_seq * Ld * C;
+    if (total <= 0) return 0;
+    fpn_upsample_add_kernel<<<GRID1D(total, 256), 256, 0, st>>>(dst, src, n_seq, Ld, Ls, C);
+    RIFT_LAUNCH_OK();
+    return 0;
+}
+
+// =====================================================================================
+// PointsEncoder pooling (layers/embedding.py:271-296): features of invalid points are 0 and take
+// part in the max; argmax = -1 when the winning value is such a zero (gradient is dropped there).
+// =====================================================================================
+__global__ void masked_maxpool_kernel(const float* __restrict__ x, const uint8_t* __restrict__ mask, int groups, int n, int C,
+                                      float* __restrict__ out, int* __restrict__ argmax) {
+    const long long total = (long long)groups * C;
+    FOR_GRID(e, total) {
+        const int c = (int)(e % C);
+        const long long g = e / C;
+        float best = -INFINITY;
+        int arg = -1;
+        for (int p = 0; p < n; ++p) {
+            const bool v = mask[g * n + p] != 0;
+            const float val = v ? x[(g * n + p) * C + c] : 0.f;
+            if (val > best) { best = val; arg = v ? p : -1; }
+        }
+        out[e] = best;
+        if (argmax) argmax[e] = arg;
+    }
+}
+int launch_masked_maxpool(const float* x, const uint8_t* mask, int groups, int n, int C, float* out, int* argmax,
+                          cudaStream_t st) {
+    const long long total = (long long)groups * C;
+    if (total <= 0) return 0;
+    masked_maxpool_kernel<<<GRID1D(total, 256), 256, 0, st>>>(x, mask, groups, n, C, out, argmax);
+    RIFT_LAUNCH_OK();
+    return 0;
+}
+
+__global__ void mask_any_kernel(const uint8_t* __restrict__ mask, int rows, int n, uint8_t* __restrict__ any_out,
+                                uint8_t* __restrict__ none_out) {
+    FOR_GRID(r, rows) {
+        bool a = false;
+        for (int i = 0; i < n; ++i) a = a || (mask[r * n + i] != 0);
+        if (any_out) any_out[r] = a ? 1 : 0;
+        if (none_out) none_out[r] = a ? 0 : 1;
+    }
+}
+int launch_mask_any(const uint8_t* mask, int rows, int n, uint8_t* any_out, uint8_t* none_out, cudaStream_t st) {
+    if (rows <= 0) return 0;
+    mask_any_kernel<<<GRID1D(rows, 128), 128, 0, st>>>(mask, rows, n, any_out, none_out);
+    RIFT_LAUNCH_OK();
+    return 0;
+}
+
+// key padding (pluto_model.py:136-138): token s of sample b is padded when it has no valid step / point
+__global__ void token_masks_kernel(const uint8_t* __restrict__ agent_valid, int agent_T, int Th,
+                                   const uint8_t* __restrict__ map_valid, int P, int bs, int A, int Mp,
+                                   uint8_t* __restrict__ agent_any, uint8_t* __restrict__ key_pad) {
+    const int S = A + Mp;
+    FOR_GRID(e, (long long)bs * S) {
+        const int s = (int)(e % S);
+        const long long b = e / S;
+        bool a = false;
+        if (s < A) {
+            const uint8_t* v = agent_valid + (b * A + s) * agent_T;
+            for (int t = 0; t < Th; ++t) a = a || (v[t] != 0);
+            agent_any[b * A + s] = a ? 1 : 0;
+        } else {
+            const uint8_t* v = map_valid + (b * Mp + (s - A)) * P;
+            for (int t = 0; t < P; ++t) a = a || (v[t] != 0);
+        }
+        key_pad[e] = a ? 0 : 1;
+    }
+}
+int launch_token_masks(const uint8_t* agent_valid, int agent_T, int Th, const uint8_t* map_valid, int P, int bs, int A,
+                       int Mp, uint8_t* agent_any, uint8_t* key_pad, cudaStream_t st) {
+    if (bs <= 0) return 0;
+    token_masks_kernel<<<GRID1D((long long)bs * (A + Mp), 128), 128, 0, st>>>(agent_valid, agent_T, Th, map_valid, P, bs, A,
+                                                                             Mp, agent_any, key_pad);
+    RIFT_LAUNCH_OK();
+    return 0;
+}
+
+// eval-mode BatchNorm1d folded into the preceding Linear: y = (x W^T) * scale + shift
+__global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
+                               const float* __restrict__ var, const float* __restrict__ lin_bias, int n,
+                               float* __restrict__ scale, float* __restrict__ shift) {
+    FOR_GRID(i, n) {
+        const float s = gamma[i] / sqrtf(var[i] + 1e-5f);
+        scale[i] = s;
+        shift[i] = ((lin_bias ? lin_bias[i] : 0.f) - mean[i]) * s + beta[i];
+    }
+}
+int launch_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, const float* lin_bias,
+                   int n, float* scale, float* shift, cudaStream_t st) {
+    bn_fold_kernel<<<cdiv(n, 128), 128, 0, st>>>(gamma, beta, mean, var, lin_bias, n, scale, shift);
+    RIFT_LAUNCH_OK();
+    return 0;
+}
+
+// =====================================================================================
+// Input feature builders
+// =====================================================================================
+// AgentEncoder.forward / to_vector (modules/agent_encoder.py:41-76): feat (n_agents, Th-1, 9) channel-last
+__global__ void agent_features_kernel(const float* __restrict__ pos, const float* __restrict__ heading,
+                                      const float* __restrict__ vel, const float* __restrict__ shape,
+                                      const uint8_t* __restrict__ valid, int n_agents, int Th, int Ts,
+                                      float* __restrict__ feat) {
+    const int L = Th - 1;
+    const long long total = (long long)n_agents * L;
+    FOR_GRID(e, total) {
+        const int t = (int)(e % L);
+        const long long n = e / L;
+        const long long i0 = n * Ts + t, i1 = i0 + 1;
+        const bool vm = valid[i0] && valid[i1];
+        float* f = feat + e * 9;
+        const float dh = vm ? heading[i1] - heading[i0] : 0.f;
+        f[0] = vm ? pos[i1 * 2] - pos[i0 * 2] : 0.f;
+        f[1] = vm ? pos[i1 * 2 + 1] - pos[i0 * 2 + 1] : 0.f;
+        f[2] = vm ? vel[i1 * 2] - vel[i0 * 2] : 0.f;
+        f[3] = vm ? vel[i1 * 2 + 1] - vel[i0 * 2 + 1] : 0.f;
+        f[4] = cosf(dh);
+        f[5] = sinf(dh);
+        f[6] = shape[i1 * 2];
+        f[7] = shape[i1 * 2 + 1];
+        f[8] = vm ? 1.f : 0.f;
+    }
+}
+int launch_agent_features(const float* pos, const float* heading, const float* vel, const float* shape,
+                          const uint8_t* valid, int n_agents, int Th, int Tstride, float* feat, cudaStream_t st) {
+    const long long total = (long long)n_agents * (Th - 1);
+    if (total <= 0) return 0;
+    agent_features_kernel<<<GRID1D(total, 128), 128, 0, st>>>(pos, heading, vel, shape, valid, n_agents, Th, Tstride, feat);
+    RIFT_LAUNCH_OK();
+    return 0;
+}
+
+// MapEncoder polygon feature (modules/map_encoder.py:43-60): (n_poly, P, 10)
+__global__ void map_features_kernel(const float* __restrict__ pp, const float* __restrict__ pv, const float* __restrict__ po,
+                                    const float* __restrict__ pc, int n_poly, int P, float* __restrict__ feat) {
+    const long long total = (long long)n_poly * P;
+    FOR_GRID(e, total) {
+        const int p = (int)(e % P);
+        const long long m = e / P;
+        const long long s0 = (m * 3 + 0) * P + p, s1 = (m * 3 + 1) * P + p, s2 = (m * 3 + 2) * P + p;
+        float* f = feat + e * 10;
+        const float x0 = pp[s0 * 2], y0 = pp[s0 * 2 + 1];
+        f[0] = x0 - pc[m * 3];
+        f[1] = y0 - pc[m * 3 + 1];
+        f[2] = pv[s0 * 2];
+        f[3] = pv[s0 * 2 + 1];
+        f[4] = cosf(po[s0]);
+        f[5] = sinf(po[s0]);
+        f[6] = pp[s1 * 2] - x0;
+        f[7] = pp[s1 * 2 + 1] - y0;
+        f[8] = pp[s2 * 2] - x0;
+        f[9] = pp[s2 * 2 + 1] - y0;
+    }
+}
+int launch_map_features(const float* point_position, const float* point_vector, const float* point_orientation,
+                        const float* polygon_center, int n_poly, int P, float* feat, cudaStream_t st) {
+    const long long total = (long long)n_poly * P;
+    if (total <= 0) return 0;
+    map_features_kernel<<<GRID1D(total, 128), 128, 0, st>>>(point_position, point_vector, point_orientation, polygon_center,
+                                                            n_poly, P, feat);
+    RIFT_LAUNCH_OK();
+    return 0;
+}
+
+// PlanningDecoder reference-line feature (modules/planning_decoder.py:137-160): (n_ref, Pr, 6) and
+// r_pos (n_ref, 3) = [position[0], orientation[0]]
+__global__ void ref_features_kernel(const float* __restrict__ pos, const float* __restrict__ vec, const float* __restrict__ ori,
+                                    int n_ref, int Pr, float* __restrict__ feat, float* __restrict__ rpos) {
+    const long long total = (long long)n_ref * Pr;
+    FOR_GRID(e, total) {
+        const int p = (int)(e % Pr);
+        const long long r = e / Pr;
+        float* f = feat + e * 6;
+        const float x0 = pos[(r * Pr) * 2], y0 = pos[(r * Pr) * 2 + 1];
+        f[0] = pos[e * 2] - x0;
+        f[1] = pos[e * 2 + 1] - y0;
+        f[2] = vec[e * 2];
+        f[3] = vec[e * 2 + 1];
+        f[4] = cosf(ori[e]);
+        f[5] = sinf(ori[e]);
+        if (p == 0) { rpos[r * 3] = x0; rpos[r * 3 + 1] = y0; rpos[r * 3 + 2] = ori[e]; }
+    }
+}
+int launch_ref_features(const float* position, const float* vector, const float* orientation, int n_ref, int Pr,
+                        float* feat, float* rpos, cudaStream_t st) {
+    const long long total = (long long)n_ref * Pr;
+    if (total <= 0) return 0;
+    ref_features_kernel<<<GRID1D(total, 128), 128, 0, st>>>(position, vector, orientation, n_ref, Pr, feat, rpos);
+    RIFT_LAUNCH_OK();
+    return 0;
+}
+
+// token positions for pos_emb (pluto_model.py:123-135): [x, y, wrap(angle)], angle wrapped like
+// (angle + pi) % (2 pi) - pi with torch's floor-mod semantics
+__device__ __forceinline__ float wrap_angle(float a) {
+    const float two_pi = 6.283185307179586f;
+    const float x = a + 3.141592653589793f;
+    float m = fmodf(x, two_pi);
+    if (m != 0.f && (m < 0.f)) m += two_pi;
+    return m - 3.141592653589793f;
+}
+__global__ void token_pos_kernel(const float* __restrict__ apos, const float* __restrict__ ahead, const float* __restrict__ pc,
+                                 int bs, int A, int Th, int Ts, int Mp, float* __restrict__ pos) {
+    const int S = A + Mp;
+    FOR_GRID(e, (long long)bs * S) {
+        const int s = (int)(e % S);
+        const long long b = e / S;
+        float x, y, ang;
+        if (s < A) {
+            const long long i = (b * A + s) * Ts + (Th - 1);
+            x = apos[i * 2]; y = apos[i * 2 + 1]; ang = ahead[i];
+        } else {
+            const long long i = b * Mp + (s - A);
+            x = pc[i * 3]; y = pc[i * 3 + 1]; ang = pc[i * 3 + 2];
+        }
+        pos[e * 3] = x; pos[e * 3 + 1] = y; pos[e * 3 + 2] = wrap_angle(ang);
+    }
+}
+int launch_token_pos(const float* agent_pos, const float* agent_heading, const float* polygon_center, int bs, int A,
+                     int Th, int Tstride, int Mp, float* pos, cudaStream_t st) {
+    if (bs <= 0) return 0;
+    token_pos_kernel<<<GRID1D((long long)bs * (A + Mp), 128), 128, 0, st>>>(agent_pos, agent_heading, polygon_center, bs, A,
+                                                                           Th, Tstride, Mp, pos);
+    RIFT_LAUNCH_OK();
+    return 0;
+}
+
+// FourierEmbedding input features (layers/fourier_embedding.py:45-50) for input dimension `dsel`:
+// [cos(x f 2 pi) (nfreq), sin(x f 2 pi) (nfreq), x], zero padded to ldf columns
+__global__ void fourier_features_kernel(const float* __restrict__ x, int rows, int d, int dsel, const float* __restrict__ freqs,
+                                        int nfreq, float* __restrict__ feat, int ldf) {
+    FOR_GRID(e, (long long)rows * ldf) {
+        const int c = (int)(e % ldf);
+        const long long r = e / ldf;
+        const float xv = x[r * d + dsel];
+        float v = 0.f;
+        if (c < 2 * nfreq) {
+            const int j = c < nfreq ? c : c - nfreq;
+            const float ang = ((xv * freqs[dsel * nfreq + j]) * 2.f) * 3.141592653589793f;
+            v = c < nfreq ? cosf(ang) : sinf(ang);
+        } else if (c == 2 * nfreq) {
+            v = xv;
+        }
+        feat[e] = v;
+    }
+}
+int launch_fourier_features(const float* x, int rows, int d, int dsel, const float* freqs, int nfreq, float* feat,
+                            int ldf, cudaStream_t st) {
+    if (rows <= 0) return 0;
+    RIFT_REQUIRE(ldf >= 2 * nfreq + 1, "fourier_features: ldf too small");
+    fourier_features_kernel<<<GRID1D((long long)rows * ldf, 256), 256, 0, st>>>(x, rows, d, dsel, freqs, nfreq, feat, ldf);
+    RIFT_LAUNCH_OK();
+    return 0;
+}
+
+// StateAttentionEncoder tokens (modules/agent_encoder.py:116-122): tok[b,i,:] = x[b,i] * W_i[:,0] + b_i + pos_embed[i]
+struct StateTokParams { const float* w[8]; const float* b[8]; };
+__global__ void state_tokens_kernel(const float* __restrict__ cur, int cs_stride, int bs, int n_tok, int D, StateTokParams p,
+                                    const float* __restrict__ pos_embed, float* __restrict__ toks) {
+    FOR_GRID(e, (long long)bs * n_tok * D) {
+        const int c = (int)(e % D);
+        const long long r = e / D;
+        const int i = (int)(r % n_tok);
+        const long long b = r / n_tok;
+        toks[e] = cur[b * cs_stride + i] * p.w[i][c] + p.b[i][c] + pos_embed[i * D + c];
+    }
+}
+int launch_state_tokens(const float* cur_state, int cs_stride, int bs, int n_tok, int D, const float* const* w,
+                        const float* const* b, const float* pos_embed, float* toks, cudaStream_t st) {
+    RIFT_REQUIRE(n_tok <= 8, "state_tokens: at most 8 state channels");
+    if (bs <= 0) return 0;
+    StateTokParams p;
+    for (int i = 0; i < 8; ++i) { p.w[i] = i < n_tok ? w[i] : nullptr; p.b[i] = i < n_tok ? b[i] : nullptr; }
+    state_tokens_kernel<<<GRID1D((long long)bs * n_tok * D, 256), 256, 0, st>>>(cur_state, cs_stride, bs, n_tok, D, p,
+                                                                               pos_embed, toks);
+    RIFT_LAUNCH_OK();
+    return 0;
+}
+
+// agent tokens (modules/agent_encoder.py:78-94): history embedding for valid agents, 0 otherwise,
+// token 0 <- ego state embedding, + type_emb[category]; written into tokens[b, a, :] of (bs, S, D)
+__global__ void agent_assemble_kernel(const float* __restrict__ x_hist, const float* __restrict__ x_ego,
+                                      const uint8_t* __restrict__ agent_any, const int8_t* __restrict__ category,
+                                      const float* __restrict__ type_emb, int bs, int A, int S, int D,
+                                      float* __restrict__ tokens) {
+    FOR_GRID(e, (long long)bs * A * D) {
+        const int c = (int)(e % D);
+        const long long r = e / D;
+        const int a = (int)(r % A);
+        const long long b = r / A;
+        float v;
+        if (a == 0) v = x_ego[b * D + c];
+        else v = agent_any[r] ? x_hist[r * D + c] : 0.f;
+        v += type_emb[(int)category[r] * D + c];
+        tokens[(b * S + a) * D + c] = v;
+    }
+}
+int launch_agent_assemble(const float* x_hist, const float* x_ego, const uint8_t* agent_any, const int8_t* category,
+                          const float* type_emb, int bs, int A, int S, int D, float* tokens, cudaStream_t st) {
+    if (bs <= 0) return 0;
+    agent_assemble_kernel<<<GRID1D((long long)bs * A * D, 256), 256, 0, st>>>(x_hist, x_ego, agent_any, category, type_emb,
+                                                                             bs, A, S, D, tokens);
+    RIFT_LAUNCH_OK();
+    return 0;
+}
+
+// map tokens (modules/map_encoder.py:79-93)
+__global__ void map_assemble_kernel(const float* __restrict__ x_poly, const float* __restrict__ x_speed,
+                                    const int8_t* __restrict__ ptype, const uint8_t* __restrict__ on_route,
+                                    const int8_t* __restrict__ tl, const uint8_t* __restrict__ has_speed,
+                                    const float* __restrict__ type_emb, const float* __restrict__ route_emb,
+                                    const float* __restrict__ tl_emb, const float* __restrict__ unknown_emb, int bs, int Mp,
+                                    int A, int S, int D, float* __restrict__ tokens) {
+    FOR_GRID(e, (long long)bs * Mp * D) {
+        const int c = (int)(e % D);
+        const long long r = e / D;
+        const int m = (int)(r % Mp);
+        const long long b = r / Mp;
+        float v = x_poly[e];
+        v += type_emb[(int)ptype[r] * D + c] + route_emb[(on_route[r] ? 1 : 0) * D + c] + tl_emb[(int)tl[r] * D + c] +
+             (has_speed[r] ? x_speed[e] : unknown_emb[c]);
+        tokens[(b * S + A + m) * D + c] = v;
+    }
+}
+int launch_map_assemble(const float* x_poly, const float* x_speed, const int8_t* ptype, const uint8_t* on_route,
+                        const int8_t* tl, const uint8_t* has_speed, const float* type_emb, const float* route_emb,
+                        const float* tl_emb, const float* unknown_emb, int bs, int Mp, int A, int S, int D, float* tokens,
+                        cudaStream_t st) {
+    if (bs <= 0 || Mp <= 0) return 0;
+    map_assemble_kernel<<<GRID1D((long long)bs * Mp * D, 256), 256, 0, st>>>(x_poly, x_speed, ptype, on_route, tl, has_speed,
+                                                                            type_emb, route_emb, tl_emb, unknown_emb, bs,
+                                                                            Mp, A, S, D, tokens);
+    RIFT_LAUNCH_OK();
+    return 0;
+}
+
+// decoder query init: q[row, :] = u[row / Mo, :] + v[row % Mo, :]
+// (q_proj(cat[r_emb, m_emb]) split into its two column blocks, modules/planning_decoder.py:162-167)
+__global__ void query_init_kernel(const float* __restrict__ u, const float* __restrict__ v, long long rows, int Mo, int D,
+                                  float* __restrict__ q) {
+    FOR_GRID(e, rows * D) {
+        const int c = (int)(e % D);
+        const long long r = e / D;
+        q[e] = u[(r / Mo) * D + c] + v[(r % Mo) * D + c];
+    }
+}
+int launch_query_init(const float* u, const float* v, int rows, int Mo, int D, float* q, cudaStream_t st) {
+    if (rows <= 0) return 0;
+    query_init_kernel<<<GRID1D((long long)rows * D, 256), 256, 0, st>>>(u, v, rows, Mo, D, q);
+    RIFT_LAUNCH_OK();
+    return 0;
+}
+
+__global__ void zero_rows_kernel(float* __restrict__ x, const uint8_t* __restrict__ flag, int div, long long rows, int C) {
+    FOR_GRID(e, rows * C) {
+        if (flag[(e / C) / div]) x[e] = 0.f;
+    }
+}
+int launch_zero_rows(float* x, const uint8_t* rowflag, int flag_div, int rows, int C, cudaStream_t st) {
+    if (rows <= 0) return 0;
+    zero_rows_kernel<<<GRID1D((long long)rows * C, 256), 256, 0, st>>>(x, rowflag, flag_div, rows, C);
+    RIFT_LAUNCH_OK();
+    return 0;
+}
+
+// trajectory = cat([loc, yaw, vel], -1) with each head viewed (.., T, 2)  (modules/planning_decoder.py:180-186)
+__global__ void interleave_heads_kernel(const float* __restrict__ loc, const float* __restrict__ yaw, const float* __restrict__ vel,
+                                        long long rows, int T, float* __restrict__ out) {
+    FOR_GRID(e, rows * T * 6) {
+        const int c = (int)(e % 6);
+        const long long rt = e / 6;                  // row * T + t
+        const float* src = c < 2 ? loc : (c < 4 ? yaw : vel);
+        out[e] = src[rt * 2 + (c & 1)];
+    }
+}
+int launch_interleave_heads(const float* loc, const float* yaw, const float* vel, long long rows, int T, float* out,
+                            cudaStream_t st) {
+    if (rows <= 0) return 0;
+    interleave_heads_kernel<<<GRID1D(rows * T * 6, 256), 256, 0, st>>>(loc, yaw, vel, rows, T, out);
+    RIFT_LAUNCH_OK();
+    return 0;
+}
+
+// probability.masked_fill_(r_padding_mask, -1e6)  (pluto_model.py:203); pi is (rows=bs*R, Mo)
+__global__ void mask_logits_kernel(float* __restrict__ pi, const uint8_t* __restrict__ r_pad, long long rows, int Mo, float fill) {
+    FOR_GRID(e, rows * Mo) {
+        if (r_pad[e / Mo]) pi[e] = fill;
+    }
+}
+int launch_mask_logits(float* pi, const uint8_t* r_pad, long long rows, int Mo, float fill, cudaStream_t st) {
+    if (rows <= 0) return 0;
+    mask_logits_kernel<<<GRID1D(rows * Mo, 256), 256, 0, st>>>(pi, r_pad, rows, Mo, fill);
+    RIFT_LAUNCH_OK();
+    return 0;
+}
+
+// out[b*nrows + i, :] = x[b*ldx_batch + (row0+i)*C + :]
+__global__ void gather_rows_kernel(const float* __restrict__ x, long long ldb, int bs, int row0, int nrows, int C,
+                                   float* __restrict__ out) {
+    FOR_GRID(e, (long long)bs * nrows * C) {
+        const int c = (int)(e % C);
+        const long long r = e / C;
+        const int i = (int)(r % nrows);
+        const long long b = r / nrows;
+        out[e] = x[b * ldb + (long long)(row0 + i) * C + c];
+    }
+}
+int launch_gather_rows(const float* x, long long ldx_batch, int bs, int row0, int nrows, int C, float* out, cudaStream_t st) {
+    if (bs <= 0 || nrows <= 0) return 0;
+    gather_rows_kernel<<<GRID1D((long long)bs * nrows * C, 256), 256, 0, st>>>(x, ldx_batch, bs, row0, nrows, C, out);
+    RIFT_LAUNCH_OK();
+    return 0;
+}
+
+// dy *= act'(.) in place.  ReLU: ref = post-activation (y > 0) ; GELU: ref = pre-activation
+__global__ void act_bwd_kernel(const float* __restrict__ ref, float* __restrict__ dy, long long n, int act) {
+    FOR_GRID(e, n) {
+        if (act == ACT_RELU) { if (!(ref[e] > 0.f)) dy[e] = 0.f; }
+        else if (act == ACT_GELU) dy[e] *= gelu_erf_grad(ref[e]);
+    }
+}
+int launch_act_bwd(const float* pre_or_post, float* dy, long long n, int act, cudaStream_t st) {
+    if (n <= 0 || act == ACT_NONE) return 0;
+    act_bwd_kernel<<<GRID1D(n, 256), 256, 0, st>>>(pre_or_post, dy, n, act);
+    RIFT_LAUNCH_OK();
+    return 0;
+}
+
+__global__ void add_inplace_kernel(float* __restrict__ dst, const float* __restrict__ src, long long n) {
+    FOR_GRID(e, n) dst[e] += src[e];
+}
+int launch_add_inplace(float* dst, const float* src, long long n, cudaStream_t st) {
+    if (n <= 0) return 0;
+    add_inplace_kernel<<<GRID1D(n, 256), 256, 0, st>>>(dst, src, n);
+    RIFT_LAUNCH_OK();
+    return 0;
+}
+
+// candidate_trajectories = cat([traj[..., :2], atan2(traj[..., 3], traj[..., 2])])  (pluto_model.py:205-212)
+__global__ void traj_outputs_kernel(const float* __restrict__ traj, long long n, float* __restrict__ cand) {
+    FOR_GRID(e, n) {
+        const float* t = traj + e * 6;
+        cand[e * 3] = t[0];
+        cand[e * 3 + 1] = t[1];
+        cand[e * 3 + 2] = atan2f(t[3], t[2]);
+    }
+}
+int launch_traj_outputs(const float* trajectory, long long n_traj, int T, float* cand, cudaStream_t st) {
+    const long long n = n_traj * T;
+    if (n <= 0) return 0;
+    traj_outputs_kernel<<<GRID1D(n, 256), 256, 0, st>>>(trajectory, n, cand);
+    RIFT_LAUNCH_OK();
+    return 0;
+}
+
+}  // namespace rift

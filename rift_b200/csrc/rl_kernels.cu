@@ -1,0 +1,627 @@
+// GRPO / RIFT / PPO / REINFORCE objective kernels and the group-relative advantage kernel.
+//
+// Reference semantics (file:line relative to /root/reference):
+//   group advantage        rift/cbv/planning/fine_tuner/rlft/traj_eval/traj_evaluator.py:466-470
+//   RIFT objective         rift/cbv/planning/fine_tuner/rlft/rift_pluto/rift_trainer.py:140-182
+//   GRPO objective         rift/cbv/planning/fine_tuner/rlft/grpo_pluto/grpo_trainer.py:140-194
+//   PPO objective          rift/cbv/planning/fine_tuner/rlft/ppo_pluto/ppo_trainer.py:161-183
+//   REINFORCE objective    rift/cbv/planning/fine_tuner/rlft/reinforce_pluto/reinforce_trainer.py:120-170
+//   GAE / returns          .../ppo_pluto/ppo_datamodule.py:22-37,163 ; .../reinforce_datamodule.py:19-38
+//
+// All of these are HBM-bound byte movers: coalesced (vectorised where alignment allows) loads,
+// shared-memory staging of the group block, warp-shuffle reductions, fp64 with explicit
+// round-to-nearest intrinsics (no FMA contraction) where the reference computes in numpy float64.
+#include "common.cuh"
+#include "ops.h"
+
+namespace rift {
+
+// =====================================================================================
+// group-relative advantage, bit-exact with numpy float64 mean/std (pairwise summation)
+// =====================================================================================
+// numpy's pairwise_sum (numpy/_core/src/umath/loops_utils.h.src) for a contiguous array:
+//   n < 8      : sequential from 0
+//   n <= 128   : eight accumulators over strides of 8, ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), tail sequential
+//   n > 128    : split at n/2 rounded down to a multiple of 8, recurse, add the halves
+// Eight lanes of a warp play the eight accumulators; the butterfly (xor 1,2,4) reproduces the
+// combine tree exactly because IEEE addition is commutative.
+
+template <bool SQ>
+__device__ __forceinline__ double pw_term(const double* a, int i) {
+    const double v = a[i];
+    return SQ ? __dmul_rn(v, v) : v;
+}
+
+template <bool SQ>
+__device__ __forceinline__ double pw_leaf8(const double* a, int n, int lane8, unsigned gmask) {
+    if (n < 8) {
+        double res = 0.0;
+        for (int i = 0; i < n; ++i) res = __dadd_rn(res, pw_term<SQ>(a, i));
+        return res;
+    }
+    double r = pw_term<SQ>(a, lane8);
+    const int nfull = n - (n & 7);
+    for (int i = 8; i < nfull; i += 8) r = __dadd_rn(r, pw_term<SQ>(a, i + lane8));
+    r = __dadd_rn(r, __shfl_xor_sync(gmask, r, 1));
+    r = __dadd_rn(r, __shfl_xor_sync(gmask, r, 2));
+    r = __dadd_rn(r, __shfl_xor_sync(gmask, r, 4));
+    for (int i = nfull; i < n; ++i) r = __dadd_rn(r, pw_term<SQ>(a, i));
+    return r;
+}
+
+template <bool SQ>
+__device__ double pw_sum8(const double* a, int n, int lane8, unsigned gmask) {
+    if (n <= 128) return pw_leaf8<SQ>(a, n, lane8, gmask);
+    // explicit post-order walk of the split tree (depth <= 24 covers n < 2^31)
+    int s_off[26], s_n[26], s_state[26];
+    double vals[26];
+    int top = 0, vtop = 0;
+    s_off[0] = 0; s_n[0] = n; s_state[0] = 0; top = 1;
+    while (top > 0) {
+        const int f = top - 1;
+        if (s_n[f] <= 128) {
+            vals[vtop++] = pw_leaf8<SQ>(a + s_off[f], s_n[f], lane8, gmask);
+            --top;
+            continue;
+        }
+        int n2 = s_n[f] / 2;
+        n2 -= n2 % 8;
+        if (s_state[f] == 0) {
+            s_state[f] = 1;
+            s_off[top] = s_off[f]; s_n[top] = n2; s_state[top] = 0; ++top;
+        } else if (s_state[f] == 1) {
+            s_state[f] = 2;
+            s_off[top] = s_off[f] + n2; s_n[top] = s_n[f] - n2; s_state[top] = 0; ++top;
+        } else {
+            const double r = __dadd_rn(vals[vtop - 2], vals[vtop - 1]);
+            vtop -= 2;
+            vals[vtop++] = r;
+            --top;
+        }
+    }
+    return vals[0];
+}
+
+// one group held in (shared or global) memory at x[0..n): writes adv to out[0..n)
+__device__ __forceinline__ void advantage_group8(double* x, double* out, int n, int lane8, unsigned gmask) {
+    const double dn = (double)n;
+    const double mean = __ddiv_rn(pw_sum8<false>(x, n, lane8, gmask), dn);
+    for (int i = lane8; i < n; i += 8) out[i] = __dadd_rn(x[i], -mean);   // x - mean
+    __syncwarp(gmask);
+    const double var = __ddiv_rn(pw_sum8<true>(out, n, lane8, gmask), dn);
+    const double sd = __dadd_rn(__dsqrt_rn(var), 1e-5);
+    __syncwarp(gmask);
+    for (int i = lane8; i < n; i += 8) out[i] = __ddiv_rn(out[i], sd);
+}
+
+// Fixed group size: a block stages GPB groups through shared memory with 16-byte loads.
+constexpr int ADV_THREADS = 256;
+constexpr int ADV_GPB = ADV_THREADS / 8;   // 32 groups per block pass
+
+__global__ void __launch_bounds__(ADV_THREADS)
+group_advantage_fixed_kernel(const double* __restrict__ ret, double* __restrict__ adv,
+                             long long n_groups, int G, int Gp) {
+    extern __shared__ double sm[];
+    const int tid = threadIdx.x;
+    const int lane8 = tid & 7;
+    const int gl = tid >> 3;
+    const unsigned gmask = 0xFFu << ((tid & 31) & ~7);
+    const long long n_chunks = (n_groups + ADV_GPB - 1) / ADV_GPB;
+    for (long long chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+        const long long g0 = chunk * ADV_GPB;
+        const int ng = (int)min((long long)ADV_GPB, n_groups - g0);
+        const long long base = g0 * G;
+        const int total = ng * G;
+        // ---- coalesced global -> shared (double2 when the chunk base is 16B aligned)
+        if (((base & 1) == 0) && ((G & 1) == 0)) {
+            const double2* src = reinterpret_cast<const double2*>(ret + base);
+            for (int e = tid; e < total / 2; e += ADV_THREADS) {
+                const double2 v = __ldg(src + e);
+                const int i = 2 * e;
+                const int g = i / G, k = i - g * G;
+                sm[g * Gp + k] = v.x;
+                sm[g * Gp + k + 1] = v.y;
+            }
+        } else {
+            for (int i = tid; i < total; i += ADV_THREADS) {
+                const int g = i / G, k = i - g * G;
+                sm[g * Gp + k] = __ldg(ret + base + i);
+            }
+        }
+        __syncthreads();
+        if (gl < ng) {
+            double* x = sm + gl * Gp;
+            advantage_group8(x, x, G, lane8, gmask);
+        }
+        __syncthreads();
+        // ---- shared -> global, coalesced
+        if (((base & 1) == 0) && ((G & 1) == 0)) {
+            double2* dst = reinterpret_cast<double2*>(adv + base);
+            for (int e = tid; e < total / 2; e += ADV_THREADS) {
+                const int i = 2 * e;
+                const int g = i / G, k = i - g * G;
+                dst[e] = make_double2(sm[g * Gp + k], sm[g * Gp + k + 1]);
+            }
+        } else {
+            for (int i = tid; i < total; i += ADV_THREADS) {
+                const int g = i / G, k = i - g * G;
+                adv[base + i] = sm[g * Gp + k];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// Ragged groups (offsets[n_groups+1]); eight lanes per group straight from global memory.
+__global__ void __launch_bounds__(ADV_THREADS)
+group_advantage_ragged_kernel(const double* __restrict__ ret, const long long* __restrict__ offsets,
+                              double* __restrict__ adv, long long n_groups) {
+    const int tid = threadIdx.x;
+    const int lane8 = tid & 7;
+    const unsigned gmask = 0xFFu << ((tid & 31) & ~7);
+    const long long g = (long long)blockIdx.x * ADV_GPB + (tid >> 3);
+    if (g >= n_groups) return;
+    const long long o0 = offsets[g], o1 = offsets[g + 1];
+    const int n = (int)(o1 - o0);
+    if (n <= 0) return;
+    // x - mean is written to adv first, so the variance pass re-reads our own output (L1/L2 hit)
+    advantage_group8(const_cast<double*>(ret) + o0, adv + o0, n, lane8, gmask);
+}
+
+// advantage_group8 writes `out` before it finished reading `x` only when out == x, which is the
+// staged case where the in-place update is element-wise safe; the ragged kernel has out != x.
+
+int launch_group_advantage(const double* ret, const long long* offsets, long long n_groups, int G,
+                           double* adv, cudaStream_t st) {
+    if (n_groups <= 0) return 0;
+    if (offsets == nullptr) {
+        RIFT_REQUIRE(G > 0, "group size must be positive");
+        const int Gp = G | 1;                                   // odd stride: conflict-free 64-bit lanes
+        const size_t smem = (size_t)ADV_GPB * Gp * sizeof(double);
+        if (smem <= 200 * 1024) {
+            static bool attr_done = false;
+            if (!attr_done) {
+                RIFT_CUDA_OK(cudaFuncSetAttribute(group_advantage_fixed_kernel,
+                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                attr_done = true;
+            }
+            const long long n_chunks = (n_groups + ADV_GPB - 1) / ADV_GPB;
+            const int per_sm = (int)max((size_t)1, min((size_t)8, (size_t)(220 * 1024) / (smem + 1024)));
+            const int grid = (int)min(n_chunks, (long long)148 * per_sm);
+            group_advantage_fixed_kernel<<<grid, ADV_THREADS, smem, st>>>(ret, adv, n_groups, G, Gp);
+            RIFT_LAUNCH_OK();
+            return 0;
+        }
+        RIFT_REQUIRE(false, "fixed group size too large for the staged kernel; pass offsets");
+    }
+    const int grid = (int)((n_groups + ADV_GPB - 1) / ADV_GPB);
+    group_advantage_ragged_kernel<<<grid, ADV_THREADS, 0, st>>>(ret, offsets, adv, n_groups);
+    RIFT_LAUNCH_OK();
+    return 0;
+}
+
+// =====================================================================================
+// RIFT / GRPO group objective: forward value + d(loss)/d(logits) in one pass over the batch
+// =====================================================================================
+// One warp per sample (G = R*Mo candidates, typically 12..144).  Outputs per sample:
+//   part_sum[b]  (double)  sum of the objective over valid candidates
+//   part_cnt[b]  (int)     number of valid candidates
+//   dlogits[b,:] (float)   d(-sum_valid obj)/d logits  -- NOT yet divided by the global valid count
+// The division by the (all-rank) valid count happens in finalize / in the optimizer kernel, which
+// is what makes the data-parallel loss an exact global masked mean (rift_trainer.py:173-178).
+
+constexpr int LOSS_MAX_PER_LANE = 16;   // G <= 512
+
+template <bool GRPO>
+__global__ void __launch_bounds__(128)
+group_objective_kernel(const float* __restrict__ logits, const float* __restrict__ old_logits,
+                       const float* __restrict__ ref_logits, const double* __restrict__ adv,
+                       const uint8_t* __restrict__ valid, const uint8_t* __restrict__ r_pad,
+                       int bs, int R, int Mo, float clip_lo, float clip_hi, float dual_clip, float kl_w,
+                       double* __restrict__ part_sum, int* __restrict__ part_cnt,
+                       float* __restrict__ dlogits) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= bs) return;
+    const int G = R * Mo;
+    const long long base = (long long)warp * G;
+    float z[LOSS_MAX_PER_LANE], o[LOSS_MAX_PER_LANE], f[LOSS_MAX_PER_LANE];
+    bool pad[LOSS_MAX_PER_LANE];
+    float zmax = -INFINITY, omax = -INFINITY, fmax_ = -INFINITY;
+#pragma unroll
+    for (int t = 0; t < LOSS_MAX_PER_LANE; ++t) {
+        const int i = lane + 32 * t;
+        z[t] = o[t] = f[t] = -INFINITY;
+        pad[t] = true;
+        if (i < G) {
+            const int r = i / Mo;
+            bool p;
+            if (r_pad) {
+                p = r_pad[(long long)warp * R + r] != 0;
+            } else {                                   // r_padding = ~valid.any(-1)
+                p = true;
+                for (int m = 0; m < Mo; ++m) p = p && (valid[base + r * Mo + m] == 0);
+            }
+            pad[t] = p;
+            z[t] = p ? -1e8f : logits[base + i];
+            o[t] = p ? -1e8f : old_logits[base + i];
+            if (GRPO) f[t] = p ? -1e8f : ref_logits[base + i];
+            zmax = fmaxf(zmax, z[t]);
+            omax = fmaxf(omax, o[t]);
+            if (GRPO) fmax_ = fmaxf(fmax_, f[t]);
+        }
+    }
+    zmax = warp_max(zmax); omax = warp_max(omax);
+    if (GRPO) fmax_ = warp_max(fmax_);
+    float zs = 0.f, os = 0.f, fs = 0.f;
+#pragma unroll
+    for (int t = 0; t < LOSS_MAX_PER_LANE; ++t) {
+        if (lane + 32 * t < G) {
+            zs += expf(z[t] - zmax);
+            os += expf(o[t] - omax);
+            if (GRPO) fs += expf(f[t] - fmax_);
+        }
+    }
+    zs = warp_sum(zs); os = warp_sum(os);
+    if (GRPO) fs = warp_sum(fs);
+    const float zl = logf(zs), ol = logf(os);
+
+    double lsum = 0.0;
+    int lcnt = 0;
+    float gsum = 0.f;                 // sum_i g_i (g = d obj / d lp)
+    float g[LOSS_MAX_PER_LANE], p[LOSS_MAX_PER_LANE];
+#pragma unroll
+    for (int t = 0; t < LOSS_MAX_PER_LANE; ++t) {
+        const int i = lane + 32 * t;
+        g[t] = 0.f; p[t] = 0.f;
+        if (i < G) {
+            const float lp = (z[t] - zmax) - zl;
+            const float lo = (o[t] - omax) - ol;
+            p[t] = expf(lp);
+            const bool v = valid[base + i] != 0;
+            if (v) {
+                const float ratio = expf(lp - lo);
+                const double a = adv[base + i];
+                const float rc = fminf(fmaxf(ratio, clip_lo), clip_hi);
+                const double t1 = a * (double)ratio;
+                const double t2 = a * (double)rc;
+                const double mn = fmin(t1, t2);
+                // torch sub-gradients: min/max split 0.5/0.5 on ties, clamp passes lo<=x<=hi
+                const double w1 = t1 < t2 ? 1.0 : (t1 == t2 ? 0.5 : 0.0);
+                const double w2 = (1.0 - w1) * ((ratio >= clip_lo && ratio <= clip_hi) ? 1.0 : 0.0);
+                double obj = mn, wmn = 1.0;
+                if (!GRPO) {
+                    if (a < 0.0) {
+                        const double dc = a * (double)dual_clip;
+                        obj = fmax(mn, dc);
+                        wmn = mn > dc ? 1.0 : (mn == dc ? 0.5 : 0.0);
+                    }
+                }
+                double dobj_dlp = wmn * (w1 + w2) * a * (double)ratio;
+                if (GRPO) {
+                    const float pf = expf((f[t] - fmax_) - logf(fs));
+                    // F.kl_div(input=lp, target=pf): xlogy(pf, pf) - pf * lp   (fp32)
+                    const float kl = (pf > 0.f ? pf * logf(pf) : 0.f) - pf * lp;
+                    obj = mn - (double)(kl_w * kl);
+                    dobj_dlp += (double)(kl_w * pf);
+                }
+                lsum += obj;
+                lcnt += 1;
+                g[t] = (float)dobj_dlp;
+                gsum += g[t];
+            }
+        }
+    }
+    lsum = warp_sum_d(lsum);
+    gsum = warp_sum(gsum);
+#pragma unroll
+    for (int o2 = 16; o2 > 0; o2 >>= 1) lcnt += __shfl_xor_sync(0xffffffffu, lcnt, o2);
+    if (lane == 0) { part_sum[warp] = lsum; part_cnt[warp] = lcnt; }
+    if (dlogits) {
+#pragma unroll
+        for (int t = 0; t < LOSS_MAX_PER_LANE; ++t) {
+            const int i = lane + 32 * t;
+            // loss = -sum obj / N  ->  d/dz_j = -(g_j - softmax_j * sum_i g_i) / N ; padded rows get 0
+            if (i < G) dlogits[base + i] = pad[t] ? 0.f : -(g[t] - p[t] * gsum);
+        }
+    }
+}
+
+// Deterministic finalize: fixed-order tree over the per-sample partials, one block.
+// out[0] = loss (= -sum/count, 0 when count == 0), out[1] = sum of objectives, out[2] = count.
+// If `scale_dlogits` the gradient is divided by the local count (single-GPU drop-in use).
+__global__ void __launch_bounds__(256)
+objective_finalize_kernel(const double* __restrict__ part_sum, const int* __restrict__ part_cnt, int bs,
+                          double* __restrict__ out, float* __restrict__ dlogits, long long n_dlogits,
+                          int scale_dlogits) {
+    __shared__ double ssum[256];
+    __shared__ long long scnt[256];
+    double s = 0.0;
+    long long c = 0;
+    for (int i = threadIdx.x; i < bs; i += 256) { s += part_sum[i]; c += part_cnt[i]; }
+    ssum[threadIdx.x] = s; scnt[threadIdx.x] = c;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) { ssum[threadIdx.x] += ssum[threadIdx.x + o]; scnt[threadIdx.x] += scnt[threadIdx.x + o]; }
+        __syncthreads();
+    }
+    const double tot = ssum[0];
+    const long long cnt = scnt[0];
+    if (threadIdx.x == 0) {
+        out[0] = cnt > 0 ? -(tot / (double)cnt) : 0.0;
+        out[1] = tot;
+        out[2] = (double)cnt;
+    }
+    if (scale_dlogits && dlogits) {
+        const float inv = cnt > 0 ? (float)(1.0 / (double)cnt) : 0.f;
+        for (long long i = threadIdx.x; i < n_dlogits; i += 256) dlogits[i] *= inv;
+    }
+}
+
+__global__ void scale_f32_by_count_kernel(float* __restrict__ x, long long n, const double* __restrict__ out3) {
+    const double cnt = out3[2];
+    const float inv = cnt > 0 ? (float)(1.0 / cnt) : 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        x[i] *= inv;
+}
+
+int launch_group_objective(int algo, const float* logits, const float* old_logits, const float* ref_logits,
+                           const double* adv, const uint8_t* valid, const uint8_t* r_pad, int bs, int R, int Mo,
+                           float clip_lo, float clip_hi, float dual_clip, float kl_w,
+                           double* part_sum, int* part_cnt, double* out3, float* dlogits, int scale_dlogits,
+                           cudaStream_t st) {
+    RIFT_REQUIRE(R * Mo <= 32 * LOSS_MAX_PER_LANE, "R*num_modes exceeds 512 candidates per sample");
+    RIFT_REQUIRE(algo == 0 || ref_logits != nullptr, "GRPO needs ref_logits");
+    if (bs <= 0) return 0;
+    const int grid = cdiv((long long)bs * 32, 128);
+    if (algo == 0)
+        group_objective_kernel<false><<<grid, 128, 0, st>>>(logits, old_logits, ref_logits, adv, valid, r_pad, bs, R, Mo,
+                                                            clip_lo, clip_hi, dual_clip, kl_w, part_sum, part_cnt, dlogits);
+    else
+        group_objective_kernel<true><<<grid, 128, 0, st>>>(logits, old_logits, ref_logits, adv, valid, r_pad, bs, R, Mo,
+                                                           clip_lo, clip_hi, dual_clip, kl_w, part_sum, part_cnt, dlogits);
+    RIFT_LAUNCH_OK();
+    const long long n = (long long)bs * R * Mo;
+    // small batches: the single finalize block also rescales; large ones use a wide kernel
+    const bool wide = scale_dlogits && dlogits && n > 65536;
+    objective_finalize_kernel<<<1, 256, 0, st>>>(part_sum, part_cnt, bs, out3, dlogits, n, scale_dlogits && !wide);
+    RIFT_LAUNCH_OK();
+    if (wide) {
+        scale_f32_by_count_kernel<<<min(cdiv(n, 256), 148 * 8), 256, 0, st>>>(dlogits, n, out3);
+        RIFT_LAUNCH_OK();
+    }
+    return 0;
+}
+
+// =====================================================================================
+// PPO (chosen action + entropy) and REINFORCE (argmax action) objectives
+// =====================================================================================
+// mode 0: PPO   per-sample term  -(min(A rho, A clamp(rho)) + lambda * H)          (ppo_trainer.py:161-183)
+// mode 1: REINFORCE per-sample   -(lp[argmax] * return)                            (reinforce_trainer.py:154-170)
+// part[b] = per-sample term (float, the reference computes these in fp32); the mean over the
+// (global) batch and the matching gradient scale `inv_n` are applied here directly because the
+// batch size is known on the host.
+__global__ void __launch_bounds__(128)
+action_objective_kernel(int mode, const float* __restrict__ logits, const uint8_t* __restrict__ r_pad,
+                        const long long* __restrict__ action_mode, const float* __restrict__ weight,   // advantage | return
+                        const float* __restrict__ old_log_prob, int bs, int R, int Mo, float eps_clip,
+                        float lambda_entropy, float inv_n, float* __restrict__ part, float* __restrict__ dlogits,
+                        int* __restrict__ chosen) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= bs) return;
+    const int G = R * Mo;
+    const long long base = (long long)warp * G;
+    float z[LOSS_MAX_PER_LANE];
+    bool pad[LOSS_MAX_PER_LANE];
+    float zmax = -INFINITY;
+    int amax = 0x7fffffff;
+#pragma unroll
+    for (int t = 0; t < LOSS_MAX_PER_LANE; ++t) {
+        const int i = lane + 32 * t;
+        z[t] = -INFINITY; pad[t] = true;
+        if (i < G) {
+            pad[t] = r_pad[(long long)warp * R + i / Mo] != 0;
+            z[t] = pad[t] ? -1e8f : logits[base + i];
+            if (z[t] > zmax) { zmax = z[t]; amax = i; }     // first maximum within the lane
+        }
+    }
+    // warp arg-max with first-index tie-break (torch.argmax returns the first maximal index)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float om = __shfl_xor_sync(0xffffffffu, zmax, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, amax, o);
+        if (om > zmax || (om == zmax && oi < amax)) { zmax = om; amax = oi; }
+    }
+    float zs = 0.f;
+#pragma unroll
+    for (int t = 0; t < LOSS_MAX_PER_LANE; ++t)
+        if (lane + 32 * t < G) zs += expf(z[t] - zmax);
+    zs = warp_sum(zs);
+    const float zl = logf(zs);
+    int idx;
+    if (mode == 0) idx = (int)(action_mode[2 * warp] * Mo + action_mode[2 * warp + 1]);
+    else idx = amax;
+    float ent = 0.f, lp_idx = 0.f;
+    float lp[LOSS_MAX_PER_LANE];
+#pragma unroll
+    for (int t = 0; t < LOSS_MAX_PER_LANE; ++t) {
+        const int i = lane + 32 * t;
+        lp[t] = 0.f;
+        if (i < G) {
+            lp[t] = (z[t] - zmax) - zl;
+            ent -= expf(lp[t]) * lp[t];
+            if (i == idx) lp_idx = lp[t];
+        }
+    }
+    ent = warp_sum(ent);
+    lp_idx = warp_sum(lp_idx);
+    const float w = weight[warp];
+    float term, coef;             // term = per-sample loss contribution ; coef = d term / d lp[idx]
+    if (mode == 0) {
+        const float ratio = expf(lp_idx - old_log_prob[warp]);
+        const float lo = 1.f - eps_clip, hi = 1.f + eps_clip;
+        const float rc = fminf(fmaxf(ratio, lo), hi);
+        const float t1 = w * ratio, t2 = w * rc;
+        const float w1 = t1 < t2 ? 1.f : (t1 == t2 ? 0.5f : 0.f);
+        const float w2 = (1.f - w1) * ((ratio >= lo && ratio <= hi) ? 1.f : 0.f);
+        term = -(fminf(t1, t2) + lambda_entropy * ent);
+        coef = -(w1 + w2) * w * ratio;
+    } else {
+        term = -(lp_idx * w);
+        coef = -w;
+    }
+    if (lane == 0) { part[warp] = term; if (chosen) chosen[warp] = idx; }
+    if (dlogits) {
+        // g_i = d term / d lp_i ; dz_j = g_j - softmax_j * sum_i g_i
+        float g[LOSS_MAX_PER_LANE], gsum = 0.f;
+#pragma unroll
+        for (int t = 0; t < LOSS_MAX_PER_LANE; ++t) {
+            const int i = lane + 32 * t;
+            g[t] = 0.f;
+            if (i < G) {
+                if (i == idx) g[t] += coef;
+                if (mode == 0) g[t] += lambda_entropy * expf(lp[t]) * (lp[t] + 1.f);   // d(-lambda H)/d lp
+                gsum += g[t];
+            }
+        }
+        gsum = warp_sum(gsum);
+#pragma unroll
+        for (int t = 0; t < LOSS_MAX_PER_LANE; ++t) {
+            const int i = lane + 32 * t;
+            if (i < G) dlogits[base + i] = pad[t] ? 0.f : (g[t] - expf(lp[t]) * gsum) * inv_n;
+        }
+    }
+}
+
+// out[0] = inv_n * sum_b part[b] (+ extra[0] if given), sequential fixed order -> deterministic
+__global__ void __launch_bounds__(256)
+mean_finalize_kernel(const float* __restrict__ part, int bs, float inv_n, const float* __restrict__ extra,
+                     float* __restrict__ out) {
+    __shared__ float s[256];
+    float a = 0.f;
+    for (int i = threadIdx.x; i < bs; i += 256) a += part[i];
+    s[threadIdx.x] = a;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = s[0] * inv_n + (extra ? extra[0] : 0.f);
+}
+
+int launch_action_objective(int mode, const float* logits, const uint8_t* r_pad, const long long* action_mode,
+                            const float* weight, const float* old_log_prob, int bs, int R, int Mo, float eps_clip,
+                            float lambda_entropy, float inv_n, const float* extra_loss, float* part, float* loss_out,
+                            float* dlogits, int* chosen, cudaStream_t st) {
+    RIFT_REQUIRE(R * Mo <= 32 * LOSS_MAX_PER_LANE, "R*num_modes exceeds 512 candidates per sample");
+    RIFT_REQUIRE(r_pad != nullptr, "r_pad is required");
+    if (bs <= 0) return 0;
+    action_objective_kernel<<<cdiv((long long)bs * 32, 128), 128, 0, st>>>(
+        mode, logits, r_pad, action_mode, weight, old_log_prob, bs, R, Mo, eps_clip, lambda_entropy, inv_n, part,
+        dlogits, chosen);
+    RIFT_LAUNCH_OK();
+    mean_finalize_kernel<<<1, 256, 0, st>>>(part, bs, inv_n, extra_loss, loss_out);
+    RIFT_LAUNCH_OK();
+    return 0;
+}
+
+// SmoothL1(value, target) mean (beta = 1) and its gradient wrt value, one block (bs is a batch size).
+__global__ void __launch_bounds__(256)
+smooth_l1_kernel(const float* __restrict__ value, const float* __restrict__ target, int n, float inv_n,
+                 float* __restrict__ loss_out, float* __restrict__ dvalue) {
+    __shared__ float s[256];
+    float a = 0.f;
+    for (int i = threadIdx.x; i < n; i += 256) {
+        const float d = value[i] - target[i];
+        const float ad = fabsf(d);
+        a += ad < 1.f ? 0.5f * d * d : ad - 0.5f;
+        if (dvalue) dvalue[i] = (ad < 1.f ? d : (d > 0.f ? 1.f : -1.f)) * inv_n;
+    }
+    s[threadIdx.x] = a;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) loss_out[0] = s[0] * inv_n;
+}
+
+int launch_smooth_l1(const float* value, const float* target, int n, float inv_n, float* loss_out, float* dvalue,
+                     cudaStream_t st) {
+    smooth_l1_kernel<<<1, 256, 0, st>>>(value, target, n, inv_n, loss_out, dvalue);
+    RIFT_LAUNCH_OK();
+    return 0;
+}
+
+// =====================================================================================
+// PPO buffer pass: GAE reverse scan + normalisation ; REINFORCE discounted return
+// =====================================================================================
+// The scans are first-order linear recurrences over the (<= 4096-deep) buffer; they are evaluated
+// in the reference's sequential fp32 order by one thread (4096 dependent FMAs-without-fusion is
+// ~20 us) so results are bit-identical to ppo_datamodule.py:22-37 / reinforce_datamodule.py:19-38.
+__global__ void gae_scan_kernel(const float* __restrict__ rewards, const float* __restrict__ undones,
+                                const float* __restrict__ values, const float* __restrict__ next_values,
+                                const float* __restrict__ unterminated, int n, float gamma, float lam,
+                                float* __restrict__ adv, float* __restrict__ reward_sum) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    float a = 0.f;
+    for (int t = n - 1; t >= 0; --t) {
+        // delta = rewards[t] + unterminated[t] * gamma * next_values[t] - values[t]
+        const float delta = __fsub_rn(__fadd_rn(rewards[t], __fmul_rn(__fmul_rn(unterminated[t], gamma), next_values[t])), values[t]);
+        // advantage = delta + undones[t] * gamma * lambda * advantage
+        a = __fadd_rn(delta, __fmul_rn(__fmul_rn(__fmul_rn(undones[t], gamma), lam), a));
+        adv[t] = a;
+        if (reward_sum) reward_sum[t] = __fadd_rn(a, values[t]);
+    }
+}
+
+// (x - mean) / (std_unbiased + 1e-5), fp32 like torch (ppo_datamodule.py:163); one block.
+__global__ void __launch_bounds__(1024)
+normalise_unbiased_kernel(const float* __restrict__ x, int n, float* __restrict__ y) {
+    __shared__ double s[1024];
+    double a = 0.0;
+    for (int i = threadIdx.x; i < n; i += 1024) a += x[i];
+    s[threadIdx.x] = a;
+    __syncthreads();
+    for (int o = 512; o > 0; o >>= 1) { if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o]; __syncthreads(); }
+    const float mean = (float)(s[0] / n);
+    __syncthreads();
+    a = 0.0;
+    for (int i = threadIdx.x; i < n; i += 1024) { const double d = (double)x[i] - (double)mean; a += d * d; }
+    s[threadIdx.x] = a;
+    __syncthreads();
+    for (int o = 512; o > 0; o >>= 1) { if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o]; __syncthreads(); }
+    const float sd = (float)sqrt(s[0] / (n > 1 ? n - 1 : 1));
+    for (int i = threadIdx.x; i < n; i += 1024) y[i] = (x[i] - mean) / (sd + 1e-5f);
+}
+
+__global__ void discounted_return_kernel(const float* __restrict__ rewards, const float* __restrict__ dones, int n,
+                                         float gamma, float* __restrict__ out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    float g = 0.f;
+    for (int t = n - 1; t >= 0; --t) {
+        g = dones[t] == 1.f ? rewards[t] : __fadd_rn(rewards[t], __fmul_rn(gamma, g));
+        out[t] = g;
+    }
+}
+
+int launch_gae(const float* rewards, const float* undones, const float* values, const float* next_values,
+               const float* unterminated, int n, float gamma, float lam, float* adv, float* reward_sum,
+               float* adv_normalised, cudaStream_t st) {
+    gae_scan_kernel<<<1, 32, 0, st>>>(rewards, undones, values, next_values, unterminated, n, gamma, lam, adv, reward_sum);
+    RIFT_LAUNCH_OK();
+    if (adv_normalised) {
+        normalise_unbiased_kernel<<<1, 1024, 0, st>>>(adv, n, adv_normalised);
+        RIFT_LAUNCH_OK();
+    }
+    return 0;
+}
+
+int launch_discounted_return(const float* rewards, const float* dones, int n, float gamma, float* out, cudaStream_t st) {
+    discounted_return_kernel<<<1, 32, 0, st>>>(rewards, dones, n, gamma, out);
+    RIFT_LAUNCH_OK();
+    return 0;
+}
+
+}  // namespace rift

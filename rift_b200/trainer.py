@@ -1,0 +1,234 @@
+"""``LightningTrainer`` mirrors — the operator-level drop-in boundary of the fine-tuner.
+
+Constructor signature, ``training_step`` / ``validation_step`` / ``forward`` /
+``configure_optimizers`` / ``state_dict`` (``model.``-prefixed keys) follow
+rift/cbv/planning/fine_tuner/rlft/{rift,grpo,ppo,reinforce}_pluto/*_trainer.py.  Lightning itself
+is not required: ``training_step`` computes the loss AND leaves d(loss)/d(params) in the model's
+gradient arena (there is no autograd graph), ``optimizer_step`` performs Lightning's
+clip_grad_norm_(0.5) -> AdamW.step (custom_lightning.yaml:40-41), ``on_train_epoch_end`` advances the
+WarmupCos schedule (interval = epoch).  ``fit`` strings these together for callers without Lightning.
+
+Data parallelism (not in the reference): when torch.distributed is initialised, each rank
+holds a shard of the batch; ONE all-reduce carries the flat gradient arena plus (objective sum,
+valid count), and every rank applies the identical update, reproducing the reference's global
+masked mean exactly (rift_trainer.py:173-178).
+"""
+import math
+from typing import Dict, List, Optional
+
+import torch
+
+from . import functional as F
+from .planning_model import PlanningModel
+
+
+class WarmupCosLR:
+    """pluto/optim/warmup_cos_lr.py:6-54 (per-epoch warm-up + cosine) without the `verbose`
+    positional argument that breaks on torch >= 2.2."""
+
+    def __init__(self, optimizer, lr, min_lr, epochs, warmup_epochs):
+        self.optimizer, self.lr, self.min_lr, self.epochs, self.warmup_epochs = optimizer, lr, min_lr, epochs, warmup_epochs
+        self.last_epoch = 0
+        self._apply()
+
+    def get_lr(self, epoch=None):
+        e = self.last_epoch if epoch is None else epoch
+        if e < self.warmup_epochs:
+            return self.lr * (e + 1) / self.warmup_epochs
+        return self.min_lr + 0.5 * (self.lr - self.min_lr) * (
+            1 + math.cos(math.pi * (e - self.warmup_epochs) / (self.epochs - self.warmup_epochs)))
+
+    def _apply(self):
+        for g in self.optimizer.param_groups:
+            g["lr"] = self.get_lr()
+
+    def step(self):
+        self.last_epoch += 1
+        self._apply()
+
+
+class LightningTrainer:
+    ALGO = "rift"
+
+    def __init__(self, model: PlanningModel, lr, cl_lr_decay, weight_decay, epochs, warmup_epochs, frame_rate: int,
+                 trainable_layers: List[str], use_drivable_area_loss=True, use_regulate_yaw=True,
+                 objective_aggregate_mode: str = "mean", clip=(0.8, 1.2), kl_weight=0.2, gradient_clip_val=0.5):
+        self.model = model
+        self.lr, self.cl_lr_decay, self.weight_decay = lr, cl_lr_decay, weight_decay
+        self.epochs, self.warmup_epochs = epochs, warmup_epochs
+        self.objective_aggregate_mode = objective_aggregate_mode
+        self.history_steps, self.future_steps = model.history_steps, model.future_steps
+        self.frame_rate = int(frame_rate)
+        self.trainable_layers = list(trainable_layers)
+        self.use_drivable_area_loss, self.use_regulate_yaw = use_drivable_area_loss, use_regulate_yaw
+        self.radius, self.num_modes = model.radius, model.num_modes
+        self.mode_interval = self.radius / self.num_modes
+        self.clip, self.kl_weight, self.gradient_clip_val = clip, kl_weight, gradient_clip_val
+        self.training = True
+        self.logged: Dict[str, float] = {}
+        self.freeze_parameters(self.trainable_layers)
+        self.optimizer: Optional[F.ClipAdamW] = None
+        self.scheduler: Optional[WarmupCosLR] = None
+        self._count = None            # device fp64 valid count of the last training_step (group objectives)
+
+    # ------------------------------------------------------------------ reference surface
+    def freeze_parameters(self, trainable_layers=("planning_decoder.pi_head",)):
+        """rift_trainer.py:78-90 — raises ValueError for an unknown layer name."""
+        self.model.set_trainable_layers(trainable_layers)
+
+    def forward(self, features):
+        return self.model(features)
+
+    def train(self, mode=True):
+        self.training = mode
+        return self
+
+    def eval(self):
+        return self.train(False)
+
+    def log(self, name, value, **kw):
+        self.logged[name] = float(value)
+
+    def configure_optimizers(self):
+        a = self.model.arena
+        self.optimizer = F.ClipAdamW(a.params, a.grads, a.n_train, a.n_decay, lr=self.lr, weight_decay=self.weight_decay,
+                                     max_norm=self.gradient_clip_val)
+        self.scheduler = WarmupCosLR(self.optimizer, lr=self.lr, min_lr=self.lr * self.cl_lr_decay, epochs=self.epochs,
+                                     warmup_epochs=self.warmup_epochs)
+        return [self.optimizer], [self.scheduler]
+
+    def state_dict(self):
+        return {"model." + k: v for k, v in self.model.state_dict().items()}
+
+    def load_state_dict(self, sd, strict=True):
+        return self.model.load_state_dict(sd, strict)
+
+    # ------------------------------------------------------------------ objectives
+    @staticmethod
+    def _features(batch):
+        f = batch["cur_pluto_feature_torch"]
+        return f.data if hasattr(f, "data") and isinstance(getattr(f, "data"), dict) else f
+
+    def _world(self):
+        import torch.distributed as dist
+        return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+    def _objective(self, res, batch, need_grad):
+        """Returns (loss tensor, dlogits or None).  dlogits is NOT divided by the valid count when
+        training (the optimizer kernel divides by the all-reduced count)."""
+        dev = self.model.device
+        loss, dz, stats = F.group_objective(
+            self.ALGO, res["probability"], batch["old_group_logits_torch"].to(dev),
+            batch["group_advantage_torch"].to(dev), batch["group_advantage_mask_torch"].to(dev),
+            res["r_padding_mask"], batch["ref_group_logits_torch"].to(dev) if self.ALGO == "grpo" else None,
+            clip=self.clip, kl_weight=self.kl_weight, need_grad=need_grad, scale_by_count=False)
+        self._stats = stats
+        return loss, dz
+
+    def _step(self, batch, prefix: str):
+        res = self.model.forward(self._features(batch), outputs=(), save_for_backward=self.training)
+        loss, dz = self._objective(res, batch, need_grad=self.training)
+        if self.training:
+            self.model.backward(dz)
+            loss = self._reduce(loss)
+        self._last_loss = loss
+        return loss if self.training else 0.0
+
+    def _reduce(self, loss):
+        """Single collective of the step: [flat grads | objective sum | valid count]."""
+        stats = self._stats
+        if self._world() > 1:
+            import torch.distributed as dist
+            a = self.model.arena
+            n = a.n_train
+            # the gradient arena has a 4-float tail: the two fp64 scalars travel with the fp32
+            # gradients in the same buffer, each split into (hi, lo) floats, so the step has exactly
+            # one collective and no staging copy
+            comm = a.grads[:n + 4]
+            s = stats[1:3]
+            hi = s.to(torch.float32)
+            lo = (s - hi.to(torch.float64)).to(torch.float32)
+            comm[n:n + 2].copy_(hi)
+            comm[n + 2:n + 4].copy_(lo)
+            dist.all_reduce(comm, op=dist.ReduceOp.SUM)
+            s = comm[n:n + 2].to(torch.float64) + comm[n + 2:n + 4].to(torch.float64)
+            self._count = s[1:2].clone()
+            return torch.where(s[1] > 0, -s[0] / s[1], torch.zeros_like(s[0]))
+        self._count = stats[2:3].clone()
+        return loss
+
+    def training_step(self, batch, batch_idx=0):
+        self.training = True
+        return self._step(batch, "train")
+
+    def validation_step(self, batch, batch_idx=0):
+        self.training = False
+        try:
+            return self._step(batch, "val")
+        finally:
+            self.training = True
+
+    def optimizer_step(self):
+        if self.optimizer is None:
+            self.configure_optimizers()
+        self.optimizer.step(count=self._count)
+
+    def on_train_epoch_end(self):
+        if self.scheduler is not None:
+            self.scheduler.step()
+
+    # ------------------------------------------------------------------ loop for callers without Lightning
+    def step(self, batch):
+        loss = self.training_step(batch)
+        self.optimizer_step()
+        return loss
+
+    def fit(self, batches, epochs: Optional[int] = None):
+        """`batches`: a re-iterable of collated batch dicts (one pass = one epoch)."""
+        if self.optimizer is None:
+            self.configure_optimizers()
+        last = None
+        for _ in range(epochs if epochs is not None else self.epochs):
+            for b in batches:
+                last = self.step(b)
+            self.on_train_epoch_end()
+        return last
+
+
+class RIFTTrainer(LightningTrainer):
+    """rift_pluto/rift_trainer.py — clip [0.8, 1.2] + dual clip 3.0."""
+    ALGO = "rift"
+
+
+class GRPOTrainer(LightningTrainer):
+    """grpo_pluto/grpo_trainer.py — clip [0.8, 1.2] - 0.2 * KL(ref || new)."""
+    ALGO = "grpo"
+
+
+class ReinforceTrainer(LightningTrainer):
+    """reinforce_pluto/reinforce_trainer.py — -mean(log pi(argmax) * return)."""
+    ALGO = "reinforce"
+
+    def _objective(self, res, batch, need_grad):
+        dev = self.model.device
+        bs = res["probability"].shape[0]
+        loss, dz, _ = F.action_objective("reinforce", res["probability"], res["r_padding_mask"],
+                                         batch["return_torch"].to(dev), global_batch=bs * self._world(),
+                                         need_grad=need_grad)
+        self._stats = None
+        return loss, dz
+
+    def _reduce(self, loss):
+        self._count = None
+        if self._world() > 1:
+            import torch.distributed as dist
+            a = self.model.arena
+            n = a.n_train
+            comm = a.grads[:n + 1]
+            comm[n:n + 1].copy_(loss.reshape(1))       # per-rank term already carries 1 / global batch
+            dist.all_reduce(comm, op=dist.ReduceOp.SUM)
+            return comm[n].clone()
+        return loss
+
+
+TRAINERS = {"rift": RIFTTrainer, "grpo": GRPOTrainer, "reinforce": ReinforceTrainer}
