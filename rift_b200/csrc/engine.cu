@@ -549,7 +549,10 @@ int rift_b200_engine::forward(const rift_b200_batch& bt, const rift_b200_outputs
             a.B = bs * Mo; a.H = H; a.Sq = R; a.Sk = R; a.hd = D / H;
             a.q_inner_n = Mo; a.q_outer = (long long)R * Mo; a.q_inner = 1; a.q_seq = Mo;
             a.k_inner_n = Mo; a.k_outer = (long long)R * Mo; a.k_inner = 1; a.k_seq = Mo;
-            a.kpm = r_pad; a.kpm_div = Mo; a.scale = att_scale;
+            // The reference passes key_padding_mask = r_pad.repeat(Mo, 1) for a batch laid out (b, m)
+            // (planning_decoder.py:56-60): batch row j = b*Mo + m is masked with r_pad[j % bs], not with
+            // r_pad[b].  Reproduced as is - parity is defined by what the reference computes.
+            a.kpm = r_pad; a.kpm_mod = bs; a.scale = att_scale;
             TRY(launch_attention(a, c.st));
         }
         TRY(linear(c, a1, D, rowsQ, db.r2r.out, q1, D, ACT_NONE, q, D, 1));

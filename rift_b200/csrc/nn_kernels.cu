@@ -204,7 +204,7 @@ attention_kernel(AttnArgs a) {
         Vs[e] = a.v[r * a.ldv + h * HD + d];
     }
     __syncthreads();
-    const uint8_t* kpm = a.kpm ? a.kpm + (long long)(b / a.kpm_div) * a.Sk : nullptr;
+    const uint8_t* kpm = a.kpm ? a.kpm + (long long)(a.kpm_mod > 0 ? b % a.kpm_mod : b / a.kpm_div) * a.Sk : nullptr;
     const long long qrow0 = attn_row(b, a.q_inner_n, a.q_outer, a.q_inner);
     for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < a.Sq; i += gridDim.y * blockDim.x) {
         const long long qr = qrow0 + (long long)i * a.q_seq;

@@ -155,13 +155,13 @@ group_advantage_fixed_kernel(const double* __restrict__ ret, double* __restrict_
 // Ragged groups (offsets[n_groups+1]); eight lanes per group straight from global memory.
 __global__ void __launch_bounds__(ADV_THREADS)
 group_advantage_ragged_kernel(const double* __restrict__ ret, const long long* __restrict__ offsets,
-                              double* __restrict__ adv, long long n_groups) {
+                              double* __restrict__ adv, long long n_groups, int G) {
     const int tid = threadIdx.x;
     const int lane8 = tid & 7;
     const unsigned gmask = 0xFFu << ((tid & 31) & ~7);
     const long long g = (long long)blockIdx.x * ADV_GPB + (tid >> 3);
     if (g >= n_groups) return;
-    const long long o0 = offsets[g], o1 = offsets[g + 1];
+    const long long o0 = offsets ? offsets[g] : g * G, o1 = offsets ? offsets[g + 1] : (g + 1) * G;
     const int n = (int)(o1 - o0);
     if (n <= 0) return;
     // x - mean is written to adv first, so the variance pass re-reads our own output (L1/L2 hit)
@@ -192,10 +192,10 @@ int launch_group_advantage(const double* ret, const long long* offsets, long lon
             RIFT_LAUNCH_OK();
             return 0;
         }
-        RIFT_REQUIRE(false, "fixed group size too large for the staged kernel; pass offsets");
+        // very large groups: straight from global memory (second pass re-reads through L1/L2)
     }
     const int grid = (int)((n_groups + ADV_GPB - 1) / ADV_GPB);
-    group_advantage_ragged_kernel<<<grid, ADV_THREADS, 0, st>>>(ret, offsets, adv, n_groups);
+    group_advantage_ragged_kernel<<<grid, ADV_THREADS, 0, st>>>(ret, offsets, adv, n_groups, G);
     RIFT_LAUNCH_OK();
     return 0;
 }
