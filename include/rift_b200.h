@@ -100,6 +100,15 @@ int rift_b200_bind_arena(rift_b200_engine* e, float* params, float* grads, long 
 /* bytes of workspace rift_b200_forward/backward need for a batch of this shape */
 size_t rift_b200_workspace_bytes(const rift_b200_engine* e, const rift_b200_batch* shape);
 
+/* tcgen05 path: the engine keeps split-bf16 copies (hi + lo planes) of every weight matrix and the TMA
+ * descriptors over them in caller-owned memory; without a bound cache every GEMM runs on the exact-fp32
+ * SIMT kernel.  Call rift_b200_params_updated after the parameter arena was written from outside the
+ * library (optimizer step: trainable_only = 1; checkpoint load: 0) - the planes are refreshed lazily by
+ * the next forward. */
+size_t rift_b200_weight_cache_bytes(const rift_b200_engine* e);
+int rift_b200_bind_weight_cache(rift_b200_engine* e, void* cache, size_t bytes);
+int rift_b200_params_updated(rift_b200_engine* e, int trainable_only);
+
 /* flags */
 #define RIFT_B200_FWD_SAVE_FOR_BACKWARD 1   /* keep activations needed by rift_b200_backward in the workspace */
 #define RIFT_B200_GEMM_SIMT 2               /* force the exact-fp32 SIMT GEMM (validation path) */
@@ -155,6 +164,9 @@ int rift_b200_clip_adamw(float* p, const float* g, float* m, float* v, long long
 /* ---- primitive operators exported for the kernel-level parity tests (tests/test_ops_gpu.py) ---- */
 int rift_b200_op_linear(const float* x, int rows, int K, const float* w, const float* bias, int N, int act,
                         const float* res, float* y, int simt, void* stream);
+size_t rift_b200_op_linear_tc_scratch_bytes(int rows, int N, int K);
+int rift_b200_op_linear_tc(const float* x, int rows, int K, const float* w, const float* bias, int N, int act,
+                           const float* res, float* y, void* scratch, size_t scratch_bytes, int resplit, void* stream);
 int rift_b200_op_gemm(const float* A, long long sam, long long sak, const float* B, long long sbn, long long sbk,
                       float* C, long long ldc, int M, int N, int K, float beta, int split_k, float* split_ws,
                       int simt, void* stream);

@@ -61,7 +61,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             if log:
                 print(log)
     if force or not os.path.exists(LIB) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs):
-        cmd = [NVCC, *ARCH, "-shared", "-o", LIB, *objs, "-lcudart", "-lcuda"]
+        cmd = [NVCC, *ARCH, "-shared", "-o", LIB, *objs, "-lcudart"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

@@ -60,7 +60,7 @@ int rift_b200_bind_arena(rift_b200_engine* e, float* params, float* grads, long 
 size_t rift_b200_workspace_bytes(const rift_b200_engine* e_, const rift_b200_batch* shape) {
     if (!e_ || !shape || !e_->bound) return 0;
     rift_b200_engine* e = const_cast<rift_b200_engine*>(e_);
-    Ctx c; c.dry = true; c.save = true;
+    Ctx c; c.dry = true; c.save = true; c.simt = false;     // size for the tensor-core path (superset)
     rift_b200_outputs out;
     float* dummy = reinterpret_cast<float*>(0x100);
     out.probability = dummy; out.trajectory = dummy; out.prediction = dummy; out.hidden = dummy;
@@ -79,8 +79,21 @@ int rift_b200_forward(rift_b200_engine* e, const rift_b200_batch* batch, const r
     RIFT_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "forward: workspace must be 256-byte aligned");
     Ctx c; c.st = S(stream); c.base = static_cast<char*>(workspace); c.cap = workspace_bytes;
     c.save = (flags & RIFT_B200_FWD_SAVE_FOR_BACKWARD) != 0;
-    c.simt = true;
+    c.simt = (flags & RIFT_B200_GEMM_SIMT) != 0;
     return e->forward(*batch, *out, c);
+}
+
+size_t rift_b200_weight_cache_bytes(const rift_b200_engine* e) { return (e && e->bound) ? e->weight_cache_bytes() : 0; }
+
+int rift_b200_bind_weight_cache(rift_b200_engine* e, void* cache, size_t bytes) {
+    RIFT_REQUIRE(e && e->bound, "bind_weight_cache: bind_arena first");
+    return e->bind_weight_cache(cache, bytes);
+}
+
+int rift_b200_params_updated(rift_b200_engine* e, int trainable_only) {
+    RIFT_REQUIRE(e != nullptr, "params_updated: null engine");
+    if (trainable_only) e->dirty_train = true; else e->dirty_all = true;
+    return 0;
 }
 
 int rift_b200_backward(rift_b200_engine* e, const rift_b200_batch* batch, const float* dlogits, void* workspace,
@@ -161,6 +174,45 @@ int rift_b200_op_linear(const float* x, int rows, int K, const float* w, const f
     a.bias = bias; a.act = act; a.res = res; a.ldres = N;
     (void)simt;
     return launch_gemm_simt(a, S(stream));
+}
+
+size_t rift_b200_op_linear_tc_scratch_bytes(int rows, int N, int K) {
+    const int Kp = (K + 63) / 64 * 64;
+    return 2 * (((size_t)N * Kp * 2 + 255) & ~(size_t)255) + 512 + 2 * (((size_t)rows * Kp * 2 + 255) & ~(size_t)255);
+}
+
+// tcgen05 path of op_linear: splits `w` into bf16 planes inside `scratch`, builds the TMA descriptors and runs
+// the tensor-core kernel (synchronises the stream once; test / micro-benchmark use only)
+int rift_b200_op_linear_tc(const float* x, int rows, int K, const float* w, const float* bias, int N, int act,
+                           const float* res, float* y, void* scratch, size_t scratch_bytes, int resplit, void* stream) {
+    RIFT_REQUIRE(x && w && y && scratch, "op_linear_tc: null argument");
+    RIFT_REQUIRE(scratch_bytes >= rift_b200_op_linear_tc_scratch_bytes(rows, N, K), "op_linear_tc: scratch too small");
+    RIFT_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 255) == 0, "op_linear_tc: scratch must be 256-byte aligned");
+    TcWeight tw;
+    tw.src = w; tw.ld_src = K; tw.N = N; tw.K = K; tw.Kp = (K + 63) / 64 * 64;
+    const size_t plane = ((size_t)N * tw.Kp * 2 + 255) & ~(size_t)255;
+    char* p = static_cast<char*>(scratch);
+    tw.hi = p; tw.lo = p + plane;
+    if (resplit) {
+        std::vector<char> job(split_job_bytes());
+        fill_split_job(job.data(), w, K, N, K, tw.Kp, tw.hi, tw.lo, 0);
+        RIFT_CUDA_OK(cudaMemcpyAsync(p + 2 * plane, job.data(), job.size(), cudaMemcpyHostToDevice, S(stream)));
+        RIFT_CUDA_OK(cudaStreamSynchronize(S(stream)));
+        int r = launch_split_weights(p + 2 * plane, 1, (long long)N * tw.Kp, S(stream));
+        if (r) return r;
+    }
+    int r = make_weight_tensor_map(tw.tm_hi, tw.hi, N, tw.Kp);
+    if (r) return r;
+    r = make_weight_tensor_map(tw.tm_lo, tw.lo, N, tw.Kp);
+    if (r) return r;
+    GemmArgs a;
+    a.A = x; a.sam = K; a.B = w; a.sbn = K; a.C = y; a.ldc = N; a.M = rows; a.N = N; a.K = K;
+    a.bias = bias; a.act = act; a.res = res; a.ldres = N;
+    char* ap = p + 2 * plane + 512;
+    const size_t aplane = ((size_t)rows * tw.Kp * 2 + 255) & ~(size_t)255;
+    r = launch_pack_split(x, K, rows, K, tw.Kp, ap, ap + aplane, S(stream));      // part of the timed op: the
+    if (r) return r;                                                              // A planes are per-call data
+    return launch_gemm_tc(a, ap, ap + aplane, tw.Kp, tw, 0, 0, S(stream));
 }
 
 int rift_b200_op_gemm(const float* A, long long sam, long long sak, const float* B, long long sbn, long long sbk, float* C,

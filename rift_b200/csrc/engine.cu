@@ -36,18 +36,44 @@ static int gemm(Ctx& c, const GemmArgs& a) {
     return launch_gemm_simt(a, c.st);
 }
 
-// Y = act((X W^T [+pre]) [*colscale] + b) [+ res]
-static int linear(Ctx& c, const float* X, long long ldx, int M, const Lin& L, float* Y, long long ldy, int act = ACT_NONE,
-                  const float* res = nullptr, long long ldres = 0, int res_div = 1, float* preact = nullptr) {
-    GemmArgs a;
-    a.A = X; a.sam = ldx; a.sak = 1;
-    a.B = L.W; a.sbn = L.K; a.sbk = 1;
-    a.C = Y; a.ldc = ldy; a.M = M; a.N = L.N; a.K = L.K;
-    a.bias = L.b; a.act = act; a.res = res; a.ldres = ldres; a.res_div = res_div; a.preact = preact;
-    return gemm(c, a);
+// GEMM against a (possibly sliced) weight matrix: tcgen05 path when the shape qualifies and the
+// weight has pre-split planes, exact-fp32 SIMT otherwise (tiny K / N == 1 / misaligned views).
+static int gemm_w(Ctx& c, GemmArgs& a, const Lin& L, long long ldw) {
+    a.B = L.W; a.sbn = ldw; a.sbk = 1; a.N = L.N; a.K = L.K;
+    // shape-only decision so that the dry (sizing) pass and the real pass allocate identically
+    const bool tc = !c.simt && L.tc >= 0 && c.tcw && a.sak == 1 && gemm_tc_shape_ok(a.M, a.N, a.K) && (a.ldc % 4) == 0 &&
+                    (a.ldres % 4) == 0 && (a.ldpre % 4) == 0;
+    if (tc) {
+        const int Kp = tc_pitch(a.K);
+        ALLOC(a_hi, uint16_t, (size_t)a.M * Kp);
+        ALLOC(a_lo, uint16_t, (size_t)a.M * Kp);
+        if (c.dry) return 0;
+        if (gemm_tc_eligible(a)) {
+            TRY(launch_pack_split(a.A, a.sam, a.M, a.K, Kp, a_hi, a_lo, c.st));
+            return launch_gemm_tc(a, a_hi, a_lo, Kp, (*c.tcw)[L.tc], L.tc_n0, L.tc_k0, c.st);
+        }
+    }
+    if (c.dry) return 0;
+    return launch_gemm_simt(a, c.st);
 }
 
-// slice of a Linear: output rows [n0, n0+n), input columns [k0, k0+k)
+// Y = act((X W^T [+pre]) [*colscale] + b) [+ res]
+static int linear_ld(Ctx& c, const float* X, long long ldx, int M, const Lin& L, long long ldw, float* Y, long long ldy,
+                     int act = ACT_NONE, const float* res = nullptr, long long ldres = 0, int res_div = 1,
+                     float* preact = nullptr) {
+    GemmArgs a;
+    a.A = X; a.sam = ldx; a.sak = 1;
+    a.C = Y; a.ldc = ldy; a.M = M;
+    a.bias = L.b; a.act = act; a.res = res; a.ldres = ldres; a.res_div = res_div; a.preact = preact;
+    return gemm_w(c, a, L, ldw);
+}
+static int linear(Ctx& c, const float* X, long long ldx, int M, const Lin& L, float* Y, long long ldy, int act = ACT_NONE,
+                  const float* res = nullptr, long long ldres = 0, int res_div = 1, float* preact = nullptr) {
+    return linear_ld(c, X, ldx, M, L, L.K, Y, ldy, act, res, ldres, res_div, preact);
+}
+
+// slice of a Linear: output rows [n0, n0+n), input columns [k0, k0+k).  NOTE: a slice keeps the parent's
+// row pitch; callers pass it as `ldw` to linear_ld.
 static Lin slice(const Lin& L, int n0, int n, int k0, int k, bool with_bias) {
     Lin s;
     s.W = L.W + (long long)n0 * L.K + k0;
@@ -55,16 +81,8 @@ static Lin slice(const Lin& L, int n0, int n, int k0, int k, bool with_bias) {
     s.dW = L.dW ? L.dW + (long long)n0 * L.K + k0 : nullptr;
     s.db = (with_bias && L.db) ? L.db + n0 : nullptr;
     s.N = n; s.K = k; s.train = L.train;
+    s.tc = L.tc; s.tc_n0 = L.tc_n0 + n0; s.tc_k0 = L.tc_k0 + k0;
     return s;
-}
-static int linear_ld(Ctx& c, const float* X, long long ldx, int M, const Lin& L, long long ldw, float* Y, long long ldy,
-                     int act = ACT_NONE, const float* res = nullptr, long long ldres = 0, int res_div = 1) {
-    GemmArgs a;
-    a.A = X; a.sam = ldx; a.sak = 1;
-    a.B = L.W; a.sbn = ldw; a.sbk = 1;
-    a.C = Y; a.ldc = ldy; a.M = M; a.N = L.N; a.K = L.K;
-    a.bias = L.b; a.act = act; a.res = res; a.ldres = ldres; a.res_div = res_div;
-    return gemm(c, a);
 }
 
 static int layernorm(Ctx& c, const float* x, int rows, const Norm& n, float* y, int relu = 0, float* mean = nullptr,
@@ -131,9 +149,9 @@ static int points_encoder(Ctx& c, const float* F, int groups, int n, int Cin, co
     }
     {   // first_mlp: Linear(C,128) + BN + ReLU + Linear(128,256)
         GemmArgs a;
-        a.A = F; a.sam = Cin; a.B = p.f0.W; a.sbn = Cin; a.C = h1; a.ldc = PE_H1; a.M = rows; a.N = PE_H1; a.K = Cin;
+        a.A = F; a.sam = Cin; a.C = h1; a.ldc = PE_H1; a.M = rows;
         a.colscale = sc1; a.bias = sh1; a.act = ACT_RELU;
-        TRY(gemm(c, a));
+        TRY(gemm_w(c, a, p.f0, Cin));
         TRY(linear(c, h1, PE_H1, rows, p.f3, f, PE_H2));
     }
     if (!c.dry) TRY(launch_masked_maxpool(f, mask, groups, n, PE_H2, pooled, arg1, c.st));
@@ -141,9 +159,9 @@ static int points_encoder(Ctx& c, const float* F, int groups, int n, int Cin, co
         Lin wb = slice(p.s0, 0, PE_H2, PE_H2, PE_H2, false);
         TRY(linear_ld(c, pooled, PE_H2, groups, wb, 2 * PE_H2, gp, PE_H2));
         GemmArgs a;
-        a.A = f; a.sam = PE_H2; a.B = p.s0.W; a.sbn = 2 * PE_H2; a.C = h2; a.ldc = PE_H2; a.M = rows; a.N = PE_H2; a.K = PE_H2;
+        a.A = f; a.sam = PE_H2; a.C = h2; a.ldc = PE_H2; a.M = rows;
         a.pre = gp; a.ldpre = PE_H2; a.pre_div = n; a.colscale = sc2; a.bias = sh2; a.act = ACT_RELU;
-        TRY(gemm(c, a));
+        TRY(gemm_w(c, a, slice(p.s0, 0, PE_H2, 0, PE_H2, false), 2 * PE_H2));
         TRY(linear(c, h2, PE_H2, rows, p.s3, o, Cout));
     }
     if (!c.dry) TRY(launch_masked_maxpool(o, mask, groups, n, Cout, out, arg2, c.st));
@@ -204,6 +222,12 @@ struct Binder {
             if (r->numel != (long long)N * K) { set_last_error("shape mismatch for " + p + wname); err = -1; }
             l.W = e->params + r->offset; l.train = r->trainable && e->grads;
             l.dW = l.train ? e->grads + r->offset : nullptr;
+            if (N >= 16 && K >= 32) {          // candidate for the tcgen05 path: gets pre-split bf16 planes
+                TcWeight w;
+                w.src = l.W; w.ld_src = K; w.N = N; w.K = K; w.Kp = (K + 63) / 64 * 64; w.trainable = r->trainable;
+                l.tc = (int)e->tcw.size();
+                e->tcw.push_back(w);
+            }
         }
         if (bias) if (auto r = find(p + bname)) {
             l.b = e->params + r->offset;
@@ -257,10 +281,56 @@ struct Binder {
 };
 }  // namespace
 
+// ---- pre-split weight planes for the tcgen05 path -------------------------------------------
+// cache layout: [plane hi | plane lo] per weight (256 B aligned), then the two split-job tables.
+size_t rift_b200_engine::weight_cache_bytes() const {
+    size_t off = 0;
+    for (const TcWeight& w : tcw) off += 2 * (((size_t)w.N * w.Kp * 2 + 255) & ~(size_t)255);
+    off += 2 * ((tcw.size() * split_job_bytes() + 255) & ~(size_t)255);
+    return off + 256;
+}
+
+int rift_b200_engine::bind_weight_cache(void* cache, size_t bytes) {
+    RIFT_REQUIRE(cache != nullptr && bytes >= weight_cache_bytes(), "bind_weight_cache: buffer too small");
+    RIFT_REQUIRE((reinterpret_cast<uintptr_t>(cache) & 255) == 0, "bind_weight_cache: buffer must be 256-byte aligned");
+    wcache = cache; wcache_bytes = bytes;
+    char* p = static_cast<char*>(cache);
+    std::vector<char> all(tcw.size() * split_job_bytes()), tr(tcw.size() * split_job_bytes());
+    n_jobs_all = n_jobs_train = 0; total_all = total_train = 0;
+    for (TcWeight& w : tcw) {
+        const size_t plane = ((size_t)w.N * w.Kp * 2 + 255) & ~(size_t)255;
+        w.hi = p; w.lo = p + plane; p += 2 * plane;
+        TRY(make_weight_tensor_map(w.tm_hi, w.hi, w.N, w.Kp));
+        TRY(make_weight_tensor_map(w.tm_lo, w.lo, w.N, w.Kp));
+        fill_split_job(all.data() + n_jobs_all * split_job_bytes(), w.src, w.ld_src, w.N, w.K, w.Kp, w.hi, w.lo, total_all);
+        ++n_jobs_all; total_all += (long long)w.N * w.Kp;
+        if (w.trainable) {
+            fill_split_job(tr.data() + n_jobs_train * split_job_bytes(), w.src, w.ld_src, w.N, w.K, w.Kp, w.hi, w.lo, total_train);
+            ++n_jobs_train; total_train += (long long)w.N * w.Kp;
+        }
+    }
+    const size_t tbl = (tcw.size() * split_job_bytes() + 255) & ~(size_t)255;
+    jobs_all = p; jobs_train = p + tbl;
+    if (n_jobs_all) RIFT_CUDA_OK(cudaMemcpy(jobs_all, all.data(), n_jobs_all * split_job_bytes(), cudaMemcpyHostToDevice));
+    if (n_jobs_train) RIFT_CUDA_OK(cudaMemcpy(jobs_train, tr.data(), n_jobs_train * split_job_bytes(), cudaMemcpyHostToDevice));
+    dirty_all = true; dirty_train = true;
+    return 0;
+}
+
+int rift_b200_engine::refresh_weights(cudaStream_t st) {
+    if (!wcache) return 0;
+    if (dirty_all) TRY(launch_split_weights(jobs_all, n_jobs_all, total_all, st));
+    else if (dirty_train) TRY(launch_split_weights(jobs_train, n_jobs_train, total_train, st));
+    dirty_all = dirty_train = false;
+    return 0;
+}
+
 int rift_b200_engine::build_model() {
     Binder b{this};
     const int D = cfg.dim, T = cfg.future_steps;
     m = Model();
+    tcw.clear();
+    wcache = nullptr;
     m.pos_emb = b.fourier("pos_emb", 3, D);
     {   // NATSequenceEncoder (layers/embedding.py:8-87)
         const std::string p = "agent_encoder.history_encoder";
@@ -351,6 +421,9 @@ int rift_b200_engine::forward(const rift_b200_batch& bt, const rift_b200_outputs
     RIFT_REQUIRE(bt.agent_T >= Th, "forward: agent tensors shorter than history_steps");
     RIFT_REQUIRE(D % H == 0 && D / H == 32, "forward: encoder head_dim must be 32");
     pi_tape.valid = false;
+    if (!wcache) c.simt = true;            // no pre-split planes bound: exact-fp32 SIMT GEMMs only
+    c.tcw = &tcw;
+    if (!c.dry && !c.simt) TRY(refresh_weights(c.st));
 
     // ---------------- masks
     ALLOC(agent_any, uint8_t, (size_t)bs * A);

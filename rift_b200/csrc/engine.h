@@ -8,6 +8,7 @@
 #include "../../include/rift_b200.h"
 #include "common.cuh"
 #include "ops.h"
+#include "gemm_tc.h"
 
 namespace rift {
 
@@ -16,6 +17,7 @@ struct Lin {            // nn.Linear / flattened Conv1d: W [N, K] row-major, b [
     float* dW = nullptr; float* db = nullptr;
     int N = 0, K = 0;
     bool train = false;
+    int tc = -1, tc_n0 = 0, tc_k0 = 0;      // index into the engine's pre-split weight planes (+ slice origin)
 };
 struct Norm {           // LayerNorm
     const float* g = nullptr; const float* b = nullptr;
@@ -70,6 +72,7 @@ struct Ctx {            // per-call state: stream + bump allocator over the call
     bool dry = false;      // measure only: advance the allocator, launch nothing
     bool simt = true;      // force the exact-fp32 GEMM
     bool save = false;
+    const std::vector<TcWeight>* tcw = nullptr;
     template <class T> T* alloc(size_t n) {
         const size_t bytes = (n * sizeof(T) + 255) & ~(size_t)255;
         const size_t at = off;
@@ -102,6 +105,15 @@ struct rift_b200_engine {
     rift::Model m;
     bool bound = false;
     rift::PiHeadTape pi_tape;
+    // tcgen05 path: pre-split bf16 weight planes (caller-owned memory) + TMA descriptors
+    std::vector<rift::TcWeight> tcw;
+    void* wcache = nullptr; size_t wcache_bytes = 0;
+    void* jobs_all = nullptr; void* jobs_train = nullptr;
+    int n_jobs_all = 0, n_jobs_train = 0; long long total_all = 0, total_train = 0;
+    bool dirty_all = true, dirty_train = true;
+    size_t weight_cache_bytes() const;
+    int bind_weight_cache(void* cache, size_t bytes);
+    int refresh_weights(cudaStream_t st);
     size_t fwd_ws_end = 0;                    // workspace offset where backward scratch may start
 
     int build_model();

@@ -3,6 +3,8 @@
 // Role: (1) the numerically exact device path every tensor-core kernel is validated against,
 // (2) the carrier for shapes the tcgen05 path does not take (K < 16, N == 1, strided views,
 // transposed operands of the weight-gradient products).  64x64x16 tiles, 256 threads, 4x4 per thread.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ops.h"
 
@@ -34,11 +36,20 @@ __device__ __forceinline__ float apply_epilogue(const Epilogue& e, float acc, in
     return v;
 }
 
+// precision emulation for numerics studies (env RIFT_B200_EMULATE): 0 exact, 1 tf32 round-to-nearest,
+// 2 tf32 truncation (what kind::tf32 does to raw fp32 bits), 3 bf16 round-to-nearest
+__device__ __forceinline__ float emulate_round(float x, int mode) {
+    if (mode == 1) { uint32_t u; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x)); return __uint_as_float(u); }
+    if (mode == 2) return __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+    if (mode == 3) return __uint_as_float(((__float_as_uint(x) + 0x7fffu + ((__float_as_uint(x) >> 16) & 1u)) & 0xffff0000u));
+    return x;
+}
+
 template <bool A_KMAJOR, bool B_KMAJOR>
 __global__ void __launch_bounds__(256)
 gemm_simt_kernel(const float* __restrict__ A, long long sam, long long sak, const float* __restrict__ B, long long sbn,
                  long long sbk, float* __restrict__ C, long long ldc, int M, int N, int K, int k_chunk, Epilogue ep,
-                 float* __restrict__ split_ws) {
+                 float* __restrict__ split_ws, int emu) {
     __shared__ __align__(16) float As[BK][BM + PADM];
     __shared__ __align__(16) float Bs[BK][BN + PADM];
     const int tid = threadIdx.x;
@@ -59,7 +70,7 @@ gemm_simt_kernel(const float* __restrict__ A, long long sam, long long sak, cons
             int m, k;
             if (A_KMAJOR) { k = e & 15; m = e >> 4; } else { m = e & 63; k = e >> 6; }
             const int gm = m0 + m, gk = k0 + k;
-            As[k][m] = (gm < M && gk < kend) ? __ldg(A + (long long)gm * sam + (long long)gk * sak) : 0.f;
+            As[k][m] = (gm < M && gk < kend) ? emulate_round(__ldg(A + (long long)gm * sam + (long long)gk * sak), emu) : 0.f;
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -67,7 +78,7 @@ gemm_simt_kernel(const float* __restrict__ A, long long sam, long long sak, cons
             int n, k;
             if (B_KMAJOR) { k = e & 15; n = e >> 4; } else { n = e & 63; k = e >> 6; }
             const int gn = n0 + n, gk = k0 + k;
-            Bs[k][n] = (gn < N && gk < kend) ? __ldg(B + (long long)gn * sbn + (long long)gk * sbk) : 0.f;
+            Bs[k][n] = (gn < N && gk < kend) ? emulate_round(__ldg(B + (long long)gn * sbn + (long long)gk * sbk), emu) : 0.f;
         }
         __syncthreads();
 #pragma unroll
@@ -129,10 +140,12 @@ int launch_gemm_simt(const GemmArgs& a, cudaStream_t st) {
     }
     dim3 grid(cdiv(a.N, BN), cdiv(a.M, BM), splits);
     float* ws = splits > 1 ? a.split_ws : nullptr;
+    static int emu = -1;
+    if (emu < 0) { const char* s = getenv("RIFT_B200_EMULATE"); emu = s ? atoi(s) : 0; }
     const bool ak = (a.sak == 1), bk = (a.sbk == 1);
 #define RIFT_GEMM_LAUNCH(AK, BK_)                                                                                     \
     gemm_simt_kernel<AK, BK_><<<grid, 256, 0, st>>>(a.A, a.sam, a.sak, a.B, a.sbn, a.sbk, a.C, a.ldc, a.M, a.N, a.K, \
-                                                    k_chunk, ep, ws)
+                                                    k_chunk, ep, ws, emu)
     if (ak && bk) RIFT_GEMM_LAUNCH(true, true);
     else if (ak && !bk) RIFT_GEMM_LAUNCH(true, false);
     else if (!ak && bk) RIFT_GEMM_LAUNCH(false, true);

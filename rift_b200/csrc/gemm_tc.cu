@@ -1,0 +1,479 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a:  C[M,N] = epilogue( A[M,K] x W[N,K]^T ), fp32 in / fp32 out.
+//
+// Numerics: "split-bf16 x3".  Every fp32 operand x is carried as two bf16 planes hi = bf16(x),
+// lo = bf16(x - hi) (16 mantissa bits together) and the product is accumulated in fp32 in TMEM as
+//     A_lo*W_hi + A_hi*W_lo + A_hi*W_hi
+// i.e. three kind::f16 (bf16) UMMAs per k-step.  Measured end to end (tools_precision_study.py):
+// plain bf16 operands give 1e-2 relative logit error and single-pass tf32 1-2e-3, both outside the
+// 1e-3 parity tolerance of BASELINE.json; the split form stays at the 1e-5 level for 3x the MMA work
+// of bf16 (= 1.5x tf32), which these memory-bound shapes (K <= 1024, N <= 1024) hide.
+//
+// Structure: persistent, warp-specialised, one CTA per SM, 320 threads
+//   warp 0      TMA producer: A_hi / A_lo (box 64 x 128) and W_hi / W_lo (box 64 x 64) tiles, SWIZZLE_128B,
+//               3-stage ring of 64 KB stages, mbarrier complete_tx
+//   warp 1      TMEM allocation (2 x BN columns: double-buffered accumulator) + single-thread tcgen05.mma
+//               issue; tcgen05.commit releases smem stages and publishes finished accumulators
+//   warps 2-9   epilogue: tcgen05.ld (32 lanes x 32 columns per instruction), fused
+//               alpha / pre-add / BatchNorm scale / bias / ReLU|GELU / residual / beta*C, float4 stores;
+//               the epilogue of tile i overlaps the main loop of tile i+1 through the second accumulator
+// The A planes are produced by pack_split (below) or directly by the producing kernel (LayerNorm etc.);
+// the W planes are refreshed after every optimizer step (split_weights_kernel).
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <cuda_bf16.h>
+
+#include <unordered_map>
+
+#include "common.cuh"
+#include "gemm_tc.h"
+
+namespace rift {
+
+constexpr int TC_BM = 128, TC_BK = 64, TC_STAGES = 3;
+constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
+
+// ---------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+// [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major) | [32,46) SBO>>4 = 1024 B (8 rows x 128 B)
+// | [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = f32, A = B = bf16, both K-major, M = 128, N = BN
+__host__ __device__ constexpr uint32_t make_idesc(int bn) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+}
+
+struct TcEpilogue {
+    const float* bias; const float* colscale;
+    const float* pre; long long ldpre; int pre_div;
+    const float* res; long long ldres; int res_div; int res_mod;
+    int act; float beta; float alpha;
+    float* preact;
+};
+
+struct TcKernelArgs {
+    float* C; long long ldc;
+    int M, N, K;
+    int w_n0, w_k0;          // origin of this (possibly sliced) weight inside the split planes
+    TcEpilogue ep;
+};
+
+template <int BN>
+struct TcSmem {
+    static constexpr int A_TILE = TC_BM * TC_BK * 2;     // bytes per bf16 plane
+    static constexpr int B_TILE = BN * TC_BK * 2;
+    static constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;
+    static constexpr int TOTAL = TC_STAGES * STAGE + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+               const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, TcKernelArgs g) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    using SM = TcSmem<BN>;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_STAGES * SM::STAGE);
+    uint64_t* full = bars;                          // [stages] 1 arrival + TMA bytes
+    uint64_t* empty = bars + TC_STAGES;             // [stages] tcgen05.commit
+    uint64_t* acc_full = bars + 2 * TC_STAGES;      // [2] accumulator complete (tcgen05.commit)
+    uint64_t* acc_empty = bars + 2 * TC_STAGES + 2; // [2] accumulator drained (one arrival per epilogue warp)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_n = (g.N + BN - 1) / BN;
+    const int tiles_m = (g.M + TC_BM - 1) / TC_BM;
+    const int n_tiles = tiles_m * tiles_n;
+    const int num_kb = (g.K + TC_BK - 1) / TC_BK;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], TC_EPI_WARPS); }
+        fence_barrier_init();
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_lo) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB_lo) : "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int it = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int m0 = (tile / tiles_n) * TC_BM, n0 = (tile % tiles_n) * BN;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % TC_STAGES;
+                    const uint32_t ph = (it / TC_STAGES) & 1;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    uint8_t* a_hi = smem + s * SM::STAGE;
+                    uint8_t* a_lo = a_hi + SM::A_TILE;
+                    uint8_t* b_hi = a_lo + SM::A_TILE;
+                    uint8_t* b_lo = b_hi + SM::B_TILE;
+                    mbar_arrive_expect_tx(&full[s], SM::STAGE);
+                    tma_load_2d(a_hi, &tmA_hi, &full[s], kb * TC_BK, m0);
+                    tma_load_2d(a_lo, &tmA_lo, &full[s], kb * TC_BK, m0);
+                    const int ck = g.w_k0 + kb * TC_BK;
+#pragma unroll
+                    for (int rb = 0; rb < BN / 64; ++rb) {      // the weight tensor-map box is 64 (k) x 64 (rows)
+                        tma_load_2d(b_hi + rb * (64 * TC_BK * 2), &tmB_hi, &full[s], ck, g.w_n0 + n0 + rb * 64);
+                        tma_load_2d(b_lo + rb * (64 * TC_BK * 2), &tmB_lo, &full[s], ck, g.w_n0 + n0 + rb * 64);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BN);
+            int it = 0, ti = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+                const int buf = ti & 1;
+                mbar_wait(&acc_empty[buf], ((ti >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t tacc = tmem_base + (uint32_t)(buf * BN);
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % TC_STAGES;
+                    const uint32_t ph = (it / TC_STAGES) & 1;
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    const uint32_t a_hi = smem_u32(smem + s * SM::STAGE);
+                    const uint32_t a_lo = a_hi + SM::A_TILE;
+                    const uint32_t b_hi = a_lo + SM::A_TILE;
+                    const uint32_t b_lo = b_hi + SM::B_TILE;
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 16; ++k) {       // UMMA_K = 16 bf16 = 32 B inside the 128 B swizzle atom
+                        const uint64_t dah = make_sdesc(a_hi + k * 32), dal = make_sdesc(a_lo + k * 32);
+                        const uint64_t dbh = make_sdesc(b_hi + k * 32), dbl = make_sdesc(b_lo + k * 32);
+                        umma_bf16(tacc, dal, dbh, idesc, (kb | k) != 0);     // small terms first
+                        umma_bf16(tacc, dah, dbl, idesc, 1);
+                        umma_bf16(tacc, dah, dbh, idesc, 1);
+                    }
+                    umma_commit(&empty[s]);                      // frees the stage once these MMAs retire
+                }
+                umma_commit(&acc_full[buf]);
+            }
+        }
+    } else {
+        // ===================== epilogue (8 warps) =====================
+        const int ew = warp - 2;
+        const int quarter = warp & 3;                // TMEM lane quarter this warp may access
+        const int half = ew >> 2;                    // column half of the tile
+        const TcEpilogue& e = g.ep;
+        int ti = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+            const int m0 = (tile / tiles_n) * TC_BM, n0 = (tile % tiles_n) * BN;
+            const int buf = ti & 1;
+            mbar_wait(&acc_full[buf], (ti >> 1) & 1);
+            tc_fence_after();
+            const int m = m0 + quarter * 32 + lane;
+            const bool row_ok = m < g.M;
+            const float* pre_row = e.pre ? e.pre + (long long)(m / e.pre_div) * e.ldpre : nullptr;
+            const float* res_row = nullptr;
+            if (e.res) res_row = e.res + (long long)(e.res_mod > 0 ? (m % e.res_mod) : (m / e.res_div)) * e.ldres;
+            float* c_row = g.C + (long long)m * g.ldc;
+            float* pa_row = e.preact ? e.preact + (long long)m * g.ldc : nullptr;
+#pragma unroll 1
+            for (int cc = 0; cc < BN / 2; cc += 32) {
+                const int c0 = half * (BN / 2) + cc;
+                uint32_t r[32];
+                tmem_ld_32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN + c0), r);
+                tmem_ld_wait();
+                if (row_ok) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const int n = n0 + c0 + j;
+                        if (n < g.N) {
+                            float4 v = make_float4(__uint_as_float(r[j]) * e.alpha, __uint_as_float(r[j + 1]) * e.alpha,
+                                                   __uint_as_float(r[j + 2]) * e.alpha, __uint_as_float(r[j + 3]) * e.alpha);
+                            if (pre_row) { const float4 t = ld4(pre_row + n); v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
+                            if (e.colscale) { const float4 t = ld4(e.colscale + n); v.x *= t.x; v.y *= t.y; v.z *= t.z; v.w *= t.w; }
+                            if (e.bias) { const float4 t = ld4(e.bias + n); v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
+                            if (pa_row) *reinterpret_cast<float4*>(pa_row + n) = v;
+                            if (e.act == ACT_RELU) {
+                                v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+                            } else if (e.act == ACT_GELU) {
+                                v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
+                            }
+                            if (res_row) { const float4 t = ld4(res_row + n); v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
+                            if (e.beta != 0.f) {
+                                const float4 t = ld4(c_row + n);
+                                v.x += e.beta * t.x; v.y += e.beta * t.y; v.z += e.beta * t.z; v.w += e.beta * t.w;
+                            }
+                            *reinterpret_cast<float4*>(c_row + n) = v;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 2 * BN);
+    }
+}
+
+// ---------------------------------------------------------------------------------- operand planes
+// fp32 [M, K] (row pitch ld) -> bf16 planes hi / lo [M, Kp], zero padded to Kp
+__global__ void __launch_bounds__(256)
+pack_split_kernel(const float* __restrict__ src, long long ld, int M, int K, int Kp, __nv_bfloat16* __restrict__ hi,
+                  __nv_bfloat16* __restrict__ lo, int vec) {
+    const int kq = Kp >> 2;
+    const long long total = (long long)M * kq;
+    for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
+        const int m = (int)(e / kq), k = (int)(e - (long long)m * kq) << 2;
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float* p = src + (long long)m * ld + k;
+        if (vec && k + 3 < K) x = __ldg(reinterpret_cast<const float4*>(p));
+        else {
+            if (k < K) x.x = __ldg(p);
+            if (k + 1 < K) x.y = __ldg(p + 1);
+            if (k + 2 < K) x.z = __ldg(p + 2);
+            if (k + 3 < K) x.w = __ldg(p + 3);
+        }
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(x.x), h1 = __float2bfloat16_rn(x.y), h2 = __float2bfloat16_rn(x.z),
+                            h3 = __float2bfloat16_rn(x.w);
+        __nv_bfloat162 a = __halves2bfloat162(h0, h1), b = __halves2bfloat162(h2, h3);
+        __nv_bfloat162 c = __floats2bfloat162_rn(x.x - __bfloat162float(h0), x.y - __bfloat162float(h1));
+        __nv_bfloat162 d = __floats2bfloat162_rn(x.z - __bfloat162float(h2), x.w - __bfloat162float(h3));
+        uint2 uh, ul;
+        uh.x = *reinterpret_cast<uint32_t*>(&a); uh.y = *reinterpret_cast<uint32_t*>(&b);
+        ul.x = *reinterpret_cast<uint32_t*>(&c); ul.y = *reinterpret_cast<uint32_t*>(&d);
+        *reinterpret_cast<uint2*>(hi + (long long)m * Kp + k) = uh;
+        *reinterpret_cast<uint2*>(lo + (long long)m * Kp + k) = ul;
+    }
+}
+
+int launch_pack_split(const float* src, long long ld, int M, int K, int Kp, void* hi, void* lo, cudaStream_t st) {
+    if (M <= 0) return 0;
+    const int vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+    const long long total = (long long)M * (Kp >> 2);
+    pack_split_kernel<<<(int)min((long long)148 * 16, (total + 255) / 256), 256, 0, st>>>(
+        src, ld, M, K, Kp, static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(lo), vec);
+    RIFT_LAUNCH_OK();
+    return 0;
+}
+
+struct SplitJob { const float* src; long long ld; int N, K, Kp; __nv_bfloat16* hi; __nv_bfloat16* lo; long long first; };
+
+__global__ void __launch_bounds__(256)
+split_weights_kernel(const SplitJob* __restrict__ jobs, int n_jobs, long long total) {
+    for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
+        int lo_j = 0, hi_j = n_jobs - 1;                 // last job whose first <= e
+        while (lo_j < hi_j) {
+            const int mid = (lo_j + hi_j + 1) >> 1;
+            if (jobs[mid].first <= e) lo_j = mid; else hi_j = mid - 1;
+        }
+        const SplitJob j = jobs[lo_j];
+        const long long i = e - j.first;
+        const int n = (int)(i / j.Kp), k = (int)(i - (long long)n * j.Kp);
+        const float x = k < j.K ? j.src[(long long)n * j.ld + k] : 0.f;
+        const __nv_bfloat16 h = __float2bfloat16_rn(x);
+        j.hi[i] = h;
+        j.lo[i] = __float2bfloat16_rn(x - __bfloat162float(h));
+    }
+}
+
+int launch_split_weights(const void* jobs_dev, int n_jobs, long long total, cudaStream_t st) {
+    if (n_jobs <= 0 || total <= 0) return 0;
+    split_weights_kernel<<<(int)min((long long)148 * 8, (total + 255) / 256), 256, 0, st>>>(
+        static_cast<const SplitJob*>(jobs_dev), n_jobs, total);
+    RIFT_LAUNCH_OK();
+    return 0;
+}
+
+size_t split_job_bytes() { return sizeof(SplitJob); }
+void fill_split_job(void* dst, const float* src, long long ld, int N, int K, int Kp, void* hi, void* lo, long long first) {
+    SplitJob j{src, ld, N, K, Kp, static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(lo), first};
+    *static_cast<SplitJob*>(dst) = j;
+}
+
+// ---------------------------------------------------------------------------------- host side
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    }
+    return fn;
+}
+
+static int encode_plane_map(void* map_out, const void* plane, int rows, int Kp, int box_rows) {
+    auto enc = get_encode();
+    RIFT_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+    static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap size");
+    cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)Kp * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(static_cast<CUtensorMap*>(map_out), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(plane), dims,
+                     strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    RIFT_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    return 0;
+}
+
+int make_weight_tensor_map(void* map_out, const void* plane, int N, int Kp) { return encode_plane_map(map_out, plane, N, Kp, 64); }
+
+// activation planes live at fixed workspace addresses, so their descriptors are encoded once and reused
+struct MapKey {
+    const void* p; int rows, Kp;
+    bool operator==(const MapKey& o) const { return p == o.p && rows == o.rows && Kp == o.Kp; }
+};
+struct MapKeyHash {
+    size_t operator()(const MapKey& k) const {
+        return std::hash<const void*>()(k.p) ^ (std::hash<long long>()(((long long)k.rows << 20) ^ k.Kp) * 1000003u);
+    }
+};
+struct MapVal { alignas(64) unsigned char m[128]; };
+
+static int activation_map(const void* plane, int rows, int Kp, const CUtensorMap** out) {
+    static std::unordered_map<MapKey, MapVal, MapKeyHash> cache;
+    MapKey key{plane, rows, Kp};
+    auto it = cache.find(key);
+    if (it == cache.end()) {
+        if (cache.size() > 65536) cache.clear();
+        MapVal v;
+        int r = encode_plane_map(v.m, plane, rows, Kp, TC_BM);
+        if (r) return r;
+        it = cache.emplace(key, v).first;
+    }
+    *out = reinterpret_cast<const CUtensorMap*>(it->second.m);
+    return 0;
+}
+
+bool gemm_tc_shape_ok(int M, int N, int K) { return K >= 32 && N >= 16 && (N % 4) == 0 && M >= 64; }
+
+bool gemm_tc_eligible(const GemmArgs& a) {
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    return a.sak == 1 && a.sbk == 1 && gemm_tc_shape_ok(a.M, a.N, a.K) && a.split_k <= 1 && (a.ldc % 4) == 0 && al16(a.C) &&
+           al16(a.bias) && al16(a.colscale) && al16(a.pre) && (a.ldpre % 4) == 0 && al16(a.res) && (a.ldres % 4) == 0 &&
+           al16(a.preact);
+}
+
+template <int BN>
+static int launch_tc(const GemmArgs& a, const void* a_hi, const void* a_lo, int Kp, const TcWeight& w, int n0, int k0,
+                     cudaStream_t st) {
+    static bool attr = false;
+    static int sms = 148;
+    if (!attr) {
+        RIFT_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<BN>::TOTAL));
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        attr = true;
+    }
+    const CUtensorMap *ma_hi, *ma_lo;
+    int r = activation_map(a_hi, a.M, Kp, &ma_hi);
+    if (r) return r;
+    r = activation_map(a_lo, a.M, Kp, &ma_lo);
+    if (r) return r;
+    TcKernelArgs g;
+    g.C = a.C; g.ldc = a.ldc; g.M = a.M; g.N = a.N; g.K = a.K; g.w_n0 = n0; g.w_k0 = k0;
+    g.ep = TcEpilogue{a.bias, a.colscale, a.pre, a.ldpre, a.pre_div, a.res, a.ldres, a.res_div, a.res_mod, a.act, a.beta,
+                      a.alpha, a.preact};
+    const int n_tiles = cdiv(a.N, BN) * cdiv(a.M, TC_BM);
+    gemm_tc_kernel<BN><<<min(n_tiles, sms), TC_THREADS, TcSmem<BN>::TOTAL, st>>>(
+        *ma_hi, *ma_lo, *reinterpret_cast<const CUtensorMap*>(w.tm_hi), *reinterpret_cast<const CUtensorMap*>(w.tm_lo), g);
+    RIFT_LAUNCH_OK();
+    return 0;
+}
+
+int launch_gemm_tc(const GemmArgs& a, const void* a_hi, const void* a_lo, int Kp, const TcWeight& w, int n0, int k0,
+                   cudaStream_t st) {
+    RIFT_REQUIRE(gemm_tc_eligible(a), "gemm_tc: shape / layout not eligible");
+    RIFT_REQUIRE(n0 + a.N <= w.N && k0 + a.K <= w.Kp, "gemm_tc: weight slice out of range");
+    RIFT_REQUIRE(Kp % 64 == 0 && Kp >= a.K, "gemm_tc: bad activation plane pitch");
+    if (a.M <= 0 || a.N <= 0) return 0;
+    if (a.N <= 64) return launch_tc<64>(a, a_hi, a_lo, Kp, w, n0, k0, st);
+    return launch_tc<128>(a, a_hi, a_lo, Kp, w, n0, k0, st);
+}
+
+}  // namespace rift

@@ -11,6 +11,7 @@ BatchNorm running statistics) — what the reference computes under ``model.eval
 rollout path (``get_action``) uses.
 """
 import ctypes as C
+import os
 from typing import Dict, Iterable, Optional
 
 import torch
@@ -99,6 +100,8 @@ class PlanningModel:
         self.drop_path, self.dropout, self.state_dropout = drop_path, dropout, state_dropout   # inert: parity mode
         self.device = torch.device(device)
         self.training = False
+        # True: every GEMM on the exact-fp32 SIMT kernel (validation); False: tcgen05 split-bf16 path
+        self.exact_fp32 = bool(int(os.environ.get("RIFT_B200_EXACT_FP32", "0")))
         self._engine = C.c_void_p()
         self._workspace = None
         self._ws_shape = None
@@ -135,7 +138,16 @@ class PlanningModel:
         _lib.check(L.rift_b200_create(C.byref(mc), arr, len(ents), C.byref(self._engine)), "create")
         _lib.check(L.rift_b200_bind_arena(self._engine, _lib.ptr(self.arena.params), _lib.ptr(self.arena.grads),
                                           self.arena.params.numel()), "bind_arena")
+        # split-bf16 weight planes + TMA descriptors for the tcgen05 GEMM path
+        self._wcache = torch.empty(L.rift_b200_weight_cache_bytes(self._engine), dtype=torch.uint8, device=self.device)
+        _lib.check(L.rift_b200_bind_weight_cache(self._engine, _lib.ptr(self._wcache), self._wcache.numel()),
+                   "bind_weight_cache")
         self._ws_shape = None
+
+    def params_updated(self, trainable_only: bool = False):
+        """Tell the engine the fp32 arena changed (optimizer step / checkpoint load): the bf16 weight
+        planes of the tensor-core path are re-split by the next forward."""
+        _lib.check(_lib.lib().rift_b200_params_updated(self._engine, int(trainable_only)), "params_updated")
 
     def __del__(self):
         try:
@@ -151,7 +163,9 @@ class PlanningModel:
     def load_state_dict(self, sd, strict=True):
         if any(k.startswith("model.") for k in sd):        # training ckpt keys (pluto.py:135-137)
             sd = {k[len("model."):]: v for k, v in sd.items() if k.startswith("model.")}
-        return self.arena.load_state_dict(sd, strict)
+        r = self.arena.load_state_dict(sd, strict)
+        self.params_updated(False)
+        return r
 
     def eval(self):
         self.training = False
@@ -213,7 +227,7 @@ class PlanningModel:
         for name in ("probability", "trajectory", "prediction", "hidden", "ref_free_trajectory",
                      "candidate_trajectories", "r_padding_mask"):
             setattr(o, name, res[name].data_ptr() if name in res and res[name].numel() else None)
-        flags = _lib.FWD_SAVE_FOR_BACKWARD if save_for_backward else 0
+        flags = (_lib.FWD_SAVE_FOR_BACKWARD if save_for_backward else 0) | (_lib.GEMM_SIMT if self.exact_fp32 else 0)
         _lib.check(_lib.lib().rift_b200_forward(self._engine, C.byref(pb.struct), C.byref(o),
                                                 _lib.ptr(self._workspace), self._workspace.numel(), flags,
                                                 _lib.stream_ptr()), "forward")

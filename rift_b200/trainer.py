@@ -172,6 +172,7 @@ class LightningTrainer:
         if self.optimizer is None:
             self.configure_optimizers()
         self.optimizer.step(count=self._count)
+        self.model.params_updated(trainable_only=True)
 
     def on_train_epoch_end(self):
         if self.scheduler is not None:

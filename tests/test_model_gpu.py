@@ -142,6 +142,23 @@ def test_freezing_preserves_values_and_forward():
     assert torch.equal(model(d)["probability"], p0)
 
 
+def test_tensor_core_path_agrees_with_exact_fp32_path():
+    """The tcgen05 split-bf16 GEMMs against the exact-fp32 SIMT GEMMs of the same library, whole forward."""
+    cfg = MODEL_ZOO["medium"]()
+    sd = synth_state_dict(cfg, seed=7)
+    feats = synth_features(cfg, 16, 32, 20, 6, seed=5, ragged=True)
+    d = to_torch_tree(feats, "cuda")
+    model = build(cfg, sd)
+    model.exact_fp32 = False
+    a = model(d)
+    model.exact_fp32 = True
+    b = model(d)
+    keep = torch.from_numpy(feats["reference_line"]["valid_mask"].any(-1))
+    for k in ("probability", "trajectory", "hidden", "prediction"):
+        x, y = (a[k].cpu()[keep], b[k].cpu()[keep]) if k == "probability" else (a[k].cpu(), b[k].cpu())
+        assert (x - y).abs().max().item() <= 2e-4 * y.abs().max().item(), k
+
+
 def test_cfg2_shape_properties():
     """BASELINE configs[1] shape (64 x 32 agents, R=6, Pluto-medium): finite outputs, exact padding,
     softmax-gradient rows sum to zero, loss decreases over a few updates on a fixed batch."""

@@ -41,6 +41,21 @@ def test_linear_epilogues(rows, K, N, act):
     close(y, ref + r, 1e-5, "linear")
 
 
+@pytest.mark.parametrize("rows,K,N", [(128, 64, 128), (64, 32, 16), (300, 256, 160), (1000, 132, 96), (4608, 512, 256),
+                                      (3328, 256, 1024), (129, 1024, 256), (46080, 256, 256), (777, 192, 64)])
+@pytest.mark.parametrize("act", [0, 2])
+def test_linear_tcgen05_split_bf16(rows, K, N, act):
+    """tcgen05 GEMM (A split in-kernel, W pre-split planes via TMA, 3 bf16 MMAs per k-step) vs fp32."""
+    x, w, b, r = rnd(rows, K, seed=1), rnd(N, K, seed=2, scale=K ** -0.5), rnd(N, seed=3), rnd(rows, N, seed=4)
+    y = torch.full((rows, N), float("nan"), device="cuda")
+    L = _lib.lib()
+    scratch = torch.empty(L.rift_b200_op_linear_tc_scratch_bytes(rows, N, K), dtype=torch.uint8, device="cuda")
+    _lib.check(L.rift_b200_op_linear_tc(P(x), rows, K, P(w), P(b), N, act, P(r), P(y), P(scratch), scratch.numel(), 1, S()))
+    ref = TF.linear(x.double(), w.double(), b.double())
+    ref = TF.gelu(ref) if act == 2 else ref
+    close(y, ref + r.double(), 3e-5, "linear_tc")     # split-bf16: 16 mantissa bits per operand
+
+
 @pytest.mark.parametrize("layout", ["nt", "nn", "tn", "tt"])
 @pytest.mark.parametrize("M,N,K,split", [(65, 70, 33, 1), (256, 192, 4000, 8), (1, 256, 4608, 9)])
 def test_gemm_strides_and_split_k(layout, M, N, K, split):
