@@ -46,6 +46,17 @@ def trainable_names(cfg: PlutoConfig, trainable_layers: Iterable[str]) -> List[s
     return names
 
 
+# Parameters whose outputs never reach an RL objective: autograd leaves their .grad = None in the
+# reference, and torch.optim.AdamW skips such parameters entirely (no update, no weight decay).  They are
+# therefore laid out with the frozen parameters even when their module is listed as trainable.
+NO_GRAD_PREFIXES = ("static_objects_encoder.", "agent_predictor.", "hidden_proj.", "ref_free_decoder.",
+                    "planning_decoder.loc_head.", "planning_decoder.yaw_head.", "planning_decoder.vel_head.")
+
+
+def receives_gradient(name: str) -> bool:
+    return not name.startswith(NO_GRAD_PREFIXES)
+
+
 def is_decay(name: str, shape: Tuple[int, ...]) -> bool:
     """True for Linear / Conv1d / MultiheadAttention weights; biases, LayerNorm / BatchNorm /
     Embedding weights and bare parameters (m_emb, m_pos, query, pos_embed, rpb) do not decay."""
@@ -64,7 +75,7 @@ class ParamArena:
         self.device = torch.device(device)
         spec = param_spec(cfg)
         self.spec = {n: (tuple(s), k) for n, s, k in spec}
-        train = set(trainable_names(cfg, trainable_layers))
+        train = set(n for n in trainable_names(cfg, trainable_layers) if receives_gradient(n))
         groups = {0: [], 1: [], 2: [], 3: []}
         for n, s, k in spec:
             if k != "f32":

@@ -66,7 +66,7 @@ size_t rift_b200_workspace_bytes(const rift_b200_engine* e_, const rift_b200_bat
     out.probability = dummy; out.trajectory = dummy; out.prediction = dummy; out.hidden = dummy;
     out.ref_free_trajectory = dummy; out.candidate_trajectories = dummy; out.r_padding_mask = nullptr;
     if (e->forward(*shape, out, c) != 0) return 0;
-    if (e->grads && !e->m.any_trainable_outside_pi_head) {
+    if (e->grads) {
         if (e->backward(*shape, nullptr, c) != 0) return 0;
     }
     return c.off + 4096;

@@ -70,6 +70,6 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
 }
 #endif
 
-enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2 };
+enum ActKind { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2 };
 
 }  // namespace rift

@@ -1,4 +1,4 @@
-// Forward / backward schedule of the Pluto trajectory policy on the rift_b200 kernels.
+// Parameter binding and the forward schedule of the Pluto trajectory policy on the rift_b200 kernels.
 //
 // Mirrors PlanningModel.forward (rift/cbv/planning/pluto/model/pluto_model.py:122-225) in the
 // deterministic parity mode of SURVEY 8(c): dropout / drop-path identity, BatchNorm running
@@ -6,191 +6,16 @@
 // handled densely: every padded row is computed and then masked, which is equivalent because no
 // op in the model mixes rows of different agents / polylines except through masked attention and
 // masked max-pooling.
-#include "engine.h"
+//
+// Activations that feed a GEMM travel as split-bf16 planes written directly by their producer
+// (LayerNorm, attention, GEMM epilogues, im2col, pooling); fp32 copies are kept only where another
+// kernel reads them (residual stream, attention q/k/v, pooling inputs) or when the backward needs them.
+#include "engine_ops.h"
 
-#include <math.h>
-
-namespace rift {
-
-#define TRY(x)                   \
-    do {                         \
-        int _r = (x);            \
-        if (_r != 0) return _r;  \
-    } while (0)
-
-#define ALLOC(var, T, n)                                                           \
-    T* var = c.alloc<T>((size_t)(n));                                              \
-    if (!var) {                                                                    \
-        set_last_error("workspace too small (see rift_b200_workspace_bytes)");     \
-        return -1;                                                                 \
-    }
+using namespace rift;
 
 static const int NAT_HEADS_[3] = {2, 4, 8};
 static const int NAT_K_[3] = {3, 3, 5};
-static const int NFREQ = 64, FIN = 129, FLD = 132;    // Fourier feature width, padded row stride
-static const int PE_H1 = 128, PE_H2 = 256;
-
-// ---------------------------------------------------------------------------------- ops
-static int gemm(Ctx& c, const GemmArgs& a) {
-    if (c.dry) return 0;
-    return launch_gemm_simt(a, c.st);
-}
-
-// GEMM against a (possibly sliced) weight matrix: tcgen05 path when the shape qualifies and the
-// weight has pre-split planes, exact-fp32 SIMT otherwise (tiny K / N == 1 / misaligned views).
-static int gemm_w(Ctx& c, GemmArgs& a, const Lin& L, long long ldw) {
-    a.B = L.W; a.sbn = ldw; a.sbk = 1; a.N = L.N; a.K = L.K;
-    // shape-only decision so that the dry (sizing) pass and the real pass allocate identically
-    const bool tc = !c.simt && L.tc >= 0 && c.tcw && a.sak == 1 && gemm_tc_shape_ok(a.M, a.N, a.K) && (a.ldc % 4) == 0 &&
-                    (a.ldres % 4) == 0 && (a.ldpre % 4) == 0;
-    if (tc) {
-        const int Kp = tc_pitch(a.K);
-        ALLOC(a_hi, uint16_t, (size_t)a.M * Kp);
-        ALLOC(a_lo, uint16_t, (size_t)a.M * Kp);
-        if (c.dry) return 0;
-        if (gemm_tc_eligible(a)) {
-            TRY(launch_pack_split(a.A, a.sam, a.M, a.K, Kp, a_hi, a_lo, c.st));
-            return launch_gemm_tc(a, a_hi, a_lo, Kp, (*c.tcw)[L.tc], L.tc_n0, L.tc_k0, c.st);
-        }
-    }
-    if (c.dry) return 0;
-    return launch_gemm_simt(a, c.st);
-}
-
-// Y = act((X W^T [+pre]) [*colscale] + b) [+ res]
-static int linear_ld(Ctx& c, const float* X, long long ldx, int M, const Lin& L, long long ldw, float* Y, long long ldy,
-                     int act = ACT_NONE, const float* res = nullptr, long long ldres = 0, int res_div = 1,
-                     float* preact = nullptr) {
-    GemmArgs a;
-    a.A = X; a.sam = ldx; a.sak = 1;
-    a.C = Y; a.ldc = ldy; a.M = M;
-    a.bias = L.b; a.act = act; a.res = res; a.ldres = ldres; a.res_div = res_div; a.preact = preact;
-    return gemm_w(c, a, L, ldw);
-}
-static int linear(Ctx& c, const float* X, long long ldx, int M, const Lin& L, float* Y, long long ldy, int act = ACT_NONE,
-                  const float* res = nullptr, long long ldres = 0, int res_div = 1, float* preact = nullptr) {
-    return linear_ld(c, X, ldx, M, L, L.K, Y, ldy, act, res, ldres, res_div, preact);
-}
-
-// slice of a Linear: output rows [n0, n0+n), input columns [k0, k0+k).  NOTE: a slice keeps the parent's
-// row pitch; callers pass it as `ldw` to linear_ld.
-static Lin slice(const Lin& L, int n0, int n, int k0, int k, bool with_bias) {
-    Lin s;
-    s.W = L.W + (long long)n0 * L.K + k0;
-    s.b = (with_bias && L.b) ? L.b + n0 : nullptr;
-    s.dW = L.dW ? L.dW + (long long)n0 * L.K + k0 : nullptr;
-    s.db = (with_bias && L.db) ? L.db + n0 : nullptr;
-    s.N = n; s.K = k; s.train = L.train;
-    s.tc = L.tc; s.tc_n0 = L.tc_n0 + n0; s.tc_k0 = L.tc_k0 + k0;
-    return s;
-}
-
-static int layernorm(Ctx& c, const float* x, int rows, const Norm& n, float* y, int relu = 0, float* mean = nullptr,
-                     float* rstd = nullptr, const float* add_rowmod = nullptr, int rowmod = 0, float* y2 = nullptr) {
-    if (c.dry) return 0;
-    return launch_layernorm(x, n.C, rows, n.C, n.g, n.b, y, n.C, relu, add_rowmod, rowmod, y2, mean, rstd, c.st);
-}
-
-// MLPLayer: Linear -> LayerNorm -> ReLU -> Linear  (layers/mlp_layer.py:4-16)
-static int mlp_layer(Ctx& c, const float* X, long long ldx, int M, const MLPLayerP& p, float* Y, long long ldy,
-                     float** h_out = nullptr, float** a_out = nullptr, float** mean_out = nullptr, float** rstd_out = nullptr) {
-    ALLOC(h, float, (size_t)M * p.l0.N);
-    ALLOC(a, float, (size_t)M * p.l0.N);
-    float* mean = nullptr; float* rstd = nullptr;
-    if (mean_out) {
-        mean = c.alloc<float>(M); rstd = c.alloc<float>(M);
-        if (!mean || !rstd) { set_last_error("workspace too small"); return -1; }
-    }
-    TRY(linear(c, X, ldx, M, p.l0, h, p.l0.N));
-    TRY(layernorm(c, h, M, p.n, a, 1, mean, rstd));
-    TRY(linear(c, a, p.l0.N, M, p.l3, Y, ldy));
-    if (h_out) *h_out = h;
-    if (a_out) *a_out = a;
-    if (mean_out) { *mean_out = mean; *rstd_out = rstd; }
-    return 0;
-}
-
-// FourierEmbedding (layers/fourier_embedding.py:45-55): out = to_out(sum_i mlp_i(feat_i)) [+ res]
-static int fourier(Ctx& c, const float* x, int rows, const FourierP& p, float* out, const float* res) {
-    const int D = p.out_l.N;
-    ALLOC(acc, float, (size_t)rows * D);
-    for (int i = 0; i < p.d; ++i) {
-        ALLOC(feat, float, (size_t)rows * FLD);
-        ALLOC(h, float, (size_t)rows * D);
-        ALLOC(hn, float, (size_t)rows * D);
-        if (!c.dry) TRY(launch_fourier_features(x, rows, p.d, i, p.freqs.p, NFREQ, feat, FLD, c.st));
-        TRY(linear(c, feat, FLD, rows, p.mlps[i].l0, h, D));
-        TRY(layernorm(c, h, rows, p.mlps[i].n, hn, 1));
-        TRY(linear(c, hn, D, rows, p.mlps[i].l3, acc, D, ACT_NONE, i > 0 ? acc : nullptr, D, 1));
-    }
-    ALLOC(on, float, (size_t)rows * D);
-    TRY(layernorm(c, acc, rows, p.out_n, on, 1));
-    TRY(linear(c, on, D, rows, p.out_l, out, D, ACT_NONE, res, D, 1));
-    return 0;
-}
-
-// PointsEncoder (layers/embedding.py:271-296) over `groups` polylines of `n` points, C_in channels
-static int points_encoder(Ctx& c, const float* F, int groups, int n, int Cin, const uint8_t* mask, const PointsEncP& p,
-                          float* out) {
-    const int rows = groups * n;
-    const int Cout = p.s3.N;
-    ALLOC(sc1, float, PE_H1); ALLOC(sh1, float, PE_H1); ALLOC(sc2, float, PE_H2); ALLOC(sh2, float, PE_H2);
-    ALLOC(h1, float, (size_t)rows * PE_H1);
-    ALLOC(f, float, (size_t)rows * PE_H2);
-    ALLOC(pooled, float, (size_t)groups * PE_H2);
-    ALLOC(arg1, int, (size_t)groups * PE_H2);
-    ALLOC(gp, float, (size_t)groups * PE_H2);
-    ALLOC(h2, float, (size_t)rows * PE_H2);
-    ALLOC(o, float, (size_t)rows * Cout);
-    ALLOC(arg2, int, (size_t)groups * Cout);
-    if (!c.dry) {
-        TRY(launch_bn_fold(p.fbn.affine.g, p.fbn.affine.b, p.fbn.mean, p.fbn.var, p.f0.b, PE_H1, sc1, sh1, c.st));
-        TRY(launch_bn_fold(p.sbn.affine.g, p.sbn.affine.b, p.sbn.mean, p.sbn.var, p.s0.b, PE_H2, sc2, sh2, c.st));
-    }
-    {   // first_mlp: Linear(C,128) + BN + ReLU + Linear(128,256)
-        GemmArgs a;
-        a.A = F; a.sam = Cin; a.C = h1; a.ldc = PE_H1; a.M = rows;
-        a.colscale = sc1; a.bias = sh1; a.act = ACT_RELU;
-        TRY(gemm_w(c, a, p.f0, Cin));
-        TRY(linear(c, h1, PE_H1, rows, p.f3, f, PE_H2));
-    }
-    if (!c.dry) TRY(launch_masked_maxpool(f, mask, groups, n, PE_H2, pooled, arg1, c.st));
-    {   // second_mlp on cat[feat, pooled]: the pooled half of the weight acts once per polyline
-        Lin wb = slice(p.s0, 0, PE_H2, PE_H2, PE_H2, false);
-        TRY(linear_ld(c, pooled, PE_H2, groups, wb, 2 * PE_H2, gp, PE_H2));
-        GemmArgs a;
-        a.A = f; a.sam = PE_H2; a.C = h2; a.ldc = PE_H2; a.M = rows;
-        a.pre = gp; a.ldpre = PE_H2; a.pre_div = n; a.colscale = sc2; a.bias = sh2; a.act = ACT_RELU;
-        TRY(gemm_w(c, a, slice(p.s0, 0, PE_H2, 0, PE_H2, false), 2 * PE_H2));
-        TRY(linear(c, h2, PE_H2, rows, p.s3, o, Cout));
-    }
-    if (!c.dry) TRY(launch_masked_maxpool(o, mask, groups, n, Cout, out, arg2, c.st));
-    return 0;
-}
-
-// nn.MultiheadAttention self-attention over rows laid out (B, S, D) contiguous
-static int mha_self(Ctx& c, const float* x, int B, int S, int D, int H, const MHAP& p, const uint8_t* kpm, float* out,
-                    const float* res) {
-    const int rows = B * S;
-    ALLOC(qkv, float, (size_t)rows * 3 * D);
-    ALLOC(att, float, (size_t)rows * D);
-    TRY(linear(c, x, D, rows, p.in, qkv, 3 * D));
-    if (!c.dry) {
-        AttnArgs a;
-        a.q = qkv; a.k = qkv + D; a.v = qkv + 2 * D; a.o = att;
-        a.ldq = a.ldk = a.ldv = 3 * D; a.ldo = D;
-        a.B = B; a.H = H; a.Sq = S; a.Sk = S; a.hd = D / H;
-        a.q_outer = S; a.k_outer = S;
-        a.kpm = kpm; a.kpm_div = 1; a.scale = 1.f / sqrtf((float)(D / H));
-        TRY(launch_attention(a, c.st));
-    }
-    TRY(linear(c, att, D, rows, p.out, out, D, ACT_NONE, res, D, 1));
-    return 0;
-}
-
-}  // namespace rift
-
-using namespace rift;
 
 // =====================================================================================
 // parameter views
@@ -217,14 +42,14 @@ struct Binder {
         return v;
     }
     Lin lin(const std::string& p, int N, int K, bool bias = true, const char* wname = ".weight", const char* bname = ".bias") {
-        Lin l; l.N = N; l.K = K;
+        Lin l; l.N = N; l.K = K; l.ldw = K;
         if (auto r = find(p + wname)) {
             if (r->numel != (long long)N * K) { set_last_error("shape mismatch for " + p + wname); err = -1; }
             l.W = e->params + r->offset; l.train = r->trainable && e->grads;
             l.dW = l.train ? e->grads + r->offset : nullptr;
             if (N >= 16 && K >= 32) {          // candidate for the tcgen05 path: gets pre-split bf16 planes
                 TcWeight w;
-                w.src = l.W; w.ld_src = K; w.N = N; w.K = K; w.Kp = (K + 63) / 64 * 64; w.trainable = r->trainable;
+                w.src = l.W; w.ld_src = K; w.N = N; w.K = K; w.Kp = tc_pitch(K); w.trainable = r->trainable;
                 l.tc = (int)e->tcw.size();
                 e->tcw.push_back(w);
             }
@@ -403,12 +228,103 @@ int rift_b200_engine::build_model() {
     m.hidden0 = b.lin("hidden_proj.0", D, D); m.hidden2 = b.lin("hidden_proj.2", D, D);
     m.ref_free = b.mlp("ref_free_decoder", D, 2 * D, 4 * T);
     if (b.err) return b.err;
-    m.any_trainable_outside_pi_head = false;
+    m.full = false;
     for (auto& kv : table)
         if (kv.second.trainable && kv.first.rfind("planning_decoder.pi_head.", 0) != 0 && kv.first.rfind("value_net.", 0) != 0)
-            m.any_trainable_outside_pi_head = true;
+            m.full = true;
+    if (!grads) m.full = false;
     return 0;
 }
+
+// =====================================================================================
+// forward building blocks
+// =====================================================================================
+namespace rift {
+
+// MLPLayer: Linear -> LayerNorm -> ReLU -> Linear  (layers/mlp_layer.py:4-16); Y fp32 into dst (pitch ldy)
+static int mlp_layer(Ctx& c, Act& X, const MLPLayerP& p, float* dst, long long ldy, MlpTape* tape) {
+    Act h, a;
+    LNSave ln;
+    TRY(linear_new(c, X, p.l0, Epi(), W_F, &h));
+    // `a` feeds l3; the backward of the fused LN+ReLU reads it in fp32
+    TRY(layernorm_new(c, h.f, X.rows, p.n, 1, want_in(c, X.rows, {&p.l3}, tape != nullptr), &a, tape ? &ln : nullptr));
+    TRY(linear_into(c, a, p.l3, Epi(), dst, ldy));
+    if (tape) { tape->x = X; tape->h = h; tape->ln = ln; tape->a = a; }
+    return 0;
+}
+
+// FourierEmbedding (layers/fourier_embedding.py:45-55): out = to_out(sum_i mlp_i(feat_i)) [+ res]
+static int fourier(Ctx& c, const float* x, int rows, const FourierP& p, float* out, const float* res, FourierTape* tape) {
+    const int D = p.out_l.N;
+    ALLOC(acc, float, (size_t)rows * D);
+    if (tape) { tape->x = x; tape->rows = rows; tape->dims.clear(); tape->acc = acc; }
+    for (int i = 0; i < p.d; ++i) {
+        Act feat, h, hn;
+        LNSave ln;
+        const MLPLayerP& ml = p.mlps[i];
+        TRY(new_act(c, rows, FIN, want_in(c, rows, {&ml.l0}), &feat));
+        if (feat.f) feat.ld = FIN;
+        if (!c.dry) TRY(launch_fourier_features(x, rows, p.d, i, p.freqs.p, NFREQ, feat.f, FIN, c.st, feat.p));
+        TRY(linear_new(c, feat, ml.l0, Epi(), W_F, &h));
+        TRY(layernorm_new(c, h.f, rows, ml.n, 1, want_in(c, rows, {&ml.l3}, tape != nullptr), &hn, tape ? &ln : nullptr));
+        Epi e;
+        if (i > 0) { e.res = acc; e.ldres = D; }
+        TRY(linear_into(c, hn, ml.l3, e, acc, D));
+        if (tape) tape->dims.push_back(FourierTape::Dim{feat, h, ln, hn});
+    }
+    Act on;
+    LNSave lno;
+    TRY(layernorm_new(c, acc, rows, p.out_n, 1, want_in(c, rows, {&p.out_l}, tape != nullptr), &on, tape ? &lno : nullptr));
+    Epi e;
+    e.res = res; e.ldres = D;
+    TRY(linear_into(c, on, p.out_l, e, out, D));
+    if (tape) { tape->ln_o = lno; tape->on = on; }
+    return 0;
+}
+
+// PointsEncoder (layers/embedding.py:271-296) over `groups` polylines of `n` points, C_in channels
+static int points_encoder(Ctx& c, Act& F, int groups, int n, const uint8_t* mask, const PointsEncP& p, Act* out, int out_want,
+                          PointsTape* tape) {
+    const int rows = groups * n, Cin = F.C, Cout = p.s3.N;
+    ALLOC(sc1, float, PE_H1); ALLOC(sh1, float, PE_H1); ALLOC(sc2, float, PE_H2); ALLOC(sh2, float, PE_H2);
+    ALLOC(arg1, int, (size_t)groups * PE_H2);
+    ALLOC(arg2, int, (size_t)groups * Cout);
+    float *h1pre = nullptr, *h2pre = nullptr;
+    if (tape) {
+        h1pre = c.alloc<float>((size_t)rows * PE_H1); h2pre = c.alloc<float>((size_t)rows * PE_H2);
+        if (!h1pre || !h2pre) { set_last_error("workspace too small"); return -1; }
+    }
+    if (!c.dry) {
+        TRY(launch_bn_fold(p.fbn.affine.g, p.fbn.affine.b, p.fbn.mean, p.fbn.var, p.f0.b, PE_H1, sc1, sh1, c.st));
+        TRY(launch_bn_fold(p.sbn.affine.g, p.sbn.affine.b, p.sbn.mean, p.sbn.var, p.s0.b, PE_H2, sc2, sh2, c.st));
+    }
+    const Lin s0a = slice(p.s0, 0, PE_H2, 0, PE_H2, false), s0b = slice(p.s0, 0, PE_H2, PE_H2, PE_H2, false);
+    Act h1, f, pooled, gp, h2, o;
+    {   // first_mlp: Linear(C,128) + BN + ReLU + Linear(128,256)
+        Epi e; e.colscale = sc1; e.shift = sh1; e.act = ACT_RELU; e.preact = h1pre;
+        TRY(linear_new(c, F, p.f0, e, want_in(c, rows, {&p.f3}, tape != nullptr), &h1));
+        TRY(linear_new(c, h1, p.f3, Epi(), want_in(c, rows, {&s0a}, true), &f));       // fp32: pooled over points
+    }
+    TRY(new_act(c, groups, PE_H2, want_in(c, groups, {&s0b}), &pooled));
+    if (!c.dry) TRY(launch_masked_maxpool(f.f, mask, groups, n, PE_H2, pooled.f, arg1, c.st, pooled.p));
+    {   // second_mlp on cat[feat, pooled]: the pooled half of the weight acts once per polyline
+        TRY(linear_new(c, pooled, s0b, Epi(), W_F, &gp));
+        Epi e; e.pre = gp.f; e.ldpre = PE_H2; e.pre_div = n; e.colscale = sc2; e.shift = sh2; e.act = ACT_RELU; e.preact = h2pre;
+        TRY(linear_new(c, f, s0a, e, want_in(c, rows, {&p.s3}, tape != nullptr), &h2));
+        TRY(linear_new(c, h2, p.s3, Epi(), W_F, &o));
+    }
+    TRY(new_act(c, groups, Cout, out_want, out));
+    if (!c.dry) TRY(launch_masked_maxpool(o.f, mask, groups, n, Cout, out->f, arg2, c.st, out->p));
+    if (tape) {
+        tape->F = F; tape->groups = groups; tape->n = n; tape->Cin = Cin; tape->mask = mask;
+        tape->sc1 = sc1; tape->sh1 = sh1; tape->sc2 = sc2; tape->sh2 = sh2;
+        tape->h1pre = h1pre; tape->h1 = h1; tape->f = f; tape->pooled = pooled; tape->arg1 = arg1; tape->gp = gp.f;
+        tape->h2pre = h2pre; tape->h2 = h2; tape->o = o; tape->arg2 = arg2;
+    }
+    return 0;
+}
+
+}  // namespace rift
 
 // =====================================================================================
 // forward
@@ -420,10 +336,18 @@ int rift_b200_engine::forward(const rift_b200_batch& bt, const rift_b200_outputs
     RIFT_REQUIRE(bs > 0 && A > 0 && R > 0 && Mp >= 0, "forward: empty batch");
     RIFT_REQUIRE(bt.agent_T >= Th, "forward: agent tensors shorter than history_steps");
     RIFT_REQUIRE(D % H == 0 && D / H == 32, "forward: encoder head_dim must be 32");
-    pi_tape.valid = false;
     if (!wcache) c.simt = true;            // no pre-split planes bound: exact-fp32 SIMT GEMMs only
     c.tcw = &tcw;
+    c.full = c.save && m.full;
+    const bool full = c.full;
     if (!c.dry && !c.simt) TRY(refresh_weights(c.st));
+    Tape& tp = tape;
+    if (!c.dry) {
+        tp = Tape();
+        tp.bs = bs; tp.A = A; tp.Mp = Mp; tp.P = P; tp.R = R; tp.Pr = Pr; tp.S = S;
+    }
+    Tape scratch_tape;                      // the sizing pass records into a throw-away tape
+    Tape& T_ = c.dry ? scratch_tape : tp;
 
     // ---------------- masks
     ALLOC(agent_any, uint8_t, (size_t)bs * A);
@@ -436,114 +360,134 @@ int rift_b200_engine::forward(const rift_b200_batch& bt, const rift_b200_outputs
         if (out.r_padding_mask)
             RIFT_CUDA_OK(cudaMemcpyAsync(out.r_padding_mask, r_pad, (size_t)bs * R, cudaMemcpyDeviceToDevice, c.st));
     }
+    T_.agent_any = agent_any; T_.key_pad = key_pad; T_.r_pad = r_pad;
     ALLOC(tokens, float, (size_t)bs * S * D);
 
     // ---------------- AgentEncoder (modules/agent_encoder.py:54-94)
     {
+        NatTape& nt = T_.nat;
         const int NA = bs * A;
         const int Ls[3] = {Th - 1, (Th - 1 + 2 - 3) / 2 + 1, ((Th - 1 + 2 - 3) / 2 + 1 + 2 - 3) / 2 + 1};
+        nt.NA = NA; nt.Ls[0] = Ls[0]; nt.Ls[1] = Ls[1]; nt.Ls[2] = Ls[2];
+        nt.blocks.clear();
         ALLOC(F0, float, (size_t)NA * Ls[0] * 9);
-        ALLOC(col0, float, (size_t)NA * Ls[0] * 27);
+        Act col0;
+        TRY(new_act(c, NA * Ls[0], 27, W_F, &col0));
         if (!c.dry) {
             TRY(launch_agent_features(bt.agent_position, bt.agent_heading, bt.agent_velocity, bt.agent_shape,
                                       bt.agent_valid_mask, NA, Th, bt.agent_T, F0, c.st));
-            TRY(launch_im2col_k3(F0, NA, Ls[0], 9, 1, col0, c.st));
+            TRY(launch_im2col_k3(F0, NA, Ls[0], 9, 1, col0.f, c.st));
         }
-        float* x = c.alloc<float>((size_t)NA * Ls[0] * m.hist.embed.N);
-        if (!x) { set_last_error("workspace too small"); return -1; }
-        TRY(linear(c, col0, 27, NA * Ls[0], m.hist.embed, x, m.hist.embed.N));
+        nt.col0 = col0;
+        Act xa;
+        TRY(linear_new(c, col0, m.hist.embed, Epi(), W_F, &xa));
+        float* x = xa.f;
         float* lat[3] = {nullptr, nullptr, nullptr};
         for (int i = 0; i < 3; ++i) {
             const NatLevelP& lv = m.hist.levels[i];
             const int d = lv.dim, L = Ls[i], rows = NA * L;
             for (const NatBlockP& nb : lv.blocks) {
-                ALLOC(t1, float, (size_t)rows * d);
+                NatBlockTape bt_;
+                bt_.x = x;
                 ALLOC(qkv, float, (size_t)rows * 3 * d);
-                ALLOC(att, float, (size_t)rows * d);
                 ALLOC(x1, float, (size_t)rows * d);
-                ALLOC(t2, float, (size_t)rows * d);
-                ALLOC(hm, float, (size_t)rows * 3 * d);
                 ALLOC(x2, float, (size_t)rows * d);
-                TRY(layernorm(c, x, rows, nb.n1, t1));
-                TRY(linear(c, t1, d, rows, nb.qkv, qkv, 3 * d));
-                if (!c.dry) TRY(launch_nat_attention(qkv, NA, L, lv.heads, d / lv.heads, lv.ksize, nb.rpb.p, att, c.st));
-                TRY(linear(c, att, d, rows, nb.proj, x1, d, ACT_NONE, x, d, 1));
-                TRY(layernorm(c, x1, rows, nb.n2, t2));
-                TRY(linear(c, t2, d, rows, nb.fc1, hm, 3 * d, ACT_GELU));
-                TRY(linear(c, hm, 3 * d, rows, nb.fc2, x2, d, ACT_NONE, x1, d, 1));
+                float* hpre = nullptr;
+                if (full) { hpre = c.alloc<float>((size_t)rows * 3 * d); if (!hpre) { set_last_error("workspace too small"); return -1; } }
+                Act t1, att, t2, hm;
+                TRY(layernorm_new(c, x, rows, nb.n1, 0, want_in(c, rows, {&nb.qkv}), &t1, full ? &bt_.ln1 : nullptr));
+                TRY(linear_into(c, t1, nb.qkv, Epi(), qkv, 3 * d));
+                TRY(new_act(c, rows, d, want_in(c, rows, {&nb.proj}), &att));
+                if (!c.dry) TRY(launch_nat_attention(qkv, NA, L, lv.heads, d / lv.heads, lv.ksize, nb.rpb.p, att.f, c.st, att.p));
+                { Epi e; e.res = x; e.ldres = d; TRY(linear_into(c, att, nb.proj, e, x1, d)); }
+                TRY(layernorm_new(c, x1, rows, nb.n2, 0, want_in(c, rows, {&nb.fc1}), &t2, full ? &bt_.ln2 : nullptr));
+                { Epi e; e.act = ACT_GELU; e.preact = hpre; TRY(linear_new(c, t2, nb.fc1, e, want_in(c, rows, {&nb.fc2}), &hm)); }
+                { Epi e; e.res = x1; e.ldres = d; TRY(linear_into(c, hm, nb.fc2, e, x2, d)); }
+                bt_.t1 = t1; bt_.qkv = qkv; bt_.att = att; bt_.x1 = x1; bt_.t2 = t2; bt_.hpre = hpre; bt_.hm = hm;
+                nt.blocks.push_back(bt_);
                 x = x2;
             }
+            nt.xlev[i] = x;
             // per-level output -> LayerNorm -> lateral Conv1d(k3) to D channels
-            ALLOC(o, float, (size_t)rows * d);
-            ALLOC(colL, float, (size_t)rows * 3 * d);
+            Act o, colL;
+            TRY(layernorm_new(c, x, rows, m.hist.norms[i], 0, W_F, &o, full ? &nt.ln_lev[i] : nullptr));
+            TRY(new_act(c, rows, 3 * d, want_in(c, rows, {&m.hist.lateral[i]}), &colL));
+            if (!c.dry) TRY(launch_im2col_k3(o.f, NA, L, d, 1, colL.f, c.st, colL.p));
             lat[i] = c.alloc<float>((size_t)rows * D);
             if (!lat[i]) { set_last_error("workspace too small"); return -1; }
-            TRY(layernorm(c, x, rows, m.hist.norms[i], o));
-            if (!c.dry) TRY(launch_im2col_k3(o, NA, L, d, 1, colL, c.st));
-            TRY(linear(c, colL, 3 * d, rows, m.hist.lateral[i], lat[i], D));
+            TRY(linear_into(c, colL, m.hist.lateral[i], Epi(), lat[i], D));
+            nt.colL[i] = colL;
             if (lv.has_down) {
                 const int Ln = Ls[i + 1];
-                ALLOC(colD, float, (size_t)NA * Ln * 3 * d);
+                Act colD, xdn;
                 ALLOC(xd, float, (size_t)NA * Ln * 2 * d);
-                ALLOC(xn, float, (size_t)NA * Ln * 2 * d);
-                if (!c.dry) TRY(launch_im2col_k3(x, NA, L, d, 2, colD, c.st));
-                TRY(linear(c, colD, 3 * d, NA * Ln, lv.down, xd, 2 * d));
-                TRY(layernorm(c, xd, NA * Ln, lv.down_n, xn));
-                x = xn;
+                TRY(new_act(c, NA * Ln, 3 * d, want_in(c, NA * Ln, {&lv.down}), &colD));
+                if (!c.dry) TRY(launch_im2col_k3(x, NA, L, d, 2, colD.f, c.st, colD.p));
+                TRY(linear_into(c, colD, lv.down, Epi(), xd, 2 * d));
+                TRY(layernorm_new(c, xd, NA * Ln, lv.down_n, 0, W_F, &xdn, full ? &nt.ln_down[i] : nullptr));
+                nt.colD[i] = colD; nt.xd[i] = xd;
+                x = xdn.f;
             }
         }
         if (!c.dry) {
             TRY(launch_fpn_upsample_add(lat[1], lat[2], NA, Ls[1], Ls[2], D, c.st));
             TRY(launch_fpn_upsample_add(lat[0], lat[1], NA, Ls[0], Ls[1], D, c.st));
         }
-        ALLOC(colF, float, (size_t)NA * 3 * D);
-        ALLOC(x_hist, float, (size_t)NA * D);
-        if (!c.dry) TRY(launch_im2col_k3_last(lat[0], NA, Ls[0], D, colF, c.st));
-        TRY(linear(c, colF, 3 * D, NA, m.hist.fpn, x_hist, D));
+        Act colF, x_hist;
+        TRY(new_act(c, NA, 3 * D, want_in(c, NA, {&m.hist.fpn}), &colF));
+        if (!c.dry) TRY(launch_im2col_k3_last(lat[0], NA, Ls[0], D, colF.f, c.st, colF.p));
+        TRY(linear_new(c, colF, m.hist.fpn, Epi(), W_F, &x_hist));
+        nt.colF = colF;
 
         // StateAttentionEncoder (modules/agent_encoder.py:97-140), 4 heads hard-coded (:104)
-        const int nt = cfg.state_channel, eh = 4;
-        ALLOC(toks, float, (size_t)bs * nt * D);
-        ALLOC(kv, float, (size_t)bs * nt * 2 * D);
+        EgoTape& et = T_.ego;
+        const int ntok = cfg.state_channel, eh = 4;
+        const Lin in_q = slice(m.ego.attn.in, 0, D, 0, D, true), in_kv = slice(m.ego.attn.in, D, 2 * D, 0, D, true);
+        Act toks, eo, x_ego;
+        ALLOC(kv, float, (size_t)bs * ntok * 2 * D);
         ALLOC(qv, float, (size_t)D);
-        ALLOC(eo, float, (size_t)bs * D);
-        ALLOC(x_ego, float, (size_t)bs * D);
+        ALLOC(elsp, float, (size_t)bs * eh);
+        TRY(new_act(c, bs * ntok, D, W_F, &toks));
         if (!c.dry) {
             const float* w[8]; const float* bb[8];
-            for (int i = 0; i < nt; ++i) { w[i] = m.ego.lin[i].W; bb[i] = m.ego.lin[i].b; }
-            TRY(launch_state_tokens(bt.current_state, bt.cs_stride, bs, nt, D, w, bb, m.ego.pos_embed.p, toks, c.st));
+            for (int i = 0; i < ntok; ++i) { w[i] = m.ego.lin[i].W; bb[i] = m.ego.lin[i].b; }
+            TRY(launch_state_tokens(bt.current_state, bt.cs_stride, bs, ntok, D, w, bb, m.ego.pos_embed.p, toks.f, c.st));
         }
-        TRY(linear(c, m.ego.query.p, D, 1, slice(m.ego.attn.in, 0, D, 0, D, true), qv, D));
-        TRY(linear(c, toks, D, bs * nt, slice(m.ego.attn.in, D, 2 * D, 0, D, true), kv, 2 * D));
+        Act qa = act_f32(const_cast<float*>(m.ego.query.p), D, 1, D);
+        TRY(linear_into(c, qa, in_q, Epi(), qv, D));
+        TRY(linear_into(c, toks, in_kv, Epi(), kv, 2 * D));
+        TRY(new_act(c, bs, D, want_in(c, bs, {&m.ego.attn.out}), &eo));
         if (!c.dry) {
             AttnArgs a;
-            a.q = qv; a.k = kv; a.v = kv + D; a.o = eo;
+            a.q = qv; a.k = kv; a.v = kv + D; a.o = eo.f; a.o_planes = eo.p;
             a.ldq = D; a.ldk = a.ldv = 2 * D; a.ldo = D;
-            a.B = bs; a.H = eh; a.Sq = 1; a.Sk = nt; a.hd = D / eh;
+            a.B = bs; a.H = eh; a.Sq = 1; a.Sk = ntok; a.hd = D / eh;
             a.q_outer = 0; a.q_seq = 0;                    // one learned query shared by every sample
-            a.k_outer = nt;
+            a.k_outer = ntok;
             a.o_custom = 1; a.o_outer = 1; a.o_seq = 0;    // ... but one output row per sample
             a.scale = 1.f / sqrtf((float)(D / eh));
+            a.lse = full ? elsp : nullptr;
             TRY(launch_attention(a, c.st));
         }
-        TRY(linear(c, eo, D, bs, m.ego.attn.out, x_ego, D));
+        TRY(linear_new(c, eo, m.ego.attn.out, Epi(), W_F, &x_ego));
+        et.toks = toks.f; et.toks_a = toks; et.kv = kv; et.qv = qv; et.lse = elsp; et.eo = eo;
         if (!c.dry)
-            TRY(launch_agent_assemble(x_hist, x_ego, agent_any, bt.agent_category, m.agent_type_emb.p, bs, A, S, D, tokens, c.st));
+            TRY(launch_agent_assemble(x_hist.f, x_ego.f, agent_any, bt.agent_category, m.agent_type_emb.p, bs, A, S, D, tokens, c.st));
     }
 
     // ---------------- MapEncoder (modules/map_encoder.py:31-93)
     if (Mp > 0) {
         const int NP = bs * Mp;
-        ALLOC(Fm, float, (size_t)NP * P * 10);
-        ALLOC(x_poly, float, (size_t)NP * D);
+        Act Fm, x_poly;
+        TRY(new_act(c, NP * P, 10, W_F, &Fm));
         ALLOC(x_speed, float, (size_t)NP * D);
         if (!c.dry)
             TRY(launch_map_features(bt.map_point_position, bt.map_point_vector, bt.map_point_orientation, bt.map_polygon_center,
-                                    NP, P, Fm, c.st));
-        TRY(points_encoder(c, Fm, NP, P, 10, bt.map_valid_mask, m.poly_enc, x_poly));
-        TRY(fourier(c, bt.map_polygon_speed_limit, NP, m.speed_emb, x_speed, nullptr));
+                                    NP, P, Fm.f, c.st));
+        TRY(points_encoder(c, Fm, NP, P, bt.map_valid_mask, m.poly_enc, &x_poly, W_F, full ? &T_.poly : nullptr));
+        TRY(fourier(c, bt.map_polygon_speed_limit, NP, m.speed_emb, x_speed, nullptr, full ? &T_.speed : nullptr));
         if (!c.dry)
-            TRY(launch_map_assemble(x_poly, x_speed, bt.map_polygon_type, bt.map_polygon_on_route, bt.map_polygon_tl_status,
+            TRY(launch_map_assemble(x_poly.f, x_speed, bt.map_polygon_type, bt.map_polygon_on_route, bt.map_polygon_tl_status,
                                     bt.map_polygon_has_speed_limit, m.map_type_emb.p, m.map_route_emb.p, m.map_tl_emb.p,
                                     m.map_unknown_emb.p, bs, Mp, A, S, D, tokens, c.st));
     }
@@ -554,35 +498,65 @@ int rift_b200_engine::forward(const rift_b200_batch& bt, const rift_b200_outputs
     if (!X) { set_last_error("workspace too small"); return -1; }
     if (!c.dry)
         TRY(launch_token_pos(bt.agent_position, bt.agent_heading, bt.map_polygon_center, bs, A, Th, bt.agent_T, Mp, pos, c.st));
-    TRY(fourier(c, pos, bs * S, m.pos_emb, X, tokens));
+    T_.pos = pos;
+    TRY(fourier(c, pos, bs * S, m.pos_emb, X, tokens, full ? &T_.pos_emb : nullptr));
     const int rowsE = bs * S;
+    const float att_scale = 1.f / sqrtf((float)(D / H));
+    T_.enc.clear();
     for (const EncBlockP& eb : m.enc) {
-        ALLOC(t1, float, (size_t)rowsE * D);
+        EncBlockTape et;
+        et.X = X;
+        ALLOC(qkv, float, (size_t)rowsE * 3 * D);
         ALLOC(X1, float, (size_t)rowsE * D);
-        ALLOC(t2, float, (size_t)rowsE * D);
-        ALLOC(hm, float, (size_t)rowsE * 4 * D);
         ALLOC(X2, float, (size_t)rowsE * D);
-        TRY(layernorm(c, X, rowsE, eb.n1, t1));
-        TRY(mha_self(c, t1, bs, S, D, H, eb.attn, key_pad, X1, X));
-        TRY(layernorm(c, X1, rowsE, eb.n2, t2));
-        TRY(linear(c, t2, D, rowsE, eb.fc1, hm, 4 * D, ACT_GELU));
-        TRY(linear(c, hm, 4 * D, rowsE, eb.fc2, X2, D, ACT_NONE, X1, D, 1));
+        float *hpre = nullptr, *lse = nullptr;
+        if (full) {
+            hpre = c.alloc<float>((size_t)rowsE * 4 * D); lse = c.alloc<float>((size_t)bs * H * S);
+            if (!hpre || !lse) { set_last_error("workspace too small"); return -1; }
+        }
+        Act t1, att, t2, hm;
+        TRY(layernorm_new(c, X, rowsE, eb.n1, 0, want_in(c, rowsE, {&eb.attn.in}), &t1, full ? &et.ln1 : nullptr));
+        TRY(linear_into(c, t1, eb.attn.in, Epi(), qkv, 3 * D));
+        TRY(new_act(c, rowsE, D, want_in(c, rowsE, {&eb.attn.out}), &att));
+        if (!c.dry) {
+            AttnArgs a;
+            a.q = qkv; a.k = qkv + D; a.v = qkv + 2 * D; a.o = att.f; a.o_planes = att.p;
+            a.ldq = a.ldk = a.ldv = 3 * D; a.ldo = D;
+            a.B = bs; a.H = H; a.Sq = S; a.Sk = S; a.hd = D / H;
+            a.q_outer = S; a.k_outer = S;
+            a.kpm = key_pad; a.kpm_div = 1; a.scale = att_scale; a.lse = lse;
+            TRY(launch_attention(a, c.st));
+        }
+        { Epi e; e.res = X; e.ldres = D; TRY(linear_into(c, att, eb.attn.out, e, X1, D)); }
+        TRY(layernorm_new(c, X1, rowsE, eb.n2, 0, want_in(c, rowsE, {&eb.fc1}), &t2, full ? &et.ln2 : nullptr));
+        { Epi e; e.act = ACT_GELU; e.preact = hpre; TRY(linear_new(c, t2, eb.fc1, e, want_in(c, rowsE, {&eb.fc2}), &hm)); }
+        { Epi e; e.res = X1; e.ldres = D; TRY(linear_into(c, hm, eb.fc2, e, X2, D)); }
+        et.t1 = t1; et.qkv = qkv; et.lse = lse; et.att = att; et.X1 = X1; et.t2 = t2; et.hpre = hpre; et.hm = hm;
+        T_.enc.push_back(et);
         X = X2;
     }
-    ALLOC(Xn, float, (size_t)rowsE * D);
-    TRY(layernorm(c, X, rowsE, m.final_norm, Xn));
+    T_.Xlast = X;
+    Act Xn;
+    {
+        // consumers: cross-attention K/V projections (every decoder layer), cat_x_proj, hidden / ref-free heads
+        const Lin kv0 = slice(m.dec.empty() ? m.cat_x_proj : m.dec[0].cross.in, D, 2 * D, 0, D, true);
+        TRY(layernorm_new(c, X, rowsE, m.final_norm, 0, want_in(c, rowsE, {&kv0}, true), &Xn, full ? &T_.ln_final : nullptr));
+    }
+    T_.Xn = Xn;
+    Act xego_rows = act_f32(Xn.f, (long long)S * D, bs, D);       // x[:, 0]
 
     // ---------------- AgentPredictor (modules/agent_predictor.py:17-29) — only when asked for
     if (out.prediction && A > 1) {
         const int rows = bs * (A - 1);
-        ALLOC(xa, float, (size_t)rows * D);
+        Act xa;
+        TRY(new_act(c, rows, D, W_F, &xa));
         ALLOC(pl, float, (size_t)rows * 2 * T);
         ALLOC(py, float, (size_t)rows * 2 * T);
         ALLOC(pv, float, (size_t)rows * 2 * T);
-        if (!c.dry) TRY(launch_gather_rows(Xn, (long long)S * D, bs, 1, A - 1, D, xa, c.st));
-        TRY(mlp_layer(c, xa, D, rows, m.pred_loc, pl, 2 * T));
-        TRY(mlp_layer(c, xa, D, rows, m.pred_yaw, py, 2 * T));
-        TRY(mlp_layer(c, xa, D, rows, m.pred_vel, pv, 2 * T));
+        if (!c.dry) TRY(launch_gather_rows(Xn.f, (long long)S * D, bs, 1, A - 1, D, xa.f, c.st));
+        TRY(mlp_layer(c, xa, m.pred_loc, pl, 2 * T, nullptr));
+        TRY(mlp_layer(c, xa, m.pred_yaw, py, 2 * T, nullptr));
+        TRY(mlp_layer(c, xa, m.pred_vel, pv, 2 * T, nullptr));
         if (!c.dry) TRY(launch_interleave_heads(pl, py, pv, rows, T, out.prediction, c.st));
     }
 
@@ -590,34 +564,46 @@ int rift_b200_engine::forward(const rift_b200_batch& bt, const rift_b200_outputs
     const int NR = bs * R, rowsQ = bs * R * Mo;
     float* q = nullptr;
     {
-        ALLOC(Fr, float, (size_t)NR * Pr * 6);
+        Act Fr, r_enc, r_emb, u, v;
+        const Lin qa = slice(m.q_proj, 0, D, 0, D, false), qb = slice(m.q_proj, 0, D, D, D, true);
+        TRY(new_act(c, NR * Pr, 6, W_F, &Fr));
         ALLOC(rpos, float, (size_t)NR * 3);
-        ALLOC(r_enc, float, (size_t)NR * D);
-        ALLOC(r_emb, float, (size_t)NR * D);
-        ALLOC(u, float, (size_t)NR * D);
-        ALLOC(v, float, (size_t)Mo * D);
+        if (!c.dry) TRY(launch_ref_features(bt.ref_position, bt.ref_vector, bt.ref_orientation, NR, Pr, Fr.f, rpos, c.st));
+        T_.rpos = rpos;
+        TRY(points_encoder(c, Fr, NR, Pr, bt.ref_valid_mask, m.r_enc, &r_enc, W_F, full ? &T_.renc : nullptr));
+        TRY(new_act(c, NR, D, W_F, &r_emb));
+        TRY(fourier(c, rpos, NR, m.r_pos_emb, r_emb.f, r_enc.f, full ? &T_.rpos_emb : nullptr));
+        T_.r_emb = r_emb;
+        // q = q_proj(cat[r_emb (per line), m_emb (per mode)]) split into its two column blocks
+        TRY(linear_new(c, r_emb, qa, Epi(), W_F, &u));
+        Act me = act_f32(const_cast<float*>(m.m_emb.p), D, Mo, D);
+        TRY(linear_new(c, me, qb, Epi(), W_F, &v));
         q = c.alloc<float>((size_t)rowsQ * D);
         if (!q) { set_last_error("workspace too small"); return -1; }
-        if (!c.dry) TRY(launch_ref_features(bt.ref_position, bt.ref_vector, bt.ref_orientation, NR, Pr, Fr, rpos, c.st));
-        TRY(points_encoder(c, Fr, NR, Pr, 6, bt.ref_valid_mask, m.r_enc, r_enc));
-        TRY(fourier(c, rpos, NR, m.r_pos_emb, r_emb, r_enc));
-        // q = q_proj(cat[r_emb (per line), m_emb (per mode)]) split into its two column blocks
-        TRY(linear_ld(c, r_emb, D, NR, slice(m.q_proj, 0, D, 0, D, false), 2 * D, u, D));
-        TRY(linear_ld(c, m.m_emb.p, D, Mo, slice(m.q_proj, 0, D, D, D, true), 2 * D, v, D));
-        if (!c.dry) TRY(launch_query_init(u, v, rowsQ, Mo, D, q, c.st));
+        if (!c.dry) TRY(launch_query_init(u.f, v.f, rowsQ, Mo, D, q, c.st));
     }
-    const float att_scale = 1.f / sqrtf((float)(D / H));
+    T_.dec.clear();
     for (const DecBlockP& db : m.dec) {
+        DecBlockTape dt;
+        dt.q = q;
+        const Lin m2m_qk = slice(db.m2m.in, 0, 2 * D, 0, D, true), m2m_v = slice(db.m2m.in, 2 * D, D, 0, D, true);
+        const Lin cr_q = slice(db.cross.in, 0, D, 0, D, true), cr_kv = slice(db.cross.in, D, 2 * D, 0, D, true);
+        float *lse1 = nullptr, *lse2 = nullptr, *lse3 = nullptr;
+        if (full) {
+            lse1 = c.alloc<float>((size_t)bs * Mo * H * R); lse2 = c.alloc<float>((size_t)NR * H * Mo);
+            lse3 = c.alloc<float>((size_t)bs * H * R * Mo);
+            if (!lse1 || !lse2 || !lse3) { set_last_error("workspace too small"); return -1; }
+        }
         // (i) r2r self-attention over reference lines, per mode
-        ALLOC(t1, float, (size_t)rowsQ * D);
         ALLOC(qkv1, float, (size_t)rowsQ * 3 * D);
-        ALLOC(a1, float, (size_t)rowsQ * D);
         ALLOC(q1, float, (size_t)rowsQ * D);
-        TRY(layernorm(c, q, rowsQ, db.n1, t1));
-        TRY(linear(c, t1, D, rowsQ, db.r2r.in, qkv1, 3 * D));
+        Act t1, a1;
+        TRY(layernorm_new(c, q, rowsQ, db.n1, 0, want_in(c, rowsQ, {&db.r2r.in}), &t1, full ? &dt.ln1 : nullptr));
+        TRY(linear_into(c, t1, db.r2r.in, Epi(), qkv1, 3 * D));
+        TRY(new_act(c, rowsQ, D, want_in(c, rowsQ, {&db.r2r.out}), &a1));
         if (!c.dry) {
             AttnArgs a;
-            a.q = qkv1; a.k = qkv1 + D; a.v = qkv1 + 2 * D; a.o = a1;
+            a.q = qkv1; a.k = qkv1 + D; a.v = qkv1 + 2 * D; a.o = a1.f; a.o_planes = a1.p;
             a.ldq = a.ldk = a.ldv = 3 * D; a.ldo = D;
             a.B = bs * Mo; a.H = H; a.Sq = R; a.Sk = R; a.hd = D / H;
             a.q_inner_n = Mo; a.q_outer = (long long)R * Mo; a.q_inner = 1; a.q_seq = Mo;
@@ -625,70 +611,84 @@ int rift_b200_engine::forward(const rift_b200_batch& bt, const rift_b200_outputs
             // The reference passes key_padding_mask = r_pad.repeat(Mo, 1) for a batch laid out (b, m)
             // (planning_decoder.py:56-60): batch row j = b*Mo + m is masked with r_pad[j % bs], not with
             // r_pad[b].  Reproduced as is - parity is defined by what the reference computes.
-            a.kpm = r_pad; a.kpm_mod = bs; a.scale = att_scale;
+            a.kpm = r_pad; a.kpm_mod = bs; a.scale = att_scale; a.lse = lse1;
             TRY(launch_attention(a, c.st));
         }
-        TRY(linear(c, a1, D, rowsQ, db.r2r.out, q1, D, ACT_NONE, q, D, 1));
+        { Epi e; e.res = q; e.ldres = D; TRY(linear_into(c, a1, db.r2r.out, e, q1, D)); }
         // (ii) m2m self-attention over modes on valid reference lines; padded lines -> 0
-        ALLOC(t2, float, (size_t)rowsQ * D);
-        ALLOC(t2p, float, (size_t)rowsQ * D);
         ALLOC(qkv2, float, (size_t)rowsQ * 3 * D);
-        ALLOC(a2, float, (size_t)rowsQ * D);
         ALLOC(q2, float, (size_t)rowsQ * D);
-        TRY(layernorm(c, q1, rowsQ, db.n2, t2, 0, nullptr, nullptr, m.m_pos.p, Mo, t2p));
-        TRY(linear(c, t2p, D, rowsQ, slice(db.m2m.in, 0, 2 * D, 0, D, true), qkv2, 3 * D));
-        TRY(linear(c, t2, D, rowsQ, slice(db.m2m.in, 2 * D, D, 0, D, true), qkv2 + 2 * D, 3 * D));
+        Act t2, t2p, a2;
+        TRY(layernorm_new(c, q1, rowsQ, db.n2, 0, want_in(c, rowsQ, {&m2m_v}), &t2, full ? &dt.ln2 : nullptr, m.m_pos.p, Mo,
+                          want_in(c, rowsQ, {&m2m_qk}), &t2p));
+        TRY(linear_into(c, t2p, m2m_qk, Epi(), qkv2, 3 * D));
+        TRY(linear_into(c, t2, m2m_v, Epi(), qkv2 + 2 * D, 3 * D));
+        TRY(new_act(c, rowsQ, D, want_in(c, rowsQ, {&db.m2m.out}), &a2));
         if (!c.dry) {
             AttnArgs a;
-            a.q = qkv2; a.k = qkv2 + D; a.v = qkv2 + 2 * D; a.o = a2;
+            a.q = qkv2; a.k = qkv2 + D; a.v = qkv2 + 2 * D; a.o = a2.f; a.o_planes = a2.p;
             a.ldq = a.ldk = a.ldv = 3 * D; a.ldo = D;
             a.B = NR; a.H = H; a.Sq = Mo; a.Sk = Mo; a.hd = D / H;
-            a.q_outer = Mo; a.k_outer = Mo; a.scale = att_scale;
+            a.q_outer = Mo; a.k_outer = Mo; a.scale = att_scale; a.lse = lse2;
             TRY(launch_attention(a, c.st));
         }
-        TRY(linear(c, a2, D, rowsQ, db.m2m.out, q2, D, ACT_NONE, q1, D, 1));
+        { Epi e; e.res = q1; e.ldres = D; TRY(linear_into(c, a2, db.m2m.out, e, q2, D)); }
         if (!c.dry) TRY(launch_zero_rows(q2, r_pad, Mo, rowsQ, D, c.st));
         // (iii) cross-attention to the scene encoding
-        ALLOC(t3, float, (size_t)rowsQ * D);
         ALLOC(qc, float, (size_t)rowsQ * D);
         ALLOC(kvc, float, (size_t)rowsE * 2 * D);
-        ALLOC(a3, float, (size_t)rowsQ * D);
         ALLOC(q3, float, (size_t)rowsQ * D);
-        TRY(layernorm(c, q2, rowsQ, db.n3, t3));
-        TRY(linear(c, t3, D, rowsQ, slice(db.cross.in, 0, D, 0, D, true), qc, D));
-        TRY(linear(c, Xn, D, rowsE, slice(db.cross.in, D, 2 * D, 0, D, true), kvc, 2 * D));
+        Act t3, a3;
+        TRY(layernorm_new(c, q2, rowsQ, db.n3, 0, want_in(c, rowsQ, {&cr_q}), &t3, full ? &dt.ln3 : nullptr));
+        TRY(linear_into(c, t3, cr_q, Epi(), qc, D));
+        TRY(linear_into(c, Xn, cr_kv, Epi(), kvc, 2 * D));
+        TRY(new_act(c, rowsQ, D, want_in(c, rowsQ, {&db.cross.out}), &a3));
         if (!c.dry) {
             AttnArgs a;
-            a.q = qc; a.k = kvc; a.v = kvc + D; a.o = a3;
+            a.q = qc; a.k = kvc; a.v = kvc + D; a.o = a3.f; a.o_planes = a3.p;
             a.ldq = D; a.ldk = a.ldv = 2 * D; a.ldo = D;
             a.B = bs; a.H = H; a.Sq = R * Mo; a.Sk = S; a.hd = D / H;
             a.q_outer = (long long)R * Mo; a.k_outer = S;
-            a.kpm = key_pad; a.kpm_div = 1; a.scale = att_scale;
+            a.kpm = key_pad; a.kpm_div = 1; a.scale = att_scale; a.lse = lse3;
             TRY(launch_attention(a, c.st));
         }
-        TRY(linear(c, a3, D, rowsQ, db.cross.out, q3, D, ACT_NONE, q2, D, 1));
+        { Epi e; e.res = q2; e.ldres = D; TRY(linear_into(c, a3, db.cross.out, e, q3, D)); }
         // (iv) ReLU FFN
-        ALLOC(t4, float, (size_t)rowsQ * D);
-        ALLOC(hm, float, (size_t)rowsQ * 4 * D);
         ALLOC(q4, float, (size_t)rowsQ * D);
-        TRY(layernorm(c, q3, rowsQ, db.n4, t4));
-        TRY(linear(c, t4, D, rowsQ, db.ffn0, hm, 4 * D, ACT_RELU));
-        TRY(linear(c, hm, 4 * D, rowsQ, db.ffn3, q4, D, ACT_NONE, q3, D, 1));
+        Act t4, hm;
+        TRY(layernorm_new(c, q3, rowsQ, db.n4, 0, want_in(c, rowsQ, {&db.ffn0}), &t4, full ? &dt.ln4 : nullptr));
+        { Epi e; e.act = ACT_RELU; TRY(linear_new(c, t4, db.ffn0, e, want_in(c, rowsQ, {&db.ffn3}), &hm)); }
+        { Epi e; e.res = q3; e.ldres = D; TRY(linear_into(c, hm, db.ffn3, e, q4, D)); }
+        dt.t1 = t1; dt.qkv1 = qkv1; dt.lse1 = lse1; dt.a1 = a1; dt.q1 = q1;
+        dt.t2 = t2; dt.t2p = t2p; dt.qkv2 = qkv2; dt.lse2 = lse2; dt.a2 = a2; dt.q2 = q2;
+        dt.t3 = t3; dt.qc = qc; dt.kvc = kvc; dt.lse3 = lse3; dt.a3 = a3; dt.q3 = q3;
+        dt.t4 = t4; dt.hm = hm;
+        T_.dec.push_back(dt);
         q = q4;
     }
+    T_.qlast = q;
     // cat_x_proj(cat[q, x_ego]) : the ego half of the weight acts once per sample
-    ALLOC(eg, float, (size_t)bs * D);
-    ALLOC(qf, float, (size_t)rowsQ * D);
-    TRY(linear_ld(c, Xn, (long long)S * D, bs, slice(m.cat_x_proj, 0, D, D, D, true), 2 * D, eg, D));
-    TRY(linear_ld(c, q, D, rowsQ, slice(m.cat_x_proj, 0, D, 0, D, false), 2 * D, qf, D, ACT_NONE, eg, D, R * Mo));
+    Act eg, qf;
+    {
+        const Lin ca = slice(m.cat_x_proj, 0, D, 0, D, false), cb = slice(m.cat_x_proj, 0, D, D, D, true);
+        Act qa = act_f32(q, D, rowsQ, D);
+        TRY(linear_new(c, xego_rows, cb, Epi(), W_F, &eg));
+        Epi e; e.res = eg.f; e.ldres = D; e.res_div = R * Mo;
+        const bool heads = out.trajectory != nullptr;
+        TRY(linear_new(c, qa, ca, e,
+                       heads ? want_in(c, rowsQ, {&m.pi_head.l0, &m.loc_head.l0}, c.save) : want_in(c, rowsQ, {&m.pi_head.l0}, c.save),
+                       &qf));
+        T_.qlast_a = qa; T_.xego_rows = xego_rows;
+    }
+    T_.qf = qf;
 
     if (out.trajectory) {
         ALLOC(tl, float, (size_t)rowsQ * 2 * T);
         ALLOC(ty, float, (size_t)rowsQ * 2 * T);
         ALLOC(tv, float, (size_t)rowsQ * 2 * T);
-        TRY(mlp_layer(c, qf, D, rowsQ, m.loc_head, tl, 2 * T));
-        TRY(mlp_layer(c, qf, D, rowsQ, m.yaw_head, ty, 2 * T));
-        TRY(mlp_layer(c, qf, D, rowsQ, m.vel_head, tv, 2 * T));
+        TRY(mlp_layer(c, qf, m.loc_head, tl, 2 * T, nullptr));
+        TRY(mlp_layer(c, qf, m.yaw_head, ty, 2 * T, nullptr));
+        TRY(mlp_layer(c, qf, m.vel_head, tv, 2 * T, nullptr));
         if (!c.dry) {
             TRY(launch_interleave_heads(tl, ty, tv, rowsQ, T, out.trajectory, c.st));
             if (out.candidate_trajectories) TRY(launch_traj_outputs(out.trajectory, rowsQ, T, out.candidate_trajectories, c.st));
@@ -696,78 +696,20 @@ int rift_b200_engine::forward(const rift_b200_batch& bt, const rift_b200_outputs
     }
     {
         ALLOC(pi, float, (size_t)rowsQ);
-        float *h = nullptr, *a = nullptr, *mean = nullptr, *rstd = nullptr;
-        TRY(mlp_layer(c, qf, D, rowsQ, m.pi_head, pi, 1, &h, &a, &mean, &rstd));
+        TRY(mlp_layer(c, qf, m.pi_head, pi, 1, c.save ? &T_.pi : nullptr));
         if (!c.dry) {
             TRY(launch_mask_logits(pi, r_pad, NR, Mo, -1e6f, c.st));
             if (out.probability)
                 RIFT_CUDA_OK(cudaMemcpyAsync(out.probability, pi, (size_t)rowsQ * sizeof(float), cudaMemcpyDeviceToDevice, c.st));
-            pi_tape.q = qf; pi_tape.h = h; pi_tape.a = a; pi_tape.mean = mean; pi_tape.rstd = rstd; pi_tape.rows = rowsQ;
-            pi_tape.valid = c.save;
         }
     }
     if (out.hidden) {
-        ALLOC(hh, float, (size_t)bs * D);
-        TRY(linear(c, Xn, (long long)S * D, bs, m.hidden0, hh, D, ACT_RELU));
-        TRY(linear(c, hh, D, bs, m.hidden2, out.hidden, D));
+        Act hh;
+        { Epi e; e.act = ACT_RELU; TRY(linear_new(c, xego_rows, m.hidden0, e, want_in(c, bs, {&m.hidden2}), &hh)); }
+        TRY(linear_into(c, hh, m.hidden2, Epi(), out.hidden, D));
     }
-    if (out.ref_free_trajectory) TRY(mlp_layer(c, Xn, (long long)S * D, bs, m.ref_free, out.ref_free_trajectory, 4 * T));
+    if (out.ref_free_trajectory) TRY(mlp_layer(c, xego_rows, m.ref_free, out.ref_free_trajectory, 4 * T, nullptr));
+    if (!c.dry) { tp.valid = c.save; tp.full = full; }
     fwd_ws_end = c.off;
-    return 0;
-}
-
-// =====================================================================================
-// backward (gradient of the objective wrt the trainable parameters)
-// =====================================================================================
-namespace rift {
-// dW += dY^T X ; db += colsum(dY) ; dX = dY W   (each optional)
-static int linear_bwd(Ctx& c, const float* X, long long ldx, const float* dY, long long lddy, int M, const Lin& L,
-                      long long ldw, float* dX, long long lddx, float dx_beta) {
-    if (L.train && L.dW) {
-        const int splits = M >= 2048 ? std::min(64, M / 512) : 1;
-        float* ws = nullptr;
-        if (splits > 1) { ws = c.alloc<float>((size_t)splits * L.N * L.K); if (!ws) { set_last_error("workspace too small"); return -1; } }
-        GemmArgs a;
-        a.A = dY; a.sam = 1; a.sak = lddy;             // A(m = out feature, k = row)
-        a.B = X; a.sbn = 1; a.sbk = ldx;               // B(n = in feature,  k = row)
-        a.C = L.dW; a.ldc = ldw; a.M = L.N; a.N = L.K; a.K = M; a.beta = 1.f;
-        a.split_k = splits; a.split_ws = ws;
-        TRY(gemm(c, a));
-    }
-    if (L.train && L.db) {
-        ALLOC(sc, float, (size_t)148 * L.N);
-        if (!c.dry) TRY(launch_colsum(dY, lddy, M, L.N, L.db, 1, sc, c.st));
-    }
-    if (dX) {
-        GemmArgs a;
-        a.A = dY; a.sam = lddy; a.sak = 1;             // A(m = row, k = out feature)
-        a.B = L.W; a.sbn = 1; a.sbk = ldw;             // B(n = in feature, k = out feature)
-        a.C = dX; a.ldc = lddx; a.M = M; a.N = L.K; a.K = L.N; a.beta = dx_beta;
-        TRY(gemm(c, a));
-    }
-    return 0;
-}
-}  // namespace rift
-
-int rift_b200_engine::backward(const rift_b200_batch& bt, const float* dlogits, Ctx& c) {
-    RIFT_REQUIRE(grads != nullptr, "backward: no gradient arena bound");
-    RIFT_REQUIRE(c.dry || pi_tape.valid, "backward: run forward with RIFT_B200_FWD_SAVE_FOR_BACKWARD first");
-    RIFT_REQUIRE(!m.any_trainable_outside_pi_head,
-                 "backward: trainable layers outside planning_decoder.pi_head are not supported by this build");
-    const int D = cfg.dim;
-    const long long rows = c.dry ? (long long)bt.bs * bt.R * cfg.num_modes : pi_tape.rows;
-    if (!c.dry && train_hi > train_lo)
-        RIFT_CUDA_OK(cudaMemsetAsync(grads + train_lo, 0, (size_t)(train_hi - train_lo) * sizeof(float), c.st));
-    const MLPLayerP& p = m.pi_head;
-    if (!p.l0.train) return 0;
-    // pi = l3(a) ; a = relu(LN(h)) ; h = l0(q)
-    ALLOC(da, float, (size_t)rows * D);
-    ALLOC(dh, float, (size_t)rows * D);
-    ALLOC(lnsc, float, (size_t)layernorm_bwd_scratch_floats(D));
-    TRY(linear_bwd(c, pi_tape.a, D, dlogits, 1, (int)rows, p.l3, D, da, D, 0.f));
-    if (!c.dry)
-        TRY(launch_layernorm_bwd(pi_tape.h, D, da, D, (int)rows, D, p.n.g, pi_tape.mean, pi_tape.rstd, pi_tape.a, D, dh, D, 0,
-                                 p.n.dg, p.n.db, lnsc, c.st));
-    TRY(linear_bwd(c, pi_tape.q, D, dh, D, (int)rows, p.l0, D, nullptr, 0, 0.f));
     return 0;
 }

@@ -7,8 +7,8 @@
 
 #include "../../include/rift_b200.h"
 #include "common.cuh"
-#include "ops.h"
 #include "gemm_tc.h"
+#include "ops.h"
 
 namespace rift {
 
@@ -16,6 +16,7 @@ struct Lin {            // nn.Linear / flattened Conv1d: W [N, K] row-major, b [
     const float* W = nullptr; const float* b = nullptr;
     float* dW = nullptr; float* db = nullptr;
     int N = 0, K = 0;
+    long long ldw = 0;      // row pitch of W (== K unless this is a column slice of a wider matrix)
     bool train = false;
     int tc = -1, tc_n0 = 0, tc_k0 = 0;      // index into the engine's pre-split weight planes (+ slice origin)
 };
@@ -62,7 +63,14 @@ struct Model {
     MLPLayerP loc_head, yaw_head, vel_head, pi_head;
     Lin hidden0, hidden2;
     MLPLayerP ref_free;
-    bool any_trainable_outside_pi_head = false;
+    bool full = false;      // some trainable parameter lies outside planning_decoder.pi_head
+};
+
+// An activation [rows, C]: fp32 (row pitch ld) and / or split-bf16 planes for the tcgen05 GEMM
+struct Act {
+    float* f = nullptr; long long ld = 0;
+    Planes p;
+    int rows = 0, C = 0;
 };
 
 struct Ctx {            // per-call state: stream + bump allocator over the caller's workspace
@@ -70,8 +78,9 @@ struct Ctx {            // per-call state: stream + bump allocator over the call
     char* base = nullptr;
     size_t cap = 0, off = 0;
     bool dry = false;      // measure only: advance the allocator, launch nothing
-    bool simt = true;      // force the exact-fp32 GEMM
-    bool save = false;
+    bool simt = true;      // force the exact-fp32 GEMM everywhere
+    bool save = false;     // keep what backward needs
+    bool full = false;     // save && trainable parameters outside pi_head: keep every activation (fp32)
     const std::vector<TcWeight>* tcw = nullptr;
     template <class T> T* alloc(size_t n) {
         const size_t bytes = (n * sizeof(T) + 255) & ~(size_t)255;
@@ -81,16 +90,58 @@ struct Ctx {            // per-call state: stream + bump allocator over the call
         if (off > cap) return nullptr;
         return reinterpret_cast<T*>(base + at);
     }
+    bool planes_for(int C) const { return !simt && C >= 32; }
 };
 
-// Activations kept between forward and backward (pointers into the workspace).
-struct PiHeadTape {
-    const float* q = nullptr;      // (rows, D) input of pi_head
-    float* h = nullptr;            // (rows, D) l0 output
-    float* a = nullptr;            // (rows, D) relu(LN(h))
-    float* mean = nullptr; float* rstd = nullptr;
-    long long rows = 0;
-    bool valid = false;
+// ---------------------------------------------------------------- saved activations (forward -> backward)
+struct LNSave { const float* x = nullptr; float* mean = nullptr; float* rstd = nullptr; int rows = 0; };
+struct MlpTape { Act x; Act h; LNSave ln; Act a; };                       // MLPLayer: x -> l0 -> h -> LN+ReLU -> a -> l3
+struct FourierTape {
+    const float* x = nullptr; int rows = 0;
+    struct Dim { Act feat; Act h; LNSave ln; Act hn; };
+    std::vector<Dim> dims;
+    float* acc = nullptr; LNSave ln_o; Act on;
+};
+struct PointsTape {
+    Act F; int groups = 0, n = 0, Cin = 0; const uint8_t* mask = nullptr;
+    float *sc1 = nullptr, *sh1 = nullptr, *sc2 = nullptr, *sh2 = nullptr;
+    float* h1pre = nullptr; Act h1; Act f; Act pooled; int* arg1 = nullptr; float* gp = nullptr;
+    float* h2pre = nullptr; Act h2; Act o; int* arg2 = nullptr;
+};
+struct NatBlockTape { float* x = nullptr; LNSave ln1; Act t1; float* qkv = nullptr; Act att; float* x1 = nullptr; LNSave ln2; Act t2;
+                      float* hpre = nullptr; Act hm; };
+struct NatTape {
+    int NA = 0; int Ls[3] = {0, 0, 0};
+    Act col0;
+    std::vector<NatBlockTape> blocks;       // 6, in forward order
+    float* xlev[3] = {nullptr, nullptr, nullptr};   // level output (input of norm_i and of the downsample)
+    LNSave ln_lev[3]; Act colL[3];
+    Act colD[2]; float* xd[2] = {nullptr, nullptr}; LNSave ln_down[2];
+    Act colF;
+};
+struct EgoTape { float* toks = nullptr; Act toks_a; float* kv = nullptr; float* qv = nullptr; float* lse = nullptr; Act eo; };
+struct EncBlockTape { float* X = nullptr; LNSave ln1; Act t1; float* qkv = nullptr; float* lse = nullptr; Act att; float* X1 = nullptr;
+                      LNSave ln2; Act t2; float* hpre = nullptr; Act hm; };
+struct DecBlockTape {
+    float* q = nullptr; LNSave ln1; Act t1; float* qkv1 = nullptr; float* lse1 = nullptr; Act a1; float* q1 = nullptr;
+    LNSave ln2; Act t2; Act t2p; float* qkv2 = nullptr; float* lse2 = nullptr; Act a2; float* q2 = nullptr;
+    LNSave ln3; Act t3; float* qc = nullptr; float* kvc = nullptr; float* lse3 = nullptr; Act a3; float* q3 = nullptr;
+    LNSave ln4; Act t4; Act hm;
+};
+struct Tape {
+    bool valid = false, full = false;
+    int bs = 0, A = 0, Mp = 0, P = 0, R = 0, Pr = 0, S = 0;
+    uint8_t *agent_any = nullptr, *key_pad = nullptr, *r_pad = nullptr;
+    NatTape nat; EgoTape ego;
+    PointsTape poly; FourierTape speed;
+    float* pos = nullptr; FourierTape pos_emb;
+    std::vector<EncBlockTape> enc;
+    float* Xlast = nullptr; LNSave ln_final; Act Xn;
+    float* rpos = nullptr; PointsTape renc; FourierTape rpos_emb; Act r_emb;
+    std::vector<DecBlockTape> dec;
+    float* qlast = nullptr; Act qlast_a;
+    Act xego_rows;            // Xn[:, 0] viewed (bs rows, pitch S*D)
+    Act qf; MlpTape pi;
 };
 
 struct ParamRef { long long offset, numel; bool trainable; };
@@ -104,7 +155,7 @@ struct rift_b200_engine {
     long long train_lo = 0, train_hi = 0;     // element span covering every trainable entry
     rift::Model m;
     bool bound = false;
-    rift::PiHeadTape pi_tape;
+    rift::Tape tape;
     // tcgen05 path: pre-split bf16 weight planes (caller-owned memory) + TMA descriptors
     std::vector<rift::TcWeight> tcw;
     void* wcache = nullptr; size_t wcache_bytes = 0;

@@ -1,0 +1,238 @@
+// Operator wrappers shared by the forward (engine.cu) and backward (engine_bwd.cu) schedules.
+#pragma once
+#include <math.h>
+
+#include <initializer_list>
+
+#include "engine.h"
+
+namespace rift {
+
+#define TRY(x)                   \
+    do {                         \
+        int _r = (x);            \
+        if (_r != 0) return _r;  \
+    } while (0)
+
+#define ALLOC(var, T, n)                                                           \
+    T* var = c.alloc<T>((size_t)(n));                                              \
+    if (!var) {                                                                    \
+        set_last_error("workspace too small (see rift_b200_workspace_bytes)");     \
+        return -1;                                                                 \
+    }
+
+constexpr int W_F = 1, W_P = 2;             // "want" bits for an activation: fp32 / split planes
+constexpr int NFREQ = 64, FIN = 129;
+constexpr int PE_H1 = 128, PE_H2 = 256;
+
+// shape-only routing decision (identical in the sizing pass and the real pass)
+inline bool route_tc(const Ctx& c, const Lin& L, int M, long long ldc) {
+    return !c.simt && L.tc >= 0 && c.tcw && gemm_tc_shape_ok(M, L.N, L.K) && (ldc % 4) == 0;
+}
+
+// which representations a GEMM-input activation needs: planes when some consuming Linear runs on the
+// tcgen05 path, fp32 when some consumer runs on the SIMT kernel, another kernel reads it, or the
+// full-backward mode keeps every activation
+inline int want_in(const Ctx& c, int rows, std::initializer_list<const Lin*> consumers, bool f32_reader = false) {
+    bool p = false, f = f32_reader || c.full || c.simt;
+    for (const Lin* L : consumers) {
+        if (route_tc(c, *L, rows, 4)) p = true; else f = true;
+    }
+    return (p ? W_P : 0) | (f ? W_F : 0);
+}
+
+inline int new_act(Ctx& c, int rows, int C, int want, Act* a) {
+    *a = Act();
+    a->rows = rows; a->C = C;
+    if (want & W_F) {
+        a->f = c.alloc<float>((size_t)rows * C); a->ld = C;
+        if (!a->f) { set_last_error("workspace too small"); return -1; }
+    }
+    if (want & W_P) {
+        a->p.Kp = tc_pitch(C);
+        a->p.hi = c.alloc<uint16_t>((size_t)rows * a->p.Kp);
+        a->p.lo = c.alloc<uint16_t>((size_t)rows * a->p.Kp);
+        if (!a->p.hi || !a->p.lo) { set_last_error("workspace too small"); return -1; }
+    }
+    return 0;
+}
+inline Act act_f32(float* f, long long ld, int rows, int C) { Act a; a.f = f; a.ld = ld; a.rows = rows; a.C = C; return a; }
+
+inline int ensure_planes(Ctx& c, Act& x) {
+    if (x.p.on()) return 0;
+    x.p.Kp = tc_pitch(x.C);
+    x.p.hi = c.alloc<uint16_t>((size_t)x.rows * x.p.Kp);
+    x.p.lo = c.alloc<uint16_t>((size_t)x.rows * x.p.Kp);
+    if (!x.p.hi || !x.p.lo) { set_last_error("workspace too small"); return -1; }
+    if (c.dry) return 0;
+    if (!x.f) { set_last_error("internal: activation has neither fp32 nor planes"); return -1; }
+    return launch_pack_split(x.f, x.ld, x.rows, x.C, x.p.Kp, x.p.hi, x.p.lo, c.st);
+}
+
+struct Epi {
+    int act = ACT_NONE;
+    const float* res = nullptr; long long ldres = 0; int res_div = 1, res_mod = 0;
+    const float* pre = nullptr; long long ldpre = 0; int pre_div = 1;
+    const float* colscale = nullptr; const float* shift = nullptr;     // eval-BatchNorm fold: replaces the bias
+    float* preact = nullptr;
+};
+
+// dst (fp32, pitch ldc; may be null on the tensor-core path when only planes are wanted) and / or planes
+inline int gemm_fwd(Ctx& c, Act& X, const Lin& L, const Epi& e, float* dst, long long ldc, Planes outp) {
+    GemmArgs a;
+    a.A = X.f; a.sam = X.ld; a.sak = 1;
+    a.B = L.W; a.sbn = L.ldw; a.sbk = 1;
+    a.C = dst; a.ldc = ldc; a.M = X.rows; a.N = L.N; a.K = L.K;
+    a.bias = e.colscale ? e.shift : L.b; a.colscale = e.colscale;
+    a.act = e.act; a.res = e.res; a.ldres = e.ldres; a.res_div = e.res_div; a.res_mod = e.res_mod;
+    a.pre = e.pre; a.ldpre = e.ldpre; a.pre_div = e.pre_div; a.preact = e.preact;
+    a.out_planes = outp;
+    if (route_tc(c, L, X.rows, ldc)) {
+        TRY(ensure_planes(c, X));
+        if (c.dry) return 0;
+        if (!gemm_tc_eligible(a)) { set_last_error("internal: tensor-core GEMM arguments misaligned"); return -1; }
+        return launch_gemm_tc(a, X.p.hi, X.p.lo, X.p.Kp, (*c.tcw)[L.tc], L.tc_n0, L.tc_k0, c.st);
+    }
+    if (c.dry) return 0;
+    if (!X.f || !dst) { set_last_error("internal: SIMT GEMM needs fp32 operands"); return -1; }
+    a.out_planes = Planes();
+    TRY(launch_gemm_simt(a, c.st));
+    if (outp.on()) TRY(launch_pack_split(dst, ldc, X.rows, L.N, outp.Kp, outp.hi, outp.lo, c.st));
+    return 0;
+}
+
+// Y = epilogue(X W^T): allocates Y in the requested representations
+inline int linear_new(Ctx& c, Act& X, const Lin& L, const Epi& e, int want, Act* Y) {
+    if (!route_tc(c, L, X.rows, L.N)) want |= W_F;          // the SIMT kernel only writes fp32
+    TRY(new_act(c, X.rows, L.N, want, Y));
+    return gemm_fwd(c, X, L, e, Y->f, L.N, Y->p);
+}
+// fp32 result into caller-provided storage (column block of a wider buffer)
+inline int linear_into(Ctx& c, Act& X, const Lin& L, const Epi& e, float* dst, long long ldc) {
+    return gemm_fwd(c, X, L, e, dst, ldc, Planes());
+}
+
+// slice of a Linear: output rows [n0, n0+n), input columns [k0, k0+k) (keeps the parent's row pitch)
+inline Lin slice(const Lin& L, int n0, int n, int k0, int k, bool with_bias) {
+    Lin s;
+    s.W = L.W + (long long)n0 * L.ldw + k0;
+    s.b = (with_bias && L.b) ? L.b + n0 : nullptr;
+    s.dW = L.dW ? L.dW + (long long)n0 * L.ldw + k0 : nullptr;
+    s.db = (with_bias && L.db) ? L.db + n0 : nullptr;
+    s.N = n; s.K = k; s.ldw = L.ldw; s.train = L.train;
+    s.tc = L.tc; s.tc_n0 = L.tc_n0 + n0; s.tc_k0 = L.tc_k0 + k0;
+    return s;
+}
+
+// y = LN(x) [ReLU] in the requested representations; optional y2 = y + add[row % rowmod]
+inline int layernorm_new(Ctx& c, const float* x, int rows, const Norm& n, int relu, int want, Act* y, LNSave* save,
+                         const float* add_rowmod = nullptr, int rowmod = 0, int want2 = 0, Act* y2 = nullptr) {
+    TRY(new_act(c, rows, n.C, want, y));
+    if (y2) TRY(new_act(c, rows, n.C, want2, y2));
+    float* mean = nullptr; float* rstd = nullptr;
+    if (save) {
+        mean = c.alloc<float>(rows); rstd = c.alloc<float>(rows);
+        if (!mean || !rstd) { set_last_error("workspace too small"); return -1; }
+        save->x = x; save->mean = mean; save->rstd = rstd; save->rows = rows;
+    }
+    if (c.dry) return 0;
+    return launch_layernorm(x, n.C, rows, n.C, n.g, n.b, y->f, n.C, relu, add_rowmod, rowmod, y2 ? y2->f : nullptr, mean, rstd,
+                            c.st, y->p, y2 ? y2->p : Planes());
+}
+
+// ---------------------------------------------------------------- attention argument builders (fwd + bwd)
+inline AttnArgs attn_self(const float* qkv, int B, int S, int D, int H, const uint8_t* kpm, float scale) {
+    AttnArgs a;
+    a.q = qkv; a.k = qkv + D; a.v = qkv + 2 * D;
+    a.ldq = a.ldk = a.ldv = 3 * D; a.ldo = D;
+    a.B = B; a.H = H; a.Sq = S; a.Sk = S; a.hd = D / H;
+    a.q_outer = S; a.k_outer = S;
+    a.kpm = kpm; a.kpm_div = 1; a.scale = scale;
+    return a;
+}
+// r2r: batch (b, m), sequence over reference lines.  The reference passes key_padding_mask =
+// r_pad.repeat(Mo, 1) for a batch laid out (b, m) (planning_decoder.py:56-60): batch row j = b*Mo + m is
+// masked with r_pad[j % bs], not with r_pad[b].  Reproduced as is - parity is what the reference computes.
+inline AttnArgs attn_r2r(const float* qkv, int bs, int R, int Mo, int D, int H, const uint8_t* r_pad, float scale) {
+    AttnArgs a;
+    a.q = qkv; a.k = qkv + D; a.v = qkv + 2 * D;
+    a.ldq = a.ldk = a.ldv = 3 * D; a.ldo = D;
+    a.B = bs * Mo; a.H = H; a.Sq = R; a.Sk = R; a.hd = D / H;
+    a.q_inner_n = Mo; a.q_outer = (long long)R * Mo; a.q_inner = 1; a.q_seq = Mo;
+    a.k_inner_n = Mo; a.k_outer = (long long)R * Mo; a.k_inner = 1; a.k_seq = Mo;
+    a.kpm = r_pad; a.kpm_mod = bs; a.scale = scale;
+    return a;
+}
+inline AttnArgs attn_m2m(const float* qkv, int NR, int Mo, int D, int H, float scale) {
+    AttnArgs a;
+    a.q = qkv; a.k = qkv + D; a.v = qkv + 2 * D;
+    a.ldq = a.ldk = a.ldv = 3 * D; a.ldo = D;
+    a.B = NR; a.H = H; a.Sq = Mo; a.Sk = Mo; a.hd = D / H;
+    a.q_outer = Mo; a.k_outer = Mo; a.scale = scale;
+    return a;
+}
+inline AttnArgs attn_cross(const float* qc, const float* kvc, int bs, int RM, int S, int D, int H, const uint8_t* key_pad,
+                           float scale) {
+    AttnArgs a;
+    a.q = qc; a.k = kvc; a.v = kvc + D;
+    a.ldq = D; a.ldk = a.ldv = 2 * D; a.ldo = D;
+    a.B = bs; a.H = H; a.Sq = RM; a.Sk = S; a.hd = D / H;
+    a.q_outer = RM; a.k_outer = S;
+    a.kpm = key_pad; a.kpm_div = 1; a.scale = scale;
+    return a;
+}
+// StateAttentionEncoder: one learned query shared by every sample, one output row per sample
+inline AttnArgs attn_ego(const float* qv, const float* kv, int bs, int ntok, int D, int eh) {
+    AttnArgs a;
+    a.q = qv; a.k = kv; a.v = kv + D;
+    a.ldq = D; a.ldk = a.ldv = 2 * D; a.ldo = D;
+    a.B = bs; a.H = eh; a.Sq = 1; a.Sk = ntok; a.hd = D / eh;
+    a.q_outer = 0; a.q_seq = 0;
+    a.k_outer = ntok;
+    a.o_custom = 1; a.o_outer = 1; a.o_seq = 0;
+    a.scale = 1.f / sqrtf((float)(D / eh));
+    return a;
+}
+
+// ---------------------------------------------------------------- backward helpers (exact-fp32 SIMT GEMMs)
+inline int simt(Ctx& c, const GemmArgs& a) {
+    if (c.dry) return 0;
+    return launch_gemm_simt(a, c.st);
+}
+// dW += dY^T X ; db += colsum(dY) ; dX (=|+=) dY W        (X: fp32 [M, K] pitch ldx)
+inline int lin_bwd(Ctx& c, const float* X, long long ldx, const float* dY, long long lddy, int M, const Lin& L, float* dX,
+                   long long lddx, float dx_beta, bool bias_grad = true) {
+    if (L.train && L.dW) {
+        const int splits = M >= 2048 ? (M / 512 < 64 ? M / 512 : 64) : 1;
+        float* ws = nullptr;
+        if (splits > 1) { ws = c.alloc<float>((size_t)splits * L.N * L.K); if (!ws) { set_last_error("workspace too small"); return -1; } }
+        GemmArgs a;
+        a.A = dY; a.sam = 1; a.sak = lddy;             // A(m = out feature, k = row)
+        a.B = X; a.sbn = 1; a.sbk = ldx;               // B(n = in feature,  k = row)
+        a.C = L.dW; a.ldc = L.ldw; a.M = L.N; a.N = L.K; a.K = M; a.beta = 1.f;
+        a.split_k = splits; a.split_ws = ws;
+        TRY(simt(c, a));
+    }
+    if (bias_grad && L.train && L.db) {
+        ALLOC(sc, float, (size_t)148 * L.N);
+        if (!c.dry) TRY(launch_colsum(dY, lddy, M, L.N, L.db, 1, sc, c.st));
+    }
+    if (dX) {
+        GemmArgs a;
+        a.A = dY; a.sam = lddy; a.sak = 1;             // A(m = row, k = out feature)
+        a.B = L.W; a.sbn = 1; a.sbk = L.ldw;           // B(n = in feature, k = out feature)
+        a.C = dX; a.ldc = lddx; a.M = M; a.N = L.K; a.K = L.N; a.beta = dx_beta;
+        TRY(simt(c, a));
+    }
+    return 0;
+}
+// LayerNorm backward: dx (=|+=) ... ; parameter gradients accumulate
+inline int ln_bwd(Ctx& c, const LNSave& s, const Norm& n, const float* dy, const float* y_relu, float* dx, int accumulate) {
+    ALLOC(sc, float, (size_t)layernorm_bwd_scratch_floats(n.C));
+    if (c.dry) return 0;
+    const bool pg = n.train && n.dg;
+    return launch_layernorm_bwd(s.x, n.C, dy, n.C, s.rows, n.C, n.g, s.mean, s.rstd, y_relu, n.C, dx, n.C, accumulate,
+                                pg ? n.dg : nullptr, pg ? n.db : nullptr, sc, c.st);
+}
+
+}  // namespace rift

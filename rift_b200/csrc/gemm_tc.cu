@@ -26,6 +26,7 @@
 
 #include "common.cuh"
 #include "gemm_tc.h"
+#include "split.cuh"
 
 namespace rift {
 
@@ -128,6 +129,7 @@ struct TcKernelArgs {
     int M, N, K;
     int w_n0, w_k0;          // origin of this (possibly sliced) weight inside the split planes
     TcEpilogue ep;
+    Planes out;              // optional split-bf16 copy of the result for the next GEMM (C may then be null)
 };
 
 template <int BN>
@@ -250,7 +252,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             const float* pre_row = e.pre ? e.pre + (long long)(m / e.pre_div) * e.ldpre : nullptr;
             const float* res_row = nullptr;
             if (e.res) res_row = e.res + (long long)(e.res_mod > 0 ? (m % e.res_mod) : (m / e.res_div)) * e.ldres;
-            float* c_row = g.C + (long long)m * g.ldc;
+            float* c_row = g.C ? g.C + (long long)m * g.ldc : nullptr;
             float* pa_row = e.preact ? e.preact + (long long)m * g.ldc : nullptr;
 #pragma unroll 1
             for (int cc = 0; cc < BN / 2; cc += 32) {
@@ -279,7 +281,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                                 const float4 t = ld4(c_row + n);
                                 v.x += e.beta * t.x; v.y += e.beta * t.y; v.z += e.beta * t.z; v.w += e.beta * t.w;
                             }
-                            *reinterpret_cast<float4*>(c_row + n) = v;
+                            if (c_row) *reinterpret_cast<float4*>(c_row + n) = v;
+                            if (g.out.on()) split4_store(g.out, m, n, v.x, v.y, v.z, v.w);
+                        } else if (g.out.on() && n < g.out.Kp) {
+                            split4_store(g.out, m, n, 0.f, 0.f, 0.f, 0.f);       // zero the pad columns [N, Kp)
                         }
                     }
                 }
@@ -433,7 +438,9 @@ bool gemm_tc_shape_ok(int M, int N, int K) { return K >= 32 && N >= 16 && (N % 4
 
 bool gemm_tc_eligible(const GemmArgs& a) {
     auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-    return a.sak == 1 && a.sbk == 1 && gemm_tc_shape_ok(a.M, a.N, a.K) && a.split_k <= 1 && (a.ldc % 4) == 0 && al16(a.C) &&
+    if (a.C == nullptr && !a.out_planes.on()) return false;
+    if (a.beta != 0.f && a.C == nullptr) return false;
+    return a.sbk == 1 && gemm_tc_shape_ok(a.M, a.N, a.K) && a.split_k <= 1 && (a.ldc % 4) == 0 && al16(a.C) &&
            al16(a.bias) && al16(a.colscale) && al16(a.pre) && (a.ldpre % 4) == 0 && al16(a.res) && (a.ldres % 4) == 0 &&
            al16(a.preact);
 }
@@ -459,6 +466,7 @@ static int launch_tc(const GemmArgs& a, const void* a_hi, const void* a_lo, int 
     g.C = a.C; g.ldc = a.ldc; g.M = a.M; g.N = a.N; g.K = a.K; g.w_n0 = n0; g.w_k0 = k0;
     g.ep = TcEpilogue{a.bias, a.colscale, a.pre, a.ldpre, a.pre_div, a.res, a.ldres, a.res_div, a.res_mod, a.act, a.beta,
                       a.alpha, a.preact};
+    g.out = a.out_planes;
     const int n_tiles = cdiv(a.N, BN) * cdiv(a.M, TC_BM);
     gemm_tc_kernel<BN><<<min(n_tiles, sms), TC_THREADS, TcSmem<BN>::TOTAL, st>>>(
         *ma_hi, *ma_lo, *reinterpret_cast<const CUtensorMap*>(w.tm_hi), *reinterpret_cast<const CUtensorMap*>(w.tm_lo), g);

@@ -1,0 +1,508 @@
+// Backward kernels of the non-GEMM operators (see nn_kernels.cu for the forward definitions).
+// All reductions are two-stage / fixed-order, so gradients are run-to-run deterministic.
+#include "common.cuh"
+#include "ops.h"
+
+namespace rift {
+
+#define GRID1D(n, t) (int)min((long long)148 * 16, ((long long)(n) + (t) - 1) / (t))
+#define FOR_GRID(i, n) \
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)(n); i += (long long)gridDim.x * blockDim.x)
+
+__device__ __forceinline__ long long attn_row_b(int b, int inner_n, long long outer, long long inner) {
+    return (long long)(b / inner_n) * outer + (long long)(b % inner_n) * inner;
+}
+
+// =====================================================================================
+// Multi-head attention backward (recompute form).  One CTA per (batch, head); Q, K, V, dO of the head are
+// staged in shared memory.  p_ij = exp(s_ij - lse_i), delta_i = sum_j p_ij dP_ij, dS = p (dP - delta).
+//   phase A (thread = query i): delta_i and dQ_i = scale * sum_j dS_ij K_j
+//   phase B (thread = key j)  : dV_j = sum_i p_ij dO_i ; dK_j = scale * sum_i dS_ij Q_i
+// Gradients are written with the operand's own row mapping (each element exactly once).  With a shared
+// query (q_outer = 0, o_custom) dQ is written per batch row of `dq` using the OUTPUT mapping.
+// =====================================================================================
+template <int HD>
+__global__ void __launch_bounds__(128)
+attention_bwd_kernel(AttnArgs a, const float* __restrict__ d_o, long long lddo, float* __restrict__ dq, long long lddq,
+                     float* __restrict__ dk, float* __restrict__ dv, long long lddk, long long lddv) {
+    extern __shared__ float sm[];
+    float* Qs = sm;                                  // [Sq][HD]
+    float* dOs = Qs + (size_t)a.Sq * HD;             // [Sq][HD]
+    float* Ks = dOs + (size_t)a.Sq * HD;             // [Sk][HD]
+    float* Vs = Ks + (size_t)a.Sk * HD;              // [Sk][HD]
+    float* delta = Vs + (size_t)a.Sk * HD;           // [Sq]
+    float* lse_s = delta + a.Sq;                     // [Sq]
+    const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
+    const long long krow0 = attn_row_b(b, a.k_inner_n, a.k_outer, a.k_inner);
+    const long long qrow0 = attn_row_b(b, a.q_inner_n, a.q_outer, a.q_inner);
+    const long long orow0 = a.o_custom ? attn_row_b(b, a.o_inner_n, a.o_outer, a.o_inner) : qrow0;
+    const long long oseq = a.o_custom ? a.o_seq : a.q_seq;
+    for (int e = threadIdx.x; e < a.Sk * HD; e += blockDim.x) {
+        const int j = e / HD, d = e - j * HD;
+        const long long r = krow0 + (long long)j * a.k_seq;
+        Ks[e] = a.k[r * a.ldk + h * HD + d];
+        Vs[e] = a.v[r * a.ldv + h * HD + d];
+    }
+    for (int e = threadIdx.x; e < a.Sq * HD; e += blockDim.x) {
+        const int i = e / HD, d = e - i * HD;
+        Qs[e] = a.q[(qrow0 + (long long)i * a.q_seq) * a.ldq + h * HD + d] * a.scale;     // pre-scaled q
+        dOs[e] = d_o[(orow0 + (long long)i * oseq) * lddo + h * HD + d];
+    }
+    for (int i = threadIdx.x; i < a.Sq; i += blockDim.x) lse_s[i] = a.lse[((long long)b * a.H + h) * a.Sq + i];
+    __syncthreads();
+    const uint8_t* kpm = a.kpm ? a.kpm + (long long)(a.kpm_mod > 0 ? b % a.kpm_mod : b / a.kpm_div) * a.Sk : nullptr;
+    // ---- phase A
+    for (int i = threadIdx.x; i < a.Sq; i += blockDim.x) {
+        const float lse = lse_s[i];
+        float dl = 0.f;
+        if (lse != INFINITY) {
+            for (int j = 0; j < a.Sk; ++j) {
+                if (kpm && kpm[j]) continue;
+                float s = 0.f, dp = 0.f;
+#pragma unroll
+                for (int d = 0; d < HD; ++d) { s = fmaf(Qs[i * HD + d], Ks[j * HD + d], s); dp = fmaf(dOs[i * HD + d], Vs[j * HD + d], dp); }
+                dl += __expf(s - lse) * dp;
+            }
+        }
+        delta[i] = dl;
+        float acc[HD];
+#pragma unroll
+        for (int d = 0; d < HD; ++d) acc[d] = 0.f;
+        if (lse != INFINITY) {
+            for (int j = 0; j < a.Sk; ++j) {
+                if (kpm && kpm[j]) continue;
+                float s = 0.f, dp = 0.f;
+#pragma unroll
+                for (int d = 0; d < HD; ++d) { s = fmaf(Qs[i * HD + d], Ks[j * HD + d], s); dp = fmaf(dOs[i * HD + d], Vs[j * HD + d], dp); }
+                const float ds = __expf(s - lse) * (dp - dl);
+#pragma unroll
+                for (int d = 0; d < HD; ++d) acc[d] = fmaf(ds, Ks[j * HD + d], acc[d]);
+            }
+        }
+        const long long dr = a.o_custom ? (orow0 + (long long)i * oseq) : (qrow0 + (long long)i * a.q_seq);
+#pragma unroll
+        for (int d = 0; d < HD; ++d) dq[dr * lddq + h * HD + d] = acc[d] * a.scale;
+    }
+    __syncthreads();
+    // ---- phase B
+    for (int j = threadIdx.x; j < a.Sk; j += blockDim.x) {
+        float ak[HD], av[HD];
+#pragma unroll
+        for (int d = 0; d < HD; ++d) { ak[d] = 0.f; av[d] = 0.f; }
+        if (!(kpm && kpm[j])) {
+            for (int i = 0; i < a.Sq; ++i) {
+                const float lse = lse_s[i];
+                if (lse == INFINITY) continue;
+                float s = 0.f, dp = 0.f;
+#pragma unroll
+                for (int d = 0; d < HD; ++d) { s = fmaf(Qs[i * HD + d], Ks[j * HD + d], s); dp = fmaf(dOs[i * HD + d], Vs[j * HD + d], dp); }
+                const float p = __expf(s - lse);
+                const float ds = p * (dp - delta[i]);
+#pragma unroll
+                for (int d = 0; d < HD; ++d) { av[d] = fmaf(p, dOs[i * HD + d], av[d]); ak[d] = fmaf(ds, Qs[i * HD + d], ak[d]); }
+            }
+        }
+        const long long r = krow0 + (long long)j * a.k_seq;
+#pragma unroll
+        for (int d = 0; d < HD; ++d) {
+            dk[r * lddk + h * HD + d] = ak[d];          // Qs is pre-scaled, so dK already carries `scale`
+            dv[r * lddv + h * HD + d] = av[d];
+        }
+    }
+}
+
+int launch_attention_bwd(const AttnArgs& a, const float* d_o, long long lddo, float* dq, long long lddq, float* dk,
+                         float* dv, long long lddk, long long lddv, cudaStream_t st) {
+    if (a.B <= 0 || a.Sq <= 0) return 0;
+    RIFT_REQUIRE(a.hd == 32 || a.hd == 64, "attention_bwd: head_dim must be 32 or 64");
+    RIFT_REQUIRE(a.lse != nullptr, "attention_bwd: forward must have saved the log-sum-exp");
+    const size_t smem = ((size_t)2 * a.Sq * a.hd + (size_t)2 * a.Sk * a.hd + 2 * a.Sq) * sizeof(float);
+    RIFT_REQUIRE(smem <= 200 * 1024, "attention_bwd: sequence too long for the shared-memory kernel");
+    static bool attr = false;
+    if (!attr) {
+        RIFT_CUDA_OK(cudaFuncSetAttribute(attention_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        RIFT_CUDA_OK(cudaFuncSetAttribute(attention_bwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr = true;
+    }
+    const int threads = min(128, (max(a.Sq, a.Sk) + 31) / 32 * 32);
+    if (a.hd == 32) attention_bwd_kernel<32><<<a.B * a.H, threads, smem, st>>>(a, d_o, lddo, dq, lddq, dk, dv, lddk, lddv);
+    else attention_bwd_kernel<64><<<a.B * a.H, threads, smem, st>>>(a, d_o, lddo, dq, lddq, dk, dv, lddk, lddv);
+    RIFT_LAUNCH_OK();
+    return 0;
+}
+
+// =====================================================================================
+// Neighbourhood attention backward: one warp per (sequence, head), lane = channel; dk / dv accumulate in
+// shared memory (a key is seen by up to `ksize` queries).  drpb partials per warp: [n_seq*heads][2k-1].
+// =====================================================================================
+constexpr int NATB_MAXL = 32, NATB_MAXK = 7;
+
+__global__ void __launch_bounds__(128)
+nat_attention_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ d_out, int n_seq, int L, int heads, int hd,
+                         int ksize, const float* __restrict__ rpb, float* __restrict__ dqkv, float* __restrict__ drpb_partial) {
+    __shared__ float s_dk[4][NATB_MAXL][32];
+    __shared__ float s_dv[4][NATB_MAXL][32];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = blockIdx.x * 4 + wib;
+    if (warp >= n_seq * heads) return;
+    const int n = warp / heads, h = warp % heads;
+    const int dim = heads * hd;
+    const float scale = rsqrtf((float)hd);
+    const float* base = qkv + (long long)n * L * 3 * dim + h * hd;
+    float* dbase = dqkv + (long long)n * L * 3 * dim + h * hd;
+    const bool on = lane < hd;
+    for (int j = 0; j < L; ++j) { s_dk[wib][j][lane] = 0.f; s_dv[wib][j][lane] = 0.f; }
+    float drpb[2 * NATB_MAXK - 1];
+#pragma unroll
+    for (int t = 0; t < 2 * NATB_MAXK - 1; ++t) drpb[t] = 0.f;
+    __syncwarp();
+    for (int i = 0; i < L; ++i) {
+        const int start = min(max(i - ksize / 2, 0), L - ksize);
+        const float q = on ? base[(long long)i * 3 * dim + lane] * scale : 0.f;
+        const float go = on ? d_out[((long long)n * L + i) * dim + h * hd + lane] : 0.f;
+        float p[NATB_MAXK], dp[NATB_MAXK];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int kk = 0; kk < NATB_MAXK; ++kk) {
+            p[kk] = 0.f; dp[kk] = 0.f;
+            if (kk < ksize) {
+                const int j = start + kk;
+                const float kv = on ? base[(long long)j * 3 * dim + dim + lane] : 0.f;
+                const float vv = on ? base[(long long)j * 3 * dim + 2 * dim + lane] : 0.f;
+                p[kk] = warp_sum(q * kv) + rpb[h * (2 * ksize - 1) + (j - i + ksize - 1)];
+                dp[kk] = warp_sum(go * vv);
+                mx = fmaxf(mx, p[kk]);
+            }
+        }
+        float den = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < NATB_MAXK; ++kk)
+            if (kk < ksize) { p[kk] = __expf(p[kk] - mx); den += p[kk]; }
+        float dl = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < NATB_MAXK; ++kk)
+            if (kk < ksize) { p[kk] /= den; dl += p[kk] * dp[kk]; }
+        float dqv = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < NATB_MAXK; ++kk) {
+            if (kk < ksize) {
+                const int j = start + kk;
+                const float ds = p[kk] * (dp[kk] - dl);
+                if (on) {
+                    const float kv = base[(long long)j * 3 * dim + dim + lane];
+                    dqv += ds * kv;
+                    s_dk[wib][j][lane] += ds * q;                 // q already carries the scale
+                    s_dv[wib][j][lane] += p[kk] * go;
+                }
+                // relative index (j - i + k - 1) depends on i only through `start`: accumulate per slot
+#pragma unroll
+                for (int t = 0; t < 2 * NATB_MAXK - 1; ++t)
+                    if (t == j - i + ksize - 1) drpb[t] += ds;
+            }
+        }
+        if (on) dbase[(long long)i * 3 * dim + lane] = dqv * scale;
+    }
+    __syncwarp();
+    if (on) {
+        for (int j = 0; j < L; ++j) {
+            dbase[(long long)j * 3 * dim + dim + lane] = s_dk[wib][j][lane];
+            dbase[(long long)j * 3 * dim + 2 * dim + lane] = s_dv[wib][j][lane];
+        }
+    }
+    if (drpb_partial && lane == 0) {
+        for (int t = 0; t < 2 * ksize - 1; ++t) drpb_partial[(long long)warp * (2 * ksize - 1) + t] = drpb[t];
+    }
+}
+
+int launch_nat_attention_bwd(const float* qkv, const float* d_out, int n_seq, int L, int heads, int hd, int ksize,
+                             const float* rpb, float* dqkv, float* drpb_partial, cudaStream_t st) {
+    if (n_seq <= 0) return 0;
+    RIFT_REQUIRE(hd <= 32 && ksize <= NATB_MAXK && L >= ksize && L <= NATB_MAXL, "nat_attention_bwd: unsupported shape");
+    nat_attention_bwd_kernel<<<cdiv((long long)n_seq * heads, 4), 128, 0, st>>>(qkv, d_out, n_seq, L, heads, hd, ksize, rpb, dqkv,
+                                                                             drpb_partial);
+    RIFT_LAUNCH_OK();
+    return 0;
+}
+
+// =====================================================================================
+// gather / scatter style backward kernels
+// =====================================================================================
+// max-pool: the gradient of a pooled value goes to the arg-max point (nowhere when the winner was a padded zero)
+__global__ void masked_maxpool_bwd_kernel(const float* __restrict__ dout, const int* __restrict__ argmax, int groups, int n,
+                                          int C, float* __restrict__ dx, int accumulate) {
+    FOR_GRID(e, (long long)groups * n * C) {
+        const int c = (int)(e % C);
+        const long long r = e / C;
+        const int p = (int)(r % n);
+        const long long g = r / n;
+        const float v = (argmax[g * C + c] == p) ? dout[g * C + c] : 0.f;
+        dx[e] = accumulate ? dx[e] + v : v;
+    }
+}
+int launch_masked_maxpool_bwd(const float* dout, const int* argmax, int groups, int n, int C, float* dx, int accumulate,
+                              cudaStream_t st) {
+    const long long total = (long long)groups * n * C;
+    if (total <= 0) return 0;
+    masked_maxpool_bwd_kernel<<<GRID1D(total, 256), 256, 0, st>>>(dout, argmax, groups, n, C, dx, accumulate);
+    RIFT_LAUNCH_OK();
+    return 0;
+}
+
+// col2im for the k=3, pad=1 im2col (gather form: every dx element sums its <= 3 contributions)
+__global__ void col2im_k3_kernel(const float* __restrict__ dcols, int n_seq, int L, int Lout, int C, int stride,
+                                 float* __restrict__ dx, int accumulate) {
+    FOR_GRID(e, (long long)n_seq * L * C) {
+        const int c = (int)(e % C);
+        const long long r = e / C;
+        const int ts = (int)(r % L);
+        const long long n = r / L;
+        float a = 0.f;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int num = ts + 1 - k;                   // t * stride
+            if (num >= 0 && num % stride == 0) {
+                const int t = num / stride;
+                if (t < Lout) a += dcols[((n * Lout + t) * C + c) * 3 + k];
+            }
+        }
+        dx[e] = accumulate ? dx[e] + a : a;
+    }
+}
+int launch_col2im_k3(const float* dcols, int n_seq, int L, int C, int stride, float* dx, int accumulate, cudaStream_t st) {
+    const int Lout = (L + 2 - 3) / stride + 1;
+    const long long total = (long long)n_seq * L * C;
+    if (total <= 0) return 0;
+    col2im_k3_kernel<<<GRID1D(total, 256), 256, 0, st>>>(dcols, n_seq, L, Lout, C, stride, dx, accumulate);
+    RIFT_LAUNCH_OK();
+    return 0;
+}
+// im2col_k3_last: dx[n, L-2+k, c] += dcols[n, c*3+k] for k = 0, 1 ; everything else 0
+__global__ void col2im_k3_last_kernel(const float* __restrict__ dcols, int n_seq, int L, int C, float* __restrict__ dx) {
+    FOR_GRID(e, (long long)n_seq * L * C) {
+        const int c = (int)(e % C);
+        const long long r = e / C;
+        const int ts = (int)(r % L);
+        const long long n = r / L;
+        const int k = ts - (L - 2);
+        dx[e] = (k == 0 || k == 1) ? dcols[(n * C + c) * 3 + k] : 0.f;
+    }
+}
+int launch_col2im_k3_last(const float* dcols, int n_seq, int L, int C, float* dx, cudaStream_t st) {
+    const long long total = (long long)n_seq * L * C;
+    if (total <= 0) return 0;
+    col2im_k3_last_kernel<<<GRID1D(total, 256), 256, 0, st>>>(dcols, n_seq, L, C, dx);
+    RIFT_LAUNCH_OK();
+    return 0;
+}
+
+// transpose of fpn_upsample_add: dsrc[n, i, c] += sum_j w(j -> i) ddst[n, j, c]
+__global__ void fpn_upsample_add_bwd_kernel(const float* __restrict__ ddst, float* __restrict__ dsrc, int n_seq, int Ld, int Ls,
+                                            int C) {
+    const float rscale = (float)Ls / (float)Ld;
+    FOR_GRID(e, (long long)n_seq * Ls * C) {
+        const int c = (int)(e % C);
+        const long long r = e / C;
+        const int i = (int)(r % Ls);
+        const long long n = r / Ls;
+        float a = 0.f;
+        for (int j = 0; j < Ld; ++j) {
+            float sp = ((float)j + 0.5f) * rscale - 0.5f;
+            sp = fmaxf(sp, 0.f);
+            const int i0 = min((int)sp, Ls - 1);
+            const int i1 = min(i0 + 1, Ls - 1);
+            const float w1 = sp - (float)i0, w0 = 1.f - w1;
+            float w = 0.f;
+            if (i0 == i) w += w0;
+            if (i1 == i) w += w1;
+            if (w != 0.f) a += w * ddst[(n * Ld + j) * C + c];
+        }
+        dsrc[e] += a;
+    }
+}
+int launch_fpn_upsample_add_bwd(const float* ddst, float* dsrc, int n_seq, int Ld, int Ls, int C, cudaStream_t st) {
+    const long long total = (long long)n_seq * Ls * C;
+    if (total <= 0) return 0;
+    fpn_upsample_add_bwd_kernel<<<GRID1D(total, 256), 256, 0, st>>>(ddst, dsrc, n_seq, Ld, Ls, C);
+    RIFT_LAUNCH_OK();
+    return 0;
+}
+
+// out[g, c] (+)= sum_{i<n} x[(g*n + i), c]        (broadcast-over-points / over-modes terms)
+__global__ void groupsum_kernel(const float* __restrict__ x, long long ldx, int groups, int n, int C, float* __restrict__ out,
+                                long long ldo, int accumulate) {
+    FOR_GRID(e, (long long)groups * C) {
+        const int c = (int)(e % C);
+        const long long g = e / C;
+        float a = 0.f;
+        for (int i = 0; i < n; ++i) a += x[(g * n + i) * ldx + c];
+        float* o = out + g * ldo + c;
+        *o = accumulate ? *o + a : a;
+    }
+}
+int launch_groupsum(const float* x, long long ldx, int groups, int n, int C, float* out, long long ldo, int accumulate,
+                    cudaStream_t st) {
+    if (groups <= 0 || C <= 0) return 0;
+    groupsum_kernel<<<GRID1D((long long)groups * C, 256), 256, 0, st>>>(x, ldx, groups, n, C, out, ldo, accumulate);
+    RIFT_LAUNCH_OK();
+    return 0;
+}
+
+// out[m, c] (+)= sum_{rows r with r % mod == m} x[r, c]   (per-mode parameters m_pos / m_emb, pos_embed)
+__global__ void __launch_bounds__(256)
+modsum_kernel(const float* __restrict__ x, long long ldx, long long rows, int C, int mod, float* __restrict__ out, int accumulate) {
+    // block = (m, column chunk); threads stride the columns; rows walked in order -> deterministic
+    const int m = blockIdx.x;
+    for (int c = blockIdx.y * 256 + threadIdx.x; c < C; c += gridDim.y * 256) {
+        float a = 0.f;
+        for (long long r = m; r < rows; r += mod) a += x[r * ldx + c];
+        float* o = out + (long long)m * C + c;
+        *o = accumulate ? *o + a : a;
+    }
+}
+int launch_modsum(const float* x, long long ldx, long long rows, int C, int mod, float* out, int accumulate, cudaStream_t st) {
+    if (rows <= 0 || C <= 0) return 0;
+    modsum_kernel<<<dim3(mod, cdiv(C, 256)), 256, 0, st>>>(x, ldx, rows, C, mod, out, accumulate);
+    RIFT_LAUNCH_OK();
+    return 0;
+}
+
+// embedding tables: demb[k, c] += sum_{rows with idx == k (and keep)} dy[row, c]; idx may be int8 or a 0/1 byte mask
+__global__ void __launch_bounds__(256)
+embedding_bwd_kernel(const float* __restrict__ dy, long long lddy, long long row0_stride, int inner, int outer_stride_rows,
+                     const int8_t* __restrict__ idx, long long rows, int C, float* __restrict__ demb, int invert_mask) {
+    // rows are addressed as dy[(row / inner) * outer_stride_rows + row % inner + row0_stride]
+    const int k = blockIdx.x;
+    for (int c = blockIdx.y * 256 + threadIdx.x; c < C; c += gridDim.y * 256) {
+        float a = 0.f;
+        for (long long r = 0; r < rows; ++r) {
+            int v = (int)idx[r];
+            if (invert_mask) v = v ? -1 : 0;            // "unknown" embedding: selected where the mask is 0
+            if (v == k) a += dy[((r / inner) * outer_stride_rows + (r % inner) + row0_stride) * lddy + c];
+        }
+        demb[(long long)k * C + c] += a;
+    }
+}
+int launch_embedding_bwd(const float* dy, long long lddy, long long row_offset, int inner, int outer_stride_rows,
+                         const int8_t* idx, long long rows, int C, int n_emb, float* demb, int invert_mask, cudaStream_t st) {
+    if (rows <= 0) return 0;
+    embedding_bwd_kernel<<<dim3(n_emb, cdiv(C, 256)), 256, 0, st>>>(dy, lddy, row_offset, inner, outer_stride_rows, idx, rows, C,
+                                                                   demb, invert_mask);
+    RIFT_LAUNCH_OK();
+    return 0;
+}
+
+// out[r, c] = keep[r] ? src[(r / inner) * outer_stride_rows + r % inner + row_offset, c] : 0
+__global__ void masked_gather_rows_kernel(const float* __restrict__ src, long long lds, long long row_offset, int inner,
+                                          int outer_stride_rows, const uint8_t* __restrict__ keep, long long rows, int C,
+                                          float* __restrict__ out, int zero_inner0) {
+    FOR_GRID(e, rows * C) {
+        const int c = (int)(e % C);
+        const long long r = e / C;
+        bool k = keep ? keep[r] != 0 : true;
+        if (zero_inner0 && (r % inner) == 0) k = false;
+        out[e] = k ? src[((r / inner) * outer_stride_rows + (r % inner) + row_offset) * lds + c] : 0.f;
+    }
+}
+int launch_masked_gather_rows(const float* src, long long lds, long long row_offset, int inner, int outer_stride_rows,
+                              const uint8_t* keep, long long rows, int C, float* out, int zero_inner0, cudaStream_t st) {
+    if (rows <= 0) return 0;
+    masked_gather_rows_kernel<<<GRID1D(rows * C, 256), 256, 0, st>>>(src, lds, row_offset, inner, outer_stride_rows, keep, rows,
+                                                                    C, out, zero_inner0);
+    RIFT_LAUNCH_OK();
+    return 0;
+}
+
+// dy[r, c] *= colscale[c]
+__global__ void scale_cols_kernel(float* __restrict__ dy, const float* __restrict__ s, long long rows, int C) {
+    FOR_GRID(e, rows * C) dy[e] *= s[e % C];
+}
+int launch_scale_cols(float* dy, const float* colscale, long long rows, int C, cudaStream_t st) {
+    if (rows <= 0) return 0;
+    scale_cols_kernel<<<GRID1D(rows * C, 256), 256, 0, st>>>(dy, colscale, rows, C);
+    RIFT_LAUNCH_OK();
+    return 0;
+}
+
+// eval-mode BatchNorm affine parameters: v = xhat * gamma + beta (pre-ReLU value saved by the forward)
+//   dgamma[c] += sum_r dz[r,c] * (v[r,c] - beta[c]) / gamma[c] ; dbeta[c] += sum_r dz[r,c]
+__global__ void __launch_bounds__(256)
+bn_affine_bwd_partial_kernel(const float* __restrict__ dz, const float* __restrict__ v, long long rows, int C,
+                             const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ partial) {
+    for (int c = threadIdx.x; c < C; c += 256) {
+        float ag = 0.f, ab = 0.f;
+        const float g = gamma[c], b = beta[c];
+        for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+            const float d = dz[r * C + c];
+            ag += d * (v[r * C + c] - b) / g;
+            ab += d;
+        }
+        partial[((long long)blockIdx.x * 2 + 0) * C + c] = ag;
+        partial[((long long)blockIdx.x * 2 + 1) * C + c] = ab;
+    }
+}
+__global__ void bn_affine_bwd_final_kernel(const float* __restrict__ partial, int nb, int C, float* __restrict__ dgamma,
+                                           float* __restrict__ dbeta) {
+    FOR_GRID(c, C) {
+        float ag = 0.f, ab = 0.f;
+        for (int b = 0; b < nb; ++b) { ag += partial[((long long)b * 2) * C + c]; ab += partial[((long long)b * 2 + 1) * C + c]; }
+        dgamma[c] += ag;
+        dbeta[c] += ab;
+    }
+}
+int launch_bn_affine_bwd(const float* dz, const float* v, long long rows, int C, const float* gamma, const float* beta,
+                         float* dgamma, float* dbeta, float* scratch, cudaStream_t st) {
+    if (rows <= 0) return 0;
+    const int nb = (int)min((long long)148, rows);
+    bn_affine_bwd_partial_kernel<<<nb, 256, 0, st>>>(dz, v, rows, C, gamma, beta, scratch);
+    RIFT_LAUNCH_OK();
+    bn_affine_bwd_final_kernel<<<cdiv(C, 256), 256, 0, st>>>(scratch, nb, C, dgamma, dbeta);
+    RIFT_LAUNCH_OK();
+    return 0;
+}
+
+// FourierEmbedding frequencies: feat = [cos(a_j), sin(a_j), x], a_j = 2 pi f_j x
+//   contrib[r, j] = (-sin(a_j) dfeat[r, j] + cos(a_j) dfeat[r, nfreq + j]) * 2 pi x[r]   (then column-summed)
+__global__ void fourier_freq_bwd_kernel(const float* __restrict__ x, int rows, int d, int dsel, const float* __restrict__ freqs,
+                                        int nfreq, const float* __restrict__ dfeat, int ldf, float* __restrict__ contrib) {
+    FOR_GRID(e, (long long)rows * nfreq) {
+        const int j = (int)(e % nfreq);
+        const long long r = e / nfreq;
+        const float xv = x[r * d + dsel];
+        const float ang = ((xv * freqs[dsel * nfreq + j]) * 2.f) * 3.141592653589793f;
+        contrib[e] = (-sinf(ang) * dfeat[r * ldf + j] + cosf(ang) * dfeat[r * ldf + nfreq + j]) * 6.283185307179586f * xv;
+    }
+}
+int launch_fourier_freq_bwd(const float* x, int rows, int d, int dsel, const float* freqs, int nfreq, const float* dfeat,
+                            int ldf, float* contrib, cudaStream_t st) {
+    if (rows <= 0) return 0;
+    fourier_freq_bwd_kernel<<<GRID1D((long long)rows * nfreq, 256), 256, 0, st>>>(x, rows, d, dsel, freqs, nfreq, dfeat, ldf,
+                                                                                 contrib);
+    RIFT_LAUNCH_OK();
+    return 0;
+}
+
+// StateAttentionEncoder token linears (Linear(1, D) each): dw_i[c] += sum_b cur[b,i] dtok[b,i,c] ; db_i[c] += sum_b dtok[b,i,c]
+__global__ void __launch_bounds__(256)
+state_tokens_bwd_kernel(const float* __restrict__ cur, int cs_stride, int bs, int n_tok, int D, const float* __restrict__ dtok,
+                        float* __restrict__ dw_all /*[n_tok][D]*/, float* __restrict__ db_all /*[n_tok][D]*/) {
+    const int i = blockIdx.x;
+    for (int c = blockIdx.y * 256 + threadIdx.x; c < D; c += gridDim.y * 256) {
+        float aw = 0.f, ab = 0.f;
+        for (int b = 0; b < bs; ++b) {
+            const float g = dtok[((long long)b * n_tok + i) * D + c];
+            aw += cur[(long long)b * cs_stride + i] * g;
+            ab += g;
+        }
+        dw_all[(long long)i * D + c] = aw;
+        db_all[(long long)i * D + c] = ab;
+    }
+}
+int launch_state_tokens_bwd(const float* cur, int cs_stride, int bs, int n_tok, int D, const float* dtok, float* dw_all,
+                            float* db_all, cudaStream_t st) {
+    if (bs <= 0) return 0;
+    state_tokens_bwd_kernel<<<dim3(n_tok, cdiv(D, 256)), 256, 0, st>>>(cur, cs_stride, bs, n_tok, D, dtok, dw_all, db_all);
+    RIFT_LAUNCH_OK();
+    return 0;
+}
+
+}  // namespace rift

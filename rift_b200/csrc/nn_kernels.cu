@@ -18,7 +18,7 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, long long ldx, int rows, int C, const float* __restrict__ gamma,
                  const float* __restrict__ beta, float* __restrict__ y, long long ldy, int relu,
                  const float* __restrict__ add_rowmod, int rowmod, float* __restrict__ y2, float* __restrict__ mean_out,
-                 float* __restrict__ rstd_out) {
+                 float* __restrict__ rstd_out, Planes yp, Planes y2p) {
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
     for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += gridDim.x * wpb) {
@@ -33,23 +33,30 @@ layernorm_kernel(const float* __restrict__ x, long long ldx, int rows, int C, co
             if (mean_out) mean_out[row] = mean;
             if (rstd_out) rstd_out[row] = rstd;
         }
-        float* yr = y + (long long)row * ldy;
         for (int c = lane; c < C; c += 32) {
             float v = (xr[c] - mean) * rstd * gamma[c] + beta[c];
             if (relu) v = fmaxf(v, 0.f);
-            yr[c] = v;
-            if (y2) y2[(long long)row * ldy + c] = v + add_rowmod[(long long)(row % rowmod) * C + c];
+            if (y) y[(long long)row * ldy + c] = v;
+            if (yp.on()) split_store(yp, row, c, v);
+            if (add_rowmod) {
+                const float v2 = v + add_rowmod[(long long)(row % rowmod) * C + c];
+                if (y2) y2[(long long)row * ldy + c] = v2;
+                if (y2p.on()) split_store(y2p, row, c, v2);
+            }
         }
+        if (yp.on()) split_zero_pad(yp, row, C, lane, 32);
+        if (y2p.on()) split_zero_pad(y2p, row, C, lane, 32);
     }
 }
 
 int launch_layernorm(const float* x, long long ldx, int rows, int C, const float* gamma, const float* beta, float* y,
                      long long ldy, int relu, const float* add_rowmod, int rowmod, float* y2, float* mean, float* rstd,
-                     cudaStream_t st) {
+                     cudaStream_t st, Planes yp, Planes y2p) {
     if (rows <= 0) return 0;
-    RIFT_REQUIRE(y2 == nullptr || (add_rowmod != nullptr && rowmod > 0), "layernorm: y2 needs add_rowmod");
+    RIFT_REQUIRE((y2 == nullptr && !y2p.on()) || (add_rowmod != nullptr && rowmod > 0), "layernorm: y2 needs add_rowmod");
+    if (y2 == nullptr && !y2p.on()) add_rowmod = nullptr;
     layernorm_kernel<<<min(cdiv(rows, 8), 148 * 8), 256, 0, st>>>(x, ldx, rows, C, gamma, beta, y, ldy, relu, add_rowmod,
-                                                                  rowmod, y2, mean, rstd);
+                                                                  rowmod, y2, mean, rstd, yp, y2p);
     RIFT_LAUNCH_OK();
     return 0;
 }
@@ -229,7 +236,10 @@ attention_kernel(AttnArgs a) {
 #pragma unroll
         const long long orow = a.o_custom ? attn_row(b, a.o_inner_n, a.o_outer, a.o_inner) + (long long)i * a.o_seq : qr;
 #pragma unroll
-        for (int d = 0; d < HD; ++d) a.o[orow * a.ldo + h * HD + d] = acc[d] * inv;
+        for (int d = 0; d < HD; ++d) {
+            if (a.o) a.o[orow * a.ldo + h * HD + d] = acc[d] * inv;
+            if (a.o_planes.on()) split_store(a.o_planes, orow, h * HD + d, acc[d] * inv);
+        }
         if (a.lse) a.lse[((long long)b * a.H + h) * a.Sq + i] = l > 0.f ? m + logf(l) : INFINITY;
     }
 }
@@ -264,7 +274,7 @@ constexpr int NAT_MAXL = 32, NAT_MAXK = 7;
 
 __global__ void __launch_bounds__(128)
 nat_attention_kernel(const float* __restrict__ qkv, int n_seq, int L, int heads, int hd, int ksize,
-                     const float* __restrict__ rpb, float* __restrict__ out) {
+                     const float* __restrict__ rpb, float* __restrict__ out, Planes op) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= n_seq * heads) return;
     const int n = warp / heads, h = warp % heads;
@@ -294,15 +304,19 @@ nat_attention_kernel(const float* __restrict__ qkv, int n_seq, int L, int heads,
 #pragma unroll
         for (int kk = 0; kk < NAT_MAXK; ++kk)
             if (kk < ksize && on) o += logit[kk] * base[(long long)(start + kk) * 3 * dim + 2 * dim + lane];
-        if (on) out[((long long)n * L + i) * dim + h * hd + lane] = o / den;
+        if (on) {
+            if (out) out[((long long)n * L + i) * dim + h * hd + lane] = o / den;
+            if (op.on()) split_store(op, (long long)n * L + i, h * hd + lane, o / den);
+        }
+        if (op.on() && h == 0) split_zero_pad(op, (long long)n * L + i, dim, lane, 32);
     }
 }
 
 int launch_nat_attention(const float* qkv, int n_seq, int L, int heads, int hd, int ksize, const float* rpb, float* out,
-                         cudaStream_t st) {
+                         cudaStream_t st, Planes op) {
     if (n_seq <= 0) return 0;
     RIFT_REQUIRE(hd <= 32 && ksize <= NAT_MAXK && L >= ksize && L <= NAT_MAXL, "nat_attention: unsupported shape");
-    nat_attention_kernel<<<cdiv((long long)n_seq * heads * 32, 128), 128, 0, st>>>(qkv, n_seq, L, heads, hd, ksize, rpb, out);
+    nat_attention_kernel<<<cdiv((long long)n_seq * heads * 32, 128), 128, 0, st>>>(qkv, n_seq, L, heads, hd, ksize, rpb, out, op);
     RIFT_LAUNCH_OK();
     return 0;
 }
@@ -313,43 +327,54 @@ int launch_nat_attention(const float* qkv, int n_seq, int L, int heads, int hd, 
 // x is channel-last (n_seq, L, C).
 // =====================================================================================
 __global__ void im2col_k3_kernel(const float* __restrict__ x, int n_seq, int L, int Lout, int C, int stride,
-                                 float* __restrict__ out) {
-    const long long total = (long long)n_seq * Lout * C * 3;
+                                 float* __restrict__ out, Planes op) {
+    const int W = op.on() ? op.Kp : C * 3;          // with planes the pad columns are written (as zeros) too
+    const long long total = (long long)n_seq * Lout * W;
     FOR_GRID(e, total) {
-        const int k = (int)(e % 3);
-        const long long r = e / 3;
-        const int c = (int)(r % C);
-        const long long row = r / C;               // n * Lout + t
-        const int t = (int)(row % Lout);
-        const long long n = row / Lout;
-        const int ts = t * stride - 1 + k;
-        out[e] = (ts >= 0 && ts < L) ? x[(n * L + ts) * C + c] : 0.f;
+        const int j = (int)(e % W);
+        const long long row = e / W;               // n * Lout + t
+        float v = 0.f;
+        if (j < C * 3) {
+            const int k = j % 3, c = j / 3;
+            const int t = (int)(row % Lout);
+            const long long n = row / Lout;
+            const int ts = t * stride - 1 + k;
+            v = (ts >= 0 && ts < L) ? x[(n * L + ts) * C + c] : 0.f;
+            if (out) out[row * (C * 3) + j] = v;
+        }
+        if (op.on()) split_store(op, row, j, v);
     }
 }
-int launch_im2col_k3(const float* x, int n_seq, int L, int C, int stride, float* out, cudaStream_t st) {
+int launch_im2col_k3(const float* x, int n_seq, int L, int C, int stride, float* out, cudaStream_t st, Planes op) {
     const int Lout = (L + 2 - 3) / stride + 1;
-    const long long total = (long long)n_seq * Lout * C * 3;
+    const long long total = (long long)n_seq * Lout * (op.on() ? op.Kp : C * 3);
     if (total <= 0) return 0;
-    im2col_k3_kernel<<<GRID1D(total, 256), 256, 0, st>>>(x, n_seq, L, Lout, C, stride, out);
+    im2col_k3_kernel<<<GRID1D(total, 256), 256, 0, st>>>(x, n_seq, L, Lout, C, stride, out, op);
     RIFT_LAUNCH_OK();
     return 0;
 }
 // only the last output position (the encoder keeps out[:, :, -1], layers/embedding.py:87)
-__global__ void im2col_k3_last_kernel(const float* __restrict__ x, int n_seq, int L, int C, float* __restrict__ out) {
-    const long long total = (long long)n_seq * C * 3;
+__global__ void im2col_k3_last_kernel(const float* __restrict__ x, int n_seq, int L, int C, float* __restrict__ out,
+                                      Planes op) {
+    const int W = op.on() ? op.Kp : C * 3;
+    const long long total = (long long)n_seq * W;
     FOR_GRID(e, total) {
-        const int k = (int)(e % 3);
-        const long long r = e / 3;
-        const int c = (int)(r % C);
-        const long long n = r / C;
-        const int ts = L - 2 + k;
-        out[e] = (ts >= 0 && ts < L) ? x[(n * L + ts) * C + c] : 0.f;
+        const int j = (int)(e % W);
+        const long long n = e / W;
+        float v = 0.f;
+        if (j < C * 3) {
+            const int k = j % 3, c = j / 3;
+            const int ts = L - 2 + k;
+            v = (ts >= 0 && ts < L) ? x[(n * L + ts) * C + c] : 0.f;
+            if (out) out[n * (C * 3) + j] = v;
+        }
+        if (op.on()) split_store(op, n, j, v);
     }
 }
-int launch_im2col_k3_last(const float* x, int n_seq, int L, int C, float* out, cudaStream_t st) {
-    const long long total = (long long)n_seq * C * 3;
+int launch_im2col_k3_last(const float* x, int n_seq, int L, int C, float* out, cudaStream_t st, Planes op) {
+    const long long total = (long long)n_seq * (op.on() ? op.Kp : C * 3);
     if (total <= 0) return 0;
-    im2col_k3_last_kernel<<<GRID1D(total, 256), 256, 0, st>>>(x, n_seq, L, C, out);
+    im2col_k3_last_kernel<<<GRID1D(total, 256), 256, 0, st>>>(x, n_seq, L, C, out, op);
     RIFT_LAUNCH_OK();
     return 0;
 }
@@ -385,7 +410,7 @@ int launch_fpn_upsample_add(float* dst, const float* src, int n_seq, int Ld, int
 // part in the max; argmax = -1 when the winning value is such a zero (gradient is dropped there).
 // =====================================================================================
 __global__ void masked_maxpool_kernel(const float* __restrict__ x, const uint8_t* __restrict__ mask, int groups, int n, int C,
-                                      float* __restrict__ out, int* __restrict__ argmax) {
+                                      float* __restrict__ out, int* __restrict__ argmax, Planes op) {
     const long long total = (long long)groups * C;
     FOR_GRID(e, total) {
         const int c = (int)(e % C);
@@ -397,15 +422,19 @@ __global__ void masked_maxpool_kernel(const float* __restrict__ x, const uint8_t
             const float val = v ? x[(g * n + p) * C + c] : 0.f;
             if (val > best) { best = val; arg = v ? p : -1; }
         }
-        out[e] = best;
+        if (out) out[e] = best;
+        if (op.on()) {
+            split_store(op, g, c, best);
+            if (c == 0) split_zero_pad(op, g, C, 0, 1);
+        }
         if (argmax) argmax[e] = arg;
     }
 }
 int launch_masked_maxpool(const float* x, const uint8_t* mask, int groups, int n, int C, float* out, int* argmax,
-                          cudaStream_t st) {
+                          cudaStream_t st, Planes op) {
     const long long total = (long long)groups * C;
     if (total <= 0) return 0;
-    masked_maxpool_kernel<<<GRID1D(total, 256), 256, 0, st>>>(x, mask, groups, n, C, out, argmax);
+    masked_maxpool_kernel<<<GRID1D(total, 256), 256, 0, st>>>(x, mask, groups, n, C, out, argmax, op);
     RIFT_LAUNCH_OK();
     return 0;
 }
@@ -607,7 +636,8 @@ int launch_token_pos(const float* agent_pos, const float* agent_heading, const f
 // FourierEmbedding input features (layers/fourier_embedding.py:45-50) for input dimension `dsel`:
 // [cos(x f 2 pi) (nfreq), sin(x f 2 pi) (nfreq), x], zero padded to ldf columns
 __global__ void fourier_features_kernel(const float* __restrict__ x, int rows, int d, int dsel, const float* __restrict__ freqs,
-                                        int nfreq, float* __restrict__ feat, int ldf) {
+                                        int nfreq, float* __restrict__ feat, int ldfeat, Planes op) {
+    const int ldf = op.on() ? op.Kp : ldfeat;          // loop width: the planes' zero pad is written too
     FOR_GRID(e, (long long)rows * ldf) {
         const int c = (int)(e % ldf);
         const long long r = e / ldf;
@@ -620,14 +650,16 @@ __global__ void fourier_features_kernel(const float* __restrict__ x, int rows, i
         } else if (c == 2 * nfreq) {
             v = xv;
         }
-        feat[e] = v;
+        if (op.on()) split_store(op, r, c, v);
+        if (feat && c < ldfeat) feat[r * ldfeat + c] = v;
     }
 }
 int launch_fourier_features(const float* x, int rows, int d, int dsel, const float* freqs, int nfreq, float* feat,
-                            int ldf, cudaStream_t st) {
+                            int ldf, cudaStream_t st, Planes op) {
     if (rows <= 0) return 0;
     RIFT_REQUIRE(ldf >= 2 * nfreq + 1, "fourier_features: ldf too small");
-    fourier_features_kernel<<<GRID1D((long long)rows * ldf, 256), 256, 0, st>>>(x, rows, d, dsel, freqs, nfreq, feat, ldf);
+    const int width = op.on() ? op.Kp : ldf;
+    fourier_features_kernel<<<GRID1D((long long)rows * width, 256), 256, 0, st>>>(x, rows, d, dsel, freqs, nfreq, feat, ldf, op);
     RIFT_LAUNCH_OK();
     return 0;
 }

@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "split.cuh"
+
 namespace rift {
 
 // ------------------------------------------------------------------ rl_kernels.cu
@@ -43,19 +45,20 @@ struct GemmArgs {
     const float* pre = nullptr; long long ldpre = 0; int pre_div = 1;   // added before scale/bias/act
     const float* res = nullptr; long long ldres = 0; int res_div = 1;   // added after act
     int res_mod = 0;                     // if >0 the residual row is (m % res_mod) instead of m / res_div
-    int act = 0;                         // Act
+    int act = 0;                         // ActKind
     float beta = 0.f;                    // accumulate into C (gradient arenas)
     float alpha = 1.f;                   // scales the raw product
     int split_k = 1;                     // >1: partial products in workspace, reduced deterministically
     float* split_ws = nullptr;           // [split_k, M, N] when split_k > 1
     float* preact = nullptr;             // optional copy of the value before `act` (same ldc), for backward
+    Planes out_planes;                   // optional split-bf16 copy of the result (tcgen05 path; C may then be null)
 };
 int launch_gemm_simt(const GemmArgs& a, cudaStream_t st);
 
 // ------------------------------------------------------------------ nn_kernels.cu
 int launch_layernorm(const float* x, long long ldx, int rows, int C, const float* gamma, const float* beta, float* y,
                      long long ldy, int relu, const float* add_rowmod, int rowmod, float* y2, float* mean, float* rstd,
-                     cudaStream_t st);
+                     cudaStream_t st, Planes yp = Planes(), Planes y2p = Planes());
 int launch_layernorm_bwd(const float* x, long long ldx, const float* dy, long long lddy, int rows, int C,
                          const float* gamma, const float* mean, const float* rstd, const float* y_for_relu, long long ldy,
                          float* dx, long long lddx, int dx_accumulate, float* dgamma, float* dbeta, float* scratch,
@@ -75,25 +78,28 @@ struct AttnArgs {
     // output rows default to the query rows; o_custom selects an own mapping (shared learned query)
     int o_custom = 0; int o_inner_n = 1; long long o_outer = 0, o_inner = 0, o_seq = 1;
     float* lse = nullptr;                            // [B, H, Sq] log-sum-exp of scaled logits (for backward)
+    Planes o_planes;                                 // optional split-bf16 copy of the output (o may then be null)
 };
 int launch_attention(const AttnArgs& a, cudaStream_t st);
 int launch_attention_bwd(const AttnArgs& a, const float* d_o, long long lddo, float* dq, long long lddq, float* dk,
                          float* dv, long long lddk, long long lddv, cudaStream_t st);
 
 int launch_nat_attention(const float* qkv, int n_seq, int L, int heads, int hd, int ksize, const float* rpb, float* out,
-                         cudaStream_t st);
+                         cudaStream_t st, Planes op = Planes());
 int launch_nat_attention_bwd(const float* qkv, const float* d_out, int n_seq, int L, int heads, int hd, int ksize,
                              const float* rpb, float* dqkv, float* drpb_partial, cudaStream_t st);
 
-int launch_im2col_k3(const float* x, int n_seq, int L, int C, int stride, float* out, cudaStream_t st);   // -> (n_seq*Lout, C*3)
-int launch_im2col_k3_last(const float* x, int n_seq, int L, int C, float* out, cudaStream_t st);           // -> (n_seq, C*3) at t=L-1
+int launch_im2col_k3(const float* x, int n_seq, int L, int C, int stride, float* out, cudaStream_t st,
+                     Planes op = Planes());   // -> (n_seq*Lout, C*3)
+int launch_im2col_k3_last(const float* x, int n_seq, int L, int C, float* out, cudaStream_t st,
+                          Planes op = Planes());           // -> (n_seq, C*3) at t=L-1
 int launch_col2im_k3(const float* dcols, int n_seq, int L, int C, int stride, float* dx, int accumulate, cudaStream_t st);
 int launch_col2im_k3_last(const float* dcols, int n_seq, int L, int C, float* dx, cudaStream_t st);
 int launch_fpn_upsample_add(float* dst, const float* src, int n_seq, int Ld, int Ls, int C, cudaStream_t st);
 int launch_fpn_upsample_add_bwd(const float* ddst, float* dsrc, int n_seq, int Ld, int Ls, int C, cudaStream_t st);
 
 int launch_masked_maxpool(const float* x, const uint8_t* mask, int groups, int n, int C, float* out, int* argmax,
-                          cudaStream_t st);
+                          cudaStream_t st, Planes op = Planes());
 int launch_masked_maxpool_bwd(const float* dout, const int* argmax, int groups, int n, int C, float* dx, int accumulate,
                               cudaStream_t st);
 int launch_mask_any(const uint8_t* mask, int rows, int n, uint8_t* any_out, uint8_t* none_out, cudaStream_t st);
@@ -111,7 +117,7 @@ int launch_ref_features(const float* position, const float* vector, const float*
 int launch_token_pos(const float* agent_pos, const float* agent_heading, const float* polygon_center, int bs, int A,
                      int Th, int Tstride, int Mp, float* pos, cudaStream_t st);
 int launch_fourier_features(const float* x, int rows, int d, int dsel, const float* freqs, int nfreq, float* feat,
-                            int ldf, cudaStream_t st);
+                            int ldf, cudaStream_t st, Planes op = Planes());
 int launch_fourier_features_bwd(const float* x, int rows, int d, int dsel, const float* freqs, int nfreq,
                                 const float* dfeat, int ldf, float* dfreqs_partial, cudaStream_t st);
 
@@ -135,5 +141,21 @@ int launch_act_bwd(const float* pre_or_post, float* dy, long long n, int act, cu
 int launch_add_inplace(float* dst, const float* src, long long n, cudaStream_t st);
 int launch_scale_shift_rows_bwd(float* dy, const float* colscale, long long rows, int C, cudaStream_t st);
 int launch_traj_outputs(const float* trajectory, long long n_traj, int T, float* cand, cudaStream_t st);
+
+// ------------------------------------------------------------------ nn_bwd_kernels.cu
+int launch_groupsum(const float* x, long long ldx, int groups, int n, int C, float* out, long long ldo, int accumulate,
+                    cudaStream_t st);
+int launch_modsum(const float* x, long long ldx, long long rows, int C, int mod, float* out, int accumulate, cudaStream_t st);
+int launch_embedding_bwd(const float* dy, long long lddy, long long row_offset, int inner, int outer_stride_rows,
+                         const int8_t* idx, long long rows, int C, int n_emb, float* demb, int invert_mask, cudaStream_t st);
+int launch_masked_gather_rows(const float* src, long long lds, long long row_offset, int inner, int outer_stride_rows,
+                              const uint8_t* keep, long long rows, int C, float* out, int zero_inner0, cudaStream_t st);
+int launch_scale_cols(float* dy, const float* colscale, long long rows, int C, cudaStream_t st);
+int launch_bn_affine_bwd(const float* dz, const float* v, long long rows, int C, const float* gamma, const float* beta,
+                         float* dgamma, float* dbeta, float* scratch, cudaStream_t st);
+int launch_fourier_freq_bwd(const float* x, int rows, int d, int dsel, const float* freqs, int nfreq, const float* dfeat,
+                            int ldf, float* contrib, cudaStream_t st);
+int launch_state_tokens_bwd(const float* cur, int cs_stride, int bs, int n_tok, int D, const float* dtok, float* dw_all,
+                            float* db_all, cudaStream_t st);
 
 }  // namespace rift
