@@ -60,16 +60,21 @@ int rift_b200_bind_arena(rift_b200_engine* e, float* params, float* grads, long 
 size_t rift_b200_workspace_bytes(const rift_b200_engine* e_, const rift_b200_batch* shape) {
     if (!e_ || !shape || !e_->bound) return 0;
     rift_b200_engine* e = const_cast<rift_b200_engine*>(e_);
-    Ctx c; c.dry = true; c.save = true; c.simt = false;     // size for the tensor-core path (superset)
     rift_b200_outputs out;
     float* dummy = reinterpret_cast<float*>(0x100);
     out.probability = dummy; out.trajectory = dummy; out.prediction = dummy; out.hidden = dummy;
     out.ref_free_trajectory = dummy; out.candidate_trajectories = dummy; out.r_padding_mask = nullptr;
-    if (e->forward(*shape, out, c) != 0) return 0;
-    if (e->grads) {
-        if (e->backward(*shape, nullptr, c) != 0) return 0;
+    size_t need = 0;
+    for (int mode = 0; mode < 2; ++mode) {          // the tensor-core and the exact-fp32 schedules allocate differently
+        Ctx c; c.dry = true; c.save = true; c.simt = (mode == 1);
+        if (e->forward(*shape, out, c) != 0) return 0;
+        if (e->grads) {
+            c.simt = (mode == 1);
+            if (e->backward(*shape, nullptr, c) != 0) return 0;
+        }
+        if (c.off > need) need = c.off;
     }
-    return c.off + 4096;
+    return need + 4096;
 }
 
 int rift_b200_forward(rift_b200_engine* e, const rift_b200_batch* batch, const rift_b200_outputs* out, void* workspace,
@@ -102,7 +107,7 @@ int rift_b200_backward(rift_b200_engine* e, const rift_b200_batch* batch, const 
     RIFT_REQUIRE(e->bound, "backward: bind_arena first");
     Ctx c; c.st = S(stream); c.base = static_cast<char*>(workspace); c.cap = workspace_bytes;
     c.off = e->fwd_ws_end;          // scratch goes after the activations saved by forward
-    (void)flags;
+    c.simt = (flags & RIFT_B200_GEMM_SIMT) != 0;
     return e->backward(*batch, dlogits, c);
 }
 
@@ -195,16 +200,13 @@ int rift_b200_op_linear_tc(const float* x, int rows, int K, const float* w, cons
     tw.hi = p; tw.lo = p + plane;
     if (resplit) {
         std::vector<char> job(split_job_bytes());
-        fill_split_job(job.data(), w, K, N, K, tw.Kp, tw.hi, tw.lo, 0);
+        fill_split_job(job.data(), w, K, N, K, tw.Kp, tw.hi, tw.lo, 0, 0);
         RIFT_CUDA_OK(cudaMemcpyAsync(p + 2 * plane, job.data(), job.size(), cudaMemcpyHostToDevice, S(stream)));
         RIFT_CUDA_OK(cudaStreamSynchronize(S(stream)));
         int r = launch_split_weights(p + 2 * plane, 1, (long long)N * tw.Kp, S(stream));
         if (r) return r;
     }
-    int r = make_weight_tensor_map(tw.tm_hi, tw.hi, N, tw.Kp);
-    if (r) return r;
-    r = make_weight_tensor_map(tw.tm_lo, tw.lo, N, tw.Kp);
-    if (r) return r;
+    int r = 0;
     GemmArgs a;
     a.A = x; a.sam = K; a.B = w; a.sbn = K; a.C = y; a.ldc = N; a.M = rows; a.N = N; a.K = K;
     a.bias = bias; a.act = act; a.res = res; a.ldres = N;

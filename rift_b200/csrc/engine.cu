@@ -52,6 +52,12 @@ struct Binder {
                 w.src = l.W; w.ld_src = K; w.N = N; w.K = K; w.Kp = tc_pitch(K); w.trainable = r->trainable;
                 l.tc = (int)e->tcw.size();
                 e->tcw.push_back(w);
+                if (e->grads) {                // W^T planes [K, Np] for the data-gradient product dX = dY W
+                    TcWeight t;
+                    t.src = l.W; t.ld_src = K; t.N = K; t.K = N; t.Kp = tc_pitch(N); t.trainable = r->trainable; t.transpose = true;
+                    l.tcT = (int)e->tcw.size();
+                    e->tcw.push_back(t);
+                }
             }
         }
         if (bias) if (auto r = find(p + bname)) {
@@ -125,12 +131,12 @@ int rift_b200_engine::bind_weight_cache(void* cache, size_t bytes) {
     for (TcWeight& w : tcw) {
         const size_t plane = ((size_t)w.N * w.Kp * 2 + 255) & ~(size_t)255;
         w.hi = p; w.lo = p + plane; p += 2 * plane;
-        TRY(make_weight_tensor_map(w.tm_hi, w.hi, w.N, w.Kp));
-        TRY(make_weight_tensor_map(w.tm_lo, w.lo, w.N, w.Kp));
-        fill_split_job(all.data() + n_jobs_all * split_job_bytes(), w.src, w.ld_src, w.N, w.K, w.Kp, w.hi, w.lo, total_all);
+        fill_split_job(all.data() + n_jobs_all * split_job_bytes(), w.src, w.ld_src, w.N, w.K, w.Kp, w.hi, w.lo, total_all,
+                       w.transpose ? 1 : 0);
         ++n_jobs_all; total_all += (long long)w.N * w.Kp;
         if (w.trainable) {
-            fill_split_job(tr.data() + n_jobs_train * split_job_bytes(), w.src, w.ld_src, w.N, w.K, w.Kp, w.hi, w.lo, total_train);
+            fill_split_job(tr.data() + n_jobs_train * split_job_bytes(), w.src, w.ld_src, w.N, w.K, w.Kp, w.hi, w.lo, total_train,
+                           w.transpose ? 1 : 0);
             ++n_jobs_train; total_train += (long long)w.N * w.Kp;
         }
     }

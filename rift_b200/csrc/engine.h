@@ -19,6 +19,7 @@ struct Lin {            // nn.Linear / flattened Conv1d: W [N, K] row-major, b [
     long long ldw = 0;      // row pitch of W (== K unless this is a column slice of a wider matrix)
     bool train = false;
     int tc = -1, tc_n0 = 0, tc_k0 = 0;      // index into the engine's pre-split weight planes (+ slice origin)
+    int tcT = -1;                           // index of the transposed planes (W^T) used by the backward
 };
 struct Norm {           // LayerNorm
     const float* g = nullptr; const float* b = nullptr;
@@ -81,6 +82,7 @@ struct Ctx {            // per-call state: stream + bump allocator over the call
     bool simt = true;      // force the exact-fp32 GEMM everywhere
     bool save = false;     // keep what backward needs
     bool full = false;     // save && trainable parameters outside pi_head: keep every activation (fp32)
+    bool tc_bwd = false;   // backward GEMMs on the tcgen05 path (false: exact-fp32 SIMT)
     const std::vector<TcWeight>* tcw = nullptr;
     template <class T> T* alloc(size_t n) {
         const size_t bytes = (n * sizeof(T) + 255) & ~(size_t)255;

@@ -122,7 +122,9 @@ int rift_b200_engine::backward(const rift_b200_batch& bt, const float* dlogits, 
     const int NR = bs * R, rowsQ = NR * Mo, rowsE = bs * S;
     const float att_scale = 1.f / sqrtf((float)(D / H));
     const bool full = c.dry ? m.full : tape.full;
-    c.simt = true;                  // the backward GEMMs run on the exact-fp32 SIMT kernel in this round
+    c.tcw = &tcw;
+    c.tc_bwd = !c.simt && wcache != nullptr;      // c.simt on entry = caller asked for the exact-fp32 path
+    c.simt = true;                                // (forward-style routing helpers are not used below)
     c.full = full;
     Tape dry_tape;
     if (c.dry) {                    // sizing pass: a tape with the right block counts, pointers unused

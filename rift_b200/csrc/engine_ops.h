@@ -120,7 +120,7 @@ inline Lin slice(const Lin& L, int n0, int n, int k0, int k, bool with_bias) {
     s.dW = L.dW ? L.dW + (long long)n0 * L.ldw + k0 : nullptr;
     s.db = (with_bias && L.db) ? L.db + n0 : nullptr;
     s.N = n; s.K = k; s.ldw = L.ldw; s.train = L.train;
-    s.tc = L.tc; s.tc_n0 = L.tc_n0 + n0; s.tc_k0 = L.tc_k0 + k0;
+    s.tc = L.tc; s.tcT = L.tcT; s.tc_n0 = L.tc_n0 + n0; s.tc_k0 = L.tc_k0 + k0;
     return s;
 }
 
@@ -199,10 +199,49 @@ inline int simt(Ctx& c, const GemmArgs& a) {
     if (c.dry) return 0;
     return launch_gemm_simt(a, c.st);
 }
-// dW += dY^T X ; db += colsum(dY) ; dX (=|+=) dY W        (X: fp32 [M, K] pitch ldx)
+// dW += dY^T X ; db += colsum(dY) ; dX (=|+=) dY W        (X: fp32 [M, K] pitch ldx, optional planes Xp)
+// Tensor-core route (c.tc_bwd): dY is packed once into split-bf16 planes [M, Np];
+//   dX = dYp x (W^T planes)            K-major tcgen05 GEMM
+//   dW += dYp^T x Xp                   MN-major tcgen05 GEMM over the same [rows, features] planes, split-K over rows
 inline int lin_bwd(Ctx& c, const float* X, long long ldx, const float* dY, long long lddy, int M, const Lin& L, float* dX,
-                   long long lddx, float dx_beta, bool bias_grad = true) {
-    if (L.train && L.dW) {
+                   long long lddx, float dx_beta, bool bias_grad = true, const Planes* Xp = nullptr) {
+    const bool want_w = L.train && L.dW;
+    const bool tc_on = c.tc_bwd && c.tcw && L.tcT >= 0;
+    const bool tc_d = tc_on && dX && gemm_tc_shape_ok(M, L.K, L.N) && (lddx % 4) == 0;
+    const bool tc_w = tc_on && want_w && gemm_tc_shape_ok(L.N, L.K, M) && L.N >= 64 && (L.ldw % 4) == 0;
+    Planes dYp;
+    if (tc_d || tc_w) {
+        dYp.Kp = tc_pitch(L.N);
+        dYp.hi = c.alloc<uint16_t>((size_t)M * dYp.Kp);
+        dYp.lo = c.alloc<uint16_t>((size_t)M * dYp.Kp);
+        if (!dYp.hi || !dYp.lo) { set_last_error("workspace too small"); return -1; }
+        if (!c.dry) TRY(launch_pack_split(dY, lddy, M, L.N, dYp.Kp, dYp.hi, dYp.lo, c.st));
+    }
+    if (tc_w) {
+        Planes xp;
+        if (Xp && Xp->on()) xp = *Xp;
+        else {
+            xp.Kp = tc_pitch(L.K);
+            xp.hi = c.alloc<uint16_t>((size_t)M * xp.Kp);
+            xp.lo = c.alloc<uint16_t>((size_t)M * xp.Kp);
+            if (!xp.hi || !xp.lo) { set_last_error("workspace too small"); return -1; }
+            if (!c.dry) TRY(launch_pack_split(X, ldx, M, L.K, xp.Kp, xp.hi, xp.lo, c.st));
+        }
+        const int tiles = ((L.N + 127) / 128) * ((L.K + (L.K <= 64 ? 63 : 127)) / (L.K <= 64 ? 64 : 128));
+        const int num_kb = (M + 63) / 64;
+        int splits = 296 / tiles;
+        if (splits > num_kb) splits = num_kb;
+        if (splits < 1) splits = 1;
+        float* ws = nullptr;
+        if (splits > 1) { ws = c.alloc<float>((size_t)splits * L.N * L.K); if (!ws) { set_last_error("workspace too small"); return -1; } }
+        if (!c.dry) {
+            GemmArgs a;
+            a.C = L.dW; a.ldc = L.ldw; a.M = L.N; a.N = L.K; a.K = M; a.beta = 1.f;
+            PlaneOp A{dYp.hi, dYp.lo, M, dYp.Kp, 0, 0};
+            PlaneOp B{xp.hi, xp.lo, M, xp.Kp, 0, 0};
+            TRY(launch_gemm_tc_ex(a, A, B, true, splits, ws, c.st));
+        }
+    } else if (want_w) {
         const int splits = M >= 2048 ? (M / 512 < 64 ? M / 512 : 64) : 1;
         float* ws = nullptr;
         if (splits > 1) { ws = c.alloc<float>((size_t)splits * L.N * L.K); if (!ws) { set_last_error("workspace too small"); return -1; } }
@@ -217,7 +256,16 @@ inline int lin_bwd(Ctx& c, const float* X, long long ldx, const float* dY, long 
         ALLOC(sc, float, (size_t)148 * L.N);
         if (!c.dry) TRY(launch_colsum(dY, lddy, M, L.N, L.db, 1, sc, c.st));
     }
-    if (dX) {
+    if (tc_d) {
+        if (!c.dry) {
+            const TcWeight& wt = (*c.tcw)[L.tcT];          // planes [K_full, Np_full] of W^T; the slice origin swaps roles
+            GemmArgs a;
+            a.C = dX; a.ldc = lddx; a.M = M; a.N = L.K; a.K = L.N; a.beta = dx_beta;
+            PlaneOp A{dYp.hi, dYp.lo, M, dYp.Kp, 0, 0};
+            PlaneOp B{wt.hi, wt.lo, wt.N, wt.Kp, L.tc_k0, L.tc_n0};
+            TRY(launch_gemm_tc_ex(a, A, B, false, 1, nullptr, c.st));
+        }
+    } else if (dX) {
         GemmArgs a;
         a.A = dY; a.sam = lddy; a.sak = 1;             // A(m = row, k = out feature)
         a.B = L.W; a.sbn = 1; a.sbk = L.ldw;           // B(n = in feature, k = out feature)

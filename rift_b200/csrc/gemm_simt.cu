@@ -125,6 +125,15 @@ gemm_splitk_reduce_kernel(const float* __restrict__ ws, int splits, float* __res
     }
 }
 
+// fixed-order reduction of split-K partials [splits, M, N] + the epilogue of `a` into a.C (shared with gemm_tc.cu)
+int launch_splitk_reduce(const float* ws, int splits, const GemmArgs& a, cudaStream_t st) {
+    Epilogue ep{a.bias, a.colscale, a.pre, a.ldpre, a.pre_div, a.res, a.ldres, a.res_div, a.res_mod, a.act, a.beta, a.alpha, a.preact, a.ldc};
+    const long long total = (long long)a.M * a.N;
+    gemm_splitk_reduce_kernel<<<(int)min((long long)148 * 8, (total + 255) / 256), 256, 0, st>>>(ws, splits, a.C, a.ldc, a.M, a.N, ep);
+    RIFT_LAUNCH_OK();
+    return 0;
+}
+
 int launch_gemm_simt(const GemmArgs& a, cudaStream_t st) {
     RIFT_REQUIRE(a.A && a.B && a.C, "gemm: null operand");
     if (a.M <= 0 || a.N <= 0) return 0;

@@ -9,7 +9,7 @@
 // of bf16 (= 1.5x tf32), which these memory-bound shapes (K <= 1024, N <= 1024) hide.
 //
 // Structure: persistent, warp-specialised, one CTA per SM, 320 threads
-//   warp 0      TMA producer: A_hi / A_lo (box 64 x 128) and W_hi / W_lo (box 64 x 64) tiles, SWIZZLE_128B,
+//   warp 0      TMA producer: A_hi / A_lo and B_hi / B_lo tiles as 64 x 64 boxes, SWIZZLE_128B,
 //               3-stage ring of 64 KB stages, mbarrier complete_tx
 //   warp 1      TMEM allocation (2 x BN columns: double-buffered accumulator) + single-thread tcgen05.mma
 //               issue; tcgen05.commit releases smem stages and publishes finished accumulators
@@ -17,7 +17,10 @@
 //               alpha / pre-add / BatchNorm scale / bias / ReLU|GELU / residual / beta*C, float4 stores;
 //               the epilogue of tile i overlaps the main loop of tile i+1 through the second accumulator
 // The A planes are produced by pack_split (below) or directly by the producing kernel (LayerNorm etc.);
-// the W planes are refreshed after every optimizer step (split_weights_kernel).
+// the W planes (and their transposes, for dX = dY W) are refreshed after every optimizer step.
+// Operand majorness is a template switch: the forward and the data-gradient products read K-major
+// tiles, the weight-gradient product dW = dY^T X reads the SAME [rows, features] planes as MN-major
+// tiles (reduction over rows), with split-K over the row range and a deterministic partial reduce.
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <cuda_bf16.h>
@@ -105,15 +108,21 @@ __device__ __forceinline__ void tmem_ld_32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
-// [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major) | [32,46) SBO>>4 = 1024 B (8 rows x 128 B)
-// | [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
-__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr) {
-    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+// SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+// [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
+// Every operand tile is a stack of 64 x 64 bf16 TMA boxes (64 rows of 128 B, 8-row swizzle atoms of 1024 B):
+//   K-major  (rows = M/N index, 128 B = 64 k)  : SBO = 1024 (next 8 rows); k-step of 16 = +32 B inside the atom
+//   MN-major (rows = k index, 128 B = 64 m/n)  : SBO = 1024 (next 8 k), LBO = 8192 (next block of 64 m/n = next
+//                                                box); k-step of 16 = +2 atoms = +2048 B
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr, uint32_t lbo_bytes) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
+           (1ull << 46) | (2ull << 61);
 }
-// instruction descriptor (cute::UMMA::InstrDescriptor): D = f32, A = B = bf16, both K-major, M = 128, N = BN
-__host__ __device__ constexpr uint32_t make_idesc(int bn) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = f32, A = B = bf16, M = 128, N = BN,
+// bits 15 / 16 = A / B major (0 = K-major, 1 = MN-major)
+__host__ __device__ constexpr uint32_t make_idesc(int bn, bool mn_major) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (mn_major ? (3u << 15) : 0u) | ((uint32_t)(bn >> 3) << 17) |
+           ((uint32_t)(TC_BM >> 4) << 24);
 }
 
 struct TcEpilogue {
@@ -127,7 +136,8 @@ struct TcEpilogue {
 struct TcKernelArgs {
     float* C; long long ldc;
     int M, N, K;
-    int w_n0, w_k0;          // origin of this (possibly sliced) weight inside the split planes
+    int a_mn0, a_k0, b_mn0, b_k0;   // origins of the operand tiles inside their planes
+    int splits, kb_per_split; long long split_stride;     // split-K: slab `s` writes raw sums to C + s * split_stride
     TcEpilogue ep;
     Planes out;              // optional split-bf16 copy of the result for the next GEMM (C may then be null)
 };
@@ -139,10 +149,11 @@ struct TcSmem {
     static constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;
     static constexpr int TOTAL = TC_STAGES * STAGE + 1024 /*align*/ + 256 /*barriers*/;
 };
+constexpr int TC_BOX = 64 * 64 * 2;      // bytes of one 64 x 64 bf16 TMA box
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
-template <int BN>
+template <int BN, bool MN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, TcKernelArgs g) {
@@ -159,7 +170,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_n = (g.N + BN - 1) / BN;
     const int tiles_m = (g.M + TC_BM - 1) / TC_BM;
-    const int n_tiles = tiles_m * tiles_n;
+    const int tiles_mn = tiles_m * tiles_n;
+    const int n_tiles = tiles_mn * g.splits;
     const int num_kb = (g.K + TC_BK - 1) / TC_BK;
 
     if (warp == 0 && lane == 0) {
@@ -182,8 +194,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         if (lane == 0) {
             int it = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                const int m0 = (tile / tiles_n) * TC_BM, n0 = (tile % tiles_n) * BN;
-                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                const int sp = tile / tiles_mn, tmn = tile - sp * tiles_mn;
+                const int m0 = (tmn / tiles_n) * TC_BM, n0 = (tmn % tiles_n) * BN;
+                const int kb0 = sp * g.kb_per_split, kb1 = min(num_kb, kb0 + g.kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
                     const int s = it % TC_STAGES;
                     const uint32_t ph = (it / TC_STAGES) & 1;
                     mbar_wait(&empty[s], ph ^ 1);
@@ -192,13 +206,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                     uint8_t* b_hi = a_lo + SM::A_TILE;
                     uint8_t* b_lo = b_hi + SM::B_TILE;
                     mbar_arrive_expect_tx(&full[s], SM::STAGE);
-                    tma_load_2d(a_hi, &tmA_hi, &full[s], kb * TC_BK, m0);
-                    tma_load_2d(a_lo, &tmA_lo, &full[s], kb * TC_BK, m0);
-                    const int ck = g.w_k0 + kb * TC_BK;
+                    const int ka = g.a_k0 + kb * TC_BK, kbb = g.b_k0 + kb * TC_BK;
 #pragma unroll
-                    for (int rb = 0; rb < BN / 64; ++rb) {      // the weight tensor-map box is 64 (k) x 64 (rows)
-                        tma_load_2d(b_hi + rb * (64 * TC_BK * 2), &tmB_hi, &full[s], ck, g.w_n0 + n0 + rb * 64);
-                        tma_load_2d(b_lo + rb * (64 * TC_BK * 2), &tmB_lo, &full[s], ck, g.w_n0 + n0 + rb * 64);
+                    for (int rb = 0; rb < TC_BM / 64; ++rb) {
+                        const int mn = g.a_mn0 + m0 + rb * 64;
+                        tma_load_2d(a_hi + rb * TC_BOX, &tmA_hi, &full[s], MN ? mn : ka, MN ? ka : mn);
+                        tma_load_2d(a_lo + rb * TC_BOX, &tmA_lo, &full[s], MN ? mn : ka, MN ? ka : mn);
+                    }
+#pragma unroll
+                    for (int rb = 0; rb < BN / 64; ++rb) {
+                        const int mn = g.b_mn0 + n0 + rb * 64;
+                        tma_load_2d(b_hi + rb * TC_BOX, &tmB_hi, &full[s], MN ? mn : kbb, MN ? kbb : mn);
+                        tma_load_2d(b_lo + rb * TC_BOX, &tmB_lo, &full[s], MN ? mn : kbb, MN ? kbb : mn);
                     }
                 }
             }
@@ -206,14 +225,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(BN);
+            constexpr uint32_t idesc = make_idesc(BN, MN);
+            constexpr uint32_t kstep = MN ? 2048u : 32u;          // bytes per UMMA_K = 16 step
+            constexpr uint32_t lbo = MN ? (uint32_t)TC_BOX : 0u;
             int it = 0, ti = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+                const int sp = tile / tiles_mn;
+                const int kb0 = sp * g.kb_per_split, kb1 = min(num_kb, kb0 + g.kb_per_split);
                 const int buf = ti & 1;
                 mbar_wait(&acc_empty[buf], ((ti >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + (uint32_t)(buf * BN);
-                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
                     const int s = it % TC_STAGES;
                     const uint32_t ph = (it / TC_STAGES) & 1;
                     mbar_wait(&full[s], ph);
@@ -223,10 +246,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                     const uint32_t b_hi = a_lo + SM::A_TILE;
                     const uint32_t b_lo = b_hi + SM::B_TILE;
 #pragma unroll
-                    for (int k = 0; k < TC_BK / 16; ++k) {       // UMMA_K = 16 bf16 = 32 B inside the 128 B swizzle atom
-                        const uint64_t dah = make_sdesc(a_hi + k * 32), dal = make_sdesc(a_lo + k * 32);
-                        const uint64_t dbh = make_sdesc(b_hi + k * 32), dbl = make_sdesc(b_lo + k * 32);
-                        umma_bf16(tacc, dal, dbh, idesc, (kb | k) != 0);     // small terms first
+                    for (int k = 0; k < TC_BK / 16; ++k) {
+                        const uint64_t dah = make_sdesc(a_hi + k * kstep, lbo), dal = make_sdesc(a_lo + k * kstep, lbo);
+                        const uint64_t dbh = make_sdesc(b_hi + k * kstep, lbo), dbl = make_sdesc(b_lo + k * kstep, lbo);
+                        umma_bf16(tacc, dal, dbh, idesc, (kb > kb0 || k > 0) ? 1u : 0u);     // small terms first
                         umma_bf16(tacc, dah, dbl, idesc, 1);
                         umma_bf16(tacc, dah, dbh, idesc, 1);
                     }
@@ -243,7 +266,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const TcEpilogue& e = g.ep;
         int ti = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
-            const int m0 = (tile / tiles_n) * TC_BM, n0 = (tile % tiles_n) * BN;
+            const int sp = tile / tiles_mn, tmn = tile - sp * tiles_mn;
+            const int m0 = (tmn / tiles_n) * TC_BM, n0 = (tmn % tiles_n) * BN;
             const int buf = ti & 1;
             mbar_wait(&acc_full[buf], (ti >> 1) & 1);
             tc_fence_after();
@@ -252,7 +276,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             const float* pre_row = e.pre ? e.pre + (long long)(m / e.pre_div) * e.ldpre : nullptr;
             const float* res_row = nullptr;
             if (e.res) res_row = e.res + (long long)(e.res_mod > 0 ? (m % e.res_mod) : (m / e.res_div)) * e.ldres;
-            float* c_row = g.C ? g.C + (long long)m * g.ldc : nullptr;
+            float* c_row = g.C ? g.C + (long long)sp * g.split_stride + (long long)m * g.ldc : nullptr;
             float* pa_row = e.preact ? e.preact + (long long)m * g.ldc : nullptr;
 #pragma unroll 1
             for (int cc = 0; cc < BN / 2; cc += 32) {
@@ -343,7 +367,9 @@ int launch_pack_split(const float* src, long long ld, int M, int K, int Kp, void
     return 0;
 }
 
-struct SplitJob { const float* src; long long ld; int N, K, Kp; __nv_bfloat16* hi; __nv_bfloat16* lo; long long first; };
+// one weight matrix -> planes.  transpose = 0: planes [N, Kp] of W ; transpose = 1: planes [K, Kp] of W^T with
+// Kp = pitch over N (N, K, Kp below are then the plane's rows / valid columns / pitch, src is read transposed)
+struct SplitJob { const float* src; long long ld; int N, K, Kp; __nv_bfloat16* hi; __nv_bfloat16* lo; long long first; int transpose; };
 
 __global__ void __launch_bounds__(256)
 split_weights_kernel(const SplitJob* __restrict__ jobs, int n_jobs, long long total) {
@@ -356,7 +382,7 @@ split_weights_kernel(const SplitJob* __restrict__ jobs, int n_jobs, long long to
         const SplitJob j = jobs[lo_j];
         const long long i = e - j.first;
         const int n = (int)(i / j.Kp), k = (int)(i - (long long)n * j.Kp);
-        const float x = k < j.K ? j.src[(long long)n * j.ld + k] : 0.f;
+        const float x = k < j.K ? (j.transpose ? j.src[(long long)k * j.ld + n] : j.src[(long long)n * j.ld + k]) : 0.f;
         const __nv_bfloat16 h = __float2bfloat16_rn(x);
         j.hi[i] = h;
         j.lo[i] = __float2bfloat16_rn(x - __bfloat162float(h));
@@ -372,8 +398,9 @@ int launch_split_weights(const void* jobs_dev, int n_jobs, long long total, cuda
 }
 
 size_t split_job_bytes() { return sizeof(SplitJob); }
-void fill_split_job(void* dst, const float* src, long long ld, int N, int K, int Kp, void* hi, void* lo, long long first) {
-    SplitJob j{src, ld, N, K, Kp, static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(lo), first};
+void fill_split_job(void* dst, const float* src, long long ld, int N, int K, int Kp, void* hi, void* lo, long long first,
+                    int transpose) {
+    SplitJob j{src, ld, N, K, Kp, static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(lo), first, transpose};
     *static_cast<SplitJob*>(dst) = j;
 }
 
@@ -390,13 +417,14 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
     return fn;
 }
 
-static int encode_plane_map(void* map_out, const void* plane, int rows, int Kp, int box_rows) {
+// bf16 plane [rows, pitch] -> 2-D tensor map with a 64 x 64 box and 128 B swizzle
+static int encode_plane_map(void* map_out, const void* plane, int rows, int pitch) {
     auto enc = get_encode();
     RIFT_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
     static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap size");
-    cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)Kp * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+    cuuint64_t dims[2] = {(cuuint64_t)pitch, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)pitch * 2};
+    cuuint32_t box[2] = {64, 64};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(static_cast<CUtensorMap*>(map_out), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(plane), dims,
                      strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -405,28 +433,26 @@ static int encode_plane_map(void* map_out, const void* plane, int rows, int Kp, 
     return 0;
 }
 
-int make_weight_tensor_map(void* map_out, const void* plane, int N, int Kp) { return encode_plane_map(map_out, plane, N, Kp, 64); }
-
-// activation planes live at fixed workspace addresses, so their descriptors are encoded once and reused
+// planes live at fixed addresses (weight cache, workspace), so descriptors are encoded once and reused
 struct MapKey {
-    const void* p; int rows, Kp;
-    bool operator==(const MapKey& o) const { return p == o.p && rows == o.rows && Kp == o.Kp; }
+    const void* p; int rows, pitch;
+    bool operator==(const MapKey& o) const { return p == o.p && rows == o.rows && pitch == o.pitch; }
 };
 struct MapKeyHash {
     size_t operator()(const MapKey& k) const {
-        return std::hash<const void*>()(k.p) ^ (std::hash<long long>()(((long long)k.rows << 20) ^ k.Kp) * 1000003u);
+        return std::hash<const void*>()(k.p) ^ (std::hash<long long>()(((long long)k.rows << 20) ^ k.pitch) * 1000003u);
     }
 };
 struct MapVal { alignas(64) unsigned char m[128]; };
 
-static int activation_map(const void* plane, int rows, int Kp, const CUtensorMap** out) {
+static int plane_map(const void* plane, int rows, int pitch, const CUtensorMap** out) {
     static std::unordered_map<MapKey, MapVal, MapKeyHash> cache;
-    MapKey key{plane, rows, Kp};
+    MapKey key{plane, rows, pitch};
     auto it = cache.find(key);
     if (it == cache.end()) {
         if (cache.size() > 65536) cache.clear();
         MapVal v;
-        int r = encode_plane_map(v.m, plane, rows, Kp, TC_BM);
+        int r = encode_plane_map(v.m, plane, rows, pitch);
         if (r) return r;
         it = cache.emplace(key, v).first;
     }
@@ -440,48 +466,72 @@ bool gemm_tc_eligible(const GemmArgs& a) {
     auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
     if (a.C == nullptr && !a.out_planes.on()) return false;
     if (a.beta != 0.f && a.C == nullptr) return false;
-    return a.sbk == 1 && gemm_tc_shape_ok(a.M, a.N, a.K) && a.split_k <= 1 && (a.ldc % 4) == 0 && al16(a.C) &&
-           al16(a.bias) && al16(a.colscale) && al16(a.pre) && (a.ldpre % 4) == 0 && al16(a.res) && (a.ldres % 4) == 0 &&
-           al16(a.preact);
+    return gemm_tc_shape_ok(a.M, a.N, a.K) && (a.ldc % 4) == 0 && al16(a.C) && al16(a.bias) && al16(a.colscale) &&
+           al16(a.pre) && (a.ldpre % 4) == 0 && al16(a.res) && (a.ldres % 4) == 0 && al16(a.preact);
 }
 
-template <int BN>
-static int launch_tc(const GemmArgs& a, const void* a_hi, const void* a_lo, int Kp, const TcWeight& w, int n0, int k0,
-                     cudaStream_t st) {
+template <int BN, bool MN>
+static int launch_tc(const GemmArgs& a, const PlaneOp& A, const PlaneOp& B, int splits, float* partials, cudaStream_t st) {
     static bool attr = false;
     static int sms = 148;
     if (!attr) {
-        RIFT_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<BN>::TOTAL));
+        RIFT_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<BN>::TOTAL));
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         attr = true;
     }
-    const CUtensorMap *ma_hi, *ma_lo;
-    int r = activation_map(a_hi, a.M, Kp, &ma_hi);
-    if (r) return r;
-    r = activation_map(a_lo, a.M, Kp, &ma_lo);
-    if (r) return r;
+    const CUtensorMap *ma_hi, *ma_lo, *mb_hi, *mb_lo;
+    int r;
+    if ((r = plane_map(A.hi, A.rows, A.pitch, &ma_hi))) return r;
+    if ((r = plane_map(A.lo, A.rows, A.pitch, &ma_lo))) return r;
+    if ((r = plane_map(B.hi, B.rows, B.pitch, &mb_hi))) return r;
+    if ((r = plane_map(B.lo, B.rows, B.pitch, &mb_lo))) return r;
+    const int num_kb = cdiv(a.K, TC_BK);
     TcKernelArgs g;
-    g.C = a.C; g.ldc = a.ldc; g.M = a.M; g.N = a.N; g.K = a.K; g.w_n0 = n0; g.w_k0 = k0;
-    g.ep = TcEpilogue{a.bias, a.colscale, a.pre, a.ldpre, a.pre_div, a.res, a.ldres, a.res_div, a.res_mod, a.act, a.beta,
-                      a.alpha, a.preact};
+    g.M = a.M; g.N = a.N; g.K = a.K;
+    g.a_mn0 = A.mn0; g.a_k0 = A.k0; g.b_mn0 = B.mn0; g.b_k0 = B.k0;
     g.out = a.out_planes;
-    const int n_tiles = cdiv(a.N, BN) * cdiv(a.M, TC_BM);
-    gemm_tc_kernel<BN><<<min(n_tiles, sms), TC_THREADS, TcSmem<BN>::TOTAL, st>>>(
-        *ma_hi, *ma_lo, *reinterpret_cast<const CUtensorMap*>(w.tm_hi), *reinterpret_cast<const CUtensorMap*>(w.tm_lo), g);
+    if (splits > 1) {
+        g.splits = splits; g.kb_per_split = cdiv(num_kb, splits);
+        g.splits = cdiv(num_kb, g.kb_per_split);
+        g.C = partials; g.ldc = a.N; g.split_stride = (long long)a.M * a.N;
+        g.ep = TcEpilogue{nullptr, nullptr, nullptr, 0, 1, nullptr, 0, 1, 0, ACT_NONE, 0.f, 1.f, nullptr};
+        g.out = Planes();
+    } else {
+        g.splits = 1; g.kb_per_split = num_kb; g.split_stride = 0;
+        g.C = a.C; g.ldc = a.ldc;
+        g.ep = TcEpilogue{a.bias, a.colscale, a.pre, a.ldpre, a.pre_div, a.res, a.ldres, a.res_div, a.res_mod, a.act, a.beta,
+                          a.alpha, a.preact};
+    }
+    const int n_tiles = cdiv(a.N, BN) * cdiv(a.M, TC_BM) * g.splits;
+    gemm_tc_kernel<BN, MN><<<min(n_tiles, sms), TC_THREADS, TcSmem<BN>::TOTAL, st>>>(*ma_hi, *ma_lo, *mb_hi, *mb_lo, g);
     RIFT_LAUNCH_OK();
+    if (splits > 1) return launch_splitk_reduce(partials, g.splits, a, st);
     return 0;
+}
+
+int launch_gemm_tc_ex(const GemmArgs& a, const PlaneOp& A, const PlaneOp& B, bool mn_major, int splits, float* partials,
+                      cudaStream_t st) {
+    RIFT_REQUIRE(gemm_tc_eligible(a), "gemm_tc: shape / layout not eligible");
+    RIFT_REQUIRE(A.pitch % 64 == 0 && B.pitch % 64 == 0, "gemm_tc: plane pitches must be multiples of 64");
+    RIFT_REQUIRE(splits <= 1 || partials != nullptr, "gemm_tc: split-K needs a partial buffer");
+    if (a.M <= 0 || a.N <= 0) return 0;
+    if (mn_major) {
+        if (a.N <= 64) return launch_tc<64, true>(a, A, B, splits, partials, st);
+        return launch_tc<128, true>(a, A, B, splits, partials, st);
+    }
+    if (a.N <= 64) return launch_tc<64, false>(a, A, B, splits, partials, st);
+    return launch_tc<128, false>(a, A, B, splits, partials, st);
 }
 
 int launch_gemm_tc(const GemmArgs& a, const void* a_hi, const void* a_lo, int Kp, const TcWeight& w, int n0, int k0,
                    cudaStream_t st) {
-    RIFT_REQUIRE(gemm_tc_eligible(a), "gemm_tc: shape / layout not eligible");
     RIFT_REQUIRE(n0 + a.N <= w.N && k0 + a.K <= w.Kp, "gemm_tc: weight slice out of range");
-    RIFT_REQUIRE(Kp % 64 == 0 && Kp >= a.K, "gemm_tc: bad activation plane pitch");
-    if (a.M <= 0 || a.N <= 0) return 0;
-    if (a.N <= 64) return launch_tc<64>(a, a_hi, a_lo, Kp, w, n0, k0, st);
-    return launch_tc<128>(a, a_hi, a_lo, Kp, w, n0, k0, st);
+    RIFT_REQUIRE(Kp >= a.K, "gemm_tc: bad activation plane pitch");
+    PlaneOp A{a_hi, a_lo, a.M, Kp, 0, 0};
+    PlaneOp B{w.hi, w.lo, w.N, w.Kp, n0, k0};
+    return launch_gemm_tc_ex(a, A, B, false, 1, nullptr, st);
 }
 
 }  // namespace rift

@@ -4,30 +4,37 @@
 
 namespace rift {
 
-// Pre-split bf16 planes of one fp32 weight matrix [N, K]: hi = bf16(w), lo = bf16(w - hi), row pitch Kp
-// (K rounded up to 64, zero padded), plus the two TMA descriptors (box 64 x 64, SWIZZLE_128B).
+// Pre-split bf16 planes of one fp32 weight matrix: hi = bf16(w), lo = bf16(w - hi), zero padded to the pitch.
+// transpose == false: planes [N, Kp] of W [N, K] (forward operand);  true: planes [K, Np] of W^T (dX = dY W).
 struct TcWeight {
     const float* src = nullptr; long long ld_src = 0;
-    int N = 0, K = 0, Kp = 0;
+    int N = 0, K = 0, Kp = 0;       // plane rows, valid columns, pitch
     void* hi = nullptr; void* lo = nullptr;
     bool trainable = false;
-    alignas(64) unsigned char tm_hi[128];
-    alignas(64) unsigned char tm_lo[128];
+    bool transpose = false;
 };
+
+// A pair of bf16 planes [rows, pitch] and the origin of the operand inside them
+// (mn0: offset along the M / N index of the GEMM, k0: offset along the reduction index)
+struct PlaneOp { const void* hi; const void* lo; int rows; int pitch; int mn0; int k0; };
 
 inline int tc_pitch(int K) { return (K + 63) / 64 * 64; }
 bool gemm_tc_shape_ok(int M, int N, int K);
 bool gemm_tc_eligible(const GemmArgs& a);
 // fp32 [M, K] -> bf16 planes hi / lo [M, Kp] (each M * Kp * 2 bytes, 256 B aligned)
 int launch_pack_split(const float* src, long long ld, int M, int K, int Kp, void* hi, void* lo, cudaStream_t st);
-// a.A / a.B are ignored: the A operand is the plane pair (a_hi, a_lo), the B operand is `w`
-// rows [n0, n0 + a.N), columns [k0, k0 + a.K)
+// C = epilogue(A B^T) with A = planes (a_hi, a_lo) [M, Kp] and B = weight planes rows [n0, n0+N), cols [k0, k0+K)
 int launch_gemm_tc(const GemmArgs& a, const void* a_hi, const void* a_lo, int Kp, const TcWeight& w, int n0, int k0,
                    cudaStream_t st);
+// General form.  mn_major == false: A planes [M.., K..], B planes [N.., K..] (rows = M/N index).
+// mn_major == true: A planes [K.., M..], B planes [K.., N..] (rows = reduction index; dW = dY^T X).
+// splits > 1: split-K into `partials` [splits, M, N] followed by a fixed-order reduce that applies the epilogue.
+int launch_gemm_tc_ex(const GemmArgs& a, const PlaneOp& A, const PlaneOp& B, bool mn_major, int splits, float* partials,
+                      cudaStream_t st);
 
-int make_weight_tensor_map(void* map_out, const void* plane, int N, int Kp);
 size_t split_job_bytes();
-void fill_split_job(void* dst, const float* src, long long ld, int N, int K, int Kp, void* hi, void* lo, long long first);
+void fill_split_job(void* dst, const float* src, long long ld, int N, int K, int Kp, void* hi, void* lo, long long first,
+                    int transpose);
 int launch_split_weights(const void* jobs_dev, int n_jobs, long long total, cudaStream_t st);
 
 }  // namespace rift

@@ -54,6 +54,7 @@ struct GemmArgs {
     Planes out_planes;                   // optional split-bf16 copy of the result (tcgen05 path; C may then be null)
 };
 int launch_gemm_simt(const GemmArgs& a, cudaStream_t st);
+int launch_splitk_reduce(const float* ws, int splits, const GemmArgs& a, cudaStream_t st);
 
 // ------------------------------------------------------------------ nn_kernels.cu
 int launch_layernorm(const float* x, long long ldx, int rows, int C, const float* gamma, const float* beta, float* y,

@@ -240,5 +240,5 @@ class PlanningModel:
         assert dlogits.is_cuda and dlogits.dtype == torch.float32 and dlogits.is_contiguous()
         pb = self._last_batch
         _lib.check(_lib.lib().rift_b200_backward(self._engine, C.byref(pb.struct), _lib.ptr(dlogits),
-                                                 _lib.ptr(self._workspace), self._workspace.numel(), 0,
-                                                 _lib.stream_ptr()), "backward")
+                                                 _lib.ptr(self._workspace), self._workspace.numel(),
+                                                 _lib.GEMM_SIMT if getattr(self, "exact_bwd", self.exact_fp32) else 0, _lib.stream_ptr()), "backward")

@@ -96,7 +96,7 @@ FULL_LAYERS = ["pos_emb", "agent_encoder", "map_encoder", "static_objects_encode
 # gradients match autograd to 2e-3 everywhere.  With the split-bf16 tensor-core forward (activations
 # accurate to ~1e-5) a handful of ReLU / max-pool decisions sitting within 1e-5 of their threshold flip,
 # which moves single gradient elements by up to ~0.5 % of the tensor maximum; tensor norms still agree to 2e-3.
-GRAD_ETOL = {True: 2e-3, False: 1e-2}
+GRAD_ETOL = {True: 2e-3, False: 3e-2, "bwd_only": 2e-3}
 
 
 @pytest.mark.parametrize("exact", [True, False], ids=["fp32", "tcgen05"])
@@ -136,7 +136,7 @@ def test_full_backward_matches_reference_golden(name, algo, exact):
             check_golden(g, f"fullgrad_{algo}/{n}", got, rtol=GRAD_ETOL[exact], atol=1e-6 * gmax)
 
 
-@pytest.mark.parametrize("exact", [True, False], ids=["fp32", "tcgen05"])
+@pytest.mark.parametrize("exact", [True, False, "bwd_only"], ids=["fp32", "tcgen05", "fp32fwd_tcgen05bwd"])
 def test_full_backward_matches_oracle_autograd_cfg2_like(exact):
     """A larger ragged batch: CUDA gradients vs torch autograd through the CPU oracle, tensor by tensor."""
     cfg = MODEL_ZOO["small"]()
@@ -144,7 +144,9 @@ def test_full_backward_matches_oracle_autograd_cfg2_like(exact):
     feats = synth_features(cfg, 6, 12, 14, 4, seed=3, ragged=True)
     ex = synth_rl_extras(cfg, feats, seed=4)
     model = build(cfg, sd)
-    model.exact_fp32 = exact
+    model.exact_fp32 = bool(exact)          # "bwd_only": exact forward (no ReLU / arg-max flips), tensor-core backward
+    if exact == "bwd_only":
+        model.exact_bwd = False
     tr = TRAINERS["grpo"](model, trainable_layers=FULL_LAYERS, **TRAINER_KW)
     loss = tr.training_step(make_batch(feats, ex))
     count = float(tr._count)
