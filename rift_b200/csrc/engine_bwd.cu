@@ -270,15 +270,15 @@ int rift_b200_engine::backward(const rift_b200_batch& bt, const float* dlogits, 
             TRY(launch_masked_gather_rows(dX, D, A, Mp, S, nullptr, NP, D, dx_poly, 0, c.st));
             TRY(launch_masked_gather_rows(dX, D, A, Mp, S, bt.map_polygon_has_speed_limit, NP, D, dx_speed, 0, c.st));
             if (m.map_type_emb.train)
-                TRY(launch_embedding_bwd(dX, D, A, Mp, S, bt.map_polygon_type, NP, D, 3, m.map_type_emb.d, 0, c.st));
+                TRY(launch_embedding_bwd(dX, D, A, Mp, S, bt.map_polygon_type, NP, D, 3, m.map_type_emb.d, 0, esc, c.st));
             if (m.map_route_emb.train)
                 TRY(launch_embedding_bwd(dX, D, A, Mp, S, reinterpret_cast<const int8_t*>(bt.map_polygon_on_route), NP, D, 2,
-                                         m.map_route_emb.d, 0, c.st));
+                                         m.map_route_emb.d, 0, esc, c.st));
             if (m.map_tl_emb.train)
-                TRY(launch_embedding_bwd(dX, D, A, Mp, S, bt.map_polygon_tl_status, NP, D, 4, m.map_tl_emb.d, 0, c.st));
+                TRY(launch_embedding_bwd(dX, D, A, Mp, S, bt.map_polygon_tl_status, NP, D, 4, m.map_tl_emb.d, 0, esc, c.st));
             if (m.map_unknown_emb.train)
                 TRY(launch_embedding_bwd(dX, D, A, Mp, S, reinterpret_cast<const int8_t*>(bt.map_polygon_has_speed_limit), NP, D, 1,
-                                         m.map_unknown_emb.d, 1, c.st));
+                                         m.map_unknown_emb.d, 1, esc, c.st));
         }
         TRY(points_bwd(c, tp.poly, m.poly_enc, dx_poly));
         TRY(fourier_bwd(c, tp.speed, m.speed_emb, dx_speed));
@@ -292,7 +292,7 @@ int rift_b200_engine::backward(const rift_b200_batch& bt, const float* dlogits, 
             TRY(launch_masked_gather_rows(dX, D, 0, A, S, tp.agent_any, NA, D, dx_hist, 1, c.st));     // token 0 is the ego embedding
             TRY(launch_masked_gather_rows(dX, D, 0, 1, S, nullptr, bs, D, dx_ego, 0, c.st));
             if (m.agent_type_emb.train)
-                TRY(launch_embedding_bwd(dX, D, 0, A, S, bt.agent_category, NA, D, 4, m.agent_type_emb.d, 0, c.st));
+                TRY(launch_embedding_bwd(dX, D, 0, A, S, bt.agent_category, NA, D, 4, m.agent_type_emb.d, 0, esc, c.st));
         }
         // ---- StateAttentionEncoder
         {

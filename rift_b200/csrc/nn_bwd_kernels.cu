@@ -22,11 +22,35 @@ __device__ __forceinline__ long long attn_row_b(int b, int inner_n, long long ou
 // query (q_outer = 0, o_custom) dQ is written per batch row of `dq` using the OUTPUT mapping.
 // =====================================================================================
 template <int HD>
+__device__ __forceinline__ float dot_bcast(const float (&r)[HD], const float* __restrict__ s) {
+    const float4* s4 = reinterpret_cast<const float4*>(s);          // broadcast 16-byte shared loads
+    float a = 0.f;
+#pragma unroll
+    for (int d = 0; d < HD / 4; ++d) {
+        const float4 t = s4[d];
+        a = fmaf(r[4 * d], t.x, a); a = fmaf(r[4 * d + 1], t.y, a); a = fmaf(r[4 * d + 2], t.z, a); a = fmaf(r[4 * d + 3], t.w, a);
+    }
+    return a;
+}
+template <int HD>
+__device__ __forceinline__ void axpy_bcast(float (&acc)[HD], float w, const float* __restrict__ s) {
+    const float4* s4 = reinterpret_cast<const float4*>(s);
+#pragma unroll
+    for (int d = 0; d < HD / 4; ++d) {
+        const float4 t = s4[d];
+        acc[4 * d] = fmaf(w, t.x, acc[4 * d]); acc[4 * d + 1] = fmaf(w, t.y, acc[4 * d + 1]);
+        acc[4 * d + 2] = fmaf(w, t.z, acc[4 * d + 2]); acc[4 * d + 3] = fmaf(w, t.w, acc[4 * d + 3]);
+    }
+}
+
+// The thread's own row (query in phase A, key in phase B) lives in registers; the other operand is read from
+// shared memory with warp-wide broadcast loads, so there are no bank conflicts.
+template <int HD>
 __global__ void __launch_bounds__(128)
 attention_bwd_kernel(AttnArgs a, const float* __restrict__ d_o, long long lddo, float* __restrict__ dq, long long lddq,
                      float* __restrict__ dk, float* __restrict__ dv, long long lddk, long long lddv) {
-    extern __shared__ float sm[];
-    float* Qs = sm;                                  // [Sq][HD]
+    extern __shared__ __align__(16) float sm[];
+    float* Qs = sm;                                  // [Sq][HD]  (pre-scaled)
     float* dOs = Qs + (size_t)a.Sq * HD;             // [Sq][HD]
     float* Ks = dOs + (size_t)a.Sq * HD;             // [Sk][HD]
     float* Vs = Ks + (size_t)a.Sk * HD;              // [Sk][HD]
@@ -45,67 +69,55 @@ attention_bwd_kernel(AttnArgs a, const float* __restrict__ d_o, long long lddo, 
     }
     for (int e = threadIdx.x; e < a.Sq * HD; e += blockDim.x) {
         const int i = e / HD, d = e - i * HD;
-        Qs[e] = a.q[(qrow0 + (long long)i * a.q_seq) * a.ldq + h * HD + d] * a.scale;     // pre-scaled q
+        Qs[e] = a.q[(qrow0 + (long long)i * a.q_seq) * a.ldq + h * HD + d] * a.scale;
         dOs[e] = d_o[(orow0 + (long long)i * oseq) * lddo + h * HD + d];
     }
     for (int i = threadIdx.x; i < a.Sq; i += blockDim.x) lse_s[i] = a.lse[((long long)b * a.H + h) * a.Sq + i];
     __syncthreads();
     const uint8_t* kpm = a.kpm ? a.kpm + (long long)(a.kpm_mod > 0 ? b % a.kpm_mod : b / a.kpm_div) * a.Sk : nullptr;
-    // ---- phase A
+    // ---- phase A: thread = query i
     for (int i = threadIdx.x; i < a.Sq; i += blockDim.x) {
         const float lse = lse_s[i];
+        float q[HD], go[HD], acc[HD];
+#pragma unroll
+        for (int d = 0; d < HD; ++d) { q[d] = Qs[i * HD + d]; go[d] = dOs[i * HD + d]; acc[d] = 0.f; }
         float dl = 0.f;
         if (lse != INFINITY) {
             for (int j = 0; j < a.Sk; ++j) {
                 if (kpm && kpm[j]) continue;
-                float s = 0.f, dp = 0.f;
-#pragma unroll
-                for (int d = 0; d < HD; ++d) { s = fmaf(Qs[i * HD + d], Ks[j * HD + d], s); dp = fmaf(dOs[i * HD + d], Vs[j * HD + d], dp); }
-                dl += __expf(s - lse) * dp;
+                dl += __expf(dot_bcast<HD>(q, Ks + j * HD) - lse) * dot_bcast<HD>(go, Vs + j * HD);
+            }
+            for (int j = 0; j < a.Sk; ++j) {
+                if (kpm && kpm[j]) continue;
+                const float ds = __expf(dot_bcast<HD>(q, Ks + j * HD) - lse) * (dot_bcast<HD>(go, Vs + j * HD) - dl);
+                axpy_bcast<HD>(acc, ds, Ks + j * HD);
             }
         }
         delta[i] = dl;
-        float acc[HD];
-#pragma unroll
-        for (int d = 0; d < HD; ++d) acc[d] = 0.f;
-        if (lse != INFINITY) {
-            for (int j = 0; j < a.Sk; ++j) {
-                if (kpm && kpm[j]) continue;
-                float s = 0.f, dp = 0.f;
-#pragma unroll
-                for (int d = 0; d < HD; ++d) { s = fmaf(Qs[i * HD + d], Ks[j * HD + d], s); dp = fmaf(dOs[i * HD + d], Vs[j * HD + d], dp); }
-                const float ds = __expf(s - lse) * (dp - dl);
-#pragma unroll
-                for (int d = 0; d < HD; ++d) acc[d] = fmaf(ds, Ks[j * HD + d], acc[d]);
-            }
-        }
         const long long dr = a.o_custom ? (orow0 + (long long)i * oseq) : (qrow0 + (long long)i * a.q_seq);
 #pragma unroll
         for (int d = 0; d < HD; ++d) dq[dr * lddq + h * HD + d] = acc[d] * a.scale;
     }
     __syncthreads();
-    // ---- phase B
+    // ---- phase B: thread = key j
     for (int j = threadIdx.x; j < a.Sk; j += blockDim.x) {
-        float ak[HD], av[HD];
+        float kr[HD], vr[HD], ak[HD], av[HD];
 #pragma unroll
-        for (int d = 0; d < HD; ++d) { ak[d] = 0.f; av[d] = 0.f; }
+        for (int d = 0; d < HD; ++d) { kr[d] = Ks[j * HD + d]; vr[d] = Vs[j * HD + d]; ak[d] = 0.f; av[d] = 0.f; }
         if (!(kpm && kpm[j])) {
             for (int i = 0; i < a.Sq; ++i) {
                 const float lse = lse_s[i];
                 if (lse == INFINITY) continue;
-                float s = 0.f, dp = 0.f;
-#pragma unroll
-                for (int d = 0; d < HD; ++d) { s = fmaf(Qs[i * HD + d], Ks[j * HD + d], s); dp = fmaf(dOs[i * HD + d], Vs[j * HD + d], dp); }
-                const float p = __expf(s - lse);
-                const float ds = p * (dp - delta[i]);
-#pragma unroll
-                for (int d = 0; d < HD; ++d) { av[d] = fmaf(p, dOs[i * HD + d], av[d]); ak[d] = fmaf(ds, Qs[i * HD + d], ak[d]); }
+                const float p = __expf(dot_bcast<HD>(kr, Qs + i * HD) - lse);
+                const float ds = p * (dot_bcast<HD>(vr, dOs + i * HD) - delta[i]);
+                axpy_bcast<HD>(av, p, dOs + i * HD);
+                axpy_bcast<HD>(ak, ds, Qs + i * HD);              // Qs is pre-scaled, so dK already carries `scale`
             }
         }
         const long long r = krow0 + (long long)j * a.k_seq;
 #pragma unroll
         for (int d = 0; d < HD; ++d) {
-            dk[r * lddk + h * HD + d] = ak[d];          // Qs is pre-scaled, so dK already carries `scale`
+            dk[r * lddk + h * HD + d] = ak[d];
             dv[r * lddv + h * HD + d] = av[d];
         }
     }
@@ -366,27 +378,50 @@ int launch_modsum(const float* x, long long ldx, long long rows, int C, int mod,
     return 0;
 }
 
-// embedding tables: demb[k, c] += sum_{rows with idx == k (and keep)} dy[row, c]; idx may be int8 or a 0/1 byte mask
+// embedding tables: demb[k, c] += sum_{rows with idx == k} dy[row, c]; idx may be int8 or a 0/1 byte mask.
+// Two-stage like colsum: block (32 columns x 8 row lanes) per (column chunk, row slab, table entry k).
+// rows are addressed as dy[(row / inner) * outer_stride_rows + row % inner + row_offset]
 __global__ void __launch_bounds__(256)
-embedding_bwd_kernel(const float* __restrict__ dy, long long lddy, long long row0_stride, int inner, int outer_stride_rows,
-                     const int8_t* __restrict__ idx, long long rows, int C, float* __restrict__ demb, int invert_mask) {
-    // rows are addressed as dy[(row / inner) * outer_stride_rows + row % inner + row0_stride]
-    const int k = blockIdx.x;
-    for (int c = blockIdx.y * 256 + threadIdx.x; c < C; c += gridDim.y * 256) {
-        float a = 0.f;
-        for (long long r = 0; r < rows; ++r) {
+embedding_bwd_partial_kernel(const float* __restrict__ dy, long long lddy, long long row_offset, int inner, int outer_stride_rows,
+                             const int8_t* __restrict__ idx, long long rows, int C, int invert_mask, float* __restrict__ partial) {
+    __shared__ float sm[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + tx, k = blockIdx.z;
+    float a = 0.f;
+    if (c < C) {
+        for (long long r = blockIdx.y * 8 + ty; r < rows; r += (long long)gridDim.y * 8) {
             int v = (int)idx[r];
             if (invert_mask) v = v ? -1 : 0;            // "unknown" embedding: selected where the mask is 0
-            if (v == k) a += dy[((r / inner) * outer_stride_rows + (r % inner) + row0_stride) * lddy + c];
+            if (v == k) a += dy[((r / inner) * outer_stride_rows + (r % inner) + row_offset) * lddy + c];
         }
-        demb[(long long)k * C + c] += a;
+    }
+    sm[ty][tx] = a;
+    __syncthreads();
+    if (ty == 0 && c < C) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += sm[i][tx];
+        partial[((long long)k * gridDim.y + blockIdx.y) * C + c] = s;
+    }
+}
+__global__ void embedding_bwd_final_kernel(const float* __restrict__ partial, int slabs, int C, int n_emb, float* __restrict__ demb) {
+    FOR_GRID(e, (long long)n_emb * C) {
+        const int c = (int)(e % C);
+        const int k = (int)(e / C);
+        float a = 0.f;
+        for (int s = 0; s < slabs; ++s) a += partial[((long long)k * slabs + s) * C + c];
+        demb[e] += a;
     }
 }
 int launch_embedding_bwd(const float* dy, long long lddy, long long row_offset, int inner, int outer_stride_rows,
-                         const int8_t* idx, long long rows, int C, int n_emb, float* demb, int invert_mask, cudaStream_t st) {
+                         const int8_t* idx, long long rows, int C, int n_emb, float* demb, int invert_mask, float* scratch,
+                         cudaStream_t st) {
     if (rows <= 0) return 0;
-    embedding_bwd_kernel<<<dim3(n_emb, cdiv(C, 256)), 256, 0, st>>>(dy, lddy, row_offset, inner, outer_stride_rows, idx, rows, C,
-                                                                   demb, invert_mask);
+    const int slabs = (int)max(1LL, min(148LL / n_emb, (rows + 63) / 64));
+    embedding_bwd_partial_kernel<<<dim3(cdiv(C, 32), slabs, n_emb), 256, 0, st>>>(dy, lddy, row_offset, inner, outer_stride_rows,
+                                                                                 idx, rows, C, invert_mask, scratch);
+    RIFT_LAUNCH_OK();
+    embedding_bwd_final_kernel<<<GRID1D((long long)n_emb * C, 256), 256, 0, st>>>(scratch, slabs, C, n_emb, demb);
     RIFT_LAUNCH_OK();
     return 0;
 }

@@ -137,6 +137,9 @@ partial_reduce_accumulate_kernel(const float* __restrict__ partial, int nb, long
 
 int layernorm_bwd_scratch_floats(int C) { return LNB_BLOCKS * 2 * C; }
 
+__global__ void colsum_final_kernel(const float* __restrict__ partial, int nb, long long stride, int C, float* __restrict__ out,
+                                    int accumulate);
+
 int launch_layernorm_bwd(const float* x, long long ldx, const float* dy, long long lddy, int rows, int C,
                          const float* gamma, const float* mean, const float* rstd, const float* y_for_relu, long long ldy,
                          float* dx, long long lddx, int dx_accumulate, float* dgamma, float* dbeta, float* scratch,
@@ -156,32 +159,69 @@ int launch_layernorm_bwd(const float* x, long long ldx, const float* dy, long lo
                                                 dx_accumulate, dgamma ? scratch : nullptr);
     RIFT_LAUNCH_OK();
     if (dgamma) {
-        partial_reduce_accumulate_kernel<<<cdiv(C, 256), 256, 0, st>>>(scratch, nb, 2LL * C, C, dgamma, 1);
+        colsum_final_kernel<<<cdiv(C, 32), 256, 0, st>>>(scratch, nb, 2LL * C, C, dgamma, 1);
         RIFT_LAUNCH_OK();
-        partial_reduce_accumulate_kernel<<<cdiv(C, 256), 256, 0, st>>>(scratch + C, nb, 2LL * C, C, dbeta, 1);
+        colsum_final_kernel<<<cdiv(C, 32), 256, 0, st>>>(scratch + C, nb, 2LL * C, C, dbeta, 1);
         RIFT_LAUNCH_OK();
     }
     return 0;
 }
 
 // ---- column sum (bias gradients): out[c] (+)= sum_r x[r, c], two-stage deterministic
-constexpr int COLSUM_BLOCKS = 148;
+// block (32 columns x 8 row lanes): blockIdx.x = 32-column chunk, blockIdx.y = row slab; each warp reads
+// 128 contiguous bytes of a row, four independent accumulators per thread keep loads in flight.
+// scratch: [slabs][C] with slabs <= 148 (callers size it 148 * C).
 __global__ void __launch_bounds__(256)
 colsum_partial_kernel(const float* __restrict__ x, long long ldx, int rows, int C, float* __restrict__ partial) {
-    // block b owns rows b, b+grid, ...; thread t owns columns t, t+256, ...
-    for (int c = threadIdx.x; c < C; c += 256) {
-        float a = 0.f;
-        for (int r = blockIdx.x; r < rows; r += gridDim.x) a += x[(long long)r * ldx + c];
-        partial[(long long)blockIdx.x * C + c] = a;
+    __shared__ float sm[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + tx;
+    const int stride = gridDim.y * 8;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    if (c < C) {
+        int r = blockIdx.y * 8 + ty;
+        for (; r + 3 * stride < rows; r += 4 * stride) {
+            a0 += x[(long long)r * ldx + c];
+            a1 += x[(long long)(r + stride) * ldx + c];
+            a2 += x[(long long)(r + 2 * stride) * ldx + c];
+            a3 += x[(long long)(r + 3 * stride) * ldx + c];
+        }
+        for (; r < rows; r += stride) a0 += x[(long long)r * ldx + c];
+    }
+    sm[ty][tx] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    if (ty == 0 && c < C) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += sm[i][tx];
+        partial[(long long)blockIdx.y * C + c] = s;
+    }
+}
+// out[c] (+)= sum over nb partial rows, 8 row lanes per column, fixed order
+__global__ void __launch_bounds__(256)
+colsum_final_kernel(const float* __restrict__ partial, int nb, long long stride, int C, float* __restrict__ out, int accumulate) {
+    __shared__ float sm[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + tx;
+    float a = 0.f;
+    if (c < C) for (int b = ty; b < nb; b += 8) a += partial[(long long)b * stride + c];
+    sm[ty][tx] = a;
+    __syncthreads();
+    if (ty == 0 && c < C) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += sm[i][tx];
+        out[c] = accumulate ? out[c] + s : s;
     }
 }
 int launch_colsum(const float* x, long long ldx, int rows, int C, float* out, int accumulate, float* scratch,
                   cudaStream_t st) {
     if (C <= 0) return 0;
-    const int nb = max(1, min(rows, COLSUM_BLOCKS));
-    colsum_partial_kernel<<<nb, 256, 0, st>>>(x, ldx, rows, C, scratch);
+    const int chunks = cdiv(C, 32);
+    int slabs = max(1, min(148, min(cdiv(rows, 32), cdiv(148 * 4, chunks))));
+    colsum_partial_kernel<<<dim3(chunks, slabs), 256, 0, st>>>(x, ldx, rows, C, scratch);
     RIFT_LAUNCH_OK();
-    partial_reduce_accumulate_kernel<<<cdiv(C, 256), 256, 0, st>>>(scratch, nb, C, C, out, accumulate);
+    colsum_final_kernel<<<chunks, 256, 0, st>>>(scratch, slabs, C, C, out, accumulate);
     RIFT_LAUNCH_OK();
     return 0;
 }
@@ -222,14 +262,24 @@ attention_kernel(AttnArgs a) {
         for (int j = 0; j < a.Sk; ++j) {
             if (kpm && kpm[j]) continue;
             float s = 0.f;
+            const float4* k4 = reinterpret_cast<const float4*>(Ks + j * HD);     // broadcast 16-byte shared loads
+            const float4* v4 = reinterpret_cast<const float4*>(Vs + j * HD);
 #pragma unroll
-            for (int d = 0; d < HD; ++d) s = fmaf(q[d], Ks[j * HD + d], s);
+            for (int d = 0; d < HD / 4; ++d) {
+                const float4 kk = k4[d];
+                s = fmaf(q[4 * d], kk.x, s); s = fmaf(q[4 * d + 1], kk.y, s);
+                s = fmaf(q[4 * d + 2], kk.z, s); s = fmaf(q[4 * d + 3], kk.w, s);
+            }
             const float mn = fmaxf(m, s);
             const float corr = __expf(m - mn);      // m = -inf on the first key: exp(-inf) = 0
             const float p = __expf(s - mn);
             l = l * corr + p;
 #pragma unroll
-            for (int d = 0; d < HD; ++d) acc[d] = acc[d] * corr + p * Vs[j * HD + d];
+            for (int d = 0; d < HD / 4; ++d) {
+                const float4 vv = v4[d];
+                acc[4 * d] = acc[4 * d] * corr + p * vv.x; acc[4 * d + 1] = acc[4 * d + 1] * corr + p * vv.y;
+                acc[4 * d + 2] = acc[4 * d + 2] * corr + p * vv.z; acc[4 * d + 3] = acc[4 * d + 3] * corr + p * vv.w;
+            }
             m = mn;
         }
         const float inv = l > 0.f ? 1.f / l : 0.f;

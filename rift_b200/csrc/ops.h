@@ -148,7 +148,8 @@ int launch_groupsum(const float* x, long long ldx, int groups, int n, int C, flo
                     cudaStream_t st);
 int launch_modsum(const float* x, long long ldx, long long rows, int C, int mod, float* out, int accumulate, cudaStream_t st);
 int launch_embedding_bwd(const float* dy, long long lddy, long long row_offset, int inner, int outer_stride_rows,
-                         const int8_t* idx, long long rows, int C, int n_emb, float* demb, int invert_mask, cudaStream_t st);
+                         const int8_t* idx, long long rows, int C, int n_emb, float* demb, int invert_mask, float* scratch,
+                         cudaStream_t st);
 int launch_masked_gather_rows(const float* src, long long lds, long long row_offset, int inner, int outer_stride_rows,
                               const uint8_t* keep, long long rows, int C, float* out, int zero_inner0, cudaStream_t st);
 int launch_scale_cols(float* dy, const float* colscale, long long rows, int C, cudaStream_t st);
