@@ -25,6 +25,8 @@
 #include <cudaTypedefs.h>
 #include <cuda_bf16.h>
 
+#include <stdlib.h>
+
 #include <unordered_map>
 
 #include "common.cuh"
@@ -140,6 +142,7 @@ struct TcKernelArgs {
     int splits, kb_per_split; long long split_stride;     // split-K: slab `s` writes raw sums to C + s * split_stride
     TcEpilogue ep;
     Planes out;              // optional split-bf16 copy of the result for the next GEMM (C may then be null)
+    int dbg;                 // bottleneck experiments only (RIFT_B200_TC_DBG)
 };
 
 template <int BN>
@@ -147,7 +150,8 @@ struct TcSmem {
     static constexpr int A_TILE = TC_BM * TC_BK * 2;     // bytes per bf16 plane
     static constexpr int B_TILE = BN * TC_BK * 2;
     static constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;
-    static constexpr int TOTAL = TC_STAGES * STAGE + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int EPI = TC_EPI_WARPS * 32 * 33 * 4;                 // per-warp 32 x 33 fp32 transpose tiles
+    static constexpr int TOTAL = TC_STAGES * STAGE + 1024 /*align*/ + 256 /*barriers*/ + EPI;
 };
 constexpr int TC_BOX = 64 * 64 * 2;      // bytes of one 64 x 64 bf16 TMA box
 
@@ -166,6 +170,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     uint64_t* acc_full = bars + 2 * TC_STAGES;      // [2] accumulator complete (tcgen05.commit)
     uint64_t* acc_empty = bars + 2 * TC_STAGES + 2; // [2] accumulator drained (one arrival per epilogue warp)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 4);
+    float* stage_t = reinterpret_cast<float*>(smem + TC_STAGES * SM::STAGE + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_n = (g.N + BN - 1) / BN;
@@ -205,6 +210,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                     uint8_t* a_lo = a_hi + SM::A_TILE;
                     uint8_t* b_hi = a_lo + SM::A_TILE;
                     uint8_t* b_lo = b_hi + SM::B_TILE;
+                    if (g.dbg & 2) { mbar_arrive(&full[s]); continue; }
                     mbar_arrive_expect_tx(&full[s], SM::STAGE);
                     const int ka = g.a_k0 + kb * TC_BK, kbb = g.b_k0 + kb * TC_BK;
 #pragma unroll
@@ -247,6 +253,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                     const uint32_t b_lo = b_hi + SM::B_TILE;
 #pragma unroll
                     for (int k = 0; k < TC_BK / 16; ++k) {
+                        if (g.dbg & 4) break;
                         const uint64_t dah = make_sdesc(a_hi + k * kstep, lbo), dal = make_sdesc(a_lo + k * kstep, lbo);
                         const uint64_t dbh = make_sdesc(b_hi + k * kstep, lbo), dbl = make_sdesc(b_lo + k * kstep, lbo);
                         umma_bf16(tacc, dal, dbh, idesc, (kb > kb0 || k > 0) ? 1u : 0u);     // small terms first
@@ -271,47 +278,93 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             const int buf = ti & 1;
             mbar_wait(&acc_full[buf], (ti >> 1) & 1);
             tc_fence_after();
-            const int m = m0 + quarter * 32 + lane;
+            // Row phase: TMEM hands every thread one accumulator ROW; the fused epilogue math runs there with
+            // 16-byte operand loads.  Store phase: a 32 x 32 transpose through shared memory gives every lane one
+            // COLUMN, so fp32 rows leave as 128-byte and the bf16 planes as 64-byte coalesced warp stores.
+            const int mrow0 = m0 + quarter * 32;
+            const int m = mrow0 + lane;
             const bool row_ok = m < g.M;
             const float* pre_row = e.pre ? e.pre + (long long)(m / e.pre_div) * e.ldpre : nullptr;
             const float* res_row = nullptr;
             if (e.res) res_row = e.res + (long long)(e.res_mod > 0 ? (m % e.res_mod) : (m / e.res_div)) * e.ldres;
-            float* c_row = g.C ? g.C + (long long)sp * g.split_stride + (long long)m * g.ldc : nullptr;
-            float* pa_row = e.preact ? e.preact + (long long)m * g.ldc : nullptr;
+            float* c_base = g.C ? g.C + (long long)sp * g.split_stride + (long long)mrow0 * g.ldc : nullptr;
+            float* pa_base = e.preact ? e.preact + (long long)mrow0 * g.ldc : nullptr;
+            float* tbuf = stage_t + ew * (32 * 33);
+            const int rows_here = min(32, g.M - mrow0);
+            const int l16 = lane & 15;
 #pragma unroll 1
             for (int cc = 0; cc < BN / 2; cc += 32) {
                 const int c0 = half * (BN / 2) + cc;
                 uint32_t r[32];
                 tmem_ld_32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN + c0), r);
                 tmem_ld_wait();
-                if (row_ok) {
+                if (g.dbg & 1) continue;
+                const int ncol = n0 + c0 + lane;                 // this lane's column in the store phase
+                if (pa_base) {                                   // value before the activation (saved for backward)
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         const int n = n0 + c0 + j;
-                        if (n < g.N) {
-                            float4 v = make_float4(__uint_as_float(r[j]) * e.alpha, __uint_as_float(r[j + 1]) * e.alpha,
-                                                   __uint_as_float(r[j + 2]) * e.alpha, __uint_as_float(r[j + 3]) * e.alpha);
+                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (row_ok && n < g.N) {
+                            v = make_float4(__uint_as_float(r[j]) * e.alpha, __uint_as_float(r[j + 1]) * e.alpha,
+                                            __uint_as_float(r[j + 2]) * e.alpha, __uint_as_float(r[j + 3]) * e.alpha);
                             if (pre_row) { const float4 t = ld4(pre_row + n); v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
                             if (e.colscale) { const float4 t = ld4(e.colscale + n); v.x *= t.x; v.y *= t.y; v.z *= t.z; v.w *= t.w; }
                             if (e.bias) { const float4 t = ld4(e.bias + n); v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
-                            if (pa_row) *reinterpret_cast<float4*>(pa_row + n) = v;
-                            if (e.act == ACT_RELU) {
-                                v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-                            } else if (e.act == ACT_GELU) {
-                                v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
-                            }
-                            if (res_row) { const float4 t = ld4(res_row + n); v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
-                            if (e.beta != 0.f) {
-                                const float4 t = ld4(c_row + n);
-                                v.x += e.beta * t.x; v.y += e.beta * t.y; v.z += e.beta * t.z; v.w += e.beta * t.w;
-                            }
-                            if (c_row) *reinterpret_cast<float4*>(c_row + n) = v;
-                            if (g.out.on()) split4_store(g.out, m, n, v.x, v.y, v.z, v.w);
-                        } else if (g.out.on() && n < g.out.Kp) {
-                            split4_store(g.out, m, n, 0.f, 0.f, 0.f, 0.f);       // zero the pad columns [N, Kp)
+                        }
+                        tbuf[lane * 33 + j] = v.x; tbuf[lane * 33 + j + 1] = v.y; tbuf[lane * 33 + j + 2] = v.z; tbuf[lane * 33 + j + 3] = v.w;
+                    }
+                    __syncwarp();
+                    if (ncol < g.N)
+                        for (int rr = 0; rr < rows_here; ++rr) pa_base[(long long)rr * g.ldc + ncol] = tbuf[rr * 33 + lane];
+                    __syncwarp();
+                }
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const int n = n0 + c0 + j;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (row_ok && n < g.N) {
+                        v = make_float4(__uint_as_float(r[j]) * e.alpha, __uint_as_float(r[j + 1]) * e.alpha,
+                                        __uint_as_float(r[j + 2]) * e.alpha, __uint_as_float(r[j + 3]) * e.alpha);
+                        if (pre_row) { const float4 t = ld4(pre_row + n); v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
+                        if (e.colscale) { const float4 t = ld4(e.colscale + n); v.x *= t.x; v.y *= t.y; v.z *= t.z; v.w *= t.w; }
+                        if (e.bias) { const float4 t = ld4(e.bias + n); v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
+                        if (e.act == ACT_RELU) {
+                            v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+                        } else if (e.act == ACT_GELU) {
+                            v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
+                        }
+                        if (res_row) { const float4 t = ld4(res_row + n); v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
+                    }
+                    tbuf[lane * 33 + j] = v.x; tbuf[lane * 33 + j + 1] = v.y; tbuf[lane * 33 + j + 2] = v.z; tbuf[lane * 33 + j + 3] = v.w;
+                }
+                __syncwarp();
+                if (c_base && ncol < g.N) {
+                    float* cp = c_base + ncol;
+                    if (e.beta != 0.f) {
+                        for (int rr = 0; rr < rows_here; ++rr) cp[(long long)rr * g.ldc] = tbuf[rr * 33 + lane] + e.beta * cp[(long long)rr * g.ldc];
+                    } else {
+#pragma unroll 4
+                        for (int rr = 0; rr < rows_here; ++rr) cp[(long long)rr * g.ldc] = tbuf[rr * 33 + lane];
+                    }
+                }
+                if (g.out.on()) {
+                    // lanes 0-15 write the hi plane, lanes 16-31 the lo plane; two columns (one bf16x2 word) per lane.
+                    // columns >= N hold zeros in the tile, which is exactly the planes' zero padding up to Kp
+                    const int pc = n0 + c0 + 2 * l16;
+                    if (pc < g.out.Kp) {
+                        uint16_t* dst = (lane < 16 ? g.out.hi : g.out.lo) + (long long)mrow0 * g.out.Kp + pc;
+#pragma unroll 4
+                        for (int rr = 0; rr < rows_here; ++rr) {
+                            const float a = tbuf[rr * 33 + 2 * l16], b = tbuf[rr * 33 + 2 * l16 + 1];
+                            const __nv_bfloat16 h0 = __float2bfloat16_rn(a), h1 = __float2bfloat16_rn(b);
+                            __nv_bfloat162 w = (lane < 16) ? __halves2bfloat162(h0, h1)
+                                                           : __floats2bfloat162_rn(a - __bfloat162float(h0), b - __bfloat162float(h1));
+                            *reinterpret_cast<uint32_t*>(dst + (long long)rr * g.out.Kp) = *reinterpret_cast<uint32_t*>(&w);
                         }
                     }
                 }
+                __syncwarp();
             }
             tc_fence_before();
             __syncwarp();
@@ -492,6 +545,7 @@ static int launch_tc(const GemmArgs& a, const PlaneOp& A, const PlaneOp& B, int 
     g.M = a.M; g.N = a.N; g.K = a.K;
     g.a_mn0 = A.mn0; g.a_k0 = A.k0; g.b_mn0 = B.mn0; g.b_k0 = B.k0;
     g.out = a.out_planes;
+    { static int dbg = -1; if (dbg < 0) { const char* e = getenv("RIFT_B200_TC_DBG"); dbg = e ? atoi(e) : 0; } g.dbg = dbg; }
     if (splits > 1) {
         g.splits = splits; g.kb_per_split = cdiv(num_kb, splits);
         g.splits = cdiv(num_kb, g.kb_per_split);

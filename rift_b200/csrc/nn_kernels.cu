@@ -49,12 +49,78 @@ layernorm_kernel(const float* __restrict__ x, long long ldx, int rows, int C, co
     }
 }
 
+// 16-byte vectorised variant (C % 4 == 0, 16-byte aligned rows): every lane owns float4 column groups, so the
+// fp32 and the split-bf16 plane stores are 16 / 8 byte vector stores.  The row is cached in registers (C <= 1024).
+__global__ void __launch_bounds__(256)
+layernorm4_kernel(const float* __restrict__ x, long long ldx, int rows, int C, const float* __restrict__ gamma,
+                  const float* __restrict__ beta, float* __restrict__ y, long long ldy, int relu,
+                  const float* __restrict__ add_rowmod, int rowmod, float* __restrict__ y2, float* __restrict__ mean_out,
+                  float* __restrict__ rstd_out, Planes yp, Planes y2p) {
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    const int C4 = C >> 2;
+    for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += gridDim.x * wpb) {
+        const float4* xr = reinterpret_cast<const float4*>(x + (long long)row * ldx);
+        float4 v[8];
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int c4 = lane + 32 * i;
+            if (c4 < C4) { v[i] = xr[c4]; s += (v[i].x + v[i].y) + (v[i].z + v[i].w); }
+        }
+        const float mean = warp_sum(s) / C;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int c4 = lane + 32 * i;
+            if (c4 < C4) {
+                const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+                q += (a * a + b * b) + (c * c + d * d);
+            }
+        }
+        const float rstd = rsqrtf(warp_sum(q) / C + 1e-5f);
+        if (lane == 0) {
+            if (mean_out) mean_out[row] = mean;
+            if (rstd_out) rstd_out[row] = rstd;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int c4 = lane + 32 * i;
+            if (c4 < C4) {
+                const float4 g = reinterpret_cast<const float4*>(gamma)[c4], b = reinterpret_cast<const float4*>(beta)[c4];
+                float4 o;
+                o.x = (v[i].x - mean) * rstd * g.x + b.x; o.y = (v[i].y - mean) * rstd * g.y + b.y;
+                o.z = (v[i].z - mean) * rstd * g.z + b.z; o.w = (v[i].w - mean) * rstd * g.w + b.w;
+                if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                if (y) *reinterpret_cast<float4*>(y + (long long)row * ldy + 4 * c4) = o;
+                if (yp.on()) split4_store(yp, row, 4 * c4, o.x, o.y, o.z, o.w);
+                if (add_rowmod) {
+                    const float4 a = *reinterpret_cast<const float4*>(add_rowmod + (long long)(row % rowmod) * C + 4 * c4);
+                    o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+                    if (y2) *reinterpret_cast<float4*>(y2 + (long long)row * ldy + 4 * c4) = o;
+                    if (y2p.on()) split4_store(y2p, row, 4 * c4, o.x, o.y, o.z, o.w);
+                }
+            }
+        }
+        if (yp.on()) split_zero_pad(yp, row, C, lane, 32);
+        if (y2p.on()) split_zero_pad(y2p, row, C, lane, 32);
+    }
+}
+
 int launch_layernorm(const float* x, long long ldx, int rows, int C, const float* gamma, const float* beta, float* y,
                      long long ldy, int relu, const float* add_rowmod, int rowmod, float* y2, float* mean, float* rstd,
                      cudaStream_t st, Planes yp, Planes y2p) {
     if (rows <= 0) return 0;
     RIFT_REQUIRE((y2 == nullptr && !y2p.on()) || (add_rowmod != nullptr && rowmod > 0), "layernorm: y2 needs add_rowmod");
     if (y2 == nullptr && !y2p.on()) add_rowmod = nullptr;
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    if ((C & 3) == 0 && C <= 1024 && (ldx & 3) == 0 && (ldy & 3) == 0 && al16(x) && al16(y) && al16(y2) && al16(gamma) &&
+        al16(beta) && al16(add_rowmod)) {
+        layernorm4_kernel<<<min(cdiv(rows, 8), 148 * 8), 256, 0, st>>>(x, ldx, rows, C, gamma, beta, y, ldy, relu, add_rowmod,
+                                                                       rowmod, y2, mean, rstd, yp, y2p);
+        RIFT_LAUNCH_OK();
+        return 0;
+    }
     layernorm_kernel<<<min(cdiv(rows, 8), 148 * 8), 256, 0, st>>>(x, ldx, rows, C, gamma, beta, y, ldy, relu, add_rowmod,
                                                                   rowmod, y2, mean, rstd, yp, y2p);
     RIFT_LAUNCH_OK();
@@ -286,9 +352,10 @@ attention_kernel(AttnArgs a) {
 #pragma unroll
         const long long orow = a.o_custom ? attn_row(b, a.o_inner_n, a.o_outer, a.o_inner) + (long long)i * a.o_seq : qr;
 #pragma unroll
-        for (int d = 0; d < HD; ++d) {
-            if (a.o) a.o[orow * a.ldo + h * HD + d] = acc[d] * inv;
-            if (a.o_planes.on()) split_store(a.o_planes, orow, h * HD + d, acc[d] * inv);
+        for (int d = 0; d < HD; d += 4) {
+            const float4 o4 = make_float4(acc[d] * inv, acc[d + 1] * inv, acc[d + 2] * inv, acc[d + 3] * inv);
+            if (a.o) *reinterpret_cast<float4*>(a.o + orow * a.ldo + h * HD + d) = o4;
+            if (a.o_planes.on()) split4_store(a.o_planes, orow, h * HD + d, o4.x, o4.y, o4.z, o4.w);
         }
         if (a.lse) a.lse[((long long)b * a.H + h) * a.Sq + i] = l > 0.f ? m + logf(l) : INFINITY;
     }
