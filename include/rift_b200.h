@@ -179,6 +179,10 @@ int rift_b200_op_attention(const float* qkv, int B, int S, int H, int hd, const 
                            void* stream);
 int rift_b200_op_nat_attention(const float* qkv, int n_seq, int L, int heads, int hd, int ksize, const float* rpb,
                                float* out, void* stream);
+/* dy *= act'(ref) in place (act 1: ReLU, ref = output; act 2: GELU, ref = pre-activation) */
+int rift_b200_op_act_bwd(const float* ref, float* dy, long long n, int act, void* stream);
+/* out[c] (+)= sum_r x[r, c]; scratch: 148 * C floats */
+int rift_b200_op_colsum(const float* x, int rows, int C, float* out, int accumulate, float* scratch, void* stream);
 int rift_b200_op_masked_maxpool(const float* x, const uint8_t* mask, int groups, int n, int C, float* out, int* argmax,
                                 void* stream);
 

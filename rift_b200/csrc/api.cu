@@ -198,7 +198,7 @@ int rift_b200_op_linear_tc(const float* x, int rows, int K, const float* w, cons
     const size_t plane = ((size_t)N * tw.Kp * 2 + 255) & ~(size_t)255;
     char* p = static_cast<char*>(scratch);
     tw.hi = p; tw.lo = p + plane;
-    if (resplit) {
+    if (resplit & 1) {
         std::vector<char> job(split_job_bytes());
         fill_split_job(job.data(), w, K, N, K, tw.Kp, tw.hi, tw.lo, 0, 0);
         RIFT_CUDA_OK(cudaMemcpyAsync(p + 2 * plane, job.data(), job.size(), cudaMemcpyHostToDevice, S(stream)));
@@ -212,7 +212,7 @@ int rift_b200_op_linear_tc(const float* x, int rows, int K, const float* w, cons
     a.bias = bias; a.act = act; a.res = res; a.ldres = N;
     char* ap = p + 2 * plane + 512;
     const size_t aplane = ((size_t)rows * tw.Kp * 2 + 255) & ~(size_t)255;
-    r = launch_pack_split(x, K, rows, K, tw.Kp, ap, ap + aplane, S(stream));      // part of the timed op: the
+    if (!(resplit & 2)) r = launch_pack_split(x, K, rows, K, tw.Kp, ap, ap + aplane, S(stream));   // bit 1: reuse the A planes
     if (r) return r;                                                              // A planes are per-call data
     return launch_gemm_tc(a, ap, ap + aplane, tw.Kp, tw, 0, 0, S(stream));
 }
@@ -252,6 +252,14 @@ int rift_b200_op_attention(const float* qkv, int B, int Sq, int H, int hd, const
 int rift_b200_op_nat_attention(const float* qkv, int n_seq, int L, int heads, int hd, int ksize, const float* rpb, float* out,
                                void* stream) {
     return launch_nat_attention(qkv, n_seq, L, heads, hd, ksize, rpb, out, S(stream));
+}
+
+int rift_b200_op_act_bwd(const float* ref, float* dy, long long n, int act, void* stream) {
+    return launch_act_bwd(ref, dy, n, act, S(stream));
+}
+
+int rift_b200_op_colsum(const float* x, int rows, int C, float* out, int accumulate, float* scratch, void* stream) {
+    return launch_colsum(x, C, rows, C, out, accumulate, scratch, S(stream));
 }
 
 int rift_b200_op_masked_maxpool(const float* x, const uint8_t* mask, int groups, int n, int C, float* out, int* argmax,

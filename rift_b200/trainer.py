@@ -22,6 +22,25 @@ from . import functional as F
 from .planning_model import PlanningModel
 
 
+def allreduce_grads_and_stats(grads: torch.Tensor, n_train: int, stats: torch.Tensor) -> torch.Tensor:
+    """The step's single collective: SUM all-reduce of [flat fp32 gradients | objective sum | valid count].
+
+    The gradient arena has a 4-float tail after its n_train gradient elements; the two fp64 scalars travel
+    in it as (hi, lo) float pairs (hi = fp32(x), lo = fp32(x - hi): a 48-bit mantissa, exact for counts and
+    ample for the objective sum), so there is no second collective and no staging copy.
+    Returns the all-reduced (sum, count) as fp64."""
+    import torch.distributed as dist
+    n = n_train
+    comm = grads[:n + 4]
+    s = stats.to(torch.float64)
+    hi = s.to(torch.float32)
+    lo = (s - hi.to(torch.float64)).to(torch.float32)
+    comm[n:n + 2].copy_(hi)
+    comm[n + 2:n + 4].copy_(lo)
+    dist.all_reduce(comm, op=dist.ReduceOp.SUM)
+    return comm[n:n + 2].to(torch.float64) + comm[n + 2:n + 4].to(torch.float64)
+
+
 class WarmupCosLR:
     """pluto/optim/warmup_cos_lr.py:6-54 (per-epoch warm-up + cosine) without the `verbose`
     positional argument that breaks on torch >= 2.2."""
@@ -140,18 +159,7 @@ class LightningTrainer:
         if self._world() > 1:
             import torch.distributed as dist
             a = self.model.arena
-            n = a.n_train
-            # the gradient arena has a 4-float tail: the two fp64 scalars travel with the fp32
-            # gradients in the same buffer, each split into (hi, lo) floats, so the step has exactly
-            # one collective and no staging copy
-            comm = a.grads[:n + 4]
-            s = stats[1:3]
-            hi = s.to(torch.float32)
-            lo = (s - hi.to(torch.float64)).to(torch.float32)
-            comm[n:n + 2].copy_(hi)
-            comm[n + 2:n + 4].copy_(lo)
-            dist.all_reduce(comm, op=dist.ReduceOp.SUM)
-            s = comm[n:n + 2].to(torch.float64) + comm[n + 2:n + 4].to(torch.float64)
+            s = allreduce_grads_and_stats(a.grads, a.n_train, stats[1:3])
             self._count = s[1:2].clone()
             return torch.where(s[1] > 0, -s[0] / s[1], torch.zeros_like(s[0]))
         self._count = stats[2:3].clone()
@@ -167,6 +175,11 @@ class LightningTrainer:
             return self._step(batch, "val")
         finally:
             self.training = True
+
+    def validation_loss(self, batch):
+        """The value Lightning logs as 'loss/val_loss' (monitored by ModelCheckpoint, training_builder.py:131-140)."""
+        self.validation_step(batch)
+        return self._last_loss
 
     def optimizer_step(self):
         if self.optimizer is None:
@@ -232,4 +245,81 @@ class ReinforceTrainer(LightningTrainer):
         return loss
 
 
-TRAINERS = {"rift": RIFTTrainer, "grpo": GRPOTrainer, "reinforce": ReinforceTrainer}
+class PPOPlutoModel(PlanningModel):
+    """ppo_pluto/ppo_pluto.py:24-37 — PlanningModel + CriticPPO value net + PPO hyper-parameters."""
+
+    def __init__(self, radius, state_dim=None, action_dim=1, hidden_dim=(256, 256), clip_epsilon=0.2, lambda_entropy=0.01,
+                 **kw):
+        super().__init__(radius=radius, value_hidden=tuple(hidden_dim), **kw)
+        if state_dim is not None and state_dim != self.dim:
+            raise ValueError("state_dim must equal the policy's hidden size (the value net reads `hidden`)")
+        self.clip_epsilon, self.lambda_entropy = clip_epsilon, lambda_entropy
+        self.init_value_net()
+
+    def init_value_net(self, seed: int = 0):
+        """CriticPPO's own initialisation (net.py:355-372,420-433): identity normalisation constants, torch's
+        default Linear init for the hidden layers, orthogonal(std=0.5) / bias 1e-6 for the output layer."""
+        gen = torch.Generator().manual_seed(seed)
+        sd = {}
+        for n, (shape, kind) in self.arena.spec.items():
+            if not n.startswith("value_net."):
+                continue
+            leaf = n.split(".", 1)[1]
+            if leaf in ("state_std", "value_std"):
+                sd[n] = torch.ones(shape)
+            elif leaf in ("state_avg", "value_avg"):
+                sd[n] = torch.zeros(shape)
+            elif leaf.endswith(".weight"):
+                bound = 1.0 / (shape[1] ** 0.5)
+                sd[n] = (torch.rand(shape, generator=gen) * 2 - 1) * bound
+            else:
+                fan_in = self.arena.spec[n.replace(".bias", ".weight")][0][1]
+                sd[n] = (torch.rand(shape, generator=gen) * 2 - 1) / (fan_in ** 0.5)
+        last = max(int(n.split(".")[2]) for n in sd if n.startswith("value_net.net."))
+        w = torch.empty(self.arena.spec[f"value_net.net.{last}.weight"][0])
+        torch.nn.init.orthogonal_(w, 0.5)
+        sd[f"value_net.net.{last}.weight"] = w
+        sd[f"value_net.net.{last}.bias"] = torch.full(self.arena.spec[f"value_net.net.{last}.bias"][0], 1e-6)
+        self.load_state_dict(sd, strict=False)
+
+
+class PPOTrainer(ReinforceTrainer):
+    """ppo_pluto/ppo_trainer.py:126-183 — SmoothL1 value loss - (clipped surrogate + lambda * entropy)."""
+    ALGO = "ppo"
+
+    def __init__(self, model, *a, **kw):
+        super().__init__(model, *a, **kw)
+        self.clip_epsilon = getattr(model, "clip_epsilon", 0.2)
+        self.lambda_entropy = getattr(model, "lambda_entropy", 0.01)
+
+    def freeze_parameters(self, trainable_layers=("planning_decoder.pi_head", "value_net")):
+        super().freeze_parameters(trainable_layers)
+        from .value_net import ValueNet
+        self.value_net = ValueNet(self.model.arena)
+
+    def _objective(self, res, batch, need_grad):
+        dev = self.model.device
+        bs = res["probability"].shape[0]
+        gb = bs * self._world()
+        value = self.value_net.forward(batch["state_torch"].to(dev).float().contiguous(), save=need_grad)
+        vloss, self._dvalue = F.smooth_l1(value, batch["reward_sum_torch"].to(dev).float(), global_batch=gb, need_grad=need_grad)
+        loss, dz, _ = F.action_objective("ppo", res["probability"], res["r_padding_mask"], batch["advantage_torch"].to(dev).float(),
+                                         action_mode=batch["action_mode_torch"].to(dev),
+                                         old_log_prob=batch["old_log_prob_torch"].to(dev).float(),
+                                         clip_epsilon=self.clip_epsilon, lambda_entropy=self.lambda_entropy,
+                                         extra_loss=vloss, global_batch=gb, need_grad=need_grad)
+        self._stats = None
+        return loss, dz
+
+    def _step(self, batch, prefix: str):
+        res = self.model.forward(self._features(batch), outputs=(), save_for_backward=self.training)
+        loss, dz = self._objective(res, batch, need_grad=self.training)
+        if self.training:
+            self.model.backward(dz)                      # zeroes the gradient span, then the policy gradients
+            self.value_net.backward(self._dvalue)        # += value-net gradients
+            loss = self._reduce(loss)
+        self._last_loss = loss
+        return loss if self.training else 0.0
+
+
+TRAINERS = {"rift": RIFTTrainer, "grpo": GRPOTrainer, "reinforce": ReinforceTrainer, "ppo": PPOTrainer}

@@ -1,0 +1,151 @@
+"""GPU: PPO trainer (value net) against the reference goldens, and the policy plugin's train(e_i) loop on a
+small in-memory rollout buffer (checkpoint naming, LR decay, what moves and what stays frozen)."""
+import glob
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from rift_b200.feature import PlutoFeature
+from rift_b200.policy import CBV_POLICY_LIST
+from rift_b200.trainer import TRAINERS, PPOPlutoModel
+from rift_b200.config import pluto_small
+from rift_b200.synth import synth_features, synth_rl_extras, synth_state_dict
+from tests.helpers import CASES, case_inputs, golden, check_golden, to_torch_tree
+
+pytestmark = pytest.mark.gpu
+
+TRAINER_KW = dict(lr=1e-4, cl_lr_decay=0.9, weight_decay=1e-5, epochs=16, warmup_epochs=3, frame_rate=10)
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_ppo_training_step_matches_reference_golden(name):
+    cfg, sd, feats, ex = case_inputs(name, ppo=True)
+    g = golden(name)
+    model = PPOPlutoModel(cfg.radius, hidden_dim=(256, 256), dim=cfg.dim, num_heads=cfg.num_heads,
+                          encoder_depth=cfg.encoder_depth, decoder_depth=cfg.decoder_depth, future_steps=cfg.future_steps)
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    tr = TRAINERS["ppo"](model, trainable_layers=["planning_decoder.pi_head", "value_net"], **TRAINER_KW)
+    batch = {"cur_pluto_feature_torch": to_torch_tree(feats, "cuda")}
+    for k in ("state", "advantage", "reward_sum", "old_log_prob", "action_mode"):
+        batch[k + "_torch"] = torch.from_numpy(ex[k].copy()).cuda()
+    loss = tr.training_step(batch)
+    ref = float(g["loss_ppo"])
+    assert abs(float(loss) - ref) <= 1e-3 * max(abs(ref), 1e-3)
+    for k in g.files:
+        if k.startswith("grad_ppo/") and not k.endswith("@stats"):
+            n = k.split("/", 1)[1].split("@")[0]
+            check_golden(g, f"grad_ppo/{n}", model.arena.grad_view(n).cpu().numpy(), rtol=1e-3, atol=2e-6)
+    # three updates run and move the value net and the head, nothing else
+    before = {k: v.clone() for k, v in model.state_dict().items()}
+    tr.configure_optimizers()
+    for _ in range(3):
+        tr.step(batch)
+    after = model.state_dict()
+    moved = {k for k in before if before[k].dtype.is_floating_point and not torch.equal(before[k].cpu(), after[k].cpu())}
+    assert moved and all(k.startswith(("planning_decoder.pi_head.", "value_net.")) for k in moved)
+
+
+class _Buffer:
+    """Minimal stand-in with the read-only interface of CBVRolloutBuffer (cbv_rollout_buffer.py:77-138)."""
+
+    def __init__(self, items, extra):
+        self.items, self.extra = items, extra
+        self.buffer_capacity = len(items)
+        self.buffer_full = True
+        self.was_reset = False
+
+    def __len__(self):
+        return len(self.items)
+
+    def sample(self, idx):
+        d = dict(self.items[idx])
+        d.update({k: v[idx] for k, v in self.extra.items()})
+        return d
+
+    def get_key_data(self, key):
+        return [it[key] for it in self.items] if key in self.items[0] else self.extra[key]
+
+    def add_extra_data(self, data):
+        assert all(len(v) == self.buffer_capacity for v in data.values())
+        self.extra.update(data)
+
+    def reset_buffer(self):
+        self.was_reset = True
+
+
+def _make_buffer(n=40, seed=0):
+    cfg = pluto_small()
+    rng = np.random.Generator(np.random.PCG64(seed))
+    items = []
+    for i in range(n):
+        A, Mp, R = int(rng.integers(3, 8)), int(rng.integers(2, 7)), int(rng.integers(1, 4))
+        f = synth_features(cfg, 1, A, Mp, R, seed=1000 + i)
+        d = {k: ({kk: vv[0] for kk, vv in v.items()} if isinstance(v, dict) else v[0]) for k, v in f.items()}
+        ret = rng.normal(-5, 20, R * 12)
+        adv = ((ret - ret.mean()) / (ret.std() + 1e-5)).reshape(R, 12)
+        vm = np.ones((R, 12), bool)
+        items.append({
+            "CBVs_obs": {"raw_pluto_feature": PlutoFeature(data=d)}, "CBVs_next_obs": {"raw_pluto_feature": PlutoFeature(data=d)},
+            "CBVs_group_advantage": {"advantage": adv, "valid_mask": vm},
+            "CBVs_actions_old_group_logits": {"logits": rng.normal(0, 1, (R, 12)).astype(np.float32), "valid_mask": vm},
+            "CBVs_actions_ref_group_logits": {"logits": rng.normal(0, 1, (R, 12)).astype(np.float32), "valid_mask": vm},
+            "CBVs_reward": np.float32(rng.normal(-0.5, 2)), "CBVs_done": np.float32(rng.uniform() < 0.1),
+            "CBVs_terminated": np.float32(0.0), "CBVs_actions_old_log_prob": np.float32(-rng.uniform(1, 4)),
+            "CBVs_actions_mode": np.array([0, int(rng.integers(0, 12))], np.int64),
+        })
+    return _Buffer(items, {})
+
+
+@pytest.mark.parametrize("policy_name", ["rift_pluto", "grpo_pluto", "ppo_pluto", "reinforce_pluto"])
+def test_plugin_train_loop(policy_name, tmp_path):
+    cfg = pluto_small()
+    pre = tmp_path / "pretrained.ckpt"
+    sd = {k: torch.from_numpy(v) for k, v in synth_state_dict(cfg, seed=7).items()}
+    torch.save({"state_dict": {"model." + k: v for k, v in sd.items()}}, pre)
+    config = {"ckpt_path": str(pre), "ROOT_DIR": str(tmp_path), "model_path": "models", "load_agent_info": policy_name,
+              "obs": {"radius": 120}, "frame_rate": 10, "ppo": {"hidden_dim": [256, 256], "clip_epsilon": 0.2, "lambda_entropy": 0.01},
+              "rlft": {"epochs": 2, "warmup_epochs": 1, "train_batch_size": 16}}
+    pol = CBV_POLICY_LIST[policy_name](config)
+    pol.load_model(resume=True)
+    assert pol.continue_episode == 0 and pol.current_epoch == 0
+    buf = _make_buffer()
+    pol.set_buffer(buf, total_routes=1)
+    pol.set_mode("train")
+    before = {k: v.clone().cpu() for k, v in pol.pluto_model.state_dict().items()}
+    pol.train(e_i=3)
+    files = glob.glob(str(tmp_path / "models" / policy_name / "*.ckpt"))
+    assert len(files) == 1 and re.search(r"carla_episode=3-epoch=\d+-val_loss=-?[\d.]+\.ckpt$", files[0]), files
+    assert pol.current_epoch == 1 and buf.was_reset
+    ck = torch.load(files[0], weights_only=False)["state_dict"]
+    assert all(k.startswith("model.") for k in ck)
+    after = pol.pluto_model.state_dict()
+    moved = {k for k in before if before[k].dtype.is_floating_point and not torch.equal(before[k], after[k].cpu())}
+    allowed = ("planning_decoder.pi_head.", "value_net.") if policy_name == "ppo_pluto" else ("planning_decoder.pi_head.",)
+    assert moved and all(k.startswith(allowed) for k in moved), sorted(moved)[:5]
+    # resume picks the newest episode and decays the closed-loop learning rate
+    pol2 = CBV_POLICY_LIST[policy_name](config)
+    pol2.load_model(resume=True)
+    assert pol2.continue_episode == 3 and pol2.current_epoch == 1
+    for k in moved:
+        assert torch.equal(pol2.pluto_model.state_dict()[k].cpu(), after[k].cpu())
+
+
+def test_policy_outputs_advantage_is_numpy_exact():
+    cfg = pluto_small()
+    config = {"obs": {"radius": 120}}
+    pol = CBV_POLICY_LIST["rift_pluto"](config)
+    pol.pluto_model.load_state_dict({k: torch.from_numpy(v) for k, v in synth_state_dict(cfg, seed=7).items()})
+    buf = _make_buffer(3, seed=5)
+    feats = [it["CBVs_obs"]["raw_pluto_feature"] for it in buf.items]
+    rng = np.random.Generator(np.random.PCG64(1))
+    rets = [rng.normal(-5, 20, f.data["reference_line"]["position"].shape[0] * 12) for f in feats]
+    out = pol.policy_outputs(feats, rets)
+    for b, r in enumerate(rets):
+        ref = (r - np.mean(r)) / (np.std(r) + 1e-5)
+        got = out["group_advantage"][b].reshape(-1)[: len(r)].cpu().numpy()
+        assert np.array_equal(got, ref)
+        assert int(out["group_advantage_mask"][b].sum()) == len(r)
+    assert out["candidate_trajectories"].shape[-1] == 3
