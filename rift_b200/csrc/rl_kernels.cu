@@ -106,6 +106,7 @@ group_advantage_fixed_kernel(const double* __restrict__ ret, double* __restrict_
     const int lane8 = tid & 7;
     const int gl = tid >> 3;
     const unsigned gmask = 0xFFu << ((tid & 31) & ~7);
+    const float invG = 1.f / (float)G;
     const long long n_chunks = (n_groups + ADV_GPB - 1) / ADV_GPB;
     for (long long chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
         const long long g0 = chunk * ADV_GPB;
@@ -118,13 +119,13 @@ group_advantage_fixed_kernel(const double* __restrict__ ret, double* __restrict_
             for (int e = tid; e < total / 2; e += ADV_THREADS) {
                 const double2 v = __ldg(src + e);
                 const int i = 2 * e;
-                const int g = i / G, k = i - g * G;
+                const int g = (int)(((float)i + 0.5f) * invG), k = i - g * G;   // exact for i < 2^14 (no integer division)
                 sm[g * Gp + k] = v.x;
                 sm[g * Gp + k + 1] = v.y;
             }
         } else {
             for (int i = tid; i < total; i += ADV_THREADS) {
-                const int g = i / G, k = i - g * G;
+                const int g = (int)(((float)i + 0.5f) * invG), k = i - g * G;   // exact for i < 2^14 (no integer division)
                 sm[g * Gp + k] = __ldg(ret + base + i);
             }
         }
@@ -139,12 +140,12 @@ group_advantage_fixed_kernel(const double* __restrict__ ret, double* __restrict_
             double2* dst = reinterpret_cast<double2*>(adv + base);
             for (int e = tid; e < total / 2; e += ADV_THREADS) {
                 const int i = 2 * e;
-                const int g = i / G, k = i - g * G;
+                const int g = (int)(((float)i + 0.5f) * invG), k = i - g * G;   // exact for i < 2^14 (no integer division)
                 dst[e] = make_double2(sm[g * Gp + k], sm[g * Gp + k + 1]);
             }
         } else {
             for (int i = tid; i < total; i += ADV_THREADS) {
-                const int g = i / G, k = i - g * G;
+                const int g = (int)(((float)i + 0.5f) * invG), k = i - g * G;   // exact for i < 2^14 (no integer division)
                 adv[base + i] = sm[g * Gp + k];
             }
         }
