@@ -1,0 +1,57 @@
+"""Data-parallel numerics check (run under torchrun on >= 2 GPUs): a ragged batch sharded over the ranks must give
+the same loss, gradient norm and updated parameters as one rank holding the whole batch."""
+import os, sys, torch, numpy as np
+import torch.distributed as dist
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from rift_b200.config import MODEL_ZOO
+from rift_b200.planning_model import PlanningModel
+from rift_b200.trainer import TRAINERS
+from rift_b200.synth import synth_state_dict, synth_features, synth_rl_extras
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+cfg = MODEL_ZOO["small"]()
+sd = {k: torch.from_numpy(v) for k, v in synth_state_dict(cfg, seed=7).items()}
+bs = 4 * world
+# Reference lines are all valid here on purpose: the reference's r2r key-padding quirk (r_pad[j % bs])
+# makes a sample's output depend on the OTHER samples of its batch whenever validity differs, so a ragged-R batch is
+# not shard-invariant in the reference either.  Unequal valid counts per rank come from the candidate mask instead.
+feats = synth_features(cfg, bs, 12, 14, 4, seed=3, ragged=False)
+ex = synth_rl_extras(cfg, feats, seed=4)
+rng = np.random.Generator(np.random.PCG64(9))
+drop = rng.uniform(size=ex["group_advantage_mask"].shape) < rng.uniform(0.0, 0.6, (bs, 1, 1))
+drop[..., 0] = False
+ex["group_advantage_mask"] = ex["group_advantage_mask"] & ~drop
+KW = dict(lr=1e-3, cl_lr_decay=0.9, weight_decay=1e-5, epochs=16, warmup_epochs=3, frame_rate=10)
+def tree(t, sl):
+    return {k: tree(v, sl) for k, v in t.items()} if isinstance(t, dict) else torch.from_numpy(np.ascontiguousarray(t[sl])).cuda()
+def batch(sl):
+    b = {"cur_pluto_feature_torch": tree(feats, sl)}
+    for k in ("group_advantage", "group_advantage_mask", "old_group_logits", "ref_group_logits"):
+        b[k + "_torch"] = torch.from_numpy(ex[k][sl].copy()).cuda()
+    return b
+def run(sl, distributed, exact):
+    m = PlanningModel.from_config(cfg); m.load_state_dict(sd)
+    m.exact_fp32 = exact
+    tr = TRAINERS["grpo"](m, trainable_layers=["planning_decoder"], **KW)
+    tr.configure_optimizers()
+    if not distributed:
+        tr._world = lambda: 1
+    loss = float(tr.training_step(batch(sl)))                       # forward + objective + backward (+ all-reduce)
+    g = (m.arena.grads[:m.arena.n_train] / float(tr._count)).clone()
+    tr.optimizer_step()
+    return loss, float(tr._count), tr.optimizer.grad_norm(), g
+# Compared after ONE backward: Adam's update lr*g/(|g|+eps) turns round-off-sized gradient elements (exact-zero
+# sums) into +-lr steps, so parameters after several steps are not a meaningful equality target (the same holds
+# between the reference and itself under a different summation order).
+for exact, tol in ((True, 2e-5), (False, 1e-2)):
+    # exact-fp32 GEMMs: sharded == unsharded to round-off.  Tensor-core GEMMs: shards of 4 samples route more (small)
+    # GEMMs to the exact kernel than the 8-sample batch, the ~1e-5 activation differences flip a few ReLU / arg-max
+    # decisions, and single gradient elements move by ~0.2 % of the maximum.
+    l_dp, c_dp, n_dp, g_dp = run(slice(rank * 4, rank * 4 + 4), True, exact)
+    l_1, c_1, n_1, g_1 = run(slice(0, bs), False, exact)
+    err = float((g_dp - g_1).abs().max()) / float(g_1.abs().max())
+    print(f"rank {rank} [{'exact fp32' if exact else 'tcgen05'}]: loss dp {l_dp:.9f} single {l_1:.9f} | valid count {c_dp:.0f}/{c_1:.0f} | "
+          f"grad norm {n_dp:.6f}/{n_1:.6f} | max grad diff / max grad {err:.2e}", flush=True)
+    assert abs(l_dp - l_1) <= 2e-6 * max(1, abs(l_1)) and c_dp == c_1 and abs(n_dp - n_1) <= 10 * tol * n_1 and err < tol
+dist.destroy_process_group()
