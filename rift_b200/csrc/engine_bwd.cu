@@ -29,9 +29,9 @@ static int mlp_bwd(Ctx& c, const MlpTape& t, const MLPLayerP& p, const float* dY
     const int rows = t.x.rows, Hd = p.l0.N;
     ALLOC(da, float, (size_t)rows * Hd);
     ALLOC(dh, float, (size_t)rows * Hd);
-    TRY(lin_bwd(c, t.a.f, Hd, dY, lddy, rows, p.l3, da, Hd, 0.f));
+    TRY(lin_bwd(c, t.a.f, Hd, dY, lddy, rows, p.l3, da, Hd, 0.f, true, &t.a.p));
     TRY(ln_bwd(c, t.ln, p.n, da, t.a.f, dh, 0));
-    TRY(lin_bwd(c, t.x.f, t.x.ld, dh, Hd, rows, p.l0, dX, p.l0.K, 0.f));
+    TRY(lin_bwd(c, t.x.f, t.x.ld, dh, Hd, rows, p.l0, dX, p.l0.K, 0.f, true, &t.x.p));
     return 0;
 }
 
@@ -40,18 +40,18 @@ static int fourier_bwd(Ctx& c, const FourierTape& t, const FourierP& p, const fl
     const int rows = t.rows, D = p.out_l.N;
     ALLOC(d_on, float, (size_t)rows * D);
     ALLOC(d_acc, float, (size_t)rows * D);
-    TRY(lin_bwd(c, t.on.f, D, dOut, D, rows, p.out_l, d_on, D, 0.f));
+    TRY(lin_bwd(c, t.on.f, D, dOut, D, rows, p.out_l, d_on, D, 0.f, true, &t.on.p));
     TRY(ln_bwd(c, t.ln_o, p.out_n, d_on, t.on.f, d_acc, 0));
     for (int i = 0; i < p.d; ++i) {
         const MLPLayerP& ml = p.mlps[i];
         const FourierTape::Dim& dm = t.dims[i];
         ALLOC(d_hn, float, (size_t)rows * D);
         ALLOC(d_h, float, (size_t)rows * D);
-        TRY(lin_bwd(c, dm.hn.f, D, d_acc, D, rows, ml.l3, d_hn, D, 0.f));
+        TRY(lin_bwd(c, dm.hn.f, D, d_acc, D, rows, ml.l3, d_hn, D, 0.f, true, &dm.hn.p));
         TRY(ln_bwd(c, dm.ln, ml.n, d_hn, dm.hn.f, d_h, 0));
         float* d_feat = nullptr;
         if (p.freqs.train) { d_feat = c.alloc<float>((size_t)rows * FIN); if (!d_feat) { set_last_error("workspace too small"); return -1; } }
-        TRY(lin_bwd(c, dm.feat.f, FIN, d_h, D, rows, ml.l0, d_feat, FIN, 0.f));
+        TRY(lin_bwd(c, dm.feat.f, FIN, d_h, D, rows, ml.l0, d_feat, FIN, 0.f, true, &dm.feat.p));
         if (p.freqs.train) {
             ALLOC(contrib, float, (size_t)rows * NFREQ);
             ALLOC(sc, float, (size_t)148 * NFREQ);
@@ -76,7 +76,7 @@ static int points_bwd(Ctx& c, const PointsTape& t, const PointsEncP& p, const fl
     ALLOC(d_h1, float, (size_t)rows * PE_H1);
     ALLOC(sc, float, (size_t)148 * 2 * PE_H2);
     if (!c.dry) TRY(launch_masked_maxpool_bwd(dOut, t.arg2, groups, n, Cout, d_o, 0, c.st));
-    TRY(lin_bwd(c, t.h2.f, PE_H2, d_o, Cout, rows, p.s3, d_h2, PE_H2, 0.f));
+    TRY(lin_bwd(c, t.h2.f, PE_H2, d_o, Cout, rows, p.s3, d_h2, PE_H2, 0.f, true, &t.h2.p));
     TRY(act_bwd(c, t.h2.f, d_h2, (long long)rows * PE_H2, ACT_RELU));
     if (!c.dry) {
         if (p.sbn.affine.train)
@@ -84,11 +84,11 @@ static int points_bwd(Ctx& c, const PointsTape& t, const PointsEncP& p, const fl
         TRY(launch_scale_cols(d_h2, t.sc2, rows, PE_H2, c.st));                      // through the folded BatchNorm scale
         if (p.s0.train && p.s0.db) TRY(launch_colsum(d_h2, PE_H2, rows, PE_H2, p.s0.db, 1, sc, c.st));
     }
-    TRY(lin_bwd(c, t.f.f, PE_H2, d_h2, PE_H2, rows, s0a, df, PE_H2, 0.f, false));
+    TRY(lin_bwd(c, t.f.f, PE_H2, d_h2, PE_H2, rows, s0a, df, PE_H2, 0.f, false, &t.f.p));
     if (!c.dry) TRY(launch_groupsum(d_h2, PE_H2, groups, n, PE_H2, d_gp, PE_H2, 0, c.st));
-    TRY(lin_bwd(c, t.pooled.f, PE_H2, d_gp, PE_H2, groups, s0b, d_pooled, PE_H2, 0.f, false));
+    TRY(lin_bwd(c, t.pooled.f, PE_H2, d_gp, PE_H2, groups, s0b, d_pooled, PE_H2, 0.f, false, &t.pooled.p));
     if (!c.dry) TRY(launch_masked_maxpool_bwd(d_pooled, t.arg1, groups, n, PE_H2, df, 1, c.st));
-    TRY(lin_bwd(c, t.h1.f, PE_H1, df, PE_H2, rows, p.f3, d_h1, PE_H1, 0.f));
+    TRY(lin_bwd(c, t.h1.f, PE_H1, df, PE_H2, rows, p.f3, d_h1, PE_H1, 0.f, true, &t.h1.p));
     TRY(act_bwd(c, t.h1.f, d_h1, (long long)rows * PE_H1, ACT_RELU));
     if (!c.dry) {
         if (p.fbn.affine.train)
@@ -96,7 +96,7 @@ static int points_bwd(Ctx& c, const PointsTape& t, const PointsEncP& p, const fl
         TRY(launch_scale_cols(d_h1, t.sc1, rows, PE_H1, c.st));
         if (p.f0.train && p.f0.db) TRY(launch_colsum(d_h1, PE_H1, rows, PE_H1, p.f0.db, 1, sc, c.st));
     }
-    TRY(lin_bwd(c, t.F.f, t.F.ld, d_h1, PE_H1, rows, p.f0, nullptr, 0, 0.f, false));
+    TRY(lin_bwd(c, t.F.f, t.F.ld, d_h1, PE_H1, rows, p.f0, nullptr, 0, 0.f, false, &t.F.p));
     return 0;
 }
 
@@ -105,9 +105,9 @@ static int mlp_tail_bwd(Ctx& c, int rows, int D, int Hd, const Act& hm, const fl
                         const Norm& n2, const Lin& fc1, const Lin& fc2, float* dX) {
     ALLOC(d_hm, float, (size_t)rows * Hd);
     ALLOC(d_t2, float, (size_t)rows * D);
-    TRY(lin_bwd(c, hm.f, Hd, dX, D, rows, fc2, d_hm, Hd, 0.f));
+    TRY(lin_bwd(c, hm.f, Hd, dX, D, rows, fc2, d_hm, Hd, 0.f, true, &hm.p));
     TRY(act_bwd(c, act_ref, d_hm, (long long)rows * Hd, act));
-    TRY(lin_bwd(c, t2.f, D, d_hm, Hd, rows, fc1, d_t2, D, 0.f));
+    TRY(lin_bwd(c, t2.f, D, d_hm, Hd, rows, fc1, d_t2, D, 0.f, true, &t2.p));
     TRY(ln_bwd(c, ln2, n2, d_t2, nullptr, dX, 1));
     return 0;
 }
@@ -176,13 +176,13 @@ int rift_b200_engine::backward(const rift_b200_batch& bt, const float* dlogits, 
             ALLOC(d_qc, float, (size_t)rowsQ * D);
             ALLOC(d_kvc, float, (size_t)rowsE * 2 * D);
             ALLOC(d_t3, float, (size_t)rowsQ * D);
-            TRY(lin_bwd(c, dt.a3.f, D, dq, D, rowsQ, db.cross.out, d_a3, D, 0.f));
+            TRY(lin_bwd(c, dt.a3.f, D, dq, D, rowsQ, db.cross.out, d_a3, D, 0.f, true, &dt.a3.p));
             if (!c.dry) {
                 AttnArgs a = attn_cross(dt.qc, dt.kvc, bs, R * Mo, S, D, H, tp.key_pad, att_scale);
                 a.lse = dt.lse3;
                 TRY(launch_attention_bwd(a, d_a3, D, d_qc, D, d_kvc, d_kvc + D, 2 * D, 2 * D, c.st));
             }
-            TRY(lin_bwd(c, dt.t3.f, D, d_qc, D, rowsQ, cr_q, d_t3, D, 0.f));
+            TRY(lin_bwd(c, dt.t3.f, D, d_qc, D, rowsQ, cr_q, d_t3, D, 0.f, true, &dt.t3.p));
             TRY(lin_bwd(c, tp.Xn.f, D, d_kvc, 2 * D, rowsE, cr_kv, dXn, D, 1.f));
             TRY(ln_bwd(c, dt.ln3, db.n3, d_t3, nullptr, dq, 1));
         }
@@ -193,16 +193,16 @@ int rift_b200_engine::backward(const rift_b200_batch& bt, const float* dlogits, 
             ALLOC(dqkv2, float, (size_t)rowsQ * 3 * D);
             ALLOC(d_t2, float, (size_t)rowsQ * D);
             ALLOC(sc, float, (size_t)Mo * D);
-            TRY(lin_bwd(c, dt.a2.f, D, dq, D, rowsQ, db.m2m.out, d_a2, D, 0.f));
+            TRY(lin_bwd(c, dt.a2.f, D, dq, D, rowsQ, db.m2m.out, d_a2, D, 0.f, true, &dt.a2.p));
             if (!c.dry) {
                 AttnArgs a = attn_m2m(dt.qkv2, NR, Mo, D, H, att_scale);
                 a.lse = dt.lse2;
                 TRY(launch_attention_bwd(a, d_a2, D, dqkv2, 3 * D, dqkv2 + D, dqkv2 + 2 * D, 3 * D, 3 * D, c.st));
             }
-            TRY(lin_bwd(c, dt.t2p.f, D, dqkv2, 3 * D, rowsQ, m2m_qk, d_t2, D, 0.f));            // d(LN2 out + m_pos)
+            TRY(lin_bwd(c, dt.t2p.f, D, dqkv2, 3 * D, rowsQ, m2m_qk, d_t2, D, 0.f, true, &dt.t2p.p));            // d(LN2 out + m_pos)
             if (m.m_pos.train && !c.dry) TRY(launch_modsum(d_t2, D, rowsQ, D, Mo, m.m_pos.d, 1, c.st));
             (void)sc;
-            TRY(lin_bwd(c, dt.t2.f, D, dqkv2 + 2 * D, 3 * D, rowsQ, m2m_v, d_t2, D, 1.f));       // + value path
+            TRY(lin_bwd(c, dt.t2.f, D, dqkv2 + 2 * D, 3 * D, rowsQ, m2m_v, d_t2, D, 1.f, true, &dt.t2.p));       // + value path
             TRY(ln_bwd(c, dt.ln2, db.n2, d_t2, nullptr, dq, 1));
         }
         // (i) r2r
@@ -210,13 +210,13 @@ int rift_b200_engine::backward(const rift_b200_batch& bt, const float* dlogits, 
             ALLOC(d_a1, float, (size_t)rowsQ * D);
             ALLOC(dqkv1, float, (size_t)rowsQ * 3 * D);
             ALLOC(d_t1, float, (size_t)rowsQ * D);
-            TRY(lin_bwd(c, dt.a1.f, D, dq, D, rowsQ, db.r2r.out, d_a1, D, 0.f));
+            TRY(lin_bwd(c, dt.a1.f, D, dq, D, rowsQ, db.r2r.out, d_a1, D, 0.f, true, &dt.a1.p));
             if (!c.dry) {
                 AttnArgs a = attn_r2r(dt.qkv1, bs, R, Mo, D, H, tp.r_pad, att_scale);
                 a.lse = dt.lse1;
                 TRY(launch_attention_bwd(a, d_a1, D, dqkv1, 3 * D, dqkv1 + D, dqkv1 + 2 * D, 3 * D, 3 * D, c.st));
             }
-            TRY(lin_bwd(c, dt.t1.f, D, dqkv1, 3 * D, rowsQ, db.r2r.in, d_t1, D, 0.f));
+            TRY(lin_bwd(c, dt.t1.f, D, dqkv1, 3 * D, rowsQ, db.r2r.in, d_t1, D, 0.f, true, &dt.t1.p));
             TRY(ln_bwd(c, dt.ln1, db.n1, d_t1, nullptr, dq, 1));
         }
     }
@@ -248,13 +248,13 @@ int rift_b200_engine::backward(const rift_b200_batch& bt, const float* dlogits, 
         ALLOC(d_att, float, (size_t)rowsE * D);
         ALLOC(dqkv, float, (size_t)rowsE * 3 * D);
         ALLOC(d_t1, float, (size_t)rowsE * D);
-        TRY(lin_bwd(c, et.att.f, D, dX, D, rowsE, eb.attn.out, d_att, D, 0.f));
+        TRY(lin_bwd(c, et.att.f, D, dX, D, rowsE, eb.attn.out, d_att, D, 0.f, true, &et.att.p));
         if (!c.dry) {
             AttnArgs a = attn_self(et.qkv, bs, S, D, H, tp.key_pad, att_scale);
             a.lse = et.lse;
             TRY(launch_attention_bwd(a, d_att, D, dqkv, 3 * D, dqkv + D, dqkv + 2 * D, 3 * D, 3 * D, c.st));
         }
-        TRY(lin_bwd(c, et.t1.f, D, dqkv, 3 * D, rowsE, eb.attn.in, d_t1, D, 0.f));
+        TRY(lin_bwd(c, et.t1.f, D, dqkv, 3 * D, rowsE, eb.attn.in, d_t1, D, 0.f, true, &et.t1.p));
         TRY(ln_bwd(c, et.ln1, eb.n1, d_t1, nullptr, dX, 1));
     }
 
@@ -305,7 +305,7 @@ int rift_b200_engine::backward(const rift_b200_batch& bt, const float* dlogits, 
             ALLOC(d_qv, float, (size_t)D);
             ALLOC(d_toks, float, (size_t)bs * ntok * D);
             ALLOC(dwb, float, (size_t)2 * ntok * D);
-            TRY(lin_bwd(c, et.eo.f, D, dx_ego, D, bs, m.ego.attn.out, d_eo, D, 0.f));
+            TRY(lin_bwd(c, et.eo.f, D, dx_ego, D, bs, m.ego.attn.out, d_eo, D, 0.f, true, &et.eo.p));
             if (!c.dry) {
                 AttnArgs a = attn_ego(et.qv, et.kv, bs, ntok, D, eh);
                 a.lse = et.lse;
@@ -331,7 +331,7 @@ int rift_b200_engine::backward(const rift_b200_batch& bt, const float* dlogits, 
             ALLOC(dlat0, float, (size_t)NA * Ls[0] * D);
             ZALLOC(dlat1, (size_t)NA * Ls[1] * D);
             ZALLOC(dlat2, (size_t)NA * Ls[2] * D);
-            TRY(lin_bwd(c, nt.colF.f, 3 * D, dx_hist, D, NA, m.hist.fpn, d_colF, 3 * D, 0.f));
+            TRY(lin_bwd(c, nt.colF.f, 3 * D, dx_hist, D, NA, m.hist.fpn, d_colF, 3 * D, 0.f, true, &nt.colF.p));
             if (!c.dry) {
                 TRY(launch_col2im_k3_last(d_colF, NA, Ls[0], D, dlat0, c.st));
                 TRY(launch_fpn_upsample_add_bwd(dlat0, dlat1, NA, Ls[0], Ls[1], D, c.st));
@@ -345,7 +345,7 @@ int rift_b200_engine::backward(const rift_b200_batch& bt, const float* dlogits, 
                 ALLOC(d_colL, float, (size_t)rows * 3 * d);
                 ALLOC(d_o, float, (size_t)rows * d);
                 ALLOC(dx, float, (size_t)rows * d);
-                TRY(lin_bwd(c, nt.colL[i].f, 3 * d, dlat[i], D, rows, m.hist.lateral[i], d_colL, 3 * d, 0.f));
+                TRY(lin_bwd(c, nt.colL[i].f, 3 * d, dlat[i], D, rows, m.hist.lateral[i], d_colL, 3 * d, 0.f, true, &nt.colL[i].p));
                 if (!c.dry) TRY(launch_col2im_k3(d_colL, NA, L, d, 1, d_o, 0, c.st));
                 TRY(ln_bwd(c, nt.ln_lev[i], m.hist.norms[i], d_o, nullptr, dx, 0));
                 if (lv.has_down) {
@@ -353,7 +353,7 @@ int rift_b200_engine::backward(const rift_b200_batch& bt, const float* dlogits, 
                     ALLOC(d_xd, float, (size_t)NA * Ln * 2 * d);
                     ALLOC(d_colD, float, (size_t)NA * Ln * 3 * d);
                     TRY(ln_bwd(c, nt.ln_down[i], lv.down_n, dxn, nullptr, d_xd, 0));
-                    TRY(lin_bwd(c, nt.colD[i].f, 3 * d, d_xd, 2 * d, NA * Ln, lv.down, d_colD, 3 * d, 0.f));
+                    TRY(lin_bwd(c, nt.colD[i].f, 3 * d, d_xd, 2 * d, NA * Ln, lv.down, d_colD, 3 * d, 0.f, true, &nt.colD[i].p));
                     if (!c.dry) TRY(launch_col2im_k3(d_colD, NA, L, d, 2, dx, 1, c.st));
                 }
                 for (int j = 1; j >= 0; --j) {
@@ -365,18 +365,18 @@ int rift_b200_engine::backward(const rift_b200_batch& bt, const float* dlogits, 
                     ALLOC(d_t1, float, (size_t)rows * d);
                     const int nrel = 2 * lv.ksize - 1;
                     ALLOC(drpb, float, (size_t)NA * lv.heads * nrel);
-                    TRY(lin_bwd(c, bt_.att.f, d, dx, d, rows, nb.proj, d_att, d, 0.f));
+                    TRY(lin_bwd(c, bt_.att.f, d, dx, d, rows, nb.proj, d_att, d, 0.f, true, &bt_.att.p));
                     if (!c.dry) {
                         TRY(launch_nat_attention_bwd(bt_.qkv, d_att, NA, L, lv.heads, d / lv.heads, lv.ksize, nb.rpb.p, dqkv,
                                                      nb.rpb.train ? drpb : nullptr, c.st));
                         if (nb.rpb.train) TRY(launch_colsum(drpb, lv.heads * nrel, NA, lv.heads * nrel, nb.rpb.d, 1, esc, c.st));
                     }
-                    TRY(lin_bwd(c, bt_.t1.f, d, dqkv, 3 * d, rows, nb.qkv, d_t1, d, 0.f));
+                    TRY(lin_bwd(c, bt_.t1.f, d, dqkv, 3 * d, rows, nb.qkv, d_t1, d, 0.f, true, &bt_.t1.p));
                     TRY(ln_bwd(c, bt_.ln1, nb.n1, d_t1, nullptr, dx, 1));
                 }
                 dxn = dx;
             }
-            TRY(lin_bwd(c, nt.col0.f, 27, dxn, m.hist.embed.N, NA * Ls[0], m.hist.embed, nullptr, 0, 0.f));
+            TRY(lin_bwd(c, nt.col0.f, 27, dxn, m.hist.embed.N, NA * Ls[0], m.hist.embed, nullptr, 0, 0.f, true, &nt.col0.p));
         }
     }
     return 0;

@@ -206,6 +206,86 @@ int layernorm_bwd_scratch_floats(int C) { return LNB_BLOCKS * 2 * C; }
 __global__ void colsum_final_kernel(const float* __restrict__ partial, int nb, long long stride, int C, float* __restrict__ out,
                                     int accumulate);
 
+// 16-byte vectorised backward (C = 128 * NV, rows 16-byte aligned): each lane owns NV float4 column groups, the
+// whole row lives in registers between the statistics pass and the dx pass, and the per-lane dgamma / dbeta
+// accumulators have exactly the width the row needs.
+template <int NV>
+__global__ void __launch_bounds__(256)
+layernorm_bwd4_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ dy, long long lddy, int rows, int C,
+                      const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
+                      const float* __restrict__ y_relu, long long ldy, float* __restrict__ dx, long long lddx,
+                      int dx_accumulate, float* __restrict__ partial /*[grid][2][C]*/) {
+    extern __shared__ float sm[];      // [8 warps][2][C]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int C4 = C >> 2;
+    float4 dg[NV], db[NV], gm[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        dg[i] = db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int c4 = lane + 32 * i;
+        gm[i] = c4 < C4 ? reinterpret_cast<const float4*>(gamma)[c4] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int row = blockIdx.x * 8 + warp; row < rows; row += gridDim.x * 8) {
+        const float4* xr = reinterpret_cast<const float4*>(x + (long long)row * ldx);
+        const float4* dyr = reinterpret_cast<const float4*>(dy + (long long)row * lddy);
+        const float4* yr = y_relu ? reinterpret_cast<const float4*>(y_relu + (long long)row * ldy) : nullptr;
+        const float mu = mean[row], rs = rstd[row];
+        float4 xh[NV], d[NV];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c4 = lane + 32 * i;
+            if (c4 < C4) {
+                const float4 xv = xr[c4];
+                float4 dv = dyr[c4];
+                if (yr) {
+                    const float4 yv = yr[c4];
+                    if (!(yv.x > 0.f)) dv.x = 0.f; if (!(yv.y > 0.f)) dv.y = 0.f;
+                    if (!(yv.z > 0.f)) dv.z = 0.f; if (!(yv.w > 0.f)) dv.w = 0.f;
+                }
+                xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+                d[i] = dv;
+                const float4 g = make_float4(dv.x * gm[i].x, dv.y * gm[i].y, dv.z * gm[i].z, dv.w * gm[i].w);
+                s1 += (g.x + g.y) + (g.z + g.w);
+                s2 += (g.x * xh[i].x + g.y * xh[i].y) + (g.z * xh[i].z + g.w * xh[i].w);
+                dg[i].x += dv.x * xh[i].x; dg[i].y += dv.y * xh[i].y; dg[i].z += dv.z * xh[i].z; dg[i].w += dv.w * xh[i].w;
+                db[i].x += dv.x; db[i].y += dv.y; db[i].z += dv.z; db[i].w += dv.w;
+            }
+        }
+        s1 = warp_sum(s1) / C; s2 = warp_sum(s2) / C;
+        if (dx) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                const int c4 = lane + 32 * i;
+                if (c4 < C4) {
+                    float4 v;
+                    v.x = rs * (d[i].x * gm[i].x - s1 - xh[i].x * s2); v.y = rs * (d[i].y * gm[i].y - s1 - xh[i].y * s2);
+                    v.z = rs * (d[i].z * gm[i].z - s1 - xh[i].z * s2); v.w = rs * (d[i].w * gm[i].w - s1 - xh[i].w * s2);
+                    float4* o = reinterpret_cast<float4*>(dx + (long long)row * lddx) + c4;
+                    if (dx_accumulate) { const float4 t = *o; v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
+                    *o = v;
+                }
+            }
+        }
+    }
+    if (partial == nullptr) return;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c4 = lane + 32 * i;
+        if (c4 < C4) {
+            *reinterpret_cast<float4*>(&sm[(warp * 2 + 0) * C + 4 * c4]) = dg[i];
+            *reinterpret_cast<float4*>(&sm[(warp * 2 + 1) * C + 4 * c4]) = db[i];
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < 2 * C; c += 256) {
+        const int which = c / C, cc = c - which * C;
+        float a = 0.f;
+        for (int w = 0; w < 8; ++w) a += sm[(w * 2 + which) * C + cc];
+        partial[((long long)blockIdx.x * 2 + which) * C + cc] = a;
+    }
+}
+
 int launch_layernorm_bwd(const float* x, long long ldx, const float* dy, long long lddy, int rows, int C,
                          const float* gamma, const float* mean, const float* rstd, const float* y_for_relu, long long ldy,
                          float* dx, long long lddx, int dx_accumulate, float* dgamma, float* dbeta, float* scratch,
@@ -214,6 +294,36 @@ int launch_layernorm_bwd(const float* x, long long ldx, const float* dy, long lo
     RIFT_REQUIRE(C <= LNB_MAXC, "layernorm_bwd: C too large");
     RIFT_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "layernorm_bwd: dgamma/dbeta go together");
     RIFT_REQUIRE(dgamma == nullptr || scratch != nullptr, "layernorm_bwd: scratch required for parameter gradients");
+    {
+        auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+        const bool vec = (C & 3) == 0 && (ldx & 3) == 0 && (lddy & 3) == 0 && (ldy & 3) == 0 && (lddx & 3) == 0 && al16(x) &&
+                         al16(dy) && al16(y_for_relu) && al16(dx) && al16(gamma);
+        if (vec) {
+            // more, smaller blocks than the partial buffer has slots is not possible: LNB_BLOCKS partial rows
+            const int nb4 = min(cdiv(rows, 8), LNB_BLOCKS);
+            const size_t smem4 = (size_t)8 * 2 * C * sizeof(float);
+            float* part = dgamma ? scratch : nullptr;
+            const int nv = cdiv(C, 128);
+#define RIFT_LNB4(NV)                                                                                                       \
+    layernorm_bwd4_kernel<NV><<<nb4, 256, smem4, st>>>(x, ldx, dy, lddy, rows, C, gamma, mean, rstd, y_for_relu, ldy, dx, \
+                                                       lddx, dx_accumulate, part)
+            static bool attr4 = false;
+            if (!attr4) {
+                RIFT_CUDA_OK(cudaFuncSetAttribute(layernorm_bwd4_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * LNB_MAXC * 4));
+                attr4 = true;
+            }
+            if (nv <= 1) RIFT_LNB4(1); else if (nv == 2) RIFT_LNB4(2); else if (nv <= 4) RIFT_LNB4(4); else RIFT_LNB4(8);
+#undef RIFT_LNB4
+            RIFT_LAUNCH_OK();
+            if (dgamma) {
+                colsum_final_kernel<<<cdiv(C, 32), 256, 0, st>>>(scratch, nb4, 2LL * C, C, dgamma, 1);
+                RIFT_LAUNCH_OK();
+                colsum_final_kernel<<<cdiv(C, 32), 256, 0, st>>>(scratch + C, nb4, 2LL * C, C, dbeta, 1);
+                RIFT_LAUNCH_OK();
+            }
+            return 0;
+        }
+    }
     const int nb = min(cdiv(rows, 8), LNB_BLOCKS);
     const size_t smem = (size_t)8 * 2 * C * sizeof(float);
     static bool attr = false;
