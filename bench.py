@@ -219,6 +219,16 @@ def run_ours(args, wl_name, wl, cfg):
     for _ in range(args.warmup):
         tr.step(batch_dev)
     sync()
+    if args.ncu:
+        # profiling aid (never a bench number): exactly one policy update between cudaProfilerStart/Stop, for
+        # `ncu --profile-from-start off ... python bench.py --ncu`
+        flush.zero_()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        tr.step(batch_dev)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
     sampler = ClockSampler(local)
     sampler.start()
     L = _lib.lib()
@@ -329,7 +339,10 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--trainable", default="pi_head", choices=["pi_head", "full"])
+    ap.add_argument("--trainable", default="full", choices=["pi_head", "full"],
+                    help="full = differentiate the whole policy (headline, SURVEY 8d); pi_head = the reference's default "
+                         "trainable_layers (rift_training.yaml:26-27)")
+    ap.add_argument("--ncu", action="store_true", help="run one step inside cudaProfilerStart/Stop and exit (for ncu)")
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", dest="no_cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
