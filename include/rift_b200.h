@@ -36,6 +36,10 @@ const char* rift_b200_last_error(void);
 int rift_b200_version(void);
 /* number of CUDA kernels this library has launched so far in this process (bench.py: gpu_launches) */
 long long rift_b200_launch_count(void);
+/* profiling aid: CTA 0 of every following tcgen05 GEMM launch writes %globaltimer stamps (ns) into dev_buf
+ * (64 uint64: 0 entry, 1 set-up done, 2 first operands landed, 3 first tile's MMAs issued, 4+2i / 5+2i
+ * epilogue start / end of its i-th tile, 60 last role done, 61 TMEM released); NULL switches it off */
+void rift_b200_debug_gemm_trace(void* dev_buf);
 
 /* ---- model description (PlanningModel.__init__, pluto_model.py:23-44) ---- */
 typedef struct {

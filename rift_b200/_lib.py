@@ -60,6 +60,7 @@ _SIGNATURES = {
     "rift_b200_last_error": (C.c_char_p, []),
     "rift_b200_version": (C.c_int, []),
     "rift_b200_launch_count": (C.c_longlong, []),
+    "rift_b200_debug_gemm_trace": (None, [_V]),
     "rift_b200_create": (C.c_int, [C.POINTER(ModelConfig), C.POINTER(ParamEntry), C.c_int, C.POINTER(_V)]),
     "rift_b200_destroy": (None, [_V]),
     "rift_b200_bind_arena": (C.c_int, [_V, _V, _V, C.c_longlong]),

@@ -20,6 +20,7 @@ extern "C" {
 const char* rift_b200_last_error(void) { return get_last_error(); }
 int rift_b200_version(void) { return 100; }
 long long rift_b200_launch_count(void) { return g_kernel_launches; }
+void rift_b200_debug_gemm_trace(void* dev_buf) { set_gemm_tc_trace(dev_buf); }
 
 int rift_b200_create(const rift_b200_model_config* cfg, const rift_b200_param_entry* entries, int n_entries,
                      rift_b200_engine** out) {

@@ -10,6 +10,8 @@
 // Activations that feed a GEMM travel as split-bf16 planes written directly by their producer
 // (LayerNorm, attention, GEMM epilogues, im2col, pooling); fp32 copies are kept only where another
 // kernel reads them (residual stream, attention q/k/v, pooling inputs) or when the backward needs them.
+#include <stdlib.h>
+
 #include "engine_ops.h"
 
 using namespace rift;
@@ -154,6 +156,30 @@ int rift_b200_engine::refresh_weights(cudaStream_t st) {
     else if (dirty_train) TRY(launch_split_weights(jobs_train, n_jobs_train, total_train, st));
     dirty_all = dirty_train = false;
     return 0;
+}
+
+// ---- fork / join streams ----------------------------------------------------------------------
+int rift_b200_engine::attach_streams(Ctx& c) {
+    if (c.dry) return 0;
+    if (streams_state == 0) {
+        const char* env = getenv("RIFT_B200_STREAMS");
+        if (env && atoi(env) == 0) streams_state = -1;
+        else {
+            RIFT_CUDA_OK(cudaStreamCreateWithFlags(&s_side, cudaStreamNonBlocking));
+            RIFT_CUDA_OK(cudaStreamCreateWithFlags(&s_br, cudaStreamNonBlocking));
+            events.resize(64);
+            for (auto& ev : events) RIFT_CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            streams_state = 1;
+        }
+    }
+    if (streams_state == 1) { c.side = s_side; c.br = s_br; c.events = events.data(); c.n_events = (int)events.size(); }
+    return 0;
+}
+
+rift_b200_engine::~rift_b200_engine() {
+    for (auto& ev : events) cudaEventDestroy(ev);
+    if (s_side) cudaStreamDestroy(s_side);
+    if (s_br) cudaStreamDestroy(s_br);
 }
 
 int rift_b200_engine::build_model() {

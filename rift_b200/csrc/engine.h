@@ -84,6 +84,12 @@ struct Ctx {            // per-call state: stream + bump allocator over the call
     bool full = false;     // save && trainable parameters outside pi_head: keep every activation (fp32)
     bool tc_bwd = false;   // backward GEMMs on the tcgen05 path (false: exact-fp32 SIMT)
     const std::vector<TcWeight>* tcw = nullptr;
+    // fork / join streams (null: everything stays on `st`).  `side` carries parameter-gradient work of the
+    // backward (weight-gradient GEMMs, bias / LayerNorm-parameter reductions), `br` whole independent branches
+    // (map / reference-line encoders in the forward, parameter-only sub-graphs in the backward).
+    cudaStream_t side = nullptr, br = nullptr;
+    cudaEvent_t* events = nullptr; int n_events = 0; int ev_next = 0;
+    cudaEvent_t next_event() { cudaEvent_t e = events[ev_next]; ev_next = (ev_next + 1) % n_events; return e; }
     template <class T> T* alloc(size_t n) {
         const size_t bytes = (n * sizeof(T) + 255) & ~(size_t)255;
         const size_t at = off;
@@ -168,6 +174,12 @@ struct rift_b200_engine {
     int bind_weight_cache(void* cache, size_t bytes);
     int refresh_weights(cudaStream_t st);
     size_t fwd_ws_end = 0;                    // workspace offset where backward scratch may start
+    // fork / join streams of the schedules (created on first use; RIFT_B200_STREAMS=0 keeps one stream)
+    cudaStream_t s_side = nullptr, s_br = nullptr;
+    std::vector<cudaEvent_t> events;
+    int streams_state = 0;                    // 0 = not initialised, 1 = on, -1 = off
+    int attach_streams(rift::Ctx& c);
+    ~rift_b200_engine();
 
     int build_model();
     int forward(const rift_b200_batch& bt, const rift_b200_outputs& out, rift::Ctx& c);

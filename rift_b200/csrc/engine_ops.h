@@ -21,6 +21,30 @@ namespace rift {
         return -1;                                                                 \
     }
 
+// ---------------------------------------------------------------- fork / join between the schedule's streams
+// `to` starts after everything enqueued on c.st so far
+inline int fork_to(Ctx& c, cudaStream_t to) {
+    if (c.dry || !to || to == c.st) return 0;
+    cudaEvent_t e = c.next_event();
+    RIFT_CUDA_OK(cudaEventRecord(e, c.st));
+    RIFT_CUDA_OK(cudaStreamWaitEvent(to, e, 0));
+    return 0;
+}
+// c.st continues after everything enqueued on `from` so far
+inline int join_from(Ctx& c, cudaStream_t from) {
+    if (c.dry || !from || from == c.st) return 0;
+    cudaEvent_t e = c.next_event();
+    RIFT_CUDA_OK(cudaEventRecord(e, from));
+    RIFT_CUDA_OK(cudaStreamWaitEvent(c.st, e, 0));
+    return 0;
+}
+// launches inside the scope go to `s` (when non-null)
+struct OnStream {
+    Ctx& c; cudaStream_t saved;
+    OnStream(Ctx& c_, cudaStream_t s) : c(c_), saved(c_.st) { if (s) c.st = s; }
+    ~OnStream() { c.st = saved; }
+};
+
 constexpr int W_F = 1, W_P = 2;             // "want" bits for an activation: fp32 / split planes
 constexpr int NFREQ = 64, FIN = 129;
 constexpr int PE_H1 = 128, PE_H2 = 256;

@@ -37,6 +37,7 @@ namespace rift {
 
 constexpr int TC_BM = 128, TC_BK = 64, TC_STAGES = 3;
 constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_EPI_PITCH = 32;         // floats per staged row (128 B); 16-byte chunks are XOR-swizzled with (row & 7)
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 
 // ---------------------------------------------------------------------------------- PTX wrappers
@@ -143,19 +144,36 @@ struct TcKernelArgs {
     TcEpilogue ep;
     Planes out;              // optional split-bf16 copy of the result for the next GEMM (C may then be null)
     int dbg;                 // bottleneck experiments only (RIFT_B200_TC_DBG)
+    unsigned long long* trace;   // profiling aid (rift_b200_debug_gemm_trace): CTA 0 writes %globaltimer stamps
 };
+
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define TC_TRACE(slot) do { if (g.trace && blockIdx.x == 0) g.trace[(slot)] = gtimer(); } while (0)
 
 template <int BN>
 struct TcSmem {
     static constexpr int A_TILE = TC_BM * TC_BK * 2;     // bytes per bf16 plane
     static constexpr int B_TILE = BN * TC_BK * 2;
     static constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;
-    static constexpr int EPI = TC_EPI_WARPS * 32 * 33 * 4;                 // per-warp 32 x 33 fp32 transpose tiles
+    static constexpr int EPI = TC_EPI_WARPS * 32 * TC_EPI_PITCH * 4;       // per-warp 32 x 32 fp32 staging tiles
     static constexpr int TOTAL = TC_STAGES * STAGE + 1024 /*align*/ + 256 /*barriers*/ + EPI;
 };
 constexpr int TC_BOX = 64 * 64 * 2;      // bytes of one 64 x 64 bf16 TMA box
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+// explicit shared-space 16-byte accesses (a generic pointer into dynamic shared memory compiles to slow generic LD / ST)
+__device__ __forceinline__ void sts4(uint32_t addr, const float4& v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
+}
+__device__ __forceinline__ float4 lds4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
 
 template <int BN, bool MN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -173,6 +191,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     float* stage_t = reinterpret_cast<float*>(smem + TC_STAGES * SM::STAGE + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) TC_TRACE(0);
     const int tiles_n = (g.N + BN - 1) / BN;
     const int tiles_m = (g.M + TC_BM - 1) / TC_BM;
     const int tiles_mn = tiles_m * tiles_n;
@@ -193,6 +212,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) TC_TRACE(1);
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -247,6 +267,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                     const uint32_t ph = (it / TC_STAGES) & 1;
                     mbar_wait(&full[s], ph);
                     tc_fence_after();
+                    if (it == 0) TC_TRACE(2);
                     const uint32_t a_hi = smem_u32(smem + s * SM::STAGE);
                     const uint32_t a_lo = a_hi + SM::A_TILE;
                     const uint32_t b_hi = a_lo + SM::A_TILE;
@@ -263,6 +284,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                     umma_commit(&empty[s]);                      // frees the stage once these MMAs retire
                 }
                 umma_commit(&acc_full[buf]);
+                if (ti == 0) TC_TRACE(3);
             }
         }
     } else {
@@ -278,20 +300,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             const int buf = ti & 1;
             mbar_wait(&acc_full[buf], (ti >> 1) & 1);
             tc_fence_after();
-            // Row phase: TMEM hands every thread one accumulator ROW; the fused epilogue math runs there with
-            // 16-byte operand loads.  Store phase: a 32 x 32 transpose through shared memory gives every lane one
-            // COLUMN, so fp32 rows leave as 128-byte and the bf16 planes as 64-byte coalesced warp stores.
+            if (ew == 0 && lane == 0 && ti < 24) TC_TRACE(4 + 2 * ti);
+            // Row phase: TMEM hands every thread one accumulator ROW.  The fused epilogue math runs there as
+            // straight-line, branch-free code (operand addresses are clamped, out-of-range results are zeroed by a
+            // select) so the eight 4-column groups of a chunk are independent instruction streams the scheduler can
+            // interleave; the row is then parked in a 32 x 32 shared-memory tile whose 16-byte chunks are
+            // XOR-swizzled with (row & 7) - conflict free for both phases.  Store phase: lane = (row l/8 + 4*it,
+            // column quad l%8), so one warp instruction moves 4 rows x 128 B of fp32 (or 4 x 64 B of each bf16
+            // plane) with 16-byte accesses.
             const int mrow0 = m0 + quarter * 32;
             const int m = mrow0 + lane;
             const bool row_ok = m < g.M;
-            const float* pre_row = e.pre ? e.pre + (long long)(m / e.pre_div) * e.ldpre : nullptr;
+            const int mc = min(m, g.M - 1);                  // clamped row for operand addresses
+            const float* pre_row = e.pre ? e.pre + (long long)(mc / e.pre_div) * e.ldpre : nullptr;
             const float* res_row = nullptr;
-            if (e.res) res_row = e.res + (long long)(e.res_mod > 0 ? (m % e.res_mod) : (m / e.res_div)) * e.ldres;
-            float* c_base = g.C ? g.C + (long long)sp * g.split_stride + (long long)mrow0 * g.ldc : nullptr;
-            float* pa_base = e.preact ? e.preact + (long long)mrow0 * g.ldc : nullptr;
-            float* tbuf = stage_t + ew * (32 * 33);
+            if (e.res) res_row = e.res + (long long)(e.res_mod > 0 ? (mc % e.res_mod) : (mc / e.res_div)) * e.ldres;
+            const uint32_t tb = smem_u32(stage_t + ew * (32 * TC_EPI_PITCH));
+            const uint32_t tb_row = tb + (uint32_t)lane * (TC_EPI_PITCH * 4);              // row phase: my row
+            const uint32_t sw_row = (uint32_t)(lane & 7);
+            const int srow = lane >> 3, sq = (lane & 7) * 4;                               // store phase: my row offset / quad
+            // store-phase row = srow + 4 * it, so (row & 7) = (srow + 4 * (it & 1)) & 7
+            const uint32_t tb_st0 = tb + (uint32_t)srow * (TC_EPI_PITCH * 4) + ((((uint32_t)lane & 7) ^ ((uint32_t)srow & 7)) << 4);
+            const uint32_t tb_st1 = tb + (uint32_t)srow * (TC_EPI_PITCH * 4) + ((((uint32_t)lane & 7) ^ ((uint32_t)(srow + 4) & 7)) << 4);
             const int rows_here = min(32, g.M - mrow0);
-            const int l16 = lane & 15;
+            const long long row_step = 4LL * g.ldc;
+            float* c_row = g.C ? g.C + (long long)sp * g.split_stride + (long long)(mrow0 + srow) * g.ldc : nullptr;
+            float* pa_row = e.preact ? e.preact + (long long)(mrow0 + srow) * g.ldc : nullptr;
 #pragma unroll 1
             for (int cc = 0; cc < BN / 2; cc += 32) {
                 const int c0 = half * (BN / 2) + cc;
@@ -299,68 +333,113 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 tmem_ld_32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN + c0), r);
                 tmem_ld_wait();
                 if (g.dbg & 1) continue;
-                const int ncol = n0 + c0 + lane;                 // this lane's column in the store phase
-                if (pa_base) {                                   // value before the activation (saved for backward)
+                const int ncol = n0 + c0 + sq;                   // this lane's first column in the store phase
+                const bool col_ok = ncol < g.N;
+                // ---- linear part: r <- (alpha * acc + pre) * colscale + bias
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const int n = n0 + c0 + j;
-                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (row_ok && n < g.N) {
-                            v = make_float4(__uint_as_float(r[j]) * e.alpha, __uint_as_float(r[j + 1]) * e.alpha,
-                                            __uint_as_float(r[j + 2]) * e.alpha, __uint_as_float(r[j + 3]) * e.alpha);
-                            if (pre_row) { const float4 t = ld4(pre_row + n); v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
-                            if (e.colscale) { const float4 t = ld4(e.colscale + n); v.x *= t.x; v.y *= t.y; v.z *= t.z; v.w *= t.w; }
-                            if (e.bias) { const float4 t = ld4(e.bias + n); v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
-                        }
-                        tbuf[lane * 33 + j] = v.x; tbuf[lane * 33 + j + 1] = v.y; tbuf[lane * 33 + j + 2] = v.z; tbuf[lane * 33 + j + 3] = v.w;
+                for (int j = 0; j < 32; j += 4) {
+                    const int n = min(n0 + c0 + j, g.N - 4);     // clamped (N % 4 == 0, N >= 16)
+                    float4 v = make_float4(__uint_as_float(r[j]) * e.alpha, __uint_as_float(r[j + 1]) * e.alpha,
+                                           __uint_as_float(r[j + 2]) * e.alpha, __uint_as_float(r[j + 3]) * e.alpha);
+                    if (pre_row) { const float4 t = ld4(pre_row + n); v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
+                    if (e.colscale) { const float4 t = ld4(e.colscale + n); v.x *= t.x; v.y *= t.y; v.z *= t.z; v.w *= t.w; }
+                    if (e.bias) { const float4 t = ld4(e.bias + n); v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
+                    r[j] = __float_as_uint(v.x); r[j + 1] = __float_as_uint(v.y);
+                    r[j + 2] = __float_as_uint(v.z); r[j + 3] = __float_as_uint(v.w);
+                }
+                if (pa_row) {                                    // value before the activation (saved for backward)
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        sts4(tb_row + ((((uint32_t)j >> 2) ^ sw_row) << 4),
+                             make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                         __uint_as_float(r[j + 3])));
+                    __syncwarp();
+                    float4 w[8];
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) w[it] = lds4(((it & 1) ? tb_st1 : tb_st0) + it * (4 * TC_EPI_PITCH * 4));
+                    if (col_ok) {
+                        float* pp = pa_row + ncol;
+#pragma unroll
+                        for (int it = 0; it < 8; ++it)
+                            if (srow + 4 * it < rows_here) *reinterpret_cast<float4*>(pp + it * row_step) = w[it];
                     }
                     __syncwarp();
-                    if (ncol < g.N)
-                        for (int rr = 0; rr < rows_here; ++rr) pa_base[(long long)rr * g.ldc + ncol] = tbuf[rr * 33 + lane];
-                    __syncwarp();
+                }
+                // ---- activation, residual, zero outside the valid range (uniform switches hoisted out of the loops)
+                if (e.act == ACT_RELU) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(fmaxf(__uint_as_float(r[j]), 0.f));
+                } else if (e.act == ACT_GELU) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(gelu_erf(__uint_as_float(r[j])));
+                }
+                if (res_row) {
+                    float4 t[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) t[j] = ld4(res_row + min(n0 + c0 + 4 * j, g.N - 4));
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        r[4 * j] = __float_as_uint(__uint_as_float(r[4 * j]) + t[j].x);
+                        r[4 * j + 1] = __float_as_uint(__uint_as_float(r[4 * j + 1]) + t[j].y);
+                        r[4 * j + 2] = __float_as_uint(__uint_as_float(r[4 * j + 2]) + t[j].z);
+                        r[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) + t[j].w);
+                    }
                 }
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
-                    const int n = n0 + c0 + j;
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (row_ok && n < g.N) {
-                        v = make_float4(__uint_as_float(r[j]) * e.alpha, __uint_as_float(r[j + 1]) * e.alpha,
-                                        __uint_as_float(r[j + 2]) * e.alpha, __uint_as_float(r[j + 3]) * e.alpha);
-                        if (pre_row) { const float4 t = ld4(pre_row + n); v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
-                        if (e.colscale) { const float4 t = ld4(e.colscale + n); v.x *= t.x; v.y *= t.y; v.z *= t.z; v.w *= t.w; }
-                        if (e.bias) { const float4 t = ld4(e.bias + n); v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
-                        if (e.act == ACT_RELU) {
-                            v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-                        } else if (e.act == ACT_GELU) {
-                            v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
-                        }
-                        if (res_row) { const float4 t = ld4(res_row + n); v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
-                    }
-                    tbuf[lane * 33 + j] = v.x; tbuf[lane * 33 + j + 1] = v.y; tbuf[lane * 33 + j + 2] = v.z; tbuf[lane * 33 + j + 3] = v.w;
+                    const bool ok = row_ok && (n0 + c0 + j < g.N);
+                    sts4(tb_row + ((((uint32_t)j >> 2) ^ sw_row) << 4),
+                         make_float4(ok ? __uint_as_float(r[j]) : 0.f, ok ? __uint_as_float(r[j + 1]) : 0.f,
+                                     ok ? __uint_as_float(r[j + 2]) : 0.f, ok ? __uint_as_float(r[j + 3]) : 0.f));
                 }
                 __syncwarp();
-                if (c_base && ncol < g.N) {
-                    float* cp = c_base + ncol;
-                    if (e.beta != 0.f) {
-                        for (int rr = 0; rr < rows_here; ++rr) cp[(long long)rr * g.ldc] = tbuf[rr * 33 + lane] + e.beta * cp[(long long)rr * g.ldc];
-                    } else {
-#pragma unroll 4
-                        for (int rr = 0; rr < rows_here; ++rr) cp[(long long)rr * g.ldc] = tbuf[rr * 33 + lane];
+                if (!(g.dbg & 8)) {
+                    float4 w[8];
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) w[it] = lds4(((it & 1) ? tb_st1 : tb_st0) + it * (4 * TC_EPI_PITCH * 4));
+                    if (c_row && col_ok) {
+                        float* cp = c_row + ncol;
+                        if (e.beta != 0.f) {
+                            float4 o[8];
+#pragma unroll
+                            for (int it = 0; it < 8; ++it)
+                                o[it] = srow + 4 * it < rows_here ? *reinterpret_cast<const float4*>(cp + it * row_step)
+                                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                            for (int it = 0; it < 8; ++it)
+                                if (srow + 4 * it < rows_here)
+                                    *reinterpret_cast<float4*>(cp + it * row_step) =
+                                        make_float4(w[it].x + e.beta * o[it].x, w[it].y + e.beta * o[it].y,
+                                                    w[it].z + e.beta * o[it].z, w[it].w + e.beta * o[it].w);
+                        } else {
+#pragma unroll
+                            for (int it = 0; it < 8; ++it)
+                                if (srow + 4 * it < rows_here) *reinterpret_cast<float4*>(cp + it * row_step) = w[it];
+                        }
                     }
-                }
-                if (g.out.on()) {
-                    // lanes 0-15 write the hi plane, lanes 16-31 the lo plane; two columns (one bf16x2 word) per lane.
-                    // columns >= N hold zeros in the tile, which is exactly the planes' zero padding up to Kp
-                    const int pc = n0 + c0 + 2 * l16;
-                    if (pc < g.out.Kp) {
-                        uint16_t* dst = (lane < 16 ? g.out.hi : g.out.lo) + (long long)mrow0 * g.out.Kp + pc;
-#pragma unroll 4
-                        for (int rr = 0; rr < rows_here; ++rr) {
-                            const float a = tbuf[rr * 33 + 2 * l16], b = tbuf[rr * 33 + 2 * l16 + 1];
-                            const __nv_bfloat16 h0 = __float2bfloat16_rn(a), h1 = __float2bfloat16_rn(b);
-                            __nv_bfloat162 w = (lane < 16) ? __halves2bfloat162(h0, h1)
-                                                           : __floats2bfloat162_rn(a - __bfloat162float(h0), b - __bfloat162float(h1));
-                            *reinterpret_cast<uint32_t*>(dst + (long long)rr * g.out.Kp) = *reinterpret_cast<uint32_t*>(&w);
+                    if (g.out.on()) {
+                        // columns >= N hold zeros in the tile, which is exactly the planes' zero padding up to Kp
+                        const int pc = n0 + c0 + sq;
+                        if (pc < g.out.Kp) {
+                            uint16_t* dh = g.out.hi + (long long)(mrow0 + srow) * g.out.Kp + pc;
+                            uint16_t* dl = g.out.lo + (long long)(mrow0 + srow) * g.out.Kp + pc;
+                            const long long pstep = 4LL * g.out.Kp;
+#pragma unroll
+                            for (int it = 0; it < 8; ++it) {
+                                if (srow + 4 * it < rows_here) {
+                                    const float4 x = w[it];
+                                    const __nv_bfloat16 h0 = __float2bfloat16_rn(x.x), h1 = __float2bfloat16_rn(x.y),
+                                                        h2 = __float2bfloat16_rn(x.z), h3 = __float2bfloat16_rn(x.w);
+                                    __nv_bfloat162 a = __halves2bfloat162(h0, h1), b = __halves2bfloat162(h2, h3);
+                                    __nv_bfloat162 c2 = __floats2bfloat162_rn(x.x - __bfloat162float(h0), x.y - __bfloat162float(h1));
+                                    __nv_bfloat162 d2 = __floats2bfloat162_rn(x.z - __bfloat162float(h2), x.w - __bfloat162float(h3));
+                                    uint2 uh, ul;
+                                    uh.x = *reinterpret_cast<uint32_t*>(&a); uh.y = *reinterpret_cast<uint32_t*>(&b);
+                                    ul.x = *reinterpret_cast<uint32_t*>(&c2); ul.y = *reinterpret_cast<uint32_t*>(&d2);
+                                    *reinterpret_cast<uint2*>(dh + it * pstep) = uh;
+                                    *reinterpret_cast<uint2*>(dl + it * pstep) = ul;
+                                }
+                            }
                         }
                     }
                 }
@@ -369,13 +448,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[buf]);
+            if (ew == 0 && lane == 0 && ti < 24) TC_TRACE(5 + 2 * ti);
         }
     }
+    if (threadIdx.x == 0) TC_TRACE(60);
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 2 * BN);
+        if (lane == 0) TC_TRACE(61);
     }
 }
 
@@ -458,6 +540,9 @@ void fill_split_job(void* dst, const float* src, long long ld, int N, int K, int
 }
 
 // ---------------------------------------------------------------------------------- host side
+static unsigned long long* g_tc_trace = nullptr;      // device buffer of >= 64 u64, or null (rift_b200_debug_gemm_trace)
+void set_gemm_tc_trace(void* dev_buf) { g_tc_trace = static_cast<unsigned long long*>(dev_buf); }
+
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
     static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
     if (!fn) {
@@ -545,6 +630,7 @@ static int launch_tc(const GemmArgs& a, const PlaneOp& A, const PlaneOp& B, int 
     g.M = a.M; g.N = a.N; g.K = a.K;
     g.a_mn0 = A.mn0; g.a_k0 = A.k0; g.b_mn0 = B.mn0; g.b_k0 = B.k0;
     g.out = a.out_planes;
+    g.trace = g_tc_trace;
     { static int dbg = -1; if (dbg < 0) { const char* e = getenv("RIFT_B200_TC_DBG"); dbg = e ? atoi(e) : 0; } g.dbg = dbg; }
     if (splits > 1) {
         g.splits = splits; g.kb_per_split = cdiv(num_kb, splits);

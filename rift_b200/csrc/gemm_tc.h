@@ -32,6 +32,9 @@ int launch_gemm_tc(const GemmArgs& a, const void* a_hi, const void* a_lo, int Kp
 int launch_gemm_tc_ex(const GemmArgs& a, const PlaneOp& A, const PlaneOp& B, bool mn_major, int splits, float* partials,
                       cudaStream_t st);
 
+// profiling aid: CTA 0 of every following tcgen05 GEMM writes %globaltimer stamps into dev_buf (64 u64); null = off
+void set_gemm_tc_trace(void* dev_buf);
+
 size_t split_job_bytes();
 void fill_split_job(void* dst, const float* src, long long ld, int N, int K, int Kp, void* hi, void* lo, long long first,
                     int transpose);
