@@ -394,6 +394,10 @@ int rift_b200_engine::forward(const rift_b200_batch& bt, const rift_b200_outputs
     }
     T_.agent_any = agent_any; T_.key_pad = key_pad; T_.r_pad = r_pad;
     ALLOC(tokens, float, (size_t)bs * S * D);
+    // The map encoder and the reference-line encoder / query initialisation depend only on the inputs: they run
+    // on the branch stream next to the agent encoder (joined before pos_emb and before the decoder respectively).
+    TRY(attach_streams(c));
+    TRY(fork_to(c, c.br));
 
     // ---------------- AgentEncoder (modules/agent_encoder.py:54-94)
     {
@@ -509,6 +513,7 @@ int rift_b200_engine::forward(const rift_b200_batch& bt, const rift_b200_outputs
 
     // ---------------- MapEncoder (modules/map_encoder.py:31-93)
     if (Mp > 0) {
+        OnStream on_br(c, c.br);
         const int NP = bs * Mp;
         Act Fm, x_poly;
         TRY(new_act(c, NP * P, 10, W_F, &Fm));
@@ -524,7 +529,34 @@ int rift_b200_engine::forward(const rift_b200_batch& bt, const rift_b200_outputs
                                     m.map_unknown_emb.p, bs, Mp, A, S, D, tokens, c.st));
     }
 
+    // recorded here, waited for by the main stream right before pos_emb: covers the map tokens only (the branch
+    // keeps going with the reference lines / queries)
+    cudaEvent_t map_done = nullptr;
+    if (!c.dry && c.br) { map_done = c.next_event(); RIFT_CUDA_OK(cudaEventRecord(map_done, c.br)); }
+    const int NR = bs * R, rowsQ = bs * R * Mo;
+    float* q = nullptr;
+    {   // reference-line encoder + query initialisation (planning_decoder.py:135-160), on the branch stream
+        OnStream on_br(c, c.br);
+        Act Fr, r_enc, r_emb, u, v;
+        const Lin qa = slice(m.q_proj, 0, D, 0, D, false), qb = slice(m.q_proj, 0, D, D, D, true);
+        TRY(new_act(c, NR * Pr, 6, W_F, &Fr));
+        ALLOC(rpos, float, (size_t)NR * 3);
+        if (!c.dry) TRY(launch_ref_features(bt.ref_position, bt.ref_vector, bt.ref_orientation, NR, Pr, Fr.f, rpos, c.st));
+        T_.rpos = rpos;
+        TRY(points_encoder(c, Fr, NR, Pr, bt.ref_valid_mask, m.r_enc, &r_enc, W_F, full ? &T_.renc : nullptr));
+        TRY(new_act(c, NR, D, W_F, &r_emb));
+        TRY(fourier(c, rpos, NR, m.r_pos_emb, r_emb.f, r_enc.f, full ? &T_.rpos_emb : nullptr));
+        T_.r_emb = r_emb;
+        // q = q_proj(cat[r_emb (per line), m_emb (per mode)]) split into its two column blocks
+        TRY(linear_new(c, r_emb, qa, Epi(), W_F, &u));
+        Act me = act_f32(const_cast<float*>(m.m_emb.p), D, Mo, D);
+        TRY(linear_new(c, me, qb, Epi(), W_F, &v));
+        q = c.alloc<float>((size_t)rowsQ * D);
+        if (!q) { set_last_error("workspace too small"); return -1; }
+        if (!c.dry) TRY(launch_query_init(u.f, v.f, rowsQ, Mo, D, q, c.st));
+    }
     // ---------------- + pos_emb, encoder blocks, final norm (pluto_model.py:144-154)
+    if (map_done) RIFT_CUDA_OK(cudaStreamWaitEvent(c.st, map_done, 0));
     ALLOC(pos, float, (size_t)bs * S * 3);
     float* X = c.alloc<float>((size_t)bs * S * D);
     if (!X) { set_last_error("workspace too small"); return -1; }
@@ -593,27 +625,7 @@ int rift_b200_engine::forward(const rift_b200_batch& bt, const rift_b200_outputs
     }
 
     // ---------------- PlanningDecoder (modules/planning_decoder.py:135-188)
-    const int NR = bs * R, rowsQ = bs * R * Mo;
-    float* q = nullptr;
-    {
-        Act Fr, r_enc, r_emb, u, v;
-        const Lin qa = slice(m.q_proj, 0, D, 0, D, false), qb = slice(m.q_proj, 0, D, D, D, true);
-        TRY(new_act(c, NR * Pr, 6, W_F, &Fr));
-        ALLOC(rpos, float, (size_t)NR * 3);
-        if (!c.dry) TRY(launch_ref_features(bt.ref_position, bt.ref_vector, bt.ref_orientation, NR, Pr, Fr.f, rpos, c.st));
-        T_.rpos = rpos;
-        TRY(points_encoder(c, Fr, NR, Pr, bt.ref_valid_mask, m.r_enc, &r_enc, W_F, full ? &T_.renc : nullptr));
-        TRY(new_act(c, NR, D, W_F, &r_emb));
-        TRY(fourier(c, rpos, NR, m.r_pos_emb, r_emb.f, r_enc.f, full ? &T_.rpos_emb : nullptr));
-        T_.r_emb = r_emb;
-        // q = q_proj(cat[r_emb (per line), m_emb (per mode)]) split into its two column blocks
-        TRY(linear_new(c, r_emb, qa, Epi(), W_F, &u));
-        Act me = act_f32(const_cast<float*>(m.m_emb.p), D, Mo, D);
-        TRY(linear_new(c, me, qb, Epi(), W_F, &v));
-        q = c.alloc<float>((size_t)rowsQ * D);
-        if (!q) { set_last_error("workspace too small"); return -1; }
-        if (!c.dry) TRY(launch_query_init(u.f, v.f, rowsQ, Mo, D, q, c.st));
-    }
+    TRY(join_from(c, c.br));                 // query initialisation (branch stream) is complete
     T_.dec.clear();
     for (const DecBlockP& db : m.dec) {
         DecBlockTape dt;

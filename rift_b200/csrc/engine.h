@@ -184,4 +184,5 @@ struct rift_b200_engine {
     int build_model();
     int forward(const rift_b200_batch& bt, const rift_b200_outputs& out, rift::Ctx& c);
     int backward(const rift_b200_batch& bt, const float* dlogits, rift::Ctx& c);
+    int backward_impl(const rift_b200_batch& bt, const float* dlogits, rift::Ctx& c);
 };

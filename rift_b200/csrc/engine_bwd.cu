@@ -115,6 +115,16 @@ static int mlp_tail_bwd(Ctx& c, int rows, int D, int Hd, const Act& hm, const fl
 }  // namespace rift
 
 int rift_b200_engine::backward(const rift_b200_batch& bt, const float* dlogits, Ctx& c) {
+    TRY(attach_streams(c));
+    int r = backward_impl(bt, dlogits, c);
+    if (r) return r;
+    // parameter-gradient work (side stream) and the parameter-only branches rejoin the caller's stream here
+    TRY(join_from(c, c.br));
+    TRY(join_from(c, c.side));
+    return 0;
+}
+
+int rift_b200_engine::backward_impl(const rift_b200_batch& bt, const float* dlogits, Ctx& c) {
     RIFT_REQUIRE(grads != nullptr, "backward: no gradient arena bound");
     RIFT_REQUIRE(c.dry || tape.valid, "backward: run forward with RIFT_B200_FWD_SAVE_FOR_BACKWARD first");
     const int D = cfg.dim, H = cfg.num_heads, Mo = cfg.num_modes;
@@ -233,9 +243,13 @@ int rift_b200_engine::backward(const rift_b200_batch& bt, const float* dlogits, 
         }
         TRY(lin_bwd(c, tp.r_emb.f, D, du, D, NR, qa, d_remb, D, 0.f, false));
         TRY(lin_bwd(c, m.m_emb.p, D, dv, D, Mo, qb, m.m_emb.train ? m.m_emb.d : nullptr, D, 1.f));
-        // r_emb = r_encoder(points) + r_pos_emb(first point)
-        TRY(fourier_bwd(c, tp.rpos_emb, m.r_pos_emb, d_remb));
-        TRY(points_bwd(c, tp.renc, m.r_enc, d_remb));
+        // r_emb = r_encoder(points) + r_pos_emb(first point): parameter-only sub-graphs -> branch stream
+        TRY(fork_to(c, c.br));
+        {
+            OnStream on_br(c, c.br);
+            TRY(fourier_bwd(c, tp.rpos_emb, m.r_pos_emb, d_remb));
+            TRY(points_bwd(c, tp.renc, m.r_enc, d_remb));
+        }
     }
 
     // ---------------- scene encoding: final norm <- encoder blocks
@@ -259,7 +273,12 @@ int rift_b200_engine::backward(const rift_b200_batch& bt, const float* dlogits, 
     }
 
     // ---------------- tokens = [agent tokens ; map tokens] + pos_emb
-    TRY(fourier_bwd(c, tp.pos_emb, m.pos_emb, dX));
+    // dX is final from here on (only read below): pos_emb's parameters on the branch stream
+    TRY(fork_to(c, c.br));
+    {
+        OnStream on_br(c, c.br);
+        TRY(fourier_bwd(c, tp.pos_emb, m.pos_emb, dX));
+    }
     ALLOC(esc, float, (size_t)148 * 4 * D);
     // map side
     if (Mp > 0) {
@@ -280,8 +299,12 @@ int rift_b200_engine::backward(const rift_b200_batch& bt, const float* dlogits, 
                 TRY(launch_embedding_bwd(dX, D, A, Mp, S, reinterpret_cast<const int8_t*>(bt.map_polygon_has_speed_limit), NP, D, 1,
                                          m.map_unknown_emb.d, 1, esc, c.st));
         }
-        TRY(points_bwd(c, tp.poly, m.poly_enc, dx_poly));
-        TRY(fourier_bwd(c, tp.speed, m.speed_emb, dx_speed));
+        TRY(fork_to(c, c.br));
+        {
+            OnStream on_br(c, c.br);
+            TRY(points_bwd(c, tp.poly, m.poly_enc, dx_poly));
+            TRY(fourier_bwd(c, tp.speed, m.speed_emb, dx_speed));
+        }
     }
     // agent side
     {

@@ -241,6 +241,18 @@ inline int lin_bwd(Ctx& c, const float* X, long long ldx, const float* dY, long 
         if (!dYp.hi || !dYp.lo) { set_last_error("workspace too small"); return -1; }
         if (!c.dry) TRY(launch_pack_split(dY, lddy, M, L.N, dYp.Kp, dYp.hi, dYp.lo, c.st));
     }
+    // Parameter gradients go to the side stream: they read only dYp / the saved operand planes / private partial
+    // buffers (never the fp32 dY, which the main stream may update in place later) and nothing downstream on the
+    // main stream depends on them before the final join of backward().
+    bool forked = false;
+    if (bias_grad && L.train && L.db) {
+        ALLOC(sc, float, (size_t)148 * L.N);
+        if (!c.dry) {
+            SideStream fin;
+            if (c.side) { fin.st = c.side; fin.ev = c.next_event(); forked = true; }
+            TRY(launch_colsum(dY, lddy, M, L.N, L.db, 1, sc, c.st, fin));
+        }
+    }
     if (tc_w) {
         Planes xp;
         if (Xp && Xp->on()) xp = *Xp;
@@ -250,6 +262,7 @@ inline int lin_bwd(Ctx& c, const float* X, long long ldx, const float* dY, long 
             xp.lo = c.alloc<uint16_t>((size_t)M * xp.Kp);
             if (!xp.hi || !xp.lo) { set_last_error("workspace too small"); return -1; }
             if (!c.dry) TRY(launch_pack_split(X, ldx, M, L.K, xp.Kp, xp.hi, xp.lo, c.st));
+            forked = false;                      // the side stream has not seen this pack yet
         }
         const int tiles = ((L.N + 127) / 128) * ((L.K + (L.K <= 64 ? 63 : 127)) / (L.K <= 64 ? 64 : 128));
         const int num_kb = (M + 63) / 64;
@@ -259,6 +272,8 @@ inline int lin_bwd(Ctx& c, const float* X, long long ldx, const float* dY, long 
         float* ws = nullptr;
         if (splits > 1) { ws = c.alloc<float>((size_t)splits * L.N * L.K); if (!ws) { set_last_error("workspace too small"); return -1; } }
         if (!c.dry) {
+            if (!forked) TRY(fork_to(c, c.side));
+            OnStream on(c, c.side);
             GemmArgs a;
             a.C = L.dW; a.ldc = L.ldw; a.M = L.N; a.N = L.K; a.K = M; a.beta = 1.f;
             PlaneOp A{dYp.hi, dYp.lo, M, dYp.Kp, 0, 0};
@@ -275,10 +290,6 @@ inline int lin_bwd(Ctx& c, const float* X, long long ldx, const float* dY, long 
         a.C = L.dW; a.ldc = L.ldw; a.M = L.N; a.N = L.K; a.K = M; a.beta = 1.f;
         a.split_k = splits; a.split_ws = ws;
         TRY(simt(c, a));
-    }
-    if (bias_grad && L.train && L.db) {
-        ALLOC(sc, float, (size_t)148 * L.N);
-        if (!c.dry) TRY(launch_colsum(dY, lddy, M, L.N, L.db, 1, sc, c.st));
     }
     if (tc_d) {
         if (!c.dry) {
@@ -303,8 +314,10 @@ inline int ln_bwd(Ctx& c, const LNSave& s, const Norm& n, const float* dy, const
     ALLOC(sc, float, (size_t)layernorm_bwd_scratch_floats(n.C));
     if (c.dry) return 0;
     const bool pg = n.train && n.dg;
+    SideStream fin;
+    if (pg && c.side) { fin.st = c.side; fin.ev = c.next_event(); }       // dgamma / dbeta reduction off the main chain
     return launch_layernorm_bwd(s.x, n.C, dy, n.C, s.rows, n.C, n.g, s.mean, s.rstd, y_relu, n.C, dx, n.C, accumulate,
-                                pg ? n.dg : nullptr, pg ? n.db : nullptr, sc, c.st);
+                                pg ? n.dg : nullptr, pg ? n.db : nullptr, sc, c.st, fin);
 }
 
 }  // namespace rift

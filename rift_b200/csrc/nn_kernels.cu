@@ -205,6 +205,19 @@ int layernorm_bwd_scratch_floats(int C) { return LNB_BLOCKS * 2 * C; }
 
 __global__ void colsum_final_kernel(const float* __restrict__ partial, int nb, long long stride, int C, float* __restrict__ out,
                                     int accumulate);
+// dgamma (blockIdx.y = 0) and dbeta (1) of one LayerNorm in a single launch
+__global__ void colsum_final2_kernel(const float* __restrict__ partial, int nb, int C, float* __restrict__ out0,
+                                     float* __restrict__ out1);
+// stream the second reduction stage runs on (see SideStream)
+static inline int second_stage_stream(cudaStream_t st, const SideStream& fin, cudaStream_t* out) {
+    *out = st;
+    if (fin.st && fin.st != st) {
+        RIFT_CUDA_OK(cudaEventRecord(fin.ev, st));
+        RIFT_CUDA_OK(cudaStreamWaitEvent(fin.st, fin.ev, 0));
+        *out = fin.st;
+    }
+    return 0;
+}
 
 // 16-byte vectorised backward (C = 128 * NV, rows 16-byte aligned): each lane owns NV float4 column groups, the
 // whole row lives in registers between the statistics pass and the dx pass, and the per-lane dgamma / dbeta
@@ -289,7 +302,7 @@ layernorm_bwd4_kernel(const float* __restrict__ x, long long ldx, const float* _
 int launch_layernorm_bwd(const float* x, long long ldx, const float* dy, long long lddy, int rows, int C,
                          const float* gamma, const float* mean, const float* rstd, const float* y_for_relu, long long ldy,
                          float* dx, long long lddx, int dx_accumulate, float* dgamma, float* dbeta, float* scratch,
-                         cudaStream_t st) {
+                         cudaStream_t st, SideStream fin) {
     if (rows <= 0) return 0;
     RIFT_REQUIRE(C <= LNB_MAXC, "layernorm_bwd: C too large");
     RIFT_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "layernorm_bwd: dgamma/dbeta go together");
@@ -316,9 +329,10 @@ int launch_layernorm_bwd(const float* x, long long ldx, const float* dy, long lo
 #undef RIFT_LNB4
             RIFT_LAUNCH_OK();
             if (dgamma) {
-                colsum_final_kernel<<<cdiv(C, 32), 256, 0, st>>>(scratch, nb4, 2LL * C, C, dgamma, 1);
-                RIFT_LAUNCH_OK();
-                colsum_final_kernel<<<cdiv(C, 32), 256, 0, st>>>(scratch + C, nb4, 2LL * C, C, dbeta, 1);
+                cudaStream_t s2;
+                int r2 = second_stage_stream(st, fin, &s2);
+                if (r2) return r2;
+                colsum_final2_kernel<<<dim3(cdiv(C, 32), 2), 256, 0, s2>>>(scratch, nb4, C, dgamma, dbeta);
                 RIFT_LAUNCH_OK();
             }
             return 0;
@@ -335,9 +349,10 @@ int launch_layernorm_bwd(const float* x, long long ldx, const float* dy, long lo
                                                 dx_accumulate, dgamma ? scratch : nullptr);
     RIFT_LAUNCH_OK();
     if (dgamma) {
-        colsum_final_kernel<<<cdiv(C, 32), 256, 0, st>>>(scratch, nb, 2LL * C, C, dgamma, 1);
-        RIFT_LAUNCH_OK();
-        colsum_final_kernel<<<cdiv(C, 32), 256, 0, st>>>(scratch + C, nb, 2LL * C, C, dbeta, 1);
+        cudaStream_t s2;
+        int r2 = second_stage_stream(st, fin, &s2);
+        if (r2) return r2;
+        colsum_final2_kernel<<<dim3(cdiv(C, 32), 2), 256, 0, s2>>>(scratch, nb, C, dgamma, dbeta);
         RIFT_LAUNCH_OK();
     }
     return 0;
@@ -390,14 +405,35 @@ colsum_final_kernel(const float* __restrict__ partial, int nb, long long stride,
         out[c] = accumulate ? out[c] + s : s;
     }
 }
+__global__ void __launch_bounds__(256)
+colsum_final2_kernel(const float* __restrict__ partial, int nb, int C, float* __restrict__ out0, float* __restrict__ out1) {
+    __shared__ float sm[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + tx;
+    const float* p = partial + (long long)blockIdx.y * C;          // layout [nb][2][C]
+    float a = 0.f;
+    if (c < C) for (int b = ty; b < nb; b += 8) a += p[(long long)b * 2 * C + c];
+    sm[ty][tx] = a;
+    __syncthreads();
+    if (ty == 0 && c < C) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += sm[i][tx];
+        float* out = blockIdx.y ? out1 : out0;
+        out[c] += s;
+    }
+}
 int launch_colsum(const float* x, long long ldx, int rows, int C, float* out, int accumulate, float* scratch,
-                  cudaStream_t st) {
+                  cudaStream_t st, SideStream fin) {
     if (C <= 0) return 0;
     const int chunks = cdiv(C, 32);
     int slabs = max(1, min(148, min(cdiv(rows, 32), cdiv(148 * 4, chunks))));
     colsum_partial_kernel<<<dim3(chunks, slabs), 256, 0, st>>>(x, ldx, rows, C, scratch);
     RIFT_LAUNCH_OK();
-    colsum_final_kernel<<<chunks, 256, 0, st>>>(scratch, slabs, C, C, out, accumulate);
+    cudaStream_t s2;
+    int r2 = second_stage_stream(st, fin, &s2);
+    if (r2) return r2;
+    colsum_final_kernel<<<chunks, 256, 0, s2>>>(scratch, slabs, C, C, out, accumulate);
     RIFT_LAUNCH_OK();
     return 0;
 }

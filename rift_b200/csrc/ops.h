@@ -56,6 +56,11 @@ struct GemmArgs {
 int launch_gemm_simt(const GemmArgs& a, cudaStream_t st);
 int launch_splitk_reduce(const float* ws, int splits, const GemmArgs& a, cudaStream_t st);
 
+// Second stage of a two-stage reduction may run on another stream: after the first stage is enqueued on the
+// caller's stream, `ev` is recorded there and `st` waits for it (null st: everything stays on the caller's stream).
+// The partial buffer must then stay untouched until that stream has consumed it.
+struct SideStream { cudaStream_t st = nullptr; cudaEvent_t ev = nullptr; };
+
 // ------------------------------------------------------------------ nn_kernels.cu
 int launch_layernorm(const float* x, long long ldx, int rows, int C, const float* gamma, const float* beta, float* y,
                      long long ldy, int relu, const float* add_rowmod, int rowmod, float* y2, float* mean, float* rstd,
@@ -63,7 +68,7 @@ int launch_layernorm(const float* x, long long ldx, int rows, int C, const float
 int launch_layernorm_bwd(const float* x, long long ldx, const float* dy, long long lddy, int rows, int C,
                          const float* gamma, const float* mean, const float* rstd, const float* y_for_relu, long long ldy,
                          float* dx, long long lddx, int dx_accumulate, float* dgamma, float* dbeta, float* scratch,
-                         cudaStream_t st);
+                         cudaStream_t st, SideStream fin = SideStream());
 int layernorm_bwd_scratch_floats(int C);
 
 struct AttnArgs {
@@ -137,7 +142,7 @@ int launch_interleave_heads(const float* loc, const float* yaw, const float* vel
 int launch_mask_logits(float* pi, const uint8_t* r_pad, long long rows, int Mo, float fill, cudaStream_t st);
 int launch_gather_rows(const float* x, long long ldx_batch, int bs, int row0, int nrows, int C, float* out, cudaStream_t st);
 int launch_colsum(const float* x, long long ldx, int rows, int C, float* out, int accumulate, float* scratch,
-                  cudaStream_t st);
+                  cudaStream_t st, SideStream fin = SideStream());
 int launch_act_bwd(const float* pre_or_post, float* dy, long long n, int act, cudaStream_t st);   // in place dy *= act'(.)
 int launch_add_inplace(float* dst, const float* src, long long n, cudaStream_t st);
 int launch_scale_shift_rows_bwd(float* dy, const float* colscale, long long rows, int C, cudaStream_t st);
