@@ -105,6 +105,7 @@ class PlanningModel:
         self._engine = C.c_void_p()
         self._workspace = None
         self._ws_shape = None
+        self.ws_generation = 0        # bumped whenever the workspace is re-allocated (captured CUDA graphs go stale)
         self.arena: Optional[ParamArena] = None
         self.set_trainable_layers(trainable_layers)
 
@@ -195,6 +196,7 @@ class PlanningModel:
                                    _lib.lib().rift_b200_last_error().decode())
             if self._workspace is None or self._workspace.numel() < need:
                 self._workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
+                self.ws_generation += 1
             self._ws_shape = pb.shape
 
     def pack(self, data) -> PackedBatch:

@@ -14,6 +14,7 @@ valid count), and every rank applies the identical update, reproducing the refer
 masked mean exactly (rift_trainer.py:173-178).
 """
 import math
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -89,11 +90,19 @@ class LightningTrainer:
         self.optimizer: Optional[F.ClipAdamW] = None
         self.scheduler: Optional[WarmupCosLR] = None
         self._count = None            # device fp64 valid count of the last training_step (group objectives)
+        # CUDA-graph replay of forward + objective + backward (launch-bound: ~1.5k kernels per full update).
+        # A batch signature (shapes / dtypes) is captured the second time it is seen; inputs are copied into the
+        # graph's static buffers, so varying shapes simply stay on the eager path.  RIFT_B200_CUDA_GRAPH=0 disables.
+        self.use_cuda_graph = bool(int(os.environ.get("RIFT_B200_CUDA_GRAPH", "1")))
+        self._graphs: Dict[tuple, dict] = {}
+        self._graph_seen: Dict[tuple, int] = {}
 
     # ------------------------------------------------------------------ reference surface
     def freeze_parameters(self, trainable_layers=("planning_decoder.pi_head",)):
         """rift_trainer.py:78-90 — raises ValueError for an unknown layer name."""
         self.model.set_trainable_layers(trainable_layers)
+        self._graphs = {}
+        self._graph_seen = {}
 
     def forward(self, features):
         return self.model(features)
@@ -120,7 +129,7 @@ class LightningTrainer:
         return {"model." + k: v for k, v in self.model.state_dict().items()}
 
     def load_state_dict(self, sd, strict=True):
-        return self.model.load_state_dict(sd, strict)
+        return self.model.load_state_dict(sd, strict)       # graphs stay valid: they read the arena in place
 
     # ------------------------------------------------------------------ objectives
     @staticmethod
@@ -144,14 +153,105 @@ class LightningTrainer:
         self._stats = stats
         return loss, dz
 
+    def _train_core(self, batch):
+        """forward -> objective -> backward on the current stream; returns the local loss tensor."""
+        res = self.model.forward(self._features(batch), outputs=(), save_for_backward=True)
+        loss, dz = self._objective(res, batch, need_grad=True)
+        self.model.backward(dz)
+        return loss
+
     def _step(self, batch, prefix: str):
-        res = self.model.forward(self._features(batch), outputs=(), save_for_backward=self.training)
-        loss, dz = self._objective(res, batch, need_grad=self.training)
         if self.training:
-            self.model.backward(dz)
+            loss = self._graphed_core(batch) if self.use_cuda_graph else self._train_core(batch)
             loss = self._reduce(loss)
+        else:
+            res = self.model.forward(self._features(batch), outputs=(), save_for_backward=False)
+            loss, _ = self._objective(res, batch, need_grad=False)
         self._last_loss = loss
         return loss if self.training else 0.0
+
+    # ------------------------------------------------------------------ CUDA-graph replay of the training core
+    _FEATURE_KEYS = (("agent", "agent_", ("position", "heading", "velocity", "shape", "category", "valid_mask")),
+                     ("map", "map_", ("point_position", "point_vector", "point_orientation", "polygon_center",
+                                      "polygon_type", "polygon_on_route", "polygon_tl_status",
+                                      "polygon_has_speed_limit", "polygon_speed_limit", "valid_mask")),
+                     ("reference_line", "ref_", ("position", "vector", "orientation", "valid_mask")))
+
+    @classmethod
+    def _flatten_batch(cls, batch, feats):
+        """(name, tensor) pairs of everything the training core reads from a batch dict; feature names are
+        PackedBatch.keep's."""
+        from .planning_model import PackedBatch
+        if isinstance(feats, PackedBatch):
+            items = [("f." + k, v) for k, v in feats.keep.items()]
+        else:
+            items = [("f." + prefix + k, torch.as_tensor(feats[grp][k])) for grp, prefix, keys in cls._FEATURE_KEYS for k in keys]
+            items.append(("f.current_state", torch.as_tensor(feats["current_state"])))
+        items += [("b." + k, v) for k, v in batch.items() if torch.is_tensor(v)]
+        return items
+
+    def _graphed_core(self, batch):
+        from .planning_model import PackedBatch
+        feats = self._features(batch)
+        if not isinstance(feats, PackedBatch):
+            so = feats.get("static_objects")
+            if so is not None and so["position"].shape[1] != 0:
+                return self._train_core(batch)           # raises the documented NotImplementedError
+        items = self._flatten_batch(batch, feats)
+        key = (isinstance(feats, PackedBatch),) + tuple((n, tuple(t.shape), t.dtype) for n, t in items)
+        g = self._graphs.get(key)
+        if g is not None and g["ws_gen"] != self.model.ws_generation:
+            del self._graphs[key]                        # the workspace moved: the captured pointers are stale
+            g = None
+        if g is None:
+            seen = self._graph_seen.get(key, 0)
+            self._graph_seen[key] = seen + 1
+            if seen == 0 or len(self._graphs) >= 8:
+                return self._train_core(batch)           # first sight of this signature (or cache full): eager
+            g = self._capture(batch, feats, items, key)
+        # refresh the static inputs (skipped for tensors that already ARE the static ones: a device-resident PackedBatch)
+        for (_, t), st in zip(items, g["static"]):
+            if t.data_ptr() != st.data_ptr():
+                st.copy_(t, non_blocking=True)
+        g["graph"].replay()
+        self._stats = g["stats"]
+        return g["loss"].clone()                         # the graph's own output buffer is overwritten by the next replay
+
+    def _capture(self, batch, feats, items, key):
+        from .planning_model import PackedBatch
+        dev = self.model.device
+        if isinstance(feats, PackedBatch):
+            spb = feats                                  # explicit device-resident batch: used in place
+        else:
+            data = {grp: {} for grp, _, _ in self._FEATURE_KEYS}
+            for grp, prefix, keys in self._FEATURE_KEYS:
+                for k in keys:
+                    data[grp][k] = torch.as_tensor(feats[grp][k]).to(dev, copy=True)   # private static copies
+            data["current_state"] = torch.as_tensor(feats["current_state"]).to(dev, copy=True)
+            spb = PackedBatch(data, dev)
+        sbatch = dict(batch)
+        sbatch["cur_pluto_feature_torch"] = spb
+        static = []
+        for n, t in items:
+            if n.startswith("f."):
+                static.append(spb.keep[n[2:]])
+            else:
+                st = t.to(dev, copy=True)
+                sbatch[n[2:]] = st
+                static.append(st)
+        self.model.params_updated(trainable_only=True)   # the re-split of the trainable weight planes is part of the graph
+        graph = torch.cuda.CUDAGraph()
+        cap = torch.cuda.Stream(device=dev)
+        cap.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(cap):
+            with torch.cuda.graph(graph, stream=cap):
+                loss = self._train_core(sbatch)
+                stats = self._stats
+        torch.cuda.current_stream(dev).wait_stream(cap)
+        g = {"graph": graph, "static": static, "loss": loss, "stats": stats, "batch": sbatch,
+             "ws_gen": self.model.ws_generation}
+        self._graphs[key] = g
+        return g
 
     def _reduce(self, loss):
         """Single collective of the step: [flat grads | objective sum | valid count]."""
@@ -311,15 +411,12 @@ class PPOTrainer(ReinforceTrainer):
         self._stats = None
         return loss, dz
 
-    def _step(self, batch, prefix: str):
-        res = self.model.forward(self._features(batch), outputs=(), save_for_backward=self.training)
-        loss, dz = self._objective(res, batch, need_grad=self.training)
-        if self.training:
-            self.model.backward(dz)                      # zeroes the gradient span, then the policy gradients
-            self.value_net.backward(self._dvalue)        # += value-net gradients
-            loss = self._reduce(loss)
-        self._last_loss = loss
-        return loss if self.training else 0.0
+    def _train_core(self, batch):
+        res = self.model.forward(self._features(batch), outputs=(), save_for_backward=True)
+        loss, dz = self._objective(res, batch, need_grad=True)
+        self.model.backward(dz)                          # zeroes the gradient span, then the policy gradients
+        self.value_net.backward(self._dvalue)            # += value-net gradients
+        return loss
 
 
 TRAINERS = {"rift": RIFTTrainer, "grpo": GRPOTrainer, "reinforce": ReinforceTrainer, "ppo": PPOTrainer}
