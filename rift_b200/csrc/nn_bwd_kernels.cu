@@ -1,5 +1,7 @@
 // Backward kernels of the non-GEMM operators (see nn_kernels.cu for the forward definitions).
 // All reductions are two-stage / fixed-order, so gradients are run-to-run deterministic.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ops.h"
 
@@ -123,11 +125,202 @@ attention_bwd_kernel(AttnArgs a, const float* __restrict__ d_o, long long lddo, 
     }
 }
 
+// ---- head_dim 32, cooperative form ------------------------------------------------------------------
+// Several (batch, head) problems per CTA (PB) and G lanes per row: in phase A the G lanes of query i split the
+// keys (j = g, g+G, ...), in phase B the G lanes of key j split the queries; partial results are combined with
+// xor-butterflies inside the lane group.  P = exp(S - lse) and dS = P (dP - delta) are computed ONCE and kept
+// in shared memory, so phase B is two AXPYs per (i, j).  Rows are padded to 36 floats: 16-byte broadcast reads
+// of up to eight different rows by one quarter-warp stay conflict free.
+constexpr int AB_PITCH = 36;
+
+struct AttnBwdShape { int PB, G, tpp; size_t smem_per_problem; };
+
+__host__ __device__ inline size_t attn_bwd2_smem_floats(int Sq, int Sk) {
+    const int Skp = Sk | 1;
+    const size_t n = (size_t)2 * Sq * AB_PITCH + (size_t)2 * Sk * AB_PITCH + (size_t)2 * Sq * Skp + (size_t)Sq + ((Sk + 3) / 4);
+    return (n + 3) & ~(size_t)3;                         // problems stay 16-byte aligned
+}
+
+template <int G>
+__global__ void __launch_bounds__(512)
+attention_bwd2_kernel(AttnArgs a, const float* __restrict__ d_o, long long lddo, float* __restrict__ dq, long long lddq,
+                      float* __restrict__ dk, float* __restrict__ dv, long long lddk, long long lddv, int PB, int tpp) {
+    constexpr int HD = 32;
+    extern __shared__ __align__(16) float sm[];
+    const int Sq = a.Sq, Sk = a.Sk, Skp = Sk | 1;
+    const int pl = threadIdx.x / tpp;                    // problem slot inside the CTA
+    const int t = threadIdx.x - pl * tpp;                // thread inside the problem
+    const long long prob = (long long)blockIdx.x * PB + pl;
+    const bool live = pl < PB && prob < (long long)a.B * a.H;
+    float* base = sm + (size_t)pl * attn_bwd2_smem_floats(Sq, Sk);
+    float* Qs = base;                                    // [Sq][36]  (pre-scaled)
+    float* dOs = Qs + (size_t)Sq * AB_PITCH;             // [Sq][36]
+    float* Ks = dOs + (size_t)Sq * AB_PITCH;             // [Sk][36]
+    float* Vs = Ks + (size_t)Sk * AB_PITCH;              // [Sk][36]
+    float* Ps = Vs + (size_t)Sk * AB_PITCH;              // [Sq][Skp]
+    float* dSs = Ps + (size_t)Sq * Skp;                  // [Sq][Skp]  (dP first, then dS)
+    float* lse_s = dSs + (size_t)Sq * Skp;               // [Sq]
+    uint8_t* msk = reinterpret_cast<uint8_t*>(lse_s + Sq);   // [Sk]
+    const int b = live ? (int)(prob / a.H) : 0, h = live ? (int)(prob % a.H) : 0;
+    const long long krow0 = attn_row_b(b, a.k_inner_n, a.k_outer, a.k_inner);
+    const long long qrow0 = attn_row_b(b, a.q_inner_n, a.q_outer, a.q_inner);
+    const long long orow0 = a.o_custom ? attn_row_b(b, a.o_inner_n, a.o_outer, a.o_inner) : qrow0;
+    const long long oseq = a.o_custom ? a.o_seq : a.q_seq;
+    if (live) {
+        // 16-byte loads: 8 lanes per row
+        for (int e = t; e < Sk * 8; e += tpp) {
+            const int j = e >> 3, c = (e & 7) * 4;
+            const long long r = krow0 + (long long)j * a.k_seq;
+            *reinterpret_cast<float4*>(Ks + j * AB_PITCH + c) = *reinterpret_cast<const float4*>(a.k + r * a.ldk + h * HD + c);
+            *reinterpret_cast<float4*>(Vs + j * AB_PITCH + c) = *reinterpret_cast<const float4*>(a.v + r * a.ldv + h * HD + c);
+        }
+        for (int e = t; e < Sq * 8; e += tpp) {
+            const int i = e >> 3, c = (e & 7) * 4;
+            float4 q = *reinterpret_cast<const float4*>(a.q + (qrow0 + (long long)i * a.q_seq) * a.ldq + h * HD + c);
+            q.x *= a.scale; q.y *= a.scale; q.z *= a.scale; q.w *= a.scale;
+            *reinterpret_cast<float4*>(Qs + i * AB_PITCH + c) = q;
+            *reinterpret_cast<float4*>(dOs + i * AB_PITCH + c) =
+                *reinterpret_cast<const float4*>(d_o + (orow0 + (long long)i * oseq) * lddo + h * HD + c);
+        }
+        for (int i = t; i < Sq; i += tpp) lse_s[i] = a.lse[((long long)b * a.H + h) * Sq + i];
+        const uint8_t* kpm = a.kpm ? a.kpm + (long long)(a.kpm_mod > 0 ? b % a.kpm_mod : b / a.kpm_div) * Sk : nullptr;
+        for (int j = t; j < Sk; j += tpp) msk[j] = kpm ? kpm[j] : 0;
+    }
+    __syncthreads();
+    const int row = t / G, g = t % G;
+    // ---- phase A: lane group = query i.  Every thread runs the shuffles (inactive groups loop zero times).
+    {
+        const bool act = live && row < Sq;
+        const int i = act ? row : 0;
+        const int Skl = act ? Sk : 0;
+        const float lse = act ? lse_s[i] : 0.f;
+        const bool dead = (lse == INFINITY);
+        float q[HD], go[HD];
+#pragma unroll
+        for (int d = 0; d < HD; d += 4) {
+            const float4 x = *reinterpret_cast<const float4*>(Qs + i * AB_PITCH + d);
+            const float4 y = *reinterpret_cast<const float4*>(dOs + i * AB_PITCH + d);
+            q[d] = x.x; q[d + 1] = x.y; q[d + 2] = x.z; q[d + 3] = x.w;
+            go[d] = y.x; go[d + 1] = y.y; go[d + 2] = y.z; go[d + 3] = y.w;
+        }
+        float dl = 0.f;
+        for (int j = g; j < Skl; j += G) {
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+#pragma unroll
+            for (int d = 0; d < HD; d += 4) {
+                const float4 kk = *reinterpret_cast<const float4*>(Ks + j * AB_PITCH + d);
+                const float4 vv = *reinterpret_cast<const float4*>(Vs + j * AB_PITCH + d);
+                s0 = fmaf(q[d], kk.x, s0); s1 = fmaf(q[d + 1], kk.y, s1); s2 = fmaf(q[d + 2], kk.z, s2); s3 = fmaf(q[d + 3], kk.w, s3);
+                p0 = fmaf(go[d], vv.x, p0); p1 = fmaf(go[d + 1], vv.y, p1); p2 = fmaf(go[d + 2], vv.z, p2); p3 = fmaf(go[d + 3], vv.w, p3);
+            }
+            const float sc = (s0 + s1) + (s2 + s3), dp = (p0 + p1) + (p2 + p3);
+            const float p = (dead || msk[j]) ? 0.f : __expf(sc - lse);
+            Ps[i * Skp + j] = p;
+            dSs[i * Skp + j] = dp;
+            dl = fmaf(p, dp, dl);
+        }
+#pragma unroll
+        for (int o = 1; o < G; o <<= 1) dl += __shfl_xor_sync(0xffffffffu, dl, o, G);
+        float acc[HD];
+#pragma unroll
+        for (int d = 0; d < HD; ++d) acc[d] = 0.f;
+        for (int j = g; j < Skl; j += G) {
+            const float ds = Ps[i * Skp + j] * (dSs[i * Skp + j] - dl);
+            dSs[i * Skp + j] = ds;
+#pragma unroll
+            for (int d = 0; d < HD; d += 4) {
+                const float4 kk = *reinterpret_cast<const float4*>(Ks + j * AB_PITCH + d);
+                acc[d] = fmaf(ds, kk.x, acc[d]); acc[d + 1] = fmaf(ds, kk.y, acc[d + 1]);
+                acc[d + 2] = fmaf(ds, kk.z, acc[d + 2]); acc[d + 3] = fmaf(ds, kk.w, acc[d + 3]);
+            }
+        }
+#pragma unroll
+        for (int o = 1; o < G; o <<= 1) {
+#pragma unroll
+            for (int d = 0; d < HD; ++d) acc[d] += __shfl_xor_sync(0xffffffffu, acc[d], o, G);
+        }
+        // every lane of the group holds the full row: lane g writes columns [g * HD / G, (g + 1) * HD / G)
+        const long long dr = a.o_custom ? (orow0 + (long long)i * oseq) : (qrow0 + (long long)i * a.q_seq);
+        float* dst = dq + dr * lddq + h * HD;
+#pragma unroll
+        for (int d = 0; d < HD; d += 4) {
+            if (act && d / (HD / G) == g)
+                *reinterpret_cast<float4*>(dst + d) =
+                    make_float4(acc[d] * a.scale, acc[d + 1] * a.scale, acc[d + 2] * a.scale, acc[d + 3] * a.scale);
+        }
+    }
+    __syncthreads();
+    // ---- phase B: lane group = key j
+    {
+        const bool act = live && row < Sk;
+        const int j = act ? row : 0;
+        const int Sql = act ? Sq : 0;
+        float ak[HD], av[HD];
+#pragma unroll
+        for (int d = 0; d < HD; ++d) { ak[d] = 0.f; av[d] = 0.f; }
+        for (int i = g; i < Sql; i += G) {
+            const float p = Ps[i * Skp + j], ds = dSs[i * Skp + j];
+#pragma unroll
+            for (int d = 0; d < HD; d += 4) {
+                const float4 oo = *reinterpret_cast<const float4*>(dOs + i * AB_PITCH + d);
+                const float4 qq = *reinterpret_cast<const float4*>(Qs + i * AB_PITCH + d);
+                av[d] = fmaf(p, oo.x, av[d]); av[d + 1] = fmaf(p, oo.y, av[d + 1]);
+                av[d + 2] = fmaf(p, oo.z, av[d + 2]); av[d + 3] = fmaf(p, oo.w, av[d + 3]);
+                ak[d] = fmaf(ds, qq.x, ak[d]); ak[d + 1] = fmaf(ds, qq.y, ak[d + 1]);       // Qs is pre-scaled: dK carries `scale`
+                ak[d + 2] = fmaf(ds, qq.z, ak[d + 2]); ak[d + 3] = fmaf(ds, qq.w, ak[d + 3]);
+            }
+        }
+#pragma unroll
+        for (int o = 1; o < G; o <<= 1) {
+#pragma unroll
+            for (int d = 0; d < HD; ++d) {
+                ak[d] += __shfl_xor_sync(0xffffffffu, ak[d], o, G);
+                av[d] += __shfl_xor_sync(0xffffffffu, av[d], o, G);
+            }
+        }
+        const long long r = krow0 + (long long)j * a.k_seq;
+        float* dkp = dk + r * lddk + h * HD;
+        float* dvp = dv + r * lddv + h * HD;
+#pragma unroll
+        for (int d = 0; d < HD; d += 4) {
+            if (act && d / (HD / G) == g) {
+                *reinterpret_cast<float4*>(dkp + d) = make_float4(ak[d], ak[d + 1], ak[d + 2], ak[d + 3]);
+                *reinterpret_cast<float4*>(dvp + d) = make_float4(av[d], av[d + 1], av[d + 2], av[d + 3]);
+            }
+        }
+    }
+}
+
 int launch_attention_bwd(const AttnArgs& a, const float* d_o, long long lddo, float* dq, long long lddq, float* dk,
                          float* dv, long long lddk, long long lddv, cudaStream_t st) {
     if (a.B <= 0 || a.Sq <= 0) return 0;
     RIFT_REQUIRE(a.hd == 32 || a.hd == 64, "attention_bwd: head_dim must be 32 or 64");
     RIFT_REQUIRE(a.lse != nullptr, "attention_bwd: forward must have saved the log-sum-exp");
+    {
+        auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+        const bool vec = a.hd == 32 && al16(a.q) && al16(a.k) && al16(a.v) && al16(d_o) && al16(dq) && al16(dk) && al16(dv) &&
+                         (a.ldq & 3) == 0 && (a.ldk & 3) == 0 && (a.ldv & 3) == 0 && (lddo & 3) == 0 && (lddq & 3) == 0 &&
+                         (lddk & 3) == 0 && (lddv & 3) == 0;
+        const int smax = max(a.Sq, a.Sk);
+        const size_t per = attn_bwd2_smem_floats(a.Sq, a.Sk) * sizeof(float);
+        static const bool legacy = getenv("RIFT_B200_ATTN_BWD_LEGACY") != nullptr;
+        if (vec && !legacy && 4 * smax <= 512 && per <= 200 * 1024) {
+            constexpr int G = 4;
+            const int tpp = (G * smax + 31) / 32 * 32;
+            int PB = max(1, 256 / tpp);
+            while (PB > 1 && PB * per > 96 * 1024) --PB;
+            const long long nprob = (long long)a.B * a.H;
+            static bool attr2 = false;
+            if (!attr2) {
+                RIFT_CUDA_OK(cudaFuncSetAttribute(attention_bwd2_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                attr2 = true;
+            }
+            attention_bwd2_kernel<G><<<(unsigned)((nprob + PB - 1) / PB), PB * tpp, PB * per, st>>>(a, d_o, lddo, dq, lddq, dk, dv, lddk,
+                                                                                                 lddv, PB, tpp);
+            RIFT_LAUNCH_OK();
+            return 0;
+        }
+    }
     const size_t smem = ((size_t)2 * a.Sq * a.hd + (size_t)2 * a.Sk * a.hd + 2 * a.Sq) * sizeof(float);
     RIFT_REQUIRE(smem <= 200 * 1024, "attention_bwd: sequence too long for the shared-memory kernel");
     static bool attr = false;
@@ -362,18 +555,35 @@ int launch_groupsum(const float* x, long long ldx, int groups, int n, int C, flo
 // out[m, c] (+)= sum_{rows r with r % mod == m} x[r, c]   (per-mode parameters m_pos / m_emb, pos_embed)
 __global__ void __launch_bounds__(256)
 modsum_kernel(const float* __restrict__ x, long long ldx, long long rows, int C, int mod, float* __restrict__ out, int accumulate) {
-    // block = (m, column chunk); threads stride the columns; rows walked in order -> deterministic
-    const int m = blockIdx.x;
-    for (int c = blockIdx.y * 256 + threadIdx.x; c < C; c += gridDim.y * 256) {
-        float a = 0.f;
-        for (long long r = m; r < rows; r += mod) a += x[r * ldx + c];
+    // block = (m, 32-column chunk); 8 row lanes x 4 independent accumulators, combined in a fixed order -> deterministic
+    __shared__ float sm[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int m = blockIdx.x, c = blockIdx.y * 32 + tx;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    if (c < C) {
+        const long long step = 8LL * mod;
+        long long r = m + (long long)ty * mod;
+        for (; r + 3 * step < rows; r += 4 * step) {
+            a0 += x[r * ldx + c];
+            a1 += x[(r + step) * ldx + c];
+            a2 += x[(r + 2 * step) * ldx + c];
+            a3 += x[(r + 3 * step) * ldx + c];
+        }
+        for (; r < rows; r += step) a0 += x[r * ldx + c];
+    }
+    sm[ty][tx] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    if (ty == 0 && c < C) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += sm[i][tx];
         float* o = out + (long long)m * C + c;
-        *o = accumulate ? *o + a : a;
+        *o = accumulate ? *o + s : s;
     }
 }
 int launch_modsum(const float* x, long long ldx, long long rows, int C, int mod, float* out, int accumulate, cudaStream_t st) {
     if (rows <= 0 || C <= 0) return 0;
-    modsum_kernel<<<dim3(mod, cdiv(C, 256)), 256, 0, st>>>(x, ldx, rows, C, mod, out, accumulate);
+    modsum_kernel<<<dim3(mod, cdiv(C, 32)), 256, 0, st>>>(x, ldx, rows, C, mod, out, accumulate);
     RIFT_LAUNCH_OK();
     return 0;
 }
@@ -464,33 +674,48 @@ __global__ void __launch_bounds__(256)
 bn_affine_bwd_partial_kernel(const float* __restrict__ dz, const float* __restrict__ v, long long rows, int C,
                              const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ partial) {
     for (int c = threadIdx.x; c < C; c += 256) {
-        float ag = 0.f, ab = 0.f;
+        float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
         const float g = gamma[c], b = beta[c];
-        for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
-            const float d = dz[r * C + c];
-            ag += d * (v[r * C + c] - b) / g;
-            ab += d;
+        const long long st = gridDim.x;
+        long long r = blockIdx.x;
+        for (; r + 3 * st < rows; r += 4 * st) {
+            const float d0 = dz[r * C + c], d1 = dz[(r + st) * C + c], d2 = dz[(r + 2 * st) * C + c], d3 = dz[(r + 3 * st) * C + c];
+            g0 = fmaf(d0, v[r * C + c] - b, g0); g1 = fmaf(d1, v[(r + st) * C + c] - b, g1);
+            g2 = fmaf(d2, v[(r + 2 * st) * C + c] - b, g2); g3 = fmaf(d3, v[(r + 3 * st) * C + c] - b, g3);
+            b0 += d0; b1 += d1; b2 += d2; b3 += d3;
         }
-        partial[((long long)blockIdx.x * 2 + 0) * C + c] = ag;
-        partial[((long long)blockIdx.x * 2 + 1) * C + c] = ab;
+        for (; r < rows; r += st) { const float d0 = dz[r * C + c]; g0 = fmaf(d0, v[r * C + c] - b, g0); b0 += d0; }
+        // (v - beta) / gamma is the normalised input; the division is applied once to the sum
+        partial[((long long)blockIdx.x * 2 + 0) * C + c] = ((g0 + g1) + (g2 + g3)) / g;
+        partial[((long long)blockIdx.x * 2 + 1) * C + c] = (b0 + b1) + (b2 + b3);
     }
 }
-__global__ void bn_affine_bwd_final_kernel(const float* __restrict__ partial, int nb, int C, float* __restrict__ dgamma,
-                                           float* __restrict__ dbeta) {
-    FOR_GRID(c, C) {
-        float ag = 0.f, ab = 0.f;
-        for (int b = 0; b < nb; ++b) { ag += partial[((long long)b * 2) * C + c]; ab += partial[((long long)b * 2 + 1) * C + c]; }
-        dgamma[c] += ag;
-        dbeta[c] += ab;
+// second stage: fixed-order sum over the nb partial rows ([nb][2][C]), 8 row lanes per column; blockIdx.y: 0 dgamma, 1 dbeta
+__global__ void __launch_bounds__(256)
+bn_affine_bwd_final_kernel(const float* __restrict__ partial, int nb, int C, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    __shared__ float sm[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + tx;
+    const float* p = partial + (long long)blockIdx.y * C;
+    float a = 0.f;
+    if (c < C) for (int b = ty; b < nb; b += 8) a += p[(long long)b * 2 * C + c];
+    sm[ty][tx] = a;
+    __syncthreads();
+    if (ty == 0 && c < C) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += sm[i][tx];
+        float* out = blockIdx.y ? dbeta : dgamma;
+        out[c] += s;
     }
 }
 int launch_bn_affine_bwd(const float* dz, const float* v, long long rows, int C, const float* gamma, const float* beta,
                          float* dgamma, float* dbeta, float* scratch, cudaStream_t st) {
     if (rows <= 0) return 0;
-    const int nb = (int)min((long long)148, rows);
+    const int nb = (int)min((long long)148, rows);          // scratch holds 148 x 2 x C partials
     bn_affine_bwd_partial_kernel<<<nb, 256, 0, st>>>(dz, v, rows, C, gamma, beta, scratch);
     RIFT_LAUNCH_OK();
-    bn_affine_bwd_final_kernel<<<cdiv(C, 256), 256, 0, st>>>(scratch, nb, C, dgamma, dbeta);
+    bn_affine_bwd_final_kernel<<<dim3(cdiv(C, 32), 2), 256, 0, st>>>(scratch, nb, C, dgamma, dbeta);
     RIFT_LAUNCH_OK();
     return 0;
 }

@@ -1,0 +1,17 @@
+#!/bin/bash
+# tests + benches + launch list (profiling numbers are never bench values)
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
+timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu > gpurun_out/q_full.json 2> gpurun_out/q_full.err; tail -2 gpurun_out/q_full.err
+timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu --trainable pi_head > gpurun_out/q_pi.json 2> gpurun_out/q_pi.err
+python - <<'PY'
+import json
+for f in ("q_full", "q_pi"):
+    try:
+        d = json.load(open(f"gpurun_out/{f}.json")); print(f, "ms", round(d["ms_per_step"], 3), "e2e ms", round(d["e2e"]["ms_per_step"], 3), "launches", d["gpu_launches"], "roofline", round(d["roofline"]["frac"], 3), d["roofline"]["kernel_ms"])
+    except Exception as e:
+        print(f, "failed", e)
+PY
+if [ "$1" = "list" ]; then
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches_full.csv python bench.py --ncu --no-cpu > gpurun_out/ncu_full.log 2>&1; echo "ncu list rc=$?"
+fi
