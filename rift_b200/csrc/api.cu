@@ -204,7 +204,7 @@ int rift_b200_op_linear_tc(const float* x, int rows, int K, const float* w, cons
         fill_split_job(job.data(), w, K, N, K, tw.Kp, tw.hi, tw.lo, 0, 0);
         RIFT_CUDA_OK(cudaMemcpyAsync(p + 2 * plane, job.data(), job.size(), cudaMemcpyHostToDevice, S(stream)));
         RIFT_CUDA_OK(cudaStreamSynchronize(S(stream)));
-        int r = launch_split_weights(p + 2 * plane, 1, (long long)N * tw.Kp, S(stream));
+        int r = launch_split_weights(p + 2 * plane, 1, split_job_units(N, tw.Kp), S(stream));
         if (r) return r;
     }
     int r = 0;

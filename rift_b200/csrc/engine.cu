@@ -135,11 +135,11 @@ int rift_b200_engine::bind_weight_cache(void* cache, size_t bytes) {
         w.hi = p; w.lo = p + plane; p += 2 * plane;
         fill_split_job(all.data() + n_jobs_all * split_job_bytes(), w.src, w.ld_src, w.N, w.K, w.Kp, w.hi, w.lo, total_all,
                        w.transpose ? 1 : 0);
-        ++n_jobs_all; total_all += (long long)w.N * w.Kp;
+        ++n_jobs_all; total_all += split_job_units(w.N, w.Kp);
         if (w.trainable) {
             fill_split_job(tr.data() + n_jobs_train * split_job_bytes(), w.src, w.ld_src, w.N, w.K, w.Kp, w.hi, w.lo, total_train,
                            w.transpose ? 1 : 0);
-            ++n_jobs_train; total_train += (long long)w.N * w.Kp;
+            ++n_jobs_train; total_train += split_job_units(w.N, w.Kp);
         }
     }
     const size_t tbl = (tcw.size() * split_job_bytes() + 255) & ~(size_t)255;

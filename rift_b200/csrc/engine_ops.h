@@ -233,25 +233,36 @@ inline int lin_bwd(Ctx& c, const float* X, long long ldx, const float* dY, long 
     const bool tc_on = c.tc_bwd && c.tcw && L.tcT >= 0;
     const bool tc_d = tc_on && dX && gemm_tc_shape_ok(M, L.K, L.N) && (lddx % 4) == 0;
     const bool tc_w = tc_on && want_w && gemm_tc_shape_ok(L.N, L.K, M) && L.N >= 64 && (L.ldw % 4) == 0;
+    // Parameter gradients go to the side stream: they read only dYp / the saved operand planes / private partial
+    // buffers (never the fp32 dY, which the main stream may update in place later) and nothing downstream on the
+    // main stream depends on them before the final join of backward().
+    const bool want_b = bias_grad && L.train && L.db;
+    float* sc = nullptr;
+    if (want_b) { sc = c.alloc<float>((size_t)148 * L.N); if (!sc) { set_last_error("workspace too small"); return -1; } }
     Planes dYp;
+    bool forked = false, bias_done = false;
     if (tc_d || tc_w) {
         dYp.Kp = tc_pitch(L.N);
         dYp.hi = c.alloc<uint16_t>((size_t)M * dYp.Kp);
         dYp.lo = c.alloc<uint16_t>((size_t)M * dYp.Kp);
         if (!dYp.hi || !dYp.lo) { set_last_error("workspace too small"); return -1; }
-        if (!c.dry) TRY(launch_pack_split(dY, lddy, M, L.N, dYp.Kp, dYp.hi, dYp.lo, c.st));
-    }
-    // Parameter gradients go to the side stream: they read only dYp / the saved operand planes / private partial
-    // buffers (never the fp32 dY, which the main stream may update in place later) and nothing downstream on the
-    // main stream depends on them before the final join of backward().
-    bool forked = false;
-    if (bias_grad && L.train && L.db) {
-        ALLOC(sc, float, (size_t)148 * L.N);
         if (!c.dry) {
-            SideStream fin;
-            if (c.side) { fin.st = c.side; fin.ev = c.next_event(); forked = true; }
-            TRY(launch_colsum(dY, lddy, M, L.N, L.db, 1, sc, c.st, fin));
+            int slabs = 0;
+            if (want_b) TRY(launch_pack_split_colsum(dY, lddy, M, L.N, dYp.Kp, dYp.hi, dYp.lo, sc, &slabs, c.st));   // one pass over dY
+            if (slabs > 0) {
+                SideStream fin;
+                if (c.side) { fin.st = c.side; fin.ev = c.next_event(); forked = true; }
+                TRY(launch_colsum_final(sc, slabs, L.N, L.db, 1, c.st, fin));
+                bias_done = true;
+            } else {
+                TRY(launch_pack_split(dY, lddy, M, L.N, dYp.Kp, dYp.hi, dYp.lo, c.st));
+            }
         }
+    }
+    if (want_b && !bias_done && !c.dry) {
+        SideStream fin;
+        if (c.side) { fin.st = c.side; fin.ev = c.next_event(); forked = true; }
+        TRY(launch_colsum(dY, lddy, M, L.N, L.db, 1, sc, c.st, fin));
     }
     if (tc_w) {
         Planes xp;

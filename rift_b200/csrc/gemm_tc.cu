@@ -492,6 +492,68 @@ pack_split_kernel(const float* __restrict__ src, long long ld, int M, int K, int
     }
 }
 
+// pack_split fused with the first stage of a column sum (bias gradient): one pass over dY writes its planes and
+// per-slab column partials [slabs][K] (second stage: launch_colsum_final).  block = 8 row lanes x 32 column quads.
+__global__ void __launch_bounds__(256)
+pack_split_colsum_kernel(const float* __restrict__ src, long long ld, int M, int K, int Kp, __nv_bfloat16* __restrict__ hi,
+                         __nv_bfloat16* __restrict__ lo, float* __restrict__ partial) {
+    __shared__ float4 sm[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int k = (blockIdx.x * 32 + tx) * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (k < Kp) {
+        for (int m = blockIdx.y * 8 + ty; m < M; m += gridDim.y * 8) {
+            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float* p = src + (long long)m * ld + k;
+            if (k + 3 < K) x = __ldg(reinterpret_cast<const float4*>(p));
+            else {
+                if (k < K) x.x = __ldg(p);
+                if (k + 1 < K) x.y = __ldg(p + 1);
+                if (k + 2 < K) x.z = __ldg(p + 2);
+            }
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(x.x), h1 = __float2bfloat16_rn(x.y), h2 = __float2bfloat16_rn(x.z),
+                                h3 = __float2bfloat16_rn(x.w);
+            __nv_bfloat162 a = __halves2bfloat162(h0, h1), b = __halves2bfloat162(h2, h3);
+            __nv_bfloat162 c = __floats2bfloat162_rn(x.x - __bfloat162float(h0), x.y - __bfloat162float(h1));
+            __nv_bfloat162 d = __floats2bfloat162_rn(x.z - __bfloat162float(h2), x.w - __bfloat162float(h3));
+            uint2 uh, ul;
+            uh.x = *reinterpret_cast<uint32_t*>(&a); uh.y = *reinterpret_cast<uint32_t*>(&b);
+            ul.x = *reinterpret_cast<uint32_t*>(&c); ul.y = *reinterpret_cast<uint32_t*>(&d);
+            *reinterpret_cast<uint2*>(hi + (long long)m * Kp + k) = uh;
+            *reinterpret_cast<uint2*>(lo + (long long)m * Kp + k) = ul;
+            acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+        }
+    }
+    sm[ty][tx] = acc;
+    __syncthreads();
+    if (ty == 0 && k < K) {
+        float4 s = sm[0][tx];
+#pragma unroll
+        for (int i = 1; i < 8; ++i) { const float4 t = sm[i][tx]; s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w; }
+        float* o = partial + (long long)blockIdx.y * K + k;
+        o[0] = s.x;
+        if (k + 1 < K) o[1] = s.y;
+        if (k + 2 < K) o[2] = s.z;
+        if (k + 3 < K) o[3] = s.w;
+    }
+}
+
+// returns the number of partial slabs through *slabs_out (0: the fused form does not apply, use the separate kernels)
+int launch_pack_split_colsum(const float* src, long long ld, int M, int K, int Kp, void* hi, void* lo, float* partial,
+                             int* slabs_out, cudaStream_t st) {
+    *slabs_out = 0;
+    if (M <= 0) return 0;
+    const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+    if (!vec) return 0;
+    const int chunks = cdiv(Kp, 128);
+    const int slabs = max(1, min(148, min(cdiv(M, 16), cdiv(148 * 4, chunks))));
+    pack_split_colsum_kernel<<<dim3(chunks, slabs), 256, 0, st>>>(src, ld, M, K, Kp, static_cast<__nv_bfloat16*>(hi),
+                                                                 static_cast<__nv_bfloat16*>(lo), partial);
+    RIFT_LAUNCH_OK();
+    *slabs_out = slabs;
+    return 0;
+}
+
 int launch_pack_split(const float* src, long long ld, int M, int K, int Kp, void* hi, void* lo, cudaStream_t st) {
     if (M <= 0) return 0;
     const int vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
@@ -503,31 +565,67 @@ int launch_pack_split(const float* src, long long ld, int M, int K, int Kp, void
 }
 
 // one weight matrix -> planes.  transpose = 0: planes [N, Kp] of W ; transpose = 1: planes [K, Kp] of W^T with
-// Kp = pitch over N (N, K, Kp below are then the plane's rows / valid columns / pitch, src is read transposed)
+// Kp = pitch over N (N, K, Kp below are then the plane's rows / valid columns / pitch, src is read transposed).
+// Work unit = one 32 x 64 tile of a plane; `first` = index of the job's first tile in the launch.
 struct SplitJob { const float* src; long long ld; int N, K, Kp; __nv_bfloat16* hi; __nv_bfloat16* lo; long long first; int transpose; };
+
+long long split_job_units(int N, int Kp) { return (long long)((N + 31) / 32) * (Kp / 64); }
 
 __global__ void __launch_bounds__(256)
 split_weights_kernel(const SplitJob* __restrict__ jobs, int n_jobs, long long total) {
-    for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
-        int lo_j = 0, hi_j = n_jobs - 1;                 // last job whose first <= e
+    __shared__ float tile[64][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (long long u = blockIdx.x; u < total; u += gridDim.x) {
+        int lo_j = 0, hi_j = n_jobs - 1;                 // last job whose first <= u (uniform across the block)
         while (lo_j < hi_j) {
             const int mid = (lo_j + hi_j + 1) >> 1;
-            if (jobs[mid].first <= e) lo_j = mid; else hi_j = mid - 1;
+            if (jobs[mid].first <= u) lo_j = mid; else hi_j = mid - 1;
         }
         const SplitJob j = jobs[lo_j];
-        const long long i = e - j.first;
-        const int n = (int)(i / j.Kp), k = (int)(i - (long long)n * j.Kp);
-        const float x = k < j.K ? (j.transpose ? j.src[(long long)k * j.ld + n] : j.src[(long long)n * j.ld + k]) : 0.f;
-        const __nv_bfloat16 h = __float2bfloat16_rn(x);
-        j.hi[i] = h;
-        j.lo[i] = __float2bfloat16_rn(x - __bfloat162float(h));
+        const int tiles_c = j.Kp >> 6;
+        const int t = (int)(u - j.first);
+        const int r0 = (t / tiles_c) * 32, c0 = (t % tiles_c) * 64;
+        const int c = c0 + 2 * tx;
+        if (!j.transpose) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int r = r0 + ty + 8 * i;
+                if (r < j.N) {
+                    const float* p = j.src + (long long)r * j.ld + c;
+                    const float x0 = c < j.K ? __ldg(p) : 0.f, x1 = c + 1 < j.K ? __ldg(p + 1) : 0.f;
+                    const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+                    *reinterpret_cast<__nv_bfloat162*>(j.hi + (long long)r * j.Kp + c) = __halves2bfloat162(h0, h1);
+                    *reinterpret_cast<__nv_bfloat162*>(j.lo + (long long)r * j.Kp + c) =
+                        __floats2bfloat162_rn(x0 - __bfloat162float(h0), x1 - __bfloat162float(h1));
+                }
+            }
+        } else {
+            // plane[r][c] = src[c * ld + r]: read 64 source rows x 32 contiguous floats, transpose through shared memory
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int cc = c0 + ty + 8 * i, rr = r0 + tx;
+                tile[ty + 8 * i][tx] = (cc < j.K && rr < j.N) ? __ldg(j.src + (long long)cc * j.ld + rr) : 0.f;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int rl = ty + 8 * i, r = r0 + rl;
+                if (r < j.N) {
+                    const float x0 = tile[2 * tx][rl], x1 = tile[2 * tx + 1][rl];
+                    const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+                    *reinterpret_cast<__nv_bfloat162*>(j.hi + (long long)r * j.Kp + c) = __halves2bfloat162(h0, h1);
+                    *reinterpret_cast<__nv_bfloat162*>(j.lo + (long long)r * j.Kp + c) =
+                        __floats2bfloat162_rn(x0 - __bfloat162float(h0), x1 - __bfloat162float(h1));
+                }
+            }
+        }
     }
 }
 
 int launch_split_weights(const void* jobs_dev, int n_jobs, long long total, cudaStream_t st) {
     if (n_jobs <= 0 || total <= 0) return 0;
-    split_weights_kernel<<<(int)min((long long)148 * 8, (total + 255) / 256), 256, 0, st>>>(
-        static_cast<const SplitJob*>(jobs_dev), n_jobs, total);
+    split_weights_kernel<<<(int)min((long long)148 * 16, total), 256, 0, st>>>(static_cast<const SplitJob*>(jobs_dev), n_jobs, total);
     RIFT_LAUNCH_OK();
     return 0;
 }

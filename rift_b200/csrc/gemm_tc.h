@@ -23,6 +23,10 @@ bool gemm_tc_shape_ok(int M, int N, int K);
 bool gemm_tc_eligible(const GemmArgs& a);
 // fp32 [M, K] -> bf16 planes hi / lo [M, Kp] (each M * Kp * 2 bytes, 256 B aligned)
 int launch_pack_split(const float* src, long long ld, int M, int K, int Kp, void* hi, void* lo, cudaStream_t st);
+// the same pass also produces per-slab column partials [slabs][K] of src (bias gradient, finished by launch_colsum_final);
+// *slabs_out == 0 means the fused form does not apply (unaligned source) and nothing was launched
+int launch_pack_split_colsum(const float* src, long long ld, int M, int K, int Kp, void* hi, void* lo, float* partial,
+                             int* slabs_out, cudaStream_t st);
 // C = epilogue(A B^T) with A = planes (a_hi, a_lo) [M, Kp] and B = weight planes rows [n0, n0+N), cols [k0, k0+K)
 int launch_gemm_tc(const GemmArgs& a, const void* a_hi, const void* a_lo, int Kp, const TcWeight& w, int n0, int k0,
                    cudaStream_t st);
@@ -35,6 +39,8 @@ int launch_gemm_tc_ex(const GemmArgs& a, const PlaneOp& A, const PlaneOp& B, boo
 // profiling aid: CTA 0 of every following tcgen05 GEMM writes %globaltimer stamps into dev_buf (64 u64); null = off
 void set_gemm_tc_trace(void* dev_buf);
 
+// work units (32 x 64 plane tiles) of one weight; `first` / `total` of the job table count these
+long long split_job_units(int N, int Kp);
 size_t split_job_bytes();
 void fill_split_job(void* dst, const float* src, long long ld, int N, int K, int Kp, void* hi, void* lo, long long first,
                     int transpose);

@@ -423,6 +423,15 @@ colsum_final2_kernel(const float* __restrict__ partial, int nb, int C, float* __
         out[c] += s;
     }
 }
+int launch_colsum_final(const float* partial, int slabs, int C, float* out, int accumulate, cudaStream_t st, SideStream fin) {
+    if (C <= 0 || slabs <= 0) return 0;
+    cudaStream_t s2;
+    int r2 = second_stage_stream(st, fin, &s2);
+    if (r2) return r2;
+    colsum_final_kernel<<<cdiv(C, 32), 256, 0, s2>>>(partial, slabs, C, C, out, accumulate);
+    RIFT_LAUNCH_OK();
+    return 0;
+}
 int launch_colsum(const float* x, long long ldx, int rows, int C, float* out, int accumulate, float* scratch,
                   cudaStream_t st, SideStream fin) {
     if (C <= 0) return 0;

@@ -143,6 +143,9 @@ int launch_mask_logits(float* pi, const uint8_t* r_pad, long long rows, int Mo, 
 int launch_gather_rows(const float* x, long long ldx_batch, int bs, int row0, int nrows, int C, float* out, cudaStream_t st);
 int launch_colsum(const float* x, long long ldx, int rows, int C, float* out, int accumulate, float* scratch,
                   cudaStream_t st, SideStream fin = SideStream());
+// second stage alone: out[c] (+)= sum over `slabs` partial rows of pitch C
+int launch_colsum_final(const float* partial, int slabs, int C, float* out, int accumulate, cudaStream_t st,
+                        SideStream fin = SideStream());
 int launch_act_bwd(const float* pre_or_post, float* dy, long long n, int act, cudaStream_t st);   // in place dy *= act'(.)
 int launch_add_inplace(float* dst, const float* src, long long n, cudaStream_t st);
 int launch_scale_shift_rows_bwd(float* dy, const float* colscale, long long rows, int C, cudaStream_t st);
