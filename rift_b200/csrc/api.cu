@@ -1,4 +1,6 @@
 // extern "C" surface declared in include/rift_b200.h.
+#include <stdlib.h>
+
 #include <mutex>
 #include <new>
 
@@ -7,6 +9,10 @@
 namespace rift {
 static thread_local std::string g_last_error;
 long long g_kernel_launches = 0;
+bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("RIFT_B200_PDL"); return !(e && atoi(e) == 0); }();
+    return on;
+}
 void set_last_error(const std::string& msg) { g_last_error = msg; }
 const char* get_last_error() { return g_last_error.c_str(); }
 }  // namespace rift

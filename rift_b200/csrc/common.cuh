@@ -44,6 +44,36 @@ extern long long g_kernel_launches;    // every kernel launch of this library pa
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------
+// Every kernel of the library is launched with cudaLaunchAttributeProgrammaticStreamSerialization and starts
+// with pdl_grid_sync(): `launch_dependents` lets the NEXT kernel of the stream be scheduled while this one
+// runs (its CTAs then park in `griddepcontrol.wait`), `wait` blocks until the PREVIOUS kernel has completed and
+// its memory is visible.  Memory semantics are therefore those of plain stream order; what is gained is the
+// launch latency / prologue of ~1.5k small kernels per policy update.  RIFT_B200_PDL=0 launches without the
+// attribute (both instructions are then no-ops).
+bool pdl_enabled();
+
+#ifdef __CUDACC__
+#ifdef RIFT_PDL_EARLY_TRIGGER
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#else
+__device__ __forceinline__ void pdl_trigger() {}      // dependents are released when this grid's CTAs exit
+#endif
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_grid_sync() { pdl_trigger(); pdl_wait(); }
+
+template <class... KArgs, class... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 #ifdef __CUDACC__
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

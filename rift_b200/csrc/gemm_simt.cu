@@ -50,6 +50,7 @@ __global__ void __launch_bounds__(256)
 gemm_simt_kernel(const float* __restrict__ A, long long sam, long long sak, const float* __restrict__ B, long long sbn,
                  long long sbk, float* __restrict__ C, long long ldc, int M, int N, int K, int k_chunk, Epilogue ep,
                  float* __restrict__ split_ws, int emu) {
+    pdl_grid_sync();
     __shared__ __align__(16) float As[BK][BM + PADM];
     __shared__ __align__(16) float Bs[BK][BN + PADM];
     const int tid = threadIdx.x;
@@ -115,6 +116,7 @@ gemm_simt_kernel(const float* __restrict__ A, long long sam, long long sak, cons
 __global__ void __launch_bounds__(256)
 gemm_splitk_reduce_kernel(const float* __restrict__ ws, int splits, float* __restrict__ C, long long ldc, int M, int N,
                           Epilogue ep) {
+    pdl_grid_sync();
     const long long total = (long long)M * N;
     for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
         const int m = (int)(i / N), n = (int)(i - (long long)m * N);
@@ -129,7 +131,7 @@ gemm_splitk_reduce_kernel(const float* __restrict__ ws, int splits, float* __res
 int launch_splitk_reduce(const float* ws, int splits, const GemmArgs& a, cudaStream_t st) {
     Epilogue ep{a.bias, a.colscale, a.pre, a.ldpre, a.pre_div, a.res, a.ldres, a.res_div, a.res_mod, a.act, a.beta, a.alpha, a.preact, a.ldc};
     const long long total = (long long)a.M * a.N;
-    gemm_splitk_reduce_kernel<<<(int)min((long long)148 * 8, (total + 255) / 256), 256, 0, st>>>(ws, splits, a.C, a.ldc, a.M, a.N, ep);
+    launch_k(gemm_splitk_reduce_kernel, (int)min((long long)148 * 8, (total + 255) / 256), 256, 0, st, ws, splits, a.C, a.ldc, a.M, a.N, ep);
     RIFT_LAUNCH_OK();
     return 0;
 }
@@ -153,7 +155,7 @@ int launch_gemm_simt(const GemmArgs& a, cudaStream_t st) {
     if (emu < 0) { const char* s = getenv("RIFT_B200_EMULATE"); emu = s ? atoi(s) : 0; }
     const bool ak = (a.sak == 1), bk = (a.sbk == 1);
 #define RIFT_GEMM_LAUNCH(AK, BK_)                                                                                     \
-    gemm_simt_kernel<AK, BK_><<<grid, 256, 0, st>>>(a.A, a.sam, a.sak, a.B, a.sbn, a.sbk, a.C, a.ldc, a.M, a.N, a.K, \
+    launch_k(gemm_simt_kernel<AK, BK_>, grid, 256, 0, st, a.A, a.sam, a.sak, a.B, a.sbn, a.sbk, a.C, a.ldc, a.M, a.N, a.K, \
                                                     k_chunk, ep, ws, emu)
     if (ak && bk) RIFT_GEMM_LAUNCH(true, true);
     else if (ak && !bk) RIFT_GEMM_LAUNCH(true, false);
@@ -163,7 +165,7 @@ int launch_gemm_simt(const GemmArgs& a, cudaStream_t st) {
     RIFT_LAUNCH_OK();
     if (splits > 1) {
         const long long total = (long long)a.M * a.N;
-        gemm_splitk_reduce_kernel<<<(int)min((long long)148 * 8, (total + 255) / 256), 256, 0, st>>>(ws, splits, a.C, a.ldc,
+        launch_k(gemm_splitk_reduce_kernel, (int)min((long long)148 * 8, (total + 255) / 256), 256, 0, st, ws, splits, a.C, a.ldc,
                                                                                                     a.M, a.N, ep);
         RIFT_LAUNCH_OK();
     }

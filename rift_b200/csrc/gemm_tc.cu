@@ -179,6 +179,7 @@ template <int BN, bool MN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, TcKernelArgs g) {
+    pdl_trigger();        // the dependent kernel may be scheduled; our own dependency is awaited after the set-up below
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     using SM = TcSmem<BN>;
@@ -191,7 +192,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     float* stage_t = reinterpret_cast<float*>(smem + TC_STAGES * SM::STAGE + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) TC_TRACE(0);
     const int tiles_n = (g.N + BN - 1) / BN;
     const int tiles_m = (g.M + TC_BM - 1) / TC_BM;
     const int tiles_mn = tiles_m * tiles_n;
@@ -212,7 +212,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    if (threadIdx.x == 0) TC_TRACE(1);
+    pdl_wait();           // barriers, TMEM and descriptor prefetch above overlap the previous kernel's tail
+    if (threadIdx.x == 0) { if (g.trace && blockIdx.x == 0) g.trace[0] = gtimer(); TC_TRACE(1); }
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -466,6 +467,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 __global__ void __launch_bounds__(256)
 pack_split_kernel(const float* __restrict__ src, long long ld, int M, int K, int Kp, __nv_bfloat16* __restrict__ hi,
                   __nv_bfloat16* __restrict__ lo, int vec) {
+    pdl_grid_sync();
     const int kq = Kp >> 2;
     const long long total = (long long)M * kq;
     for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
@@ -497,6 +499,7 @@ pack_split_kernel(const float* __restrict__ src, long long ld, int M, int K, int
 __global__ void __launch_bounds__(256)
 pack_split_colsum_kernel(const float* __restrict__ src, long long ld, int M, int K, int Kp, __nv_bfloat16* __restrict__ hi,
                          __nv_bfloat16* __restrict__ lo, float* __restrict__ partial) {
+    pdl_grid_sync();
     __shared__ float4 sm[8][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int k = (blockIdx.x * 32 + tx) * 4;
@@ -547,7 +550,7 @@ int launch_pack_split_colsum(const float* src, long long ld, int M, int K, int K
     if (!vec) return 0;
     const int chunks = cdiv(Kp, 128);
     const int slabs = max(1, min(148, min(cdiv(M, 16), cdiv(148 * 4, chunks))));
-    pack_split_colsum_kernel<<<dim3(chunks, slabs), 256, 0, st>>>(src, ld, M, K, Kp, static_cast<__nv_bfloat16*>(hi),
+    launch_k(pack_split_colsum_kernel, dim3(chunks, slabs), 256, 0, st, src, ld, M, K, Kp, static_cast<__nv_bfloat16*>(hi),
                                                                  static_cast<__nv_bfloat16*>(lo), partial);
     RIFT_LAUNCH_OK();
     *slabs_out = slabs;
@@ -558,7 +561,7 @@ int launch_pack_split(const float* src, long long ld, int M, int K, int Kp, void
     if (M <= 0) return 0;
     const int vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
     const long long total = (long long)M * (Kp >> 2);
-    pack_split_kernel<<<(int)min((long long)148 * 16, (total + 255) / 256), 256, 0, st>>>(
+    launch_k(pack_split_kernel, (int)min((long long)148 * 16, (total + 255) / 256), 256, 0, st, 
         src, ld, M, K, Kp, static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(lo), vec);
     RIFT_LAUNCH_OK();
     return 0;
@@ -573,6 +576,7 @@ long long split_job_units(int N, int Kp) { return (long long)((N + 31) / 32) * (
 
 __global__ void __launch_bounds__(256)
 split_weights_kernel(const SplitJob* __restrict__ jobs, int n_jobs, long long total) {
+    pdl_grid_sync();
     __shared__ float tile[64][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     for (long long u = blockIdx.x; u < total; u += gridDim.x) {
@@ -625,7 +629,7 @@ split_weights_kernel(const SplitJob* __restrict__ jobs, int n_jobs, long long to
 
 int launch_split_weights(const void* jobs_dev, int n_jobs, long long total, cudaStream_t st) {
     if (n_jobs <= 0 || total <= 0) return 0;
-    split_weights_kernel<<<(int)min((long long)148 * 16, total), 256, 0, st>>>(static_cast<const SplitJob*>(jobs_dev), n_jobs, total);
+    launch_k(split_weights_kernel, (int)min((long long)148 * 16, total), 256, 0, st, static_cast<const SplitJob*>(jobs_dev), n_jobs, total);
     RIFT_LAUNCH_OK();
     return 0;
 }
@@ -743,7 +747,7 @@ static int launch_tc(const GemmArgs& a, const PlaneOp& A, const PlaneOp& B, int 
                           a.alpha, a.preact};
     }
     const int n_tiles = cdiv(a.N, BN) * cdiv(a.M, TC_BM) * g.splits;
-    gemm_tc_kernel<BN, MN><<<min(n_tiles, sms), TC_THREADS, TcSmem<BN>::TOTAL, st>>>(*ma_hi, *ma_lo, *mb_hi, *mb_lo, g);
+    launch_k(gemm_tc_kernel<BN, MN>, min(n_tiles, sms), TC_THREADS, TcSmem<BN>::TOTAL, st, *ma_hi, *ma_lo, *mb_hi, *mb_lo, g);
     RIFT_LAUNCH_OK();
     if (splits > 1) return launch_splitk_reduce(partials, g.splits, a, st);
     return 0;

@@ -51,6 +51,7 @@ template <int HD>
 __global__ void __launch_bounds__(128)
 attention_bwd_kernel(AttnArgs a, const float* __restrict__ d_o, long long lddo, float* __restrict__ dq, long long lddq,
                      float* __restrict__ dk, float* __restrict__ dv, long long lddk, long long lddv) {
+    pdl_grid_sync();
     extern __shared__ __align__(16) float sm[];
     float* Qs = sm;                                  // [Sq][HD]  (pre-scaled)
     float* dOs = Qs + (size_t)a.Sq * HD;             // [Sq][HD]
@@ -145,6 +146,7 @@ template <int G>
 __global__ void __launch_bounds__(512)
 attention_bwd2_kernel(AttnArgs a, const float* __restrict__ d_o, long long lddo, float* __restrict__ dq, long long lddq,
                       float* __restrict__ dk, float* __restrict__ dv, long long lddk, long long lddv, int PB, int tpp) {
+    pdl_grid_sync();
     constexpr int HD = 32;
     extern __shared__ __align__(16) float sm[];
     const int Sq = a.Sq, Sk = a.Sk, Skp = Sk | 1;
@@ -315,7 +317,7 @@ int launch_attention_bwd(const AttnArgs& a, const float* d_o, long long lddo, fl
                 RIFT_CUDA_OK(cudaFuncSetAttribute(attention_bwd2_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
                 attr2 = true;
             }
-            attention_bwd2_kernel<G><<<(unsigned)((nprob + PB - 1) / PB), PB * tpp, PB * per, st>>>(a, d_o, lddo, dq, lddq, dk, dv, lddk,
+            launch_k(attention_bwd2_kernel<G>, (unsigned)((nprob + PB - 1) / PB), PB * tpp, PB * per, st, a, d_o, lddo, dq, lddq, dk, dv, lddk,
                                                                                                  lddv, PB, tpp);
             RIFT_LAUNCH_OK();
             return 0;
@@ -330,8 +332,8 @@ int launch_attention_bwd(const AttnArgs& a, const float* d_o, long long lddo, fl
         attr = true;
     }
     const int threads = min(128, (max(a.Sq, a.Sk) + 31) / 32 * 32);
-    if (a.hd == 32) attention_bwd_kernel<32><<<a.B * a.H, threads, smem, st>>>(a, d_o, lddo, dq, lddq, dk, dv, lddk, lddv);
-    else attention_bwd_kernel<64><<<a.B * a.H, threads, smem, st>>>(a, d_o, lddo, dq, lddq, dk, dv, lddk, lddv);
+    if (a.hd == 32) launch_k(attention_bwd_kernel<32>, a.B * a.H, threads, smem, st, a, d_o, lddo, dq, lddq, dk, dv, lddk, lddv);
+    else launch_k(attention_bwd_kernel<64>, a.B * a.H, threads, smem, st, a, d_o, lddo, dq, lddq, dk, dv, lddk, lddv);
     RIFT_LAUNCH_OK();
     return 0;
 }
@@ -345,6 +347,7 @@ constexpr int NATB_MAXL = 32, NATB_MAXK = 7;
 __global__ void __launch_bounds__(128)
 nat_attention_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ d_out, int n_seq, int L, int heads, int hd,
                          int ksize, const float* __restrict__ rpb, float* __restrict__ dqkv, float* __restrict__ drpb_partial) {
+    pdl_grid_sync();
     __shared__ float s_dk[4][NATB_MAXL][32];
     __shared__ float s_dv[4][NATB_MAXL][32];
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -423,7 +426,7 @@ int launch_nat_attention_bwd(const float* qkv, const float* d_out, int n_seq, in
                              const float* rpb, float* dqkv, float* drpb_partial, cudaStream_t st) {
     if (n_seq <= 0) return 0;
     RIFT_REQUIRE(hd <= 32 && ksize <= NATB_MAXK && L >= ksize && L <= NATB_MAXL, "nat_attention_bwd: unsupported shape");
-    nat_attention_bwd_kernel<<<cdiv((long long)n_seq * heads, 4), 128, 0, st>>>(qkv, d_out, n_seq, L, heads, hd, ksize, rpb, dqkv,
+    launch_k(nat_attention_bwd_kernel, cdiv((long long)n_seq * heads, 4), 128, 0, st, qkv, d_out, n_seq, L, heads, hd, ksize, rpb, dqkv,
                                                                              drpb_partial);
     RIFT_LAUNCH_OK();
     return 0;
@@ -435,6 +438,7 @@ int launch_nat_attention_bwd(const float* qkv, const float* d_out, int n_seq, in
 // max-pool: the gradient of a pooled value goes to the arg-max point (nowhere when the winner was a padded zero)
 __global__ void masked_maxpool_bwd_kernel(const float* __restrict__ dout, const int* __restrict__ argmax, int groups, int n,
                                           int C, float* __restrict__ dx, int accumulate) {
+    pdl_grid_sync();
     FOR_GRID(e, (long long)groups * n * C) {
         const int c = (int)(e % C);
         const long long r = e / C;
@@ -448,7 +452,7 @@ int launch_masked_maxpool_bwd(const float* dout, const int* argmax, int groups, 
                               cudaStream_t st) {
     const long long total = (long long)groups * n * C;
     if (total <= 0) return 0;
-    masked_maxpool_bwd_kernel<<<GRID1D(total, 256), 256, 0, st>>>(dout, argmax, groups, n, C, dx, accumulate);
+    launch_k(masked_maxpool_bwd_kernel, GRID1D(total, 256), 256, 0, st, dout, argmax, groups, n, C, dx, accumulate);
     RIFT_LAUNCH_OK();
     return 0;
 }
@@ -456,6 +460,7 @@ int launch_masked_maxpool_bwd(const float* dout, const int* argmax, int groups, 
 // col2im for the k=3, pad=1 im2col (gather form: every dx element sums its <= 3 contributions)
 __global__ void col2im_k3_kernel(const float* __restrict__ dcols, int n_seq, int L, int Lout, int C, int stride,
                                  float* __restrict__ dx, int accumulate) {
+    pdl_grid_sync();
     FOR_GRID(e, (long long)n_seq * L * C) {
         const int c = (int)(e % C);
         const long long r = e / C;
@@ -477,12 +482,13 @@ int launch_col2im_k3(const float* dcols, int n_seq, int L, int C, int stride, fl
     const int Lout = (L + 2 - 3) / stride + 1;
     const long long total = (long long)n_seq * L * C;
     if (total <= 0) return 0;
-    col2im_k3_kernel<<<GRID1D(total, 256), 256, 0, st>>>(dcols, n_seq, L, Lout, C, stride, dx, accumulate);
+    launch_k(col2im_k3_kernel, GRID1D(total, 256), 256, 0, st, dcols, n_seq, L, Lout, C, stride, dx, accumulate);
     RIFT_LAUNCH_OK();
     return 0;
 }
 // im2col_k3_last: dx[n, L-2+k, c] += dcols[n, c*3+k] for k = 0, 1 ; everything else 0
 __global__ void col2im_k3_last_kernel(const float* __restrict__ dcols, int n_seq, int L, int C, float* __restrict__ dx) {
+    pdl_grid_sync();
     FOR_GRID(e, (long long)n_seq * L * C) {
         const int c = (int)(e % C);
         const long long r = e / C;
@@ -495,7 +501,7 @@ __global__ void col2im_k3_last_kernel(const float* __restrict__ dcols, int n_seq
 int launch_col2im_k3_last(const float* dcols, int n_seq, int L, int C, float* dx, cudaStream_t st) {
     const long long total = (long long)n_seq * L * C;
     if (total <= 0) return 0;
-    col2im_k3_last_kernel<<<GRID1D(total, 256), 256, 0, st>>>(dcols, n_seq, L, C, dx);
+    launch_k(col2im_k3_last_kernel, GRID1D(total, 256), 256, 0, st, dcols, n_seq, L, C, dx);
     RIFT_LAUNCH_OK();
     return 0;
 }
@@ -503,6 +509,7 @@ int launch_col2im_k3_last(const float* dcols, int n_seq, int L, int C, float* dx
 // transpose of fpn_upsample_add: dsrc[n, i, c] += sum_j w(j -> i) ddst[n, j, c]
 __global__ void fpn_upsample_add_bwd_kernel(const float* __restrict__ ddst, float* __restrict__ dsrc, int n_seq, int Ld, int Ls,
                                             int C) {
+    pdl_grid_sync();
     const float rscale = (float)Ls / (float)Ld;
     FOR_GRID(e, (long long)n_seq * Ls * C) {
         const int c = (int)(e % C);
@@ -527,7 +534,7 @@ __global__ void fpn_upsample_add_bwd_kernel(const float* __restrict__ ddst, floa
 int launch_fpn_upsample_add_bwd(const float* ddst, float* dsrc, int n_seq, int Ld, int Ls, int C, cudaStream_t st) {
     const long long total = (long long)n_seq * Ls * C;
     if (total <= 0) return 0;
-    fpn_upsample_add_bwd_kernel<<<GRID1D(total, 256), 256, 0, st>>>(ddst, dsrc, n_seq, Ld, Ls, C);
+    launch_k(fpn_upsample_add_bwd_kernel, GRID1D(total, 256), 256, 0, st, ddst, dsrc, n_seq, Ld, Ls, C);
     RIFT_LAUNCH_OK();
     return 0;
 }
@@ -535,6 +542,7 @@ int launch_fpn_upsample_add_bwd(const float* ddst, float* dsrc, int n_seq, int L
 // out[g, c] (+)= sum_{i<n} x[(g*n + i), c]        (broadcast-over-points / over-modes terms)
 __global__ void groupsum_kernel(const float* __restrict__ x, long long ldx, int groups, int n, int C, float* __restrict__ out,
                                 long long ldo, int accumulate) {
+    pdl_grid_sync();
     FOR_GRID(e, (long long)groups * C) {
         const int c = (int)(e % C);
         const long long g = e / C;
@@ -547,7 +555,7 @@ __global__ void groupsum_kernel(const float* __restrict__ x, long long ldx, int 
 int launch_groupsum(const float* x, long long ldx, int groups, int n, int C, float* out, long long ldo, int accumulate,
                     cudaStream_t st) {
     if (groups <= 0 || C <= 0) return 0;
-    groupsum_kernel<<<GRID1D((long long)groups * C, 256), 256, 0, st>>>(x, ldx, groups, n, C, out, ldo, accumulate);
+    launch_k(groupsum_kernel, GRID1D((long long)groups * C, 256), 256, 0, st, x, ldx, groups, n, C, out, ldo, accumulate);
     RIFT_LAUNCH_OK();
     return 0;
 }
@@ -555,6 +563,7 @@ int launch_groupsum(const float* x, long long ldx, int groups, int n, int C, flo
 // out[m, c] (+)= sum_{rows r with r % mod == m} x[r, c]   (per-mode parameters m_pos / m_emb, pos_embed)
 __global__ void __launch_bounds__(256)
 modsum_kernel(const float* __restrict__ x, long long ldx, long long rows, int C, int mod, float* __restrict__ out, int accumulate) {
+    pdl_grid_sync();
     // block = (m, 32-column chunk); 8 row lanes x 4 independent accumulators, combined in a fixed order -> deterministic
     __shared__ float sm[8][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -583,7 +592,7 @@ modsum_kernel(const float* __restrict__ x, long long ldx, long long rows, int C,
 }
 int launch_modsum(const float* x, long long ldx, long long rows, int C, int mod, float* out, int accumulate, cudaStream_t st) {
     if (rows <= 0 || C <= 0) return 0;
-    modsum_kernel<<<dim3(mod, cdiv(C, 32)), 256, 0, st>>>(x, ldx, rows, C, mod, out, accumulate);
+    launch_k(modsum_kernel, dim3(mod, cdiv(C, 32)), 256, 0, st, x, ldx, rows, C, mod, out, accumulate);
     RIFT_LAUNCH_OK();
     return 0;
 }
@@ -594,6 +603,7 @@ int launch_modsum(const float* x, long long ldx, long long rows, int C, int mod,
 __global__ void __launch_bounds__(256)
 embedding_bwd_partial_kernel(const float* __restrict__ dy, long long lddy, long long row_offset, int inner, int outer_stride_rows,
                              const int8_t* __restrict__ idx, long long rows, int C, int invert_mask, float* __restrict__ partial) {
+    pdl_grid_sync();
     __shared__ float sm[8][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + tx, k = blockIdx.z;
@@ -615,6 +625,7 @@ embedding_bwd_partial_kernel(const float* __restrict__ dy, long long lddy, long 
     }
 }
 __global__ void embedding_bwd_final_kernel(const float* __restrict__ partial, int slabs, int C, int n_emb, float* __restrict__ demb) {
+    pdl_grid_sync();
     FOR_GRID(e, (long long)n_emb * C) {
         const int c = (int)(e % C);
         const int k = (int)(e / C);
@@ -628,10 +639,10 @@ int launch_embedding_bwd(const float* dy, long long lddy, long long row_offset, 
                          cudaStream_t st) {
     if (rows <= 0) return 0;
     const int slabs = (int)max(1LL, min(148LL / n_emb, (rows + 63) / 64));
-    embedding_bwd_partial_kernel<<<dim3(cdiv(C, 32), slabs, n_emb), 256, 0, st>>>(dy, lddy, row_offset, inner, outer_stride_rows,
+    launch_k(embedding_bwd_partial_kernel, dim3(cdiv(C, 32), slabs, n_emb), 256, 0, st, dy, lddy, row_offset, inner, outer_stride_rows,
                                                                                  idx, rows, C, invert_mask, scratch);
     RIFT_LAUNCH_OK();
-    embedding_bwd_final_kernel<<<GRID1D((long long)n_emb * C, 256), 256, 0, st>>>(scratch, slabs, C, n_emb, demb);
+    launch_k(embedding_bwd_final_kernel, GRID1D((long long)n_emb * C, 256), 256, 0, st, scratch, slabs, C, n_emb, demb);
     RIFT_LAUNCH_OK();
     return 0;
 }
@@ -640,6 +651,7 @@ int launch_embedding_bwd(const float* dy, long long lddy, long long row_offset, 
 __global__ void masked_gather_rows_kernel(const float* __restrict__ src, long long lds, long long row_offset, int inner,
                                           int outer_stride_rows, const uint8_t* __restrict__ keep, long long rows, int C,
                                           float* __restrict__ out, int zero_inner0) {
+    pdl_grid_sync();
     FOR_GRID(e, rows * C) {
         const int c = (int)(e % C);
         const long long r = e / C;
@@ -651,7 +663,7 @@ __global__ void masked_gather_rows_kernel(const float* __restrict__ src, long lo
 int launch_masked_gather_rows(const float* src, long long lds, long long row_offset, int inner, int outer_stride_rows,
                               const uint8_t* keep, long long rows, int C, float* out, int zero_inner0, cudaStream_t st) {
     if (rows <= 0) return 0;
-    masked_gather_rows_kernel<<<GRID1D(rows * C, 256), 256, 0, st>>>(src, lds, row_offset, inner, outer_stride_rows, keep, rows,
+    launch_k(masked_gather_rows_kernel, GRID1D(rows * C, 256), 256, 0, st, src, lds, row_offset, inner, outer_stride_rows, keep, rows,
                                                                     C, out, zero_inner0);
     RIFT_LAUNCH_OK();
     return 0;
@@ -659,11 +671,12 @@ int launch_masked_gather_rows(const float* src, long long lds, long long row_off
 
 // dy[r, c] *= colscale[c]
 __global__ void scale_cols_kernel(float* __restrict__ dy, const float* __restrict__ s, long long rows, int C) {
+    pdl_grid_sync();
     FOR_GRID(e, rows * C) dy[e] *= s[e % C];
 }
 int launch_scale_cols(float* dy, const float* colscale, long long rows, int C, cudaStream_t st) {
     if (rows <= 0) return 0;
-    scale_cols_kernel<<<GRID1D(rows * C, 256), 256, 0, st>>>(dy, colscale, rows, C);
+    launch_k(scale_cols_kernel, GRID1D(rows * C, 256), 256, 0, st, dy, colscale, rows, C);
     RIFT_LAUNCH_OK();
     return 0;
 }
@@ -673,6 +686,7 @@ int launch_scale_cols(float* dy, const float* colscale, long long rows, int C, c
 __global__ void __launch_bounds__(256)
 bn_affine_bwd_partial_kernel(const float* __restrict__ dz, const float* __restrict__ v, long long rows, int C,
                              const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ partial) {
+    pdl_grid_sync();
     for (int c = threadIdx.x; c < C; c += 256) {
         float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
         const float g = gamma[c], b = beta[c];
@@ -693,6 +707,7 @@ bn_affine_bwd_partial_kernel(const float* __restrict__ dz, const float* __restri
 // second stage: fixed-order sum over the nb partial rows ([nb][2][C]), 8 row lanes per column; blockIdx.y: 0 dgamma, 1 dbeta
 __global__ void __launch_bounds__(256)
 bn_affine_bwd_final_kernel(const float* __restrict__ partial, int nb, int C, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    pdl_grid_sync();
     __shared__ float sm[8][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + tx;
@@ -713,9 +728,9 @@ int launch_bn_affine_bwd(const float* dz, const float* v, long long rows, int C,
                          float* dgamma, float* dbeta, float* scratch, cudaStream_t st) {
     if (rows <= 0) return 0;
     const int nb = (int)min((long long)148, rows);          // scratch holds 148 x 2 x C partials
-    bn_affine_bwd_partial_kernel<<<nb, 256, 0, st>>>(dz, v, rows, C, gamma, beta, scratch);
+    launch_k(bn_affine_bwd_partial_kernel, nb, 256, 0, st, dz, v, rows, C, gamma, beta, scratch);
     RIFT_LAUNCH_OK();
-    bn_affine_bwd_final_kernel<<<dim3(cdiv(C, 32), 2), 256, 0, st>>>(scratch, nb, C, dgamma, dbeta);
+    launch_k(bn_affine_bwd_final_kernel, dim3(cdiv(C, 32), 2), 256, 0, st, scratch, nb, C, dgamma, dbeta);
     RIFT_LAUNCH_OK();
     return 0;
 }
@@ -724,6 +739,7 @@ int launch_bn_affine_bwd(const float* dz, const float* v, long long rows, int C,
 //   contrib[r, j] = (-sin(a_j) dfeat[r, j] + cos(a_j) dfeat[r, nfreq + j]) * 2 pi x[r]   (then column-summed)
 __global__ void fourier_freq_bwd_kernel(const float* __restrict__ x, int rows, int d, int dsel, const float* __restrict__ freqs,
                                         int nfreq, const float* __restrict__ dfeat, int ldf, float* __restrict__ contrib) {
+    pdl_grid_sync();
     FOR_GRID(e, (long long)rows * nfreq) {
         const int j = (int)(e % nfreq);
         const long long r = e / nfreq;
@@ -735,7 +751,7 @@ __global__ void fourier_freq_bwd_kernel(const float* __restrict__ x, int rows, i
 int launch_fourier_freq_bwd(const float* x, int rows, int d, int dsel, const float* freqs, int nfreq, const float* dfeat,
                             int ldf, float* contrib, cudaStream_t st) {
     if (rows <= 0) return 0;
-    fourier_freq_bwd_kernel<<<GRID1D((long long)rows * nfreq, 256), 256, 0, st>>>(x, rows, d, dsel, freqs, nfreq, dfeat, ldf,
+    launch_k(fourier_freq_bwd_kernel, GRID1D((long long)rows * nfreq, 256), 256, 0, st, x, rows, d, dsel, freqs, nfreq, dfeat, ldf,
                                                                                  contrib);
     RIFT_LAUNCH_OK();
     return 0;
@@ -745,6 +761,7 @@ int launch_fourier_freq_bwd(const float* x, int rows, int d, int dsel, const flo
 __global__ void __launch_bounds__(256)
 state_tokens_bwd_kernel(const float* __restrict__ cur, int cs_stride, int bs, int n_tok, int D, const float* __restrict__ dtok,
                         float* __restrict__ dw_all /*[n_tok][D]*/, float* __restrict__ db_all /*[n_tok][D]*/) {
+    pdl_grid_sync();
     const int i = blockIdx.x;
     for (int c = blockIdx.y * 256 + threadIdx.x; c < D; c += gridDim.y * 256) {
         float aw = 0.f, ab = 0.f;
@@ -760,7 +777,7 @@ state_tokens_bwd_kernel(const float* __restrict__ cur, int cs_stride, int bs, in
 int launch_state_tokens_bwd(const float* cur, int cs_stride, int bs, int n_tok, int D, const float* dtok, float* dw_all,
                             float* db_all, cudaStream_t st) {
     if (bs <= 0) return 0;
-    state_tokens_bwd_kernel<<<dim3(n_tok, cdiv(D, 256)), 256, 0, st>>>(cur, cs_stride, bs, n_tok, D, dtok, dw_all, db_all);
+    launch_k(state_tokens_bwd_kernel, dim3(n_tok, cdiv(D, 256)), 256, 0, st, cur, cs_stride, bs, n_tok, D, dtok, dw_all, db_all);
     RIFT_LAUNCH_OK();
     return 0;
 }

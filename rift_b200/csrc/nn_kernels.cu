@@ -19,6 +19,7 @@ layernorm_kernel(const float* __restrict__ x, long long ldx, int rows, int C, co
                  const float* __restrict__ beta, float* __restrict__ y, long long ldy, int relu,
                  const float* __restrict__ add_rowmod, int rowmod, float* __restrict__ y2, float* __restrict__ mean_out,
                  float* __restrict__ rstd_out, Planes yp, Planes y2p) {
+    pdl_grid_sync();
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
     for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += gridDim.x * wpb) {
@@ -56,6 +57,7 @@ layernorm4_kernel(const float* __restrict__ x, long long ldx, int rows, int C, c
                   const float* __restrict__ beta, float* __restrict__ y, long long ldy, int relu,
                   const float* __restrict__ add_rowmod, int rowmod, float* __restrict__ y2, float* __restrict__ mean_out,
                   float* __restrict__ rstd_out, Planes yp, Planes y2p) {
+    pdl_grid_sync();
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
     const int C4 = C >> 2;
@@ -116,12 +118,12 @@ int launch_layernorm(const float* x, long long ldx, int rows, int C, const float
     auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
     if ((C & 3) == 0 && C <= 1024 && (ldx & 3) == 0 && (ldy & 3) == 0 && al16(x) && al16(y) && al16(y2) && al16(gamma) &&
         al16(beta) && al16(add_rowmod)) {
-        layernorm4_kernel<<<min(cdiv(rows, 8), 148 * 8), 256, 0, st>>>(x, ldx, rows, C, gamma, beta, y, ldy, relu, add_rowmod,
+        launch_k(layernorm4_kernel, min(cdiv(rows, 8), 148 * 8), 256, 0, st, x, ldx, rows, C, gamma, beta, y, ldy, relu, add_rowmod,
                                                                        rowmod, y2, mean, rstd, yp, y2p);
         RIFT_LAUNCH_OK();
         return 0;
     }
-    layernorm_kernel<<<min(cdiv(rows, 8), 148 * 8), 256, 0, st>>>(x, ldx, rows, C, gamma, beta, y, ldy, relu, add_rowmod,
+    launch_k(layernorm_kernel, min(cdiv(rows, 8), 148 * 8), 256, 0, st, x, ldx, rows, C, gamma, beta, y, ldy, relu, add_rowmod,
                                                                   rowmod, y2, mean, rstd, yp, y2p);
     RIFT_LAUNCH_OK();
     return 0;
@@ -138,6 +140,7 @@ layernorm_bwd_kernel(const float* __restrict__ x, long long ldx, const float* __
                      int C, const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
                      const float* __restrict__ y_relu, long long ldy, float* __restrict__ dx, long long lddx,
                      int dx_accumulate, float* __restrict__ partial /*[grid][2][C]*/) {
+    pdl_grid_sync();
     extern __shared__ float sm[];      // [8 warps][2][C]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float dg[LNB_MAXC / 32], db[LNB_MAXC / 32];
@@ -194,6 +197,7 @@ layernorm_bwd_kernel(const float* __restrict__ x, long long ldx, const float* __
 __global__ void __launch_bounds__(256)
 partial_reduce_accumulate_kernel(const float* __restrict__ partial, int nb, long long stride, int C, float* __restrict__ out,
                                  int accumulate) {
+    pdl_grid_sync();
     FOR_GRID(c, C) {
         float a = 0.f;
         for (int b = 0; b < nb; ++b) a += partial[(long long)b * stride + c];
@@ -228,6 +232,7 @@ layernorm_bwd4_kernel(const float* __restrict__ x, long long ldx, const float* _
                       const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
                       const float* __restrict__ y_relu, long long ldy, float* __restrict__ dx, long long lddx,
                       int dx_accumulate, float* __restrict__ partial /*[grid][2][C]*/) {
+    pdl_grid_sync();
     extern __shared__ float sm[];      // [8 warps][2][C]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int C4 = C >> 2;
@@ -318,7 +323,7 @@ int launch_layernorm_bwd(const float* x, long long ldx, const float* dy, long lo
             float* part = dgamma ? scratch : nullptr;
             const int nv = cdiv(C, 128);
 #define RIFT_LNB4(NV)                                                                                                       \
-    layernorm_bwd4_kernel<NV><<<nb4, 256, smem4, st>>>(x, ldx, dy, lddy, rows, C, gamma, mean, rstd, y_for_relu, ldy, dx, \
+    launch_k(layernorm_bwd4_kernel<NV>, nb4, 256, smem4, st, x, ldx, dy, lddy, rows, C, gamma, mean, rstd, y_for_relu, ldy, dx, \
                                                        lddx, dx_accumulate, part)
             static bool attr4 = false;
             if (!attr4) {
@@ -332,7 +337,7 @@ int launch_layernorm_bwd(const float* x, long long ldx, const float* dy, long lo
                 cudaStream_t s2;
                 int r2 = second_stage_stream(st, fin, &s2);
                 if (r2) return r2;
-                colsum_final2_kernel<<<dim3(cdiv(C, 32), 2), 256, 0, s2>>>(scratch, nb4, C, dgamma, dbeta);
+                launch_k(colsum_final2_kernel, dim3(cdiv(C, 32), 2), 256, 0, s2, scratch, nb4, C, dgamma, dbeta);
                 RIFT_LAUNCH_OK();
             }
             return 0;
@@ -345,14 +350,14 @@ int launch_layernorm_bwd(const float* x, long long ldx, const float* dy, long lo
         RIFT_CUDA_OK(cudaFuncSetAttribute(layernorm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * LNB_MAXC * 4));
         attr = true;
     }
-    layernorm_bwd_kernel<<<nb, 256, smem, st>>>(x, ldx, dy, lddy, rows, C, gamma, mean, rstd, y_for_relu, ldy, dx, lddx,
+    launch_k(layernorm_bwd_kernel, nb, 256, smem, st, x, ldx, dy, lddy, rows, C, gamma, mean, rstd, y_for_relu, ldy, dx, lddx,
                                                 dx_accumulate, dgamma ? scratch : nullptr);
     RIFT_LAUNCH_OK();
     if (dgamma) {
         cudaStream_t s2;
         int r2 = second_stage_stream(st, fin, &s2);
         if (r2) return r2;
-        colsum_final2_kernel<<<dim3(cdiv(C, 32), 2), 256, 0, s2>>>(scratch, nb, C, dgamma, dbeta);
+        launch_k(colsum_final2_kernel, dim3(cdiv(C, 32), 2), 256, 0, s2, scratch, nb, C, dgamma, dbeta);
         RIFT_LAUNCH_OK();
     }
     return 0;
@@ -364,6 +369,7 @@ int launch_layernorm_bwd(const float* x, long long ldx, const float* dy, long lo
 // scratch: [slabs][C] with slabs <= 148 (callers size it 148 * C).
 __global__ void __launch_bounds__(256)
 colsum_partial_kernel(const float* __restrict__ x, long long ldx, int rows, int C, float* __restrict__ partial) {
+    pdl_grid_sync();
     __shared__ float sm[8][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + tx;
@@ -391,6 +397,7 @@ colsum_partial_kernel(const float* __restrict__ x, long long ldx, int rows, int 
 // out[c] (+)= sum over nb partial rows, 8 row lanes per column, fixed order
 __global__ void __launch_bounds__(256)
 colsum_final_kernel(const float* __restrict__ partial, int nb, long long stride, int C, float* __restrict__ out, int accumulate) {
+    pdl_grid_sync();
     __shared__ float sm[8][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + tx;
@@ -407,6 +414,7 @@ colsum_final_kernel(const float* __restrict__ partial, int nb, long long stride,
 }
 __global__ void __launch_bounds__(256)
 colsum_final2_kernel(const float* __restrict__ partial, int nb, int C, float* __restrict__ out0, float* __restrict__ out1) {
+    pdl_grid_sync();
     __shared__ float sm[8][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + tx;
@@ -428,7 +436,7 @@ int launch_colsum_final(const float* partial, int slabs, int C, float* out, int 
     cudaStream_t s2;
     int r2 = second_stage_stream(st, fin, &s2);
     if (r2) return r2;
-    colsum_final_kernel<<<cdiv(C, 32), 256, 0, s2>>>(partial, slabs, C, C, out, accumulate);
+    launch_k(colsum_final_kernel, cdiv(C, 32), 256, 0, s2, partial, slabs, C, C, out, accumulate);
     RIFT_LAUNCH_OK();
     return 0;
 }
@@ -437,12 +445,12 @@ int launch_colsum(const float* x, long long ldx, int rows, int C, float* out, in
     if (C <= 0) return 0;
     const int chunks = cdiv(C, 32);
     int slabs = max(1, min(148, min(cdiv(rows, 32), cdiv(148 * 4, chunks))));
-    colsum_partial_kernel<<<dim3(chunks, slabs), 256, 0, st>>>(x, ldx, rows, C, scratch);
+    launch_k(colsum_partial_kernel, dim3(chunks, slabs), 256, 0, st, x, ldx, rows, C, scratch);
     RIFT_LAUNCH_OK();
     cudaStream_t s2;
     int r2 = second_stage_stream(st, fin, &s2);
     if (r2) return r2;
-    colsum_final_kernel<<<chunks, 256, 0, s2>>>(scratch, slabs, C, C, out, accumulate);
+    launch_k(colsum_final_kernel, chunks, 256, 0, s2, scratch, slabs, C, C, out, accumulate);
     RIFT_LAUNCH_OK();
     return 0;
 }
@@ -460,6 +468,7 @@ __device__ __forceinline__ long long attn_row(int b, int inner_n, long long oute
 template <int HD>
 __global__ void __launch_bounds__(128)
 attention_kernel(AttnArgs a) {
+    pdl_grid_sync();
     extern __shared__ float sm[];
     float* Ks = sm;
     float* Vs = sm + (size_t)a.Sk * HD;
@@ -530,8 +539,8 @@ int launch_attention(const AttnArgs& a, cudaStream_t st) {
         RIFT_CUDA_OK(cudaFuncSetAttribute(attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr = true;
     }
-    if (a.hd == 32) attention_kernel<32><<<grid, threads, smem, st>>>(a);
-    else attention_kernel<64><<<grid, threads, smem, st>>>(a);
+    if (a.hd == 32) launch_k(attention_kernel<32>, grid, threads, smem, st, a);
+    else launch_k(attention_kernel<64>, grid, threads, smem, st, a);
     RIFT_LAUNCH_OK();
     return 0;
 }
@@ -547,6 +556,7 @@ constexpr int NAT_MAXL = 32, NAT_MAXK = 7;
 __global__ void __launch_bounds__(128)
 nat_attention_kernel(const float* __restrict__ qkv, int n_seq, int L, int heads, int hd, int ksize,
                      const float* __restrict__ rpb, float* __restrict__ out, Planes op) {
+    pdl_grid_sync();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= n_seq * heads) return;
     const int n = warp / heads, h = warp % heads;
@@ -588,7 +598,7 @@ int launch_nat_attention(const float* qkv, int n_seq, int L, int heads, int hd, 
                          cudaStream_t st, Planes op) {
     if (n_seq <= 0) return 0;
     RIFT_REQUIRE(hd <= 32 && ksize <= NAT_MAXK && L >= ksize && L <= NAT_MAXL, "nat_attention: unsupported shape");
-    nat_attention_kernel<<<cdiv((long long)n_seq * heads * 32, 128), 128, 0, st>>>(qkv, n_seq, L, heads, hd, ksize, rpb, out, op);
+    launch_k(nat_attention_kernel, cdiv((long long)n_seq * heads * 32, 128), 128, 0, st, qkv, n_seq, L, heads, hd, ksize, rpb, out, op);
     RIFT_LAUNCH_OK();
     return 0;
 }
@@ -600,6 +610,7 @@ int launch_nat_attention(const float* qkv, int n_seq, int L, int heads, int hd, 
 // =====================================================================================
 __global__ void im2col_k3_kernel(const float* __restrict__ x, int n_seq, int L, int Lout, int C, int stride,
                                  float* __restrict__ out, Planes op) {
+    pdl_grid_sync();
     const int W = op.on() ? op.Kp : C * 3;          // with planes the pad columns are written (as zeros) too
     const long long total = (long long)n_seq * Lout * W;
     FOR_GRID(e, total) {
@@ -621,13 +632,14 @@ int launch_im2col_k3(const float* x, int n_seq, int L, int C, int stride, float*
     const int Lout = (L + 2 - 3) / stride + 1;
     const long long total = (long long)n_seq * Lout * (op.on() ? op.Kp : C * 3);
     if (total <= 0) return 0;
-    im2col_k3_kernel<<<GRID1D(total, 256), 256, 0, st>>>(x, n_seq, L, Lout, C, stride, out, op);
+    launch_k(im2col_k3_kernel, GRID1D(total, 256), 256, 0, st, x, n_seq, L, Lout, C, stride, out, op);
     RIFT_LAUNCH_OK();
     return 0;
 }
 // only the last output position (the encoder keeps out[:, :, -1], layers/embedding.py:87)
 __global__ void im2col_k3_last_kernel(const float* __restrict__ x, int n_seq, int L, int C, float* __restrict__ out,
                                       Planes op) {
+    pdl_grid_sync();
     const int W = op.on() ? op.Kp : C * 3;
     const long long total = (long long)n_seq * W;
     FOR_GRID(e, total) {
@@ -646,7 +658,7 @@ __global__ void im2col_k3_last_kernel(const float* __restrict__ x, int n_seq, in
 int launch_im2col_k3_last(const float* x, int n_seq, int L, int C, float* out, cudaStream_t st, Planes op) {
     const long long total = (long long)n_seq * (op.on() ? op.Kp : C * 3);
     if (total <= 0) return 0;
-    im2col_k3_last_kernel<<<GRID1D(total, 256), 256, 0, st>>>(x, n_seq, L, C, out, op);
+    launch_k(im2col_k3_last_kernel, GRID1D(total, 256), 256, 0, st, x, n_seq, L, C, out, op);
     RIFT_LAUNCH_OK();
     return 0;
 }
@@ -654,6 +666,7 @@ int launch_im2col_k3_last(const float* x, int n_seq, int L, int C, float* out, c
 // FPN top-down: dst += F.interpolate(src, scale_factor=Ld/Ls, mode='linear', align_corners=False)
 __global__ void fpn_upsample_add_kernel(float* __restrict__ dst, const float* __restrict__ src, int n_seq, int Ld, int Ls,
                                         int C) {
+    pdl_grid_sync();
     const long long total = (long long)n_seq * Ld * C;
     const float rscale = (float)Ls / (float)Ld;
     FOR_GRID(e, total) {
@@ -672,7 +685,7 @@ __global__ void fpn_upsample_add_kernel(float* __restrict__ dst, const float* __
 int launch_fpn_upsample_add(float* dst, const float* src, int n_seq, int Ld, int Ls, int C, cudaStream_t st) {
     const long long total = (long long)n_seq * Ld * C;
     if (total <= 0) return 0;
-    fpn_upsample_add_kernel<<<GRID1D(total, 256), 256, 0, st>>>(dst, src, n_seq, Ld, Ls, C);
+    launch_k(fpn_upsample_add_kernel, GRID1D(total, 256), 256, 0, st, dst, src, n_seq, Ld, Ls, C);
     RIFT_LAUNCH_OK();
     return 0;
 }
@@ -683,6 +696,7 @@ int launch_fpn_upsample_add(float* dst, const float* src, int n_seq, int Ld, int
 // =====================================================================================
 __global__ void masked_maxpool_kernel(const float* __restrict__ x, const uint8_t* __restrict__ mask, int groups, int n, int C,
                                       float* __restrict__ out, int* __restrict__ argmax, Planes op) {
+    pdl_grid_sync();
     const long long total = (long long)groups * C;
     FOR_GRID(e, total) {
         const int c = (int)(e % C);
@@ -706,13 +720,14 @@ int launch_masked_maxpool(const float* x, const uint8_t* mask, int groups, int n
                           cudaStream_t st, Planes op) {
     const long long total = (long long)groups * C;
     if (total <= 0) return 0;
-    masked_maxpool_kernel<<<GRID1D(total, 256), 256, 0, st>>>(x, mask, groups, n, C, out, argmax, op);
+    launch_k(masked_maxpool_kernel, GRID1D(total, 256), 256, 0, st, x, mask, groups, n, C, out, argmax, op);
     RIFT_LAUNCH_OK();
     return 0;
 }
 
 __global__ void mask_any_kernel(const uint8_t* __restrict__ mask, int rows, int n, uint8_t* __restrict__ any_out,
                                 uint8_t* __restrict__ none_out) {
+    pdl_grid_sync();
     FOR_GRID(r, rows) {
         bool a = false;
         for (int i = 0; i < n; ++i) a = a || (mask[r * n + i] != 0);
@@ -722,7 +737,7 @@ __global__ void mask_any_kernel(const uint8_t* __restrict__ mask, int rows, int 
 }
 int launch_mask_any(const uint8_t* mask, int rows, int n, uint8_t* any_out, uint8_t* none_out, cudaStream_t st) {
     if (rows <= 0) return 0;
-    mask_any_kernel<<<GRID1D(rows, 128), 128, 0, st>>>(mask, rows, n, any_out, none_out);
+    launch_k(mask_any_kernel, GRID1D(rows, 128), 128, 0, st, mask, rows, n, any_out, none_out);
     RIFT_LAUNCH_OK();
     return 0;
 }
@@ -731,6 +746,7 @@ int launch_mask_any(const uint8_t* mask, int rows, int n, uint8_t* any_out, uint
 __global__ void token_masks_kernel(const uint8_t* __restrict__ agent_valid, int agent_T, int Th,
                                    const uint8_t* __restrict__ map_valid, int P, int bs, int A, int Mp,
                                    uint8_t* __restrict__ agent_any, uint8_t* __restrict__ key_pad) {
+    pdl_grid_sync();
     const int S = A + Mp;
     FOR_GRID(e, (long long)bs * S) {
         const int s = (int)(e % S);
@@ -750,7 +766,7 @@ __global__ void token_masks_kernel(const uint8_t* __restrict__ agent_valid, int 
 int launch_token_masks(const uint8_t* agent_valid, int agent_T, int Th, const uint8_t* map_valid, int P, int bs, int A,
                        int Mp, uint8_t* agent_any, uint8_t* key_pad, cudaStream_t st) {
     if (bs <= 0) return 0;
-    token_masks_kernel<<<GRID1D((long long)bs * (A + Mp), 128), 128, 0, st>>>(agent_valid, agent_T, Th, map_valid, P, bs, A,
+    launch_k(token_masks_kernel, GRID1D((long long)bs * (A + Mp), 128), 128, 0, st, agent_valid, agent_T, Th, map_valid, P, bs, A,
                                                                              Mp, agent_any, key_pad);
     RIFT_LAUNCH_OK();
     return 0;
@@ -760,6 +776,7 @@ int launch_token_masks(const uint8_t* agent_valid, int agent_T, int Th, const ui
 __global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
                                const float* __restrict__ var, const float* __restrict__ lin_bias, int n,
                                float* __restrict__ scale, float* __restrict__ shift) {
+    pdl_grid_sync();
     FOR_GRID(i, n) {
         const float s = gamma[i] / sqrtf(var[i] + 1e-5f);
         scale[i] = s;
@@ -768,7 +785,7 @@ __global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __r
 }
 int launch_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, const float* lin_bias,
                    int n, float* scale, float* shift, cudaStream_t st) {
-    bn_fold_kernel<<<cdiv(n, 128), 128, 0, st>>>(gamma, beta, mean, var, lin_bias, n, scale, shift);
+    launch_k(bn_fold_kernel, cdiv(n, 128), 128, 0, st, gamma, beta, mean, var, lin_bias, n, scale, shift);
     RIFT_LAUNCH_OK();
     return 0;
 }
@@ -781,6 +798,7 @@ __global__ void agent_features_kernel(const float* __restrict__ pos, const float
                                       const float* __restrict__ vel, const float* __restrict__ shape,
                                       const uint8_t* __restrict__ valid, int n_agents, int Th, int Ts,
                                       float* __restrict__ feat) {
+    pdl_grid_sync();
     const int L = Th - 1;
     const long long total = (long long)n_agents * L;
     FOR_GRID(e, total) {
@@ -805,7 +823,7 @@ int launch_agent_features(const float* pos, const float* heading, const float* v
                           const uint8_t* valid, int n_agents, int Th, int Tstride, float* feat, cudaStream_t st) {
     const long long total = (long long)n_agents * (Th - 1);
     if (total <= 0) return 0;
-    agent_features_kernel<<<GRID1D(total, 128), 128, 0, st>>>(pos, heading, vel, shape, valid, n_agents, Th, Tstride, feat);
+    launch_k(agent_features_kernel, GRID1D(total, 128), 128, 0, st, pos, heading, vel, shape, valid, n_agents, Th, Tstride, feat);
     RIFT_LAUNCH_OK();
     return 0;
 }
@@ -813,6 +831,7 @@ int launch_agent_features(const float* pos, const float* heading, const float* v
 // MapEncoder polygon feature (modules/map_encoder.py:43-60): (n_poly, P, 10)
 __global__ void map_features_kernel(const float* __restrict__ pp, const float* __restrict__ pv, const float* __restrict__ po,
                                     const float* __restrict__ pc, int n_poly, int P, float* __restrict__ feat) {
+    pdl_grid_sync();
     const long long total = (long long)n_poly * P;
     FOR_GRID(e, total) {
         const int p = (int)(e % P);
@@ -836,7 +855,7 @@ int launch_map_features(const float* point_position, const float* point_vector, 
                         const float* polygon_center, int n_poly, int P, float* feat, cudaStream_t st) {
     const long long total = (long long)n_poly * P;
     if (total <= 0) return 0;
-    map_features_kernel<<<GRID1D(total, 128), 128, 0, st>>>(point_position, point_vector, point_orientation, polygon_center,
+    launch_k(map_features_kernel, GRID1D(total, 128), 128, 0, st, point_position, point_vector, point_orientation, polygon_center,
                                                             n_poly, P, feat);
     RIFT_LAUNCH_OK();
     return 0;
@@ -846,6 +865,7 @@ int launch_map_features(const float* point_position, const float* point_vector, 
 // r_pos (n_ref, 3) = [position[0], orientation[0]]
 __global__ void ref_features_kernel(const float* __restrict__ pos, const float* __restrict__ vec, const float* __restrict__ ori,
                                     int n_ref, int Pr, float* __restrict__ feat, float* __restrict__ rpos) {
+    pdl_grid_sync();
     const long long total = (long long)n_ref * Pr;
     FOR_GRID(e, total) {
         const int p = (int)(e % Pr);
@@ -865,7 +885,7 @@ int launch_ref_features(const float* position, const float* vector, const float*
                         float* feat, float* rpos, cudaStream_t st) {
     const long long total = (long long)n_ref * Pr;
     if (total <= 0) return 0;
-    ref_features_kernel<<<GRID1D(total, 128), 128, 0, st>>>(position, vector, orientation, n_ref, Pr, feat, rpos);
+    launch_k(ref_features_kernel, GRID1D(total, 128), 128, 0, st, position, vector, orientation, n_ref, Pr, feat, rpos);
     RIFT_LAUNCH_OK();
     return 0;
 }
@@ -881,6 +901,7 @@ __device__ __forceinline__ float wrap_angle(float a) {
 }
 __global__ void token_pos_kernel(const float* __restrict__ apos, const float* __restrict__ ahead, const float* __restrict__ pc,
                                  int bs, int A, int Th, int Ts, int Mp, float* __restrict__ pos) {
+    pdl_grid_sync();
     const int S = A + Mp;
     FOR_GRID(e, (long long)bs * S) {
         const int s = (int)(e % S);
@@ -899,7 +920,7 @@ __global__ void token_pos_kernel(const float* __restrict__ apos, const float* __
 int launch_token_pos(const float* agent_pos, const float* agent_heading, const float* polygon_center, int bs, int A,
                      int Th, int Tstride, int Mp, float* pos, cudaStream_t st) {
     if (bs <= 0) return 0;
-    token_pos_kernel<<<GRID1D((long long)bs * (A + Mp), 128), 128, 0, st>>>(agent_pos, agent_heading, polygon_center, bs, A,
+    launch_k(token_pos_kernel, GRID1D((long long)bs * (A + Mp), 128), 128, 0, st, agent_pos, agent_heading, polygon_center, bs, A,
                                                                            Th, Tstride, Mp, pos);
     RIFT_LAUNCH_OK();
     return 0;
@@ -909,6 +930,7 @@ int launch_token_pos(const float* agent_pos, const float* agent_heading, const f
 // [cos(x f 2 pi) (nfreq), sin(x f 2 pi) (nfreq), x], zero padded to ldf columns
 __global__ void fourier_features_kernel(const float* __restrict__ x, int rows, int d, int dsel, const float* __restrict__ freqs,
                                         int nfreq, float* __restrict__ feat, int ldfeat, Planes op) {
+    pdl_grid_sync();
     const int ldf = op.on() ? op.Kp : ldfeat;          // loop width: the planes' zero pad is written too
     FOR_GRID(e, (long long)rows * ldf) {
         const int c = (int)(e % ldf);
@@ -931,7 +953,7 @@ int launch_fourier_features(const float* x, int rows, int d, int dsel, const flo
     if (rows <= 0) return 0;
     RIFT_REQUIRE(ldf >= 2 * nfreq + 1, "fourier_features: ldf too small");
     const int width = op.on() ? op.Kp : ldf;
-    fourier_features_kernel<<<GRID1D((long long)rows * width, 256), 256, 0, st>>>(x, rows, d, dsel, freqs, nfreq, feat, ldf, op);
+    launch_k(fourier_features_kernel, GRID1D((long long)rows * width, 256), 256, 0, st, x, rows, d, dsel, freqs, nfreq, feat, ldf, op);
     RIFT_LAUNCH_OK();
     return 0;
 }
@@ -940,6 +962,7 @@ int launch_fourier_features(const float* x, int rows, int d, int dsel, const flo
 struct StateTokParams { const float* w[8]; const float* b[8]; };
 __global__ void state_tokens_kernel(const float* __restrict__ cur, int cs_stride, int bs, int n_tok, int D, StateTokParams p,
                                     const float* __restrict__ pos_embed, float* __restrict__ toks) {
+    pdl_grid_sync();
     FOR_GRID(e, (long long)bs * n_tok * D) {
         const int c = (int)(e % D);
         const long long r = e / D;
@@ -954,7 +977,7 @@ int launch_state_tokens(const float* cur_state, int cs_stride, int bs, int n_tok
     if (bs <= 0) return 0;
     StateTokParams p;
     for (int i = 0; i < 8; ++i) { p.w[i] = i < n_tok ? w[i] : nullptr; p.b[i] = i < n_tok ? b[i] : nullptr; }
-    state_tokens_kernel<<<GRID1D((long long)bs * n_tok * D, 256), 256, 0, st>>>(cur_state, cs_stride, bs, n_tok, D, p,
+    launch_k(state_tokens_kernel, GRID1D((long long)bs * n_tok * D, 256), 256, 0, st, cur_state, cs_stride, bs, n_tok, D, p,
                                                                                pos_embed, toks);
     RIFT_LAUNCH_OK();
     return 0;
@@ -966,6 +989,7 @@ __global__ void agent_assemble_kernel(const float* __restrict__ x_hist, const fl
                                       const uint8_t* __restrict__ agent_any, const int8_t* __restrict__ category,
                                       const float* __restrict__ type_emb, int bs, int A, int S, int D,
                                       float* __restrict__ tokens) {
+    pdl_grid_sync();
     FOR_GRID(e, (long long)bs * A * D) {
         const int c = (int)(e % D);
         const long long r = e / D;
@@ -981,7 +1005,7 @@ __global__ void agent_assemble_kernel(const float* __restrict__ x_hist, const fl
 int launch_agent_assemble(const float* x_hist, const float* x_ego, const uint8_t* agent_any, const int8_t* category,
                           const float* type_emb, int bs, int A, int S, int D, float* tokens, cudaStream_t st) {
     if (bs <= 0) return 0;
-    agent_assemble_kernel<<<GRID1D((long long)bs * A * D, 256), 256, 0, st>>>(x_hist, x_ego, agent_any, category, type_emb,
+    launch_k(agent_assemble_kernel, GRID1D((long long)bs * A * D, 256), 256, 0, st, x_hist, x_ego, agent_any, category, type_emb,
                                                                              bs, A, S, D, tokens);
     RIFT_LAUNCH_OK();
     return 0;
@@ -994,6 +1018,7 @@ __global__ void map_assemble_kernel(const float* __restrict__ x_poly, const floa
                                     const float* __restrict__ type_emb, const float* __restrict__ route_emb,
                                     const float* __restrict__ tl_emb, const float* __restrict__ unknown_emb, int bs, int Mp,
                                     int A, int S, int D, float* __restrict__ tokens) {
+    pdl_grid_sync();
     FOR_GRID(e, (long long)bs * Mp * D) {
         const int c = (int)(e % D);
         const long long r = e / D;
@@ -1010,7 +1035,7 @@ int launch_map_assemble(const float* x_poly, const float* x_speed, const int8_t*
                         const float* tl_emb, const float* unknown_emb, int bs, int Mp, int A, int S, int D, float* tokens,
                         cudaStream_t st) {
     if (bs <= 0 || Mp <= 0) return 0;
-    map_assemble_kernel<<<GRID1D((long long)bs * Mp * D, 256), 256, 0, st>>>(x_poly, x_speed, ptype, on_route, tl, has_speed,
+    launch_k(map_assemble_kernel, GRID1D((long long)bs * Mp * D, 256), 256, 0, st, x_poly, x_speed, ptype, on_route, tl, has_speed,
                                                                             type_emb, route_emb, tl_emb, unknown_emb, bs,
                                                                             Mp, A, S, D, tokens);
     RIFT_LAUNCH_OK();
@@ -1021,6 +1046,7 @@ int launch_map_assemble(const float* x_poly, const float* x_speed, const int8_t*
 // (q_proj(cat[r_emb, m_emb]) split into its two column blocks, modules/planning_decoder.py:162-167)
 __global__ void query_init_kernel(const float* __restrict__ u, const float* __restrict__ v, long long rows, int Mo, int D,
                                   float* __restrict__ q) {
+    pdl_grid_sync();
     FOR_GRID(e, rows * D) {
         const int c = (int)(e % D);
         const long long r = e / D;
@@ -1029,19 +1055,20 @@ __global__ void query_init_kernel(const float* __restrict__ u, const float* __re
 }
 int launch_query_init(const float* u, const float* v, int rows, int Mo, int D, float* q, cudaStream_t st) {
     if (rows <= 0) return 0;
-    query_init_kernel<<<GRID1D((long long)rows * D, 256), 256, 0, st>>>(u, v, rows, Mo, D, q);
+    launch_k(query_init_kernel, GRID1D((long long)rows * D, 256), 256, 0, st, u, v, rows, Mo, D, q);
     RIFT_LAUNCH_OK();
     return 0;
 }
 
 __global__ void zero_rows_kernel(float* __restrict__ x, const uint8_t* __restrict__ flag, int div, long long rows, int C) {
+    pdl_grid_sync();
     FOR_GRID(e, rows * C) {
         if (flag[(e / C) / div]) x[e] = 0.f;
     }
 }
 int launch_zero_rows(float* x, const uint8_t* rowflag, int flag_div, int rows, int C, cudaStream_t st) {
     if (rows <= 0) return 0;
-    zero_rows_kernel<<<GRID1D((long long)rows * C, 256), 256, 0, st>>>(x, rowflag, flag_div, rows, C);
+    launch_k(zero_rows_kernel, GRID1D((long long)rows * C, 256), 256, 0, st, x, rowflag, flag_div, rows, C);
     RIFT_LAUNCH_OK();
     return 0;
 }
@@ -1049,6 +1076,7 @@ int launch_zero_rows(float* x, const uint8_t* rowflag, int flag_div, int rows, i
 // trajectory = cat([loc, yaw, vel], -1) with each head viewed (.., T, 2)  (modules/planning_decoder.py:180-186)
 __global__ void interleave_heads_kernel(const float* __restrict__ loc, const float* __restrict__ yaw, const float* __restrict__ vel,
                                         long long rows, int T, float* __restrict__ out) {
+    pdl_grid_sync();
     FOR_GRID(e, rows * T * 6) {
         const int c = (int)(e % 6);
         const long long rt = e / 6;                  // row * T + t
@@ -1059,20 +1087,21 @@ __global__ void interleave_heads_kernel(const float* __restrict__ loc, const flo
 int launch_interleave_heads(const float* loc, const float* yaw, const float* vel, long long rows, int T, float* out,
                             cudaStream_t st) {
     if (rows <= 0) return 0;
-    interleave_heads_kernel<<<GRID1D(rows * T * 6, 256), 256, 0, st>>>(loc, yaw, vel, rows, T, out);
+    launch_k(interleave_heads_kernel, GRID1D(rows * T * 6, 256), 256, 0, st, loc, yaw, vel, rows, T, out);
     RIFT_LAUNCH_OK();
     return 0;
 }
 
 // probability.masked_fill_(r_padding_mask, -1e6)  (pluto_model.py:203); pi is (rows=bs*R, Mo)
 __global__ void mask_logits_kernel(float* __restrict__ pi, const uint8_t* __restrict__ r_pad, long long rows, int Mo, float fill) {
+    pdl_grid_sync();
     FOR_GRID(e, rows * Mo) {
         if (r_pad[e / Mo]) pi[e] = fill;
     }
 }
 int launch_mask_logits(float* pi, const uint8_t* r_pad, long long rows, int Mo, float fill, cudaStream_t st) {
     if (rows <= 0) return 0;
-    mask_logits_kernel<<<GRID1D(rows * Mo, 256), 256, 0, st>>>(pi, r_pad, rows, Mo, fill);
+    launch_k(mask_logits_kernel, GRID1D(rows * Mo, 256), 256, 0, st, pi, r_pad, rows, Mo, fill);
     RIFT_LAUNCH_OK();
     return 0;
 }
@@ -1080,6 +1109,7 @@ int launch_mask_logits(float* pi, const uint8_t* r_pad, long long rows, int Mo, 
 // out[b*nrows + i, :] = x[b*ldx_batch + (row0+i)*C + :]
 __global__ void gather_rows_kernel(const float* __restrict__ x, long long ldb, int bs, int row0, int nrows, int C,
                                    float* __restrict__ out) {
+    pdl_grid_sync();
     FOR_GRID(e, (long long)bs * nrows * C) {
         const int c = (int)(e % C);
         const long long r = e / C;
@@ -1090,13 +1120,14 @@ __global__ void gather_rows_kernel(const float* __restrict__ x, long long ldb, i
 }
 int launch_gather_rows(const float* x, long long ldx_batch, int bs, int row0, int nrows, int C, float* out, cudaStream_t st) {
     if (bs <= 0 || nrows <= 0) return 0;
-    gather_rows_kernel<<<GRID1D((long long)bs * nrows * C, 256), 256, 0, st>>>(x, ldx_batch, bs, row0, nrows, C, out);
+    launch_k(gather_rows_kernel, GRID1D((long long)bs * nrows * C, 256), 256, 0, st, x, ldx_batch, bs, row0, nrows, C, out);
     RIFT_LAUNCH_OK();
     return 0;
 }
 
 // dy *= act'(.) in place.  ReLU: ref = post-activation (y > 0) ; GELU: ref = pre-activation
 __global__ void act_bwd_kernel(const float* __restrict__ ref, float* __restrict__ dy, long long n, int act) {
+    pdl_grid_sync();
     FOR_GRID(e, n) {
         if (act == ACT_RELU) { if (!(ref[e] > 0.f)) dy[e] = 0.f; }
         else if (act == ACT_GELU) dy[e] *= gelu_erf_grad(ref[e]);
@@ -1104,23 +1135,25 @@ __global__ void act_bwd_kernel(const float* __restrict__ ref, float* __restrict_
 }
 int launch_act_bwd(const float* pre_or_post, float* dy, long long n, int act, cudaStream_t st) {
     if (n <= 0 || act == ACT_NONE) return 0;
-    act_bwd_kernel<<<GRID1D(n, 256), 256, 0, st>>>(pre_or_post, dy, n, act);
+    launch_k(act_bwd_kernel, GRID1D(n, 256), 256, 0, st, pre_or_post, dy, n, act);
     RIFT_LAUNCH_OK();
     return 0;
 }
 
 __global__ void add_inplace_kernel(float* __restrict__ dst, const float* __restrict__ src, long long n) {
+    pdl_grid_sync();
     FOR_GRID(e, n) dst[e] += src[e];
 }
 int launch_add_inplace(float* dst, const float* src, long long n, cudaStream_t st) {
     if (n <= 0) return 0;
-    add_inplace_kernel<<<GRID1D(n, 256), 256, 0, st>>>(dst, src, n);
+    launch_k(add_inplace_kernel, GRID1D(n, 256), 256, 0, st, dst, src, n);
     RIFT_LAUNCH_OK();
     return 0;
 }
 
 // candidate_trajectories = cat([traj[..., :2], atan2(traj[..., 3], traj[..., 2])])  (pluto_model.py:205-212)
 __global__ void traj_outputs_kernel(const float* __restrict__ traj, long long n, float* __restrict__ cand) {
+    pdl_grid_sync();
     FOR_GRID(e, n) {
         const float* t = traj + e * 6;
         cand[e * 3] = t[0];
@@ -1131,7 +1164,7 @@ __global__ void traj_outputs_kernel(const float* __restrict__ traj, long long n,
 int launch_traj_outputs(const float* trajectory, long long n_traj, int T, float* cand, cudaStream_t st) {
     const long long n = n_traj * T;
     if (n <= 0) return 0;
-    traj_outputs_kernel<<<GRID1D(n, 256), 256, 0, st>>>(trajectory, n, cand);
+    launch_k(traj_outputs_kernel, GRID1D(n, 256), 256, 0, st, trajectory, n, cand);
     RIFT_LAUNCH_OK();
     return 0;
 }

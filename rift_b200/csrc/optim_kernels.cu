@@ -18,6 +18,7 @@ constexpr int NORM_THREADS = 256;
 // stage 1: per-block sum of squares (double accumulate), fixed grid -> deterministic partials
 __global__ void __launch_bounds__(NORM_THREADS)
 sumsq_partial_kernel(const float* __restrict__ g, long long n, double* __restrict__ partial) {
+    pdl_grid_sync();
     __shared__ double s[NORM_THREADS / 32];
     double a = 0.0;
     const long long n4 = n >> 2;
@@ -45,6 +46,7 @@ sumsq_partial_kernel(const float* __restrict__ g, long long n, double* __restric
 // the objective, see rl_kernels.cu), else 1.
 __global__ void sumsq_finalize_kernel(const double* __restrict__ partial, int n_partial, const double* __restrict__ count,
                                       float max_norm, float* __restrict__ scal) {
+    pdl_grid_sync();
     double t = 0.0;
     for (int i = threadIdx.x; i < n_partial; i += 32) t += partial[i];
     t = warp_sum_d(t);
@@ -63,6 +65,7 @@ __global__ void __launch_bounds__(256)
 adamw_apply_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                    long long n, long long n_decay, const float* __restrict__ scal, float lr, float beta1, float beta2,
                    float eps, float weight_decay, float bc1, float sqrt_bc2) {
+    pdl_grid_sync();
     const float gscale = scal ? scal[1] : 1.f;
     const float step_size = lr / bc1;
     const float decay_keep = 1.f - lr * weight_decay;
@@ -107,15 +110,15 @@ int launch_clip_adamw(float* p, const float* g, float* m, float* v, long long n,
                  "optimizer arenas must be 16-byte aligned");
     if (n <= 0) return 0;
     const int nb = (int)min((long long)optim_scratch_doubles(), (n / 4 + NORM_THREADS - 1) / NORM_THREADS + 1);
-    sumsq_partial_kernel<<<nb, NORM_THREADS, 0, st>>>(g, n, scratch);
+    launch_k(sumsq_partial_kernel, nb, NORM_THREADS, 0, st, g, n, scratch);
     RIFT_LAUNCH_OK();
-    sumsq_finalize_kernel<<<1, 32, 0, st>>>(scratch, nb, count, max_norm, scal);
+    launch_k(sumsq_finalize_kernel, 1, 32, 0, st, scratch, nb, count, max_norm, scal);
     RIFT_LAUNCH_OK();
     // torch computes the bias corrections in Python doubles
     const double bc1 = 1.0 - pow((double)beta1, (double)step);
     const double bc2 = 1.0 - pow((double)beta2, (double)step);
     const int grid = (int)min((long long)148 * 8, (n / 4 + 255) / 256 + 1);
-    adamw_apply_kernel<<<grid, 256, 0, st>>>(p, g, m, v, n, n_decay, scal, lr, beta1, beta2, eps, weight_decay, (float)bc1,
+    launch_k(adamw_apply_kernel, grid, 256, 0, st, p, g, m, v, n, n_decay, scal, lr, beta1, beta2, eps, weight_decay, (float)bc1,
                                              (float)sqrt(bc2));
     RIFT_LAUNCH_OK();
     return 0;

@@ -101,6 +101,7 @@ constexpr int ADV_GPB = ADV_THREADS / 8;   // 32 groups per block pass
 __global__ void __launch_bounds__(ADV_THREADS)
 group_advantage_fixed_kernel(const double* __restrict__ ret, double* __restrict__ adv,
                              long long n_groups, int G, int Gp) {
+    pdl_grid_sync();
     extern __shared__ double sm[];
     const int tid = threadIdx.x;
     const int lane8 = tid & 7;
@@ -157,6 +158,7 @@ group_advantage_fixed_kernel(const double* __restrict__ ret, double* __restrict_
 __global__ void __launch_bounds__(ADV_THREADS)
 group_advantage_ragged_kernel(const double* __restrict__ ret, const long long* __restrict__ offsets,
                               double* __restrict__ adv, long long n_groups, int G) {
+    pdl_grid_sync();
     const int tid = threadIdx.x;
     const int lane8 = tid & 7;
     const unsigned gmask = 0xFFu << ((tid & 31) & ~7);
@@ -189,14 +191,14 @@ int launch_group_advantage(const double* ret, const long long* offsets, long lon
             const long long n_chunks = (n_groups + ADV_GPB - 1) / ADV_GPB;
             const int per_sm = (int)max((size_t)1, min((size_t)8, (size_t)(220 * 1024) / (smem + 1024)));
             const int grid = (int)min(n_chunks, (long long)148 * per_sm);
-            group_advantage_fixed_kernel<<<grid, ADV_THREADS, smem, st>>>(ret, adv, n_groups, G, Gp);
+            launch_k(group_advantage_fixed_kernel, grid, ADV_THREADS, smem, st, ret, adv, n_groups, G, Gp);
             RIFT_LAUNCH_OK();
             return 0;
         }
         // very large groups: straight from global memory (second pass re-reads through L1/L2)
     }
     const int grid = (int)((n_groups + ADV_GPB - 1) / ADV_GPB);
-    group_advantage_ragged_kernel<<<grid, ADV_THREADS, 0, st>>>(ret, offsets, adv, n_groups, G);
+    launch_k(group_advantage_ragged_kernel, grid, ADV_THREADS, 0, st, ret, offsets, adv, n_groups, G);
     RIFT_LAUNCH_OK();
     return 0;
 }
@@ -221,6 +223,7 @@ group_objective_kernel(const float* __restrict__ logits, const float* __restrict
                        int bs, int R, int Mo, float clip_lo, float clip_hi, float dual_clip, float kl_w,
                        double* __restrict__ part_sum, int* __restrict__ part_cnt,
                        float* __restrict__ dlogits) {
+    pdl_grid_sync();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= bs) return;
@@ -335,6 +338,7 @@ __global__ void __launch_bounds__(256)
 objective_finalize_kernel(const double* __restrict__ part_sum, const int* __restrict__ part_cnt, int bs,
                           double* __restrict__ out, float* __restrict__ dlogits, long long n_dlogits,
                           int scale_dlogits) {
+    pdl_grid_sync();
     __shared__ double ssum[256];
     __shared__ long long scnt[256];
     double s = 0.0;
@@ -360,6 +364,7 @@ objective_finalize_kernel(const double* __restrict__ part_sum, const int* __rest
 }
 
 __global__ void scale_f32_by_count_kernel(float* __restrict__ x, long long n, const double* __restrict__ out3) {
+    pdl_grid_sync();
     const double cnt = out3[2];
     const float inv = cnt > 0 ? (float)(1.0 / cnt) : 0.f;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
@@ -376,19 +381,19 @@ int launch_group_objective(int algo, const float* logits, const float* old_logit
     if (bs <= 0) return 0;
     const int grid = cdiv((long long)bs * 32, 128);
     if (algo == 0)
-        group_objective_kernel<false><<<grid, 128, 0, st>>>(logits, old_logits, ref_logits, adv, valid, r_pad, bs, R, Mo,
+        launch_k(group_objective_kernel<false>, grid, 128, 0, st, logits, old_logits, ref_logits, adv, valid, r_pad, bs, R, Mo,
                                                             clip_lo, clip_hi, dual_clip, kl_w, part_sum, part_cnt, dlogits);
     else
-        group_objective_kernel<true><<<grid, 128, 0, st>>>(logits, old_logits, ref_logits, adv, valid, r_pad, bs, R, Mo,
+        launch_k(group_objective_kernel<true>, grid, 128, 0, st, logits, old_logits, ref_logits, adv, valid, r_pad, bs, R, Mo,
                                                            clip_lo, clip_hi, dual_clip, kl_w, part_sum, part_cnt, dlogits);
     RIFT_LAUNCH_OK();
     const long long n = (long long)bs * R * Mo;
     // small batches: the single finalize block also rescales; large ones use a wide kernel
     const bool wide = scale_dlogits && dlogits && n > 65536;
-    objective_finalize_kernel<<<1, 256, 0, st>>>(part_sum, part_cnt, bs, out3, dlogits, n, scale_dlogits && !wide);
+    launch_k(objective_finalize_kernel, 1, 256, 0, st, part_sum, part_cnt, bs, out3, dlogits, n, scale_dlogits && !wide);
     RIFT_LAUNCH_OK();
     if (wide) {
-        scale_f32_by_count_kernel<<<min(cdiv(n, 256), 148 * 8), 256, 0, st>>>(dlogits, n, out3);
+        launch_k(scale_f32_by_count_kernel, min(cdiv(n, 256), 148 * 8), 256, 0, st, dlogits, n, out3);
         RIFT_LAUNCH_OK();
     }
     return 0;
@@ -408,6 +413,7 @@ action_objective_kernel(int mode, const float* __restrict__ logits, const uint8_
                         const float* __restrict__ old_log_prob, int bs, int R, int Mo, float eps_clip,
                         float lambda_entropy, float inv_n, float* __restrict__ part, float* __restrict__ dlogits,
                         int* __restrict__ chosen) {
+    pdl_grid_sync();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= bs) return;
@@ -499,6 +505,7 @@ action_objective_kernel(int mode, const float* __restrict__ logits, const uint8_
 __global__ void __launch_bounds__(256)
 mean_finalize_kernel(const float* __restrict__ part, int bs, float inv_n, const float* __restrict__ extra,
                      float* __restrict__ out) {
+    pdl_grid_sync();
     __shared__ float s[256];
     float a = 0.f;
     for (int i = threadIdx.x; i < bs; i += 256) a += part[i];
@@ -518,11 +525,11 @@ int launch_action_objective(int mode, const float* logits, const uint8_t* r_pad,
     RIFT_REQUIRE(R * Mo <= 32 * LOSS_MAX_PER_LANE, "R*num_modes exceeds 512 candidates per sample");
     RIFT_REQUIRE(r_pad != nullptr, "r_pad is required");
     if (bs <= 0) return 0;
-    action_objective_kernel<<<cdiv((long long)bs * 32, 128), 128, 0, st>>>(
+    launch_k(action_objective_kernel, cdiv((long long)bs * 32, 128), 128, 0, st, 
         mode, logits, r_pad, action_mode, weight, old_log_prob, bs, R, Mo, eps_clip, lambda_entropy, inv_n, part,
         dlogits, chosen);
     RIFT_LAUNCH_OK();
-    mean_finalize_kernel<<<1, 256, 0, st>>>(part, bs, inv_n, extra_loss, loss_out);
+    launch_k(mean_finalize_kernel, 1, 256, 0, st, part, bs, inv_n, extra_loss, loss_out);
     RIFT_LAUNCH_OK();
     return 0;
 }
@@ -531,6 +538,7 @@ int launch_action_objective(int mode, const float* logits, const uint8_t* r_pad,
 __global__ void __launch_bounds__(256)
 smooth_l1_kernel(const float* __restrict__ value, const float* __restrict__ target, int n, float inv_n,
                  float* __restrict__ loss_out, float* __restrict__ dvalue) {
+    pdl_grid_sync();
     __shared__ float s[256];
     float a = 0.f;
     for (int i = threadIdx.x; i < n; i += 256) {
@@ -550,7 +558,7 @@ smooth_l1_kernel(const float* __restrict__ value, const float* __restrict__ targ
 
 int launch_smooth_l1(const float* value, const float* target, int n, float inv_n, float* loss_out, float* dvalue,
                      cudaStream_t st) {
-    smooth_l1_kernel<<<1, 256, 0, st>>>(value, target, n, inv_n, loss_out, dvalue);
+    launch_k(smooth_l1_kernel, 1, 256, 0, st, value, target, n, inv_n, loss_out, dvalue);
     RIFT_LAUNCH_OK();
     return 0;
 }
@@ -565,6 +573,7 @@ __global__ void gae_scan_kernel(const float* __restrict__ rewards, const float* 
                                 const float* __restrict__ values, const float* __restrict__ next_values,
                                 const float* __restrict__ unterminated, int n, float gamma, float lam,
                                 float* __restrict__ adv, float* __restrict__ reward_sum) {
+    pdl_grid_sync();
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     float a = 0.f;
     for (int t = n - 1; t >= 0; --t) {
@@ -580,6 +589,7 @@ __global__ void gae_scan_kernel(const float* __restrict__ rewards, const float* 
 // (x - mean) / (std_unbiased + 1e-5), fp32 like torch (ppo_datamodule.py:163); one block.
 __global__ void __launch_bounds__(1024)
 normalise_unbiased_kernel(const float* __restrict__ x, int n, float* __restrict__ y) {
+    pdl_grid_sync();
     __shared__ double s[1024];
     double a = 0.0;
     for (int i = threadIdx.x; i < n; i += 1024) a += x[i];
@@ -599,6 +609,7 @@ normalise_unbiased_kernel(const float* __restrict__ x, int n, float* __restrict_
 
 __global__ void discounted_return_kernel(const float* __restrict__ rewards, const float* __restrict__ dones, int n,
                                          float gamma, float* __restrict__ out) {
+    pdl_grid_sync();
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     float g = 0.f;
     for (int t = n - 1; t >= 0; --t) {
@@ -610,17 +621,17 @@ __global__ void discounted_return_kernel(const float* __restrict__ rewards, cons
 int launch_gae(const float* rewards, const float* undones, const float* values, const float* next_values,
                const float* unterminated, int n, float gamma, float lam, float* adv, float* reward_sum,
                float* adv_normalised, cudaStream_t st) {
-    gae_scan_kernel<<<1, 32, 0, st>>>(rewards, undones, values, next_values, unterminated, n, gamma, lam, adv, reward_sum);
+    launch_k(gae_scan_kernel, 1, 32, 0, st, rewards, undones, values, next_values, unterminated, n, gamma, lam, adv, reward_sum);
     RIFT_LAUNCH_OK();
     if (adv_normalised) {
-        normalise_unbiased_kernel<<<1, 1024, 0, st>>>(adv, n, adv_normalised);
+        launch_k(normalise_unbiased_kernel, 1, 1024, 0, st, adv, n, adv_normalised);
         RIFT_LAUNCH_OK();
     }
     return 0;
 }
 
 int launch_discounted_return(const float* rewards, const float* dones, int n, float gamma, float* out, cudaStream_t st) {
-    discounted_return_kernel<<<1, 32, 0, st>>>(rewards, dones, n, gamma, out);
+    launch_k(discounted_return_kernel, 1, 32, 0, st, rewards, dones, n, gamma, out);
     RIFT_LAUNCH_OK();
     return 0;
 }
