@@ -422,10 +422,88 @@ nat_attention_bwd_kernel(const float* __restrict__ qkv, const float* __restrict_
     }
 }
 
+// Register-resident form (see nat_attention_reg_kernel): q, k, v, dO of the whole (sequence, head) slice and the
+// dk / dv accumulators live in registers, every index is a compile-time constant after unrolling.
+template <int L, int KS>
+__global__ void __launch_bounds__(128)
+nat_attention_bwd_reg_kernel(const float* __restrict__ qkv, const float* __restrict__ d_out, int n_seq, int heads, int hd,
+                             const float* __restrict__ rpb, float* __restrict__ dqkv, float* __restrict__ drpb_partial) {
+    pdl_grid_sync();
+    const int lane = threadIdx.x & 31;
+    const int warp = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (warp >= n_seq * heads) return;
+    const int n = warp / heads, h = warp % heads;
+    const int dim = heads * hd;
+    const float scale = rsqrtf((float)hd);
+    const float* base = qkv + (long long)n * L * 3 * dim + h * hd;
+    float* dbase = dqkv + (long long)n * L * 3 * dim + h * hd;
+    const bool on = lane < hd;
+    float q[L], k[L], v[L], go[L], dk[L], dv[L], rb[2 * KS - 1], drpb[2 * KS - 1];
+#pragma unroll
+    for (int i = 0; i < L; ++i) {
+        q[i] = on ? base[(long long)i * 3 * dim + lane] * scale : 0.f;
+        k[i] = on ? base[(long long)i * 3 * dim + dim + lane] : 0.f;
+        v[i] = on ? base[(long long)i * 3 * dim + 2 * dim + lane] : 0.f;
+        go[i] = on ? d_out[((long long)n * L + i) * dim + h * hd + lane] : 0.f;
+        dk[i] = 0.f; dv[i] = 0.f;
+    }
+#pragma unroll
+    for (int t = 0; t < 2 * KS - 1; ++t) { rb[t] = rpb[h * (2 * KS - 1) + t]; drpb[t] = 0.f; }
+#pragma unroll
+    for (int i = 0; i < L; ++i) {
+        constexpr int half = KS / 2;
+        const int start = (i - half < 0) ? 0 : ((i - half > L - KS) ? L - KS : i - half);
+        float p[KS], dp[KS];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int kk = 0; kk < KS; ++kk) {
+            p[kk] = warp_sum(q[i] * k[start + kk]) + rb[start + kk - i + KS - 1];
+            dp[kk] = warp_sum(go[i] * v[start + kk]);
+            mx = fmaxf(mx, p[kk]);
+        }
+        float den = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < KS; ++kk) { p[kk] = __expf(p[kk] - mx); den += p[kk]; }
+        float dl = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < KS; ++kk) { p[kk] /= den; dl += p[kk] * dp[kk]; }
+        float dqv = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < KS; ++kk) {
+            const float ds = p[kk] * (dp[kk] - dl);
+            dqv += ds * k[start + kk];
+            dk[start + kk] += ds * q[i];                  // q already carries the scale
+            dv[start + kk] += p[kk] * go[i];
+            drpb[start + kk - i + KS - 1] += ds;
+        }
+        if (on) dbase[(long long)i * 3 * dim + lane] = dqv * scale;
+    }
+    if (on) {
+#pragma unroll
+        for (int j = 0; j < L; ++j) {
+            dbase[(long long)j * 3 * dim + dim + lane] = dk[j];
+            dbase[(long long)j * 3 * dim + 2 * dim + lane] = dv[j];
+        }
+    }
+    if (drpb_partial && lane == 0) {
+#pragma unroll
+        for (int t = 0; t < 2 * KS - 1; ++t) drpb_partial[(long long)warp * (2 * KS - 1) + t] = drpb[t];
+    }
+}
+
 int launch_nat_attention_bwd(const float* qkv, const float* d_out, int n_seq, int L, int heads, int hd, int ksize,
                              const float* rpb, float* dqkv, float* drpb_partial, cudaStream_t st) {
     if (n_seq <= 0) return 0;
     RIFT_REQUIRE(hd <= 32 && ksize <= NATB_MAXK && L >= ksize && L <= NATB_MAXL, "nat_attention_bwd: unsupported shape");
+#define RIFT_NATB_REG(LL, KK)                                                                                               \
+    if (L == LL && ksize == KK) {                                                                                           \
+        launch_k(nat_attention_bwd_reg_kernel<LL, KK>, cdiv((long long)n_seq * heads, 4), 128, 0, st, qkv, d_out, n_seq,    \
+                 heads, hd, rpb, dqkv, drpb_partial);                                                                       \
+        RIFT_LAUNCH_OK();                                                                                                   \
+        return 0;                                                                                                           \
+    }
+    RIFT_NATB_REG(20, 3) RIFT_NATB_REG(10, 3) RIFT_NATB_REG(5, 5)
+#undef RIFT_NATB_REG
     launch_k(nat_attention_bwd_kernel, cdiv((long long)n_seq * heads, 4), 128, 0, st, qkv, d_out, n_seq, L, heads, hd, ksize, rpb, dqkv,
                                                                              drpb_partial);
     RIFT_LAUNCH_OK();

@@ -52,42 +52,56 @@ layernorm_kernel(const float* __restrict__ x, long long ldx, int rows, int C, co
 
 // 16-byte vectorised variant (C % 4 == 0, 16-byte aligned rows): every lane owns float4 column groups, so the
 // fp32 and the split-bf16 plane stores are 16 / 8 byte vector stores.  The row is cached in registers (C <= 1024).
+// LPR = lanes per row (32, or 16 / 8 for narrow rows so that a warp works on 2 / 4 rows at once).
+template <int LPR>
 __global__ void __launch_bounds__(256)
 layernorm4_kernel(const float* __restrict__ x, long long ldx, int rows, int C, const float* __restrict__ gamma,
                   const float* __restrict__ beta, float* __restrict__ y, long long ldy, int relu,
                   const float* __restrict__ add_rowmod, int rowmod, float* __restrict__ y2, float* __restrict__ mean_out,
                   float* __restrict__ rstd_out, Planes yp, Planes y2p) {
     pdl_grid_sync();
+    constexpr int RPW = 32 / LPR;                     // rows per warp
+    constexpr int NV = LPR == 32 ? 8 : 1;             // float4 groups per lane (narrow rows: C <= 4 * LPR)
     const int lane = threadIdx.x & 31;
+    const int sl = lane % LPR, sub = lane / LPR;
     const int wpb = blockDim.x >> 5;
     const int C4 = C >> 2;
-    for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += gridDim.x * wpb) {
-        const float4* xr = reinterpret_cast<const float4*>(x + (long long)row * ldx);
-        float4 v[8];
+    const float invC = 1.f / C;
+    for (int row0 = (blockIdx.x * wpb + (threadIdx.x >> 5)) * RPW; row0 < rows; row0 += gridDim.x * wpb * RPW) {
+        const int row = row0 + sub;
+        const bool rok = row < rows;
+        const float4* xr = reinterpret_cast<const float4*>(x + (long long)(rok ? row : 0) * ldx);
+        float4 v[NV];
         float s = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int c4 = lane + 32 * i;
+        for (int i = 0; i < NV; ++i) {
+            const int c4 = sl + LPR * i;
             if (c4 < C4) { v[i] = xr[c4]; s += (v[i].x + v[i].y) + (v[i].z + v[i].w); }
         }
-        const float mean = warp_sum(s) / C;
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float mean = s / C;
         float q = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int c4 = lane + 32 * i;
+        for (int i = 0; i < NV; ++i) {
+            const int c4 = sl + LPR * i;
             if (c4 < C4) {
                 const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
                 q += (a * a + b * b) + (c * c + d * d);
             }
         }
-        const float rstd = rsqrtf(warp_sum(q) / C + 1e-5f);
-        if (lane == 0) {
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+        const float rstd = rsqrtf(q / C + 1e-5f);
+        (void)invC;
+        if (!rok) continue;
+        if (sl == 0) {
             if (mean_out) mean_out[row] = mean;
             if (rstd_out) rstd_out[row] = rstd;
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int c4 = lane + 32 * i;
+        for (int i = 0; i < NV; ++i) {
+            const int c4 = sl + LPR * i;
             if (c4 < C4) {
                 const float4 g = reinterpret_cast<const float4*>(gamma)[c4], b = reinterpret_cast<const float4*>(beta)[c4];
                 float4 o;
@@ -104,8 +118,8 @@ layernorm4_kernel(const float* __restrict__ x, long long ldx, int rows, int C, c
                 }
             }
         }
-        if (yp.on()) split_zero_pad(yp, row, C, lane, 32);
-        if (y2p.on()) split_zero_pad(y2p, row, C, lane, 32);
+        if (yp.on()) split_zero_pad(yp, row, C, sl, LPR);
+        if (y2p.on()) split_zero_pad(y2p, row, C, sl, LPR);
     }
 }
 
@@ -118,8 +132,17 @@ int launch_layernorm(const float* x, long long ldx, int rows, int C, const float
     auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
     if ((C & 3) == 0 && C <= 1024 && (ldx & 3) == 0 && (ldy & 3) == 0 && al16(x) && al16(y) && al16(y2) && al16(gamma) &&
         al16(beta) && al16(add_rowmod)) {
-        launch_k(layernorm4_kernel, min(cdiv(rows, 8), 148 * 8), 256, 0, st, x, ldx, rows, C, gamma, beta, y, ldy, relu, add_rowmod,
-                                                                       rowmod, y2, mean, rstd, yp, y2p);
+        // narrow rows: 16 / 8 lanes per row, several rows per warp; one pass per warp (no grid-stride cap) keeps
+        // enough loads in flight to cover the HBM latency
+        if (C <= 32)
+            launch_k(layernorm4_kernel<8>, min(cdiv(rows, 32), 148 * 64), 256, 0, st, x, ldx, rows, C, gamma, beta, y, ldy, relu,
+                     add_rowmod, rowmod, y2, mean, rstd, yp, y2p);
+        else if (C <= 64)
+            launch_k(layernorm4_kernel<16>, min(cdiv(rows, 16), 148 * 64), 256, 0, st, x, ldx, rows, C, gamma, beta, y, ldy, relu,
+                     add_rowmod, rowmod, y2, mean, rstd, yp, y2p);
+        else
+            launch_k(layernorm4_kernel<32>, min(cdiv(rows, 8), 148 * 64), 256, 0, st, x, ldx, rows, C, gamma, beta, y, ldy, relu,
+                     add_rowmod, rowmod, y2, mean, rstd, yp, y2p);
         RIFT_LAUNCH_OK();
         return 0;
     }
@@ -594,10 +617,69 @@ nat_attention_kernel(const float* __restrict__ qkv, int n_seq, int L, int heads,
     }
 }
 
+// Register-resident form for the shapes the history encoder uses (L, ksize compile-time): the whole (sequence,
+// head) slice - q, k, v of every position for this lane's channel - is loaded up front (3 L independent 128-byte
+// warp loads in flight instead of a dependent load chain per position) and the loops are fully unrolled.
+template <int L, int KS>
+__global__ void __launch_bounds__(128)
+nat_attention_reg_kernel(const float* __restrict__ qkv, int n_seq, int heads, int hd, const float* __restrict__ rpb,
+                         float* __restrict__ out, Planes op) {
+    pdl_grid_sync();
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n_seq * heads) return;
+    const int n = warp / heads, h = warp % heads;
+    const int dim = heads * hd;
+    const float scale = rsqrtf((float)hd);
+    const float* base = qkv + (long long)n * L * 3 * dim + h * hd;
+    const bool on = lane < hd;
+    float q[L], k[L], v[L], rb[2 * KS - 1];
+#pragma unroll
+    for (int i = 0; i < L; ++i) {
+        q[i] = on ? base[(long long)i * 3 * dim + lane] : 0.f;
+        k[i] = on ? base[(long long)i * 3 * dim + dim + lane] : 0.f;
+        v[i] = on ? base[(long long)i * 3 * dim + 2 * dim + lane] : 0.f;
+    }
+#pragma unroll
+    for (int t = 0; t < 2 * KS - 1; ++t) rb[t] = rpb[h * (2 * KS - 1) + t];
+#pragma unroll
+    for (int i = 0; i < L; ++i) {
+        constexpr int half = KS / 2;
+        const int start = (i - half < 0) ? 0 : ((i - half > L - KS) ? L - KS : i - half);
+        const float qi = q[i] * scale;
+        float logit[KS];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int kk = 0; kk < KS; ++kk) {
+            logit[kk] = warp_sum(qi * k[start + kk]) + rb[start + kk - i + KS - 1];
+            mx = fmaxf(mx, logit[kk]);
+        }
+        float den = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < KS; ++kk) { logit[kk] = __expf(logit[kk] - mx); den += logit[kk]; }
+        float o = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < KS; ++kk) o += logit[kk] * v[start + kk];
+        if (on) {
+            if (out) out[((long long)n * L + i) * dim + h * hd + lane] = o / den;
+            if (op.on()) split_store(op, (long long)n * L + i, h * hd + lane, o / den);
+        }
+        if (op.on() && h == 0) split_zero_pad(op, (long long)n * L + i, dim, lane, 32);
+    }
+}
+
 int launch_nat_attention(const float* qkv, int n_seq, int L, int heads, int hd, int ksize, const float* rpb, float* out,
                          cudaStream_t st, Planes op) {
     if (n_seq <= 0) return 0;
     RIFT_REQUIRE(hd <= 32 && ksize <= NAT_MAXK && L >= ksize && L <= NAT_MAXL, "nat_attention: unsupported shape");
+    const int nblk = cdiv((long long)n_seq * heads * 32, 128);
+#define RIFT_NAT_REG(LL, KK)                                                                                            \
+    if (L == LL && ksize == KK) {                                                                                       \
+        launch_k(nat_attention_reg_kernel<LL, KK>, nblk, 128, 0, st, qkv, n_seq, heads, hd, rpb, out, op);              \
+        RIFT_LAUNCH_OK();                                                                                               \
+        return 0;                                                                                                       \
+    }
+    RIFT_NAT_REG(20, 3) RIFT_NAT_REG(10, 3) RIFT_NAT_REG(5, 5)
+#undef RIFT_NAT_REG
     launch_k(nat_attention_kernel, cdiv((long long)n_seq * heads * 32, 128), 128, 0, st, qkv, n_seq, L, heads, hd, ksize, rpb, out, op);
     RIFT_LAUNCH_OK();
     return 0;
