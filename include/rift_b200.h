@@ -176,6 +176,7 @@ int rift_b200_op_gemm(const float* A, long long sam, long long sak, const float*
                       int simt, void* stream);
 int rift_b200_op_layernorm(const float* x, int rows, int C, const float* gamma, const float* beta, int relu, float* y,
                            float* mean, float* rstd, void* stream);
+/* scratch: 592 * 2 * C floats (needed when dgamma / dbeta are requested) */
 int rift_b200_op_layernorm_bwd(const float* x, const float* dy, int rows, int C, const float* gamma, const float* mean,
                                const float* rstd, const float* y_relu, float* dx, float* dgamma, float* dbeta,
                                float* scratch, void* stream);

@@ -625,8 +625,22 @@ int rift_b200_engine::forward(const rift_b200_batch& bt, const rift_b200_outputs
     }
 
     // ---------------- PlanningDecoder (modules/planning_decoder.py:135-188)
-    TRY(join_from(c, c.br));                 // query initialisation (branch stream) is complete
+    // cross-attention K / V projections of the scene encoding do not depend on the query chain: all layers' on the
+    // branch stream, behind the query initialisation
+    std::vector<float*> kvc_all(m.dec.size(), nullptr);
+    TRY(fork_to(c, c.br));
+    {
+        OnStream on_br(c, c.br);
+        for (size_t l = 0; l < m.dec.size(); ++l) {
+            const Lin cr_kv = slice(m.dec[l].cross.in, D, 2 * D, 0, D, true);
+            kvc_all[l] = c.alloc<float>((size_t)rowsE * 2 * D);
+            if (!kvc_all[l]) { set_last_error("workspace too small"); return -1; }
+            TRY(linear_into(c, Xn, cr_kv, Epi(), kvc_all[l], 2 * D));
+        }
+    }
+    TRY(join_from(c, c.br));                 // query initialisation + K / V projections (branch stream) are complete
     T_.dec.clear();
+    size_t dec_l = 0;
     for (const DecBlockP& db : m.dec) {
         DecBlockTape dt;
         dt.q = q;
@@ -680,12 +694,12 @@ int rift_b200_engine::forward(const rift_b200_batch& bt, const rift_b200_outputs
         if (!c.dry) TRY(launch_zero_rows(q2, r_pad, Mo, rowsQ, D, c.st));
         // (iii) cross-attention to the scene encoding
         ALLOC(qc, float, (size_t)rowsQ * D);
-        ALLOC(kvc, float, (size_t)rowsE * 2 * D);
+        float* kvc = kvc_all[dec_l++];
         ALLOC(q3, float, (size_t)rowsQ * D);
         Act t3, a3;
         TRY(layernorm_new(c, q2, rowsQ, db.n3, 0, want_in(c, rowsQ, {&cr_q}), &t3, full ? &dt.ln3 : nullptr));
         TRY(linear_into(c, t3, cr_q, Epi(), qc, D));
-        TRY(linear_into(c, Xn, cr_kv, Epi(), kvc, 2 * D));
+        (void)cr_kv;
         TRY(new_act(c, rowsQ, D, want_in(c, rowsQ, {&db.cross.out}), &a3));
         if (!c.dry) {
             AttnArgs a;

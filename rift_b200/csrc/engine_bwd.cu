@@ -193,7 +193,13 @@ int rift_b200_engine::backward_impl(const rift_b200_batch& bt, const float* dlog
                 TRY(launch_attention_bwd(a, d_a3, D, d_qc, D, d_kvc, d_kvc + D, 2 * D, 2 * D, c.st));
             }
             TRY(lin_bwd(c, dt.t3.f, D, d_qc, D, rowsQ, cr_q, d_t3, D, 0.f, true, &dt.t3.p));
-            TRY(lin_bwd(c, tp.Xn.f, D, d_kvc, 2 * D, rowsE, cr_kv, dXn, D, 1.f));
+            // the K / V projection's gradients feed dXn, which the query chain never reads: branch stream
+            // (in order there, so the accumulation into dXn stays sequential)
+            TRY(fork_to(c, c.br));
+            {
+                OnStream on_br(c, c.br);
+                TRY(lin_bwd(c, tp.Xn.f, D, d_kvc, 2 * D, rowsE, cr_kv, dXn, D, 1.f, true, &tp.Xn.p));
+            }
             TRY(ln_bwd(c, dt.ln3, db.n3, d_t3, nullptr, dq, 1));
         }
         // (ii) m2m: rows of padded reference lines were overwritten with 0 -> no gradient through them
@@ -231,6 +237,11 @@ int rift_b200_engine::backward_impl(const rift_b200_batch& bt, const float* dlog
         }
     }
 
+    // dXn is complete once the branch stream has run the last K / V projection backward (recorded before the
+    // parameter-only branches are queued behind it)
+    cudaEvent_t dxn_done = nullptr;
+    if (!c.dry && c.br) { dxn_done = c.next_event(); RIFT_CUDA_OK(cudaEventRecord(dxn_done, c.br)); }
+
     // ---------------- query init: q0[row] = u[row / Mo] + v[row % Mo]
     {
         const Lin qa = slice(m.q_proj, 0, D, 0, D, false), qb = slice(m.q_proj, 0, D, D, D, true);
@@ -254,6 +265,7 @@ int rift_b200_engine::backward_impl(const rift_b200_batch& bt, const float* dlog
 
     // ---------------- scene encoding: final norm <- encoder blocks
     ALLOC(dX, float, (size_t)rowsE * D);
+    if (dxn_done) RIFT_CUDA_OK(cudaStreamWaitEvent(c.st, dxn_done, 0));
     TRY(ln_bwd(c, tp.ln_final, m.final_norm, dXn, nullptr, dX, 0));
     for (int l = (int)m.enc.size() - 1; l >= 0; --l) {
         const EncBlockP& eb = m.enc[l];

@@ -127,18 +127,17 @@ attention_bwd_kernel(AttnArgs a, const float* __restrict__ d_o, long long lddo, 
 }
 
 // ---- head_dim 32, cooperative form ------------------------------------------------------------------
-// Several (batch, head) problems per CTA (PB) and G lanes per row: in phase A the G lanes of query i split the
-// keys (j = g, g+G, ...), in phase B the G lanes of key j split the queries; partial results are combined with
-// xor-butterflies inside the lane group.  P = exp(S - lse) and dS = P (dP - delta) are computed ONCE and kept
-// in shared memory, so phase B is two AXPYs per (i, j).  Rows are padded to 36 floats: 16-byte broadcast reads
-// of up to eight different rows by one quarter-warp stay conflict free.
+// Several (batch, head) problems per CTA (PB) and G lanes per row, each lane owning 32 / G CHANNELS.
+//   phase A (lane group = query i): per key a partial dot product + log2(G) shuffles give s_ij and dP_ij;
+//       P = exp(S - lse) and dP are written to shared memory once, delta_i = sum_j P dP, and in a second sweep
+//       dQ_i[channels of the lane] += dS_ij K_j with dS = P (dP - delta).
+//   phase B (lane group = key j): dV_j += P_ij dO_i, dK_j += dS_ij Q_i on the lane's channels - no reduction at all.
+// Rows are padded to 36 floats (16-byte aligned); few registers per thread, several CTAs per SM.
 constexpr int AB_PITCH = 36;
-
-struct AttnBwdShape { int PB, G, tpp; size_t smem_per_problem; };
 
 __host__ __device__ inline size_t attn_bwd2_smem_floats(int Sq, int Sk) {
     const int Skp = Sk | 1;
-    const size_t n = (size_t)2 * Sq * AB_PITCH + (size_t)2 * Sk * AB_PITCH + (size_t)2 * Sq * Skp + (size_t)Sq + ((Sk + 3) / 4);
+    const size_t n = (size_t)2 * Sq * AB_PITCH + (size_t)2 * Sk * AB_PITCH + (size_t)2 * Sq * Skp + (size_t)2 * Sq + ((Sk + 3) / 4);
     return (n + 3) & ~(size_t)3;                         // problems stay 16-byte aligned
 }
 
@@ -147,22 +146,23 @@ __global__ void __launch_bounds__(512)
 attention_bwd2_kernel(AttnArgs a, const float* __restrict__ d_o, long long lddo, float* __restrict__ dq, long long lddq,
                       float* __restrict__ dk, float* __restrict__ dv, long long lddk, long long lddv, int PB, int tpp) {
     pdl_grid_sync();
-    constexpr int HD = 32;
+    constexpr int HD = 32, CPL = HD / G;
     extern __shared__ __align__(16) float sm[];
     const int Sq = a.Sq, Sk = a.Sk, Skp = Sk | 1;
     const int pl = threadIdx.x / tpp;                    // problem slot inside the CTA
     const int t = threadIdx.x - pl * tpp;                // thread inside the problem
     const long long prob = (long long)blockIdx.x * PB + pl;
-    const bool live = pl < PB && prob < (long long)a.B * a.H;
+    const bool live = prob < (long long)a.B * a.H;
     float* base = sm + (size_t)pl * attn_bwd2_smem_floats(Sq, Sk);
     float* Qs = base;                                    // [Sq][36]  (pre-scaled)
     float* dOs = Qs + (size_t)Sq * AB_PITCH;             // [Sq][36]
     float* Ks = dOs + (size_t)Sq * AB_PITCH;             // [Sk][36]
     float* Vs = Ks + (size_t)Sk * AB_PITCH;              // [Sk][36]
     float* Ps = Vs + (size_t)Sk * AB_PITCH;              // [Sq][Skp]
-    float* dSs = Ps + (size_t)Sq * Skp;                  // [Sq][Skp]  (dP first, then dS)
-    float* lse_s = dSs + (size_t)Sq * Skp;               // [Sq]
-    uint8_t* msk = reinterpret_cast<uint8_t*>(lse_s + Sq);   // [Sk]
+    float* dPs = Ps + (size_t)Sq * Skp;                  // [Sq][Skp]
+    float* lse_s = dPs + (size_t)Sq * Skp;               // [Sq]
+    float* delta = lse_s + Sq;                           // [Sq]
+    uint8_t* msk = reinterpret_cast<uint8_t*>(delta + Sq);   // [Sk]
     const int b = live ? (int)(prob / a.H) : 0, h = live ? (int)(prob % a.H) : 0;
     const long long krow0 = attn_row_b(b, a.k_inner_n, a.k_outer, a.k_inner);
     const long long qrow0 = attn_row_b(b, a.q_inner_n, a.q_outer, a.q_inner);
@@ -189,106 +189,86 @@ attention_bwd2_kernel(AttnArgs a, const float* __restrict__ d_o, long long lddo,
         for (int j = t; j < Sk; j += tpp) msk[j] = kpm ? kpm[j] : 0;
     }
     __syncthreads();
-    const int row = t / G, g = t % G;
-    // ---- phase A: lane group = query i.  Every thread runs the shuffles (inactive groups loop zero times).
-    {
-        const bool act = live && row < Sq;
-        const int i = act ? row : 0;
-        const int Skl = act ? Sk : 0;
-        const float lse = act ? lse_s[i] : 0.f;
+    const int row = t / G, g = t % G, c0 = g * CPL;
+    const unsigned gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << ((threadIdx.x & 31) & ~(G - 1));
+    // ---- phase A: lane group = query i (whole groups skip together; the shuffles name the group only)
+    if (live && row < Sq) {
+        const int i = row;
+        const float lse = lse_s[i];
         const bool dead = (lse == INFINITY);
-        float q[HD], go[HD];
+        float q[CPL], go[CPL], acc[CPL];
 #pragma unroll
-        for (int d = 0; d < HD; d += 4) {
-            const float4 x = *reinterpret_cast<const float4*>(Qs + i * AB_PITCH + d);
-            const float4 y = *reinterpret_cast<const float4*>(dOs + i * AB_PITCH + d);
+        for (int d = 0; d < CPL; d += 4) {
+            const float4 x = *reinterpret_cast<const float4*>(Qs + i * AB_PITCH + c0 + d);
+            const float4 y = *reinterpret_cast<const float4*>(dOs + i * AB_PITCH + c0 + d);
             q[d] = x.x; q[d + 1] = x.y; q[d + 2] = x.z; q[d + 3] = x.w;
             go[d] = y.x; go[d + 1] = y.y; go[d + 2] = y.z; go[d + 3] = y.w;
+            acc[d] = acc[d + 1] = acc[d + 2] = acc[d + 3] = 0.f;
         }
         float dl = 0.f;
-        for (int j = g; j < Skl; j += G) {
-            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+        for (int j = 0; j < Sk; ++j) {
+            float sc = 0.f, dp = 0.f;
 #pragma unroll
-            for (int d = 0; d < HD; d += 4) {
-                const float4 kk = *reinterpret_cast<const float4*>(Ks + j * AB_PITCH + d);
-                const float4 vv = *reinterpret_cast<const float4*>(Vs + j * AB_PITCH + d);
-                s0 = fmaf(q[d], kk.x, s0); s1 = fmaf(q[d + 1], kk.y, s1); s2 = fmaf(q[d + 2], kk.z, s2); s3 = fmaf(q[d + 3], kk.w, s3);
-                p0 = fmaf(go[d], vv.x, p0); p1 = fmaf(go[d + 1], vv.y, p1); p2 = fmaf(go[d + 2], vv.z, p2); p3 = fmaf(go[d + 3], vv.w, p3);
+            for (int d = 0; d < CPL; d += 4) {
+                const float4 kk = *reinterpret_cast<const float4*>(Ks + j * AB_PITCH + c0 + d);
+                const float4 vv = *reinterpret_cast<const float4*>(Vs + j * AB_PITCH + c0 + d);
+                sc = fmaf(q[d], kk.x, sc); sc = fmaf(q[d + 1], kk.y, sc); sc = fmaf(q[d + 2], kk.z, sc); sc = fmaf(q[d + 3], kk.w, sc);
+                dp = fmaf(go[d], vv.x, dp); dp = fmaf(go[d + 1], vv.y, dp); dp = fmaf(go[d + 2], vv.z, dp); dp = fmaf(go[d + 3], vv.w, dp);
             }
-            const float sc = (s0 + s1) + (s2 + s3), dp = (p0 + p1) + (p2 + p3);
+#pragma unroll
+            for (int o = 1; o < G; o <<= 1) {
+                sc += __shfl_xor_sync(gmask, sc, o);
+                dp += __shfl_xor_sync(gmask, dp, o);
+            }
             const float p = (dead || msk[j]) ? 0.f : __expf(sc - lse);
-            Ps[i * Skp + j] = p;
-            dSs[i * Skp + j] = dp;
+            if ((j & (G - 1)) == g) { Ps[i * Skp + j] = p; dPs[i * Skp + j] = dp; }
             dl = fmaf(p, dp, dl);
         }
+        if (g == 0) delta[i] = dl;
+        __syncwarp(gmask);                               // P / dP written by the other lanes of the group
+        for (int j = 0; j < Sk; ++j) {
+            const float ds = Ps[i * Skp + j] * (dPs[i * Skp + j] - dl);
 #pragma unroll
-        for (int o = 1; o < G; o <<= 1) dl += __shfl_xor_sync(0xffffffffu, dl, o, G);
-        float acc[HD];
-#pragma unroll
-        for (int d = 0; d < HD; ++d) acc[d] = 0.f;
-        for (int j = g; j < Skl; j += G) {
-            const float ds = Ps[i * Skp + j] * (dSs[i * Skp + j] - dl);
-            dSs[i * Skp + j] = ds;
-#pragma unroll
-            for (int d = 0; d < HD; d += 4) {
-                const float4 kk = *reinterpret_cast<const float4*>(Ks + j * AB_PITCH + d);
+            for (int d = 0; d < CPL; d += 4) {
+                const float4 kk = *reinterpret_cast<const float4*>(Ks + j * AB_PITCH + c0 + d);
                 acc[d] = fmaf(ds, kk.x, acc[d]); acc[d + 1] = fmaf(ds, kk.y, acc[d + 1]);
                 acc[d + 2] = fmaf(ds, kk.z, acc[d + 2]); acc[d + 3] = fmaf(ds, kk.w, acc[d + 3]);
             }
         }
-#pragma unroll
-        for (int o = 1; o < G; o <<= 1) {
-#pragma unroll
-            for (int d = 0; d < HD; ++d) acc[d] += __shfl_xor_sync(0xffffffffu, acc[d], o, G);
-        }
-        // every lane of the group holds the full row: lane g writes columns [g * HD / G, (g + 1) * HD / G)
         const long long dr = a.o_custom ? (orow0 + (long long)i * oseq) : (qrow0 + (long long)i * a.q_seq);
-        float* dst = dq + dr * lddq + h * HD;
+        float* dst = dq + dr * lddq + h * HD + c0;
 #pragma unroll
-        for (int d = 0; d < HD; d += 4) {
-            if (act && d / (HD / G) == g)
-                *reinterpret_cast<float4*>(dst + d) =
-                    make_float4(acc[d] * a.scale, acc[d + 1] * a.scale, acc[d + 2] * a.scale, acc[d + 3] * a.scale);
-        }
+        for (int d = 0; d < CPL; d += 4)
+            *reinterpret_cast<float4*>(dst + d) =
+                make_float4(acc[d] * a.scale, acc[d + 1] * a.scale, acc[d + 2] * a.scale, acc[d + 3] * a.scale);
     }
     __syncthreads();
-    // ---- phase B: lane group = key j
-    {
-        const bool act = live && row < Sk;
-        const int j = act ? row : 0;
-        const int Sql = act ? Sq : 0;
-        float ak[HD], av[HD];
+    // ---- phase B: lane group = key j, lane = channel slice; no reductions
+    if (live && row < Sk) {
+        const int j = row;
+        float ak[CPL], av[CPL];
 #pragma unroll
-        for (int d = 0; d < HD; ++d) { ak[d] = 0.f; av[d] = 0.f; }
-        for (int i = g; i < Sql; i += G) {
-            const float p = Ps[i * Skp + j], ds = dSs[i * Skp + j];
+        for (int d = 0; d < CPL; ++d) { ak[d] = 0.f; av[d] = 0.f; }
+        for (int i = 0; i < Sq; ++i) {
+            const float p = Ps[i * Skp + j];
+            const float ds = p * (dPs[i * Skp + j] - delta[i]);
 #pragma unroll
-            for (int d = 0; d < HD; d += 4) {
-                const float4 oo = *reinterpret_cast<const float4*>(dOs + i * AB_PITCH + d);
-                const float4 qq = *reinterpret_cast<const float4*>(Qs + i * AB_PITCH + d);
+            for (int d = 0; d < CPL; d += 4) {
+                const float4 oo = *reinterpret_cast<const float4*>(dOs + i * AB_PITCH + c0 + d);
+                const float4 qq = *reinterpret_cast<const float4*>(Qs + i * AB_PITCH + c0 + d);
                 av[d] = fmaf(p, oo.x, av[d]); av[d + 1] = fmaf(p, oo.y, av[d + 1]);
                 av[d + 2] = fmaf(p, oo.z, av[d + 2]); av[d + 3] = fmaf(p, oo.w, av[d + 3]);
                 ak[d] = fmaf(ds, qq.x, ak[d]); ak[d + 1] = fmaf(ds, qq.y, ak[d + 1]);       // Qs is pre-scaled: dK carries `scale`
                 ak[d + 2] = fmaf(ds, qq.z, ak[d + 2]); ak[d + 3] = fmaf(ds, qq.w, ak[d + 3]);
             }
         }
-#pragma unroll
-        for (int o = 1; o < G; o <<= 1) {
-#pragma unroll
-            for (int d = 0; d < HD; ++d) {
-                ak[d] += __shfl_xor_sync(0xffffffffu, ak[d], o, G);
-                av[d] += __shfl_xor_sync(0xffffffffu, av[d], o, G);
-            }
-        }
         const long long r = krow0 + (long long)j * a.k_seq;
-        float* dkp = dk + r * lddk + h * HD;
-        float* dvp = dv + r * lddv + h * HD;
+        float* dkp = dk + r * lddk + h * HD + c0;
+        float* dvp = dv + r * lddv + h * HD + c0;
 #pragma unroll
-        for (int d = 0; d < HD; d += 4) {
-            if (act && d / (HD / G) == g) {
-                *reinterpret_cast<float4*>(dkp + d) = make_float4(ak[d], ak[d + 1], ak[d + 2], ak[d + 3]);
-                *reinterpret_cast<float4*>(dvp + d) = make_float4(av[d], av[d + 1], av[d + 2], av[d + 3]);
-            }
+        for (int d = 0; d < CPL; d += 4) {
+            *reinterpret_cast<float4*>(dkp + d) = make_float4(ak[d], ak[d + 1], ak[d + 2], ak[d + 3]);
+            *reinterpret_cast<float4*>(dvp + d) = make_float4(av[d], av[d + 1], av[d + 2], av[d + 3]);
         }
     }
 }

@@ -1,6 +1,8 @@
 // Row-wise / gather / attention kernels of the Pluto policy (everything that is not a GEMM).
 // Reference semantics are cited per kernel (paths relative to
 // /root/reference/rift/cbv/planning/pluto/model/).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ops.h"
 
@@ -156,7 +158,7 @@ int launch_layernorm(const float* x, long long ldx, int rows, int C, const float
 // dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy_eff * gamma
 // dgamma += sum_rows dy_eff * xhat ; dbeta += sum_rows dy_eff   (two-stage, fixed order -> deterministic)
 constexpr int LNB_MAXC = 1024;
-constexpr int LNB_BLOCKS = 148;
+constexpr int LNB_BLOCKS = 592;       // partial rows of the parameter-gradient reduction (4 CTAs per SM)
 
 __global__ void __launch_bounds__(256)
 layernorm_bwd_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ dy, long long lddy, int rows,
@@ -360,7 +362,7 @@ int launch_layernorm_bwd(const float* x, long long ldx, const float* dy, long lo
                 cudaStream_t s2;
                 int r2 = second_stage_stream(st, fin, &s2);
                 if (r2) return r2;
-                launch_k(colsum_final2_kernel, dim3(cdiv(C, 32), 2), 256, 0, s2, scratch, nb4, C, dgamma, dbeta);
+                launch_k(colsum_final2_kernel, dim3(cdiv(C, 32), 2), 1024, 0, s2, scratch, nb4, C, dgamma, dbeta);
                 RIFT_LAUNCH_OK();
             }
             return 0;
@@ -380,7 +382,7 @@ int launch_layernorm_bwd(const float* x, long long ldx, const float* dy, long lo
         cudaStream_t s2;
         int r2 = second_stage_stream(st, fin, &s2);
         if (r2) return r2;
-        launch_k(colsum_final2_kernel, dim3(cdiv(C, 32), 2), 256, 0, s2, scratch, nb, C, dgamma, dbeta);
+        launch_k(colsum_final2_kernel, dim3(cdiv(C, 32), 2), 1024, 0, s2, scratch, nb, C, dgamma, dbeta);
         RIFT_LAUNCH_OK();
     }
     return 0;
@@ -435,21 +437,25 @@ colsum_final_kernel(const float* __restrict__ partial, int nb, long long stride,
         out[c] = accumulate ? out[c] + s : s;
     }
 }
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 colsum_final2_kernel(const float* __restrict__ partial, int nb, int C, float* __restrict__ out0, float* __restrict__ out1) {
     pdl_grid_sync();
-    __shared__ float sm[8][33];
+    __shared__ float sm[32][33];                       // 32 row lanes x 32 columns, combined in a fixed order
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + tx;
     const float* p = partial + (long long)blockIdx.y * C;          // layout [nb][2][C]
-    float a = 0.f;
-    if (c < C) for (int b = ty; b < nb; b += 8) a += p[(long long)b * 2 * C + c];
-    sm[ty][tx] = a;
+    float a0 = 0.f, a1 = 0.f;
+    if (c < C) {
+        int b = ty;
+        for (; b + 32 < nb; b += 64) { a0 += p[(long long)b * 2 * C + c]; a1 += p[(long long)(b + 32) * 2 * C + c]; }
+        if (b < nb) a0 += p[(long long)b * 2 * C + c];
+    }
+    sm[ty][tx] = a0 + a1;
     __syncthreads();
     if (ty == 0 && c < C) {
         float s = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) s += sm[i][tx];
+        for (int i = 0; i < 32; ++i) s += sm[i][tx];
         float* out = blockIdx.y ? out1 : out0;
         out[c] += s;
     }
@@ -548,10 +554,124 @@ attention_kernel(AttnArgs a) {
     }
 }
 
+// ---- head_dim 32, cooperative form: PB (batch, head) problems per CTA, G lanes per query.  Q, K, V are staged with
+// coalesced 16-byte loads into rows padded to 36 floats.  The G lanes of a query split the CHANNELS (32 / G each):
+// every key costs a partial dot product plus log2(G) shuffles inside the lane group, the online-softmax state is
+// replicated, and each lane ends up owning its slice of the output row - few registers, several CTAs per SM.
+constexpr int AF_PITCH = 36;
+__host__ __device__ inline size_t attn_fwd2_smem_floats(int Sq, int Sk) {
+    const size_t n = (size_t)Sq * AF_PITCH + (size_t)2 * Sk * AF_PITCH + ((Sk + 3) / 4);
+    return (n + 3) & ~(size_t)3;
+}
+
+template <int G>
+__global__ void __launch_bounds__(512)
+attention2_kernel(AttnArgs a, int PB, int tpp) {
+    pdl_grid_sync();
+    constexpr int HD = 32, CPL = HD / G;
+    extern __shared__ __align__(16) float sm[];
+    const int Sq = a.Sq, Sk = a.Sk;
+    const int pl = threadIdx.x / tpp, t = threadIdx.x - pl * tpp;
+    const long long prob = (long long)blockIdx.x * PB + pl;
+    const bool live = prob < (long long)a.B * a.H;
+    float* base = sm + (size_t)pl * attn_fwd2_smem_floats(Sq, Sk);
+    float* Qs = base;
+    float* Ks = Qs + (size_t)Sq * AF_PITCH;
+    float* Vs = Ks + (size_t)Sk * AF_PITCH;
+    uint8_t* msk = reinterpret_cast<uint8_t*>(Vs + (size_t)Sk * AF_PITCH);
+    const int b = live ? (int)(prob / a.H) : 0, h = live ? (int)(prob % a.H) : 0;
+    const long long krow0 = attn_row(b, a.k_inner_n, a.k_outer, a.k_inner);
+    const long long qrow0 = attn_row(b, a.q_inner_n, a.q_outer, a.q_inner);
+    if (live) {
+        for (int e = t; e < Sk * 8; e += tpp) {
+            const int j = e >> 3, c = (e & 7) * 4;
+            const long long r = krow0 + (long long)j * a.k_seq;
+            *reinterpret_cast<float4*>(Ks + j * AF_PITCH + c) = *reinterpret_cast<const float4*>(a.k + r * a.ldk + h * HD + c);
+            *reinterpret_cast<float4*>(Vs + j * AF_PITCH + c) = *reinterpret_cast<const float4*>(a.v + r * a.ldv + h * HD + c);
+        }
+        for (int e = t; e < Sq * 8; e += tpp) {
+            const int i = e >> 3, c = (e & 7) * 4;
+            float4 q = *reinterpret_cast<const float4*>(a.q + (qrow0 + (long long)i * a.q_seq) * a.ldq + h * HD + c);
+            q.x *= a.scale; q.y *= a.scale; q.z *= a.scale; q.w *= a.scale;
+            *reinterpret_cast<float4*>(Qs + i * AF_PITCH + c) = q;
+        }
+        const uint8_t* kpm = a.kpm ? a.kpm + (long long)(a.kpm_mod > 0 ? b % a.kpm_mod : b / a.kpm_div) * Sk : nullptr;
+        for (int j = t; j < Sk; j += tpp) msk[j] = kpm ? kpm[j] : 0;
+    }
+    __syncthreads();
+    const int row = t / G, g = t % G;
+    if (!(live && row < Sq)) return;                 // whole lane groups leave together; shuffles below name the group only
+    const unsigned gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << ((threadIdx.x & 31) & ~(G - 1));
+    const int i = row, c0 = g * CPL;
+    float q[CPL], acc[CPL];
+#pragma unroll
+    for (int d = 0; d < CPL; d += 4) {
+        const float4 x = *reinterpret_cast<const float4*>(Qs + i * AF_PITCH + c0 + d);
+        q[d] = x.x; q[d + 1] = x.y; q[d + 2] = x.z; q[d + 3] = x.w;
+        acc[d] = acc[d + 1] = acc[d + 2] = acc[d + 3] = 0.f;
+    }
+    float m = -INFINITY, l = 0.f;
+    for (int j = 0; j < Sk; ++j) {
+        if (msk[j]) continue;
+        float sc = 0.f;
+#pragma unroll
+        for (int d = 0; d < CPL; d += 4) {
+            const float4 kk = *reinterpret_cast<const float4*>(Ks + j * AF_PITCH + c0 + d);
+            sc = fmaf(q[d], kk.x, sc); sc = fmaf(q[d + 1], kk.y, sc); sc = fmaf(q[d + 2], kk.z, sc); sc = fmaf(q[d + 3], kk.w, sc);
+        }
+#pragma unroll
+        for (int o = 1; o < G; o <<= 1) sc += __shfl_xor_sync(gmask, sc, o);
+        const float mn = fmaxf(m, sc);
+        const float corr = __expf(m - mn);          // m = -inf on the first key: exp(-inf) = 0
+        const float p = __expf(sc - mn);
+        l = l * corr + p;
+#pragma unroll
+        for (int d = 0; d < CPL; d += 4) {
+            const float4 vv = *reinterpret_cast<const float4*>(Vs + j * AF_PITCH + c0 + d);
+            acc[d] = acc[d] * corr + p * vv.x; acc[d + 1] = acc[d + 1] * corr + p * vv.y;
+            acc[d + 2] = acc[d + 2] * corr + p * vv.z; acc[d + 3] = acc[d + 3] * corr + p * vv.w;
+        }
+        m = mn;
+    }
+    const float inv = l > 0.f ? 1.f / l : 0.f;
+    const long long qr = qrow0 + (long long)i * a.q_seq;
+    const long long orow = a.o_custom ? attn_row(b, a.o_inner_n, a.o_outer, a.o_inner) + (long long)i * a.o_seq : qr;
+#pragma unroll
+    for (int d = 0; d < CPL; d += 4) {
+        const float4 o4 = make_float4(acc[d] * inv, acc[d + 1] * inv, acc[d + 2] * inv, acc[d + 3] * inv);
+        if (a.o) *reinterpret_cast<float4*>(a.o + orow * a.ldo + h * HD + c0 + d) = o4;
+        if (a.o_planes.on()) split4_store(a.o_planes, orow, h * HD + c0 + d, o4.x, o4.y, o4.z, o4.w);
+    }
+    if (a.lse && g == 0) a.lse[((long long)b * a.H + h) * Sq + i] = l > 0.f ? m + logf(l) : INFINITY;
+}
+
 int launch_attention(const AttnArgs& a, cudaStream_t st) {
     if (a.B <= 0 || a.Sq <= 0) return 0;
     RIFT_REQUIRE(a.hd == 32 || a.hd == 64, "attention: head_dim must be 32 or 64");
     RIFT_REQUIRE(a.Sk > 0, "attention: empty key sequence");
+    {
+        auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+        const bool vec = a.hd == 32 && al16(a.q) && al16(a.k) && al16(a.v) && al16(a.o) && (a.ldq & 3) == 0 && (a.ldk & 3) == 0 &&
+                         (a.ldv & 3) == 0 && (a.ldo & 3) == 0;
+        const int smax = max(a.Sq, a.Sk);
+        const size_t per = attn_fwd2_smem_floats(a.Sq, a.Sk) * sizeof(float);
+        static const bool legacy = getenv("RIFT_B200_ATTN_FWD_LEGACY") != nullptr;
+        if (vec && !legacy && 4 * a.Sq <= 512 && per <= 200 * 1024) {
+            constexpr int G = 4;
+            const int tpp = (G * max(a.Sq, min(smax, 128 / G)) + 31) / 32 * 32;     // enough threads to stage K / V quickly too
+            int PB = max(1, 256 / tpp);
+            while (PB > 1 && PB * per > 96 * 1024) --PB;
+            const long long nprob = (long long)a.B * a.H;
+            static bool attr2 = false;
+            if (!attr2) {
+                RIFT_CUDA_OK(cudaFuncSetAttribute(attention2_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                attr2 = true;
+            }
+            launch_k(attention2_kernel<G>, (unsigned)((nprob + PB - 1) / PB), PB * tpp, PB * per, st, a, PB, tpp);
+            RIFT_LAUNCH_OK();
+            return 0;
+        }
+    }
     const size_t smem = (size_t)2 * a.Sk * a.hd * sizeof(float);
     RIFT_REQUIRE(smem <= 200 * 1024, "attention: key sequence too long for the shared-memory kernel");
     const int threads = min(128, (a.Sq + 31) / 32 * 32);
