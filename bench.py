@@ -291,6 +291,10 @@ def run_ours(args, wl_name, wl, cfg):
         kt += ks.elapsed_time(ke)
     kernel_ms = kt / reps
     hbm, tf, src = peaks()
+    traffic = None          # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed ncu --set full capture
+    tpath = os.path.join(ROOT, "profiles", "r1b_gemm_big_ncu_full.json")
+    if os.path.exists(tpath) and (rows, K, N) == (46080, 256, 256):
+        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
     kernel_tf = 2.0 * rows * K * N / (kernel_ms * 1e-3) / 1e12
     # HBM view of the same launch: bf16 hi+lo planes of A (4 B/elem) in, fp32 C out, weights from L2
     kernel_gbs = (rows * K * 4 + rows * N * 4) / (kernel_ms * 1e-3) / 1e9
@@ -327,7 +331,7 @@ def run_ours(args, wl_name, wl, cfg):
             "roofline": {"bound": "hbm", "kernel": "rift::gemm_tc_kernel<128,false> (tcgen05 split-bf16 GEMM, largest shape "
                                                    f"of the step: {rows}x{K}x{N}, replayed alone, L2 flushed)",
                          "achieved": kernel_gbs, "peak": hbm, "unit": "GB/s", "frac": kernel_gbs / hbm,
-                         "traffic": None, "peak_source": src + " copy bandwidth (MEASURED_PEAKS.json)",
+                         "traffic": traffic, "peak_source": src + " copy bandwidth (MEASURED_PEAKS.json)",
                          "algorithmic_bytes": rows * K * 4 + rows * N * 4, "kernel_ms": kernel_ms,
                          "tensor_tflops_algorithmic": kernel_tf, "tensor_frac_of_bf16_sustained": kernel_tf / tf,
                          "mma_work_factor": 3},

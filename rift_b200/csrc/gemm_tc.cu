@@ -759,11 +759,21 @@ int launch_gemm_tc_ex(const GemmArgs& a, const PlaneOp& A, const PlaneOp& B, boo
     RIFT_REQUIRE(A.pitch % 64 == 0 && B.pitch % 64 == 0, "gemm_tc: plane pitches must be multiples of 64");
     RIFT_REQUIRE(splits <= 1 || partials != nullptr, "gemm_tc: split-K needs a partial buffer");
     if (a.M <= 0 || a.N <= 0) return 0;
+    // tile width: 64-wide tiles when they shorten the longest per-CTA queue (one persistent CTA per SM): small grids
+    // that leave SMs idle with 128-wide tiles, and N that is not a multiple of 128 (e.g. 192 = 3 x 64)
+    bool narrow = a.N <= 64;
+    if (!narrow && splits <= 1) {
+        static int sms = 0;
+        if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+        const long long t128 = (long long)cdiv(a.M, TC_BM) * cdiv(a.N, 128), t64 = (long long)cdiv(a.M, TC_BM) * cdiv(a.N, 64);
+        const double w128 = (double)((t128 + sms - 1) / sms), w64 = 0.5 * (double)((t64 + sms - 1) / sms);
+        narrow = w64 + 0.2 < w128;
+    }
     if (mn_major) {
-        if (a.N <= 64) return launch_tc<64, true>(a, A, B, splits, partials, st);
+        if (narrow) return launch_tc<64, true>(a, A, B, splits, partials, st);
         return launch_tc<128, true>(a, A, B, splits, partials, st);
     }
-    if (a.N <= 64) return launch_tc<64, false>(a, A, B, splits, partials, st);
+    if (narrow) return launch_tc<64, false>(a, A, B, splits, partials, st);
     return launch_tc<128, false>(a, A, B, splits, partials, st);
 }
 
