@@ -50,13 +50,14 @@ static int fourier_bwd(Ctx& c, const FourierTape& t, const FourierP& p, const fl
         TRY(lin_bwd(c, dm.hn.f, D, d_acc, D, rows, ml.l3, d_hn, D, 0.f, true, &dm.hn.p));
         TRY(ln_bwd(c, dm.ln, ml.n, d_hn, dm.hn.f, d_h, 0));
         float* d_feat = nullptr;
-        if (p.freqs.train) { d_feat = c.alloc<float>((size_t)rows * FIN); if (!d_feat) { set_last_error("workspace too small"); return -1; } }
-        TRY(lin_bwd(c, dm.feat.f, FIN, d_h, D, rows, ml.l0, d_feat, FIN, 0.f, true, &dm.feat.p));
+        constexpr int FINP = (FIN + 3) & ~3;             // pitch of d_feat: lets the data gradient run on the tcgen05 path
+        if (p.freqs.train) { d_feat = c.alloc<float>((size_t)rows * FINP); if (!d_feat) { set_last_error("workspace too small"); return -1; } }
+        TRY(lin_bwd(c, dm.feat.f, FIN, d_h, D, rows, ml.l0, d_feat, FINP, 0.f, true, &dm.feat.p));
         if (p.freqs.train) {
             ALLOC(contrib, float, (size_t)rows * NFREQ);
             ALLOC(sc, float, (size_t)148 * NFREQ);
             if (!c.dry) {
-                TRY(launch_fourier_freq_bwd(t.x, rows, p.d, i, p.freqs.p, NFREQ, d_feat, FIN, contrib, c.st));
+                TRY(launch_fourier_freq_bwd(t.x, rows, p.d, i, p.freqs.p, NFREQ, d_feat, FINP, contrib, c.st));
                 TRY(launch_colsum(contrib, NFREQ, rows, NFREQ, p.freqs.d + (long long)i * NFREQ, 1, sc, c.st));
             }
         }

@@ -231,8 +231,15 @@ inline int lin_bwd(Ctx& c, const float* X, long long ldx, const float* dY, long 
                    long long lddx, float dx_beta, bool bias_grad = true, const Planes* Xp = nullptr) {
     const bool want_w = L.train && L.dW;
     const bool tc_on = c.tc_bwd && c.tcw && L.tcT >= 0;
-    const bool tc_d = tc_on && dX && gemm_tc_shape_ok(M, L.K, L.N) && (lddx % 4) == 0;
-    const bool tc_w = tc_on && want_w && gemm_tc_shape_ok(L.N, L.K, M) && L.N >= 64 && (L.ldw % 4) == 0;
+    // data gradient dX[M, K]: when the caller's dX pitch leaves room, K is padded to a multiple of 4 (the extra
+    // columns read rows of the W^T planes that do not exist -> TMA zero fill -> zeros in dX's pad columns)
+    const int Kd = (dX && lddx % 4 == 0 && lddx >= ((L.K + 3) & ~3)) ? ((L.K + 3) & ~3) : L.K;
+    const bool tc_d = tc_on && dX && gemm_tc_shape_ok(M, Kd, L.N) && (lddx % 4) == 0;
+    // weight gradient dW[N, K] = dY^T X: K that is not a multiple of 4 (FourierEmbedding: 129) runs with the column
+    // count padded to 4 (the operand planes are zero there) and stores only the real columns through the reduce
+    const int Kpad4 = (L.K + 3) & ~3;
+    const bool w_padded = (L.K % 4) != 0 || (L.ldw % 4) != 0;
+    const bool tc_w = tc_on && want_w && gemm_tc_shape_ok(L.N, Kpad4, M) && L.N >= 64 && (Xp && Xp->on() ? Xp->Kp >= Kpad4 : true);
     // Parameter gradients go to the side stream: they read only dYp / the saved operand planes / private partial
     // buffers (never the fp32 dY, which the main stream may update in place later) and nothing downstream on the
     // main stream depends on them before the final join of backward().
@@ -277,20 +284,27 @@ inline int lin_bwd(Ctx& c, const float* X, long long ldx, const float* dY, long 
         }
         const int tiles = ((L.N + 127) / 128) * ((L.K + (L.K <= 64 ? 63 : 127)) / (L.K <= 64 ? 64 : 128));
         const int num_kb = (M + 63) / 64;
-        int splits = 296 / tiles;
+        // one wave of (tile, split) work items: more splits only add partial-slab traffic for the reduce
+        int splits = 148 / tiles;
+        if (splits > 24) splits = 24;
         if (splits > num_kb) splits = num_kb;
         if (splits < 1) splits = 1;
         float* ws = nullptr;
-        if (splits > 1) { ws = c.alloc<float>((size_t)splits * L.N * L.K); if (!ws) { set_last_error("workspace too small"); return -1; } }
+        if (splits > 1 || w_padded) { ws = c.alloc<float>((size_t)splits * L.N * Kpad4); if (!ws) { set_last_error("workspace too small"); return -1; } }
         if (!c.dry) {
             if (!forked) TRY(fork_to(c, c.side));
             OnStream on(c, c.side);
             GemmArgs a;
-            a.C = L.dW; a.ldc = L.ldw; a.M = L.N; a.N = L.K; a.K = M; a.beta = 1.f;
+            a.C = L.dW; a.ldc = L.ldw; a.M = L.N; a.N = Kpad4; a.K = M; a.beta = 1.f;
+            if (w_padded) a.n_store = L.K;
             PlaneOp A{dYp.hi, dYp.lo, M, dYp.Kp, 0, 0};
             PlaneOp B{xp.hi, xp.lo, M, xp.Kp, 0, 0};
             TRY(launch_gemm_tc_ex(a, A, B, true, splits, ws, c.st));
         }
+    } else if (want_w && L.K <= 32 && L.ldw == L.K && M >= 1024) {
+        // narrow first-layer input (raw features / im2col of 9 channels): dedicated kernel instead of the generic SIMT GEMM
+        ALLOC(wp, float, (size_t)wgrad_narrow_slabs(M) * L.N * L.K);
+        if (!c.dry) TRY(launch_wgrad_narrow(dY, lddy, X, ldx, M, L.N, L.K, L.dW, wp, c.st));
     } else if (want_w) {
         const int splits = M >= 2048 ? (M / 512 < 64 ? M / 512 : 64) : 1;
         float* ws = nullptr;
@@ -306,7 +320,7 @@ inline int lin_bwd(Ctx& c, const float* X, long long ldx, const float* dY, long 
         if (!c.dry) {
             const TcWeight& wt = (*c.tcw)[L.tcT];          // planes [K_full, Np_full] of W^T; the slice origin swaps roles
             GemmArgs a;
-            a.C = dX; a.ldc = lddx; a.M = M; a.N = L.K; a.K = L.N; a.beta = dx_beta;
+            a.C = dX; a.ldc = lddx; a.M = M; a.N = Kd; a.K = L.N; a.beta = dx_beta;
             PlaneOp A{dYp.hi, dYp.lo, M, dYp.Kp, 0, 0};
             PlaneOp B{wt.hi, wt.lo, wt.N, wt.Kp, L.tc_k0, L.tc_n0};
             TRY(launch_gemm_tc_ex(a, A, B, false, 1, nullptr, c.st));

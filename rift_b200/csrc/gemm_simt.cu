@@ -115,23 +115,25 @@ gemm_simt_kernel(const float* __restrict__ A, long long sam, long long sak, cons
 
 __global__ void __launch_bounds__(256)
 gemm_splitk_reduce_kernel(const float* __restrict__ ws, int splits, float* __restrict__ C, long long ldc, int M, int N,
-                          Epilogue ep) {
+                          Epilogue ep, int Nw) {
     pdl_grid_sync();
-    const long long total = (long long)M * N;
+    const long long total = (long long)M * N, slab = (long long)M * Nw;
     for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
         const int m = (int)(i / N), n = (int)(i - (long long)m * N);
+        const float* w = ws + (long long)m * Nw + n;
         float a = 0.f;
-        for (int z = 0; z < splits; ++z) a += ws[(long long)z * total + i];     // fixed order: deterministic
+        for (int z = 0; z < splits; ++z) a += w[(long long)z * slab];     // fixed order: deterministic
         float* c = C + (long long)m * ldc + n;
         *c = apply_epilogue(ep, a, m, n, ep.beta != 0.f ? *c : 0.f);
     }
 }
 
 // fixed-order reduction of split-K partials [splits, M, N] + the epilogue of `a` into a.C (shared with gemm_tc.cu)
-int launch_splitk_reduce(const float* ws, int splits, const GemmArgs& a, cudaStream_t st) {
+int launch_splitk_reduce(const float* ws, int splits, const GemmArgs& a, cudaStream_t st, int ws_pitch) {
     Epilogue ep{a.bias, a.colscale, a.pre, a.ldpre, a.pre_div, a.res, a.ldres, a.res_div, a.res_mod, a.act, a.beta, a.alpha, a.preact, a.ldc};
     const long long total = (long long)a.M * a.N;
-    launch_k(gemm_splitk_reduce_kernel, (int)min((long long)148 * 8, (total + 255) / 256), 256, 0, st, ws, splits, a.C, a.ldc, a.M, a.N, ep);
+    launch_k(gemm_splitk_reduce_kernel, (int)min((long long)148 * 8, (total + 255) / 256), 256, 0, st, ws, splits, a.C, a.ldc, a.M, a.N, ep,
+             ws_pitch > 0 ? ws_pitch : a.N);
     RIFT_LAUNCH_OK();
     return 0;
 }
@@ -166,7 +168,7 @@ int launch_gemm_simt(const GemmArgs& a, cudaStream_t st) {
     if (splits > 1) {
         const long long total = (long long)a.M * a.N;
         launch_k(gemm_splitk_reduce_kernel, (int)min((long long)148 * 8, (total + 255) / 256), 256, 0, st, ws, splits, a.C, a.ldc,
-                                                                                                    a.M, a.N, ep);
+                                                                                                    a.M, a.N, ep, a.N);
         RIFT_LAUNCH_OK();
     }
     return 0;

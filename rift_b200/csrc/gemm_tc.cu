@@ -706,6 +706,7 @@ bool gemm_tc_eligible(const GemmArgs& a) {
     auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
     if (a.C == nullptr && !a.out_planes.on()) return false;
     if (a.beta != 0.f && a.C == nullptr) return false;
+    if (a.n_store > 0) return gemm_tc_shape_ok(a.M, a.N, a.K) && a.C != nullptr && a.n_store <= a.N;     // scalar reduce-side epilogue
     return gemm_tc_shape_ok(a.M, a.N, a.K) && (a.ldc % 4) == 0 && al16(a.C) && al16(a.bias) && al16(a.colscale) &&
            al16(a.pre) && (a.ldpre % 4) == 0 && al16(a.res) && (a.ldres % 4) == 0 && al16(a.preact);
 }
@@ -734,7 +735,9 @@ static int launch_tc(const GemmArgs& a, const PlaneOp& A, const PlaneOp& B, int 
     g.out = a.out_planes;
     g.trace = g_tc_trace;
     { static int dbg = -1; if (dbg < 0) { const char* e = getenv("RIFT_B200_TC_DBG"); dbg = e ? atoi(e) : 0; } g.dbg = dbg; }
-    if (splits > 1) {
+    const bool via_ws = splits > 1 || a.n_store > 0;       // raw sums into the partial buffer, epilogue in the reduce
+    if (via_ws) {
+        if (splits < 1) splits = 1;
         g.splits = splits; g.kb_per_split = cdiv(num_kb, splits);
         g.splits = cdiv(num_kb, g.kb_per_split);
         g.C = partials; g.ldc = a.N; g.split_stride = (long long)a.M * a.N;
@@ -749,7 +752,10 @@ static int launch_tc(const GemmArgs& a, const PlaneOp& A, const PlaneOp& B, int 
     const int n_tiles = cdiv(a.N, BN) * cdiv(a.M, TC_BM) * g.splits;
     launch_k(gemm_tc_kernel<BN, MN>, min(n_tiles, sms), TC_THREADS, TcSmem<BN>::TOTAL, st, *ma_hi, *ma_lo, *mb_hi, *mb_lo, g);
     RIFT_LAUNCH_OK();
-    if (splits > 1) return launch_splitk_reduce(partials, g.splits, a, st);
+    if (via_ws) {
+        if (a.n_store > 0) { GemmArgs b = a; b.N = a.n_store; return launch_splitk_reduce(partials, g.splits, b, st, a.N); }
+        return launch_splitk_reduce(partials, g.splits, a, st);
+    }
     return 0;
 }
 
@@ -757,7 +763,7 @@ int launch_gemm_tc_ex(const GemmArgs& a, const PlaneOp& A, const PlaneOp& B, boo
                       cudaStream_t st) {
     RIFT_REQUIRE(gemm_tc_eligible(a), "gemm_tc: shape / layout not eligible");
     RIFT_REQUIRE(A.pitch % 64 == 0 && B.pitch % 64 == 0, "gemm_tc: plane pitches must be multiples of 64");
-    RIFT_REQUIRE(splits <= 1 || partials != nullptr, "gemm_tc: split-K needs a partial buffer");
+    RIFT_REQUIRE((splits <= 1 && a.n_store <= 0) || partials != nullptr, "gemm_tc: split-K / padded-N needs a partial buffer");
     if (a.M <= 0 || a.N <= 0) return 0;
     // tile width: 64-wide tiles when they shorten the longest per-CTA queue (one persistent CTA per SM): small grids
     // that leave SMs idle with 128-wide tiles, and N that is not a multiple of 128 (e.g. 192 = 3 x 64)

@@ -840,4 +840,57 @@ int launch_state_tokens_bwd(const float* cur, int cs_stride, int bs, int n_tok, 
     return 0;
 }
 
+// =====================================================================================
+// Weight gradient of a first-layer Linear with a narrow input (K <= 32: raw features, im2col of 9 channels):
+// dW[N, K] (+)= dY[M, N]^T X[M, K].  The tensor-core path does not take K < 32; the generic SIMT GEMM runs this shape
+// on a handful of CTAs.  Here: block = (row slab, 128 output features) x 2 row lanes, thread = one output feature with
+// its K accumulators in registers (X rows are warp-uniform broadcast loads); per-slab partials [slabs][N * K] are
+// then summed in a fixed order by launch_colsum_final.
+// =====================================================================================
+__global__ void __launch_bounds__(256)
+wgrad_narrow_kernel(const float* __restrict__ dY, long long lddy, const float* __restrict__ X, long long ldx, int M, int N, int K,
+                    int rows_per_slab, float* __restrict__ partial) {
+    pdl_grid_sync();
+    __shared__ float sm[128][33];
+    const int nl = threadIdx.x & 127, half = threadIdx.x >> 7;
+    const int n = blockIdx.y * 128 + nl;
+    const int r0 = blockIdx.x * rows_per_slab, r1 = min(M, r0 + rows_per_slab);
+    float acc[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) acc[k] = 0.f;
+    if (n < N) {
+        for (int r = r0 + half; r < r1; r += 2) {
+            const float d = dY[(long long)r * lddy + n];
+            const float* xr = X + (long long)r * ldx;
+#pragma unroll
+            for (int k = 0; k < 32; ++k)
+                if (k < K) acc[k] = fmaf(d, __ldg(xr + k), acc[k]);
+        }
+    }
+    if (half == 1) {
+#pragma unroll
+        for (int k = 0; k < 32; ++k) sm[nl][k] = acc[k];
+    }
+    __syncthreads();
+    if (half == 0 && n < N) {
+        float* o = partial + (long long)blockIdx.x * N * K + (long long)n * K;
+#pragma unroll
+        for (int k = 0; k < 32; ++k)
+            if (k < K) o[k] = acc[k] + sm[nl][k];
+    }
+}
+
+// partial: slabs * N * K floats with slabs = wgrad_narrow_slabs(M)
+int wgrad_narrow_slabs(int M) { return max(1, min(296, cdiv(M, 64))); }
+int launch_wgrad_narrow(const float* dY, long long lddy, const float* X, long long ldx, int M, int N, int K, float* dW,
+                        float* partial, cudaStream_t st) {
+    RIFT_REQUIRE(K >= 1 && K <= 32, "wgrad_narrow: K must be in [1, 32]");
+    if (M <= 0 || N <= 0) return 0;
+    const int slabs = wgrad_narrow_slabs(M);
+    const int rps = cdiv(M, slabs);
+    launch_k(wgrad_narrow_kernel, dim3(slabs, cdiv(N, 128)), 256, 0, st, dY, lddy, X, ldx, M, N, K, rps, partial);
+    RIFT_LAUNCH_OK();
+    return launch_colsum_final(partial, slabs, N * K, dW, 1, st);
+}
+
 }  // namespace rift

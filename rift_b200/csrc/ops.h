@@ -52,9 +52,12 @@ struct GemmArgs {
     float* split_ws = nullptr;           // [split_k, M, N] when split_k > 1
     float* preact = nullptr;             // optional copy of the value before `act` (same ldc), for backward
     Planes out_planes;                   // optional split-bf16 copy of the result (tcgen05 path; C may then be null)
+    int n_store = 0;                     // tcgen05 path: >0 = only the first n_store of the N (padded) columns are real; the
+                                         // result then goes through the partial buffer and C / ldc need no alignment
 };
 int launch_gemm_simt(const GemmArgs& a, cudaStream_t st);
-int launch_splitk_reduce(const float* ws, int splits, const GemmArgs& a, cudaStream_t st);
+// ws_pitch: row pitch of the partial slabs (0 = a.N); the reduce writes columns [0, a.N)
+int launch_splitk_reduce(const float* ws, int splits, const GemmArgs& a, cudaStream_t st, int ws_pitch = 0);
 
 // Second stage of a two-stage reduction may run on another stream: after the first stage is enqueued on the
 // caller's stream, `ev` is recorded there and `st` waits for it (null st: everything stays on the caller's stream).
@@ -152,6 +155,10 @@ int launch_scale_shift_rows_bwd(float* dy, const float* colscale, long long rows
 int launch_traj_outputs(const float* trajectory, long long n_traj, int T, float* cand, cudaStream_t st);
 
 // ------------------------------------------------------------------ nn_bwd_kernels.cu
+// dW[N, K] += dY^T X for narrow first-layer inputs (K <= 32, dW contiguous); partial: wgrad_narrow_slabs(M) * N * K floats
+int wgrad_narrow_slabs(int M);
+int launch_wgrad_narrow(const float* dY, long long lddy, const float* X, long long ldx, int M, int N, int K, float* dW,
+                        float* partial, cudaStream_t st);
 int launch_groupsum(const float* x, long long ldx, int groups, int n, int C, float* out, long long ldo, int accumulate,
                     cudaStream_t st);
 int launch_modsum(const float* x, long long ldx, long long rows, int C, int mod, float* out, int accumulate, cudaStream_t st);
