@@ -480,6 +480,9 @@ int rift_b200_engine::forward(const rift_b200_batch& bt, const rift_b200_outputs
         const int ntok = cfg.state_channel, eh = 4;
         const Lin in_q = slice(m.ego.attn.in, 0, D, 0, D, true), in_kv = slice(m.ego.attn.in, D, 2 * D, 0, D, true);
         Act toks, eo, x_ego;
+        cudaEvent_t ego_done = nullptr;
+        {   // independent of the history encoder above: branch stream (first in its queue)
+        OnStream on_br(c, c.br);
         ALLOC(kv, float, (size_t)bs * ntok * 2 * D);
         ALLOC(qv, float, (size_t)D);
         ALLOC(elsp, float, (size_t)bs * eh);
@@ -507,6 +510,9 @@ int rift_b200_engine::forward(const rift_b200_batch& bt, const rift_b200_outputs
         }
         TRY(linear_new(c, eo, m.ego.attn.out, Epi(), W_F, &x_ego));
         et.toks = toks.f; et.toks_a = toks; et.kv = kv; et.qv = qv; et.lse = elsp; et.eo = eo;
+        if (!c.dry && c.br) { ego_done = c.next_event(); RIFT_CUDA_OK(cudaEventRecord(ego_done, c.br)); }
+        }
+        if (ego_done) RIFT_CUDA_OK(cudaStreamWaitEvent(c.st, ego_done, 0));
         if (!c.dry)
             TRY(launch_agent_assemble(x_hist.f, x_ego.f, agent_any, bt.agent_category, m.agent_type_emb.p, bs, A, S, D, tokens, c.st));
     }

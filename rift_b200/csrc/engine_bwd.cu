@@ -330,8 +330,11 @@ int rift_b200_engine::backward_impl(const rift_b200_batch& bt, const float* dlog
             if (m.agent_type_emb.train)
                 TRY(launch_embedding_bwd(dX, D, 0, A, S, bt.agent_category, NA, D, 4, m.agent_type_emb.d, 0, esc, c.st));
         }
-        // ---- StateAttentionEncoder
+        // ---- StateAttentionEncoder: parameter-only from here (its inputs are raw states) -> branch stream
+        TRY(fork_to(c, c.br));
         {
+            OnStream on_br(c, c.br);
+            ALLOC(esc_ego, float, (size_t)148 * D);      // private reduction scratch (esc is used by the main stream below)
             const EgoTape& et = tp.ego;
             const int ntok = cfg.state_channel, eh = 4;
             const Lin in_q = slice(m.ego.attn.in, 0, D, 0, D, true), in_kv = slice(m.ego.attn.in, D, 2 * D, 0, D, true);
@@ -346,7 +349,7 @@ int rift_b200_engine::backward_impl(const rift_b200_batch& bt, const float* dlog
                 AttnArgs a = attn_ego(et.qv, et.kv, bs, ntok, D, eh);
                 a.lse = et.lse;
                 TRY(launch_attention_bwd(a, d_eo, D, dq_b, D, d_kv, d_kv + D, 2 * D, 2 * D, c.st));
-                TRY(launch_colsum(dq_b, D, bs, D, d_qv, 0, esc, c.st));
+                TRY(launch_colsum(dq_b, D, bs, D, d_qv, 0, esc_ego, c.st));
             }
             TRY(lin_bwd(c, m.ego.query.p, D, d_qv, D, 1, in_q, m.ego.query.train ? m.ego.query.d : nullptr, D, 1.f));
             TRY(lin_bwd(c, et.toks, D, d_kv, 2 * D, bs * ntok, in_kv, d_toks, D, 0.f));

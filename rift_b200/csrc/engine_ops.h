@@ -305,6 +305,11 @@ inline int lin_bwd(Ctx& c, const float* X, long long ldx, const float* dY, long 
         // narrow first-layer input (raw features / im2col of 9 channels): dedicated kernel instead of the generic SIMT GEMM
         ALLOC(wp, float, (size_t)wgrad_narrow_slabs(M) * L.N * L.K);
         if (!c.dry) TRY(launch_wgrad_narrow(dY, lddy, X, ldx, M, L.N, L.K, L.dW, wp, c.st));
+    } else if (want_w && L.N == 1 && L.K >= 32 && M >= 1024) {
+        // single-output Linear (probability head): dW[1, K] = sum_r dY[r] X[r, :] = the narrow kernel with the roles of
+        // dY and X swapped ([K, 1] and [1, K] are the same memory)
+        ALLOC(wp, float, (size_t)wgrad_narrow_slabs(M) * L.K);
+        if (!c.dry) TRY(launch_wgrad_narrow(X, ldx, dY, lddy, M, L.K, 1, L.dW, wp, c.st));
     } else if (want_w) {
         const int splits = M >= 2048 ? (M / 512 < 64 ? M / 512 : 64) : 1;
         float* ws = nullptr;

@@ -138,10 +138,33 @@ int launch_splitk_reduce(const float* ws, int splits, const GemmArgs& a, cudaStr
     return 0;
 }
 
+// N == 1 (the probability head's last Linear): one warp per row, lanes stride the reduction index
+__global__ void __launch_bounds__(256)
+gemv_rowdot_kernel(const float* __restrict__ A, long long sam, const float* __restrict__ w, const float* __restrict__ bias,
+                   float* __restrict__ C, long long ldc, int M, int K) {
+    pdl_grid_sync();
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const float* a = A + (long long)row * sam;
+    float s0 = 0.f, s1 = 0.f;
+    int k = lane;
+    for (; k + 32 < K; k += 64) { s0 = fmaf(a[k], __ldg(w + k), s0); s1 = fmaf(a[k + 32], __ldg(w + k + 32), s1); }
+    if (k < K) s0 = fmaf(a[k], __ldg(w + k), s0);
+    const float s = warp_sum(s0 + s1);
+    if (lane == 0) C[(long long)row * ldc] = s + (bias ? bias[0] : 0.f);
+}
+
 int launch_gemm_simt(const GemmArgs& a, cudaStream_t st) {
     RIFT_REQUIRE(a.A && a.B && a.C, "gemm: null operand");
     if (a.M <= 0 || a.N <= 0) return 0;
     RIFT_REQUIRE(a.K > 0, "gemm: K must be positive");
+    if (a.N == 1 && a.sak == 1 && a.sbk == 1 && a.M >= 256 && !a.colscale && !a.pre && !a.res && !a.preact && a.act == ACT_NONE &&
+        a.beta == 0.f && a.alpha == 1.f && a.split_k <= 1) {
+        launch_k(gemv_rowdot_kernel, cdiv(a.M, 8), 256, 0, st, a.A, a.sam, a.B, a.bias, a.C, a.ldc, a.M, a.K);
+        RIFT_LAUNCH_OK();
+        return 0;
+    }
     RIFT_REQUIRE(a.pre_div > 0 && a.res_div > 0, "gemm: broadcast divisors must be positive");
     Epilogue ep{a.bias, a.colscale, a.pre, a.ldpre, a.pre_div, a.res, a.ldres, a.res_div, a.res_mod, a.act, a.beta, a.alpha, a.preact, a.ldc};
     int splits = a.split_k > 1 ? a.split_k : 1;
