@@ -184,6 +184,12 @@ int rift_b200_op_attention(const float* qkv, int B, int S, int H, int hd, const 
                            void* stream);
 int rift_b200_op_nat_attention(const float* qkv, int n_seq, int L, int heads, int hd, int ksize, const float* rpb,
                                float* out, void* stream);
+/* forward (writes out [B,S,H*hd] and lse [B,H,S]) followed by the backward: dqkv [B,S,3*H*hd] = d(sum(out * d_out)) / d qkv */
+int rift_b200_op_attention_bwd(const float* qkv, const float* d_out, int B, int S, int H, int hd, const uint8_t* key_padding,
+                               float* out, float* lse, float* dqkv, void* stream);
+/* drpb_partial (may be NULL): [n_seq * heads][2 * ksize - 1] per-(sequence, head) bias gradients (column-sum them) */
+int rift_b200_op_nat_attention_bwd(const float* qkv, const float* d_out, int n_seq, int L, int heads, int hd, int ksize,
+                                   const float* rpb, float* dqkv, float* drpb_partial, void* stream);
 /* dy *= act'(ref) in place (act 1: ReLU, ref = output; act 2: GELU, ref = pre-activation) */
 int rift_b200_op_act_bwd(const float* ref, float* dy, long long n, int act, void* stream);
 /* out[c] (+)= sum_r x[r, c]; scratch: 148 * C floats */

@@ -92,6 +92,8 @@ _SIGNATURES = {
     "rift_b200_op_layernorm_bwd": (C.c_int, [_V, _V, C.c_int, C.c_int, _V, _V, _V, _V, _V, _V, _V, _V, _V]),
     "rift_b200_op_attention": (C.c_int, [_V, C.c_int, C.c_int, C.c_int, C.c_int, _V, _V, _V]),
     "rift_b200_op_nat_attention": (C.c_int, [_V, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _V, _V, _V]),
+    "rift_b200_op_attention_bwd": (C.c_int, [_V, _V, C.c_int, C.c_int, C.c_int, C.c_int, _V, _V, _V, _V, _V]),
+    "rift_b200_op_nat_attention_bwd": (C.c_int, [_V, _V, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _V, _V, _V, _V]),
     "rift_b200_op_act_bwd": (C.c_int, [_V, _V, C.c_longlong, C.c_int, _V]),
     "rift_b200_op_colsum": (C.c_int, [_V, C.c_int, C.c_int, _V, C.c_int, _V, _V]),
     "rift_b200_op_masked_maxpool": (C.c_int, [_V, _V, C.c_int, C.c_int, C.c_int, _V, _V, _V]),

@@ -261,6 +261,28 @@ int rift_b200_op_nat_attention(const float* qkv, int n_seq, int L, int heads, in
     return launch_nat_attention(qkv, n_seq, L, heads, hd, ksize, rpb, out, S(stream));
 }
 
+int rift_b200_op_attention_bwd(const float* qkv, const float* d_out, int B, int Sq, int H, int hd, const uint8_t* key_padding,
+                               float* out, float* lse, float* dqkv, void* stream) {
+    RIFT_REQUIRE(qkv && d_out && out && lse && dqkv, "op_attention_bwd: null argument");
+    const int D = H * hd;
+    AttnArgs a;
+    a.q = qkv; a.k = qkv + D; a.v = qkv + 2 * D; a.o = out;
+    a.ldq = a.ldk = a.ldv = 3 * D; a.ldo = D;
+    a.B = B; a.H = H; a.Sq = Sq; a.Sk = Sq; a.hd = hd;
+    a.q_outer = Sq; a.k_outer = Sq;
+    a.kpm = key_padding; a.scale = 1.f / sqrtf((float)hd);
+    a.lse = lse;
+    int r = launch_attention(a, S(stream));
+    if (r) return r;
+    return launch_attention_bwd(a, d_out, D, dqkv, 3 * D, dqkv + D, dqkv + 2 * D, 3 * D, 3 * D, S(stream));
+}
+
+int rift_b200_op_nat_attention_bwd(const float* qkv, const float* d_out, int n_seq, int L, int heads, int hd, int ksize,
+                                   const float* rpb, float* dqkv, float* drpb_partial, void* stream) {
+    RIFT_REQUIRE(qkv && d_out && rpb && dqkv, "op_nat_attention_bwd: null argument");
+    return launch_nat_attention_bwd(qkv, d_out, n_seq, L, heads, hd, ksize, rpb, dqkv, drpb_partial, S(stream));
+}
+
 int rift_b200_op_act_bwd(const float* ref, float* dy, long long n, int act, void* stream) {
     return launch_act_bwd(ref, dy, n, act, S(stream));
 }

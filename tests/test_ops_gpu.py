@@ -135,6 +135,55 @@ def test_neighborhood_attention(L, heads, hd, k):
     close(out, ref, 5e-6, "nat attention")
 
 
+@pytest.mark.parametrize("B,Sq,H,hd", [(3, 52, 4, 32), (7, 6, 8, 32), (5, 12, 8, 32), (2, 72, 8, 32), (2, 200, 4, 32), (5, 12, 4, 64)])
+def test_attention_backward_vs_autograd(B, Sq, H, hd):
+    """The cooperative (head_dim 32, short sequences) and the per-row attention backward kernels vs torch autograd."""
+    D = H * hd
+    qkv = rnd(B, Sq, 3 * D, seed=1)
+    d_out = rnd(B, Sq, D, seed=2)
+    kpm = torch.zeros(B, Sq, dtype=torch.bool)
+    gen = torch.Generator().manual_seed(3)
+    for b in range(B):
+        n = int(torch.randint(1, Sq + 1, (1,), generator=gen))
+        kpm[b, n:] = True
+    kpm = kpm.cuda()
+    out = torch.empty(B, Sq, D, device="cuda")
+    lse = torch.empty(B, H, Sq, device="cuda")
+    dqkv = torch.empty_like(qkv)
+    _lib.check(_lib.lib().rift_b200_op_attention_bwd(P(qkv), P(d_out), B, Sq, H, hd, P(kpm.view(torch.uint8)), P(out), P(lse),
+                                                     P(dqkv), S()))
+    x = qkv.clone().requires_grad_(True)
+    q, k, v = [t.view(B, Sq, H, hd).transpose(1, 2) for t in x.split(D, dim=-1)]
+    att = ((q * hd ** -0.5) @ k.transpose(-1, -2)).masked_fill(kpm[:, None, None, :], float("-inf")).softmax(-1)
+    ref = (att @ v).transpose(1, 2).reshape(B, Sq, D)
+    (ref * d_out).sum().backward()
+    close(out, ref.detach(), 5e-6, "attention forward")
+    close(dqkv, x.grad, 2e-5, "attention backward")       # tolerance: fp32 round-off of a different summation order
+
+
+@pytest.mark.parametrize("L,heads,hd,k", [(20, 2, 32, 3), (10, 4, 32, 3), (5, 8, 32, 5), (20, 2, 16, 3), (12, 4, 32, 3)])
+def test_neighborhood_attention_backward_vs_autograd(L, heads, hd, k):
+    """Register-resident (L, k) specialisations and the generic kernel vs torch autograd of the restated semantics."""
+    n, dim = 37, heads * hd
+    qkv = rnd(n, L, 3 * dim, seed=1)
+    rpb = rnd(heads, 2 * k - 1, seed=2, scale=0.3)
+    d_out = rnd(n, L, dim, seed=3)
+    dqkv = torch.empty_like(qkv)
+    part = torch.empty(n * heads, 2 * k - 1, device="cuda")
+    _lib.check(_lib.lib().rift_b200_op_nat_attention_bwd(P(qkv), P(d_out), n, L, heads, hd, k, P(rpb), P(dqkv), P(part), S()))
+    x = qkv.clone().requires_grad_(True)
+    rb = rpb.clone().requires_grad_(True)
+    q, kk, v = x.view(n, L, 3, heads, hd).permute(2, 0, 3, 1, 4)
+    q = q * hd ** -0.5
+    i = torch.arange(L, device="cuda")
+    idx = (i - k // 2).clamp(0, L - k)[:, None] + torch.arange(k, device="cuda")[None]
+    a = torch.einsum("bhld,bhlkd->bhlk", q, kk[:, :, idx]) + rb[:, idx - i[:, None] + (k - 1)]
+    ref = torch.einsum("bhlk,bhlkd->bhld", a.softmax(-1), v[:, :, idx]).permute(0, 2, 1, 3).reshape(n, L, dim)
+    (ref * d_out).sum().backward()
+    close(dqkv, x.grad, 2e-5, "nat attention backward")
+    close(part.view(n, heads, 2 * k - 1).sum(0), rb.grad, 2e-5, "nat attention rpb gradient")
+
+
 def test_masked_maxpool():
     groups, n, Cn = 50, 20, 96
     x = rnd(groups, n, Cn, seed=1)
