@@ -104,11 +104,28 @@ static int points_bwd(Ctx& c, const PointsTape& t, const PointsEncP& p, const fl
 // generic pre-LN attention + MLP block tail: X2 = X1 + fc2(act(fc1(LN2(X1))));  dX (rows x D) is updated in place
 static int mlp_tail_bwd(Ctx& c, int rows, int D, int Hd, const Act& hm, const float* act_ref, int act, const Act& t2, const LNSave& ln2,
                         const Norm& n2, const Lin& fc1, const Lin& fc2, float* dX) {
-    ALLOC(d_hm, float, (size_t)rows * Hd);
     ALLOC(d_t2, float, (size_t)rows * D);
-    TRY(lin_bwd(c, hm.f, Hd, dX, D, rows, fc2, d_hm, Hd, 0.f, true, &hm.p));
-    TRY(act_bwd(c, act_ref, d_hm, (long long)rows * Hd, act));
-    TRY(lin_bwd(c, t2.f, D, d_hm, Hd, rows, fc1, d_t2, D, 0.f, true, &t2.p));
+    // (ReLU only: GELU's derivative - erf + exp per element - costs more inside the GEMM epilogue, where it is
+    // instruction-latency bound, than the bandwidth-bound activation-backward kernel it would replace; measured)
+    if (act == ACT_RELU && lin_bwd_all_tc(c, rows, fc2, true) && lin_bwd_all_tc(c, rows, fc1, true) && (Hd % 4) == 0) {
+        // tensor-core route: fc2's data-gradient GEMM applies act'(.) in its epilogue and writes d_hm as split-bf16
+        // planes only; fc1's backward consumes them directly (no activation-backward kernel, no pack, bias gradient
+        // summed from the planes on the side stream)
+        Planes dhp;
+        dhp.Kp = tc_pitch(Hd);
+        dhp.hi = c.alloc<uint16_t>((size_t)rows * dhp.Kp);
+        dhp.lo = c.alloc<uint16_t>((size_t)rows * dhp.Kp);
+        if (!dhp.hi || !dhp.lo) { set_last_error("workspace too small"); return -1; }
+        LinBwdFuse f2; f2.dact_ref = act_ref; f2.lddact = Hd; f2.dact = act; f2.dX_planes = &dhp;
+        TRY(lin_bwd(c, hm.f, Hd, dX, D, rows, fc2, nullptr, Hd, 0.f, true, &hm.p, &f2));
+        LinBwdFuse f1; f1.dYp_in = &dhp;
+        TRY(lin_bwd(c, t2.f, D, nullptr, Hd, rows, fc1, d_t2, D, 0.f, true, &t2.p, &f1));
+    } else {
+        ALLOC(d_hm, float, (size_t)rows * Hd);
+        TRY(lin_bwd(c, hm.f, Hd, dX, D, rows, fc2, d_hm, Hd, 0.f, true, &hm.p));
+        TRY(act_bwd(c, act_ref, d_hm, (long long)rows * Hd, act));
+        TRY(lin_bwd(c, t2.f, D, d_hm, Hd, rows, fc1, d_t2, D, 0.f, true, &t2.p));
+    }
     TRY(ln_bwd(c, ln2, n2, d_t2, nullptr, dX, 1));
     return 0;
 }

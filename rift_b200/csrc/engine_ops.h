@@ -227,14 +227,34 @@ inline int simt(Ctx& c, const GemmArgs& a) {
 // Tensor-core route (c.tc_bwd): dY is packed once into split-bf16 planes [M, Np];
 //   dX = dYp x (W^T planes)            K-major tcgen05 GEMM
 //   dW += dYp^T x Xp                   MN-major tcgen05 GEMM over the same [rows, features] planes, split-K over rows
+// Optional fusions (tensor-core route only):
+//   dYp_in  : dY already exists as split-bf16 planes (written by the producing GEMM) - no pack; the bias gradient is
+//             then summed from the planes, entirely on the side stream, and the fp32 dY may be null
+//   dact_ref: the data gradient is multiplied by act'(dact_ref) in the GEMM epilogue and, with dX_planes, leaves as
+//             planes (dX may then be null) - the activation backward and the next layer's pack disappear
+struct LinBwdFuse {
+    const Planes* dYp_in = nullptr;
+    const float* dact_ref = nullptr; long long lddact = 0; int dact = 0;
+    Planes* dX_planes = nullptr;
+};
+// shape-only: will lin_bwd run both of this layer's products on the tensor-core route?
+inline bool lin_bwd_all_tc(const Ctx& c, int M, const Lin& L, bool need_dx) {
+    const bool tc_on = c.tc_bwd && c.tcw && L.tcT >= 0;
+    const bool want_w = L.train && L.dW;
+    const bool tc_d = gemm_tc_shape_ok(M, L.K, L.N);
+    const bool tc_w = gemm_tc_shape_ok(L.N, L.K, M) && L.N >= 64 && (L.K % 4) == 0 && (L.ldw % 4) == 0;
+    return tc_on && (!need_dx || tc_d) && (!want_w || tc_w);
+}
 inline int lin_bwd(Ctx& c, const float* X, long long ldx, const float* dY, long long lddy, int M, const Lin& L, float* dX,
-                   long long lddx, float dx_beta, bool bias_grad = true, const Planes* Xp = nullptr) {
+                   long long lddx, float dx_beta, bool bias_grad = true, const Planes* Xp = nullptr,
+                   const LinBwdFuse* fz = nullptr) {
     const bool want_w = L.train && L.dW;
     const bool tc_on = c.tc_bwd && c.tcw && L.tcT >= 0;
     // data gradient dX[M, K]: when the caller's dX pitch leaves room, K is padded to a multiple of 4 (the extra
     // columns read rows of the W^T planes that do not exist -> TMA zero fill -> zeros in dX's pad columns)
     const int Kd = (dX && lddx % 4 == 0 && lddx >= ((L.K + 3) & ~3)) ? ((L.K + 3) & ~3) : L.K;
-    const bool tc_d = tc_on && dX && gemm_tc_shape_ok(M, Kd, L.N) && (lddx % 4) == 0;
+    const bool dx_wanted = dX != nullptr || (fz && fz->dX_planes);
+    const bool tc_d = tc_on && dx_wanted && gemm_tc_shape_ok(M, Kd, L.N) && (lddx % 4) == 0;
     // weight gradient dW[N, K] = dY^T X: K that is not a multiple of 4 (FourierEmbedding: 129) runs with the column
     // count padded to 4 (the operand planes are zero there) and stores only the real columns through the reduce
     const int Kpad4 = (L.K + 3) & ~3;
@@ -248,7 +268,17 @@ inline int lin_bwd(Ctx& c, const float* X, long long ldx, const float* dY, long 
     if (want_b) { sc = c.alloc<float>((size_t)148 * L.N); if (!sc) { set_last_error("workspace too small"); return -1; } }
     Planes dYp;
     bool forked = false, bias_done = false;
-    if (tc_d || tc_w) {
+    if (fz && fz->dYp_in && fz->dYp_in->on()) {
+        if (!(tc_d || !dx_wanted) || (want_w && !tc_w)) { set_last_error("internal: pre-packed dY needs the tensor-core route"); return -1; }
+        dYp = *fz->dYp_in;
+        if (want_b && !c.dry) {                          // bias gradient from the planes, both stages on the side stream
+            TRY(fork_to(c, c.side));
+            forked = true;
+            OnStream on(c, c.side);
+            TRY(launch_colsum_planes(dYp, M, L.N, L.db, 1, sc, c.st));
+        }
+        bias_done = true;
+    } else if (tc_d || tc_w) {
         dYp.Kp = tc_pitch(L.N);
         dYp.hi = c.alloc<uint16_t>((size_t)M * dYp.Kp);
         dYp.lo = c.alloc<uint16_t>((size_t)M * dYp.Kp);
@@ -326,6 +356,10 @@ inline int lin_bwd(Ctx& c, const float* X, long long ldx, const float* dY, long 
             const TcWeight& wt = (*c.tcw)[L.tcT];          // planes [K_full, Np_full] of W^T; the slice origin swaps roles
             GemmArgs a;
             a.C = dX; a.ldc = lddx; a.M = M; a.N = Kd; a.K = L.N; a.beta = dx_beta;
+            if (fz) {
+                a.dact_ref = fz->dact_ref; a.lddact = fz->lddact; a.dact = fz->dact;
+                if (fz->dX_planes) a.out_planes = *fz->dX_planes;
+            }
             PlaneOp A{dYp.hi, dYp.lo, M, dYp.Kp, 0, 0};
             PlaneOp B{wt.hi, wt.lo, wt.N, wt.Kp, L.tc_k0, L.tc_n0};
             TRY(launch_gemm_tc_ex(a, A, B, false, 1, nullptr, c.st));

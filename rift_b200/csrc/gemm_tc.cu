@@ -134,6 +134,7 @@ struct TcEpilogue {
     const float* res; long long ldres; int res_div; int res_mod;
     int act; float beta; float alpha;
     float* preact;
+    const float* dact_ref; long long lddact; int dact;     // multiply by act'(dact_ref[m, n]) (fused activation backward)
 };
 
 struct TcKernelArgs {
@@ -175,7 +176,9 @@ __device__ __forceinline__ float4 lds4(uint32_t addr) {
     return v;
 }
 
-template <int BN, bool MN>
+// DA: the epilogue multiplies by act'(dact_ref) (fused activation backward) - a separate instantiation so that the
+// common kernels do not carry its code
+template <int BN, bool MN, bool DA>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, TcKernelArgs g) {
@@ -373,6 +376,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 } else if (e.act == ACT_GELU) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(gelu_erf(__uint_as_float(r[j])));
+                }
+                if constexpr (DA) {                              // fused activation backward: v *= act'(ref[m, n])
+                    const float* dr = e.dact_ref + (long long)mc * e.lddact;
+                    float4 t[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) t[j] = ld4(dr + min(n0 + c0 + 4 * j, g.N - 4));
+                    if (e.dact == ACT_RELU) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            if (!(t[j].x > 0.f)) r[4 * j] = 0u;
+                            if (!(t[j].y > 0.f)) r[4 * j + 1] = 0u;
+                            if (!(t[j].z > 0.f)) r[4 * j + 2] = 0u;
+                            if (!(t[j].w > 0.f)) r[4 * j + 3] = 0u;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            r[4 * j] = __float_as_uint(__uint_as_float(r[4 * j]) * gelu_erf_grad(t[j].x));
+                            r[4 * j + 1] = __float_as_uint(__uint_as_float(r[4 * j + 1]) * gelu_erf_grad(t[j].y));
+                            r[4 * j + 2] = __float_as_uint(__uint_as_float(r[4 * j + 2]) * gelu_erf_grad(t[j].z));
+                            r[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) * gelu_erf_grad(t[j].w));
+                        }
+                    }
                 }
                 if (res_row) {
                     float4 t[8];
@@ -708,15 +734,16 @@ bool gemm_tc_eligible(const GemmArgs& a) {
     if (a.beta != 0.f && a.C == nullptr) return false;
     if (a.n_store > 0) return gemm_tc_shape_ok(a.M, a.N, a.K) && a.C != nullptr && a.n_store <= a.N;     // scalar reduce-side epilogue
     return gemm_tc_shape_ok(a.M, a.N, a.K) && (a.ldc % 4) == 0 && al16(a.C) && al16(a.bias) && al16(a.colscale) &&
-           al16(a.pre) && (a.ldpre % 4) == 0 && al16(a.res) && (a.ldres % 4) == 0 && al16(a.preact);
+           al16(a.pre) && (a.ldpre % 4) == 0 && al16(a.res) && (a.ldres % 4) == 0 && al16(a.preact) && al16(a.dact_ref) &&
+           (a.lddact % 4) == 0;
 }
 
-template <int BN, bool MN>
+template <int BN, bool MN, bool DA = false>
 static int launch_tc(const GemmArgs& a, const PlaneOp& A, const PlaneOp& B, int splits, float* partials, cudaStream_t st) {
     static bool attr = false;
     static int sms = 148;
     if (!attr) {
-        RIFT_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<BN>::TOTAL));
+        RIFT_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, MN, DA>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<BN>::TOTAL));
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -741,16 +768,16 @@ static int launch_tc(const GemmArgs& a, const PlaneOp& A, const PlaneOp& B, int 
         g.splits = splits; g.kb_per_split = cdiv(num_kb, splits);
         g.splits = cdiv(num_kb, g.kb_per_split);
         g.C = partials; g.ldc = a.N; g.split_stride = (long long)a.M * a.N;
-        g.ep = TcEpilogue{nullptr, nullptr, nullptr, 0, 1, nullptr, 0, 1, 0, ACT_NONE, 0.f, 1.f, nullptr};
+        g.ep = TcEpilogue{nullptr, nullptr, nullptr, 0, 1, nullptr, 0, 1, 0, ACT_NONE, 0.f, 1.f, nullptr, nullptr, 0, 0};
         g.out = Planes();
     } else {
         g.splits = 1; g.kb_per_split = num_kb; g.split_stride = 0;
         g.C = a.C; g.ldc = a.ldc;
         g.ep = TcEpilogue{a.bias, a.colscale, a.pre, a.ldpre, a.pre_div, a.res, a.ldres, a.res_div, a.res_mod, a.act, a.beta,
-                          a.alpha, a.preact};
+                          a.alpha, a.preact, a.dact_ref, a.lddact, a.dact};
     }
     const int n_tiles = cdiv(a.N, BN) * cdiv(a.M, TC_BM) * g.splits;
-    launch_k(gemm_tc_kernel<BN, MN>, min(n_tiles, sms), TC_THREADS, TcSmem<BN>::TOTAL, st, *ma_hi, *ma_lo, *mb_hi, *mb_lo, g);
+    launch_k(gemm_tc_kernel<BN, MN, DA>, min(n_tiles, sms), TC_THREADS, TcSmem<BN>::TOTAL, st, *ma_hi, *ma_lo, *mb_hi, *mb_lo, g);
     RIFT_LAUNCH_OK();
     if (via_ws) {
         if (a.n_store > 0) { GemmArgs b = a; b.N = a.n_store; return launch_splitk_reduce(partials, g.splits, b, st, a.N); }
@@ -778,6 +805,11 @@ int launch_gemm_tc_ex(const GemmArgs& a, const PlaneOp& A, const PlaneOp& B, boo
     if (mn_major) {
         if (narrow) return launch_tc<64, true>(a, A, B, splits, partials, st);
         return launch_tc<128, true>(a, A, B, splits, partials, st);
+    }
+    if (a.dact_ref) {
+        RIFT_REQUIRE(splits <= 1 && a.n_store <= 0, "gemm_tc: fused activation backward needs the direct epilogue");
+        if (narrow) return launch_tc<64, false, true>(a, A, B, splits, partials, st);
+        return launch_tc<128, false, true>(a, A, B, splits, partials, st);
     }
     if (narrow) return launch_tc<64, false>(a, A, B, splits, partials, st);
     return launch_tc<128, false>(a, A, B, splits, partials, st);

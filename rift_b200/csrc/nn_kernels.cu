@@ -3,6 +3,8 @@
 // /root/reference/rift/cbv/planning/pluto/model/).
 #include <stdlib.h>
 
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "ops.h"
 
@@ -459,6 +461,50 @@ colsum_final2_kernel(const float* __restrict__ partial, int nb, int C, float* __
         float* out = blockIdx.y ? out1 : out0;
         out[c] += s;
     }
+}
+// first stage over a split-bf16 plane pair: value = hi + lo (16 mantissa bits, ample for a bias gradient)
+__global__ void __launch_bounds__(256)
+colsum_planes_partial_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, int Kp, int rows, int C,
+                             float* __restrict__ partial) {
+    pdl_grid_sync();
+    __shared__ float sm[8][65];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 64 + 2 * tx;              // two columns (one bf16x2 word per plane) per thread
+    const int stride = gridDim.y * 8;
+    float a0 = 0.f, a1 = 0.f;
+    if (c < C) {
+        for (int r = blockIdx.y * 8 + ty; r < rows; r += stride) {
+            const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(hi + (long long)r * Kp + c);
+            const __nv_bfloat162 l = *reinterpret_cast<const __nv_bfloat162*>(lo + (long long)r * Kp + c);
+            a0 += __bfloat162float(h.x) + __bfloat162float(l.x);
+            a1 += __bfloat162float(h.y) + __bfloat162float(l.y);
+        }
+    }
+    sm[ty][2 * tx] = a0; sm[ty][2 * tx + 1] = a1;
+    __syncthreads();
+    if (ty == 0) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int cc = c + u;
+            if (cc < C) {
+                float s2 = 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) s2 += sm[i][2 * tx + u];
+                partial[(long long)blockIdx.y * C + cc] = s2;
+            }
+        }
+    }
+}
+int launch_colsum_planes(const Planes& p, int rows, int C, float* out, int accumulate, float* scratch, cudaStream_t st,
+                         SideStream fin) {
+    if (C <= 0 || rows <= 0) return 0;
+    RIFT_REQUIRE(p.on() && (C % 2) == 0, "colsum_planes: planes required, C must be even");
+    const int chunks = cdiv(C, 64);
+    const int slabs = max(1, min(148, min(cdiv(rows, 32), cdiv(148 * 4, chunks))));
+    launch_k(colsum_planes_partial_kernel, dim3(chunks, slabs), 256, 0, st, reinterpret_cast<const __nv_bfloat16*>(p.hi),
+             reinterpret_cast<const __nv_bfloat16*>(p.lo), p.Kp, rows, C, scratch);
+    RIFT_LAUNCH_OK();
+    return launch_colsum_final(scratch, slabs, C, out, accumulate, st, fin);
 }
 int launch_colsum_final(const float* partial, int slabs, int C, float* out, int accumulate, cudaStream_t st, SideStream fin) {
     if (C <= 0 || slabs <= 0) return 0;

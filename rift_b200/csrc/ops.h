@@ -52,6 +52,9 @@ struct GemmArgs {
     float* split_ws = nullptr;           // [split_k, M, N] when split_k > 1
     float* preact = nullptr;             // optional copy of the value before `act` (same ldc), for backward
     Planes out_planes;                   // optional split-bf16 copy of the result (tcgen05 path; C may then be null)
+    // tcgen05 path, backward of an activation fused into the data-gradient product: the result is multiplied by
+    // act'(dact_ref[m, n]) (ReLU: dact_ref = the activation's OUTPUT; GELU: its pre-activation input), pitch lddact
+    const float* dact_ref = nullptr; long long lddact = 0; int dact = 0;
     int n_store = 0;                     // tcgen05 path: >0 = only the first n_store of the N (padded) columns are real; the
                                          // result then goes through the partial buffer and C / ldc need no alignment
 };
@@ -146,6 +149,9 @@ int launch_mask_logits(float* pi, const uint8_t* r_pad, long long rows, int Mo, 
 int launch_gather_rows(const float* x, long long ldx_batch, int bs, int row0, int nrows, int C, float* out, cudaStream_t st);
 int launch_colsum(const float* x, long long ldx, int rows, int C, float* out, int accumulate, float* scratch,
                   cudaStream_t st, SideStream fin = SideStream());
+// column sum of a split-bf16 plane pair (hi + lo), two-stage like launch_colsum; scratch: 148 * C floats
+int launch_colsum_planes(const Planes& p, int rows, int C, float* out, int accumulate, float* scratch, cudaStream_t st,
+                         SideStream fin = SideStream());
 // second stage alone: out[c] (+)= sum over `slabs` partial rows of pitch C
 int launch_colsum_final(const float* partial, int slabs, int C, float* out, int accumulate, cudaStream_t st,
                         SideStream fin = SideStream());
