@@ -343,8 +343,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
                     const int n = min(n0 + c0 + j, g.N - 4);     // clamped (N % 4 == 0, N >= 16)
-                    float4 v = make_float4(__uint_as_float(r[j]) * e.alpha, __uint_as_float(r[j + 1]) * e.alpha,
-                                           __uint_as_float(r[j + 2]) * e.alpha, __uint_as_float(r[j + 3]) * e.alpha);
+                    float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                           __uint_as_float(r[j + 3]));
+                    if (e.alpha != 1.f) { v.x *= e.alpha; v.y *= e.alpha; v.z *= e.alpha; v.w *= e.alpha; }
                     if (pre_row) { const float4 t = ld4(pre_row + n); v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
                     if (e.colscale) { const float4 t = ld4(e.colscale + n); v.x *= t.x; v.y *= t.y; v.z *= t.z; v.w *= t.w; }
                     if (e.bias) { const float4 t = ld4(e.bias + n); v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
@@ -412,12 +413,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                         r[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) + t[j].w);
                     }
                 }
+                if (mrow0 + 32 <= g.M && n0 + c0 + 32 <= g.N) {      // interior chunk (warp-uniform): nothing to zero
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const bool ok = row_ok && (n0 + c0 + j < g.N);
-                    sts4(tb_row + ((((uint32_t)j >> 2) ^ sw_row) << 4),
-                         make_float4(ok ? __uint_as_float(r[j]) : 0.f, ok ? __uint_as_float(r[j + 1]) : 0.f,
-                                     ok ? __uint_as_float(r[j + 2]) : 0.f, ok ? __uint_as_float(r[j + 3]) : 0.f));
+                    for (int j = 0; j < 32; j += 4)
+                        sts4(tb_row + ((((uint32_t)j >> 2) ^ sw_row) << 4),
+                             make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                         __uint_as_float(r[j + 3])));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const bool ok = row_ok && (n0 + c0 + j < g.N);
+                        sts4(tb_row + ((((uint32_t)j >> 2) ^ sw_row) << 4),
+                             make_float4(ok ? __uint_as_float(r[j]) : 0.f, ok ? __uint_as_float(r[j + 1]) : 0.f,
+                                         ok ? __uint_as_float(r[j + 2]) : 0.f, ok ? __uint_as_float(r[j + 3]) : 0.f));
+                    }
                 }
                 __syncwarp();
                 if (!(g.dbg & 8)) {
