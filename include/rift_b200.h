@@ -171,6 +171,11 @@ int rift_b200_op_linear(const float* x, int rows, int K, const float* w, const f
 size_t rift_b200_op_linear_tc_scratch_bytes(int rows, int N, int K);
 int rift_b200_op_linear_tc(const float* x, int rows, int K, const float* w, const float* bias, int N, int act,
                            const float* res, float* y, void* scratch, size_t scratch_bytes, int resplit, void* stream);
+/* every output form of the tensor-core epilogue: y = act(x w^T + bias) + res + beta * y (y may be NULL when planes are
+ * requested), preact (may be NULL) = value before `act`, out_hi / out_lo (may be NULL) = split-bf16 planes [rows, ceil64(N)] */
+int rift_b200_op_linear_tc_full(const float* x, int rows, int K, const float* w, const float* bias, int N, int act,
+                                const float* res, float* y, float beta, float* preact, void* out_hi, void* out_lo, void* scratch,
+                                size_t scratch_bytes, void* stream);
 int rift_b200_op_gemm(const float* A, long long sam, long long sak, const float* B, long long sbn, long long sbk,
                       float* C, long long ldc, int M, int N, int K, float beta, int split_k, float* split_ws,
                       int simt, void* stream);

@@ -86,6 +86,8 @@ _SIGNATURES = {
     "rift_b200_op_linear_tc_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "rift_b200_op_linear_tc": (C.c_int, [_V, C.c_int, C.c_int, _V, _V, C.c_int, C.c_int, _V, _V, _V, C.c_size_t,
                                          C.c_int, _V]),
+    "rift_b200_op_linear_tc_full": (C.c_int, [_V, C.c_int, C.c_int, _V, _V, C.c_int, C.c_int, _V, _V, C.c_float, _V, _V, _V, _V,
+                                              C.c_size_t, _V]),
     "rift_b200_op_gemm": (C.c_int, [_V, C.c_longlong, C.c_longlong, _V, C.c_longlong, C.c_longlong, _V, C.c_longlong,
                                     C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _V, C.c_int, _V]),
     "rift_b200_op_layernorm": (C.c_int, [_V, C.c_int, C.c_int, _V, _V, C.c_int, _V, _V, _V, _V]),

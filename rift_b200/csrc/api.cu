@@ -224,6 +224,34 @@ int rift_b200_op_linear_tc(const float* x, int rows, int K, const float* w, cons
     return launch_gemm_tc(a, ap, ap + aplane, tw.Kp, tw, 0, 0, S(stream));
 }
 
+// op_linear_tc with every output form of the epilogue: y (+)= beta * y, optional pre-activation copy and split-bf16 planes
+int rift_b200_op_linear_tc_full(const float* x, int rows, int K, const float* w, const float* bias, int N, int act,
+                                const float* res, float* y, float beta, float* preact, void* out_hi, void* out_lo, void* scratch,
+                                size_t scratch_bytes, void* stream) {
+    RIFT_REQUIRE(x && w && scratch && (y || (out_hi && out_lo)), "op_linear_tc_full: null argument");
+    RIFT_REQUIRE(scratch_bytes >= rift_b200_op_linear_tc_scratch_bytes(rows, N, K), "op_linear_tc_full: scratch too small");
+    TcWeight tw;
+    tw.src = w; tw.ld_src = K; tw.N = N; tw.K = K; tw.Kp = (K + 63) / 64 * 64;
+    const size_t plane = ((size_t)N * tw.Kp * 2 + 255) & ~(size_t)255;
+    char* p = static_cast<char*>(scratch);
+    tw.hi = p; tw.lo = p + plane;
+    std::vector<char> job(split_job_bytes());
+    fill_split_job(job.data(), w, K, N, K, tw.Kp, tw.hi, tw.lo, 0, 0);
+    RIFT_CUDA_OK(cudaMemcpyAsync(p + 2 * plane, job.data(), job.size(), cudaMemcpyHostToDevice, S(stream)));
+    RIFT_CUDA_OK(cudaStreamSynchronize(S(stream)));
+    int r = launch_split_weights(p + 2 * plane, 1, split_job_units(N, tw.Kp), S(stream));
+    if (r) return r;
+    GemmArgs a;
+    a.A = x; a.sam = K; a.B = w; a.sbn = K; a.C = y; a.ldc = N; a.M = rows; a.N = N; a.K = K;
+    a.bias = bias; a.act = act; a.res = res; a.ldres = N; a.beta = beta; a.preact = preact;
+    if (out_hi && out_lo) { a.out_planes.hi = static_cast<uint16_t*>(out_hi); a.out_planes.lo = static_cast<uint16_t*>(out_lo); a.out_planes.Kp = (N + 63) / 64 * 64; }
+    char* ap = p + 2 * plane + 512;
+    const size_t aplane = ((size_t)rows * tw.Kp * 2 + 255) & ~(size_t)255;
+    r = launch_pack_split(x, K, rows, K, tw.Kp, ap, ap + aplane, S(stream));
+    if (r) return r;
+    return launch_gemm_tc(a, ap, ap + aplane, tw.Kp, tw, 0, 0, S(stream));
+}
+
 int rift_b200_op_gemm(const float* A, long long sam, long long sak, const float* B, long long sbn, long long sbk, float* C,
                       long long ldc, int M, int N, int K, float beta, int split_k, float* split_ws, int simt, void* stream) {
     GemmArgs a;

@@ -497,6 +497,280 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     }
 }
 
+// ---------------------------------------------------------------------------------- v2: tall GEMMs
+// Variant for GEMMs with many M tiles per CTA and K <= KB_MAX * 64 (the history / PointNet encoders: 10^4..10^5 rows,
+// K <= 256).  Two changes against gemm_tc_kernel, which at these shapes sits at ~3 us per tile between the per-SM
+// L2 -> SMEM rate (256 KB of operand tiles per 128 x 128 tile) and the epilogue's instruction latency:
+//   * the CTA keeps ITS weight tile (all k-blocks of B hi / lo for one n-tile) resident in shared memory and walks the
+//     M tiles of that n-tile only, so the main loop streams just the A planes (half the bytes);
+//   * the epilogue leaves through TMA: the row phase parks the chunk in a swizzled shared-memory tile and one lane
+//     issues cp.async.bulk.tensor stores (cp.reduce ... add for beta = 1); M / N tails are clipped by the tensor map,
+//     so there are no per-lane loads, stores, predicates or address arithmetic in the store phase.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t smem_src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tm), "r"(smem_src), "r"(c0),
+                 "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* tm, uint32_t smem_src, int c0, int c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tm),
+                 "r"(smem_src), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void sts4u(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d));
+}
+
+constexpr int TC2_MAX_STAGES = 4;
+constexpr int TC2_EPI_BYTES = TC_EPI_WARPS * 4096;          // per-warp 32 x 32 fp32 (or 2 x 32 x 32 bf16) staging tile
+constexpr int TC2_A_STAGE = 2 * TC_BM * TC_BK * 2;          // A hi + lo of one k-block
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmP,
+                const __grid_constant__ CUtensorMap tmOh, const __grid_constant__ CUtensorMap tmOl, TcKernelArgs g, int stages) {
+    pdl_trigger();
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    constexpr int B_PLANE = BN * TC_BK * 2;                 // one bf16 plane of one k-block of the weight tile
+    constexpr int B_KB = 2 * B_PLANE;
+    const int num_kb = (g.K + TC_BK - 1) / TC_BK;
+    uint8_t* epi = smem;                                     // [8 warps][4 KB], 1024-aligned tiles
+    uint8_t* bres = smem + TC2_EPI_BYTES;                    // [num_kb][hi | lo]
+    uint8_t* astg = bres + num_kb * B_KB;                    // [stages][A hi | A lo]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(astg + stages * TC2_A_STAGE);
+    uint64_t* full = bars;                                   // [TC2_MAX_STAGES]
+    uint64_t* empty = bars + TC2_MAX_STAGES;                 // [TC2_MAX_STAGES]
+    uint64_t* b_full = bars + 2 * TC2_MAX_STAGES;            // weight tile landed
+    uint64_t* acc_full = b_full + 1;                         // [2]
+    uint64_t* acc_empty = acc_full + 2;                      // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_n = (g.N + BN - 1) / BN;
+    const int tiles_m = (g.M + TC_BM - 1) / TC_BM;
+    const int nt = blockIdx.x % tiles_n;                     // this CTA's n-tile (gridDim.x is a multiple of tiles_n)
+    const int mt0 = blockIdx.x / tiles_n, mt_step = gridDim.x / tiles_n;
+    const int n0 = nt * BN;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(b_full, 1);
+        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], TC_EPI_WARPS); }
+        fence_barrier_init();
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_lo) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB_lo) : "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            mbar_arrive_expect_tx(b_full, (uint32_t)(num_kb * B_KB));
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int kk = g.b_k0 + kb * TC_BK;
+#pragma unroll
+                for (int rb = 0; rb < BN / 64; ++rb) {
+                    const int mn = g.b_mn0 + n0 + rb * 64;
+                    tma_load_2d(bres + kb * B_KB + rb * TC_BOX, &tmB_hi, b_full, kk, mn);
+                    tma_load_2d(bres + kb * B_KB + B_PLANE + rb * TC_BOX, &tmB_lo, b_full, kk, mn);
+                }
+            }
+            int it = 0;
+            for (int mt = mt0; mt < tiles_m; mt += mt_step) {
+                const int m0 = mt * TC_BM;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % stages;
+                    const uint32_t ph = (it / stages) & 1;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    uint8_t* a_hi = astg + s * TC2_A_STAGE;
+                    uint8_t* a_lo = a_hi + TC_BM * TC_BK * 2;
+                    mbar_arrive_expect_tx(&full[s], TC2_A_STAGE);
+                    const int ka = g.a_k0 + kb * TC_BK;
+#pragma unroll
+                    for (int rb = 0; rb < TC_BM / 64; ++rb) {
+                        const int mn = g.a_mn0 + m0 + rb * 64;
+                        tma_load_2d(a_hi + rb * TC_BOX, &tmA_hi, &full[s], ka, mn);
+                        tma_load_2d(a_lo + rb * TC_BOX, &tmA_lo, &full[s], ka, mn);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BN, false);
+            mbar_wait(b_full, 0);
+            tc_fence_after();
+            int it = 0, ti = 0;
+            for (int mt = mt0; mt < tiles_m; mt += mt_step, ++ti) {
+                const int buf = ti & 1;
+                mbar_wait(&acc_empty[buf], ((ti >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t tacc = tmem_base + (uint32_t)(buf * BN);
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % stages;
+                    const uint32_t ph = (it / stages) & 1;
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    const uint32_t a_hi = smem_u32(astg + s * TC2_A_STAGE);
+                    const uint32_t a_lo = a_hi + TC_BM * TC_BK * 2;
+                    const uint32_t b_hi = smem_u32(bres + kb * B_KB);
+                    const uint32_t b_lo = b_hi + B_PLANE;
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 16; ++k) {
+                        const uint64_t dah = make_sdesc(a_hi + k * 32u, 0), dal = make_sdesc(a_lo + k * 32u, 0);
+                        const uint64_t dbh = make_sdesc(b_hi + k * 32u, 0), dbl = make_sdesc(b_lo + k * 32u, 0);
+                        umma_bf16(tacc, dal, dbh, idesc, (kb > 0 || k > 0) ? 1u : 0u);     // small terms first
+                        umma_bf16(tacc, dah, dbl, idesc, 1);
+                        umma_bf16(tacc, dah, dbh, idesc, 1);
+                    }
+                    umma_commit(&empty[s]);
+                }
+                umma_commit(&acc_full[buf]);
+            }
+        }
+    } else {
+        // ===================== epilogue (8 warps) =====================
+        const int ew = warp - 2;
+        const int quarter = warp & 3;
+        const int half = ew >> 2;
+        const TcEpilogue& e = g.ep;
+        const uint32_t tb = smem_u32(epi + ew * 4096);
+        const uint32_t tb_row = tb + (uint32_t)lane * 128u;                      // fp32 tile: my row (128 B, SWIZZLE_128B)
+        const uint32_t sw128 = (uint32_t)(lane & 7);
+        const uint32_t tb_hrow = tb + (uint32_t)lane * 64u;                      // bf16 tiles: my row (64 B, SWIZZLE_64B)
+        const uint32_t sw64 = (uint32_t)(lane >> 1) & 3u;
+        const bool has_c = g.C != nullptr, has_p = e.preact != nullptr, has_o = g.out.on();
+        int ti = 0;
+        for (int mt = mt0; mt < tiles_m; mt += mt_step, ++ti) {
+            const int m0 = mt * TC_BM;
+            const int buf = ti & 1;
+            mbar_wait(&acc_full[buf], (ti >> 1) & 1);
+            tc_fence_after();
+            const int mrow0 = m0 + quarter * 32;
+            const int mc = min(mrow0 + lane, g.M - 1);
+            const float* pre_row = e.pre ? e.pre + (long long)(mc / e.pre_div) * e.ldpre : nullptr;
+            const float* res_row = nullptr;
+            if (e.res) res_row = e.res + (long long)(e.res_mod > 0 ? (mc % e.res_mod) : (mc / e.res_div)) * e.ldres;
+#pragma unroll 1
+            for (int cc = 0; cc < BN / 2; cc += 32) {
+                const int c0 = half * (BN / 2) + cc;
+                uint32_t r[32];
+                tmem_ld_32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN + c0), r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const int n = min(n0 + c0 + j, g.N - 4);
+                    float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                           __uint_as_float(r[j + 3]));
+                    if (pre_row) { const float4 t = ld4(pre_row + n); v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
+                    if (e.colscale) { const float4 t = ld4(e.colscale + n); v.x *= t.x; v.y *= t.y; v.z *= t.z; v.w *= t.w; }
+                    if (e.bias) { const float4 t = ld4(e.bias + n); v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
+                    r[j] = __float_as_uint(v.x); r[j + 1] = __float_as_uint(v.y);
+                    r[j + 2] = __float_as_uint(v.z); r[j + 3] = __float_as_uint(v.w);
+                }
+                if (has_p) {                                     // value before the activation (saved for backward)
+                    if (lane == 0) tma_wait_read();
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) sts4u(tb_row + ((((uint32_t)j >> 2) ^ sw128) << 4), r[j], r[j + 1], r[j + 2], r[j + 3]);
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) { tma_store_2d(&tmP, tb, n0 + c0, mrow0); tma_commit(); }
+                }
+                if (e.act == ACT_RELU) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(fmaxf(__uint_as_float(r[j]), 0.f));
+                } else if (e.act == ACT_GELU) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(gelu_erf(__uint_as_float(r[j])));
+                }
+                if (res_row) {
+                    float4 t[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) t[j] = ld4(res_row + min(n0 + c0 + 4 * j, g.N - 4));
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        r[4 * j] = __float_as_uint(__uint_as_float(r[4 * j]) + t[j].x);
+                        r[4 * j + 1] = __float_as_uint(__uint_as_float(r[4 * j + 1]) + t[j].y);
+                        r[4 * j + 2] = __float_as_uint(__uint_as_float(r[4 * j + 2]) + t[j].z);
+                        r[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) + t[j].w);
+                    }
+                }
+                if (has_c) {
+                    if (lane == 0) tma_wait_read();
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) sts4u(tb_row + ((((uint32_t)j >> 2) ^ sw128) << 4), r[j], r[j + 1], r[j + 2], r[j + 3]);
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (e.beta != 0.f) tma_reduce_add_2d(&tmC, tb, n0 + c0, mrow0);
+                        else tma_store_2d(&tmC, tb, n0 + c0, mrow0);
+                        tma_commit();
+                    }
+                }
+                if (has_o) {
+                    // split-bf16 planes of the result: hi tile at tb, lo tile at tb + 2 KB (32 rows x 64 B each);
+                    // columns >= N must be zero (they are the planes' padding up to Kp)
+                    if (n0 + c0 + 32 > g.N) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) if (n0 + c0 + j >= g.N) r[j] = 0u;
+                    }
+                    if (lane == 0) tma_wait_read();
+                    __syncwarp();
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        uint32_t hw[4], lw[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const float a = __uint_as_float(r[8 * q + 2 * u]), b = __uint_as_float(r[8 * q + 2 * u + 1]);
+                            const __nv_bfloat16 h0 = __float2bfloat16_rn(a), h1 = __float2bfloat16_rn(b);
+                            __nv_bfloat162 hh = __halves2bfloat162(h0, h1);
+                            __nv_bfloat162 ll = __floats2bfloat162_rn(a - __bfloat162float(h0), b - __bfloat162float(h1));
+                            hw[u] = *reinterpret_cast<uint32_t*>(&hh);
+                            lw[u] = *reinterpret_cast<uint32_t*>(&ll);
+                        }
+                        const uint32_t off = (((uint32_t)q ^ sw64) << 4);
+                        sts4u(tb_hrow + off, hw[0], hw[1], hw[2], hw[3]);
+                        sts4u(tb_hrow + 2048u + off, lw[0], lw[1], lw[2], lw[3]);
+                    }
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&tmOh, tb, n0 + c0, mrow0);
+                        tma_store_2d(&tmOl, tb + 2048u, n0 + c0, mrow0);
+                        tma_commit();
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        }
+        if (lane == 0) tma_wait_all();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 2 * BN);
+    }
+}
+
 // ---------------------------------------------------------------------------------- operand planes
 // fp32 [M, K] (row pitch ld) -> bf16 planes hi / lo [M, Kp], zero padded to Kp
 __global__ void __launch_bounds__(256)
@@ -735,6 +1009,103 @@ static int plane_map(const void* plane, int rows, int pitch, const CUtensorMap**
     return 0;
 }
 
+// output-side tensor maps of the v2 kernel: fp32 [rows, cols] (row pitch ld floats) with a 32 x 32 box / 128 B swizzle,
+// bf16 plane [rows, Kp] with a 32 x 32 box / 64 B swizzle
+struct OutMapKey {
+    const void* p; long long rows, cols, pitch; int kind;
+    bool operator==(const OutMapKey& o) const { return p == o.p && rows == o.rows && cols == o.cols && pitch == o.pitch && kind == o.kind; }
+};
+struct OutMapKeyHash {
+    size_t operator()(const OutMapKey& k) const {
+        return std::hash<const void*>()(k.p) ^ (std::hash<long long>()((k.rows << 24) ^ (k.cols << 8) ^ k.pitch ^ k.kind) * 1000003u);
+    }
+};
+static int out_map(const void* ptr, long long rows, long long cols, long long pitch_elems, int kind /*0 fp32, 1 bf16*/,
+                   const CUtensorMap** out) {
+    static std::unordered_map<OutMapKey, MapVal, OutMapKeyHash> cache;
+    OutMapKey key{ptr, rows, cols, pitch_elems, kind};
+    auto it = cache.find(key);
+    if (it == cache.end()) {
+        if (cache.size() > 65536) cache.clear();
+        auto enc = get_encode();
+        RIFT_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+        MapVal v;
+        cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+        cuuint64_t strides[1] = {(cuuint64_t)pitch_elems * (kind ? 2 : 4)};
+        cuuint32_t box[2] = {32, 32};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = enc(reinterpret_cast<CUtensorMap*>(v.m), kind ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                         const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         kind ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        RIFT_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (output) failed (" + std::to_string((int)r) + ")");
+        it = cache.emplace(key, v).first;
+    }
+    *out = reinterpret_cast<const CUtensorMap*>(it->second.m);
+    return 0;
+}
+
+// does the weight-resident / TMA-store variant take this GEMM?  (tall: at least two M tiles per CTA; K small enough
+// for the weight tile to stay in shared memory; only the epilogue forms it implements)
+static bool tc2_takes(const GemmArgs& a, int BN, int sms) {
+    static const bool off = [] { const char* e = getenv("RIFT_B200_GEMM_V2"); return e && atoi(e) == 0; }();
+    if (off) return false;
+    const int num_kb = cdiv(a.K, TC_BK);
+    const long long tiles = (long long)cdiv(a.M, TC_BM) * cdiv(a.N, BN);
+    const int b_bytes = num_kb * 2 * BN * TC_BK * 2;
+    const int stages_fit = (227 * 1024 - 1024 - 256 - TC2_EPI_BYTES - b_bytes) / TC2_A_STAGE;
+    static const int min_stages = [] { const char* e = getenv("RIFT_B200_GEMM_V2_MIN_STAGES"); return e ? atoi(e) : 3; }();
+    return tiles >= 2LL * sms && stages_fit >= min_stages && a.alpha == 1.f && (a.beta == 0.f || a.beta == 1.f) && !a.dact_ref && a.n_store <= 0 &&
+           cdiv(a.N, BN) <= sms;
+}
+
+template <int BN>
+static int launch_tc2(const GemmArgs& a, const PlaneOp& A, const PlaneOp& B, cudaStream_t st) {
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+    const int num_kb = cdiv(a.K, TC_BK);
+    const int b_bytes = num_kb * 2 * BN * TC_BK * 2;
+    int stages = (227 * 1024 - 1024 - 256 - TC2_EPI_BYTES - b_bytes) / TC2_A_STAGE;
+    if (stages > TC2_MAX_STAGES) stages = TC2_MAX_STAGES;
+    const size_t smem = 1024 + TC2_EPI_BYTES + (size_t)b_bytes + (size_t)stages * TC2_A_STAGE + 256;
+    static bool attr = false;
+    if (!attr) {
+        RIFT_CUDA_OK(cudaFuncSetAttribute(gemm_tc2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr = true;
+    }
+    const CUtensorMap *ma_hi, *ma_lo, *mb_hi, *mb_lo, *mc = nullptr, *mp = nullptr, *moh = nullptr, *mol = nullptr;
+    int r;
+    if ((r = plane_map(A.hi, A.rows, A.pitch, &ma_hi))) return r;
+    if ((r = plane_map(A.lo, A.rows, A.pitch, &ma_lo))) return r;
+    if ((r = plane_map(B.hi, B.rows, B.pitch, &mb_hi))) return r;
+    if ((r = plane_map(B.lo, B.rows, B.pitch, &mb_lo))) return r;
+    if (a.C && (r = out_map(a.C, a.M, a.N, a.ldc, 0, &mc))) return r;
+    if (a.preact && (r = out_map(a.preact, a.M, a.N, a.ldc, 0, &mp))) return r;
+    if (a.out_planes.on()) {
+        if ((r = out_map(a.out_planes.hi, a.M, a.out_planes.Kp, a.out_planes.Kp, 1, &moh))) return r;
+        if ((r = out_map(a.out_planes.lo, a.M, a.out_planes.Kp, a.out_planes.Kp, 1, &mol))) return r;
+    }
+    // unused maps still need a valid object to copy into parameter space
+    if (!mc) mc = ma_hi;
+    if (!mp) mp = ma_hi;
+    if (!moh) moh = ma_hi;
+    if (!mol) mol = ma_hi;
+    TcKernelArgs g;
+    g.M = a.M; g.N = a.N; g.K = a.K;
+    g.a_mn0 = A.mn0; g.a_k0 = A.k0; g.b_mn0 = B.mn0; g.b_k0 = B.k0;
+    g.out = a.out_planes;
+    g.trace = nullptr; g.dbg = 0;
+    g.splits = 1; g.kb_per_split = num_kb; g.split_stride = 0;
+    g.C = a.C; g.ldc = a.ldc;
+    g.ep = TcEpilogue{a.bias, a.colscale, a.pre, a.ldpre, a.pre_div, a.res, a.ldres, a.res_div, a.res_mod, a.act, a.beta,
+                      a.alpha, a.preact, nullptr, 0, 0};
+    const int tiles_n = cdiv(a.N, BN);
+    const int grid = (sms / tiles_n) * tiles_n;              // every n-tile gets the same number of CTAs
+    launch_k(gemm_tc2_kernel<BN>, grid, TC_THREADS, smem, st, *ma_hi, *ma_lo, *mb_hi, *mb_lo, *mc, *mp, *moh, *mol, g, stages);
+    RIFT_LAUNCH_OK();
+    return 0;
+}
+
 bool gemm_tc_shape_ok(int M, int N, int K) { return K >= 32 && N >= 16 && (N % 4) == 0 && M >= 64; }
 
 bool gemm_tc_eligible(const GemmArgs& a) {
@@ -814,6 +1185,16 @@ int launch_gemm_tc_ex(const GemmArgs& a, const PlaneOp& A, const PlaneOp& B, boo
     if (mn_major) {
         if (narrow) return launch_tc<64, true>(a, A, B, splits, partials, st);
         return launch_tc<128, true>(a, A, B, splits, partials, st);
+    }
+    if (!mn_major && splits <= 1) {
+        static int sms2 = 0;
+        if (!sms2) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms2, cudaDevAttrMultiProcessorCount, dev); if (sms2 <= 0) sms2 = 148; }
+        // the weight tile must leave room for >= 3 operand stages: fall back to 64-wide tiles when 128 do not fit
+        if (!narrow && tc2_takes(a, 128, sms2)) return launch_tc2<128>(a, A, B, st);
+        // (measured: 46080 x 256 x 256 runs 30.4 us on gemm_tc_kernel, 34.6 us here with 128-wide tiles / 2 stages and
+        //  38.5 us with 64-wide tiles / 4 stages, so that fallback is off unless asked for)
+        static const bool try64 = [] { const char* e = getenv("RIFT_B200_GEMM_V2_TRY64"); return e && atoi(e) != 0; }();
+        if ((narrow || try64) && tc2_takes(a, 64, sms2)) return launch_tc2<64>(a, A, B, st);
     }
     if (a.dact_ref) {
         RIFT_REQUIRE(splits <= 1 && a.n_store <= 0, "gemm_tc: fused activation backward needs the direct epilogue");

@@ -42,7 +42,9 @@ def test_linear_epilogues(rows, K, N, act):
 
 
 @pytest.mark.parametrize("rows,K,N", [(128, 64, 128), (64, 32, 16), (300, 256, 160), (1000, 132, 96), (4608, 512, 256),
-                                      (3328, 256, 1024), (129, 1024, 256), (46080, 256, 256), (777, 192, 64)])
+                                      (3328, 256, 1024), (129, 1024, 256), (46080, 256, 256), (777, 192, 64),
+                                      # tall shapes: the weight-resident / TMA-store variant (ragged M, N = 3 x 64, N tail)
+                                      (40961, 64, 192), (20000, 128, 384), (41000, 192, 64), (37900, 256, 200)])
 @pytest.mark.parametrize("act", [0, 2])
 def test_linear_tcgen05_split_bf16(rows, K, N, act):
     """tcgen05 GEMM (A split in-kernel, W pre-split planes via TMA, 3 bf16 MMAs per k-step) vs fp32."""
@@ -54,6 +56,30 @@ def test_linear_tcgen05_split_bf16(rows, K, N, act):
     ref = TF.linear(x.double(), w.double(), b.double())
     ref = TF.gelu(ref) if act == 2 else ref
     close(y, ref + r.double(), 3e-5, "linear_tc")     # split-bf16: 16 mantissa bits per operand
+
+
+@pytest.mark.parametrize("rows,K,N", [(4608, 256, 256), (46081, 256, 256), (40960, 64, 192), (38000, 128, 72)])
+@pytest.mark.parametrize("act,beta", [(1, 0.0), (2, 0.0), (0, 1.0)])
+def test_linear_tcgen05_all_outputs(rows, K, N, act, beta):
+    """fp32 result (stored or accumulated), pre-activation copy and split-bf16 planes of both GEMM variants."""
+    x, w, b, r = rnd(rows, K, seed=1), rnd(N, K, seed=2, scale=K ** -0.5), rnd(N, seed=3), rnd(rows, N, seed=4)
+    y0 = rnd(rows, N, seed=5)
+    y = y0.clone()
+    Kp = (N + 63) // 64 * 64
+    pre = torch.full((rows, N), float("nan"), device="cuda")
+    hi = torch.full((rows, Kp), 0x7fc0, dtype=torch.int16, device="cuda")      # bf16 NaN pattern
+    lo = torch.full((rows, Kp), 0x7fc0, dtype=torch.int16, device="cuda")
+    L = _lib.lib()
+    scratch = torch.empty(L.rift_b200_op_linear_tc_scratch_bytes(rows, N, K), dtype=torch.uint8, device="cuda")
+    _lib.check(L.rift_b200_op_linear_tc_full(P(x), rows, K, P(w), P(b), N, act, P(r), P(y), beta, P(pre), P(hi), P(lo), P(scratch),
+                                             scratch.numel(), S()))
+    lin = TF.linear(x.double(), w.double(), b.double())
+    ref = (TF.relu(lin) if act == 1 else (TF.gelu(lin) if act == 2 else lin)) + r.double()
+    close(pre, lin, 3e-5, "pre-activation")
+    close(y, ref + beta * y0.double(), 3e-5, "result")
+    planes = hi.view(torch.bfloat16).double() + lo.view(torch.bfloat16).double()
+    close(planes[:, :N], ref, 3e-5, "planes")                 # the planes carry the result before beta * C
+    assert (planes[:, N:] == 0).all(), "plane padding must be zero"
 
 
 @pytest.mark.parametrize("layout", ["nt", "nn", "tn", "tt"])
