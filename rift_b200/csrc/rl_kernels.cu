@@ -11,6 +11,8 @@
 // All of these are HBM-bound byte movers: coalesced (vectorised where alignment allows) loads,
 // shared-memory staging of the group block, warp-shuffle reductions, fp64 with explicit
 // round-to-nearest intrinsics (no FMA contraction) where the reference computes in numpy float64.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ops.h"
 
@@ -82,16 +84,40 @@ __device__ double pw_sum8(const double* a, int n, int lane8, unsigned gmask) {
     return vals[0];
 }
 
+// x / d, correctly rounded (== __ddiv_rn), for a divisor shared by many quotients: y = RN(1 / d) once, then
+// q0 = RN(x y) and two FMA residual corrections.  q1 is a faithful quotient, so by Markstein's theorem q2 is the correctly
+// rounded one, provided y is the correctly rounded reciprocal, d's significand is not all ones and nothing leaves the
+// normal range (`ok` = the divisor passed that test; an operand outside +-2^400 takes the division itself).
+__device__ __forceinline__ bool div_shared_ok(double d) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(d);
+    const int e = (int)((b >> 52) & 0x7ff);
+    return e > 1023 - 400 && e < 1023 + 400 && (b & 0xFFFFFFFFFFFFFull) != 0xFFFFFFFFFFFFFull;
+}
+__device__ __forceinline__ double div_shared(double x, double d, double y, bool ok) {
+    const int xe = (int)(((unsigned long long)__double_as_longlong(x) >> 52) & 0x7ff);
+    if (ok && xe > 1023 - 400 && xe < 1023 + 400) {
+        const double q0 = __dmul_rn(x, y);
+        const double q1 = __fma_rn(__fma_rn(-d, q0, x), y, q0);
+        return __fma_rn(__fma_rn(-d, q1, x), y, q1);
+    }
+    return __ddiv_rn(x, d);                              // zero, subnormal, huge, inf, nan
+}
+
 // one group held in (shared or global) memory at x[0..n): writes adv to out[0..n)
 __device__ __forceinline__ void advantage_group8(double* x, double* out, int n, int lane8, unsigned gmask) {
     const double dn = (double)n;
-    const double mean = __ddiv_rn(pw_sum8<false>(x, n, lane8, gmask), dn);
+    const bool nok = div_shared_ok(dn);
+    const double yn = __drcp_rn(dn);
+    const double mean = div_shared(pw_sum8<false>(x, n, lane8, gmask), dn, yn, nok);
     for (int i = lane8; i < n; i += 8) out[i] = __dadd_rn(x[i], -mean);   // x - mean
     __syncwarp(gmask);
-    const double var = __ddiv_rn(pw_sum8<true>(out, n, lane8, gmask), dn);
+    const double var = div_shared(pw_sum8<true>(out, n, lane8, gmask), dn, yn, nok);
     const double sd = __dadd_rn(__dsqrt_rn(var), 1e-5);
     __syncwarp(gmask);
-    for (int i = lane8; i < n; i += 8) out[i] = __ddiv_rn(out[i], sd);
+    // __ddiv_rn costs ~25 dependent fp64 instructions per quotient; the shared-divisor form 5
+    const bool sok = div_shared_ok(sd);
+    const double ys = sok ? __drcp_rn(sd) : 0.0;
+    for (int i = lane8; i < n; i += 8) out[i] = div_shared(out[i], sd, ys, sok);
 }
 
 // Fixed group size: a block stages GPB groups through shared memory with 16-byte loads.
@@ -154,6 +180,152 @@ group_advantage_fixed_kernel(const double* __restrict__ ret, double* __restrict_
     }
 }
 
+// Fixed group size <= 128, warp-autonomous form: a warp owns four consecutive groups per pass (eight lanes each), stages
+// them through its PRIVATE slice of shared memory with fully coalesced 8-byte loads / stores and synchronises with
+// __syncwarp only - no block-wide barrier separates the load / compute / store phases of different warps - while the
+// next pass's elements are already in flight in registers (software prefetch).
+constexpr int ADVW_MAXJ = 16;                 // elements per lane per pass: ceil(4 * G / 32) <= 16  <=>  G <= 128
+
+__global__ void __launch_bounds__(ADV_THREADS)
+group_advantage_warp_kernel(const double* __restrict__ ret, double* __restrict__ adv, long long n_groups, int G, int Gp) {
+    pdl_grid_sync();
+    extern __shared__ double sm[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int lane8 = lane & 7, gl = lane >> 3;
+    const unsigned gmask = 0xFFu << (lane & ~7);
+    double* ws = sm + (size_t)wib * 4 * Gp;                        // this warp's four groups
+    const float invG = 1.f / (float)G;
+    const int per = 4 * G;                                         // elements per pass
+    const int nj = (per + 31) >> 5;
+    const long long n_quads = (n_groups + 3) >> 2;
+    const long long wstride = (long long)gridDim.x * (ADV_THREADS / 32);
+    long long quad = (long long)blockIdx.x * (ADV_THREADS / 32) + wib;
+    const long long total = n_groups * G;
+    double v[ADVW_MAXJ];
+    // element e of a pass -> (group e / G, position e % G) in the staged layout (no integer division: e < 2^10)
+    int slot[ADVW_MAXJ];
+#pragma unroll
+    for (int j = 0; j < ADVW_MAXJ; ++j) {
+        const int e = lane + 32 * j;
+        const int g = (int)(((float)e + 0.5f) * invG);
+        slot[j] = g * Gp + (e - g * G);
+    }
+    if (quad < n_quads) {
+        const long long base = quad * per;
+#pragma unroll
+        for (int j = 0; j < ADVW_MAXJ; ++j) {
+            const long long i = base + lane + 32 * j;
+            v[j] = (j < nj && lane + 32 * j < per && i < total) ? __ldg(ret + i) : 0.0;
+        }
+    }
+    for (; quad < n_quads; quad += wstride) {
+        const long long base = quad * per;
+        const int ng = (int)min(4LL, n_groups - quad * 4);
+#pragma unroll
+        for (int j = 0; j < ADVW_MAXJ; ++j)
+            if (j < nj && lane + 32 * j < per) ws[slot[j]] = v[j];
+        __syncwarp();
+        const long long nq = quad + wstride;                       // prefetch the next pass while this one computes
+        if (nq < n_quads) {
+            const long long nb = nq * per;
+#pragma unroll
+            for (int j = 0; j < ADVW_MAXJ; ++j) {
+                const long long i = nb + lane + 32 * j;
+                v[j] = (j < nj && lane + 32 * j < per && i < total) ? __ldg(ret + i) : 0.0;
+            }
+        }
+        if (gl < ng) {
+            double* x = ws + gl * Gp;
+            advantage_group8(x, x, G, lane8, gmask);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < ADVW_MAXJ; ++j) {
+            const long long i = base + lane + 32 * j;
+            if (j < nj && lane + 32 * j < per && i < total) adv[i] = ws[slot[j]];
+        }
+        __syncwarp();
+    }
+}
+
+// Fixed group size <= 128, ONE LANE PER GROUP: the per-group scalar work (two divisions by n, the square root, the
+// reciprocal - about half of all fp64 instructions when eight lanes share a group, because a warp instruction then
+// serves only four groups) is amortised over 32 groups per warp instruction, and numpy's eight accumulators are simply
+// eight registers of the lane (no shuffles).  A warp stages its 32 groups through a private shared-memory slice with
+// coalesced 8-byte loads / stores (row pitch Gp odd: lane-per-row accesses are conflict free); only __syncwarp is used.
+template <bool SQ>
+__device__ __forceinline__ double pw_leaf_lane(const double* x, int n) {        // numpy pairwise leaf, n <= 128
+    if (n < 8) {
+        double res = 0.0;
+        for (int i = 0; i < n; ++i) res = __dadd_rn(res, pw_term<SQ>(x, i));
+        return res;
+    }
+    double r[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r[k] = pw_term<SQ>(x, k);
+    const int nfull = n - (n & 7);
+    for (int i = 8; i < nfull; i += 8) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) r[k] = __dadd_rn(r[k], pw_term<SQ>(x, i + k));
+    }
+    double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                           __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+    for (int i = nfull; i < n; ++i) res = __dadd_rn(res, pw_term<SQ>(x, i));
+    return res;
+}
+
+constexpr int ADVL_THREADS = 128;
+
+__global__ void __launch_bounds__(ADVL_THREADS)
+group_advantage_lane_kernel(const double* __restrict__ ret, double* __restrict__ adv, long long n_groups, int G, int Gp) {
+    pdl_grid_sync();
+    extern __shared__ double sm[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    double* ws = sm + (size_t)wib * 32 * Gp;                       // this warp's 32 groups
+    const long long n_pass = (n_groups + 31) >> 5;
+    const long long wstride = (long long)gridDim.x * (ADVL_THREADS / 32);
+    const double dn = (double)G;
+    const bool nok = div_shared_ok(dn);
+    const double yn = __drcp_rn(dn);
+    for (long long pass = (long long)blockIdx.x * (ADVL_THREADS / 32) + wib; pass < n_pass; pass += wstride) {
+        const long long g0 = pass << 5;
+        const int ng = (int)min(32LL, n_groups - g0);
+        const long long base = g0 * G;
+        const int cnt = ng * G;
+        {   // coalesced global -> shared; (group, position) of element e tracked incrementally (e advances by 32)
+            int g = 0, k = lane;
+            while (k >= G) { k -= G; ++g; }
+            for (int e = lane; e < cnt; e += 32) {
+                ws[g * Gp + k] = __ldg(ret + base + e);
+                k += 32;
+                while (k >= G) { k -= G; ++g; }
+            }
+        }
+        __syncwarp();
+        if (lane < ng) {
+            double* x = ws + lane * Gp;
+            const double mean = div_shared(pw_leaf_lane<false>(x, G), dn, yn, nok);
+            for (int i = 0; i < G; ++i) x[i] = __dadd_rn(x[i], -mean);
+            const double var = div_shared(pw_leaf_lane<true>(x, G), dn, yn, nok);
+            const double sd = __dadd_rn(__dsqrt_rn(var), 1e-5);
+            const bool sok = div_shared_ok(sd);
+            const double ys = sok ? __drcp_rn(sd) : 0.0;
+            for (int i = 0; i < G; ++i) x[i] = div_shared(x[i], sd, ys, sok);
+        }
+        __syncwarp();
+        {
+            int g = 0, k = lane;
+            while (k >= G) { k -= G; ++g; }
+            for (int e = lane; e < cnt; e += 32) {
+                adv[base + e] = ws[g * Gp + k];
+                k += 32;
+                while (k >= G) { k -= G; ++g; }
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // Ragged groups (offsets[n_groups+1]); eight lanes per group straight from global memory.
 __global__ void __launch_bounds__(ADV_THREADS)
 group_advantage_ragged_kernel(const double* __restrict__ ret, const long long* __restrict__ offsets,
@@ -181,6 +353,33 @@ int launch_group_advantage(const double* ret, const long long* offsets, long lon
         RIFT_REQUIRE(G > 0, "group size must be positive");
         const int Gp = G | 1;                                   // odd stride: conflict-free 64-bit lanes
         const size_t smem = (size_t)ADV_GPB * Gp * sizeof(double);
+        static const bool block_form = getenv("RIFT_B200_ADV_BLOCK") != nullptr;
+        static const bool warp_form = getenv("RIFT_B200_ADV_WARP") != nullptr;
+        if (G <= 32 && n_groups >= 32768 && !block_form && !warp_form) {
+            // one lane per group: 4 warps x 32 groups staged per CTA.  Measured at 2^18 groups: G = 12: 31 vs 74 us,
+            // G = 24: 51 vs 76 us for the eight-lanes-per-group form below; from G = 36 on (94 vs 89 us) the staged
+            // rows cost too much occupancy and the eight-lane form wins (G = 72: 351 vs 105 us)
+            const size_t smem_l = (size_t)(ADVL_THREADS / 32) * 32 * Gp * sizeof(double);
+            static bool attr_l = false;
+            if (!attr_l) {
+                RIFT_CUDA_OK(cudaFuncSetAttribute(group_advantage_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                attr_l = true;
+            }
+            const long long n_pass = (n_groups + 31) / 32;
+            const int per_sm = (int)max((size_t)1, min((size_t)8, (size_t)(220 * 1024) / (smem_l + 1024)));
+            const int grid = (int)min((n_pass + 3) / 4, (long long)148 * per_sm);
+            launch_k(group_advantage_lane_kernel, grid, ADVL_THREADS, smem_l, st, ret, adv, n_groups, G, Gp);
+            RIFT_LAUNCH_OK();
+            return 0;
+        }
+        if (G <= 128 && !block_form) {
+            const long long n_quads = (n_groups + 3) / 4;
+            const int per_sm = (int)max((size_t)1, min((size_t)8, (size_t)(200 * 1024) / (smem + 1024)));
+            const int grid = (int)min((n_quads + 7) / 8, (long long)148 * per_sm);
+            launch_k(group_advantage_warp_kernel, grid, ADV_THREADS, smem, st, ret, adv, n_groups, G, Gp);
+            RIFT_LAUNCH_OK();
+            return 0;
+        }
         if (smem <= 200 * 1024) {
             static bool attr_done = false;
             if (!attr_done) {

@@ -56,6 +56,37 @@ def test_group_advantage_large_properties():
         assert np.array_equal(a[i], lo.group_advantage(r[i]))
 
 
+@pytest.mark.parametrize("G", [1, 5, 12, 24, 31, 32, 33, 36, 72, 128])
+def test_group_advantage_many_groups_bit_exact(G):
+    """Every kernel form (one lane per group for G <= 32, eight lanes per group up to 128) at a group count that selects
+    it, against numpy's vectorised expression (checked against the per-group oracle on a sample)."""
+    rng = np.random.Generator(np.random.PCG64(100 + G))
+    n = 40009
+    ret = rng.normal(-5.0, 20.0, (n, G))
+    ref = (ret - ret.mean(1, keepdims=True)) / (ret.std(1, keepdims=True) + 1e-5)
+    for i in (0, 1, 4099, n - 1):
+        assert np.array_equal(ref[i], lo.group_advantage(ret[i]))
+    adv = F.group_advantage(torch.from_numpy(ret).cuda()).cpu().numpy()
+    assert np.array_equal(adv, ref)
+
+
+def test_group_advantage_division_bit_exact_over_dynamic_range():
+    """The shared-divisor quotient (reciprocal + two FMA corrections, Markstein) must equal numpy's division bit for
+    bit: 2^17 groups whose scales span 2^-350 .. 2^350 (beyond the fast path's range on both sides), 1.5 M quotients."""
+    rng = np.random.Generator(np.random.PCG64(11))
+    n, G = 1 << 17, 12
+    scale = np.exp2(rng.uniform(-350.0, 350.0, (n, 1)))
+    ret = rng.normal(-0.25, 1.0, (n, G)) * scale
+    ret[5] = 0.0                                                   # zero spread: x - mean = 0, divisor 1e-5
+    ret[6, :6] = 0.0
+    with np.errstate(all="ignore"):
+        ref = (ret - ret.mean(1, keepdims=True)) / (ret.std(1, keepdims=True) + 1e-5)
+    for i in (0, 5, 6, 77, n - 1):                                 # the vectorised expression equals the per-group one
+        assert np.array_equal(ref[i], lo.group_advantage(ret[i]), equal_nan=True)
+    adv = F.group_advantage(torch.from_numpy(ret).cuda()).cpu().numpy()
+    assert np.array_equal(adv, ref, equal_nan=True)
+
+
 # ------------------------------------------------------------------ objectives
 def _rand_objective_inputs(bs, R, Mo, seed, ragged=True):
     rng = np.random.Generator(np.random.PCG64(seed))

@@ -9,8 +9,8 @@ peak = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "
     if os.path.exists("MEASURED_PEAKS.json") else 6650.0
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 rows = []
-for G in (12, 72):
-    for lg in (10, 12, 14, 16, 18, 20):
+for G in [int(x) for x in os.environ.get("ADV_G", "12,72").split(",")]:
+    for lg in [int(x) for x in os.environ.get("ADV_LG", "10,12,14,16,18,20").split(",")]:
         n = 1 << lg
         ret = (torch.randn(n, G, dtype=torch.float64, device="cuda") * 20 - 5)
         F.group_advantage(ret)
