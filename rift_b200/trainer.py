@@ -198,7 +198,9 @@ class LightningTrainer:
             if so is not None and so["position"].shape[1] != 0:
                 return self._train_core(batch)           # raises the documented NotImplementedError
         items = self._flatten_batch(batch, feats)
-        key = (isinstance(feats, PackedBatch),) + tuple((n, tuple(t.shape), t.dtype) for n, t in items)
+        # a PackedBatch is used in place as the graph's static input, so its identity is part of the signature (another
+        # PackedBatch object of the same shape gets its own graph instead of being copied over the first one)
+        key = (id(feats) if isinstance(feats, PackedBatch) else 0,) + tuple((n, tuple(t.shape), t.dtype) for n, t in items)
         g = self._graphs.get(key)
         if g is not None and g["ws_gen"] != self.model.ws_generation:
             del self._graphs[key]                        # the workspace moved: the captured pointers are stale
