@@ -265,7 +265,11 @@ inline int lin_bwd(Ctx& c, const float* X, long long ldx, const float* dY, long 
     // main stream depends on them before the final join of backward().
     const bool want_b = bias_grad && L.train && L.db;
     float* sc = nullptr;
-    if (want_b) { sc = c.alloc<float>((size_t)148 * L.N); if (!sc) { set_last_error("workspace too small"); return -1; } }
+    if (want_b) {
+        const size_t slabs_max = (size_t)(pack_colsum_slabs(M, tc_pitch(L.N)) > 148 ? pack_colsum_slabs(M, tc_pitch(L.N)) : 148);
+        sc = c.alloc<float>(slabs_max * L.N);
+        if (!sc) { set_last_error("workspace too small"); return -1; }
+    }
     Planes dYp;
     bool forked = false, bias_done = false;
     if (fz && fz->dYp_in && fz->dYp_in->on()) {

@@ -850,6 +850,10 @@ pack_split_colsum_kernel(const float* __restrict__ src, long long ld, int M, int
     }
 }
 
+int pack_colsum_slabs(int M, int Kp) {
+    const int chunks = cdiv(Kp, 128);
+    return max(1, min(cdiv(M, 16), cdiv(148 * 4, chunks)));
+}
 // returns the number of partial slabs through *slabs_out (0: the fused form does not apply, use the separate kernels)
 int launch_pack_split_colsum(const float* src, long long ld, int M, int K, int Kp, void* hi, void* lo, float* partial,
                              int* slabs_out, cudaStream_t st) {
@@ -858,7 +862,7 @@ int launch_pack_split_colsum(const float* src, long long ld, int M, int K, int K
     const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
     if (!vec) return 0;
     const int chunks = cdiv(Kp, 128);
-    const int slabs = max(1, min(148, min(cdiv(M, 16), cdiv(148 * 4, chunks))));
+    const int slabs = pack_colsum_slabs(M, Kp);      // four CTAs per SM in total: narrow inputs (one 128-column chunk) get up to 592 row slabs
     launch_k(pack_split_colsum_kernel, dim3(chunks, slabs), 256, 0, st, src, ld, M, K, Kp, static_cast<__nv_bfloat16*>(hi),
                                                                  static_cast<__nv_bfloat16*>(lo), partial);
     RIFT_LAUNCH_OK();

@@ -25,6 +25,7 @@ bool gemm_tc_eligible(const GemmArgs& a);
 int launch_pack_split(const float* src, long long ld, int M, int K, int Kp, void* hi, void* lo, cudaStream_t st);
 // the same pass also produces per-slab column partials [slabs][K] of src (bias gradient, finished by launch_colsum_final);
 // *slabs_out == 0 means the fused form does not apply (unaligned source) and nothing was launched
+int pack_colsum_slabs(int M, int Kp);       // rows of the partial buffer launch_pack_split_colsum writes (each K floats)
 int launch_pack_split_colsum(const float* src, long long ld, int M, int K, int Kp, void* hi, void* lo, float* partial,
                              int* slabs_out, cudaStream_t st);
 // C = epilogue(A B^T) with A = planes (a_hi, a_lo) [M, Kp] and B = weight planes rows [n0, n0+N), cols [k0, k0+K)
