@@ -2,16 +2,21 @@
 """Policy-update throughput benchmark (contract in the task statement).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--trainable pi_head|full]
+                    [--workload auto|cfg2|cfg4] [--scaling auto|strong|weak]
 
 One "step" = one policy update on one pre-collated synthetic rollout batch: PlanningModel forward
--> GRPO objective -> backward -> (N>1: one NCCL all-reduce of the flat gradient arena) ->
-clip_grad_norm_(0.5) -> AdamW.  Workload = BASELINE.json configs[1]: 64 scenes x 32 agents x 20
-polylines x 80 steps, R = 6 reference lines x 12 modes, Pluto-medium, GRPO.  Weak scaling: every
-rank holds its own 64-scene batch; `value` counts 64-scene batch-equivalents per second over all ranks.
+-> GRPO objective -> backward -> (N>1: NCCL all-reduce of the flat gradient arena) -> clip_grad_norm_(0.5)
+-> AdamW.  Which batch (BASELINE.json `configs`):
 
-`value`  : inputs already resident in HBM, CUDA events around each step, L2 flushed between steps.
+    N = 1        configs[1]  cfg2: 64 scenes x 32 agents x 20 polylines x 80 steps, R = 6 x 12 modes, Pluto-medium, GRPO
+    N = 2, 4     configs[2]  the SAME cfg2 batch split 32 / 16 scenes per rank           (strong scaling)
+    N = 8        configs[3]  cfg4: 256 scenes x 48 agents, 32 per rank, clip eps = 0.2 + 0.2 * KL-to-reference
+    --scaling weak           every rank holds its own full batch (also reported as `weak_scaling` at N > 1)
+
+`value`  : 64-scene batch equivalents per second over all ranks = (global scenes / 64) / (median step time);
+           inputs resident in HBM, CUDA events around each step, L2 flushed between steps, max over ranks.
 `e2e`    : the same step through LightningTrainer.step() starting from pinned HOST buffers (H2D of the
-           whole batch inside the timed region) and ending with the loss read back to the host.
+           rank's batch inside the timed region) and ending with the loss read back to the host.
 `--impl reference` : the CPU oracle port of the reference step on the host cores (torch CPU threads).
 """
 import argparse
@@ -34,9 +39,12 @@ from rift_b200.synth import synth_state_dict, synth_features, synth_rl_extras, W
 METRIC = "policy_update_steps_per_sec"
 UNIT = "steps/s (64-scene batch equivalents, all ranks)"
 TRAINER_KW = dict(lr=1e-4, cl_lr_decay=0.9, weight_decay=1e-5, epochs=16, warmup_epochs=3, frame_rate=10)
-# forward matmul+conv FLOPs of the reference modules for the cfg2 batch (FlopCounterMode)
-FWD_GFLOP = {"medium": 231.086, "small": 70.711}
-PI_HEAD_GFLOP = {"medium": 0.606, "small": 0.152}
+# forward matmul+conv FLOPs PER SAMPLE of the reference modules (FlopCounterMode), keyed by (model, A):
+# cfg2 shape (A = 32) and cfg4 shape (A = 48); the step is 3 x forward when the whole policy is differentiated
+FWD_GFLOP_PER_SAMPLE = {("medium", 32): 231.086 / 64, ("medium", 48): 1139.578 / 256,
+                        ("small", 32): 70.711 / 64, ("small", 48): 334.189 / 256}
+PI_HEAD_GFLOP_PER_SAMPLE = {"medium": 0.606 / 64, "small": 0.152 / 64}
+EXTRA_KEYS = ("group_advantage", "group_advantage_mask", "old_group_logits", "ref_group_logits")
 
 
 def trainable_layers(mode):
@@ -50,8 +58,17 @@ def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return d["hbm_gbs"], d["bf16_tflops_sustained"], "measured"
-    return 6650.0, 1400.0, "fallback"
+        return d["hbm_gbs"], d["bf16_tflops_sustained"], "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1400.0, "fallback (B200_PROFILING.md)"
+
+
+def step_gflop(wl, trainable, n_scenes):
+    f = FWD_GFLOP_PER_SAMPLE.get((wl["model"], wl["A"]))
+    if f is None:
+        return None
+    if trainable == "full":
+        return 3.0 * f * n_scenes
+    return (f + 3.0 * PI_HEAD_GFLOP_PER_SAMPLE[wl["model"]]) * n_scenes
 
 
 class ClockSampler:
@@ -65,7 +82,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -92,9 +109,18 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def host_batch(cfg, wl, seed):
+def tree_slice(tree, sl):
+    if isinstance(tree, dict):
+        return {k: tree_slice(v, sl) for k, v in tree.items()}
+    return np.ascontiguousarray(tree[sl])
+
+
+def host_batch(cfg, wl, seed, sl=None):
+    """The workload's synthetic batch (numpy); `sl` keeps one rank's scenes of it."""
     feats = synth_features(cfg, wl["bs"], wl["A"], wl["Mp"], wl["R"], seed=seed)
     ex = synth_rl_extras(cfg, feats, seed=seed + 1)
+    if sl is not None:
+        feats, ex = tree_slice(feats, sl), tree_slice(ex, sl)
     return feats, ex
 
 
@@ -119,18 +145,33 @@ def tree_bytes(tree):
 
 def make_batch_dict(feats_t, ex_t):
     b = {"cur_pluto_feature_torch": feats_t}
-    for k in ("group_advantage", "group_advantage_mask", "old_group_logits", "ref_group_logits"):
+    for k in EXTRA_KEYS:
         b[k + "_torch"] = ex_t[k]
     return b
 
 
+def pick_workload(args):
+    """BASELINE.json configs by GPU count (see the module docstring)."""
+    name = args.workload
+    if name == "auto":
+        name = "cfg4" if args.gpus >= 8 else "cfg2"
+    scaling = args.scaling
+    if scaling == "auto":
+        scaling = "strong" if args.gpus > 1 else "weak"
+    wl = dict(WORKLOADS[name])
+    if scaling == "strong" and wl["bs"] % args.gpus != 0:
+        raise SystemExit(f"--gpus {args.gpus} does not divide the {wl['bs']}-scene batch of {name}")
+    return name, wl, scaling
+
+
 # --------------------------------------------------------------------------------------------------
-def cpu_reference_step_time(cfg, wl, trainable, steps, warmup, threads):
+def cpu_reference_step_times(cfg, wl, trainable, steps, warmup, threads, n_scenes=None):
     """The oracle port of the reference step (forward, GRPO loss, autograd backward over the trainable
-    set, clip 0.5, AdamW) on the host cores.  Returns seconds per step (best of `steps`)."""
+    set, clip 0.5, AdamW) on the host cores, on the first `n_scenes` scenes of the workload's batch.
+    Returns (list of seconds per step, last loss)."""
     from oracle import pluto_oracle as po, loss_oracle as lo
     torch.set_num_threads(threads)
-    feats, ex = host_batch(cfg, wl, seed=1)
+    feats, ex = host_batch(cfg, wl, seed=1, sl=slice(0, n_scenes) if n_scenes else None)
     data, ext = to_torch(feats), to_torch(ex)
     sd = {k: torch.from_numpy(v) for k, v in synth_state_dict(cfg, seed=7).items()}
     from rift_b200.arena import trainable_names
@@ -140,6 +181,7 @@ def cpu_reference_step_time(cfg, wl, trainable, steps, warmup, threads):
     state = {}
     r_pad = ~data["reference_line"]["valid_mask"].any(-1)
     times = []
+    loss = None
     for i in range(warmup + steps):
         t0 = time.perf_counter()
         out = po.planning_model_forward(data, sd, cfg)
@@ -154,33 +196,125 @@ def cpu_reference_step_time(cfg, wl, trainable, steps, warmup, threads):
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
-    return min(times), float(loss.detach())
+    return times, float(loss.detach())
 
 
-def run_reference(args, wl_name, wl, cfg):
+def run_reference(args):
+    """Reference arm: the reference's own CPU implementation of the step (oracle port: a Python reference cannot
+    travel to the GPU box) on all host threads, honouring --steps / --warmup.  Each step is a bounded sample of the
+    workload: the first 64 scenes of the batch (= one 64-scene batch equivalent, the metric's unit)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    wl_name, wl, scaling = pick_workload(args)
+    cfg = MODEL_ZOO[wl["model"]](future_steps=wl["future_steps"])
     threads = os.cpu_count() or 1
-    steps = max(1, min(args.steps, 4))                 # bounded sample: a few whole steps of the same batch
-    warm = 1 if args.warmup > 0 else 0
-    sec, _ = cpu_reference_step_time(cfg, wl, args.trainable, steps, warm, threads)
-    v = 1.0 / sec
+    sample = min(64, wl["bs"])
+    times, _ = cpu_reference_step_times(cfg, wl, args.trainable, args.steps, args.warmup, threads, n_scenes=sample)
+    sec = float(np.median(times))
+    v = (sample / 64.0) / sec
     line = {
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl_name, **wl, "algo": "grpo", "trainable": args.trainable},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"best of {steps} whole policy updates of the {wl_name} batch after {warm} warm-up "
-                                   f"(oracle/ restatement of the reference's torch-CPU path; torch.set_num_threads({threads}))"},
+                         "sample": f"median of {args.steps} whole policy updates on the first {sample} scenes of the {wl_name} "
+                                   f"batch after {args.warmup} warm-up (oracle/ restatement of the reference's torch-CPU path; "
+                                   f"torch.set_num_threads({threads}))"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
 # --------------------------------------------------------------------------------------------------
-def run_ours(args, wl_name, wl, cfg):
+def timed_steps(tr, batch, steps, flush, sync):
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    sync()
+    loss = None
+    for s, e in evs:
+        flush.zero_()
+        s.record()
+        loss = tr.step(batch)
+        e.record()
+    sync()
+    return [s.elapsed_time(e) for s, e in evs], float(loss)
+
+
+def kernel_rooflines(L, _lib, dev, flush, wl, hbm, tf):
+    """Live CUDA-event timings of the step's time-dominant kernel family and of the cfg5 advantage kernel, each
+    replayed alone with the L2 flushed (algorithmic bytes per launch as defined in DESIGN.md section 4)."""
+    from rift_b200 import functional as F
+    out = {}
+
+    def time_it(fn, reps=20):
+        ks, ke = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ts = []
+        for _ in range(reps):
+            flush.zero_()
+            ks.record()
+            fn()
+            ke.record()
+            torch.cuda.synchronize()
+            ts.append(ks.elapsed_time(ke))
+        return float(np.median(ts))
+
+    # gemm_tc_kernel instances: the decoder-row class (bs*R*12 rows, 256 x 256: the most frequent launch of the step)
+    # and the largest launch (reference-line points, bs*R*120 rows)
+    for tag, rows in (("decoder_rows", wl["bs"] * wl["R"] * 12), ("refline_points", wl["bs"] * wl["R"] * 120)):
+        K = N = 256
+        x = torch.randn(rows, K, device=dev)
+        w = torch.randn(N, K, device=dev) * K ** -0.5
+        y = torch.empty(rows, N, device=dev)
+        scratch = torch.empty(L.rift_b200_op_linear_tc_scratch_bytes(rows, N, K), dtype=torch.uint8, device=dev)
+
+        def gemm_only(flag):     # 1: split W + pack A; 2: planes reused, only gemm_tc_kernel runs
+            _lib.check(L.rift_b200_op_linear_tc(_lib.ptr(x), rows, K, _lib.ptr(w), None, N, 1, None, _lib.ptr(y),
+                                                _lib.ptr(scratch), scratch.numel(), flag, _lib.stream_ptr()), "op_linear_tc")
+        gemm_only(1)
+        for _ in range(3):
+            gemm_only(2)
+        torch.cuda.synchronize()
+        ms = time_it(lambda: gemm_only(2))
+        alg = rows * K * 4 + rows * N * 4            # bf16 hi+lo planes of A in, fp32 C out, weights from L2
+        gbs = alg / (ms * 1e-3) / 1e9
+        tfl = 2.0 * rows * K * N / (ms * 1e-3) / 1e12
+        out[tag] = {"kernel": f"rift::gemm_tc_kernel {rows}x{K}x{N} (tcgen05 split-bf16 x3)", "kernel_ms": ms,
+                    "algorithmic_bytes": alg, "achieved_gbs": gbs, "frac_hbm": gbs / hbm,
+                    "tensor_tflops_algorithmic": tfl, "frac_tensor": tfl / tf}
+    # BASELINE configs[4]: group-relative advantage, 2^20 groups, G = 72 and 12 (16 * G bytes per group)
+    for G in (72, 12):
+        n = 1 << 20
+        ret = torch.randn(n, G, dtype=torch.float64, device=dev) * 20 - 5
+        F.group_advantage(ret)
+        torch.cuda.synchronize()
+        ms = time_it(lambda: F.group_advantage(ret), reps=10)
+        gbs = 16.0 * G * n / (ms * 1e-3) / 1e9
+        out[f"advantage_G{G}"] = {"kernel": f"rift::group_advantage 2^20 groups x {G} (fp64, bit-exact)", "kernel_ms": ms,
+                                  "algorithmic_bytes": 16 * G * n, "achieved_gbs": gbs, "frac_hbm": gbs / hbm}
+        del ret
+    return out
+
+
+DOMINANT = "decoder_rows"      # profiles/r1b_summary.md: gemm_tc_kernel<64> launches of this class = largest share of device time
+
+
+def dominant_roofline(kern, hbm, src):
+    k = kern.get(DOMINANT)
+    if not k:
+        return None
+    traffic = None          # dram bytes per launch of this kernel from the committed ncu --set full capture, if any
+    tpath = os.path.join(ROOT, "profiles", "r2_gemm_decoder_rows_ncu_full.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+    return {"bound": "hbm", "kernel": k["kernel"] + ", replayed alone, L2 flushed", "achieved": k["achieved_gbs"], "peak": hbm,
+            "unit": "GB/s", "frac": k["frac_hbm"], "traffic": traffic, "peak_source": src + " copy bandwidth",
+            "algorithmic_bytes": k["algorithmic_bytes"], "kernel_ms": k["kernel_ms"],
+            "tensor_tflops_algorithmic": k["tensor_tflops_algorithmic"], "tensor_frac_of_bf16_sustained": k["frac_tensor"],
+            "mma_work_factor": 3}
+
+
+def run_ours(args):
     import torch.distributed as dist
     from rift_b200 import _lib
     from rift_b200.planning_model import PlanningModel
@@ -208,24 +342,35 @@ def run_ours(args, wl_name, wl, cfg):
             os.dup2(saved_fd, 1)
             os.close(saved_fd)
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torch.distributed.run)"
+    wl_name, wl, scaling = pick_workload(args)
+    cfg = MODEL_ZOO[wl["model"]](future_steps=wl["future_steps"])
 
     model = PlanningModel.from_config(cfg, device=dev)
     model.load_state_dict({k: torch.from_numpy(v) for k, v in synth_state_dict(cfg, seed=7).items()})
-    tr = TRAINERS["grpo"](model, trainable_layers=trainable_layers(args.trainable), **TRAINER_KW)
+    # configs[3] names "PPO-clip eps = 0.2 with KL-to-reference penalty": the GRPO objective with clip (1 - eps, 1 + eps)
+    tr = TRAINERS["grpo"](model, trainable_layers=trainable_layers(args.trainable), clip=(0.8, 1.2), kl_weight=0.2, **TRAINER_KW)
     tr.configure_optimizers()
-
-    feats, ex = host_batch(cfg, wl, seed=1 + rank)                 # every rank its own scenes (weak scaling)
-    feats_h, ex_h = to_torch(feats, pin=True), to_torch(ex, pin=True)
-    keys = ("group_advantage", "group_advantage_mask", "old_group_logits", "ref_group_logits")
-    ex_h = {k: ex_h[k] for k in keys}
-    h2d = tree_bytes(feats_h) + tree_bytes(ex_h)
-    batch_dev = make_batch_dict(model.pack(to_device(feats_h, dev)), to_device(ex_h, dev))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
     def sync():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
+
+    def rank_batch(mode):
+        if mode == "strong":                  # one global batch, contiguous scene shards
+            per = wl["bs"] // world
+            feats, ex = host_batch(cfg, wl, seed=1, sl=slice(rank * per, (rank + 1) * per))
+        else:                                 # weak: every rank its own scenes
+            feats, ex = host_batch(cfg, wl, seed=1 + rank)
+        feats_h, ex_h = to_torch(feats, pin=True), to_torch(ex, pin=True)
+        ex_h = {k: ex_h[k] for k in EXTRA_KEYS}
+        return feats_h, ex_h
+
+    feats_h, ex_h = rank_batch(scaling)
+    scenes_global = wl["bs"] if scaling == "strong" else wl["bs"] * world
+    h2d = tree_bytes(feats_h) + tree_bytes(ex_h)
+    batch_dev = make_batch_dict(model.pack(to_device(feats_h, dev)), to_device(ex_h, dev))
 
     # ---- device-resident timing
     L = _lib.lib()
@@ -234,7 +379,7 @@ def run_ours(args, wl_name, wl, cfg):
     launches0 = L.rift_b200_launch_count()
     tr.step(batch_dev)
     launches = L.rift_b200_launch_count() - launches0
-    tr.use_cuda_graph = graph                 # then (default) forward + objective + backward replay from a CUDA graph
+    tr.use_cuda_graph = graph                 # then (default) the whole update replays from ONE CUDA graph
     for _ in range(args.warmup):
         tr.step(batch_dev)
     sync()
@@ -250,108 +395,83 @@ def run_ours(args, wl_name, wl, cfg):
         return
     sampler = ClockSampler(local)
     sampler.start()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    sync()
-    for s, e in evs:
-        flush.zero_()
-        s.record()
-        loss = tr.step(batch_dev)
-        e.record()
-    sync()
+    times, loss_val = timed_steps(tr, batch_dev, args.steps, flush, sync)
     clocks = sampler.stop()
-    ms = sum(s.elapsed_time(e) for s, e in evs) / args.steps
-    loss_val = float(loss)
+    ms_med, ms_mean = float(np.median(times)), float(np.mean(times))
 
     # ---- end to end: pinned host buffers -> H2D -> step -> loss on the host
-    e2e_steps = args.steps
-    # the trainer takes the pinned host batch as is: H2D copies (into the graph's static inputs, or by PackedBatch on
-    # the eager path) happen inside step(), i.e. inside the timed region
+    # the trainer takes the pinned host batch as is: H2D copies into the graph's static inputs happen inside step()
     host_batch_dict = make_batch_dict(feats_h, ex_h)
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(min(args.warmup, 5), 3)):
         float(tr.step(host_batch_dict))
     sync()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
+    e2e_t = []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
         float(tr.step(host_batch_dict))
+        e2e_t.append((time.perf_counter() - t0) * 1e3)
     sync()
-    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    e2e_ms = float(np.median(e2e_t))
 
-    # ---- dominant kernel live: the largest GEMM of the step, replayed alone under CUDA events
-    D = cfg.dim
-    rows, K, N = wl["bs"] * wl["R"] * 120, 256, 256         # PointsEncoder second_mlp.0 over reference-line points
-    x = torch.randn(rows, K, device=dev)
-    w = torch.randn(N, K, device=dev) * K ** -0.5
-    y = torch.empty(rows, N, device=dev)
-    scratch = torch.empty(L.rift_b200_op_linear_tc_scratch_bytes(rows, N, K), dtype=torch.uint8, device=dev)
-    reps = 20
-
-    def gemm_only(flag):     # flag 3: split W + pack A (first call); 0 afterwards: planes reused, only gemm_tc_kernel runs
-        _lib.check(L.rift_b200_op_linear_tc(_lib.ptr(x), rows, K, _lib.ptr(w), None, N, 1, None, _lib.ptr(y), _lib.ptr(scratch),
-                                            scratch.numel(), flag, _lib.stream_ptr()), "op_linear_tc")
-    gemm_only(1)
-    for _ in range(3):
-        gemm_only(2)
-    ks, ke = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    kt = 0.0
-    for _ in range(reps):
-        flush.zero_()
-        ks.record()
-        gemm_only(2)
-        ke.record()
-        torch.cuda.synchronize()
-        kt += ks.elapsed_time(ke)
-    kernel_ms = kt / reps
-    hbm, tf, src = peaks()
-    traffic = None          # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed ncu --set full capture
-    tpath = os.path.join(ROOT, "profiles", "r1b_gemm_big_ncu_full.json")
-    if os.path.exists(tpath) and (rows, K, N) == (46080, 256, 256):
-        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
-    kernel_tf = 2.0 * rows * K * N / (kernel_ms * 1e-3) / 1e12
-    # HBM view of the same launch: bf16 hi+lo planes of A (4 B/elem) in, fp32 C out, weights from L2
-    kernel_gbs = (rows * K * 4 + rows * N * 4) / (kernel_ms * 1e-3) / 1e9
+    # ---- secondary leg at N > 1: weak scaling (every rank its own full batch)
+    weak = None
+    if world > 1 and scaling == "strong" and not args.no_weak:
+        wf, we = rank_batch("weak")
+        wb = make_batch_dict(model.pack(to_device(wf, dev)), to_device(we, dev))
+        for _ in range(max(3, min(args.warmup, 5))):
+            tr.step(wb)
+        wt, _ = timed_steps(tr, wb, min(args.steps, 20), flush, sync)
+        weak = float(np.median(wt))
 
     # ---- max over ranks
-    t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_med, ms_mean, e2e_ms, weak or 0.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, e2e_ms = float(t[0]), float(t[1])
-    step_gflop = FWD_GFLOP[wl["model"]] * (3.0 if args.trainable == "full" else 1.0) + \
-        (3.0 * PI_HEAD_GFLOP[wl["model"]] if args.trainable == "pi_head" else 0.0)
+    ms_med, ms_mean, e2e_ms, weak_ms = (float(x) for x in t)
 
     if rank == 0:
-        threads = os.cpu_count() or 1
-        cpu_sec, _ = cpu_reference_step_time(cfg, wl, args.trainable, 2, 1, threads) if world == 1 and not args.no_cpu \
-            else (None, None)
+        hbm, tf, src = peaks()
+        kern = kernel_rooflines(L, _lib, dev, flush, dict(WORKLOADS["cfg2"]), hbm, tf) if not args.no_kernels else {}
+        gf = step_gflop(wl, args.trainable, scenes_global)
+        step_tf = gf / ms_med / world if gf else None            # GFLOP / ms = TFLOP/s, per GPU
+        value = (scenes_global / 64.0) * 1e3 / ms_med
         line = {
-            "metric": METRIC, "value": world * 1e3 / ms, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_med, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
             "dtype": "bf16x3 (split-bf16 tcgen05 operands, fp32 accumulate; fp32 master weights / activations)",
             "data": "synthetic",
-            "config": {"workload": wl_name, **wl, "algo": "grpo", "trainable": args.trainable,
-                       "l2": "256 MB memset between timed steps", "global_batch": wl["bs"] * world,
-                       "parallelism": f"dp{world}", "loss": loss_val,
-                       "launch": "forward + objective + backward replayed from one CUDA graph; all-reduce / clip / AdamW eager"
+            "config": {"workload": wl_name, **wl, "algo": "grpo", "clip": [0.8, 1.2], "kl_weight": 0.2,
+                       "trainable": args.trainable, "l2": "256 MB memset between timed steps",
+                       "global_batch": scenes_global, "per_rank_batch": scenes_global // world,
+                       "parallelism": f"dp{world}", "loss": loss_val, "timing": "median of per-step CUDA-event times",
+                       "ms_per_step_mean": ms_mean,
+                       "launch": "forward + objective + backward + all-reduce + clip + AdamW replayed from one CUDA graph"
                                  if graph else "eager launches",
-                       "step_gflop_algorithmic": step_gflop,
-                       "step_tensor_frac_of_peak": step_gflop / ms / tf},
+                       "step_gflop_algorithmic": gf, "step_tensor_frac_of_peak": (step_tf / tf) if gf else None},
             "clocks": clocks,
-            "e2e": {"value": world * 1e3 / e2e_ms, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
-                    "ms_per_step": e2e_ms},
+            "e2e": {"value": (scenes_global / 64.0) * 1e3 / e2e_ms, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": 8, "ms_per_step": e2e_ms},
             "gpu_launches": launches,
-            # K, N <= 1024 everywhere in this model: the GEMMs sit below the ridge point and are HBM-bound
-            "roofline": {"bound": "hbm", "kernel": "rift::gemm_tc_kernel<128,false> (tcgen05 split-bf16 GEMM, largest shape "
-                                                   f"of the step: {rows}x{K}x{N}, replayed alone, L2 flushed)",
-                         "achieved": kernel_gbs, "peak": hbm, "unit": "GB/s", "frac": kernel_gbs / hbm,
-                         "traffic": traffic, "peak_source": src + " copy bandwidth (MEASURED_PEAKS.json)",
-                         "algorithmic_bytes": rows * K * 4 + rows * N * 4, "kernel_ms": kernel_ms,
-                         "tensor_tflops_algorithmic": kernel_tf, "tensor_frac_of_bf16_sustained": kernel_tf / tf,
-                         "mma_work_factor": 3},
+            # `roofline`: the time-dominant kernel family of the step (profiles/: share of device time per kernel) replayed
+            # alone under CUDA events; `roofline_step`: the WHOLE update against the tensor roofline (algorithmic
+            # matmul + conv FLOPs of the step over the measured sustained bf16 rate); `kernels`: the other measured kernels
+            "roofline": dominant_roofline(kern, hbm, src),
+            "roofline_step": {"bound": "tensor", "kernel": "whole policy update (all kernels of the step)",
+                              "achieved": step_tf, "peak": tf, "unit": "TFLOP/s", "frac": (step_tf / tf) if gf else None,
+                              "mma_work_factor": 3, "peak_source": src},
+            "kernels": kern,
         }
-        if cpu_sec is not None:
+        if weak_ms > 0:
+            line["weak_scaling"] = {"value": world * (wl["bs"] / 64.0) * 1e3 / weak_ms, "unit": UNIT, "ms_per_step": weak_ms,
+                                    "global_batch": wl["bs"] * world}
+        if world == 1 and not args.no_cpu:
+            threads = os.cpu_count() or 1
+            sample = min(64, wl["bs"])
+            ct, _ = cpu_reference_step_times(cfg, wl, args.trainable, 5, 1, threads, n_scenes=sample)
+            sec = float(np.median(ct))
             line["cpu_baseline"] = {
-                "value": 1.0 / cpu_sec, "unit": UNIT, "cores": threads, "kind": "port",
-                "sample": f"best of 2 whole policy updates of the {wl_name} batch after 1 warm-up "
+                "value": (sample / 64.0) / sec, "unit": UNIT, "cores": threads, "kind": "port",
+                "sample": f"median of 5 whole policy updates on {sample} scenes of the {wl_name} batch after 1 warm-up "
                           f"(oracle/ restatement of the reference's torch-CPU path, {threads} threads)"}
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -361,24 +481,25 @@ def run_ours(args, wl_name, wl, cfg):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--trainable", default="full", choices=["pi_head", "full"],
                     help="full = differentiate the whole policy (headline, SURVEY 8d); pi_head = the reference's default "
                          "trainable_layers (rift_training.yaml:26-27)")
     ap.add_argument("--ncu", action="store_true", help="run one step inside cudaProfilerStart/Stop and exit (for ncu)")
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="auto", choices=["auto"] + sorted(WORKLOADS))
+    ap.add_argument("--scaling", default="auto", choices=["auto", "strong", "weak"])
     ap.add_argument("--no-cpu", dest="no_cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-weak", dest="no_weak", action="store_true", help="skip the secondary weak-scaling leg at N > 1")
+    ap.add_argument("--no-kernels", dest="no_kernels", action="store_true", help="skip the per-kernel roofline legs")
     ap.add_argument("--no-graph", dest="no_graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     args = ap.parse_args()
-    wl = dict(WORKLOADS[args.workload])
-    cfg = MODEL_ZOO[wl["model"]](future_steps=wl["future_steps"])
     if args.impl == "reference":
-        run_reference(args, args.workload, wl, cfg)
+        run_reference(args)
     else:
         args.warmup = max(args.warmup, 3)
-        run_ours(args, args.workload, wl, cfg)
+        run_ours(args)
 
 
 if __name__ == "__main__":

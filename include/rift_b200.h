@@ -112,6 +112,9 @@ size_t rift_b200_workspace_bytes(const rift_b200_engine* e, const rift_b200_batc
 size_t rift_b200_weight_cache_bytes(const rift_b200_engine* e);
 int rift_b200_bind_weight_cache(rift_b200_engine* e, void* cache, size_t bytes);
 int rift_b200_params_updated(rift_b200_engine* e, int trainable_only);
+/* re-split whatever rift_b200_params_updated marked stale NOW, on `stream` (a captured CUDA graph replays device
+ * work only: after a checkpoint load the frozen planes must be refreshed eagerly, not by the next eager forward) */
+int rift_b200_refresh_weights(rift_b200_engine* e, void* stream);
 
 /* flags */
 #define RIFT_B200_FWD_SAVE_FOR_BACKWARD 1   /* keep activations needed by rift_b200_backward in the workspace */
@@ -164,6 +167,15 @@ size_t rift_b200_optim_scratch_bytes(void);
 int rift_b200_clip_adamw(float* p, const float* g, float* m, float* v, long long n, long long n_decay,
                          const double* count, float max_norm, float lr, float beta1, float beta2, float eps,
                          float weight_decay, int step, void* scratch, float* scal_out, void* stream);
+/* Graph-capturable form of the same update: the learning rate and the number of updates applied so far live on the
+ * device.  hyper (device, 2 floats): [0] learning rate (the host rewrites it when WarmupCosLR steps, warmup_cos_lr.py:39-54),
+ * [1] updates applied so far (the kernel increments it).  A step whose `count` is <= 0 (no valid objective term: the
+ * reference's loss is then a constant and Lightning takes no optimizer step) leaves parameters, moments and the
+ * counter untouched.  scal_out (device, 8 floats) = { grad norm, applied scale, applied?, lr / bias1, sqrt(bias2),
+ * 1 - lr * wd, -, - }. */
+int rift_b200_clip_adamw_dev(float* p, const float* g, float* m, float* v, long long n, long long n_decay,
+                             const double* count, float max_norm, float* hyper, float beta1, float beta2, float eps,
+                             float weight_decay, void* scratch, float* scal_out, void* stream);
 
 /* ---- primitive operators exported for the kernel-level parity tests (tests/test_ops_gpu.py) ---- */
 int rift_b200_op_linear(const float* x, int rows, int K, const float* w, const float* bias, int N, int act,

@@ -169,3 +169,20 @@ def critic_ppo_cls():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod.CriticPPO
+
+
+def ref_class(relpath: str, name: str, extra_globals=None):
+    """Execute ONE top-level class of a reference file without importing the file (its module-level imports may
+    need hydra / lightning / carla).  Used for the datamodule collate callables and the rollout buffer."""
+    import ast
+    from typing import Dict, List, Optional
+    import numpy as np
+    src = open(os.path.join(REF, relpath)).read()
+    for node in ast.parse(src).body:
+        if isinstance(node, ast.ClassDef) and node.name == name:
+            g = {"torch": torch, "np": np, "Dict": Dict, "List": List, "Optional": Optional,
+                 "pad_sequence": torch.nn.utils.rnn.pad_sequence, "PlutoFeature": pluto_feature_cls()}
+            g.update(extra_globals or {})
+            exec(compile(ast.Module([node], []), relpath, "exec"), g)
+            return g[name]
+    raise KeyError(name)

@@ -79,6 +79,9 @@ _SIGNATURES = {
     "rift_b200_optim_scratch_bytes": (C.c_size_t, []),
     "rift_b200_clip_adamw": (C.c_int, [_V, _V, _V, _V, C.c_longlong, C.c_longlong, _V, C.c_float, C.c_float, C.c_float,
                                        C.c_float, C.c_float, C.c_float, C.c_int, _V, _V, _V]),
+    "rift_b200_clip_adamw_dev": (C.c_int, [_V, _V, _V, _V, C.c_longlong, C.c_longlong, _V, C.c_float, _V, C.c_float,
+                                           C.c_float, C.c_float, C.c_float, _V, _V, _V]),
+    "rift_b200_refresh_weights": (C.c_int, [_V, _V]),
     "rift_b200_op_linear": (C.c_int, [_V, C.c_int, C.c_int, _V, _V, C.c_int, C.c_int, _V, _V, C.c_int, _V]),
     "rift_b200_weight_cache_bytes": (C.c_size_t, [_V]),
     "rift_b200_bind_weight_cache": (C.c_int, [_V, _V, C.c_size_t]),

@@ -178,6 +178,19 @@ int rift_b200_clip_adamw(float* p, const float* g, float* m, float* v, long long
                              static_cast<double*>(scratch), scal_out, S(stream));
 }
 
+int rift_b200_clip_adamw_dev(float* p, const float* g, float* m, float* v, long long n, long long n_decay, const double* count,
+                             float max_norm, float* hyper, float beta1, float beta2, float eps, float weight_decay,
+                             void* scratch, float* scal_out, void* stream) {
+    RIFT_REQUIRE(p && g && m && v && scratch && scal_out && hyper, "clip_adamw_dev: null argument");
+    return launch_clip_adamw(p, g, m, v, n, n_decay, count, max_norm, 0.f, beta1, beta2, eps, weight_decay, 0,
+                             static_cast<double*>(scratch), scal_out, S(stream), hyper);
+}
+
+int rift_b200_refresh_weights(rift_b200_engine* e, void* stream) {
+    RIFT_REQUIRE(e && e->bound, "refresh_weights: bind_arena first");
+    return e->refresh_weights(S(stream));
+}
+
 // ---------------------------------------------------------------- primitive operators (tests)
 int rift_b200_op_linear(const float* x, int rows, int K, const float* w, const float* bias, int N, int act, const float* res,
                         float* y, int simt, void* stream) {

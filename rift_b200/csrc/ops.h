@@ -31,7 +31,7 @@ int launch_discounted_return(const float* rewards, const float* dones, int n, fl
 int optim_scratch_doubles();
 int launch_clip_adamw(float* p, const float* g, float* m, float* v, long long n, long long n_decay,
                       const double* count, float max_norm, float lr, float beta1, float beta2, float eps,
-                      float weight_decay, int step, double* scratch, float* scal, cudaStream_t st);
+                      float weight_decay, int step, double* scratch, float* scal, cudaStream_t st, float* hyper = nullptr);
 
 // ------------------------------------------------------------------ gemm (gemm_simt.cu / gemm_tc.cu)
 // C[m,n] = post( act( (sum_k A(m,k) B(n,k) + pre[m/pre_div, n]) * colscale[n] + bias[n] ) + res[m/res_div, n] ) + beta*C[m,n]

@@ -39,36 +39,60 @@ sumsq_partial_kernel(const float* __restrict__ g, long long n, double* __restric
     }
 }
 
-// stage 2: one warp folds the partials in a fixed order.
+// stage 2: one warp folds the partials in a fixed order and prepares every scalar of the update.
 // scal[0] = total L2 norm of the TRUE gradient (= grad_scale * raw), scal[1] = factor applied to raw
 // gradients in the update = grad_scale * min(1, max_norm / (norm + 1e-6))   (torch clip_grad_norm_)
 // grad_scale = 1 / count when `count` (device, double) is given (global masked-mean normalisation of
 // the objective, see rl_kernels.cu), else 1.
+// scal[2] = 1 when the update is applied, 0 when it is skipped: a batch without a single valid objective term
+// (count <= 0) has a constant loss in the reference, so Lightning takes no optimizer step - no weight decay, no
+// moment decay, no step-counter increment.  scal[3] = lr / (1 - beta1^step), scal[4] = sqrt(1 - beta2^step),
+// scal[5] = 1 - lr * weight_decay.
+// `hyper` (device, optional): [0] learning rate, [1] number of updates applied so far (incremented here when the
+// update is applied) - the graph-capturable form; without it lr / step come from the host arguments.
 __global__ void sumsq_finalize_kernel(const double* __restrict__ partial, int n_partial, const double* __restrict__ count,
-                                      float max_norm, float* __restrict__ scal) {
+                                      float max_norm, float* __restrict__ scal, float* __restrict__ hyper, float lr_host,
+                                      int step_host, float beta1, float beta2, float weight_decay) {
     pdl_grid_sync();
     double t = 0.0;
     for (int i = threadIdx.x; i < n_partial; i += 32) t += partial[i];
     t = warp_sum_d(t);
     if (threadIdx.x == 0) {
         float gs = 1.f;
-        if (count) gs = count[0] > 0.0 ? (float)(1.0 / count[0]) : 0.f;
+        bool apply = true;
+        if (count) { apply = count[0] > 0.0; gs = apply ? (float)(1.0 / count[0]) : 0.f; }
         const float norm = (float)sqrt(t) * gs;
         float coef = 1.f;
         if (max_norm > 0.f) coef = fminf(max_norm / (norm + 1e-6f), 1.f);
+        float lr = lr_host;
+        int step = step_host;
+        if (hyper) {
+            lr = hyper[0];
+            step = (int)hyper[1] + (apply ? 1 : 0);
+            hyper[1] = (float)step;
+        }
+        if (step < 1) step = 1;
+        // torch computes the bias corrections in Python doubles
+        const double bc1 = 1.0 - pow((double)beta1, (double)step);
+        const double bc2 = 1.0 - pow((double)beta2, (double)step);
         scal[0] = norm;
         scal[1] = gs * coef;
+        scal[2] = apply ? 1.f : 0.f;
+        scal[3] = lr / (float)bc1;
+        scal[4] = (float)sqrt(bc2);
+        scal[5] = 1.f - lr * weight_decay;
     }
 }
 
 __global__ void __launch_bounds__(256)
 adamw_apply_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                   long long n, long long n_decay, const float* __restrict__ scal, float lr, float beta1, float beta2,
-                   float eps, float weight_decay, float bc1, float sqrt_bc2) {
+                   long long n, long long n_decay, const float* __restrict__ scal, float beta1, float beta2, float eps) {
     pdl_grid_sync();
-    const float gscale = scal ? scal[1] : 1.f;
-    const float step_size = lr / bc1;
-    const float decay_keep = 1.f - lr * weight_decay;
+    if (scal[2] == 0.f) return;                               // skipped update (see sumsq_finalize_kernel)
+    const float gscale = scal[1];
+    const float step_size = scal[3];
+    const float sqrt_bc2 = scal[4];
+    const float decay_keep = scal[5];
     const long long n4 = n >> 2;
     float4* p4 = reinterpret_cast<float4*>(p);
     const float4* g4 = reinterpret_cast<const float4*>(g);
@@ -103,8 +127,8 @@ int optim_scratch_doubles() { return 148 * 4; }
 
 int launch_clip_adamw(float* p, const float* g, float* m, float* v, long long n, long long n_decay,
                       const double* count, float max_norm, float lr, float beta1, float beta2, float eps,
-                      float weight_decay, int step, double* scratch, float* scal, cudaStream_t st) {
-    RIFT_REQUIRE(step >= 1, "AdamW step counter starts at 1");
+                      float weight_decay, int step, double* scratch, float* scal, cudaStream_t st, float* hyper) {
+    RIFT_REQUIRE(hyper != nullptr || step >= 1, "AdamW step counter starts at 1");
     RIFT_REQUIRE((reinterpret_cast<uintptr_t>(p) & 15) == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0 &&
                  (reinterpret_cast<uintptr_t>(m) & 15) == 0 && (reinterpret_cast<uintptr_t>(v) & 15) == 0,
                  "optimizer arenas must be 16-byte aligned");
@@ -112,14 +136,10 @@ int launch_clip_adamw(float* p, const float* g, float* m, float* v, long long n,
     const int nb = (int)min((long long)optim_scratch_doubles(), (n / 4 + NORM_THREADS - 1) / NORM_THREADS + 1);
     launch_k(sumsq_partial_kernel, nb, NORM_THREADS, 0, st, g, n, scratch);
     RIFT_LAUNCH_OK();
-    launch_k(sumsq_finalize_kernel, 1, 32, 0, st, scratch, nb, count, max_norm, scal);
+    launch_k(sumsq_finalize_kernel, 1, 32, 0, st, scratch, nb, count, max_norm, scal, hyper, lr, step, beta1, beta2, weight_decay);
     RIFT_LAUNCH_OK();
-    // torch computes the bias corrections in Python doubles
-    const double bc1 = 1.0 - pow((double)beta1, (double)step);
-    const double bc2 = 1.0 - pow((double)beta2, (double)step);
     const int grid = (int)min((long long)148 * 8, (n / 4 + 255) / 256 + 1);
-    launch_k(adamw_apply_kernel, grid, 256, 0, st, p, g, m, v, n, n_decay, scal, lr, beta1, beta2, eps, weight_decay, (float)bc1,
-                                             (float)sqrt(bc2));
+    launch_k(adamw_apply_kernel, grid, 256, 0, st, p, g, m, v, n, n_decay, scal, beta1, beta2, eps);
     RIFT_LAUNCH_OK();
     return 0;
 }

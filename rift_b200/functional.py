@@ -154,7 +154,12 @@ def discounted_return(rewards, dones, gamma=0.98):
 # ------------------------------------------------------------------ optimizer apply
 class ClipAdamW:
     """clip_grad_norm_(max_norm) + torch.optim.AdamW semantics over one flat trainable range
-    (custom_lightning.yaml:40-41, rift_trainer.py:333-351).  The first `n_decay` elements decay."""
+    (custom_lightning.yaml:40-41, rift_trainer.py:333-351).  The first `n_decay` elements decay.
+
+    The learning rate and the count of applied updates live on the device (`hyper`), so ``step`` is pure device
+    work and can be captured into a CUDA graph; the scheduler-facing ``param_groups[0]["lr"]`` is pushed to the device
+    whenever it changed.  A step whose valid count is 0 is skipped entirely (no decay, no moment update, no counter
+    increment), like the reference, whose loss is a constant for such a batch."""
 
     def __init__(self, params: torch.Tensor, grads: torch.Tensor, n_train: int, n_decay: int, lr=1e-4,
                  weight_decay=1e-5, betas=(0.9, 0.999), eps=1e-8, max_norm=0.5):
@@ -162,19 +167,32 @@ class ClipAdamW:
         self.lr, self.weight_decay, self.betas, self.eps, self.max_norm = lr, weight_decay, betas, eps, max_norm
         self.m = torch.zeros(max(self.n, 4), dtype=torch.float32, device=params.device)
         self.v = torch.zeros_like(self.m)
-        self.step_count = 0
         self.scratch = torch.empty(_lib.lib().rift_b200_optim_scratch_bytes(), dtype=torch.uint8, device=params.device)
-        self.scal = torch.zeros(2, dtype=torch.float32, device=params.device)   # [grad norm, applied scale]
+        self.scal = torch.zeros(8, dtype=torch.float32, device=params.device)   # [grad norm, applied scale, applied?, ...]
+        self.hyper = torch.tensor([lr, 0.0], dtype=torch.float32, device=params.device)   # [lr, updates applied]
+        self._lr_on_device = lr
         self.param_groups = [{"lr": lr}]        # scheduler-facing, like torch optimizers
 
-    def step(self, count: Optional[torch.Tensor] = None):
+    @property
+    def step_count(self) -> int:
+        """Number of updates applied so far (device counter; reading it synchronises)."""
+        return int(self.hyper[1])
+
+    def sync_lr(self):
+        """Push a changed learning rate to the device (outside any graph capture)."""
+        lr = float(self.param_groups[0]["lr"])
+        if lr != self._lr_on_device:
+            self.hyper[0:1].fill_(lr)
+            self._lr_on_device = lr
+
+    def step(self, count: Optional[torch.Tensor] = None, sync_lr: bool = True):
         """count: optional device fp64 scalar; gradients are divided by it first (global valid count)."""
-        self.step_count += 1
-        lr = self.param_groups[0]["lr"]
-        _lib.check(_lib.lib().rift_b200_clip_adamw(
+        if sync_lr:
+            self.sync_lr()
+        _lib.check(_lib.lib().rift_b200_clip_adamw_dev(
             _lib.ptr(self.p), _lib.ptr(self.g), _lib.ptr(self.m), _lib.ptr(self.v), self.n, self.n_decay,
-            _lib.ptr(count), self.max_norm, lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
-            self.step_count, _lib.ptr(self.scratch), _lib.ptr(self.scal), _lib.stream_ptr()), "clip_adamw")
+            _lib.ptr(count), self.max_norm, _lib.ptr(self.hyper), self.betas[0], self.betas[1], self.eps,
+            self.weight_decay, _lib.ptr(self.scratch), _lib.ptr(self.scal), _lib.stream_ptr()), "clip_adamw_dev")
 
     def grad_norm(self) -> float:
         return float(self.scal[0])

@@ -166,6 +166,8 @@ class PlanningModel:
             sd = {k[len("model."):]: v for k, v in sd.items() if k.startswith("model.")}
         r = self.arena.load_state_dict(sd, strict)
         self.params_updated(False)
+        # eagerly: a captured CUDA graph replays device work only and would keep reading stale frozen planes
+        _lib.check(_lib.lib().rift_b200_refresh_weights(self._engine, _lib.stream_ptr()), "refresh_weights")
         return r
 
     def eval(self):
@@ -173,7 +175,9 @@ class PlanningModel:
         return self
 
     def train(self, mode=True):
-        self.training = mode      # numerics stay in the deterministic parity mode either way
+        """Numerics stay in the deterministic parity mode either way (Dropout / DropPath / state dropout identity,
+        BatchNorm running statistics, never updated); see LightningTrainer.train for the one-time warning."""
+        self.training = mode
         return self
 
     def to(self, device):

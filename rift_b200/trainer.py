@@ -27,9 +27,10 @@ def allreduce_grads_and_stats(grads: torch.Tensor, n_train: int, stats: torch.Te
     """The step's single collective: SUM all-reduce of [flat fp32 gradients | objective sum | valid count].
 
     The gradient arena has a 4-float tail after its n_train gradient elements; the two fp64 scalars travel
-    in it as (hi, lo) float pairs (hi = fp32(x), lo = fp32(x - hi): a 48-bit mantissa, exact for counts and
-    ample for the objective sum), so there is no second collective and no staging copy.
-    Returns the all-reduced (sum, count) as fp64."""
+    in it as (hi, lo) float pairs (hi = fp32(x), lo = fp32(x - hi)), so there is no second collective and no
+    staging copy.  The collective adds the hi parts of the ranks in fp32: valid counts (integers below 2^24) come
+    out exact, the objective sum - and with it the LOGGED loss - carries fp32 rounding (~1e-7 relative); the
+    parameter update only depends on the count.  Returns the all-reduced (sum, count) as fp64."""
     import torch.distributed as dist
     n = n_train
     comm = grads[:n + 4]
@@ -86,21 +87,30 @@ class LightningTrainer:
         self.clip, self.kl_weight, self.gradient_clip_val = clip, kl_weight, gradient_clip_val
         self.training = True
         self.logged: Dict[str, float] = {}
-        self.freeze_parameters(self.trainable_layers)
         self.optimizer: Optional[F.ClipAdamW] = None
         self.scheduler: Optional[WarmupCosLR] = None
+        self._graphs: Dict[tuple, dict] = {}
+        self._graph_seen: Dict[tuple, int] = {}
+        self.freeze_parameters(self.trainable_layers)
         self._count = None            # device fp64 valid count of the last training_step (group objectives)
         # CUDA-graph replay of forward + objective + backward (launch-bound: ~1.5k kernels per full update).
         # A batch signature (shapes / dtypes) is captured the second time it is seen; inputs are copied into the
         # graph's static buffers, so varying shapes simply stay on the eager path.  RIFT_B200_CUDA_GRAPH=0 disables.
         self.use_cuda_graph = bool(int(os.environ.get("RIFT_B200_CUDA_GRAPH", "1")))
-        self._graphs: Dict[tuple, dict] = {}
-        self._graph_seen: Dict[tuple, int] = {}
 
     # ------------------------------------------------------------------ reference surface
     def freeze_parameters(self, trainable_layers=("planning_decoder.pi_head",)):
-        """rift_trainer.py:78-90 — raises ValueError for an unknown layer name."""
+        """rift_trainer.py:78-90 — raises ValueError for an unknown layer name.
+
+        Re-lays out the parameter / gradient arenas, so an optimizer built for the previous trainable set (its
+        moments are sized and ordered for the old layout) is dropped: ``optimizer_step`` / ``configure_optimizers``
+        build a fresh one, exactly like the reference, where a new trainer always gets a new AdamW."""
         self.model.set_trainable_layers(trainable_layers)
+        self.optimizer = None
+        self.scheduler = None
+        self._invalidate_graphs()
+
+    def _invalidate_graphs(self):
         self._graphs = {}
         self._graph_seen = {}
 
@@ -108,6 +118,16 @@ class LightningTrainer:
         return self.model(features)
 
     def train(self, mode=True):
+        """Lightning's ``fit`` puts the module in train mode (dropout 0.1, drop-path 0.2, state-token dropout 0.75,
+        BatchNorm batch statistics).  This implementation always computes the deterministic parity mode
+        (DESIGN.md section 2): ``train(True)`` only selects training_step semantics and says so once."""
+        if mode and not getattr(LightningTrainer, "_warned_train_mode", False):
+            import warnings
+            warnings.warn("rift_b200 trains in the deterministic parity mode: Dropout / DropPath / state-token dropout are "
+                          "identity and BatchNorm uses (and does not update) its running statistics; the reference under "
+                          "Lightning's model.train() draws dropout masks and updates the BatchNorm buffers "
+                          "(DESIGN.md section 2)", stacklevel=2)
+            LightningTrainer._warned_train_mode = True
         self.training = mode
         return self
 
@@ -129,7 +149,12 @@ class LightningTrainer:
         return {"model." + k: v for k, v in self.model.state_dict().items()}
 
     def load_state_dict(self, sd, strict=True):
-        return self.model.load_state_dict(sd, strict)       # graphs stay valid: they read the arena in place
+        """Captured graphs read the fp32 arena in place but the FROZEN weights through their pre-split bf16 planes,
+        which a replay never re-splits: PlanningModel.load_state_dict refreshes every plane eagerly, and the graphs
+        are dropped anyway so that nothing captured before the load survives it."""
+        r = self.model.load_state_dict(sd, strict)
+        self._invalidate_graphs()
+        return r
 
     # ------------------------------------------------------------------ objectives
     @staticmethod
@@ -162,7 +187,9 @@ class LightningTrainer:
 
     def _step(self, batch, prefix: str):
         if self.training:
-            loss = self._graphed_core(batch) if self.use_cuda_graph else self._train_core(batch)
+            loss = self._graphed_core(batch) if self.use_cuda_graph else None
+            if loss is None:
+                loss = self._train_core(batch)
             loss = self._reduce(loss)
         else:
             res = self.model.forward(self._features(batch), outputs=(), save_for_backward=False)
@@ -190,17 +217,21 @@ class LightningTrainer:
         items += [("b." + k, v) for k, v in batch.items() if torch.is_tensor(v)]
         return items
 
-    def _graphed_core(self, batch):
+    def _graphed_core(self, batch, full_step: bool = False):
+        """Replay (capturing on second sight of a batch signature) forward + objective + backward - and, with
+        `full_step`, the gradient all-reduce, clip and AdamW as well (learning rate and step counter are device
+        scalars, optim_kernels.cu) - from one CUDA graph.  Returns None when this call has to run eagerly."""
         from .planning_model import PackedBatch
         feats = self._features(batch)
         if not isinstance(feats, PackedBatch):
             so = feats.get("static_objects")
             if so is not None and so["position"].shape[1] != 0:
-                return self._train_core(batch)           # raises the documented NotImplementedError
+                return None                              # the eager path raises the documented NotImplementedError
         items = self._flatten_batch(batch, feats)
         # a PackedBatch is used in place as the graph's static input, so its identity is part of the signature (another
         # PackedBatch object of the same shape gets its own graph instead of being copied over the first one)
-        key = (id(feats) if isinstance(feats, PackedBatch) else 0,) + tuple((n, tuple(t.shape), t.dtype) for n, t in items)
+        key = (bool(full_step), id(feats) if isinstance(feats, PackedBatch) else 0,) + \
+            tuple((n, tuple(t.shape), t.dtype) for n, t in items)
         g = self._graphs.get(key)
         if g is not None and g["ws_gen"] != self.model.ws_generation:
             del self._graphs[key]                        # the workspace moved: the captured pointers are stale
@@ -209,17 +240,22 @@ class LightningTrainer:
             seen = self._graph_seen.get(key, 0)
             self._graph_seen[key] = seen + 1
             if seen == 0 or len(self._graphs) >= 8:
-                return self._train_core(batch)           # first sight of this signature (or cache full): eager
-            g = self._capture(batch, feats, items, key)
+                return None                              # first sight of this signature (or cache full): eager
+            g = self._capture(batch, feats, items, key, full_step)
         # refresh the static inputs (skipped for tensors that already ARE the static ones: a device-resident PackedBatch)
         for (_, t), st in zip(items, g["static"]):
             if t.data_ptr() != st.data_ptr():
                 st.copy_(t, non_blocking=True)
+        if full_step:
+            self.optimizer.sync_lr()
         g["graph"].replay()
         self._stats = g["stats"]
+        if full_step:
+            self._count = g["count"]
+            self.model.params_updated(trainable_only=True)   # host flag: the next eager forward re-splits too
         return g["loss"].clone()                         # the graph's own output buffer is overwritten by the next replay
 
-    def _capture(self, batch, feats, items, key):
+    def _capture(self, batch, feats, items, key, full_step=False):
         from .planning_model import PackedBatch
         dev = self.model.device
         if isinstance(feats, PackedBatch):
@@ -241,16 +277,24 @@ class LightningTrainer:
                 st = t.to(dev, copy=True)
                 sbatch[n[2:]] = st
                 static.append(st)
+        if full_step and self.optimizer is None:
+            self.configure_optimizers()
         self.model.params_updated(trainable_only=True)   # the re-split of the trainable weight planes is part of the graph
         graph = torch.cuda.CUDAGraph()
         cap = torch.cuda.Stream(device=dev)
         cap.wait_stream(torch.cuda.current_stream(dev))
+        count = None
+        # thread_local: NCCL's watchdog thread keeps querying events while the data-parallel all-reduce is captured
         with torch.cuda.stream(cap):
-            with torch.cuda.graph(graph, stream=cap):
+            with torch.cuda.graph(graph, stream=cap, capture_error_mode="thread_local"):
                 loss = self._train_core(sbatch)
                 stats = self._stats
+                if full_step:
+                    loss = self._reduce(loss)
+                    count = self._count
+                    self.optimizer.step(count=count, sync_lr=False)
         torch.cuda.current_stream(dev).wait_stream(cap)
-        g = {"graph": graph, "static": static, "loss": loss, "stats": stats, "batch": sbatch,
+        g = {"graph": graph, "static": static, "loss": loss, "stats": stats, "batch": sbatch, "count": count,
              "ws_gen": self.model.ws_generation}
         self._graphs[key] = g
         return g
@@ -295,6 +339,14 @@ class LightningTrainer:
 
     # ------------------------------------------------------------------ loop for callers without Lightning
     def step(self, batch):
+        """One whole policy update.  With CUDA graphs on, the second and later sights of a batch signature replay
+        forward + objective + backward + all-reduce + clip + AdamW from ONE graph."""
+        if self.use_cuda_graph:
+            self.training = True
+            loss = self._graphed_core(batch, full_step=True)
+            if loss is not None:
+                self._last_loss = loss
+                return loss
         loss = self.training_step(batch)
         self.optimizer_step()
         return loss
@@ -329,7 +381,7 @@ class ReinforceTrainer(LightningTrainer):
         dev = self.model.device
         bs = res["probability"].shape[0]
         loss, dz, _ = F.action_objective("reinforce", res["probability"], res["r_padding_mask"],
-                                         batch["return_torch"].to(dev), global_batch=bs * self._world(),
+                                         batch["return_torch"].to(dev).float(), global_batch=bs * self._world(),
                                          need_grad=need_grad)
         self._stats = None
         return loss, dz

@@ -86,6 +86,58 @@ def test_collate_callables_produce_the_reference_keys():
     assert ReinforceCollate()(items)["return_torch"].shape == (3,)
 
 
+@pytest.mark.reference
+def test_collate_callables_match_reference_collates_by_value():
+    """a2: RIFT / GRPO / PPO / REINFORCE collates against the reference's own callables executed from
+    rift_datamodule.py:20-51, grpo_datamodule.py:20-57, ppo_datamodule.py:40-70, reinforce_datamodule.py:41-64
+    on ragged samples: every tensor torch.equal, same dtypes."""
+    from oracle import ref_shim
+    RefFeature = ref_shim.pluto_feature_cls()
+    base = "rift/cbv/planning/fine_tuner/rlft/"
+    ref_cls = {
+        "rift": ref_shim.ref_class(base + "rift_pluto/rift_datamodule.py", "RIFTCollate"),
+        "grpo": ref_shim.ref_class(base + "grpo_pluto/grpo_datamodule.py", "GRPOCollate"),
+        "ppo": ref_shim.ref_class(base + "ppo_pluto/ppo_datamodule.py", "PPOCollate"),
+        "reinforce": ref_shim.ref_class(base + "reinforce_pluto/reinforce_datamodule.py", "ReinforceCollate"),
+    }
+    ours_cls = {"rift": RIFTCollate, "grpo": GRPOCollate, "ppo": PPOCollate, "reinforce": ReinforceCollate}
+    samples = _samples(6, seed=9)
+    rng = np.random.default_rng(4)
+
+    def items(feature_cls, tensorise):
+        out = []
+        r2 = np.random.default_rng(4)
+        for d, A, Mp, R in samples:
+            vm = np.ones((R, 12), bool)
+            vm[R - 1, 6:] = R > 1            # a partly valid last line
+            f = feature_cls(data=d)
+            out.append({"CBVs_obs": {"raw_pluto_feature": f.to_feature_tensor() if tensorise else f},
+                        "CBVs_group_advantage": {"advantage": r2.normal(size=(R, 12)), "valid_mask": vm},
+                        "CBVs_actions_old_group_logits": {"logits": r2.normal(size=(R, 12)).astype(np.float32), "valid_mask": vm},
+                        "CBVs_actions_ref_group_logits": {"logits": r2.normal(size=(R, 12)).astype(np.float32), "valid_mask": vm},
+                        "CBVs_state": torch.from_numpy(r2.normal(size=128).astype(np.float32)),
+                        "CBVs_advantage": torch.tensor(float(r2.normal())), "CBVs_reward_sum": torch.tensor(float(r2.normal())),
+                        "CBVs_old_log_prob": torch.tensor(float(-r2.uniform(1, 5))),
+                        "CBVs_action_mode": torch.tensor([int(r2.integers(0, R)), int(r2.integers(0, 12))]),
+                        "CBVs_return": torch.tensor(float(r2.normal()))})
+        return out
+
+    def same(a, b, path):
+        if isinstance(b, dict):
+            assert set(a) == set(b), (path, set(a) ^ set(b))
+            for k in b:
+                same(a[k], b[k], path + "/" + k)
+        elif hasattr(b, "data") and isinstance(b.data, dict):
+            same(a.data, b.data, path + ".data")
+        else:
+            assert a.dtype == b.dtype and torch.equal(a, b), path
+
+    for algo in ref_cls:
+        ref = ref_cls[algo]()(items(RefFeature, True))
+        ours = ours_cls[algo]()(items(PlutoFeature, False))
+        same(ours, ref, algo)
+
+
 def test_warmup_cos_lr_matches_reference_formula():
     from rift_b200.trainer import WarmupCosLR
 

@@ -251,3 +251,56 @@ def test_cfg2_shape_properties():
     assert losses[-1] < losses[0]
     g = model.arena.grad_view("planning_decoder.pi_head.mlp.3.bias")
     assert abs(float(g.sum())) < 1e-3 * max(float(model.arena.grads.abs().max()), 1e-6)
+
+
+# BASELINE.json configs at their own shapes: cfg2 exactly, a ragged variant of it, and the
+# per-rank shard of configs[3] (256 x 48 over 8 GPUs = 32 samples of 48 agents) - Pluto-medium, every module trainable.
+BASELINE_SHAPES = {
+    "cfg2": dict(bs=64, A=32, Mp=20, R=6, ragged=False, algo="grpo", clip=(0.8, 1.2)),
+    "cfg2_ragged": dict(bs=64, A=32, Mp=20, R=6, ragged=True, algo="grpo", clip=(0.8, 1.2)),
+    "cfg4_rank": dict(bs=32, A=48, Mp=20, R=6, ragged=False, algo="grpo", clip=(0.8, 1.2)),
+}
+
+
+@pytest.mark.parametrize("name", list(BASELINE_SHAPES))
+def test_baseline_shape_parity_vs_oracle(name):
+    """The benchmarked configuration itself against the CPU oracle: logits and loss at 1e-3, the L2 norm of EVERY
+    gradient tensor at 2e-3, element-wise errors bounded by GRAD_ETOL with the number of elements beyond 2e-3 recorded
+    (they come from ReLU / arg-max decisions within 1e-5 of their threshold; a regression cannot hide among them:
+    at most 0.1 % of a tensor's elements may exceed 2e-3 of its maximum)."""
+    s = BASELINE_SHAPES[name]
+    cfg = MODEL_ZOO["medium"]()
+    sd = synth_state_dict(cfg, seed=7)
+    feats = synth_features(cfg, s["bs"], s["A"], s["Mp"], s["R"], seed=1, ragged=s["ragged"])
+    ex = synth_rl_extras(cfg, feats, seed=2)
+    model = build(cfg, sd)
+    tr = TRAINERS[s["algo"]](model, trainable_layers=FULL_LAYERS, **TRAINER_KW)
+    loss = tr.training_step(make_batch(feats, ex))
+    count = float(tr._count)
+    ref_loss, ref_out, sdt = oracle_losses(cfg, sd, feats, ex, s["algo"], requires_grad=tuple(FULL_LAYERS))
+    ref_loss.backward()
+    rl = float(ref_loss.detach())
+    assert abs(float(loss) - rl) <= RTOL * max(abs(rl), 1e-3), (float(loss), rl)
+    out = model(to_torch_tree(feats, "cuda"), outputs=("probability",))
+    a, b = valid_logits(out["probability"].cpu(), feats), valid_logits(ref_out["probability"].detach(), feats)
+    assert (a - b).abs().max().item() <= RTOL * b.abs().max().item()
+    best = out["probability"].reshape(s["bs"], -1).argmax(-1).cpu()
+    assert torch.equal(best, ref_out["probability"].detach().reshape(s["bs"], -1).argmax(-1))
+    gmax = max(float(t.grad.abs().max()) for t in sdt.values() if t.grad is not None)
+    bad, over, total = [], 0, 0
+    for n in sorted(model.arena.trainable):
+        ref = sdt[n].grad
+        assert ref is not None, n
+        got = (model.arena.grad_view(n) / count).cpu()
+        rn, gn = float(ref.double().pow(2).sum().sqrt()), float(got.double().pow(2).sum().sqrt())
+        if abs(gn - rn) > 2e-3 * rn + 1e-6 * gmax:
+            bad.append((n, gn, rn))
+        err = (got - ref).abs()
+        tmax = float(ref.abs().max())
+        assert float(err.max()) <= GRAD_ETOL[False] * tmax + 1e-6 * gmax, (n, float(err.max()), tmax)
+        n_over = int((err > 2e-3 * tmax + 1e-6 * gmax).sum())
+        assert n_over <= max(2, ref.numel() // 1000), (n, n_over, ref.numel())
+        over += n_over
+        total += ref.numel()
+    assert not bad, f"{len(bad)} gradient norms differ by more than 2e-3, first: {bad[:5]}"
+    print(f"[{name}] loss {float(loss):.6f} vs {rl:.6f}; {over} of {total} gradient elements beyond 2e-3 of their tensor max")

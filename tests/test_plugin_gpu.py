@@ -149,3 +149,38 @@ def test_policy_outputs_advantage_is_numpy_exact():
         assert np.array_equal(got, ref)
         assert int(out["group_advantage_mask"][b].sum()) == len(r)
     assert out["candidate_trajectories"].shape[-1] == 3
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_ppo_full_backward_matches_reference_golden(name):
+    """PPO with every module trainable against the reference's autograd: per-tensor L2 norm
+    and sum of all gradient tensors, value net included."""
+    from rift_b200.config import param_spec, is_buffer
+    from tests.test_model_gpu import FULL_LAYERS
+    cfg, sd, feats, ex = case_inputs(name, ppo=True)
+    g = golden(name)
+    model = PPOPlutoModel(cfg.radius, hidden_dim=(256, 256), dim=cfg.dim, num_heads=cfg.num_heads,
+                          encoder_depth=cfg.encoder_depth, decoder_depth=cfg.decoder_depth, future_steps=cfg.future_steps)
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    tr = TRAINERS["ppo"](model, trainable_layers=FULL_LAYERS + ["value_net"], **TRAINER_KW)
+    batch = {"cur_pluto_feature_torch": to_torch_tree(feats, "cuda")}
+    for k in ("state", "advantage", "reward_sum", "old_log_prob", "action_mode"):
+        batch[k + "_torch"] = torch.from_numpy(ex[k].copy()).cuda()
+    loss = tr.training_step(batch)
+    ref = float(g["loss_ppo"])
+    assert abs(float(loss) - ref) <= 1e-3 * max(abs(ref), 1e-3)
+    names = [n for n, _, _ in param_spec(cfg) if not is_buffer(n)]
+    stats = g["fullgrad_ppo_stats"]
+    assert stats.shape[0] == len(names), (stats.shape, len(names))
+    gmax = stats[:, 1].max()
+    bad = []
+    for i, n in enumerate(names):
+        if n not in model.arena.trainable:
+            assert stats[i, 1] == 0.0, f"{n} has a reference gradient but is not in the trainable arena"
+            continue
+        gv = model.arena.grad_view(n).double().cpu()
+        l2 = float(gv.pow(2).sum().sqrt())
+        if abs(l2 - stats[i, 1]) > 2e-3 * stats[i, 1] + 1e-6 * gmax or \
+                abs(float(gv.sum()) - stats[i, 0]) > 2e-3 * stats[i, 1] * np.sqrt(gv.numel()) + 1e-6 * gmax:
+            bad.append((n, l2, stats[i, 1], float(gv.sum()), stats[i, 0]))
+    assert not bad, f"{len(bad)} tensors differ, first: {bad[:5]}"

@@ -235,3 +235,21 @@ def test_clip_adamw_divides_by_device_count():
     b.step()
     assert torch.allclose(a.p, b.p, rtol=0, atol=1e-7)
     assert abs(a.grad_norm() - b.grad_norm()) < 1e-4 * b.grad_norm()
+
+
+def test_clip_adamw_skips_the_update_when_nothing_is_valid():
+    """count == 0 (no valid objective term): the reference's loss is a constant, Lightning takes no optimizer step -
+    no weight decay, no moment decay, no step-counter increment."""
+    n = 2048
+    gen = torch.Generator().manual_seed(2)
+    p0, g0 = torch.randn(n, generator=gen), torch.randn(n, generator=gen)
+    o = F.ClipAdamW(p0.clone().cuda(), g0.clone().cuda(), n, n, lr=1e-2, weight_decay=0.1, max_norm=0.5)
+    o.step(count=torch.tensor([3.0], dtype=torch.float64, device="cuda"))
+    assert o.step_count == 1
+    p1, m1, v1 = o.p.clone(), o.m.clone(), o.v.clone()
+    o.step(count=torch.tensor([0.0], dtype=torch.float64, device="cuda"))
+    assert o.step_count == 1
+    assert torch.equal(o.p, p1) and torch.equal(o.m, m1) and torch.equal(o.v, v1)
+    o.param_groups[0]["lr"] = 5e-3                      # a scheduler step reaches the device-resident learning rate
+    o.step(count=torch.tensor([3.0], dtype=torch.float64, device="cuda"))
+    assert o.step_count == 2 and abs(float(o.hyper[0]) - 5e-3) < 1e-9 and not torch.equal(o.p, p1)

@@ -52,3 +52,42 @@ def test_numpy_features_are_accepted():
     feats["current_state"] = np.zeros((2, 7), np.float64)
     items = LightningTrainer._flatten_batch({"cur_pluto_feature_torch": feats}, feats)
     assert dict(items)["f.current_state"].dtype == torch.float64
+
+
+class _StubModel:
+    """Just enough of PlanningModel for LightningTrainer's host logic (no device, no library)."""
+    history_steps, future_steps, radius, num_modes = 21, 80, 120, 12
+    ws_generation = 0
+
+    def __init__(self):
+        self.layouts = []
+
+    def set_trainable_layers(self, layers):
+        self.layouts.append(list(layers))
+
+
+def test_freeze_parameters_drops_an_optimizer_built_for_the_old_layout():
+    """the arenas are re-laid out by freeze_parameters, so an existing ClipAdamW (moments sized and ordered
+    for the old layout, pointers into the dead arena) must not survive it; captured graphs neither."""
+    tr = LightningTrainer(_StubModel(), lr=1e-4, cl_lr_decay=0.9, weight_decay=1e-5, epochs=16, warmup_epochs=3,
+                          frame_rate=10, trainable_layers=["planning_decoder.pi_head"])
+    tr.optimizer, tr.scheduler = object(), object()
+    tr._graphs[("k",)] = {"stale": True}
+    tr._graph_seen[("k",)] = 2
+    tr.freeze_parameters(["planning_decoder"])
+    assert tr.optimizer is None and tr.scheduler is None
+    assert tr._graphs == {} and tr._graph_seen == {}
+    assert tr.model.layouts == [["planning_decoder.pi_head"], ["planning_decoder"]]
+
+
+def test_train_mode_request_warns_once_about_the_parity_mode():
+    import warnings
+    LightningTrainer._warned_train_mode = False
+    tr = LightningTrainer(_StubModel(), lr=1e-4, cl_lr_decay=0.9, weight_decay=1e-5, epochs=16, warmup_epochs=3,
+                          frame_rate=10, trainable_layers=[])
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        tr.train()
+        tr.train()
+    assert len(w) == 1 and "deterministic parity mode" in str(w[0].message)
+    assert tr.training

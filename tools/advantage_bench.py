@@ -3,9 +3,9 @@ Algorithmic bytes = 16 * G per group (fp64 returns in, fp64 advantages out).  CP
 per-group numpy expression (traj_evaluator.py:466-469) and a vectorised axis=1 numpy variant."""
 import json, os, sys, time
 import numpy as np, torch
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from rift_b200 import functional as F
-peak = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "MEASURED_PEAKS.json")))["hbm_gbs"] \
+peak = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"] \
     if os.path.exists("MEASURED_PEAKS.json") else 6650.0
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 rows = []

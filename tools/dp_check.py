@@ -2,7 +2,7 @@
 the same loss, gradient norm and updated parameters as one rank holding the whole batch."""
 import os, sys, torch, numpy as np
 import torch.distributed as dist
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from rift_b200.config import MODEL_ZOO
 from rift_b200.planning_model import PlanningModel
 from rift_b200.trainer import TRAINERS

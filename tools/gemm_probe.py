@@ -1,6 +1,6 @@
 """Micro-probe: run the tcgen05 linear op on one shape (for ncu captures and quick timing)."""
 import sys, os, torch
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from rift_b200 import _lib
 rows, K, N = [int(x) for x in (sys.argv[1:4] if len(sys.argv) > 3 else (46080, 256, 256))]
 reps = int(sys.argv[4]) if len(sys.argv) > 4 else 5

@@ -1,14 +1,15 @@
 #!/bin/bash
-# tests + benches + launch list (profiling numbers are never bench values)
+# tests + benches + (optional) launch list (profiling numbers are never bench values)
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
-timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu > gpurun_out/q_full.json 2> gpurun_out/q_full.err; tail -2 gpurun_out/q_full.err
-timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu --trainable pi_head > gpurun_out/q_pi.json 2> gpurun_out/q_pi.err
+timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -15 > gpurun_out/pytest_gpu.log; tail -5 gpurun_out/pytest_gpu.log
+timeout 400 python bench.py --steps 30 --warmup 5 --no-cpu > gpurun_out/q_full.json 2> gpurun_out/q_full.err; tail -2 gpurun_out/q_full.err
+timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu --no-kernels --trainable pi_head > gpurun_out/q_pi.json 2> gpurun_out/q_pi.err
 python - <<'PY'
 import json
 for f in ("q_full", "q_pi"):
     try:
-        d = json.load(open(f"gpurun_out/{f}.json")); print(f, "ms", round(d["ms_per_step"], 3), "e2e ms", round(d["e2e"]["ms_per_step"], 3), "launches", d["gpu_launches"], "roofline", round(d["roofline"]["frac"], 3), d["roofline"]["kernel_ms"])
+        d = json.load(open(f"gpurun_out/{f}.json")); print(f, "ms", round(d["ms_per_step"], 3), "e2e ms", round(d["e2e"]["ms_per_step"], 3), "launches", d["gpu_launches"], "step frac", d["roofline_step"]["frac"])
+        for k, v in d.get("kernels", {}).items(): print("   ", k, round(v["kernel_ms"] * 1e3, 1), "us", round(v["frac_hbm"], 3))
     except Exception as e:
         print(f, "failed", e)
 PY

@@ -1,7 +1,7 @@
 """Numerics study (not a test): end-to-end logit / loss error of the forward under emulated operand
-precisions of the GEMMs.  RIFT_B200_EMULATE=0|1|2|3 python tools_precision_study.py"""
+precisions of the GEMMs.  RIFT_B200_EMULATE=0|1|2|3 python tools/precision_study.py"""
 import os, sys, torch, numpy as np
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from rift_b200.config import MODEL_ZOO
 from rift_b200.planning_model import PlanningModel
 from rift_b200.synth import synth_state_dict, synth_features, synth_rl_extras
