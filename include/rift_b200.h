@@ -188,6 +188,11 @@ int rift_b200_op_linear_tc(const float* x, int rows, int K, const float* w, cons
 int rift_b200_op_linear_tc_full(const float* x, int rows, int K, const float* w, const float* bias, int N, int act,
                                 const float* res, float* y, float beta, float* preact, void* out_hi, void* out_lo, void* scratch,
                                 size_t scratch_bytes, void* stream);
+/* weight-gradient path of the tcgen05 GEMM: dW[N, K] += dY[rows, N]^T X[rows, K], db[N] += column sums of dY (db may be NULL);
+ * split-K parts are added with red.global.add, the bias gradient comes from a second tensor-core accumulator */
+size_t rift_b200_op_wgrad_tc_scratch_bytes(int rows, int N, int K);
+int rift_b200_op_wgrad_tc(const float* dY, const float* X, int rows, int N, int K, float* dW, float* db, int splits,
+                          void* scratch, size_t scratch_bytes, void* stream);
 int rift_b200_op_gemm(const float* A, long long sam, long long sak, const float* B, long long sbn, long long sbk,
                       float* C, long long ldc, int M, int N, int K, float beta, int split_k, float* split_ws,
                       int simt, void* stream);

@@ -86,6 +86,8 @@ _SIGNATURES = {
     "rift_b200_weight_cache_bytes": (C.c_size_t, [_V]),
     "rift_b200_bind_weight_cache": (C.c_int, [_V, _V, C.c_size_t]),
     "rift_b200_params_updated": (C.c_int, [_V, C.c_int]),
+    "rift_b200_op_wgrad_tc_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "rift_b200_op_wgrad_tc": (C.c_int, [_V, _V, C.c_int, C.c_int, C.c_int, _V, _V, C.c_int, _V, C.c_size_t, _V]),
     "rift_b200_op_linear_tc_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "rift_b200_op_linear_tc": (C.c_int, [_V, C.c_int, C.c_int, _V, _V, C.c_int, C.c_int, _V, _V, _V, C.c_size_t,
                                          C.c_int, _V]),

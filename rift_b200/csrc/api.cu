@@ -265,6 +265,35 @@ int rift_b200_op_linear_tc_full(const float* x, int rows, int K, const float* w,
     return launch_gemm_tc(a, ap, ap + aplane, tw.Kp, tw, 0, 0, S(stream));
 }
 
+size_t rift_b200_op_wgrad_tc_scratch_bytes(int rows, int N, int K) {
+    const size_t np_ = (size_t)(N + 63) / 64 * 64, kp_ = (size_t)(K + 63) / 64 * 64;
+    return 2 * (((size_t)rows * np_ * 2 + 255) & ~(size_t)255) + 2 * (((size_t)rows * kp_ * 2 + 255) & ~(size_t)255);
+}
+
+// dW[N, K] += dY^T X and db[N] += colsum(dY) on the tcgen05 weight-gradient path (MN-major operands, split-K parts added
+// with red.global.add, bias gradient from the second accumulator); dW / db must hold the running sums (e.g. zeros)
+int rift_b200_op_wgrad_tc(const float* dY, const float* X, int rows, int N, int K, float* dW, float* db, int splits,
+                          void* scratch, size_t scratch_bytes, void* stream) {
+    RIFT_REQUIRE(dY && X && dW && scratch, "op_wgrad_tc: null argument");
+    RIFT_REQUIRE(scratch_bytes >= rift_b200_op_wgrad_tc_scratch_bytes(rows, N, K), "op_wgrad_tc: scratch too small");
+    RIFT_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 255) == 0, "op_wgrad_tc: scratch must be 256-byte aligned");
+    const int Np = (N + 63) / 64 * 64, Kp = (K + 63) / 64 * 64, K4 = (K + 3) & ~3;
+    char* p = static_cast<char*>(scratch);
+    const size_t ypl = ((size_t)rows * Np * 2 + 255) & ~(size_t)255, xpl = ((size_t)rows * Kp * 2 + 255) & ~(size_t)255;
+    void *yh = p, *yl = p + ypl, *xh = p + 2 * ypl, *xl = p + 2 * ypl + xpl;
+    int r = launch_pack_split(dY, N, rows, N, Np, yh, yl, S(stream));
+    if (r) return r;
+    r = launch_pack_split(X, K, rows, K, Kp, xh, xl, S(stream));
+    if (r) return r;
+    GemmArgs a;
+    a.C = dW; a.ldc = K; a.M = N; a.N = K4; a.K = rows;
+    a.atomic_out = true; a.colsum_out = db;
+    if (K4 != K) a.n_store = K;
+    PlaneOp A{yh, yl, rows, Np, 0, 0};
+    PlaneOp B{xh, xl, rows, Kp, 0, 0};
+    return launch_gemm_tc_ex(a, A, B, true, splits, nullptr, S(stream));
+}
+
 int rift_b200_op_gemm(const float* A, long long sam, long long sak, const float* B, long long sbn, long long sbk, float* C,
                       long long ldc, int M, int N, int K, float beta, int split_k, float* split_ws, int simt, void* stream) {
     GemmArgs a;

@@ -1,6 +1,7 @@
 // Operator wrappers shared by the forward (engine.cu) and backward (engine_bwd.cu) schedules.
 #pragma once
 #include <math.h>
+#include <stdlib.h>
 
 #include <initializer_list>
 
@@ -260,22 +261,27 @@ inline int lin_bwd(Ctx& c, const float* X, long long ldx, const float* dY, long 
     const int Kpad4 = (L.K + 3) & ~3;
     const bool w_padded = (L.K % 4) != 0 || (L.ldw % 4) != 0;
     const bool tc_w = tc_on && want_w && gemm_tc_shape_ok(L.N, Kpad4, M) && L.N >= 64 && (Xp && Xp->on() ? Xp->Kp >= Kpad4 : true);
-    // Parameter gradients go to the side stream: they read only dYp / the saved operand planes / private partial
-    // buffers (never the fp32 dY, which the main stream may update in place later) and nothing downstream on the
-    // main stream depends on them before the final join of backward().
+    // Parameter gradients go to the side stream: they read only dYp / the saved operand planes (never the fp32 dY, which
+    // the main stream may update in place later) and nothing downstream on the main stream depends on them before the
+    // final join of backward().  On the tensor-core route the weight-gradient GEMM adds every (tile, split-K part)
+    // straight into dW with red.global.add (the arena was zeroed when backward started) and produces the bias gradient
+    // from a second accumulator (dY^T x ones): no partial slabs, no reduce / column-sum kernels.
     const bool want_b = bias_grad && L.train && L.db;
+    // RIFT_B200_WGRAD_ATOMIC=0: the previous form (partial slabs + fixed-order reduce kernel, separate column sums)
+    static const bool atomic_w = [] { const char* e = getenv("RIFT_B200_WGRAD_ATOMIC"); return !(e && atoi(e) == 0); }();
+    const bool b_in_wgrad = want_b && tc_w && atomic_w;
     float* sc = nullptr;
-    if (want_b) {
+    if (want_b && !b_in_wgrad) {
         const size_t slabs_max = (size_t)(pack_colsum_slabs(M, tc_pitch(L.N)) > 148 ? pack_colsum_slabs(M, tc_pitch(L.N)) : 148);
         sc = c.alloc<float>(slabs_max * L.N);
         if (!sc) { set_last_error("workspace too small"); return -1; }
     }
     Planes dYp;
-    bool forked = false, bias_done = false;
+    bool forked = false, bias_done = b_in_wgrad;
     if (fz && fz->dYp_in && fz->dYp_in->on()) {
         if (!(tc_d || !dx_wanted) || (want_w && !tc_w)) { set_last_error("internal: pre-packed dY needs the tensor-core route"); return -1; }
         dYp = *fz->dYp_in;
-        if (want_b && !c.dry) {                          // bias gradient from the planes, both stages on the side stream
+        if (want_b && !bias_done && !c.dry) {            // bias gradient from the planes, both stages on the side stream
             TRY(fork_to(c, c.side));
             forked = true;
             OnStream on(c, c.side);
@@ -289,7 +295,7 @@ inline int lin_bwd(Ctx& c, const float* X, long long ldx, const float* dY, long 
         if (!dYp.hi || !dYp.lo) { set_last_error("workspace too small"); return -1; }
         if (!c.dry) {
             int slabs = 0;
-            if (want_b) TRY(launch_pack_split_colsum(dY, lddy, M, L.N, dYp.Kp, dYp.hi, dYp.lo, sc, &slabs, c.st));   // one pass over dY
+            if (want_b && !bias_done) TRY(launch_pack_split_colsum(dY, lddy, M, L.N, dYp.Kp, dYp.hi, dYp.lo, sc, &slabs, c.st));   // one pass over dY
             if (slabs > 0) {
                 SideStream fin;
                 if (c.side) { fin.st = c.side; fin.ev = c.next_event(); forked = true; }
@@ -318,18 +324,20 @@ inline int lin_bwd(Ctx& c, const float* X, long long ldx, const float* dY, long 
         }
         const int tiles = ((L.N + 127) / 128) * ((L.K + (L.K <= 64 ? 63 : 127)) / (L.K <= 64 ? 64 : 128));
         const int num_kb = (M + 63) / 64;
-        // one wave of (tile, split) work items: more splits only add partial-slab traffic for the reduce
+        // one wave of (tile, split) work items
         int splits = 148 / tiles;
         if (splits > 24) splits = 24;
         if (splits > num_kb) splits = num_kb;
         if (splits < 1) splits = 1;
         float* ws = nullptr;
-        if (splits > 1 || w_padded) { ws = c.alloc<float>((size_t)splits * L.N * Kpad4); if (!ws) { set_last_error("workspace too small"); return -1; } }
+        if (!atomic_w && (splits > 1 || w_padded)) { ws = c.alloc<float>((size_t)splits * L.N * Kpad4); if (!ws) { set_last_error("workspace too small"); return -1; } }
         if (!c.dry) {
             if (!forked) TRY(fork_to(c, c.side));
             OnStream on(c, c.side);
             GemmArgs a;
-            a.C = L.dW; a.ldc = L.ldw; a.M = L.N; a.N = Kpad4; a.K = M; a.beta = 1.f;
+            a.C = L.dW; a.ldc = L.ldw; a.M = L.N; a.N = Kpad4; a.K = M;
+            if (atomic_w) { a.atomic_out = true; if (b_in_wgrad) a.colsum_out = L.db; }
+            else a.beta = 1.f;
             if (w_padded) a.n_store = L.K;
             PlaneOp A{dYp.hi, dYp.lo, M, dYp.Kp, 0, 0};
             PlaneOp B{xp.hi, xp.lo, M, xp.Kp, 0, 0};

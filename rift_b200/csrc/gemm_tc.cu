@@ -144,6 +144,10 @@ struct TcKernelArgs {
     int splits, kb_per_split; long long split_stride;     // split-K: slab `s` writes raw sums to C + s * split_stride
     TcEpilogue ep;
     Planes out;              // optional split-bf16 copy of the result for the next GEMM (C may then be null)
+    int atomic;              // 1: every (tile, split) ADDS its raw sums into C with red.global.add (weight gradients: no partial
+                             // slabs, no reduce kernel; C was zeroed by the caller)
+    int n_store;             // atomic mode, > 0: only columns [0, n_store) exist in C (arbitrary ldc): scalar reds
+    float* colsum;           // MN-major (dW = dY^T X) only: colsum[m] += sum_k A[k, m] (bias gradient), from the tensor core
     int dbg;                 // bottleneck experiments only (RIFT_B200_TC_DBG)
     unsigned long long* trace;   // profiling aid (rift_b200_debug_gemm_trace): CTA 0 writes %globaltimer stamps
 };
@@ -161,8 +165,10 @@ struct TcSmem {
     static constexpr int B_TILE = BN * TC_BK * 2;
     static constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;
     static constexpr int EPI = TC_EPI_WARPS * 32 * TC_EPI_PITCH * 4;       // per-warp 32 x 32 fp32 staging tiles
-    static constexpr int TOTAL = TC_STAGES * STAGE + 1024 /*align*/ + 256 /*barriers*/ + EPI;
+    static constexpr int ONES = 512;                     // all-ones bf16 B operand of the bias-gradient MMA (MN kernels)
+    static constexpr int TOTAL = TC_STAGES * STAGE + 1024 /*align*/ + 256 /*barriers*/ + EPI + ONES;
 };
+static_assert(TcSmem<128>::TOTAL <= 227 * 1024, "tcgen05 GEMM shared memory");
 constexpr int TC_BOX = 64 * 64 * 2;      // bytes of one 64 x 64 bf16 TMA box
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
@@ -175,6 +181,30 @@ __device__ __forceinline__ float4 lds4(uint32_t addr) {
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
     return v;
 }
+
+__device__ __forceinline__ void red_add_v4(float* p, const float4& v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void red_add_f32(float* p, float v) {
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t tmem_ld_1(uint32_t taddr) {
+    uint32_t r;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+    return r;
+}
+// Bias gradient on the tensor core (MN-major weight-gradient kernels): next to dW[m, n] += sum_k dY[k, m] X[k, n] a second
+// accumulator of 16 columns takes dY^T x ONES, so every column of it is colsum_k dY[k, m].  The all-ones B operand is a
+// 512-byte no-swizzle K-major tile (2 x 2 core matrices of 8 rows x 16 B: LBO = 128, SBO = 256); being constant its
+// layout is irrelevant.
+constexpr int TC_CS_COLS = 16;
+__device__ __forceinline__ uint64_t make_sdesc_ones(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | (1ull << 46);
+}
+__host__ __device__ constexpr uint32_t make_idesc_colsum() {      // A MN-major (bit 15), B K-major, N = 16, M = 128
+    return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | ((uint32_t)(TC_CS_COLS >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+}
+constexpr uint32_t tmem_cols_pow2(uint32_t n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
 
 // DA: the epilogue multiplies by act'(dact_ref) (fused activation backward) - a separate instantiation so that the
 // common kernels do not carry its code
@@ -193,8 +223,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     uint64_t* acc_empty = bars + 2 * TC_STAGES + 2; // [2] accumulator drained (one arrival per epilogue warp)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 4);
     float* stage_t = reinterpret_cast<float*>(smem + TC_STAGES * SM::STAGE + 256);
+    uint8_t* ones = smem + TC_STAGES * SM::STAGE + 256 + SM::EPI;
+    constexpr uint32_t TMEM_COLS = tmem_cols_pow2(2 * BN + (MN ? 2 * TC_CS_COLS : 0));
+    const bool do_colsum = MN && g.colsum != nullptr;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (MN && threadIdx.x >= 64 && threadIdx.x < 64 + SM::ONES / 4)
+        reinterpret_cast<uint32_t*>(ones)[threadIdx.x - 64] = 0x3F803F80u;          // bf16 1.0 pairs
     const int tiles_n = (g.N + BN - 1) / BN;
     const int tiles_m = (g.M + TC_BM - 1) / TC_BM;
     const int tiles_mn = tiles_m * tiles_n;
@@ -210,7 +245,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB_hi) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB_lo) : "memory");
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
+    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    if (MN) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // the ones tile is read by the async (UMMA) proxy
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -259,13 +295,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             constexpr uint32_t kstep = MN ? 2048u : 32u;          // bytes per UMMA_K = 16 step
             constexpr uint32_t lbo = MN ? (uint32_t)TC_BOX : 0u;
             int it = 0, ti = 0;
+            const uint64_t d_ones = make_sdesc_ones(smem_u32(ones));
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
-                const int sp = tile / tiles_mn;
+                const int sp = tile / tiles_mn, tmn = tile - sp * tiles_mn;
                 const int kb0 = sp * g.kb_per_split, kb1 = min(num_kb, kb0 + g.kb_per_split);
                 const int buf = ti & 1;
                 mbar_wait(&acc_empty[buf], ((ti >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + (uint32_t)(buf * BN);
+                const bool cs_tile = do_colsum && (tmn % tiles_n) == 0;       // the first n-tile of each m-tile carries the bias sum
+                const uint32_t tcs = tmem_base + (uint32_t)(2 * BN + buf * TC_CS_COLS);
                 for (int kb = kb0; kb < kb1; ++kb, ++it) {
                     const int s = it % TC_STAGES;
                     const uint32_t ph = (it / TC_STAGES) & 1;
@@ -284,6 +323,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                         umma_bf16(tacc, dal, dbh, idesc, (kb > kb0 || k > 0) ? 1u : 0u);     // small terms first
                         umma_bf16(tacc, dah, dbl, idesc, 1);
                         umma_bf16(tacc, dah, dbh, idesc, 1);
+                        if (MN && cs_tile) {
+                            umma_bf16(tcs, dal, d_ones, make_idesc_colsum(), (kb > kb0 || k > 0) ? 1u : 0u);
+                            umma_bf16(tcs, dah, d_ones, make_idesc_colsum(), 1);
+                        }
                     }
                     umma_commit(&empty[s]);                      // frees the stage once these MMAs retire
                 }
@@ -433,7 +476,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                     float4 w[8];
 #pragma unroll
                     for (int it = 0; it < 8; ++it) w[it] = lds4(((it & 1) ? tb_st1 : tb_st0) + it * (4 * TC_EPI_PITCH * 4));
-                    if (c_row && col_ok) {
+                    if (c_row && g.atomic) {
+                        if (g.n_store > 0) {             // padded column count / unaligned C rows: scalar reds on the real columns
+#pragma unroll
+                            for (int it = 0; it < 8; ++it)
+                                if (srow + 4 * it < rows_here) {
+                                    float* cp = c_row + it * row_step + ncol;
+                                    if (ncol < g.n_store) red_add_f32(cp, w[it].x);
+                                    if (ncol + 1 < g.n_store) red_add_f32(cp + 1, w[it].y);
+                                    if (ncol + 2 < g.n_store) red_add_f32(cp + 2, w[it].z);
+                                    if (ncol + 3 < g.n_store) red_add_f32(cp + 3, w[it].w);
+                                }
+                        } else if (col_ok) {
+                            float* cp = c_row + ncol;
+#pragma unroll
+                            for (int it = 0; it < 8; ++it)
+                                if (srow + 4 * it < rows_here) red_add_v4(cp + it * row_step, w[it]);
+                        }
+                    } else if (c_row && col_ok) {
                         float* cp = c_row + ncol;
                         if (e.beta != 0.f) {
                             float4 o[8];
@@ -481,6 +541,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 }
                 __syncwarp();
             }
+            if (MN && do_colsum && half == 0 && n0 == 0) {
+                // bias gradient: column 0 of the 16-column side accumulator, one out-feature per lane
+                const uint32_t v = tmem_ld_1(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(2 * BN + buf * TC_CS_COLS));
+                tmem_ld_wait();
+                if (row_ok) red_add_f32(g.colsum + m, __uint_as_float(v));
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[buf]);
@@ -492,7 +558,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 2 * BN);
+        tmem_dealloc(tmem_base, TMEM_COLS);
         if (lane == 0) TC_TRACE(61);
     }
 }
@@ -1146,8 +1212,18 @@ static int launch_tc(const GemmArgs& a, const PlaneOp& A, const PlaneOp& B, int 
     g.out = a.out_planes;
     g.trace = g_tc_trace;
     { static int dbg = -1; if (dbg < 0) { const char* e = getenv("RIFT_B200_TC_DBG"); dbg = e ? atoi(e) : 0; } g.dbg = dbg; }
-    const bool via_ws = splits > 1 || a.n_store > 0;       // raw sums into the partial buffer, epilogue in the reduce
-    if (via_ws) {
+    const bool via_ws = !a.atomic_out && (splits > 1 || a.n_store > 0);       // raw sums into the partial buffer, epilogue in the reduce
+    g.atomic = 0; g.n_store = 0; g.colsum = nullptr;
+    if (a.atomic_out) {
+        // weight gradients: every (tile, split) adds its raw sums straight into C (zeroed by the caller)
+        if (splits < 1) splits = 1;
+        g.splits = splits; g.kb_per_split = cdiv(num_kb, splits);
+        g.splits = cdiv(num_kb, g.kb_per_split);
+        g.C = a.C; g.ldc = a.ldc; g.split_stride = 0;
+        g.ep = TcEpilogue{nullptr, nullptr, nullptr, 0, 1, nullptr, 0, 1, 0, ACT_NONE, 0.f, 1.f, nullptr, nullptr, 0, 0};
+        g.out = Planes();
+        g.atomic = 1; g.n_store = a.n_store; g.colsum = MN ? a.colsum_out : nullptr;
+    } else if (via_ws) {
         if (splits < 1) splits = 1;
         g.splits = splits; g.kb_per_split = cdiv(num_kb, splits);
         g.splits = cdiv(num_kb, g.kb_per_split);
@@ -1174,7 +1250,10 @@ int launch_gemm_tc_ex(const GemmArgs& a, const PlaneOp& A, const PlaneOp& B, boo
                       cudaStream_t st) {
     RIFT_REQUIRE(gemm_tc_eligible(a), "gemm_tc: shape / layout not eligible");
     RIFT_REQUIRE(A.pitch % 64 == 0 && B.pitch % 64 == 0, "gemm_tc: plane pitches must be multiples of 64");
-    RIFT_REQUIRE((splits <= 1 && a.n_store <= 0) || partials != nullptr, "gemm_tc: split-K / padded-N needs a partial buffer");
+    RIFT_REQUIRE(a.atomic_out || (splits <= 1 && a.n_store <= 0) || partials != nullptr, "gemm_tc: split-K / padded-N needs a partial buffer");
+    RIFT_REQUIRE(!a.atomic_out || (a.C != nullptr && a.alpha == 1.f && !a.bias && !a.res && !a.pre && !a.dact_ref && !a.out_planes.on()),
+                 "gemm_tc: the atomic-accumulate form takes no epilogue");
+    RIFT_REQUIRE(a.colsum_out == nullptr || (mn_major && a.atomic_out), "gemm_tc: colsum_out needs the MN-major atomic form");
     if (a.M <= 0 || a.N <= 0) return 0;
     // tile width: 64-wide tiles when they shorten the longest per-CTA queue (one persistent CTA per SM): small grids
     // that leave SMs idle with 128-wide tiles, and N that is not a multiple of 128 (e.g. 192 = 3 x 64)

@@ -166,7 +166,8 @@ __global__ void __launch_bounds__(256)
 layernorm_bwd_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ dy, long long lddy, int rows,
                      int C, const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
                      const float* __restrict__ y_relu, long long ldy, float* __restrict__ dx, long long lddx,
-                     int dx_accumulate, float* __restrict__ partial /*[grid][2][C]*/) {
+                     int dx_accumulate, float* __restrict__ partial /*[grid][2][C]*/, float* __restrict__ dgamma_atomic,
+                     float* __restrict__ dbeta_atomic) {
     pdl_grid_sync();
     extern __shared__ float sm[];      // [8 warps][2][C]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -206,7 +207,7 @@ layernorm_bwd_kernel(const float* __restrict__ x, long long ldx, const float* __
             }
         }
     }
-    if (partial == nullptr) return;
+    if (partial == nullptr && dgamma_atomic == nullptr) return;
 #pragma unroll
     for (int i = 0; i < LNB_MAXC / 32; ++i) {
         const int c = lane + 32 * i;
@@ -217,7 +218,8 @@ layernorm_bwd_kernel(const float* __restrict__ x, long long ldx, const float* __
         const int which = c / C, cc = c - which * C;
         float a = 0.f;
         for (int w = 0; w < 8; ++w) a += sm[(w * 2 + which) * C + cc];
-        partial[((long long)blockIdx.x * 2 + which) * C + cc] = a;
+        if (dgamma_atomic) atomicAdd((which ? dbeta_atomic : dgamma_atomic) + cc, a);   // straight into the gradient arena
+        else partial[((long long)blockIdx.x * 2 + which) * C + cc] = a;
     }
 }
 
@@ -258,7 +260,8 @@ __global__ void __launch_bounds__(256)
 layernorm_bwd4_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ dy, long long lddy, int rows, int C,
                       const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
                       const float* __restrict__ y_relu, long long ldy, float* __restrict__ dx, long long lddx,
-                      int dx_accumulate, float* __restrict__ partial /*[grid][2][C]*/) {
+                      int dx_accumulate, float* __restrict__ partial /*[grid][2][C]*/, float* __restrict__ dgamma_atomic,
+                      float* __restrict__ dbeta_atomic) {
     pdl_grid_sync();
     extern __shared__ float sm[];      // [8 warps][2][C]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -313,7 +316,7 @@ layernorm_bwd4_kernel(const float* __restrict__ x, long long ldx, const float* _
             }
         }
     }
-    if (partial == nullptr) return;
+    if (partial == nullptr && dgamma_atomic == nullptr) return;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
         const int c4 = lane + 32 * i;
@@ -327,10 +330,14 @@ layernorm_bwd4_kernel(const float* __restrict__ x, long long ldx, const float* _
         const int which = c / C, cc = c - which * C;
         float a = 0.f;
         for (int w = 0; w < 8; ++w) a += sm[(w * 2 + which) * C + cc];
-        partial[((long long)blockIdx.x * 2 + which) * C + cc] = a;
+        if (dgamma_atomic) atomicAdd((which ? dbeta_atomic : dgamma_atomic) + cc, a);   // straight into the gradient arena
+        else partial[((long long)blockIdx.x * 2 + which) * C + cc] = a;
     }
 }
 
+// Parameter gradients: by default every block adds its partial dgamma / dbeta straight into the gradient arena with
+// atomicAdd (they ACCUMULATE, like every parameter gradient of the backward; summation order not fixed).
+// RIFT_B200_LN_ATOMIC=0 restores the two-stage fixed-order reduction through `scratch` (+ colsum_final2 on `fin`).
 int launch_layernorm_bwd(const float* x, long long ldx, const float* dy, long long lddy, int rows, int C,
                          const float* gamma, const float* mean, const float* rstd, const float* y_for_relu, long long ldy,
                          float* dx, long long lddx, int dx_accumulate, float* dgamma, float* dbeta, float* scratch,
@@ -339,6 +346,11 @@ int launch_layernorm_bwd(const float* x, long long ldx, const float* dy, long lo
     RIFT_REQUIRE(C <= LNB_MAXC, "layernorm_bwd: C too large");
     RIFT_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "layernorm_bwd: dgamma/dbeta go together");
     RIFT_REQUIRE(dgamma == nullptr || scratch != nullptr, "layernorm_bwd: scratch required for parameter gradients");
+    static const bool atomic = [] { const char* e = getenv("RIFT_B200_LN_ATOMIC"); return !(e && atoi(e) == 0); }();
+    float* part = (dgamma && !atomic) ? scratch : nullptr;
+    float* dga = (dgamma && atomic) ? dgamma : nullptr;
+    float* dba = (dgamma && atomic) ? dbeta : nullptr;
+    int nb_used = 0;
     {
         auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
         const bool vec = (C & 3) == 0 && (ldx & 3) == 0 && (lddy & 3) == 0 && (ldy & 3) == 0 && (lddx & 3) == 0 && al16(x) &&
@@ -347,11 +359,10 @@ int launch_layernorm_bwd(const float* x, long long ldx, const float* dy, long lo
             // more, smaller blocks than the partial buffer has slots is not possible: LNB_BLOCKS partial rows
             const int nb4 = min(cdiv(rows, 8), LNB_BLOCKS);
             const size_t smem4 = (size_t)8 * 2 * C * sizeof(float);
-            float* part = dgamma ? scratch : nullptr;
             const int nv = cdiv(C, 128);
 #define RIFT_LNB4(NV)                                                                                                       \
     launch_k(layernorm_bwd4_kernel<NV>, nb4, 256, smem4, st, x, ldx, dy, lddy, rows, C, gamma, mean, rstd, y_for_relu, ldy, dx, \
-                                                       lddx, dx_accumulate, part)
+                                                       lddx, dx_accumulate, part, dga, dba)
             static bool attr4 = false;
             if (!attr4) {
                 RIFT_CUDA_OK(cudaFuncSetAttribute(layernorm_bwd4_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * LNB_MAXC * 4));
@@ -360,31 +371,27 @@ int launch_layernorm_bwd(const float* x, long long ldx, const float* dy, long lo
             if (nv <= 1) RIFT_LNB4(1); else if (nv == 2) RIFT_LNB4(2); else if (nv <= 4) RIFT_LNB4(4); else RIFT_LNB4(8);
 #undef RIFT_LNB4
             RIFT_LAUNCH_OK();
-            if (dgamma) {
-                cudaStream_t s2;
-                int r2 = second_stage_stream(st, fin, &s2);
-                if (r2) return r2;
-                launch_k(colsum_final2_kernel, dim3(cdiv(C, 32), 2), 1024, 0, s2, scratch, nb4, C, dgamma, dbeta);
-                RIFT_LAUNCH_OK();
-            }
-            return 0;
+            nb_used = nb4;
         }
     }
-    const int nb = min(cdiv(rows, 8), LNB_BLOCKS);
-    const size_t smem = (size_t)8 * 2 * C * sizeof(float);
-    static bool attr = false;
-    if (!attr) {
-        RIFT_CUDA_OK(cudaFuncSetAttribute(layernorm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * LNB_MAXC * 4));
-        attr = true;
+    if (!nb_used) {
+        const int nb = min(cdiv(rows, 8), LNB_BLOCKS);
+        const size_t smem = (size_t)8 * 2 * C * sizeof(float);
+        static bool attr = false;
+        if (!attr) {
+            RIFT_CUDA_OK(cudaFuncSetAttribute(layernorm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * LNB_MAXC * 4));
+            attr = true;
+        }
+        launch_k(layernorm_bwd_kernel, nb, 256, smem, st, x, ldx, dy, lddy, rows, C, gamma, mean, rstd, y_for_relu, ldy, dx, lddx,
+                                                    dx_accumulate, part, dga, dba);
+        RIFT_LAUNCH_OK();
+        nb_used = nb;
     }
-    launch_k(layernorm_bwd_kernel, nb, 256, smem, st, x, ldx, dy, lddy, rows, C, gamma, mean, rstd, y_for_relu, ldy, dx, lddx,
-                                                dx_accumulate, dgamma ? scratch : nullptr);
-    RIFT_LAUNCH_OK();
-    if (dgamma) {
+    if (part) {
         cudaStream_t s2;
         int r2 = second_stage_stream(st, fin, &s2);
         if (r2) return r2;
-        launch_k(colsum_final2_kernel, dim3(cdiv(C, 32), 2), 1024, 0, s2, scratch, nb, C, dgamma, dbeta);
+        launch_k(colsum_final2_kernel, dim3(cdiv(C, 32), 2), 1024, 0, s2, scratch, nb_used, C, dgamma, dbeta);
         RIFT_LAUNCH_OK();
     }
     return 0;

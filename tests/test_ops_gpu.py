@@ -82,6 +82,21 @@ def test_linear_tcgen05_all_outputs(rows, K, N, act, beta):
     assert (planes[:, N:] == 0).all(), "plane padding must be zero"
 
 
+@pytest.mark.parametrize("rows,N,K,splits", [(4608, 256, 256, 8), (4608, 768, 256, 4), (3328, 256, 1024, 2), (40960, 192, 64, 24),
+                                             (384, 256, 129, 3), (46080, 128, 256, 24), (100, 64, 64, 1)])
+def test_wgrad_tcgen05_atomic_accumulate_and_bias(rows, N, K, splits):
+    """dW += dY^T X with split-K parts added by red.global.add and db += colsum(dY) from the second tensor-core
+    accumulator, on top of non-zero running sums; fp32 tolerance 3e-5 of the result's scale."""
+    dY, X = rnd(rows, N, seed=11), rnd(rows, K, seed=12)
+    dW0, db0 = rnd(N, K, seed=13), rnd(N, seed=14)
+    dW, db = dW0.clone(), db0.clone()
+    L = _lib.lib()
+    scratch = torch.empty(L.rift_b200_op_wgrad_tc_scratch_bytes(rows, N, K), dtype=torch.uint8, device="cuda")
+    _lib.check(L.rift_b200_op_wgrad_tc(P(dY), P(X), rows, N, K, P(dW), P(db), splits, P(scratch), scratch.numel(), S()))
+    close(dW, dW0.double() + dY.double().t() @ X.double(), 3e-5, "dW")
+    close(db, db0.double() + dY.double().sum(0), 3e-5, "db")
+
+
 @pytest.mark.parametrize("layout", ["nt", "nn", "tn", "tt"])
 @pytest.mark.parametrize("M,N,K,split", [(65, 70, 33, 1), (256, 192, 4000, 8), (1, 256, 4608, 9)])
 def test_gemm_strides_and_split_k(layout, M, N, K, split):
