@@ -40,6 +40,10 @@ long long rift_b200_launch_count(void);
  * (64 uint64: 0 entry, 1 set-up done, 2 first operands landed, 3 first tile's MMAs issued, 4+2i / 5+2i
  * epilogue start / end of its i-th tile, 60 last role done, 61 TMEM released); NULL switches it off */
 void rift_b200_debug_gemm_trace(void* dev_buf);
+/* the same for the fused sub-block kernels (16 uint64: 0 set-up done, 1 dependency met, 2 LayerNorm planes written, 3 / 4 GEMM1
+ * starts / issued, 5 its accumulator complete, 6 / 7 GEMM2 starts / issued, 8 its accumulator complete, 9 partial tile written,
+ * 10 cluster barrier passed, 11 output stored, 12 TMEM released) */
+void rift_b200_debug_fused_trace(void* dev_buf);
 
 /* ---- model description (PlanningModel.__init__, pluto_model.py:23-44) ---- */
 typedef struct {
@@ -188,6 +192,14 @@ int rift_b200_op_linear_tc(const float* x, int rows, int K, const float* w, cons
 int rift_b200_op_linear_tc_full(const float* x, int rows, int K, const float* w, const float* bias, int N, int act,
                                 const float* res, float* y, float beta, float* preact, void* out_hi, void* out_lo, void* scratch,
                                 size_t scratch_bytes, void* stream);
+/* fused pre-LN MLP sub-block (one cluster kernel: LayerNorm -> fc1 + act -> fc2 + residual; layers/transformer.py:83-94):
+ * y = x + fc2(act(fc1(LN(x)))); optional outputs (may be NULL): LayerNorm mean / rstd [rows], LN(x) planes, fc1
+ * pre-activation [rows, Hd], hidden planes.  w1 [Hd, D], w2 [D, Hd]; resplit != 0 re-splits the weights into scratch */
+size_t rift_b200_op_fused_mlp_scratch_bytes(int D, int Hd);
+int rift_b200_op_fused_mlp(const float* x, int rows, int D, int Hd, int act, const float* ln_g, const float* ln_b,
+                           const float* w1, const float* b1, const float* w2, const float* b2, float* y, float* mean,
+                           float* rstd, void* t2_hi, void* t2_lo, float* hpre, void* hm_hi, void* hm_lo, void* scratch,
+                           size_t scratch_bytes, int resplit, void* stream);
 /* weight-gradient path of the tcgen05 GEMM: dW[N, K] += dY[rows, N]^T X[rows, K], db[N] += column sums of dY (db may be NULL);
  * split-K parts are added with red.global.add, the bias gradient comes from a second tensor-core accumulator */
 size_t rift_b200_op_wgrad_tc_scratch_bytes(int rows, int N, int K);

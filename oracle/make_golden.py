@@ -234,6 +234,59 @@ def buffer_pass_goldens():
     print("buffer_pass ok")
 
 
+class _State:
+    """Duck-typed CarlaAgentState: rear_axle.array / .heading, dynamic_car_state.center_velocity_2d.magnitude()."""
+
+    def __init__(self, x, y, heading, speed):
+        class _P: pass
+        self.rear_axle = _P(); self.rear_axle.array = np.array([x, y], np.float64); self.rear_axle.heading = float(heading)
+        v = _P(); v.magnitude = lambda s=float(speed): s
+        self.dynamic_car_state = _P(); self.dynamic_car_state.center_velocity_2d = v
+
+
+def get_action_goldens():
+    """The host half of get_action executed by the reference's own code: PLUTO._trim_candidates / _global_to_local
+    (pluto.py:196-278) and PIDController.control_pid (pid_controller.py:57-107) over a sequence of ticks."""
+    from scipy.special import softmax
+    trim = ref_shim.ref_method("rift/cbv/planning/pluto/pluto.py", "PLUTO", "_trim_candidates", {"softmax": softmax})
+    g2l = ref_shim.ref_method("rift/cbv/planning/pluto/pluto.py", "PLUTO", "_global_to_local")
+    PID = ref_shim.pid_controller_cls()
+    rng = np.random.Generator(np.random.PCG64(21))
+    out = {}
+    class _Self: _topk = 10
+    for case, (R, nvalid, with_free) in enumerate([(6, 6, True), (6, 2, True), (3, 1, False), (1, 1, True)]):
+        ctrl = PID(sample_interval=10)
+        for tick in range(4):
+            # forward-moving candidates: arc length grows along T so the PID sees plausible speeds
+            speed_c = rng.uniform(0.0, 12.0, (R, 12, 1))
+            s = np.cumsum(np.full((R, 12, 80), 0.1) * speed_c, -1)
+            curv = rng.normal(0, 0.02, (R, 12, 1))
+            th = curv * s
+            cand = np.stack([s * np.cos(th), s * np.sin(th), th], -1).astype(np.float32)
+            prob = rng.normal(0, 2.0, (R, 12)).astype(np.float32)
+            prob[nvalid:] = -1e6
+            free = None
+            if with_free:
+                sf = np.cumsum(np.full(80, 0.1) * rng.uniform(0, 10.0))
+                free = np.stack([sf, 0.05 * sf, np.full(80, 0.05)], -1).astype(np.float32)
+            st = _State(rng.normal(0, 50), rng.normal(0, 50), rng.normal(0, 1.5), rng.uniform(0, 10) if tick else 0.0)
+            traj, score, orig, n_ref, n_mode = trim(_Self, cand.astype(np.float64), prob, st,
+                                                    None if free is None else free.astype(np.float64))
+            best = int(score.argmax())
+            local = g2l(None, traj[best, 1:], st)
+            thr, steer, brake = ctrl.control_pid(local[:, :2], st.dynamic_car_state.center_velocity_2d.magnitude())
+            k = f"c{case}t{tick}_"
+            out[k + "cand"], out[k + "prob"] = cand, prob
+            if free is not None:
+                out[k + "free"] = free
+            out[k + "state"] = np.array([*st.rear_axle.array, st.rear_axle.heading, st.dynamic_car_state.center_velocity_2d.magnitude()])
+            out[k + "traj"], out[k + "score"], out[k + "orig"] = traj, score, orig
+            out[k + "local"] = local
+            out[k + "control"] = np.array([float(thr), float(steer), float(bool(brake))])
+    np.savez_compressed(os.path.join(GOLDEN, "get_action.npz"), **out)
+    print("get_action", len(out))
+
+
 def state_dict_spec():
     spec = {}
     for mname, kw in (("small", {}), ("medium", {})):
@@ -256,6 +309,8 @@ if __name__ == "__main__":
         advantage_goldens()
     if not only or "buf" in only:
         buffer_pass_goldens()
+    if not only or "act" in only:
+        get_action_goldens()
     for name, case in CASES.items():
         if not only or name in only:
             run_case(name, case)

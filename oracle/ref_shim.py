@@ -186,3 +186,32 @@ def ref_class(relpath: str, name: str, extra_globals=None):
             exec(compile(ast.Module([node], []), relpath, "exec"), g)
             return g[name]
     raise KeyError(name)
+
+
+def ref_method(relpath: str, cls: str, name: str, extra_globals=None):
+    """One method of a reference class as a plain function (first argument = self), without importing the file."""
+    import ast
+    import numpy as np
+    src = open(os.path.join(REF, relpath)).read()
+    for node in ast.parse(src).body:
+        if isinstance(node, ast.ClassDef) and node.name == cls:
+            for sub in node.body:
+                if isinstance(sub, ast.FunctionDef) and sub.name == name:
+                    g = {"torch": torch, "np": np, "npt": __import__("numpy.typing").typing}
+                    g.update(extra_globals or {})
+                    sub.returns = None
+                    for a in sub.args.args:
+                        a.annotation = None
+                    exec(compile(ast.Module([sub], []), relpath, "exec"), g)
+                    return g[name]
+    raise KeyError(f"{cls}.{name}")
+
+
+def pid_controller_cls():
+    """PIDController (rift/cbv/planning/pluto/controller/pid_controller.py) - the file imports only numpy / torch."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "_ref_pid", os.path.join(REF, "rift/cbv/planning/pluto/controller/pid_controller.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.PIDController

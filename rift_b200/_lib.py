@@ -61,6 +61,7 @@ _SIGNATURES = {
     "rift_b200_version": (C.c_int, []),
     "rift_b200_launch_count": (C.c_longlong, []),
     "rift_b200_debug_gemm_trace": (None, [_V]),
+    "rift_b200_debug_fused_trace": (None, [_V]),
     "rift_b200_create": (C.c_int, [C.POINTER(ModelConfig), C.POINTER(ParamEntry), C.c_int, C.POINTER(_V)]),
     "rift_b200_destroy": (None, [_V]),
     "rift_b200_bind_arena": (C.c_int, [_V, _V, _V, C.c_longlong]),
@@ -86,6 +87,9 @@ _SIGNATURES = {
     "rift_b200_weight_cache_bytes": (C.c_size_t, [_V]),
     "rift_b200_bind_weight_cache": (C.c_int, [_V, _V, C.c_size_t]),
     "rift_b200_params_updated": (C.c_int, [_V, C.c_int]),
+    "rift_b200_op_fused_mlp_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "rift_b200_op_fused_mlp": (C.c_int, [_V, C.c_int, C.c_int, C.c_int, C.c_int, _V, _V, _V, _V, _V, _V, _V, _V, _V, _V, _V, _V,
+                                         _V, _V, _V, C.c_size_t, C.c_int, _V]),
     "rift_b200_op_wgrad_tc_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "rift_b200_op_wgrad_tc": (C.c_int, [_V, _V, C.c_int, C.c_int, C.c_int, _V, _V, C.c_int, _V, C.c_size_t, _V]),
     "rift_b200_op_linear_tc_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),

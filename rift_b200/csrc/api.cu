@@ -5,6 +5,7 @@
 #include <new>
 
 #include "engine.h"
+#include "fused_block.h"
 
 namespace rift {
 static thread_local std::string g_last_error;
@@ -27,6 +28,7 @@ const char* rift_b200_last_error(void) { return get_last_error(); }
 int rift_b200_version(void) { return 100; }
 long long rift_b200_launch_count(void) { return g_kernel_launches; }
 void rift_b200_debug_gemm_trace(void* dev_buf) { set_gemm_tc_trace(dev_buf); }
+void rift_b200_debug_fused_trace(void* dev_buf) { set_fused_trace(dev_buf); }
 
 int rift_b200_create(const rift_b200_model_config* cfg, const rift_b200_param_entry* entries, int n_entries,
                      rift_b200_engine** out) {
@@ -263,6 +265,45 @@ int rift_b200_op_linear_tc_full(const float* x, int rows, int K, const float* w,
     r = launch_pack_split(x, K, rows, K, tw.Kp, ap, ap + aplane, S(stream));
     if (r) return r;
     return launch_gemm_tc(a, ap, ap + aplane, tw.Kp, tw, 0, 0, S(stream));
+}
+
+size_t rift_b200_op_fused_mlp_scratch_bytes(int D, int Hd) {
+    const size_t p1 = ((size_t)Hd * ((D + 63) / 64 * 64) * 2 + 255) & ~(size_t)255, p2 = ((size_t)D * ((Hd + 63) / 64 * 64) * 2 + 255) & ~(size_t)255;
+    return 2 * p1 + 2 * p2 + 1024;
+}
+
+// Pre-LN MLP sub-block y = x + fc2(act(fc1(LN(x)))) through the fused cluster kernel (fused_block.cu); the optional
+// outputs are the tensors the backward reads.  Splits w1 / w2 into planes inside `scratch` first (test / micro-benchmark use).
+int rift_b200_op_fused_mlp(const float* x, int rows, int D, int Hd, int act, const float* ln_g, const float* ln_b,
+                           const float* w1, const float* b1, const float* w2, const float* b2, float* y, float* mean,
+                           float* rstd, void* t2_hi, void* t2_lo, float* hpre, void* hm_hi, void* hm_lo, void* scratch,
+                           size_t scratch_bytes, int resplit, void* stream) {
+    RIFT_REQUIRE(x && w1 && w2 && y && scratch, "op_fused_mlp: null argument");
+    RIFT_REQUIRE(scratch_bytes >= rift_b200_op_fused_mlp_scratch_bytes(D, Hd), "op_fused_mlp: scratch too small");
+    RIFT_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 255) == 0, "op_fused_mlp: scratch must be 256-byte aligned");
+    RIFT_REQUIRE(fused_mlp_shape_ok(rows < 64 ? 64 : rows, D, Hd), "op_fused_mlp: unsupported shape");
+    TcWeight t1, t2;
+    t1.src = w1; t1.ld_src = D; t1.N = Hd; t1.K = D; t1.Kp = (D + 63) / 64 * 64;
+    t2.src = w2; t2.ld_src = Hd; t2.N = D; t2.K = Hd; t2.Kp = (Hd + 63) / 64 * 64;
+    const size_t p1 = ((size_t)Hd * t1.Kp * 2 + 255) & ~(size_t)255, p2 = ((size_t)D * t2.Kp * 2 + 255) & ~(size_t)255;
+    char* p = static_cast<char*>(scratch);
+    t1.hi = p; t1.lo = p + p1; t2.hi = p + 2 * p1; t2.lo = p + 2 * p1 + p2;
+    if (resplit) {
+        std::vector<char> jobs(2 * split_job_bytes());
+        fill_split_job(jobs.data(), w1, D, Hd, D, t1.Kp, t1.hi, t1.lo, 0, 0);
+        fill_split_job(jobs.data() + split_job_bytes(), w2, Hd, D, Hd, t2.Kp, t2.hi, t2.lo, split_job_units(Hd, t1.Kp), 0);
+        char* jd = p + 2 * p1 + 2 * p2;
+        RIFT_CUDA_OK(cudaMemcpyAsync(jd, jobs.data(), jobs.size(), cudaMemcpyHostToDevice, S(stream)));
+        RIFT_CUDA_OK(cudaStreamSynchronize(S(stream)));
+        int r = launch_split_weights(jd, 2, split_job_units(Hd, t1.Kp) + split_job_units(D, t2.Kp), S(stream));
+        if (r) return r;
+    }
+    FusedMlpArgs a;
+    a.X = x; a.ldx = D; a.Y = y; a.ldy = D; a.rows = rows; a.D = D; a.Hd = Hd; a.act = act;
+    a.ln_g = ln_g; a.ln_b = ln_b; a.b1 = b1; a.b2 = b2; a.ln_mean = mean; a.ln_rstd = rstd; a.hpre = hpre;
+    if (t2_hi && t2_lo) { a.t2p.hi = static_cast<uint16_t*>(t2_hi); a.t2p.lo = static_cast<uint16_t*>(t2_lo); a.t2p.Kp = t1.Kp; }
+    if (hm_hi && hm_lo) { a.hmp.hi = static_cast<uint16_t*>(hm_hi); a.hmp.lo = static_cast<uint16_t*>(hm_lo); a.hmp.Kp = t2.Kp; }
+    return launch_fused_mlp(a, t1, t2, S(stream));
 }
 
 size_t rift_b200_op_wgrad_tc_scratch_bytes(int rows, int N, int K) {

@@ -13,6 +13,7 @@
 #include <stdlib.h>
 
 #include "engine_ops.h"
+#include "fused_block.h"
 
 using namespace rift;
 
@@ -356,6 +357,44 @@ static int points_encoder(Ctx& c, Act& F, int groups, int n, const uint8_t* mask
     return 0;
 }
 
+// Pre-LN MLP sub-block X2 = X1 + fc2(act(fc1(LN(X1))))  (layers/transformer.py:83-94, planning_decoder.py:80-86, NATLayer MLP).
+// One fused cluster kernel (fused_block.cu) when the shape allows, else LayerNorm + two GEMMs.  With `tape` the tensors the
+// backward reads are kept: LayerNorm statistics, LN(X1) planes, the fc1 pre-activation and the hidden planes.
+struct MlpBlockTape { LNSave* ln; Act* t2; float** hpre; Act* hm; };
+static int mlp_block(Ctx& c, float* X1, int rows, const Norm& n2, const Lin& fc1, const Lin& fc2, int act, float* X2,
+                     bool keep_pre, const MlpBlockTape* tape) {
+    const int D = n2.C, Hd = fc1.N;
+    const bool fused = !c.simt && c.tcw && fc1.tc >= 0 && fc2.tc >= 0 && fc1.tc_n0 == 0 && fc1.tc_k0 == 0 && fc2.tc_n0 == 0 &&
+                       fc2.tc_k0 == 0 && fc1.b && fc2.b && fused_mlp_shape_ok(rows, D, Hd);
+    if (fused) {
+        FusedMlpArgs a;
+        a.X = X1; a.ldx = D; a.Y = X2; a.ldy = D; a.rows = rows; a.D = D; a.Hd = Hd; a.act = act;
+        a.ln_g = n2.g; a.ln_b = n2.b; a.b1 = fc1.b; a.b2 = fc2.b;
+        if (tape) {
+            Act t2, hm;
+            TRY(new_act(c, rows, D, W_P, &t2));
+            TRY(new_act(c, rows, Hd, W_P, &hm));
+            ALLOC(mean, float, rows);
+            ALLOC(rstd, float, rows);
+            ALLOC(hpre, float, (size_t)rows * Hd);
+            a.t2p = t2.p; a.hmp = hm.p; a.ln_mean = mean; a.ln_rstd = rstd; a.hpre = hpre;
+            tape->ln->x = X1; tape->ln->mean = mean; tape->ln->rstd = rstd; tape->ln->rows = rows;
+            *tape->t2 = t2; *tape->hm = hm; *tape->hpre = hpre;
+            c.used_fused = true;
+        }
+        if (c.dry) return 0;
+        return launch_fused_mlp(a, (*c.tcw)[fc1.tc], (*c.tcw)[fc2.tc], c.st);
+    }
+    float* hpre = nullptr;
+    if (tape && keep_pre) { hpre = c.alloc<float>((size_t)rows * Hd); if (!hpre) { set_last_error("workspace too small"); return -1; } }
+    Act t2, hm;
+    TRY(layernorm_new(c, X1, rows, n2, 0, want_in(c, rows, {&fc1}), &t2, tape ? tape->ln : nullptr));
+    { Epi e; e.act = act; e.preact = hpre; TRY(linear_new(c, t2, fc1, e, want_in(c, rows, {&fc2}), &hm)); }
+    { Epi e; e.res = X1; e.ldres = D; TRY(linear_into(c, hm, fc2, e, X2, D)); }
+    if (tape) { *tape->t2 = t2; *tape->hm = hm; *tape->hpre = hpre; }
+    return 0;
+}
+
 }  // namespace rift
 
 // =====================================================================================
@@ -428,18 +467,17 @@ int rift_b200_engine::forward(const rift_b200_batch& bt, const rift_b200_outputs
                 ALLOC(qkv, float, (size_t)rows * 3 * d);
                 ALLOC(x1, float, (size_t)rows * d);
                 ALLOC(x2, float, (size_t)rows * d);
-                float* hpre = nullptr;
-                if (full) { hpre = c.alloc<float>((size_t)rows * 3 * d); if (!hpre) { set_last_error("workspace too small"); return -1; } }
-                Act t1, att, t2, hm;
+                Act t1, att;
                 TRY(layernorm_new(c, x, rows, nb.n1, 0, want_in(c, rows, {&nb.qkv}), &t1, full ? &bt_.ln1 : nullptr));
                 TRY(linear_into(c, t1, nb.qkv, Epi(), qkv, 3 * d));
                 TRY(new_act(c, rows, d, want_in(c, rows, {&nb.proj}), &att));
                 if (!c.dry) TRY(launch_nat_attention(qkv, NA, L, lv.heads, d / lv.heads, lv.ksize, nb.rpb.p, att.f, c.st, att.p));
                 { Epi e; e.res = x; e.ldres = d; TRY(linear_into(c, att, nb.proj, e, x1, d)); }
-                TRY(layernorm_new(c, x1, rows, nb.n2, 0, want_in(c, rows, {&nb.fc1}), &t2, full ? &bt_.ln2 : nullptr));
-                { Epi e; e.act = ACT_GELU; e.preact = hpre; TRY(linear_new(c, t2, nb.fc1, e, want_in(c, rows, {&nb.fc2}), &hm)); }
-                { Epi e; e.res = x1; e.ldres = d; TRY(linear_into(c, hm, nb.fc2, e, x2, d)); }
-                bt_.t1 = t1; bt_.qkv = qkv; bt_.att = att; bt_.x1 = x1; bt_.t2 = t2; bt_.hpre = hpre; bt_.hm = hm;
+                {
+                    MlpBlockTape mt{&bt_.ln2, &bt_.t2, &bt_.hpre, &bt_.hm};
+                    TRY(mlp_block(c, x1, rows, nb.n2, nb.fc1, nb.fc2, ACT_GELU, x2, true, full ? &mt : nullptr));
+                }
+                bt_.t1 = t1; bt_.qkv = qkv; bt_.att = att; bt_.x1 = x1;
                 nt.blocks.push_back(bt_);
                 x = x2;
             }
@@ -579,12 +617,12 @@ int rift_b200_engine::forward(const rift_b200_batch& bt, const rift_b200_outputs
         ALLOC(qkv, float, (size_t)rowsE * 3 * D);
         ALLOC(X1, float, (size_t)rowsE * D);
         ALLOC(X2, float, (size_t)rowsE * D);
-        float *hpre = nullptr, *lse = nullptr;
+        float* lse = nullptr;
         if (full) {
-            hpre = c.alloc<float>((size_t)rowsE * 4 * D); lse = c.alloc<float>((size_t)bs * H * S);
-            if (!hpre || !lse) { set_last_error("workspace too small"); return -1; }
+            lse = c.alloc<float>((size_t)bs * H * S);
+            if (!lse) { set_last_error("workspace too small"); return -1; }
         }
-        Act t1, att, t2, hm;
+        Act t1, att;
         TRY(layernorm_new(c, X, rowsE, eb.n1, 0, want_in(c, rowsE, {&eb.attn.in}), &t1, full ? &et.ln1 : nullptr));
         TRY(linear_into(c, t1, eb.attn.in, Epi(), qkv, 3 * D));
         TRY(new_act(c, rowsE, D, want_in(c, rowsE, {&eb.attn.out}), &att));
@@ -598,10 +636,11 @@ int rift_b200_engine::forward(const rift_b200_batch& bt, const rift_b200_outputs
             TRY(launch_attention(a, c.st));
         }
         { Epi e; e.res = X; e.ldres = D; TRY(linear_into(c, att, eb.attn.out, e, X1, D)); }
-        TRY(layernorm_new(c, X1, rowsE, eb.n2, 0, want_in(c, rowsE, {&eb.fc1}), &t2, full ? &et.ln2 : nullptr));
-        { Epi e; e.act = ACT_GELU; e.preact = hpre; TRY(linear_new(c, t2, eb.fc1, e, want_in(c, rowsE, {&eb.fc2}), &hm)); }
-        { Epi e; e.res = X1; e.ldres = D; TRY(linear_into(c, hm, eb.fc2, e, X2, D)); }
-        et.t1 = t1; et.qkv = qkv; et.lse = lse; et.att = att; et.X1 = X1; et.t2 = t2; et.hpre = hpre; et.hm = hm;
+        {
+            MlpBlockTape mt{&et.ln2, &et.t2, &et.hpre, &et.hm};
+            TRY(mlp_block(c, X1, rowsE, eb.n2, eb.fc1, eb.fc2, ACT_GELU, X2, true, full ? &mt : nullptr));
+        }
+        et.t1 = t1; et.qkv = qkv; et.lse = lse; et.att = att; et.X1 = X1;
         T_.enc.push_back(et);
         X = X2;
     }
@@ -719,14 +758,13 @@ int rift_b200_engine::forward(const rift_b200_batch& bt, const rift_b200_outputs
         { Epi e; e.res = q2; e.ldres = D; TRY(linear_into(c, a3, db.cross.out, e, q3, D)); }
         // (iv) ReLU FFN
         ALLOC(q4, float, (size_t)rowsQ * D);
-        Act t4, hm;
-        TRY(layernorm_new(c, q3, rowsQ, db.n4, 0, want_in(c, rowsQ, {&db.ffn0}), &t4, full ? &dt.ln4 : nullptr));
-        { Epi e; e.act = ACT_RELU; TRY(linear_new(c, t4, db.ffn0, e, want_in(c, rowsQ, {&db.ffn3}), &hm)); }
-        { Epi e; e.res = q3; e.ldres = D; TRY(linear_into(c, hm, db.ffn3, e, q4, D)); }
+        {
+            MlpBlockTape mt{&dt.ln4, &dt.t4, &dt.hpre4, &dt.hm};
+            TRY(mlp_block(c, q3, rowsQ, db.n4, db.ffn0, db.ffn3, ACT_RELU, q4, false, full ? &mt : nullptr));
+        }
         dt.t1 = t1; dt.qkv1 = qkv1; dt.lse1 = lse1; dt.a1 = a1; dt.q1 = q1;
         dt.t2 = t2; dt.t2p = t2p; dt.qkv2 = qkv2; dt.lse2 = lse2; dt.a2 = a2; dt.q2 = q2;
         dt.t3 = t3; dt.qc = qc; dt.kvc = kvc; dt.lse3 = lse3; dt.a3 = a3; dt.q3 = q3;
-        dt.t4 = t4; dt.hm = hm;
         T_.dec.push_back(dt);
         q = q4;
     }
@@ -773,7 +811,7 @@ int rift_b200_engine::forward(const rift_b200_batch& bt, const rift_b200_outputs
         TRY(linear_into(c, hh, m.hidden2, Epi(), out.hidden, D));
     }
     if (out.ref_free_trajectory) TRY(mlp_layer(c, xego_rows, m.ref_free, out.ref_free_trajectory, 4 * T, nullptr));
-    if (!c.dry) { tp.valid = c.save; tp.full = full; }
+    if (!c.dry) { tp.valid = c.save; tp.full = full; tp.fused = c.used_fused; }
     fwd_ws_end = c.off;
     return 0;
 }

@@ -83,6 +83,7 @@ struct Ctx {            // per-call state: stream + bump allocator over the call
     bool save = false;     // keep what backward needs
     bool full = false;     // save && trainable parameters outside pi_head: keep every activation (fp32)
     bool tc_bwd = false;   // backward GEMMs on the tcgen05 path (false: exact-fp32 SIMT)
+    bool used_fused = false;   // forward: some sub-block ran as a fused kernel (its tape holds operand planes only, no fp32 copies)
     const std::vector<TcWeight>* tcw = nullptr;
     // fork / join streams (null: everything stays on `st`).  `side` carries parameter-gradient work of the
     // backward (weight-gradient GEMMs, bias / LayerNorm-parameter reductions), `br` whole independent branches
@@ -134,10 +135,10 @@ struct DecBlockTape {
     float* q = nullptr; LNSave ln1; Act t1; float* qkv1 = nullptr; float* lse1 = nullptr; Act a1; float* q1 = nullptr;
     LNSave ln2; Act t2; Act t2p; float* qkv2 = nullptr; float* lse2 = nullptr; Act a2; float* q2 = nullptr;
     LNSave ln3; Act t3; float* qc = nullptr; float* kvc = nullptr; float* lse3 = nullptr; Act a3; float* q3 = nullptr;
-    LNSave ln4; Act t4; Act hm;
+    LNSave ln4; Act t4; Act hm; float* hpre4 = nullptr;     // hpre4: fc1 pre-activation (fused forward), else null
 };
 struct Tape {
-    bool valid = false, full = false;
+    bool valid = false, full = false, fused = false;
     int bs = 0, A = 0, Mp = 0, P = 0, R = 0, Pr = 0, S = 0;
     uint8_t *agent_any = nullptr, *key_pad = nullptr, *r_pad = nullptr;
     NatTape nat; EgoTape ego;

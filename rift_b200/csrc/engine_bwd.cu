@@ -152,6 +152,8 @@ int rift_b200_engine::backward_impl(const rift_b200_batch& bt, const float* dlog
     const bool full = c.dry ? m.full : tape.full;
     c.tcw = &tcw;
     c.tc_bwd = !c.simt && wcache != nullptr;      // c.simt on entry = caller asked for the exact-fp32 path
+    RIFT_REQUIRE(c.dry || c.tc_bwd || !tape.fused, "backward: the exact-fp32 backward needs an exact-fp32 forward (the fused forward "
+                                                   "keeps operand planes only)");
     c.simt = true;                                // (forward-style routing helpers are not used below)
     c.full = full;
     Tape dry_tape;
@@ -197,7 +199,8 @@ int rift_b200_engine::backward_impl(const rift_b200_batch& bt, const float* dlog
         const Lin m2m_qk = slice(db.m2m.in, 0, 2 * D, 0, D, true), m2m_v = slice(db.m2m.in, 2 * D, D, 0, D, true);
         const Lin cr_q = slice(db.cross.in, 0, D, 0, D, true), cr_kv = slice(db.cross.in, D, 2 * D, 0, D, true);
         // (iv) ReLU FFN
-        TRY(mlp_tail_bwd(c, rowsQ, D, 4 * D, dt.hm, dt.hm.f, ACT_RELU, dt.t4, dt.ln4, db.n4, db.ffn0, db.ffn3, dq));
+        // ReLU'(.) from the post-activation values, or - after the fused forward, which keeps no fp32 hidden - from the pre-activation
+        TRY(mlp_tail_bwd(c, rowsQ, D, 4 * D, dt.hm, dt.hpre4 ? dt.hpre4 : dt.hm.f, ACT_RELU, dt.t4, dt.ln4, db.n4, db.ffn0, db.ffn3, dq));
         // (iii) cross-attention
         {
             ALLOC(d_a3, float, (size_t)rowsQ * D);

@@ -246,6 +246,13 @@ inline bool lin_bwd_all_tc(const Ctx& c, int M, const Lin& L, bool need_dx) {
     const bool tc_w = gemm_tc_shape_ok(L.N, L.K, M) && L.N >= 64 && (L.K % 4) == 0 && (L.ldw % 4) == 0;
     return tc_on && (!need_dx || tc_d) && (!want_w || tc_w);
 }
+// RIFT_B200_BWD_TERMS=1: the gradient products (dX = dY W, dW = dY^T X) run as plain bf16 (hi planes only) instead of
+// split-bf16 x3.  The 1e-3 tolerance of BASELINE.json is on logits and loss (forward: always x3); gradients are checked
+// by their norms (2e-3) - see DESIGN.md section 2 for the measured error of both forms.
+inline int bwd_terms() {
+    static const int t = [] { const char* e = getenv("RIFT_B200_BWD_TERMS"); return (e && atoi(e) == 1) ? 1 : 3; }();
+    return t;
+}
 inline int lin_bwd(Ctx& c, const float* X, long long ldx, const float* dY, long long lddy, int M, const Lin& L, float* dX,
                    long long lddx, float dx_beta, bool bias_grad = true, const Planes* Xp = nullptr,
                    const LinBwdFuse* fz = nullptr) {
@@ -338,6 +345,7 @@ inline int lin_bwd(Ctx& c, const float* X, long long ldx, const float* dY, long 
             a.C = L.dW; a.ldc = L.ldw; a.M = L.N; a.N = Kpad4; a.K = M;
             if (atomic_w) { a.atomic_out = true; if (b_in_wgrad) a.colsum_out = L.db; }
             else a.beta = 1.f;
+            a.terms = bwd_terms();
             if (w_padded) a.n_store = L.K;
             PlaneOp A{dYp.hi, dYp.lo, M, dYp.Kp, 0, 0};
             PlaneOp B{xp.hi, xp.lo, M, xp.Kp, 0, 0};
@@ -368,6 +376,7 @@ inline int lin_bwd(Ctx& c, const float* X, long long ldx, const float* dY, long 
             const TcWeight& wt = (*c.tcw)[L.tcT];          // planes [K_full, Np_full] of W^T; the slice origin swaps roles
             GemmArgs a;
             a.C = dX; a.ldc = lddx; a.M = M; a.N = Kd; a.K = L.N; a.beta = dx_beta;
+            a.terms = bwd_terms();
             if (fz) {
                 a.dact_ref = fz->dact_ref; a.lddact = fz->lddact; a.dact = fz->dact;
                 if (fz->dX_planes) a.out_planes = *fz->dX_planes;

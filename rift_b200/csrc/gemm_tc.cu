@@ -68,6 +68,8 @@ struct TcKernelArgs {
                              // slabs, no reduce kernel; C was zeroed by the caller)
     int n_store;             // atomic mode, > 0: only columns [0, n_store) exist in C (arbitrary ldc): scalar reds
     float* colsum;           // MN-major (dW = dY^T X) only: colsum[m] += sum_k A[k, m] (bias gradient), from the tensor core
+    int terms;               // 3: split-bf16 x3 (A_lo B_hi + A_hi B_lo + A_hi B_hi); 1: plain bf16 (hi planes only: a third of the
+                             // MMA work, half the operand bytes) - backward products whose tolerance allows it
     int dbg;                 // bottleneck experiments only (RIFT_B200_TC_DBG)
     unsigned long long* trace;   // profiling aid (rift_b200_debug_gemm_trace): CTA 0 writes %globaltimer stamps
 };
@@ -182,19 +184,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                     uint8_t* b_hi = a_lo + SM::A_TILE;
                     uint8_t* b_lo = b_hi + SM::B_TILE;
                     if (g.dbg & 2) { mbar_arrive(&full[s]); continue; }
-                    mbar_arrive_expect_tx(&full[s], SM::STAGE);
+                    const bool lo = g.terms != 1;
+                    mbar_arrive_expect_tx(&full[s], lo ? SM::STAGE : SM::STAGE / 2);
                     const int ka = g.a_k0 + kb * TC_BK, kbb = g.b_k0 + kb * TC_BK;
 #pragma unroll
                     for (int rb = 0; rb < TC_BM / 64; ++rb) {
                         const int mn = g.a_mn0 + m0 + rb * 64;
                         tma_load_2d(a_hi + rb * TC_BOX, &tmA_hi, &full[s], MN ? mn : ka, MN ? ka : mn);
-                        tma_load_2d(a_lo + rb * TC_BOX, &tmA_lo, &full[s], MN ? mn : ka, MN ? ka : mn);
+                        if (lo) tma_load_2d(a_lo + rb * TC_BOX, &tmA_lo, &full[s], MN ? mn : ka, MN ? ka : mn);
                     }
 #pragma unroll
                     for (int rb = 0; rb < BN / 64; ++rb) {
                         const int mn = g.b_mn0 + n0 + rb * 64;
                         tma_load_2d(b_hi + rb * TC_BOX, &tmB_hi, &full[s], MN ? mn : kbb, MN ? kbb : mn);
-                        tma_load_2d(b_lo + rb * TC_BOX, &tmB_lo, &full[s], MN ? mn : kbb, MN ? kbb : mn);
+                        if (lo) tma_load_2d(b_lo + rb * TC_BOX, &tmB_lo, &full[s], MN ? mn : kbb, MN ? kbb : mn);
                     }
                 }
             }
@@ -231,12 +234,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                         if (g.dbg & 4) break;
                         const uint64_t dah = make_sdesc(a_hi + k * kstep, lbo), dal = make_sdesc(a_lo + k * kstep, lbo);
                         const uint64_t dbh = make_sdesc(b_hi + k * kstep, lbo), dbl = make_sdesc(b_lo + k * kstep, lbo);
-                        umma_bf16(tacc, dal, dbh, idesc, (kb > kb0 || k > 0) ? 1u : 0u);     // small terms first
-                        umma_bf16(tacc, dah, dbl, idesc, 1);
-                        umma_bf16(tacc, dah, dbh, idesc, 1);
+                        const uint32_t first = (kb > kb0 || k > 0) ? 1u : 0u;
+                        if (g.terms != 1) {
+                            umma_bf16(tacc, dal, dbh, idesc, first);     // small terms first
+                            umma_bf16(tacc, dah, dbl, idesc, 1);
+                            umma_bf16(tacc, dah, dbh, idesc, 1);
+                        } else {
+                            umma_bf16(tacc, dah, dbh, idesc, first);
+                        }
                         if (MN && cs_tile) {
-                            umma_bf16(tcs, dal, d_ones, make_idesc_colsum(), (kb > kb0 || k > 0) ? 1u : 0u);
-                            umma_bf16(tcs, dah, d_ones, make_idesc_colsum(), 1);
+                            if (g.terms != 1) {
+                                umma_bf16(tcs, dal, d_ones, make_idesc_colsum(), first);
+                                umma_bf16(tcs, dah, d_ones, make_idesc_colsum(), 1);
+                            } else {
+                                umma_bf16(tcs, dah, d_ones, make_idesc_colsum(), first);
+                            }
                         }
                     }
                     umma_commit(&empty[s]);                      // frees the stage once these MMAs retire
@@ -986,6 +998,9 @@ static int plane_map(const void* plane, int rows, int pitch, const CUtensorMap**
     return 0;
 }
 
+// the same cache for the other tcgen05 kernels (fused_block.cu)
+int tc_plane_map(const void* plane, int rows, int pitch, const CUtensorMap** out) { return plane_map(plane, rows, pitch, out); }
+
 // output-side tensor maps of the v2 kernel: fp32 [rows, cols] (row pitch ld floats) with a 32 x 32 box / 128 B swizzle,
 // bf16 plane [rows, Kp] with a 32 x 32 box / 64 B swizzle
 struct OutMapKey {
@@ -1032,7 +1047,7 @@ static bool tc2_takes(const GemmArgs& a, int BN, int sms) {
     const int b_bytes = num_kb * 2 * BN * TC_BK * 2;
     const int stages_fit = (227 * 1024 - 1024 - 256 - TC2_EPI_BYTES - b_bytes) / TC2_A_STAGE;
     static const int min_stages = [] { const char* e = getenv("RIFT_B200_GEMM_V2_MIN_STAGES"); return e ? atoi(e) : 3; }();
-    return tiles >= 2LL * sms && stages_fit >= min_stages && a.alpha == 1.f && (a.beta == 0.f || a.beta == 1.f) && !a.dact_ref && a.n_store <= 0 &&
+    return a.terms != 1 && tiles >= 2LL * sms && stages_fit >= min_stages && a.alpha == 1.f && (a.beta == 0.f || a.beta == 1.f) && !a.dact_ref && a.n_store <= 0 &&
            cdiv(a.N, BN) <= sms;
 }
 
@@ -1071,7 +1086,7 @@ static int launch_tc2(const GemmArgs& a, const PlaneOp& A, const PlaneOp& B, cud
     g.M = a.M; g.N = a.N; g.K = a.K;
     g.a_mn0 = A.mn0; g.a_k0 = A.k0; g.b_mn0 = B.mn0; g.b_k0 = B.k0;
     g.out = a.out_planes;
-    g.trace = nullptr; g.dbg = 0;
+    g.trace = nullptr; g.dbg = 0; g.atomic = 0; g.n_store = 0; g.colsum = nullptr; g.terms = 3;
     g.splits = 1; g.kb_per_split = num_kb; g.split_stride = 0;
     g.C = a.C; g.ldc = a.ldc;
     g.ep = TcEpilogue{a.bias, a.colscale, a.pre, a.ldpre, a.pre_div, a.res, a.ldres, a.res_div, a.res_mod, a.act, a.beta,
@@ -1120,7 +1135,7 @@ static int launch_tc(const GemmArgs& a, const PlaneOp& A, const PlaneOp& B, int 
     g.trace = g_tc_trace;
     { static int dbg = -1; if (dbg < 0) { const char* e = getenv("RIFT_B200_TC_DBG"); dbg = e ? atoi(e) : 0; } g.dbg = dbg; }
     const bool via_ws = !a.atomic_out && (splits > 1 || a.n_store > 0);       // raw sums into the partial buffer, epilogue in the reduce
-    g.atomic = 0; g.n_store = 0; g.colsum = nullptr;
+    g.atomic = 0; g.n_store = 0; g.colsum = nullptr; g.terms = a.terms == 1 ? 1 : 3;
     if (a.atomic_out) {
         // weight gradients: every (tile, split) adds its raw sums straight into C (zeroed by the caller)
         if (splits < 1) splits = 1;

@@ -55,6 +55,7 @@ struct GemmArgs {
     // tcgen05 path, backward of an activation fused into the data-gradient product: the result is multiplied by
     // act'(dact_ref[m, n]) (ReLU: dact_ref = the activation's OUTPUT; GELU: its pre-activation input), pitch lddact
     const float* dact_ref = nullptr; long long lddact = 0; int dact = 0;
+    int terms = 3;                       // tcgen05 path: 3 = split-bf16 x3 products, 1 = plain bf16 (hi planes only)
     bool atomic_out = false;             // tcgen05 path: C += raw product with red.global.add from every (tile, split-K part):
                                          // no partial slabs, no reduce kernel, summation order not fixed (weight gradients)
     float* colsum_out = nullptr;         // with atomic_out on the MN-major (dW = dY^T X) form: colsum_out[m] += sum_k A[k, m]

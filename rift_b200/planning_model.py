@@ -144,6 +144,7 @@ class PlanningModel:
         _lib.check(L.rift_b200_bind_weight_cache(self._engine, _lib.ptr(self._wcache), self._wcache.numel()),
                    "bind_weight_cache")
         self._ws_shape = None
+        self.ws_generation += 1       # engine, arenas and weight planes were rebuilt: anything captured against them is stale
 
     def params_updated(self, trainable_only: bool = False):
         """Tell the engine the fp32 arena changed (optimizer step / checkpoint load): the bf16 weight

@@ -243,3 +243,38 @@ def test_masked_maxpool():
     hit = arg >= 0
     assert torch.equal(torch.gather(x, 1, arg.clamp(min=0).long().unsqueeze(1)).squeeze(1)[hit], ref[hit])
     assert (ref[~hit] == 0).all()
+
+
+def _planes(hi, lo):
+    return hi.view(torch.bfloat16).double() + lo.view(torch.bfloat16).double()
+
+
+@pytest.mark.parametrize("rows,D,Hd,act", [(4608, 256, 1024, 1), (3328, 256, 1024, 2), (300, 128, 512, 2), (40960, 64, 192, 2),
+                                           (20480, 128, 384, 2), (10240, 256, 768, 2), (100, 256, 1024, 1), (129, 64, 192, 1)])
+def test_fused_mlp_block(rows, D, Hd, act):
+    """One cluster kernel for y = x + fc2(act(fc1(LN(x)))) against fp64 torch: result, LayerNorm statistics, and the
+    tensors saved for the backward (LN(x) planes, fc1 pre-activation, hidden planes); tolerance 3e-5 of each scale."""
+    x = rnd(rows, D, seed=1, scale=2.0)
+    g, b = 1 + 0.1 * rnd(D, seed=2), 0.1 * rnd(D, seed=3)
+    w1, b1 = rnd(Hd, D, seed=4, scale=D ** -0.5), 0.1 * rnd(Hd, seed=5)
+    w2, b2 = rnd(D, Hd, seed=6, scale=Hd ** -0.5), 0.1 * rnd(D, seed=7)
+    y = torch.full((rows, D), float("nan"), device="cuda")
+    mean, rstd = torch.empty(rows, device="cuda"), torch.empty(rows, device="cuda")
+    t2h, t2l = (torch.full((rows, D), 0x7fc0, dtype=torch.int16, device="cuda") for _ in range(2))
+    hmh, hml = (torch.full((rows, Hd), 0x7fc0, dtype=torch.int16, device="cuda") for _ in range(2))
+    hpre = torch.full((rows, Hd), float("nan"), device="cuda")
+    L = _lib.lib()
+    scratch = torch.empty(L.rift_b200_op_fused_mlp_scratch_bytes(D, Hd), dtype=torch.uint8, device="cuda")
+    _lib.check(L.rift_b200_op_fused_mlp(P(x), rows, D, Hd, act, P(g), P(b), P(w1), P(b1), P(w2), P(b2), P(y), P(mean), P(rstd),
+                                        P(t2h), P(t2l), P(hpre), P(hmh), P(hml), P(scratch), scratch.numel(), 1, S()))
+    xd = x.double()
+    t2 = TF.layer_norm(xd, (D,), g.double(), b.double(), 1e-5)
+    pre = TF.linear(t2, w1.double(), b1.double())
+    hm = TF.relu(pre) if act == 1 else TF.gelu(pre)
+    ref = xd + TF.linear(hm, w2.double(), b2.double())
+    close(mean, xd.mean(1), 1e-5, "mean")
+    close(rstd, (xd.var(1, unbiased=False) + 1e-5).rsqrt(), 1e-5, "rstd")
+    close(_planes(t2h, t2l), t2, 3e-5, "LN planes")
+    close(hpre, pre, 3e-5, "pre-activation")
+    close(_planes(hmh, hml), hm, 3e-5, "hidden planes")
+    close(y, ref, 3e-5, "result")

@@ -184,3 +184,113 @@ def test_ppo_full_backward_matches_reference_golden(name):
                 abs(float(gv.sum()) - stats[i, 0]) > 2e-3 * stats[i, 1] * np.sqrt(gv.numel()) + 1e-6 * gmax:
             bad.append((n, l2, stats[i, 1], float(gv.sum()), stats[i, 0]))
     assert not bad, f"{len(bad)} tensors differ, first: {bad[:5]}"
+
+
+# ------------------------------------------------------------------ get_action (rollout side of the plugin)
+class _P:
+    pass
+
+
+def _agent_state(x, y, heading, speed):
+    """Duck-typed CarlaAgentState: what get_action reads (rear_axle.array / .heading, centre speed)."""
+    s = _P()
+    s.rear_axle = _P(); s.rear_axle.array = np.array([x, y], np.float64); s.rear_axle.heading = float(heading)
+    s.dynamic_car_state = _P(); s.dynamic_car_state.center_velocity_2d = _P()
+    s.dynamic_car_state.center_velocity_2d.magnitude = lambda v=float(speed): v
+    return s
+
+
+class _World:
+    """Recorded world with the CarlaDataProvider calls get_action makes (carla_data_provider.py:192,619,665,1031)."""
+
+    def __init__(self, ids, seed=0):
+        rng = np.random.default_rng(seed)
+        self.hist = {i: [_agent_state(*rng.normal(0, 20, 2), rng.normal(0, 1), rng.uniform(0, 8)) for _ in range(3)] for i in ids}
+
+    def get_actor_by_id(self, i):
+        a = _P(); a.id = i
+        return a
+
+    def get_history_state(self, actor):
+        return self.hist[actor.id]
+
+    def get_ego_vehicle_by_env_id(self, env_id):
+        e = _P(); e.id = 1000 + env_id
+        return e
+
+    def get_CBV_nearby_agents(self, ego_id, cbv_id):
+        return []
+
+
+class _Evaluator:
+    """Stand-in roll-out evaluator: deterministic pseudo-returns per candidate (the real one is the reference's
+    TrajEvaluator or the CUDA evaluator); the plugin normalises them with the bit-exact advantage kernel."""
+
+    def get_rollout_returns(self, history, raw_trajectories, ref_pos, ref_ang, nearby):
+        t = raw_trajectories.detach().double().cpu().numpy()
+        return -np.abs(t[..., :40, :2]).sum((-1, -2)).reshape(-1) - 3.0 * np.arange(t.shape[0] * t.shape[1])
+
+
+@pytest.mark.parametrize("policy_name", ["rift_pluto", "grpo_pluto", "ppo_pluto"])
+def test_get_action_keys_values_and_graph_replay(policy_name, tmp_path):
+    """get_action(CBVs_obs_list, infos) -> the reference's return keys (rift_pluto.py:66-70, grpo_pluto.py:76-81,
+    rlft_pluto.py:131-135); old / reference logits are the model's logits of the valid reference lines, the group
+    advantage is numpy-exact, and the CUDA-graph replay over padded shape buckets returns what the eager forward does."""
+    cfg = pluto_small()
+    pre = tmp_path / "pretrained.ckpt"
+    sd = {k: torch.from_numpy(v) for k, v in synth_state_dict(cfg, seed=7).items()}
+    torch.save({"state_dict": {"model." + k: v for k, v in sd.items()}}, pre)
+    config = {"ckpt_path": str(pre), "ROOT_DIR": str(tmp_path), "model_path": "models", "load_agent_info": policy_name,
+              "obs": {"radius": 120}, "frame_rate": 10, "num_scenario": 2, "topk": 10,
+              "ppo": {"hidden_dim": [256, 256], "clip_epsilon": 0.2, "lambda_entropy": 0.01}}
+    pol = CBV_POLICY_LIST[policy_name](config)
+    pol.load_model(resume=True)
+    pol.set_mode("train")
+    buf = _make_buffer(5, seed=9)
+    obs0 = {101 + i: {"raw_pluto_feature": buf.items[i]["CBVs_obs"]["raw_pluto_feature"]} for i in range(3)}
+    obs1 = {201 + i: {"raw_pluto_feature": buf.items[3 + i]["CBVs_obs"]["raw_pluto_feature"]} for i in range(2)}
+    infos = [{"env_id": 0}, {"env_id": 1}]
+    pol.set_world(_World(list(obs0) + list(obs1)))
+    pol.set_traj_evaluator(_Evaluator())
+    results = {}
+    for graph in (False, True, True):                 # second graphed call replays the captured graph
+        pol.use_rollout_graph = graph
+        pol.controllers.clear()
+        results[graph] = pol.get_action([obs0, obs1], infos, deterministic=True)
+    ref_out = pol.pluto_model.forward(PlutoFeature.collate([o["raw_pluto_feature"] for o in obs0.values()]).data, outputs=())
+    for graph, data in results.items():
+        assert len(data["CBVs_actions"]) == 2 and set(data["CBVs_actions"][0]) == set(obs0) and set(data["CBVs_actions"][1]) == set(obs1)
+        for env, obs in ((0, obs0), (1, obs1)):
+            for cid in obs:
+                thr, steer, brake = data["CBVs_actions"][env][cid]
+                assert 0.0 <= float(thr) <= 1.0 and -1.0 <= float(steer) <= 1.0 and bool(brake) in (True, False)
+        if policy_name == "ppo_pluto":
+            assert set(data) == {"CBVs_actions", "CBVs_actions_old_log_prob", "CBVs_actions_mode"}
+            for cid in obs0:
+                r, m = data["CBVs_actions_mode"][0][cid]
+                assert 0 <= r < 3 and 0 <= m < 12 and float(data["CBVs_actions_old_log_prob"][0][cid]) <= 0.0
+            continue
+        want = {"CBVs_actions", "CBVs_actions_old_group_logits", "CBVs_group_advantage"}
+        if policy_name == "grpo_pluto":
+            want.add("CBVs_actions_ref_group_logits")
+        assert set(data) == want
+        for index, cid in enumerate(obs0):
+            f = obs0[cid]["raw_pluto_feature"].data
+            R = f["reference_line"]["position"].shape[0]
+            old = data["CBVs_actions_old_group_logits"][0][cid]
+            assert old["logits"].shape == (R, 12) and old["valid_mask"].all()
+            got = torch.from_numpy(old["logits"])
+            assert (got - ref_out["probability"][index, :R].cpu()).abs().max() <= 1e-4 * ref_out["probability"][index, :R].abs().max().cpu()
+            if policy_name == "grpo_pluto":      # the frozen reference policy = the pretrained checkpoint = same weights here
+                assert np.allclose(data["CBVs_actions_ref_group_logits"][0][cid]["logits"], old["logits"], rtol=0, atol=1e-5)
+            adv = data["CBVs_group_advantage"][0][cid]
+            assert adv["advantage"].shape == (R, 12) and adv["advantage"].dtype == np.float64
+            assert abs(adv["advantage"].mean()) < 1e-9 and abs(adv["advantage"].std() - 1.0) < 1e-3
+    # eager and graphed calls agree (same kernels, same inputs; padded rows are masked)
+    a, b = results[False], results[True]
+    for env in (0, 1):
+        for cid in a["CBVs_actions"][env]:
+            assert np.allclose(np.array(a["CBVs_actions"][env][cid], float), np.array(b["CBVs_actions"][env][cid], float), atol=1e-4)
+    # CBVs that left the scene lose their PID state (pluto.py:114-125)
+    pol.get_action([{101: obs0[101]}, {}], infos, deterministic=True)
+    assert set(pol.controllers[0]) == {101} and 1 not in pol.controllers
