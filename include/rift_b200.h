@@ -86,6 +86,12 @@ typedef struct {
     const uint8_t* ref_valid_mask;           /* (bs, R, Pr)         */
     const float* current_state;              /* (bs, cs_stride), first state_channel columns used */
     int cs_stride;
+    /* Micro-batching: when this struct describes samples [b_offset, b_offset + bs) of a larger collated batch, give the
+     * WHOLE batch's reference-line mask and size.  The reference masks r2r attention row j = b * Mo + m with
+     * r_pad[j % bs] (planning_decoder.py:56-60), which depends on the position inside the whole batch; with these
+     * fields a slice computes exactly what the whole batch would.  NULL / 0 = this struct is the whole batch. */
+    const uint8_t* ref_valid_mask_global;    /* (bs_global, R, Pr) */
+    int bs_global, b_offset;
 } rift_b200_batch;
 
 /* Outputs of PlanningModel.forward; any pointer may be NULL to skip materialising that tensor. */
@@ -115,6 +121,8 @@ size_t rift_b200_workspace_bytes(const rift_b200_engine* e, const rift_b200_batc
  * the next forward. */
 size_t rift_b200_weight_cache_bytes(const rift_b200_engine* e);
 int rift_b200_bind_weight_cache(rift_b200_engine* e, void* cache, size_t bytes);
+/* trainable_only: 1 = the trainable entries changed, 0 = everything changed, 2 = mark this engine's planes CLEAN (they live
+ * in a weight cache shared with another engine of the same layout, which refreshes them) */
 int rift_b200_params_updated(rift_b200_engine* e, int trainable_only);
 /* re-split whatever rift_b200_params_updated marked stale NOW, on `stream` (a captured CUDA graph replays device
  * work only: after a checkpoint load the frozen planes must be refreshed eagerly, not by the next eager forward) */
@@ -181,7 +189,19 @@ int rift_b200_clip_adamw_dev(float* p, const float* g, float* m, float* v, long 
                              const double* count, float max_norm, float* hyper, float beta1, float beta2, float eps,
                              float weight_decay, void* scratch, float* scal_out, void* stream);
 
+/* ---- device-resident replay buffer: GPU collate (cbv_rollout_buffer.py:16-138 + pluto_feature.py:25-96 + rift_datamodule.py:20-51)
+ * One field = one tensor of the buffer arena laid out [capacity][item_stride_bytes]; the gather copies the first copy_bytes
+ * bytes of slot idx[b] to dst + b * dst_stride_bytes for every b < bs (zero padding beyond an item's own extent is already in
+ * the slot).  `fields` is a HOST array (passed to the kernel by value), idx a device array of bs slot indices. */
+#define RIFT_B200_GATHER_MAX_FIELDS 40
+typedef struct {
+    const void* src; void* dst;
+    long long item_stride_bytes, copy_bytes, dst_stride_bytes;
+} rift_b200_gather_field;
+int rift_b200_gather_fields(const rift_b200_gather_field* fields, int n_fields, const long long* idx, int bs, void* stream);
+
 /* ---- primitive operators exported for the kernel-level parity tests (tests/test_ops_gpu.py) ---- */
+int rift_b200_op_add_inplace(float* dst, const float* src, long long n, void* stream);      /* dst += src */
 int rift_b200_op_linear(const float* x, int rows, int K, const float* w, const float* bias, int N, int act,
                         const float* res, float* y, int simt, void* stream);
 size_t rift_b200_op_linear_tc_scratch_bytes(int rows, int N, int K);

@@ -40,7 +40,13 @@ class Batch(C.Structure):
         ("ref_position", C.c_void_p), ("ref_vector", C.c_void_p), ("ref_orientation", C.c_void_p),
         ("ref_valid_mask", C.c_void_p),
         ("current_state", C.c_void_p), ("cs_stride", C.c_int),
+        ("ref_valid_mask_global", C.c_void_p), ("bs_global", C.c_int), ("b_offset", C.c_int),
     ]
+
+
+class GatherField(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("item_stride_bytes", C.c_longlong), ("copy_bytes", C.c_longlong),
+                ("dst_stride_bytes", C.c_longlong)]
 
 
 class Outputs(C.Structure):
@@ -83,6 +89,8 @@ _SIGNATURES = {
     "rift_b200_clip_adamw_dev": (C.c_int, [_V, _V, _V, _V, C.c_longlong, C.c_longlong, _V, C.c_float, _V, C.c_float,
                                            C.c_float, C.c_float, C.c_float, _V, _V, _V]),
     "rift_b200_refresh_weights": (C.c_int, [_V, _V]),
+    "rift_b200_gather_fields": (C.c_int, [C.POINTER(GatherField), C.c_int, _V, C.c_int, _V]),
+    "rift_b200_op_add_inplace": (C.c_int, [_V, _V, C.c_longlong, _V]),
     "rift_b200_op_linear": (C.c_int, [_V, C.c_int, C.c_int, _V, _V, C.c_int, C.c_int, _V, _V, C.c_int, _V]),
     "rift_b200_weight_cache_bytes": (C.c_size_t, [_V]),
     "rift_b200_bind_weight_cache": (C.c_int, [_V, _V, C.c_size_t]),

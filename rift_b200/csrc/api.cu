@@ -106,7 +106,9 @@ int rift_b200_bind_weight_cache(rift_b200_engine* e, void* cache, size_t bytes) 
 
 int rift_b200_params_updated(rift_b200_engine* e, int trainable_only) {
     RIFT_REQUIRE(e != nullptr, "params_updated: null engine");
-    if (trainable_only) e->dirty_train = true; else e->dirty_all = true;
+    if (trainable_only == 2) { e->dirty_train = false; e->dirty_all = false; }
+    else if (trainable_only) e->dirty_train = true;
+    else e->dirty_all = true;
     return 0;
 }
 
@@ -396,6 +398,10 @@ int rift_b200_op_nat_attention_bwd(const float* qkv, const float* d_out, int n_s
 
 int rift_b200_op_act_bwd(const float* ref, float* dy, long long n, int act, void* stream) {
     return launch_act_bwd(ref, dy, n, act, S(stream));
+}
+
+int rift_b200_op_add_inplace(float* dst, const float* src, long long n, void* stream) {
+    return launch_add_inplace(dst, src, n, S(stream));
 }
 
 int rift_b200_op_colsum(const float* x, int rows, int C, float* out, int accumulate, float* scratch, void* stream) {

@@ -365,7 +365,7 @@ static int mlp_block(Ctx& c, float* X1, int rows, const Norm& n2, const Lin& fc1
                      bool keep_pre, const MlpBlockTape* tape) {
     const int D = n2.C, Hd = fc1.N;
     const bool fused = !c.simt && c.tcw && fc1.tc >= 0 && fc2.tc >= 0 && fc1.tc_n0 == 0 && fc1.tc_k0 == 0 && fc2.tc_n0 == 0 &&
-                       fc2.tc_k0 == 0 && fc1.b && fc2.b && fused_mlp_shape_ok(rows, D, Hd);
+                       fc2.tc_k0 == 0 && fc1.b && fc2.b && fused_blocks_enabled() && fused_mlp_shape_ok(rows, D, Hd);
     if (fused) {
         FusedMlpArgs a;
         a.X = X1; a.ldx = D; a.Y = X2; a.ldy = D; a.rows = rows; a.D = D; a.Hd = Hd; a.act = act;
@@ -432,6 +432,16 @@ int rift_b200_engine::forward(const rift_b200_batch& bt, const rift_b200_outputs
             RIFT_CUDA_OK(cudaMemcpyAsync(out.r_padding_mask, r_pad, (size_t)bs * R, cudaMemcpyDeviceToDevice, c.st));
     }
     T_.agent_any = agent_any; T_.key_pad = key_pad; T_.r_pad = r_pad;
+    // r2r key padding of a micro-batch: the mask rows of the whole batch, indexed with this slice's offset
+    const uint8_t* r_pad_r2r = r_pad;
+    int r2r_mod = bs, r2r_off = 0;
+    if (bt.ref_valid_mask_global && bt.bs_global > bs) {
+        ALLOC(rg_any, uint8_t, (size_t)bt.bs_global * R);
+        ALLOC(rg_pad, uint8_t, (size_t)bt.bs_global * R);
+        if (!c.dry) TRY(launch_mask_any(bt.ref_valid_mask_global, bt.bs_global * R, Pr, rg_any, rg_pad, c.st));
+        r_pad_r2r = rg_pad; r2r_mod = bt.bs_global; r2r_off = bt.b_offset * cfg.num_modes;
+    }
+    T_.r_pad_r2r = r_pad_r2r; T_.r2r_mod = r2r_mod; T_.r2r_off = r2r_off;
     ALLOC(tokens, float, (size_t)bs * S * D);
     // The map encoder and the reference-line encoder / query initialisation depend only on the inputs: they run
     // on the branch stream next to the agent encoder (joined before pos_emb and before the decoder respectively).
@@ -714,7 +724,7 @@ int rift_b200_engine::forward(const rift_b200_batch& bt, const rift_b200_outputs
             // The reference passes key_padding_mask = r_pad.repeat(Mo, 1) for a batch laid out (b, m)
             // (planning_decoder.py:56-60): batch row j = b*Mo + m is masked with r_pad[j % bs], not with
             // r_pad[b].  Reproduced as is - parity is defined by what the reference computes.
-            a.kpm = r_pad; a.kpm_mod = bs; a.scale = att_scale; a.lse = lse1;
+            a.kpm = r_pad_r2r; a.kpm_mod = r2r_mod; a.kpm_off = r2r_off; a.scale = att_scale; a.lse = lse1;
             TRY(launch_attention(a, c.st));
         }
         { Epi e; e.res = q; e.ldres = D; TRY(linear_into(c, a1, db.r2r.out, e, q1, D)); }

@@ -141,6 +141,7 @@ struct Tape {
     bool valid = false, full = false, fused = false;
     int bs = 0, A = 0, Mp = 0, P = 0, R = 0, Pr = 0, S = 0;
     uint8_t *agent_any = nullptr, *key_pad = nullptr, *r_pad = nullptr;
+    const uint8_t* r_pad_r2r = nullptr; int r2r_mod = 0, r2r_off = 0;     // r2r key padding: mask rows of the WHOLE batch (quirk)
     NatTape nat; EgoTape ego;
     PointsTape poly; FourierTape speed;
     float* pos = nullptr; FourierTape pos_emb;

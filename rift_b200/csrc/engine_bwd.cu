@@ -249,7 +249,8 @@ int rift_b200_engine::backward_impl(const rift_b200_batch& bt, const float* dlog
             ALLOC(d_t1, float, (size_t)rowsQ * D);
             TRY(lin_bwd(c, dt.a1.f, D, dq, D, rowsQ, db.r2r.out, d_a1, D, 0.f, true, &dt.a1.p));
             if (!c.dry) {
-                AttnArgs a = attn_r2r(dt.qkv1, bs, R, Mo, D, H, tp.r_pad, att_scale);
+                AttnArgs a = attn_r2r(dt.qkv1, bs, R, Mo, D, H, tp.r_pad_r2r, att_scale);
+                a.kpm_mod = tp.r2r_mod; a.kpm_off = tp.r2r_off;
                 a.lse = dt.lse1;
                 TRY(launch_attention_bwd(a, d_a1, D, dqkv1, 3 * D, dqkv1 + D, dqkv1 + 2 * D, 3 * D, 3 * D, c.st));
             }

@@ -448,9 +448,15 @@ static bool fb_plan(int D, int Hd, int* C_out, int* N1_out) {
 }
 
 bool fused_mlp_shape_ok(int rows, int D, int Hd) {
-    static const bool off = [] { const char* e = getenv("RIFT_B200_FUSED"); return e && atoi(e) == 0; }();
     int C, N1;
-    return !off && rows >= 64 && fb_plan(D, Hd, &C, &N1);
+    return rows >= 64 && fb_plan(D, Hd, &C, &N1);
+}
+// The forward schedule uses the fused sub-block kernels only when asked to (RIFT_B200_FUSED=1): measured on the cfg2 step
+// they are level with the unfused LayerNorm + two tcgen05 GEMMs at these row counts (9.99 vs 9.83 ms, profiles/r2b_*),
+// because one CTA walks the phases of its tile serially while the unfused kernels spread each phase over all SMs.
+bool fused_blocks_enabled() {
+    static const bool on = [] { const char* e = getenv("RIFT_B200_FUSED"); return e && atoi(e) != 0; }();
+    return on;
 }
 
 int launch_fused_mlp(const FusedMlpArgs& a, const TcWeight& w1, const TcWeight& w2, cudaStream_t st) {

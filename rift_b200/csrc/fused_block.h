@@ -20,6 +20,7 @@ struct FusedMlpArgs {
 // profiling aid: CTA 0 of every following fused launch writes %globaltimer stamps into dev_buf (16 u64); null = off
 void set_fused_trace(void* dev_buf);
 bool fused_mlp_shape_ok(int rows, int D, int Hd);
+bool fused_blocks_enabled();      // RIFT_B200_FUSED=1
 int launch_fused_mlp(const FusedMlpArgs& a, const TcWeight& w1, const TcWeight& w2, cudaStream_t st);
 
 }  // namespace rift

@@ -77,7 +77,7 @@ attention_bwd_kernel(AttnArgs a, const float* __restrict__ d_o, long long lddo, 
     }
     for (int i = threadIdx.x; i < a.Sq; i += blockDim.x) lse_s[i] = a.lse[((long long)b * a.H + h) * a.Sq + i];
     __syncthreads();
-    const uint8_t* kpm = a.kpm ? a.kpm + (long long)(a.kpm_mod > 0 ? b % a.kpm_mod : b / a.kpm_div) * a.Sk : nullptr;
+    const uint8_t* kpm = a.kpm ? a.kpm + (long long)(a.kpm_mod > 0 ? (b + a.kpm_off) % a.kpm_mod : b / a.kpm_div) * a.Sk : nullptr;
     // ---- phase A: thread = query i
     for (int i = threadIdx.x; i < a.Sq; i += blockDim.x) {
         const float lse = lse_s[i];
@@ -185,7 +185,7 @@ attention_bwd2_kernel(AttnArgs a, const float* __restrict__ d_o, long long lddo,
                 *reinterpret_cast<const float4*>(d_o + (orow0 + (long long)i * oseq) * lddo + h * HD + c);
         }
         for (int i = t; i < Sq; i += tpp) lse_s[i] = a.lse[((long long)b * a.H + h) * Sq + i];
-        const uint8_t* kpm = a.kpm ? a.kpm + (long long)(a.kpm_mod > 0 ? b % a.kpm_mod : b / a.kpm_div) * Sk : nullptr;
+        const uint8_t* kpm = a.kpm ? a.kpm + (long long)(a.kpm_mod > 0 ? (b + a.kpm_off) % a.kpm_mod : b / a.kpm_div) * Sk : nullptr;
         for (int j = t; j < Sk; j += tpp) msk[j] = kpm ? kpm[j] : 0;
     }
     __syncthreads();

@@ -563,7 +563,7 @@ attention_kernel(AttnArgs a) {
         Vs[e] = a.v[r * a.ldv + h * HD + d];
     }
     __syncthreads();
-    const uint8_t* kpm = a.kpm ? a.kpm + (long long)(a.kpm_mod > 0 ? b % a.kpm_mod : b / a.kpm_div) * a.Sk : nullptr;
+    const uint8_t* kpm = a.kpm ? a.kpm + (long long)(a.kpm_mod > 0 ? (b + a.kpm_off) % a.kpm_mod : b / a.kpm_div) * a.Sk : nullptr;
     const long long qrow0 = attn_row(b, a.q_inner_n, a.q_outer, a.q_inner);
     for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < a.Sq; i += gridDim.y * blockDim.x) {
         const long long qr = qrow0 + (long long)i * a.q_seq;
@@ -648,7 +648,7 @@ attention2_kernel(AttnArgs a, int PB, int tpp) {
             q.x *= a.scale; q.y *= a.scale; q.z *= a.scale; q.w *= a.scale;
             *reinterpret_cast<float4*>(Qs + i * AF_PITCH + c) = q;
         }
-        const uint8_t* kpm = a.kpm ? a.kpm + (long long)(a.kpm_mod > 0 ? b % a.kpm_mod : b / a.kpm_div) * Sk : nullptr;
+        const uint8_t* kpm = a.kpm ? a.kpm + (long long)(a.kpm_mod > 0 ? (b + a.kpm_off) % a.kpm_mod : b / a.kpm_div) * Sk : nullptr;
         for (int j = t; j < Sk; j += tpp) msk[j] = kpm ? kpm[j] : 0;
     }
     __syncthreads();

@@ -90,7 +90,8 @@ struct AttnArgs {
     int q_inner_n = 1; long long q_outer = 0, q_inner = 0, q_seq = 1;
     int k_inner_n = 1; long long k_outer = 0, k_inner = 0, k_seq = 1;
     const uint8_t* kpm = nullptr; int kpm_div = 1;   // key padding mask [B / kpm_div, Sk], 1 = masked
-    int kpm_mod = 0;                                 // if >0 the mask row is (b % kpm_mod) (reference r2r quirk)
+    int kpm_mod = 0;                                 // if >0 the mask row is ((b + kpm_off) % kpm_mod) (reference r2r quirk;
+    int kpm_off = 0;                                 //  kpm_off = position of this micro-batch inside the whole batch)
     float scale = 1.f;
     // output rows default to the query rows; o_custom selects an own mapping (shared learned query)
     int o_custom = 0; int o_inner_n = 1; long long o_outer = 0, o_inner = 0, o_seq = 1;

@@ -127,9 +127,10 @@ class DataModule:
         if shuffle:
             order = torch.randperm(len(idx), generator=self.gen).tolist()
             idx = [idx[i] for i in order]
+        on_device = hasattr(self.buffer, "collate_device")       # DeviceRolloutBuffer: one gather kernel, no host collate
         for i in range(0, len(idx), self.train_batch_size):
             chunk = idx[i:i + self.train_batch_size]
-            yield self.collate([self.buffer.sample(j) for j in chunk])
+            yield self.buffer.collate_device(chunk, self.algo) if on_device else self.collate([self.buffer.sample(j) for j in chunk])
 
     def train_batches(self):
         if self.train_idx is None:

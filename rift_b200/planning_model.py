@@ -79,6 +79,24 @@ class PackedBatch:
         b.cs_stride = k["current_state"].shape[1]
         self.shape = (bs, A, Mp, P, R, Pr)
 
+    def slice(self, lo: int, hi: int) -> "PackedBatch":
+        """Samples [lo, hi) of this batch as a PackedBatch over VIEWS of the same device tensors (micro-batching).  The
+        whole batch's reference-line mask travels along, so that the slice reproduces the reference's r2r key-padding
+        indexing (r_pad[j % bs] over the WHOLE batch, planning_decoder.py:56-60) exactly."""
+        sub = PackedBatch.__new__(PackedBatch)
+        sub.keep = {n: t[lo:hi] for n, t in self.keep.items()}
+        bs, A, Mp, P, R, Pr = self.shape
+        b = sub.struct = _lib.Batch()
+        b.bs, b.A, b.Mp, b.P, b.R, b.Pr, b.agent_T = hi - lo, A, Mp, P, R, Pr, self.struct.agent_T
+        for name, t in sub.keep.items():
+            setattr(b, name, t.data_ptr())
+        b.cs_stride = self.struct.cs_stride
+        b.ref_valid_mask_global = self.keep["ref_valid_mask"].data_ptr()
+        b.bs_global, b.b_offset = bs, lo
+        sub.shape = (hi - lo, A, Mp, P, R, Pr)
+        sub.parent = self
+        return sub
+
 
 class PlanningModel:
     def __init__(self, radius, dim=128, state_channel=6, polygon_channel=6, history_channel=9, history_steps=21,
@@ -105,6 +123,7 @@ class PlanningModel:
         self._engine = C.c_void_p()
         self._workspace = None
         self._ws_shape = None
+        self._extra = []              # further engines over the same parameters (micro-batches in flight together)
         self.ws_generation = 0        # bumped whenever the workspace is re-allocated (captured CUDA graphs go stale)
         self.arena: Optional[ParamArena] = None
         self.set_trainable_layers(trainable_layers)
@@ -116,17 +135,9 @@ class PlanningModel:
                    num_heads=cfg.num_heads, num_modes=cfg.num_modes, value_hidden=cfg.value_hidden, **kw)
 
     # ------------------------------------------------------------------ engine / arena
-    def set_trainable_layers(self, trainable_layers: Iterable[str]):
-        """(Re)build the arena layout for a trainable set; parameter values are preserved."""
-        old = self.arena.state_dict() if self.arena is not None else None
-        self.trainable_layers = list(trainable_layers)
-        self.arena = ParamArena(self.cfg, self.trainable_layers, self.device)
-        if old is not None:
-            self.arena.load_state_dict(old)
+    def _new_engine(self, grads):
         L = _lib.lib()
-        if self._engine:
-            L.rift_b200_destroy(self._engine)
-            self._engine = C.c_void_p()
+        eng = C.c_void_p()
         c = self.cfg
         mc = _lib.ModelConfig(c.dim, c.num_heads, c.encoder_depth, c.decoder_depth, c.num_modes, c.history_steps,
                               c.future_steps, c.state_channel, c.ref_points,
@@ -136,15 +147,46 @@ class PlanningModel:
         self._names = [n.encode() for n, _, _, _ in ents]
         for i, (n, off, ne, tr) in enumerate(ents):
             arr[i].name, arr[i].offset, arr[i].numel, arr[i].trainable = self._names[i], off, ne, tr
-        _lib.check(L.rift_b200_create(C.byref(mc), arr, len(ents), C.byref(self._engine)), "create")
-        _lib.check(L.rift_b200_bind_arena(self._engine, _lib.ptr(self.arena.params), _lib.ptr(self.arena.grads),
-                                          self.arena.params.numel()), "bind_arena")
+        _lib.check(L.rift_b200_create(C.byref(mc), arr, len(ents), C.byref(eng)), "create")
+        _lib.check(L.rift_b200_bind_arena(eng, _lib.ptr(self.arena.params), _lib.ptr(grads), self.arena.params.numel()), "bind_arena")
+        return eng
+
+    def set_trainable_layers(self, trainable_layers: Iterable[str]):
+        """(Re)build the arena layout for a trainable set; parameter values are preserved."""
+        old = self.arena.state_dict() if self.arena is not None else None
+        self.trainable_layers = list(trainable_layers)
+        self.arena = ParamArena(self.cfg, self.trainable_layers, self.device)
+        if old is not None:
+            self.arena.load_state_dict(old)
+        L = _lib.lib()
+        for e in [self._engine] + [x["engine"] for x in self._extra]:
+            if e:
+                L.rift_b200_destroy(e)
+        self._extra = []
+        self._engine = self._new_engine(self.arena.grads)
         # split-bf16 weight planes + TMA descriptors for the tcgen05 GEMM path
         self._wcache = torch.empty(L.rift_b200_weight_cache_bytes(self._engine), dtype=torch.uint8, device=self.device)
         _lib.check(L.rift_b200_bind_weight_cache(self._engine, _lib.ptr(self._wcache), self._wcache.numel()),
                    "bind_weight_cache")
         self._ws_shape = None
         self.ws_generation += 1       # engine, arenas and weight planes were rebuilt: anything captured against them is stale
+
+    def engine_slot(self, k: int) -> dict:
+        """Engine k > 0: same parameters and weight planes as engine 0, own gradient arena / workspace / tape, so that
+        several micro-batches can be in flight on different streams (LightningTrainer micro-batching)."""
+        while len(self._extra) < k:
+            L = _lib.lib()
+            grads = torch.zeros_like(self.arena.grads) if self.arena.grads is not None else None
+            eng = self._new_engine(grads)
+            torch.cuda.synchronize(self.device)      # binding re-writes the (identical) split-job tables inside the shared cache
+            _lib.check(L.rift_b200_bind_weight_cache(eng, _lib.ptr(self._wcache), self._wcache.numel()), "bind_weight_cache")
+            _lib.check(L.rift_b200_params_updated(eng, 2), "params_updated")      # engine 0 keeps the shared planes fresh
+            self._extra.append({"engine": eng, "grads": grads, "workspace": None, "ws_shape": None, "last_batch": None})
+        return self._extra[k - 1]
+
+    def refresh_weights(self):
+        """Re-split stale weight planes NOW on the current stream (before micro-batches fork onto their own streams)."""
+        _lib.check(_lib.lib().rift_b200_refresh_weights(self._engine, _lib.stream_ptr()), "refresh_weights")
 
     def params_updated(self, trainable_only: bool = False):
         """Tell the engine the fp32 arena changed (optimizer step / checkpoint load): the bf16 weight
@@ -153,8 +195,9 @@ class PlanningModel:
 
     def __del__(self):
         try:
-            if self._engine:
-                _lib.lib().rift_b200_destroy(self._engine)
+            for e in [self._engine] + [x["engine"] for x in self._extra]:
+                if e:
+                    _lib.lib().rift_b200_destroy(e)
         except Exception:
             pass
 
@@ -193,26 +236,38 @@ class PlanningModel:
         return self.forward(data, **kw)
 
     # ------------------------------------------------------------------ forward / backward
-    def _ensure_workspace(self, pb: PackedBatch):
-        if self._ws_shape != pb.shape:
-            need = _lib.lib().rift_b200_workspace_bytes(self._engine, C.byref(pb.struct))
+    def _ensure_workspace(self, pb: PackedBatch, k: int = 0):
+        """Workspace of engine k for this batch shape; returns (engine, workspace tensor)."""
+        if k == 0:
+            if self._ws_shape != pb.shape:
+                need = _lib.lib().rift_b200_workspace_bytes(self._engine, C.byref(pb.struct))
+                if need == 0:
+                    raise RuntimeError("rift_b200 workspace sizing failed: " + _lib.lib().rift_b200_last_error().decode())
+                if self._workspace is None or self._workspace.numel() < need:
+                    self._workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
+                    self.ws_generation += 1
+                self._ws_shape = pb.shape
+            return self._engine, self._workspace
+        slot = self.engine_slot(k)
+        if slot["ws_shape"] != pb.shape:
+            need = _lib.lib().rift_b200_workspace_bytes(slot["engine"], C.byref(pb.struct))
             if need == 0:
-                raise RuntimeError("rift_b200 workspace sizing failed: " +
-                                   _lib.lib().rift_b200_last_error().decode())
-            if self._workspace is None or self._workspace.numel() < need:
-                self._workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
+                raise RuntimeError("rift_b200 workspace sizing failed: " + _lib.lib().rift_b200_last_error().decode())
+            if slot["workspace"] is None or slot["workspace"].numel() < need:
+                slot["workspace"] = torch.empty(need, dtype=torch.uint8, device=self.device)
                 self.ws_generation += 1
-            self._ws_shape = pb.shape
+            slot["ws_shape"] = pb.shape
+        return slot["engine"], slot["workspace"]
 
     def pack(self, data) -> PackedBatch:
         return data if isinstance(data, PackedBatch) else PackedBatch(data, self.device)
 
     def forward(self, data, outputs=("probability", "trajectory", "prediction", "hidden", "ref_free_trajectory",
-                                     "candidate_trajectories"), save_for_backward: bool = False):
+                                     "candidate_trajectories"), save_for_backward: bool = False, engine: int = 0):
         """data: PlutoFeature.data dict (or a PackedBatch).  Returns the reference's output dict
         (pluto_model.py:219-225) restricted to `outputs` plus the derived entries."""
         pb = self.pack(data)
-        self._ensure_workspace(pb)
+        eng, ws = self._ensure_workspace(pb, engine)
         bs, A, Mp, P, R, Pr = pb.shape
         c = self.cfg
         T, Mo, D = c.future_steps, c.num_modes, c.dim
@@ -235,17 +290,30 @@ class PlanningModel:
                      "candidate_trajectories", "r_padding_mask"):
             setattr(o, name, res[name].data_ptr() if name in res and res[name].numel() else None)
         flags = (_lib.FWD_SAVE_FOR_BACKWARD if save_for_backward else 0) | (_lib.GEMM_SIMT if self.exact_fp32 else 0)
-        _lib.check(_lib.lib().rift_b200_forward(self._engine, C.byref(pb.struct), C.byref(o),
-                                                _lib.ptr(self._workspace), self._workspace.numel(), flags,
+        _lib.check(_lib.lib().rift_b200_forward(eng, C.byref(pb.struct), C.byref(o), _lib.ptr(ws), ws.numel(), flags,
                                                 _lib.stream_ptr()), "forward")
-        self._last_batch = pb
+        if engine == 0:
+            self._last_batch = pb
+        else:
+            self._extra[engine - 1]["last_batch"] = pb
         res["r_padding_mask"] = res["r_padding_mask"].view(torch.bool)
         return res
 
-    def backward(self, dlogits: torch.Tensor):
-        """d(loss)/d(probability) -> gradient arena (trainable parameters only)."""
+    def backward(self, dlogits: torch.Tensor, engine: int = 0):
+        """d(loss)/d(probability) -> gradient arena of that engine (trainable parameters only)."""
         assert dlogits.is_cuda and dlogits.dtype == torch.float32 and dlogits.is_contiguous()
-        pb = self._last_batch
-        _lib.check(_lib.lib().rift_b200_backward(self._engine, C.byref(pb.struct), _lib.ptr(dlogits),
-                                                 _lib.ptr(self._workspace), self._workspace.numel(),
+        if engine == 0:
+            pb, eng, ws = self._last_batch, self._engine, self._workspace
+        else:
+            slot = self._extra[engine - 1]
+            pb, eng, ws = slot["last_batch"], slot["engine"], slot["workspace"]
+        _lib.check(_lib.lib().rift_b200_backward(eng, C.byref(pb.struct), _lib.ptr(dlogits), _lib.ptr(ws), ws.numel(),
                                                  _lib.GEMM_SIMT if getattr(self, "exact_bwd", self.exact_fp32) else 0, _lib.stream_ptr()), "backward")
+
+    def merge_micro_batch_grads(self, n: int):
+        """grads(engine 0) += grads(engine k), k = 1 .. n - 1, over the trainable range (+ nothing else: the tail slots of
+        the arena carry the all-reduce's statistics and are written by the trainer)."""
+        L = _lib.lib()
+        for k in range(1, n):
+            _lib.check(L.rift_b200_op_add_inplace(_lib.ptr(self.arena.grads), _lib.ptr(self._extra[k - 1]["grads"]),
+                                                  self.arena.n_train, _lib.stream_ptr()), "add_inplace")

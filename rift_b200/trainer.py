@@ -97,6 +97,9 @@ class LightningTrainer:
         # A batch signature (shapes / dtypes) is captured the second time it is seen; inputs are copied into the
         # graph's static buffers, so varying shapes simply stay on the eager path.  RIFT_B200_CUDA_GRAPH=0 disables.
         self.use_cuda_graph = bool(int(os.environ.get("RIFT_B200_CUDA_GRAPH", "1")))
+        # concurrent micro-batches per training step (see _train_core); RIFT_B200_MICRO_BATCHES=1 runs the batch whole
+        self.micro_batches = int(os.environ.get("RIFT_B200_MICRO_BATCHES", "1"))
+        self._mb_streams: List[torch.cuda.Stream] = []
 
     # ------------------------------------------------------------------ reference surface
     def freeze_parameters(self, trainable_layers=("planning_decoder.pi_head",)):
@@ -178,12 +181,61 @@ class LightningTrainer:
         self._stats = stats
         return loss, dz
 
+    MICRO_OK = True        # the objective is a masked sum / count, so micro-batch (sum, count) pairs simply add up
+
+    def _micro_batches(self, bs: int) -> int:
+        k = self.micro_batches
+        while k > 1 and (bs % k or bs // k < 8):
+            k -= 1
+        return k if self.MICRO_OK else 1
+
     def _train_core(self, batch):
-        """forward -> objective -> backward on the current stream; returns the local loss tensor."""
-        res = self.model.forward(self._features(batch), outputs=(), save_for_backward=True)
-        loss, dz = self._objective(res, batch, need_grad=True)
-        self.model.backward(dz)
-        return loss
+        """forward -> objective -> backward; returns the local loss tensor.
+
+        Micro-batching (`micro_batches` > 1): the batch is cut into K contiguous slices that run forward, objective and
+        backward CONCURRENTLY on K streams, each on its own engine (own workspace, tape and gradient arena over the same
+        parameters and weight planes).  One policy update is a dependent chain of ~600 small kernels that leaves most
+        of the 148 SMs idle; K independent chains of half-sized kernels fill them.  The slices' (objective sum, valid
+        count) and gradient arenas are added afterwards, which is exactly the data-parallel reduction of SURVEY 8(e)
+        inside one GPU; the reference's r2r key-padding indexing over the whole batch is preserved (PackedBatch.slice)."""
+        feats = self._features(batch)
+        pb = self.model.pack(feats)
+        K = self._micro_batches(pb.shape[0])
+        if K <= 1:
+            res = self.model.forward(pb, outputs=(), save_for_backward=True)
+            loss, dz = self._objective(res, batch, need_grad=True)
+            self.model.backward(dz)
+            return loss
+        dev = self.model.device
+        cur = torch.cuda.current_stream(dev)
+        if len(self._mb_streams) < K:
+            self._mb_streams = [torch.cuda.Stream(device=dev) for _ in range(K)]
+        self.model.refresh_weights()                     # before the fork: every engine reads the same weight planes
+        bs = pb.shape[0]
+        per = bs // K
+        stats = []
+        for k in range(K):
+            lo, hi = k * per, (k + 1) * per
+            sub = {n: (t[lo:hi] if torch.is_tensor(t) and t.dim() > 0 and t.shape[0] == bs else t) for n, t in batch.items()}
+            st = self._mb_streams[k]
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                part = pb.slice(lo, hi)
+                res = self.model.forward(part, outputs=(), save_for_backward=True, engine=k)
+                _, dz = self._objective(res, sub, need_grad=True)
+                self.model.backward(dz, engine=k)
+                stats.append(self._stats)
+        for k in range(K):
+            cur.wait_stream(self._mb_streams[k])
+        for s_ in stats:
+            s_.record_stream(cur)
+        self.model.merge_micro_batch_grads(K)
+        tot = stats[0].clone()
+        for s_ in stats[1:]:
+            tot[1:3] += s_[1:3]
+        tot[0] = torch.where(tot[2] > 0, -tot[1] / tot[2], torch.zeros_like(tot[1]))
+        self._stats = tot
+        return tot[0]
 
     def _step(self, batch, prefix: str):
         if self.training:
@@ -376,6 +428,7 @@ class GRPOTrainer(LightningTrainer):
 class ReinforceTrainer(LightningTrainer):
     """reinforce_pluto/reinforce_trainer.py — -mean(log pi(argmax) * return)."""
     ALGO = "reinforce"
+    MICRO_OK = False       # per-sample objectives carry 1 / (global batch): run the batch whole
 
     def _objective(self, res, batch, need_grad):
         dev = self.model.device
