@@ -268,7 +268,8 @@ def test_get_action_keys_values_and_graph_replay(policy_name, tmp_path):
             assert set(data) == {"CBVs_actions", "CBVs_actions_old_log_prob", "CBVs_actions_mode"}
             for cid in obs0:
                 r, m = data["CBVs_actions_mode"][0][cid]
-                assert 0 <= r < 3 and 0 <= m < 12 and float(data["CBVs_actions_old_log_prob"][0][cid]) <= 0.0
+                # (-1, 11) = the reference-free trajectory won: its original index is -1 (pluto.py:222, rlft_pluto.py:160-162)
+                assert ((0 <= r < 3 and 0 <= m < 12) or (r, m) == (-1, 11)) and float(data["CBVs_actions_old_log_prob"][0][cid]) <= 0.0
             continue
         want = {"CBVs_actions", "CBVs_actions_old_group_logits", "CBVs_group_advantage"}
         if policy_name == "grpo_pluto":
