@@ -157,6 +157,14 @@ int rift_b200_action_objective(int mode, const float* logits, const uint8_t* r_p
                                const float* weight, const float* old_log_prob, int bs, int R, int Mo,
                                float clip_epsilon, float lambda_entropy, float inv_n, const float* extra_loss,
                                float* scratch, float* loss_out, float* dlogits, int* chosen, void* stream);
+/* SFT / RTR teacher objective (fine_tuner/sft/sft_trainer.py:123-215, rtr_pluto/rtr_trainer.py:130-195): cross-entropy of the
+ * candidate logits against the one-hot label (model's best reference line, mode whose PID target speed is closest to the
+ * teacher's).  trajectory (bs, R, Mo, T, 6); teacher_infos (bs, 5) = [target speed, origin x, origin y, heading, speed].
+ * loss_out (device float) = weight * inv_n * sum_b CE_b, assigned or (accumulate != 0) added; dlogits likewise (may be NULL);
+ * label_out (bs ints, may be NULL) = flat label index r * Mo + m.  scratch: bs floats. */
+int rift_b200_teacher_objective(const float* logits, const uint8_t* r_pad, const float* trajectory, const float* teacher_infos,
+                                int bs, int R, int Mo, int T, int frame_rate, float inv_n, float weight, float* scratch,
+                                float* loss_out, float* dlogits, int accumulate, int* label_out, void* stream);
 int rift_b200_smooth_l1(const float* value, const float* target, int n, float inv_n, float* loss_out, float* dvalue,
                         void* stream);
 

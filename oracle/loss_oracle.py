@@ -121,6 +121,41 @@ def reinforce_loss(probability, r_pad, returns):
     return -torch.mean(lp[torch.arange(bs), best] * returns)
 
 
+# ---------------------------------------------------------------- SFT / RTR teacher objective
+def teacher_label(trajectory, probability, r_pad, teacher_infos, frame_rate: int = 10):
+    """fine_tuner/sft/sft_trainer.py:175-215 (generate_target_label) with sft/utils.py:10-33 (global_to_local) and
+    pid_controller.py:121-136 (the target-speed half of batch_control_pid).  Returns (flat label index (bs,), masked logits)."""
+    bs, R, M = probability.shape
+    z = probability.masked_fill(r_pad.unsqueeze(-1), -1e8)
+    best_r = torch.argmax(z.reshape(bs, -1), dim=1) // M
+    target_speed, origin, heading = teacher_infos[:, 0], teacher_infos[:, 1:3], teacher_infos[:, 3]
+    T = trajectory.shape[3]
+    pts = trajectory[:, :, :, -1:, :2] if T < frame_rate else trajectory[:, :, :, frame_rate - 1::frame_rate, :2]
+    rot = torch.stack([torch.stack([torch.cos(heading), -torch.sin(heading)], dim=1),
+                       torch.stack([torch.sin(heading), torch.cos(heading)], dim=1)], dim=1).view(bs, 1, 1, 1, 2, 2)
+    local = torch.einsum("brmtc,brmtcd->brmtd", pts - origin.view(bs, 1, 1, 1, 2), rot)
+    if local.shape[3] == 1:
+        cand_speed = local[..., 0, :].norm(dim=-1, p=2)
+    else:
+        cand_speed = (local[..., 1:, :] - local[..., :-1, :]).norm(dim=-1, p=2).mean(dim=-1)
+    m_idx = torch.argmin(torch.abs(cand_speed - target_speed[:, None, None]).view(bs, -1), dim=1) % M
+    return best_r * M + m_idx, z
+
+
+def sft_loss(trajectory, probability, r_pad, teacher_infos, frame_rate: int = 10):
+    """sft_trainer.py:123-173: cross-entropy against the one-hot teacher label (the label is detached)."""
+    bs = probability.shape[0]
+    label, z = teacher_label(trajectory.detach(), probability, r_pad, teacher_infos, frame_rate)
+    return F.cross_entropy(z.reshape(bs, -1), F.one_hot(label, z[0].numel()).to(z.dtype))
+
+
+def rtr_loss(trajectory, probability, r_pad, teacher_infos, action_mode, value, advantage, reward_sum, old_log_prob,
+             frame_rate: int = 10, clip_epsilon: float = 0.2, lambda_entropy: float = 0.01, lambda_rl: float = 5.0):
+    """rtr_pluto/rtr_trainer.py:130-195: lambda_rl x (PPO value + actor loss) + the teacher loss."""
+    return lambda_rl * ppo_loss(probability, r_pad, action_mode, value, advantage, reward_sum, old_log_prob, clip_epsilon,
+                                lambda_entropy) + sft_loss(trajectory, probability, r_pad, teacher_infos, frame_rate)
+
+
 # ---------------------------------------------------------------- PPO / REINFORCE buffer passes
 def gae(rewards, undones, values, next_values, unterminated, gamma=0.98, lam=0.98):
     """ppo_datamodule.py:22-37 — sequential reverse scan, fp32."""

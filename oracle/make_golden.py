@@ -287,6 +287,49 @@ def get_action_goldens():
     print("get_action", len(out))
 
 
+def sft_goldens():
+    """SFT / RTR / RS objectives evaluated by the reference trainers (fine_tuner/sft/*) on the ragged small case:
+    loss, d loss / d logits, the teacher label, pi_head (and value-net) gradients."""
+    name, case = "ragged_small", CASES["ragged_small"]
+    out = {}
+    rng = np.random.Generator(np.random.PCG64(31))
+    teacher = np.stack([rng.uniform(0, 9, case["bs"]), rng.normal(0, 2, case["bs"]), rng.normal(0, 2, case["bs"]),
+                        rng.normal(0, 0.5, case["bs"]), rng.uniform(0, 9, case["bs"])], -1).astype(np.float32)
+    out["teacher_infos"] = teacher
+    for kind in ("sft", "rtr", "rs"):
+        kw = dict(case["kw"])
+        if kind == "rtr":
+            kw["value_hidden"] = (256, 256)
+        cfg = MODEL_ZOO[case["model"]](**kw)
+        model = build_model(cfg, "ppo" if kind == "rtr" else kind)
+        layers = ["planning_decoder.pi_head"] + (["value_net"] if kind == "rtr" else [])
+        Trainer = ref_shim.sft_trainer_cls(kind)
+        tr = Trainer(model=model, trainable_layers=layers, **TRAINER_KW)
+        tr.train()
+        tr.model.eval()
+        batch = build_batch(cfg, case, kind)
+        batch["teacher_infos"] = torch.from_numpy(teacher)
+        data = batch["cur_pluto_feature_torch"].data
+        res = tr.forward(data)
+        prob = res["probability"]
+        prob.retain_grad()
+        if kind in ("sft", "rtr"):
+            bs, R, M = prob.shape
+            pm = prob.detach().clone().masked_fill(~data["reference_line"]["valid_mask"].any(-1).unsqueeze(-1), -1e8)
+            mx = torch.argmax(pm.view(bs, -1), dim=1)
+            lab, _ = tr.generate_target_label(res["trajectory"].detach(), pm, batch["teacher_infos"], mx // M, mx % M)
+            out[f"label_{kind}"] = lab.argmax(-1).numpy()
+        loss = tr._compute_objectives(res, data, batch)["loss"]
+        out[f"loss_{kind}"] = np.asarray(loss.detach().double().numpy())
+        loss.backward()
+        out[f"dlogits_{kind}"] = prob.grad.numpy().copy()
+        for n, p in tr.model.named_parameters():
+            if p.grad is not None and (n.startswith("planning_decoder.pi_head") or n.startswith("value_net")):
+                out[f"grad_{kind}/{n}"] = p.grad.numpy().copy()
+    np.savez_compressed(os.path.join(GOLDEN, "sft_objectives.npz"), **out)
+    print("sft_objectives", len(out))
+
+
 def state_dict_spec():
     spec = {}
     for mname, kw in (("small", {}), ("medium", {})):
@@ -311,6 +354,8 @@ if __name__ == "__main__":
         buffer_pass_goldens()
     if not only or "act" in only:
         get_action_goldens()
+    if not only or "sft" in only:
+        sft_goldens()
     for name, case in CASES.items():
         if not only or name in only:
             run_case(name, case)

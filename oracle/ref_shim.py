@@ -154,6 +154,25 @@ def trainer_cls(algo: str):
     return mod.LightningTrainer
 
 
+def sft_trainer_cls(kind: str = "sft"):
+    """kind in {'sft', 'rtr', 'rs'} -> the reference LightningTrainer of fine_tuner/sft (rtr needs the PPO model stub)."""
+    install()
+    import importlib
+    if kind == "sft":
+        return importlib.import_module("rift.cbv.planning.fine_tuner.sft.sft_trainer").LightningTrainer
+    trainer_cls("ppo")          # installs the PPOPlutoModel stub that rtr_trainer.py imports
+    name = f"rift.cbv.planning.fine_tuner.sft.{kind}_pluto.{kind}_pluto"
+    if name not in sys.modules:
+        pkg = types.ModuleType(f"rift.cbv.planning.fine_tuner.sft.{kind}_pluto")
+        pkg.__path__ = [os.path.join(REF, f"rift/cbv/planning/fine_tuner/sft/{kind}_pluto")]
+        sys.modules.setdefault(f"rift.cbv.planning.fine_tuner.sft.{kind}_pluto", pkg)
+        stub = types.ModuleType(name)
+        stub.RTRPlutoModel = ppo_pluto_model_cls()
+        stub.PPOPlutoModel = stub.RTRPlutoModel
+        sys.modules[name] = stub
+    return importlib.import_module(f"rift.cbv.planning.fine_tuner.sft.{kind}_pluto.{kind}_trainer").LightningTrainer
+
+
 def pluto_feature_cls():
     install()
     from rift.cbv.planning.pluto.feature_builder.pluto_feature import PlutoFeature

@@ -79,6 +79,8 @@ _SIGNATURES = {
                                             C.c_float, C.c_float, C.c_float, _V, _V, _V, C.c_int, _V]),
     "rift_b200_action_objective": (C.c_int, [C.c_int, _V, _V, _V, _V, _V, C.c_int, C.c_int, C.c_int, C.c_float,
                                              C.c_float, C.c_float, _V, _V, _V, _V, _V, _V]),
+    "rift_b200_teacher_objective": (C.c_int, [_V, _V, _V, _V, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, _V,
+                                              _V, _V, C.c_int, _V, _V]),
     "rift_b200_smooth_l1": (C.c_int, [_V, _V, C.c_int, C.c_float, _V, _V, _V]),
     "rift_b200_group_advantage": (C.c_int, [_V, _V, C.c_longlong, C.c_int, _V, _V]),
     "rift_b200_gae": (C.c_int, [_V, _V, _V, _V, _V, C.c_int, C.c_float, C.c_float, _V, _V, _V, _V]),

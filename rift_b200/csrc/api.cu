@@ -147,6 +147,14 @@ int rift_b200_action_objective(int mode, const float* logits, const uint8_t* r_p
                                    lambda_entropy, inv_n, extra_loss, scratch, loss_out, dlogits, chosen, S(stream));
 }
 
+int rift_b200_teacher_objective(const float* logits, const uint8_t* r_pad, const float* trajectory, const float* teacher_infos,
+                                int bs, int R, int Mo, int T, int frame_rate, float inv_n, float weight, float* scratch,
+                                float* loss_out, float* dlogits, int accumulate, int* label_out, void* stream) {
+    RIFT_REQUIRE(logits && r_pad && trajectory && teacher_infos && scratch && loss_out, "teacher_objective: null argument");
+    return launch_teacher_objective(logits, r_pad, trajectory, teacher_infos, bs, R, Mo, T, frame_rate, inv_n, weight, scratch,
+                                    loss_out, dlogits, accumulate, label_out, S(stream));
+}
+
 int rift_b200_smooth_l1(const float* value, const float* target, int n, float inv_n, float* loss_out, float* dvalue,
                         void* stream) {
     RIFT_REQUIRE(value && target && loss_out, "smooth_l1: null argument");

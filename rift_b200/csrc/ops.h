@@ -20,6 +20,10 @@ int launch_action_objective(int mode /*0 ppo, 1 reinforce*/, const float* logits
                             const long long* action_mode, const float* weight, const float* old_log_prob, int bs, int R,
                             int Mo, float eps_clip, float lambda_entropy, float inv_n, const float* extra_loss,
                             float* part, float* loss_out, float* dlogits, int* chosen, cudaStream_t st);
+// SFT / RTR teacher cross-entropy (sft_trainer.py:123-215); dlogits assigned or accumulated, loss_out likewise
+int launch_teacher_objective(const float* logits, const uint8_t* r_pad, const float* traj, const float* teacher, int bs, int R,
+                             int Mo, int T, int step, float inv_n, float weight, float* part, float* loss_out, float* dlogits,
+                             int accumulate, int* label_out, cudaStream_t st);
 int launch_smooth_l1(const float* value, const float* target, int n, float inv_n, float* loss_out, float* dvalue,
                      cudaStream_t st);
 int launch_gae(const float* rewards, const float* undones, const float* values, const float* next_values,

@@ -733,6 +733,112 @@ int launch_action_objective(int mode, const float* logits, const uint8_t* r_pad,
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// SFT / RTR teacher objective (fine_tuner/sft/sft_trainer.py:123-215): cross-entropy of the candidate logits against a
+// one-hot label at (best reference line of the model, mode whose PID target speed is closest to the teacher's).
+//   target speed of a candidate (pid_controller.py:121-136 on sft/utils.py:10-33): the trajectory is resampled every
+//   `step` points, moved into the teacher's frame (origin, heading) and the mean segment length is taken (one point only:
+//   its distance from the origin);  label mode = argmin over ALL (R, Mo) candidates of |target speed - teacher speed| mod Mo;
+//   label line = argmax of the masked logits / Mo.  Only the logits carry gradient (the label is detached):
+//   d loss / d z_j = weight * inv_n * (softmax(z')_j - [j == label]),  loss term = -log_softmax(z')[label].
+// One warp per sample; dlogits is assigned (accumulate == 0) or added to (RTR: 5 * PPO term + teacher term).
+__global__ void __launch_bounds__(128)
+teacher_objective_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ r_pad, const float* __restrict__ traj,
+                         const float* __restrict__ teacher, int bs, int R, int Mo, int T, int step, float scale, float* __restrict__ part,
+                         float* __restrict__ dlogits, int accumulate, int* __restrict__ label_out) {
+    pdl_grid_sync();
+    const int b = (blockIdx.x * 128 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (b >= bs) return;
+    const int G = R * Mo;
+    const float* zb = logits + (long long)b * G;
+    const float t_speed = teacher[b * 5 + 0], ox = teacher[b * 5 + 1], oy = teacher[b * 5 + 2], hd = teacher[b * 5 + 3];
+    const float ch = cosf(hd), sh = sinf(hd);
+    const int t0 = T < step ? T - 1 : step - 1, tstep = T < step ? T : step;
+    const int n_pts = T < step ? 1 : (T - (step - 1) + step - 1) / step;
+    float z[LOSS_MAX_PER_LANE];
+    float zmax = -INFINITY, best_d = INFINITY;
+    int amax = 0x7fffffff, amin = 0x7fffffff;
+#pragma unroll
+    for (int t = 0; t < LOSS_MAX_PER_LANE; ++t) {
+        const int g = lane + 32 * t;
+        z[t] = -INFINITY;
+        if (g < G) {
+            const bool pad = r_pad[(long long)b * R + g / Mo] != 0;
+            z[t] = pad ? -1e8f : zb[g];
+            if (z[t] > zmax) { zmax = z[t]; amax = g; }
+            // PID target speed of candidate g in the teacher's frame
+            const float* tr = traj + ((long long)b * G + g) * T * 6;
+            float px = 0.f, py = 0.f, acc = 0.f;
+            for (int i = 0; i < n_pts; ++i) {
+                const float vx = tr[(long long)(t0 + i * tstep) * 6] - ox, vy = tr[(long long)(t0 + i * tstep) * 6 + 1] - oy;
+                const float lx = vx * ch + vy * sh, ly = vx * (-sh) + vy * ch;
+                if (i > 0) { const float dx = lx - px, dy = ly - py; acc += sqrtf(dx * dx + dy * dy); }
+                px = lx; py = ly;
+            }
+            const float speed = n_pts > 1 ? acc / (float)(n_pts - 1) : sqrtf(px * px + py * py);
+            const float d = fabsf(speed - t_speed);
+            if (d < best_d) { best_d = d; amin = g; }
+        }
+    }
+    // warp arg-max (first maximal index) and arg-min (first minimal index)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, zmax, o); const int oi = __shfl_xor_sync(0xffffffffu, amax, o);
+        if (ov > zmax || (ov == zmax && oi < amax)) { zmax = ov; amax = oi; }
+        const float od = __shfl_xor_sync(0xffffffffu, best_d, o); const int odi = __shfl_xor_sync(0xffffffffu, amin, o);
+        if (od < best_d || (od == best_d && odi < amin)) { best_d = od; amin = odi; }
+    }
+    const int label = (amax / Mo) * Mo + (amin % Mo);
+    float se = 0.f;
+#pragma unroll
+    for (int t = 0; t < LOSS_MAX_PER_LANE; ++t) if (lane + 32 * t < G) se += __expf(z[t] - zmax);
+    se = warp_sum(se);
+    const float lse = zmax + logf(se);
+#pragma unroll
+    for (int t = 0; t < LOSS_MAX_PER_LANE; ++t) {
+        const int g = lane + 32 * t;
+        if (g < G) {
+            if (g == label) part[b] = -(z[t] - lse);
+            if (dlogits) {
+                const float gr = scale * (__expf(z[t] - lse) - (g == label ? 1.f : 0.f));
+                float* o = dlogits + (long long)b * G + g;
+                *o = accumulate ? *o + gr : gr;
+            }
+        }
+    }
+    if (lane == 0 && label_out) label_out[b] = label;
+}
+
+// loss_out[0] (=|+=) weight * inv_n * sum_b part[b]
+__global__ void __launch_bounds__(256)
+weighted_mean_finalize_kernel(const float* __restrict__ part, int bs, float scale, int accumulate, float* __restrict__ out) {
+    pdl_grid_sync();
+    __shared__ float s[256];
+    float a = 0.f;
+    for (int i = threadIdx.x; i < bs; i += 256) a += part[i];
+    s[threadIdx.x] = a;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = (accumulate ? out[0] : 0.f) + s[0] * scale;
+}
+
+int launch_teacher_objective(const float* logits, const uint8_t* r_pad, const float* traj, const float* teacher, int bs, int R,
+                             int Mo, int T, int step, float inv_n, float weight, float* part, float* loss_out, float* dlogits,
+                             int accumulate, int* label_out, cudaStream_t st) {
+    RIFT_REQUIRE(R * Mo <= 32 * LOSS_MAX_PER_LANE, "R*num_modes exceeds 512 candidates per sample");
+    RIFT_REQUIRE(step >= 1 && T >= 1, "teacher_objective: bad frame rate / horizon");
+    if (bs <= 0) return 0;
+    launch_k(teacher_objective_kernel, cdiv((long long)bs * 32, 128), 128, 0, st, logits, r_pad, traj, teacher, bs, R, Mo, T, step,
+             weight * inv_n, part, dlogits, accumulate, label_out);
+    RIFT_LAUNCH_OK();
+    launch_k(weighted_mean_finalize_kernel, 1, 256, 0, st, part, bs, weight * inv_n, accumulate, loss_out);
+    RIFT_LAUNCH_OK();
+    return 0;
+}
+
 // SmoothL1(value, target) mean (beta = 1) and its gradient wrt value, one block (bs is a batch size).
 __global__ void __launch_bounds__(256)
 smooth_l1_kernel(const float* __restrict__ value, const float* __restrict__ target, int n, float inv_n,

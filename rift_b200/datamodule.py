@@ -67,7 +67,26 @@ class ReinforceCollate:
                 "return_torch": torch.stack([_t(d["CBVs_return"]) for d in batch], dim=0)}
 
 
-COLLATES = {"rift": RIFTCollate, "grpo": GRPOCollate, "ppo": PPOCollate, "reinforce": ReinforceCollate}
+class SFTCollate:
+    """fine_tuner/sft/sft_datamodule.py:18-41"""
+
+    def __call__(self, batch):
+        assert len(batch) > 0, "Batch size has to be greater than 0!"
+        return {"cur_pluto_feature_torch": PlutoFeature.collate([d["CBVs_obs"]["raw_pluto_feature"] for d in batch]),
+                "teacher_infos": torch.stack([_t(d["CBVs_teacher_infos"]) for d in batch], dim=0)}
+
+
+class RTRCollate(PPOCollate):
+    """fine_tuner/sft/rtr_pluto/rtr_datamodule.py:40-75 (PPO terms + the teacher infos)"""
+
+    def __call__(self, batch):
+        out = super().__call__(batch)
+        out["teacher_infos"] = torch.stack([_t(d["CBVs_teacher_infos"]) for d in batch], dim=0)
+        return out
+
+
+COLLATES = {"rift": RIFTCollate, "grpo": GRPOCollate, "ppo": PPOCollate, "reinforce": ReinforceCollate,
+            "sft": SFTCollate, "rtr": RTRCollate, "rs": ReinforceCollate}
 
 
 class DataModule:

@@ -116,6 +116,31 @@ def action_objective(mode: str, probability, r_padding_mask, weight, action_mode
     return loss[0], dz, chosen
 
 
+def teacher_objective(probability, r_padding_mask, trajectory, teacher_infos, frame_rate=10, global_batch=None, weight=1.0,
+                      loss_out=None, dlogits=None, need_grad=True):
+    """SFT / RTR teacher cross-entropy (sft_trainer.py:123-215).  With `loss_out` / `dlogits` given the term is ADDED to them
+    (RTR: 5 x PPO + teacher).  Returns (loss fp32 scalar tensor, dlogits or None, flat label index per sample)."""
+    z = _req(probability, torch.float32, "probability")
+    bs, R, Mo = z.shape
+    rp = _req(r_padding_mask, torch.uint8, "r_padding_mask")
+    tr = _req(trajectory, torch.float32, "trajectory")
+    ti = _req(teacher_infos, torch.float32, "teacher_infos")
+    T = tr.shape[3]
+    acc = loss_out is not None
+    loss = loss_out if acc else torch.empty(1, dtype=torch.float32, device=z.device)
+    if dlogits is None and need_grad:
+        if acc:
+            raise ValueError("accumulating into loss_out needs the dlogits to accumulate into as well")
+        dlogits = torch.empty_like(z)
+    part = torch.empty(bs, dtype=torch.float32, device=z.device)
+    label = torch.empty(bs, dtype=torch.int32, device=z.device)
+    _lib.check(_lib.lib().rift_b200_teacher_objective(
+        _lib.ptr(z), _lib.ptr(rp), _lib.ptr(tr), _lib.ptr(ti), bs, R, Mo, T, int(frame_rate), 1.0 / float(global_batch or bs),
+        float(weight), _lib.ptr(part), _lib.ptr(loss), _lib.ptr(dlogits), int(acc), _lib.ptr(label), _lib.stream_ptr()),
+        "teacher_objective")
+    return loss.reshape(-1)[0], dlogits, label
+
+
 def smooth_l1(value, target, global_batch=None, need_grad=True):
     """nn.SmoothL1Loss() (mean, beta 1) and d/d value (ppo_trainer.py value_criterion)."""
     v = _req(value, torch.float32, "value")

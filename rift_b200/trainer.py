@@ -181,6 +181,7 @@ class LightningTrainer:
         self._stats = stats
         return loss, dz
 
+    FWD_OUTPUTS = ()       # model outputs the objective reads besides the logits (SFT / RTR: the candidate trajectories)
     MICRO_OK = True        # the objective is a masked sum / count, so micro-batch (sum, count) pairs simply add up
 
     def _micro_batches(self, bs: int) -> int:
@@ -202,7 +203,7 @@ class LightningTrainer:
         pb = self.model.pack(feats)
         K = self._micro_batches(pb.shape[0])
         if K <= 1:
-            res = self.model.forward(pb, outputs=(), save_for_backward=True)
+            res = self.model.forward(pb, outputs=self.FWD_OUTPUTS, save_for_backward=True)
             loss, dz = self._objective(res, batch, need_grad=True)
             self.model.backward(dz)
             return loss
@@ -244,7 +245,7 @@ class LightningTrainer:
                 loss = self._train_core(batch)
             loss = self._reduce(loss)
         else:
-            res = self.model.forward(self._features(batch), outputs=(), save_for_backward=False)
+            res = self.model.forward(self._features(batch), outputs=self.FWD_OUTPUTS, save_for_backward=False)
             loss, _ = self._objective(res, batch, need_grad=False)
         self._last_loss = loss
         return loss if self.training else 0.0
@@ -519,11 +520,60 @@ class PPOTrainer(ReinforceTrainer):
         return loss, dz
 
     def _train_core(self, batch):
-        res = self.model.forward(self._features(batch), outputs=(), save_for_backward=True)
+        res = self.model.forward(self._features(batch), outputs=self.FWD_OUTPUTS, save_for_backward=True)
         loss, dz = self._objective(res, batch, need_grad=True)
         self.model.backward(dz)                          # zeroes the gradient span, then the policy gradients
         self.value_net.backward(self._dvalue)            # += value-net gradients
         return loss
 
 
-TRAINERS = {"rift": RIFTTrainer, "grpo": GRPOTrainer, "reinforce": ReinforceTrainer, "ppo": PPOTrainer}
+class SFTTrainer(ReinforceTrainer):
+    """fine_tuner/sft/sft_trainer.py:123-215 — supervised fine-tuning on the teacher's target speed: cross-entropy of the
+    candidate logits against (model's best reference line, mode whose PID target speed is closest to the teacher's)."""
+    ALGO = "sft"
+    FWD_OUTPUTS = ("trajectory",)
+
+    def _objective(self, res, batch, need_grad):
+        dev = self.model.device
+        bs = res["probability"].shape[0]
+        loss, dz, self._label = F.teacher_objective(res["probability"], res["r_padding_mask"], res["trajectory"],
+                                                    batch["teacher_infos"].to(dev).float(), frame_rate=self.frame_rate,
+                                                    global_batch=bs * self._world(), need_grad=need_grad)
+        self._stats = None
+        return loss, dz
+
+
+class RSTrainer(ReinforceTrainer):
+    """fine_tuner/sft/rs_pluto/rs_trainer.py:154-170 — rejection-sampling baseline: the REINFORCE objective
+    -mean(log pi(argmax) * return) on the buffer its datamodule filtered."""
+    ALGO = "rs"
+
+
+class RTRTrainer(PPOTrainer):
+    """fine_tuner/sft/rtr_pluto/rtr_trainer.py:130-195 — RTR baseline: 5 x (PPO value + actor loss) + the SFT teacher loss."""
+    ALGO = "rtr"
+    FWD_OUTPUTS = ("trajectory",)
+    LAMBDA_RL = 5.0
+
+    def _objective(self, res, batch, need_grad):
+        dev = self.model.device
+        bs = res["probability"].shape[0]
+        gb = bs * self._world()
+        gb_rl = gb / self.LAMBDA_RL                      # 1 / gb_rl = lambda_rl / gb: scales the PPO loss AND its gradients by lambda_rl
+        value = self.value_net.forward(batch["state_torch"].to(dev).float().contiguous(), save=need_grad)
+        vloss, self._dvalue = F.smooth_l1(value, batch["reward_sum_torch"].to(dev).float(), global_batch=gb_rl, need_grad=need_grad)
+        loss, dz, _ = F.action_objective("ppo", res["probability"], res["r_padding_mask"], batch["advantage_torch"].to(dev).float(),
+                                         action_mode=batch["action_mode_torch"].to(dev),
+                                         old_log_prob=batch["old_log_prob_torch"].to(dev).float(),
+                                         clip_epsilon=self.clip_epsilon, lambda_entropy=self.lambda_entropy,
+                                         extra_loss=vloss, global_batch=gb_rl, need_grad=need_grad)
+        total = loss.reshape(1).clone()
+        loss, dz, self._label = F.teacher_objective(res["probability"], res["r_padding_mask"], res["trajectory"],
+                                                    batch["teacher_infos"].to(dev).float(), frame_rate=self.frame_rate,
+                                                    global_batch=gb, loss_out=total, dlogits=dz, need_grad=need_grad)
+        self._stats = None
+        return loss, dz
+
+
+TRAINERS = {"rift": RIFTTrainer, "grpo": GRPOTrainer, "reinforce": ReinforceTrainer, "ppo": PPOTrainer,
+            "sft": SFTTrainer, "rtr": RTRTrainer, "rs": RSTrainer}

@@ -108,3 +108,35 @@ def test_full_model_decay_partition_counts():
     names = [(n, s) for n, s, _ in param_spec(cfg) if not is_buffer(n)]
     decay, no_decay = lo.decay_partition(names)
     assert (len(decay), len(no_decay)) == (137, 289)
+
+
+@pytest.mark.parametrize("kind", ["sft", "rtr", "rs"])
+def test_sft_family_objectives_match_reference_golden(kind):
+    """fine_tuner/sft: SFT teacher cross-entropy, RTR = 5 x PPO + teacher, RS = REINFORCE - loss, d loss / d logits and
+    the teacher label against the reference trainers' own outputs (tests/golden/sft_objectives.npz)."""
+    from oracle import pluto_oracle as po
+    from tests.helpers import to_torch_tree
+    g = golden("sft_objectives")
+    cfg, sd_np, feats, extras = case_inputs("ragged_small", ppo=(kind == "rtr"))
+    sd = {k: torch.from_numpy(v.copy()) for k, v in sd_np.items()}
+    data, ex = to_torch_tree(feats), to_torch_tree(extras)
+    with torch.no_grad():
+        out = po.planning_model_forward(data, sd, cfg)
+    prob = out["probability"].clone().requires_grad_(True)
+    r_pad = ~data["reference_line"]["valid_mask"].any(-1)
+    ti = torch.from_numpy(g["teacher_infos"])
+    if kind == "sft":
+        loss = lo.sft_loss(out["trajectory"], prob, r_pad, ti)
+    elif kind == "rtr":
+        value = po.critic_ppo(ex["state"], sd)
+        loss = lo.rtr_loss(out["trajectory"], prob, r_pad, ti, ex["action_mode"], value, ex["advantage"], ex["reward_sum"],
+                           ex["old_log_prob"])
+    else:
+        loss = lo.reinforce_loss(prob, r_pad, ex["return"])
+    ref = float(g[f"loss_{kind}"])
+    assert abs(float(loss.detach()) - ref) <= 1e-5 * max(abs(ref), 1e-3)
+    loss.backward()
+    assert np.abs(prob.grad.numpy() - g[f"dlogits_{kind}"]).max() <= 1e-5 * np.abs(g[f"dlogits_{kind}"]).max()
+    if kind != "rs":
+        label, _ = lo.teacher_label(out["trajectory"], prob.detach(), r_pad, ti)
+        assert np.array_equal(label.numpy(), g[f"label_{kind}"])

@@ -295,3 +295,39 @@ def test_get_action_keys_values_and_graph_replay(policy_name, tmp_path):
     # CBVs that left the scene lose their PID state (pluto.py:114-125)
     pol.get_action([{101: obs0[101]}, {}], infos, deterministic=True)
     assert set(pol.controllers[0]) == {101} and 1 not in pol.controllers
+
+
+@pytest.mark.parametrize("kind", ["sft", "rtr", "rs"])
+def test_sft_family_training_step_matches_reference_golden(kind):
+    """SFT / RTR / RS trainers (fine_tuner/sft/sft_trainer.py:123-215, rtr_trainer.py:130-195, rs_trainer.py:154-170) on the
+    CUDA path against the reference trainers' loss, teacher label and pi_head / value-net gradients."""
+    g = golden("sft_objectives")
+    cfg, sd, feats, ex = case_inputs("ragged_small", ppo=(kind == "rtr"))
+    if kind == "rtr":
+        model = PPOPlutoModel(cfg.radius, hidden_dim=(256, 256), dim=cfg.dim, num_heads=cfg.num_heads,
+                              encoder_depth=cfg.encoder_depth, decoder_depth=cfg.decoder_depth, future_steps=cfg.future_steps)
+    else:
+        from rift_b200.planning_model import PlanningModel
+        model = PlanningModel.from_config(cfg)
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    layers = ["planning_decoder.pi_head"] + (["value_net"] if kind == "rtr" else [])
+    tr = TRAINERS[kind](model, trainable_layers=layers, **TRAINER_KW)
+    batch = {"cur_pluto_feature_torch": to_torch_tree(feats, "cuda"), "teacher_infos": torch.from_numpy(g["teacher_infos"]).cuda()}
+    for k in ("state", "advantage", "reward_sum", "old_log_prob", "action_mode", "return"):
+        batch[k + "_torch"] = torch.from_numpy(ex[k].copy()).cuda()
+    loss = tr.training_step(batch)
+    ref = float(g[f"loss_{kind}"])
+    assert abs(float(loss) - ref) <= 1e-3 * max(abs(ref), 1e-3), (float(loss), ref)
+    if kind != "rs":
+        assert np.array_equal(tr._label.cpu().numpy(), g[f"label_{kind}"])          # index-exact teacher label
+    for k in g.files:
+        if k.startswith(f"grad_{kind}/"):
+            n = k.split("/", 1)[1]
+            got = model.arena.grad_view(n).cpu().numpy()
+            scale = max(float(np.abs(g[k]).max()), 1e-30)
+            assert float(np.abs(got - g[k]).max()) <= 1e-3 * scale + 2e-6, (n, float(np.abs(got - g[k]).max()), scale)
+    # validation path and a few updates run
+    assert np.isfinite(float(tr.validation_loss(batch)))
+    tr.configure_optimizers()
+    for _ in range(3):
+        tr.step(batch)
