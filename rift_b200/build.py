@@ -19,7 +19,7 @@ LIB = os.path.join(HERE, "librift_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall",
-          "--expt-relaxed-constexpr", "-Xptxas", "-v", "-I", os.path.join(ROOT, "include")]
+          "--expt-relaxed-constexpr", "-Xptxas", "-v", "-I", os.path.join(ROOT, "include")] + os.environ.get("RIFT_B200_NVCC_DEFS", "").split()
 
 
 def _sources():

@@ -5,6 +5,8 @@
 // encoder, scene encoding} <- encoder blocks <- {pos_emb, agent encoder (NAT + ego state attention), map
 // encoder}.  The trajectory / prediction / hidden / ref-free heads receive no gradient from any RL
 // objective (their outputs are not part of the loss), exactly like autograd in the reference.
+#include <stdlib.h>
+
 #include "engine_ops.h"
 
 using namespace rift;
@@ -107,7 +109,8 @@ static int mlp_tail_bwd(Ctx& c, int rows, int D, int Hd, const Act& hm, const fl
     ALLOC(d_t2, float, (size_t)rows * D);
     // (ReLU only: GELU's derivative - erf + exp per element - costs more inside the GEMM epilogue, where it is
     // instruction-latency bound, than the bandwidth-bound activation-backward kernel it would replace; measured)
-    if (act == ACT_RELU && lin_bwd_all_tc(c, rows, fc2, true) && lin_bwd_all_tc(c, rows, fc1, true) && (Hd % 4) == 0) {
+    static const bool fuse_gelu = [] { const char* e = getenv("RIFT_B200_FUSE_GELU_BWD"); return e && atoi(e) != 0; }();
+    if ((act == ACT_RELU || fuse_gelu) && lin_bwd_all_tc(c, rows, fc2, true) && lin_bwd_all_tc(c, rows, fc1, true) && (Hd % 4) == 0) {
         // tensor-core route: fc2's data-gradient GEMM applies act'(.) in its epilogue and writes d_hm as split-bf16
         // planes only; fc1's backward consumes them directly (no activation-backward kernel, no pack, bias gradient
         // summed from the planes on the side stream)

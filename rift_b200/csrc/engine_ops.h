@@ -331,8 +331,10 @@ inline int lin_bwd(Ctx& c, const float* X, long long ldx, const float* dY, long 
         }
         const int tiles = ((L.N + 127) / 128) * ((L.K + (L.K <= 64 ? 63 : 127)) / (L.K <= 64 ? 64 : 128));
         const int num_kb = (M + 63) / 64;
-        // one wave of (tile, split) work items
-        int splits = 148 / tiles;
+        // one wave of (tile, split) work items; RIFT_B200_WGRAD_CTAS caps the wave below the SM count, which leaves SMs to
+        // the data-gradient chain running next to these side-stream products
+        static const int wave = [] { const char* e = getenv("RIFT_B200_WGRAD_CTAS"); const int v = e ? atoi(e) : 148; return v > 0 ? v : 148; }();
+        int splits = wave / tiles;
         if (splits > 24) splits = 24;
         if (splits > num_kb) splits = num_kb;
         if (splits < 1) splits = 1;

@@ -36,8 +36,18 @@
 
 namespace rift {
 
+// RIFT_TC_LITE (experiment): two operand stages, four epilogue warps and 64-wide tiles only -> < 114 KB of shared memory per
+// CTA, so TWO CTAs (of the same or of different kernels / streams) share an SM and hide each other's TMA / MMA / epilogue latencies
+#ifdef RIFT_TC_LITE
+constexpr int TC_BM = 128, TC_BK = 64, TC_STAGES = 2;
+constexpr int TC_EPI_WARPS = 4;
+constexpr int TC_CTAS_PER_SM = 2;
+#else
 constexpr int TC_BM = 128, TC_BK = 64, TC_STAGES = 3;
 constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_CTAS_PER_SM = 1;
+#endif
+constexpr int TC_EPI_HALVES = TC_EPI_WARPS / 4;
 constexpr int TC_EPI_PITCH = 32;         // floats per staged row (128 B); 16-byte chunks are XOR-swizzled with (row & 7)
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 
@@ -88,9 +98,11 @@ struct TcSmem {
     static constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;
     static constexpr int EPI = TC_EPI_WARPS * 32 * TC_EPI_PITCH * 4;       // per-warp 32 x 32 fp32 staging tiles
     static constexpr int ONES = 512;                     // all-ones bf16 B operand of the bias-gradient MMA (MN kernels)
-    static constexpr int TOTAL = TC_STAGES * STAGE + 1024 /*align*/ + 256 /*barriers*/ + EPI + ONES;
+    static constexpr int TOTAL = TC_STAGES * STAGE + (TC_CTAS_PER_SM > 1 ? 0 : 1024) /*align*/ + 256 /*barriers*/ + EPI + ONES;
 };
-static_assert(TcSmem<128>::TOTAL <= 227 * 1024, "tcgen05 GEMM shared memory");
+constexpr int TC_MAX_BN = (TC_CTAS_PER_SM > 1) ? 64 : 128;
+// per SM: 228 KB, of which 1 KB is reserved per resident CTA
+static_assert(TC_CTAS_PER_SM * (TcSmem<TC_MAX_BN>::TOTAL + 1024) <= 228 * 1024, "tcgen05 GEMM shared memory");
 constexpr int TC_BOX = 64 * 64 * 2;      // bytes of one 64 x 64 bf16 TMA box
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
@@ -122,12 +134,18 @@ constexpr uint32_t tmem_cols_pow2(uint32_t n) { return n <= 32 ? 32 : n <= 64 ? 
 // DA: the epilogue multiplies by act'(dact_ref) (fused activation backward) - a separate instantiation so that the
 // common kernels do not carry its code
 template <int BN, bool MN, bool DA>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, TC_CTAS_PER_SM)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, TcKernelArgs g) {
     pdl_trigger();        // the dependent kernel may be scheduled; our own dependency is awaited after the set-up below
+#ifdef RIFT_TC_LITE
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");     // room for a second CTA per SM: let the next kernel's set-up overlap
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw;                            // no static shared memory in this kernel: the dynamic window starts 1024-aligned
+#else
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+#endif
     using SM = TcSmem<BN>;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_STAGES * SM::STAGE);
     uint64_t* full = bars;                          // [stages] 1 arrival + TMA bytes
@@ -261,7 +279,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         // ===================== epilogue (8 warps) =====================
         const int ew = warp - 2;
         const int quarter = warp & 3;                // TMEM lane quarter this warp may access
-        const int half = ew >> 2;                    // column half of the tile
+        const int half = ew >> 2;                    // column slice of the tile (TC_EPI_HALVES slices)
         const TcEpilogue& e = g.ep;
         int ti = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
@@ -297,8 +315,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             float* c_row = g.C ? g.C + (long long)sp * g.split_stride + (long long)(mrow0 + srow) * g.ldc : nullptr;
             float* pa_row = e.preact ? e.preact + (long long)(mrow0 + srow) * g.ldc : nullptr;
 #pragma unroll 1
-            for (int cc = 0; cc < BN / 2; cc += 32) {
-                const int c0 = half * (BN / 2) + cc;
+            for (int cc = 0; cc < BN / TC_EPI_HALVES; cc += 32) {
+                const int c0 = half * (BN / TC_EPI_HALVES) + cc;
                 uint32_t r[32];
                 tmem_ld_32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN + c0), r);
                 tmem_ld_wait();
@@ -1040,6 +1058,9 @@ static int out_map(const void* ptr, long long rows, long long cols, long long pi
 // does the weight-resident / TMA-store variant take this GEMM?  (tall: at least two M tiles per CTA; K small enough
 // for the weight tile to stay in shared memory; only the epilogue forms it implements)
 static bool tc2_takes(const GemmArgs& a, int BN, int sms) {
+#ifdef RIFT_TC_LITE
+    return false;
+#endif
     static const bool off = [] { const char* e = getenv("RIFT_B200_GEMM_V2"); return e && atoi(e) == 0; }();
     if (off) return false;
     const int num_kb = cdiv(a.K, TC_BK);
@@ -1159,7 +1180,7 @@ static int launch_tc(const GemmArgs& a, const PlaneOp& A, const PlaneOp& B, int 
                           a.alpha, a.preact, a.dact_ref, a.lddact, a.dact};
     }
     const int n_tiles = cdiv(a.N, BN) * cdiv(a.M, TC_BM) * g.splits;
-    launch_k(gemm_tc_kernel<BN, MN, DA>, min(n_tiles, sms), TC_THREADS, TcSmem<BN>::TOTAL, st, *ma_hi, *ma_lo, *mb_hi, *mb_lo, g);
+    launch_k(gemm_tc_kernel<BN, MN, DA>, min(n_tiles, TC_CTAS_PER_SM * sms), TC_THREADS, TcSmem<BN>::TOTAL, st, *ma_hi, *ma_lo, *mb_hi, *mb_lo, g);
     RIFT_LAUNCH_OK();
     if (via_ws) {
         if (a.n_store > 0) { GemmArgs b = a; b.N = a.n_store; return launch_splitk_reduce(partials, g.splits, b, st, a.N); }
@@ -1180,6 +1201,9 @@ int launch_gemm_tc_ex(const GemmArgs& a, const PlaneOp& A, const PlaneOp& B, boo
     // tile width: 64-wide tiles when they shorten the longest per-CTA queue (one persistent CTA per SM): small grids
     // that leave SMs idle with 128-wide tiles, and N that is not a multiple of 128 (e.g. 192 = 3 x 64)
     bool narrow = a.N <= 64;
+#ifdef RIFT_TC_LITE
+    narrow = true;
+#endif
     if (!narrow && splits <= 1) {
         static int sms = 0;
         if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
