@@ -330,6 +330,85 @@ def sft_goldens():
     print("sft_objectives", len(out))
 
 
+def evaluator_goldens():
+    """The candidate-rollout evaluator executed by the reference's own code where it runs without CARLA / shapely:
+    TrajEvaluator.get_ref_line_info / get_center_rollout / get_rollout_return (traj_evaluator.py:115-158,333-420),
+    TrackPropagate.propagate + derive_kinematics (track_propogate.py:500-699), DenseRewardModel, KinematicBicycleModel's
+    other-vehicle forecast (pdm_lite/kinematic_bicycle_model.py:33-61).  Two consecutive calls on the SAME TrackPropagate
+    object, so the PID buffers that the reference never resets carry over exactly as they do in a rollout."""
+    tp = ref_shim.track_propagate_module()
+    Reward = ref_shim.dense_reward_model_cls()
+    rel = "rift/cbv/planning/fine_tuner/rlft/traj_eval/traj_evaluator.py"
+    ref_line_info = ref_shim.ref_method(rel, "TrajEvaluator", "get_ref_line_info")
+    center_rollout = ref_shim.ref_method(rel, "TrajEvaluator", "get_center_rollout")
+    rollout_return = ref_shim.ref_method(rel, "TrajEvaluator", "get_rollout_return")
+
+    class _Self:
+        pass
+    me = _Self()
+    me.center_rollout_model = tp.TrackPropagate(virtual_time_step=0.1)
+    me.reward_model = Reward()
+    rng = np.random.Generator(np.random.PCG64(41))
+    out = {}
+    for call, (R, speed0) in enumerate([(3, 4.0), (2, 0.0), (6, 9.0)]):
+        M, T = 12, 80
+        # raw model-like trajectories: arc with per-candidate speed and curvature, (x, y, cos, sin, vx, vy)
+        spd = rng.uniform(0.0, 11.0, (R, M, 1))
+        s_ = np.cumsum(np.full((R, M, T), 0.1) * spd, -1)
+        th = rng.normal(0, 0.015, (R, M, 1)) * s_ + rng.normal(0, 0.05, (R, M, 1))
+        traj = np.stack([s_ * np.cos(th), s_ * np.sin(th) + rng.normal(0, 0.3, (R, M, 1)), np.cos(th), np.sin(th),
+                         spd * np.cos(th), spd * np.sin(th)], -1).astype(np.float32)
+        n_r = rng.integers(30, 121, R)
+        ref_pos = [np.stack([np.arange(n) * 1.0, 0.02 * np.arange(n) ** 1.3 * rng.normal()], -1).astype(np.float32) for n in n_r]
+        ref_ang = [np.arctan2(np.gradient(p[:, 1]), np.gradient(p[:, 0])).astype(np.float32) for p in ref_pos]
+        x0, y0, h0 = rng.normal(0, 40), rng.normal(0, 40), rng.normal(0, 1.5)
+
+        class _S:
+            pass
+        st = _S(); st.rear_axle = _S(); st.rear_axle.array = np.array([x0, y0]); st.rear_axle.heading = h0
+        st.dynamic_car_state = _S(); st.dynamic_car_state.speed = speed0
+        st.car_footprint = _S(); st.car_footprint.width, st.car_footprint.length = 2.0, 4.6
+        tt = torch.from_numpy(traj)[:, :, :40]
+        dd, da = ref_line_info(me, tt, [torch.from_numpy(p) for p in ref_pos], [torch.from_numpy(a) for a in ref_ang])
+        c, a, v, acc, yr, ya, vert = center_rollout(me, tt.clone(), [st])
+        col = rng.uniform(size=(R * M, 80)) < 0.01
+        off = rng.uniform(size=(R * M, 80)) < 0.03
+        ret = rollout_return(me, dd, da, v, acc, yr, ya, col, off)
+        k = f"call{call}_"
+        out[k + "traj"] = traj
+        for i, (p, an) in enumerate(zip(ref_pos, ref_ang)):
+            out[k + f"refpos{i}"], out[k + f"refang{i}"] = p, an
+        out[k + "state"] = np.array([x0, y0, h0, speed0, 2.0, 4.6])
+        out[k + "delta_dis"], out[k + "delta_angle"] = dd, da
+        out[k + "center"], out[k + "angle"], out[k + "speed"], out[k + "acc"] = c, a, v, acc
+        out[k + "yaw_rate"], out[k + "yaw_acc"], out[k + "vertices"] = yr, ya, vert
+        out[k + "collision"], out[k + "off_road"], out[k + "return"] = col, off, ret
+    # other-vehicle forecast (numpy, pdm_lite model)
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_ref_kbm", os.path.join(ref_shim.REF, "rift/ego/pdm_lite/kinematic_bicycle_model.py"))
+    kbm = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(kbm)
+
+    class _Cfg:
+        time_step, front_wheel_base, rear_wheel_base, steering_gain = 0.1, -0.090769015, 1.4178275, 0.36848336
+        brake_acceleration, throttle_acceleration = -4.952399, 0.5633837
+        throttle_values = brake_values = None
+        throttle_threshold_during_forecasting = 0.3
+    model = kbm.KinematicBicycleModel(_Cfg())
+    N = 5
+    loc = rng.normal(0, 30, (N, 3)); hd = rng.normal(0, 1.5, N); sp = rng.uniform(0, 12, N)
+    act = np.stack([rng.uniform(-0.5, 0.5, N), rng.uniform(0, 1, N), (rng.uniform(size=N) < 0.3).astype(float)], -1)
+    out["other_loc"], out["other_heading_rad"], out["other_speed"], out["other_action"] = loc, hd, sp, act
+    fl, fh, fv = [], [], []
+    l, h, v = loc.copy(), hd.copy(), sp.copy()
+    for i in range(40):
+        l, h, v = model.forecast_other_vehicles(l, h, v, act)
+        fl.append(l.copy()); fh.append(h.copy()); fv.append(v.copy())
+    out["other_future_loc"], out["other_future_heading"], out["other_future_speed"] = np.stack(fl), np.stack(fh), np.stack(fv)
+    np.savez_compressed(os.path.join(GOLDEN, "evaluator.npz"), **out)
+    print("evaluator", len(out))
+
+
 def state_dict_spec():
     spec = {}
     for mname, kw in (("small", {}), ("medium", {})):
@@ -356,6 +435,8 @@ if __name__ == "__main__":
         get_action_goldens()
     if not only or "sft" in only:
         sft_goldens()
+    if not only or "eval" in only:
+        evaluator_goldens()
     for name, case in CASES.items():
         if not only or name in only:
             run_case(name, case)

@@ -234,3 +234,29 @@ def pid_controller_cls():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod.PIDController
+
+
+def track_propagate_module():
+    """rift/cbv/planning/fine_tuner/rlft/traj_eval/track_propogate.py with its two CARLA-side imports stubbed
+    (CarlaAgentState is only a type annotation there, get_device_name -> 'cpu')."""
+    install()
+    import importlib.util
+    for name, attrs in (("rift.cbv.planning.pluto.utils.nuplan_state_utils", {"CarlaAgentState": object}),
+                        ("rift.util", {}), ("rift.util.torch_util", {"get_device_name": lambda: "cpu"})):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.__dict__.update(attrs)
+            sys.modules[name] = m
+    spec = importlib.util.spec_from_file_location(
+        "_ref_track_propagate", os.path.join(REF, "rift/cbv/planning/fine_tuner/rlft/traj_eval/track_propogate.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def dense_reward_model_cls():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_ref_reward", os.path.join(REF, "rift/gym_carla/reward/reward_model.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.DenseRewardModel

@@ -186,7 +186,10 @@ group_advantage_fixed_kernel(const double* __restrict__ ret, double* __restrict_
 // next pass's elements are already in flight in registers (software prefetch).
 constexpr int ADVW_MAXJ = 16;                 // elements per lane per pass: ceil(4 * G / 32) <= 16  <=>  G <= 128
 
-__global__ void __launch_bounds__(ADV_THREADS)
+// NJ = ceil(4 G / 32) is a template parameter: the staging loops unroll to exactly the passes this group size needs (ncu of
+// the run-time form at G = 72: 89 issued instructions per element, 116 registers -> 16 warps / SM; profiles/r2_advantage_ncu.md)
+template <int NJ>
+__global__ void __launch_bounds__(ADV_THREADS, 3)
 group_advantage_warp_kernel(const double* __restrict__ ret, double* __restrict__ adv, long long n_groups, int G, int Gp) {
     pdl_grid_sync();
     extern __shared__ double sm[];
@@ -196,42 +199,41 @@ group_advantage_warp_kernel(const double* __restrict__ ret, double* __restrict__
     double* ws = sm + (size_t)wib * 4 * Gp;                        // this warp's four groups
     const float invG = 1.f / (float)G;
     const int per = 4 * G;                                         // elements per pass
-    const int nj = (per + 31) >> 5;
     const long long n_quads = (n_groups + 3) >> 2;
     const long long wstride = (long long)gridDim.x * (ADV_THREADS / 32);
     long long quad = (long long)blockIdx.x * (ADV_THREADS / 32) + wib;
     const long long total = n_groups * G;
-    double v[ADVW_MAXJ];
+    double v[NJ];
     // element e of a pass -> (group e / G, position e % G) in the staged layout (no integer division: e < 2^10)
-    int slot[ADVW_MAXJ];
+    int slot[NJ];
 #pragma unroll
-    for (int j = 0; j < ADVW_MAXJ; ++j) {
+    for (int j = 0; j < NJ; ++j) {
         const int e = lane + 32 * j;
         const int g = (int)(((float)e + 0.5f) * invG);
-        slot[j] = g * Gp + (e - g * G);
+        slot[j] = e < per ? g * Gp + (e - g * G) : -1;
     }
     if (quad < n_quads) {
         const long long base = quad * per;
 #pragma unroll
-        for (int j = 0; j < ADVW_MAXJ; ++j) {
+        for (int j = 0; j < NJ; ++j) {
             const long long i = base + lane + 32 * j;
-            v[j] = (j < nj && lane + 32 * j < per && i < total) ? __ldg(ret + i) : 0.0;
+            v[j] = (slot[j] >= 0 && i < total) ? __ldg(ret + i) : 0.0;
         }
     }
     for (; quad < n_quads; quad += wstride) {
         const long long base = quad * per;
         const int ng = (int)min(4LL, n_groups - quad * 4);
 #pragma unroll
-        for (int j = 0; j < ADVW_MAXJ; ++j)
-            if (j < nj && lane + 32 * j < per) ws[slot[j]] = v[j];
+        for (int j = 0; j < NJ; ++j)
+            if (slot[j] >= 0) ws[slot[j]] = v[j];
         __syncwarp();
         const long long nq = quad + wstride;                       // prefetch the next pass while this one computes
         if (nq < n_quads) {
             const long long nb = nq * per;
 #pragma unroll
-            for (int j = 0; j < ADVW_MAXJ; ++j) {
+            for (int j = 0; j < NJ; ++j) {
                 const long long i = nb + lane + 32 * j;
-                v[j] = (j < nj && lane + 32 * j < per && i < total) ? __ldg(ret + i) : 0.0;
+                v[j] = (slot[j] >= 0 && i < total) ? __ldg(ret + i) : 0.0;
             }
         }
         if (gl < ng) {
@@ -240,11 +242,72 @@ group_advantage_warp_kernel(const double* __restrict__ ret, double* __restrict__
         }
         __syncwarp();
 #pragma unroll
-        for (int j = 0; j < ADVW_MAXJ; ++j) {
+        for (int j = 0; j < NJ; ++j) {
             const long long i = base + lane + 32 * j;
-            if (j < nj && lane + 32 * j < per && i < total) adv[i] = ws[slot[j]];
+            if (slot[j] >= 0 && i < total) adv[i] = ws[slot[j]];
         }
         __syncwarp();
+    }
+}
+
+// Fixed group size 8 <= G <= 128, REGISTER form: the eight lanes of a group read the group straight from global memory in
+// numpy's own order - lane k owns elements k, k + 8, k + 16, ... = exactly the terms of numpy's k-th accumulator - so the
+// whole group lives in NE = ceil(G / 8) registers per lane from the load to the store: no shared-memory staging, no
+// index arithmetic, no __syncwarp, NE independent 8-byte loads in flight per lane (every load instruction of a warp
+// covers four 64-byte segments).  The pairwise order is the one of pw_leaf8: per-lane accumulation over the full blocks
+// of eight, xor-butterfly ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), then the n % 8 tail elements added one by one.
+// (ncu of the staged form at G = 72: 89 issued instructions per element, issue-bound at 0.50 of the copy bandwidth.)
+template <int NE, bool SQ>
+__device__ __forceinline__ double pw_regs(const double (&x)[NE], int n, int lane8, unsigned gmask) {
+    const int nb = n >> 3;                                   // full blocks of eight
+    double r = SQ ? __dmul_rn(x[0], x[0]) : x[0];
+#pragma unroll
+    for (int j = 1; j < NE; ++j)
+        if (j < nb) r = __dadd_rn(r, SQ ? __dmul_rn(x[j], x[j]) : x[j]);
+    r = __dadd_rn(r, __shfl_xor_sync(gmask, r, 1));
+    r = __dadd_rn(r, __shfl_xor_sync(gmask, r, 2));
+    r = __dadd_rn(r, __shfl_xor_sync(gmask, r, 4));
+    // tail: elements 8 * nb + t live in lane t's register nb (NE - 1 when n is not a multiple of 8)
+    const int tail = n & 7;
+    if (tail) {
+        const double mine = SQ ? __dmul_rn(x[NE - 1], x[NE - 1]) : x[NE - 1];
+        const int base = (threadIdx.x & 31) & ~7;
+        for (int t = 0; t < tail; ++t) r = __dadd_rn(r, __shfl_sync(gmask, mine, base + t));
+    }
+    return r;
+}
+
+template <int NE>
+__global__ void __launch_bounds__(256)
+group_advantage_reg_kernel(const double* __restrict__ ret, double* __restrict__ adv, long long n_groups, int G) {
+    pdl_grid_sync();
+    const int lane8 = threadIdx.x & 7;
+    const unsigned gmask = 0xFFu << ((threadIdx.x & 31) & ~7);
+    const double dn = (double)G;
+    const bool nok = div_shared_ok(dn);
+    const double yn = __drcp_rn(dn);
+    const long long stride = (long long)gridDim.x * 32;      // groups per grid pass (256 threads = 32 groups per block)
+    // warp-uniform loop over the first group of the warp's four: the shuffles below need all lanes of a live warp
+    for (long long gw = (long long)blockIdx.x * 32 + (threadIdx.x >> 5) * 4; gw < n_groups; gw += stride) {
+        const long long g0 = gw + ((threadIdx.x & 31) >> 3);
+        const bool live = g0 < n_groups;
+        const double* src = ret + (live ? g0 : 0) * G;
+        double x[NE];
+#pragma unroll
+        for (int j = 0; j < NE; ++j) x[j] = (live && lane8 + 8 * j < G) ? __ldg(src + lane8 + 8 * j) : 0.0;
+        const double mean = div_shared(pw_regs<NE, false>(x, G, lane8, gmask), dn, yn, nok);
+#pragma unroll
+        for (int j = 0; j < NE; ++j) x[j] = __dadd_rn(x[j], -mean);
+        const double var = div_shared(pw_regs<NE, true>(x, G, lane8, gmask), dn, yn, nok);
+        const double sd = __dadd_rn(__dsqrt_rn(var), 1e-5);
+        const bool sok = div_shared_ok(sd);
+        const double ys = sok ? __drcp_rn(sd) : 0.0;
+        if (live) {
+            double* dst = adv + g0 * G;
+#pragma unroll
+            for (int j = 0; j < NE; ++j)
+                if (lane8 + 8 * j < G) dst[lane8 + 8 * j] = div_shared(x[j], sd, ys, sok);
+        }
     }
 }
 
@@ -276,9 +339,14 @@ __device__ __forceinline__ double pw_leaf_lane(const double* x, int n) {        
 
 constexpr int ADVL_THREADS = 128;
 
+// GT = group size at compile time: the staging loops unroll completely, so the GT coalesced 8-byte loads of a pass are all in
+// flight before the first one is used (the run-time form issued them one by one, each waiting for its own HBM round trip:
+// 0.34 of the copy bandwidth at G = 12), and the element -> (group, position) map costs a multiply instead of a loop.
+template <int GT>
 __global__ void __launch_bounds__(ADVL_THREADS)
-group_advantage_lane_kernel(const double* __restrict__ ret, double* __restrict__ adv, long long n_groups, int G, int Gp) {
+group_advantage_lane_kernel(const double* __restrict__ ret, double* __restrict__ adv, long long n_groups) {
     pdl_grid_sync();
+    constexpr int G = GT, Gp = GT | 1;
     extern __shared__ double sm[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     double* ws = sm + (size_t)wib * 32 * Gp;                       // this warp's 32 groups
@@ -292,35 +360,35 @@ group_advantage_lane_kernel(const double* __restrict__ ret, double* __restrict__
         const int ng = (int)min(32LL, n_groups - g0);
         const long long base = g0 * G;
         const int cnt = ng * G;
-        {   // coalesced global -> shared; (group, position) of element e tracked incrementally (e advances by 32)
-            int g = 0, k = lane;
-            while (k >= G) { k -= G; ++g; }
-            for (int e = lane; e < cnt; e += 32) {
-                ws[g * Gp + k] = __ldg(ret + base + e);
-                k += 32;
-                while (k >= G) { k -= G; ++g; }
-            }
+        double v[GT];
+#pragma unroll
+        for (int j = 0; j < GT; ++j) {
+            const int e = lane + 32 * j;
+            v[j] = e < cnt ? __ldg(ret + base + e) : 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < GT; ++j) {
+            const int e = lane + 32 * j;
+            ws[(e / G) * Gp + (e % G)] = v[j];
         }
         __syncwarp();
-        if (lane < ng) {
+        {
             double* x = ws + lane * Gp;
             const double mean = div_shared(pw_leaf_lane<false>(x, G), dn, yn, nok);
+#pragma unroll
             for (int i = 0; i < G; ++i) x[i] = __dadd_rn(x[i], -mean);
             const double var = div_shared(pw_leaf_lane<true>(x, G), dn, yn, nok);
             const double sd = __dadd_rn(__dsqrt_rn(var), 1e-5);
             const bool sok = div_shared_ok(sd);
             const double ys = sok ? __drcp_rn(sd) : 0.0;
+#pragma unroll
             for (int i = 0; i < G; ++i) x[i] = div_shared(x[i], sd, ys, sok);
         }
         __syncwarp();
-        {
-            int g = 0, k = lane;
-            while (k >= G) { k -= G; ++g; }
-            for (int e = lane; e < cnt; e += 32) {
-                adv[base + e] = ws[g * Gp + k];
-                k += 32;
-                while (k >= G) { k -= G; ++g; }
-            }
+#pragma unroll
+        for (int j = 0; j < GT; ++j) {
+            const int e = lane + 32 * j;
+            if (e < cnt) adv[base + e] = ws[(e / G) * Gp + (e % G)];
         }
         __syncwarp();
     }
@@ -361,14 +429,33 @@ int launch_group_advantage(const double* ret, const long long* offsets, long lon
             // rows cost too much occupancy and the eight-lane form wins (G = 72: 351 vs 105 us)
             const size_t smem_l = (size_t)(ADVL_THREADS / 32) * 32 * Gp * sizeof(double);
             static bool attr_l = false;
-            if (!attr_l) {
-                RIFT_CUDA_OK(cudaFuncSetAttribute(group_advantage_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-                attr_l = true;
-            }
+            (void)attr_l;       // 4 warps x 32 groups x 33 doubles = 33 KB at most: inside the default dynamic shared-memory limit
             const long long n_pass = (n_groups + 31) / 32;
             const int per_sm = (int)max((size_t)1, min((size_t)8, (size_t)(220 * 1024) / (smem_l + 1024)));
             const int grid = (int)min((n_pass + 3) / 4, (long long)148 * per_sm);
-            launch_k(group_advantage_lane_kernel, grid, ADVL_THREADS, smem_l, st, ret, adv, n_groups, G, Gp);
+#define RIFT_ADVL(N) case N: launch_k(group_advantage_lane_kernel<N>, grid, ADVL_THREADS, smem_l, st, ret, adv, n_groups); break;
+            switch (G) {
+                RIFT_ADVL(1) RIFT_ADVL(2) RIFT_ADVL(3) RIFT_ADVL(4) RIFT_ADVL(5) RIFT_ADVL(6) RIFT_ADVL(7) RIFT_ADVL(8)
+                RIFT_ADVL(9) RIFT_ADVL(10) RIFT_ADVL(11) RIFT_ADVL(12) RIFT_ADVL(13) RIFT_ADVL(14) RIFT_ADVL(15) RIFT_ADVL(16)
+                RIFT_ADVL(17) RIFT_ADVL(18) RIFT_ADVL(19) RIFT_ADVL(20) RIFT_ADVL(21) RIFT_ADVL(22) RIFT_ADVL(23) RIFT_ADVL(24)
+                RIFT_ADVL(25) RIFT_ADVL(26) RIFT_ADVL(27) RIFT_ADVL(28) RIFT_ADVL(29) RIFT_ADVL(30) RIFT_ADVL(31) RIFT_ADVL(32)
+                default: set_last_error("internal: advantage lane form"); return -1;
+            }
+#undef RIFT_ADVL
+            RIFT_LAUNCH_OK();
+            return 0;
+        }
+        static const bool staged_form = getenv("RIFT_B200_ADV_STAGED") != nullptr;
+        if (G >= 8 && G <= 128 && !block_form && !warp_form && !staged_form) {
+            const int ne = (G + 7) / 8;
+            const int grid = (int)min((n_groups + 31) / 32, (long long)148 * 8);
+#define RIFT_ADVR(N) case N: launch_k(group_advantage_reg_kernel<N>, grid, 256, 0, st, ret, adv, n_groups, G); break;
+            switch (ne) {
+                RIFT_ADVR(1) RIFT_ADVR(2) RIFT_ADVR(3) RIFT_ADVR(4) RIFT_ADVR(5) RIFT_ADVR(6) RIFT_ADVR(7) RIFT_ADVR(8)
+                RIFT_ADVR(9) RIFT_ADVR(10) RIFT_ADVR(11) RIFT_ADVR(12) RIFT_ADVR(13) RIFT_ADVR(14) RIFT_ADVR(15) RIFT_ADVR(16)
+                default: set_last_error("internal: advantage register count"); return -1;
+            }
+#undef RIFT_ADVR
             RIFT_LAUNCH_OK();
             return 0;
         }
@@ -376,7 +463,14 @@ int launch_group_advantage(const double* ret, const long long* offsets, long lon
             const long long n_quads = (n_groups + 3) / 4;
             const int per_sm = (int)max((size_t)1, min((size_t)8, (size_t)(200 * 1024) / (smem + 1024)));
             const int grid = (int)min((n_quads + 7) / 8, (long long)148 * per_sm);
-            launch_k(group_advantage_warp_kernel, grid, ADV_THREADS, smem, st, ret, adv, n_groups, G, Gp);
+            const int nj = (4 * G + 31) / 32;
+#define RIFT_ADVW(N) case N: launch_k(group_advantage_warp_kernel<N>, grid, ADV_THREADS, smem, st, ret, adv, n_groups, G, Gp); break;
+            switch (nj) {
+                RIFT_ADVW(1) RIFT_ADVW(2) RIFT_ADVW(3) RIFT_ADVW(4) RIFT_ADVW(5) RIFT_ADVW(6) RIFT_ADVW(7) RIFT_ADVW(8)
+                RIFT_ADVW(9) RIFT_ADVW(10) RIFT_ADVW(11) RIFT_ADVW(12) RIFT_ADVW(13) RIFT_ADVW(14) RIFT_ADVW(15) RIFT_ADVW(16)
+                default: set_last_error("internal: advantage pass count"); return -1;
+            }
+#undef RIFT_ADVW
             RIFT_LAUNCH_OK();
             return 0;
         }
