@@ -208,6 +208,31 @@ typedef struct {
 } rift_b200_gather_field;
 int rift_b200_gather_fields(const rift_b200_gather_field* fields, int n_fields, const long long* idx, int bs, void* stream);
 
+/* ---- candidate-rollout evaluator (traj_evaluator.py:115-475 TrajEvaluator.get_grpo_advantage, track_propogate.py:160-780
+ * TrackPropagate, reward_model.py:34-50 DenseRewardModel, kinematic_bicycle_model.py:33-61).  All arrays are DEVICE pointers
+ * unless named *_host.  G = R * M candidates; a candidate is scored over its first 40 frames and rolled out for 80.
+ *   ref_line_info   trajectory [R, M, T_in >= 40, 6] (x, y, cos, sin, vx, vy); reference lines packed ref_pos [sum n_r, 2],
+ *                   ref_angle [sum n_r], ref_offsets [R + 1]; out delta_dis / delta_angle [G, 40]
+ *   center_rollout  state6_host = {origin x, y, heading (rad, right-handed), speed, width, length}; pid_buf [2, pid_slots, 20],
+ *                   pid_ptr / pid_len [2, pid_slots] int32 persist between calls (zero-initialise once); out center [G, 80, 2],
+ *                   angle / speed (smoothed) / acc / yaw_rate / yaw_acc [G, 80], vertices [G, 80, 4, 2]
+ *   other_rollout   float64 like the reference: location [N, 3], heading_deg [N], speed [N], control [N, 3] = steer, throttle,
+ *                   brake; extent [N, 2]; out vertices [N, n_frames, 4, 2] in the right-handed frame
+ *   returns         off_road_mask [H, W] uint8 (1 = off road; NULL = no raster) with map_pose4_host = {origin x, y, angle,
+ *                   metres per pixel}; out returns [G] float64; collision_out / offroad_out [G, 80] uint8 (may be NULL) */
+int rift_b200_eval_ref_line_info(const float* trajectory, int R, int M, int T_in, const float* ref_pos, const float* ref_angle,
+                                 const int* ref_offsets, float* delta_dis, float* delta_angle, void* stream);
+int rift_b200_eval_center_rollout(const float* trajectory, int G, int T_in, const float* state6_host, float dt, float* pid_buf,
+                                  int* pid_ptr, int* pid_len, int pid_slots, float* center, float* angle, float* speed, float* acc,
+                                  float* yaw_rate, float* yaw_acc, float* vertices, void* stream);
+int rift_b200_eval_other_rollout(const double* location, const double* heading_deg, const double* speed, const double* control,
+                                 const double* extent, int N, int n_frames, int near_lane_change, double inflation, double* vertices,
+                                 void* stream);
+int rift_b200_eval_returns(const float* delta_dis, const float* delta_angle, const float* speed, const float* acc, const float* yaw_rate,
+                           const float* yaw_acc, const float* center, const float* vertices, const double* other_vertices, int N,
+                           int other_frames, const uint8_t* off_road_mask, int H, int W, const double* map_pose4_host, int G,
+                           double gamma, double* returns, uint8_t* collision_out, uint8_t* offroad_out, void* stream);
+
 /* ---- primitive operators exported for the kernel-level parity tests (tests/test_ops_gpu.py) ---- */
 int rift_b200_op_add_inplace(float* dst, const float* src, long long n, void* stream);      /* dst += src */
 int rift_b200_op_linear(const float* x, int rows, int K, const float* w, const float* bias, int N, int act,

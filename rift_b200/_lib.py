@@ -91,6 +91,12 @@ _SIGNATURES = {
     "rift_b200_clip_adamw_dev": (C.c_int, [_V, _V, _V, _V, C.c_longlong, C.c_longlong, _V, C.c_float, _V, C.c_float,
                                            C.c_float, C.c_float, C.c_float, _V, _V, _V]),
     "rift_b200_refresh_weights": (C.c_int, [_V, _V]),
+    "rift_b200_eval_ref_line_info": (C.c_int, [_V, C.c_int, C.c_int, C.c_int, _V, _V, _V, _V, _V, _V]),
+    "rift_b200_eval_center_rollout": (C.c_int, [_V, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_float, _V, _V, _V, C.c_int,
+                                                _V, _V, _V, _V, _V, _V, _V, _V]),
+    "rift_b200_eval_other_rollout": (C.c_int, [_V, _V, _V, _V, _V, C.c_int, C.c_int, C.c_int, C.c_double, _V, _V]),
+    "rift_b200_eval_returns": (C.c_int, [_V, _V, _V, _V, _V, _V, _V, _V, _V, C.c_int, C.c_int, _V, C.c_int, C.c_int,
+                                         C.POINTER(C.c_double), C.c_int, C.c_double, _V, _V, _V, _V]),
     "rift_b200_gather_fields": (C.c_int, [C.POINTER(GatherField), C.c_int, _V, C.c_int, _V]),
     "rift_b200_op_add_inplace": (C.c_int, [_V, _V, C.c_longlong, _V]),
     "rift_b200_op_linear": (C.c_int, [_V, C.c_int, C.c_int, _V, _V, C.c_int, C.c_int, _V, _V, C.c_int, _V]),

@@ -83,6 +83,12 @@ inline int new_act(Ctx& c, int rows, int C, int want, Act* a) {
 }
 inline Act act_f32(float* f, long long ld, int rows, int C) { Act a; a.f = f; a.ld = ld; a.rows = rows; a.C = C; return a; }
 
+// RIFT_B200_PACK_TRACE=1: one stderr line per standalone pack (site, rows, features) - which activations still reach a
+// tensor-core GEMM as fp32 and pay a pack kernel on the way
+inline void pack_trace(const char* site, int rows, int C) {
+    static const bool on = getenv("RIFT_B200_PACK_TRACE") != nullptr;
+    if (on) fprintf(stderr, "PACK %s %d %d\n", site, rows, C);
+}
 inline int ensure_planes(Ctx& c, Act& x) {
     if (x.p.on()) return 0;
     x.p.Kp = tc_pitch(x.C);
@@ -91,6 +97,7 @@ inline int ensure_planes(Ctx& c, Act& x) {
     if (!x.p.hi || !x.p.lo) { set_last_error("workspace too small"); return -1; }
     if (c.dry) return 0;
     if (!x.f) { set_last_error("internal: activation has neither fp32 nor planes"); return -1; }
+    pack_trace("operand", x.rows, x.C);
     return launch_pack_split(x.f, x.ld, x.rows, x.C, x.p.Kp, x.p.hi, x.p.lo, c.st);
 }
 
@@ -302,6 +309,7 @@ inline int lin_bwd(Ctx& c, const float* X, long long ldx, const float* dY, long 
         if (!dYp.hi || !dYp.lo) { set_last_error("workspace too small"); return -1; }
         if (!c.dry) {
             int slabs = 0;
+            pack_trace(want_b && !bias_done ? "bwd_dY_colsum" : "bwd_dY", M, L.N);
             if (want_b && !bias_done) TRY(launch_pack_split_colsum(dY, lddy, M, L.N, dYp.Kp, dYp.hi, dYp.lo, sc, &slabs, c.st));   // one pass over dY
             if (slabs > 0) {
                 SideStream fin;
@@ -326,7 +334,7 @@ inline int lin_bwd(Ctx& c, const float* X, long long ldx, const float* dY, long 
             xp.hi = c.alloc<uint16_t>((size_t)M * xp.Kp);
             xp.lo = c.alloc<uint16_t>((size_t)M * xp.Kp);
             if (!xp.hi || !xp.lo) { set_last_error("workspace too small"); return -1; }
-            if (!c.dry) TRY(launch_pack_split(X, ldx, M, L.K, xp.Kp, xp.hi, xp.lo, c.st));
+            if (!c.dry) { pack_trace("bwd_X", M, L.K); TRY(launch_pack_split(X, ldx, M, L.K, xp.Kp, xp.hi, xp.lo, c.st)); }
             forked = false;                      // the side stream has not seen this pack yet
         }
         const int tiles = ((L.N + 127) / 128) * ((L.K + (L.K <= 64 ? 63 : 127)) / (L.K <= 64 ? 64 : 128));

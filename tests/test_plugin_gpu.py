@@ -197,6 +197,9 @@ def _agent_state(x, y, heading, speed):
     s.rear_axle = _P(); s.rear_axle.array = np.array([x, y], np.float64); s.rear_axle.heading = float(heading)
     s.dynamic_car_state = _P(); s.dynamic_car_state.center_velocity_2d = _P()
     s.dynamic_car_state.center_velocity_2d.magnitude = lambda v=float(speed): v
+    s.dynamic_car_state.speed = float(speed)
+    s.car_footprint = _P(); s.car_footprint.width, s.car_footprint.length = 2.0, 4.6
+    s.center = _P(); s.center.array = np.array([x + 1.4 * np.cos(heading), y + 1.4 * np.sin(heading)]); s.center.heading = float(heading)
     return s
 
 
@@ -295,6 +298,32 @@ def test_get_action_keys_values_and_graph_replay(policy_name, tmp_path):
     # CBVs that left the scene lose their PID state (pluto.py:114-125)
     pol.get_action([{101: obs0[101]}, {}], infos, deterministic=True)
     assert set(pol.controllers[0]) == {101} and 1 not in pol.controllers
+
+
+def test_get_action_with_the_cuda_candidate_evaluator(tmp_path):
+    """Train-mode get_action with the CUDA TrajEvaluator on the reference's hook (rift_pluto.py:113-145 ->
+    traj_evaluator.py:422-475): (R, 12) float64 advantages, one group per CBV, finite and standardised."""
+    from rift_b200.evaluator import TrajEvaluator
+    cfg = pluto_small()
+    pre = tmp_path / "pretrained.ckpt"
+    sd = {k: torch.from_numpy(v) for k, v in synth_state_dict(cfg, seed=7).items()}
+    torch.save({"state_dict": {"model." + k: v for k, v in sd.items()}}, pre)
+    config = {"ckpt_path": str(pre), "ROOT_DIR": str(tmp_path), "model_path": "models", "load_agent_info": "rift_pluto",
+              "obs": {"radius": 120}, "frame_rate": 10, "num_scenario": 1, "topk": 10}
+    pol = CBV_POLICY_LIST["rift_pluto"](config)
+    pol.load_model(resume=True)
+    pol.set_mode("train")
+    buf = _make_buffer(3, seed=9)
+    obs0 = {101 + i: {"raw_pluto_feature": buf.items[i]["CBVs_obs"]["raw_pluto_feature"]} for i in range(3)}
+    pol.set_world(_World(list(obs0)))
+    pol.set_traj_evaluator(TrajEvaluator())
+    data = pol.get_action([obs0], [{"env_id": 0}], deterministic=True)
+    for cid in obs0:
+        R = obs0[cid]["raw_pluto_feature"].data["reference_line"]["position"].shape[0]
+        adv = data["CBVs_group_advantage"][0][cid]
+        assert adv["advantage"].shape == (R, 12) and adv["advantage"].dtype == np.float64 and adv["valid_mask"].all()
+        assert np.isfinite(adv["advantage"]).all() and abs(adv["advantage"].mean()) < 1e-9
+        assert adv["advantage"].std() == 0.0 or abs(adv["advantage"].std() - 1.0) < 1e-2
 
 
 @pytest.mark.parametrize("kind", ["sft", "rtr", "rs"])
