@@ -104,9 +104,12 @@ static int points_bwd(Ctx& c, const PointsTape& t, const PointsEncP& p, const fl
 }
 
 // generic pre-LN attention + MLP block tail: X2 = X1 + fc2(act(fc1(LN2(X1))));  dX (rows x D) is updated in place
+// dXp (optional): on entry the split-bf16 planes of dX when its producer wrote them (else off()), on return the planes of
+// the updated dX (or off()) - the residual-stream gradient then never needs a pack kernel between sub-blocks
 static int mlp_tail_bwd(Ctx& c, int rows, int D, int Hd, const Act& hm, const float* act_ref, int act, const Act& t2, const LNSave& ln2,
-                        const Norm& n2, const Lin& fc1, const Lin& fc2, float* dX) {
+                        const Norm& n2, const Lin& fc1, const Lin& fc2, float* dX, Planes* dXp = nullptr) {
     ALLOC(d_t2, float, (size_t)rows * D);
+    const Planes dY_in = (dXp && dXp->on() && lin_bwd_all_tc(c, rows, fc2, true)) ? *dXp : Planes();
     // (ReLU only: GELU's derivative - erf + exp per element - costs more inside the GEMM epilogue, where it is
     // instruction-latency bound, than the bandwidth-bound activation-backward kernel it would replace; measured)
     static const bool fuse_gelu = [] { const char* e = getenv("RIFT_B200_FUSE_GELU_BWD"); return e && atoi(e) != 0; }();
@@ -120,16 +123,18 @@ static int mlp_tail_bwd(Ctx& c, int rows, int D, int Hd, const Act& hm, const fl
         dhp.lo = c.alloc<uint16_t>((size_t)rows * dhp.Kp);
         if (!dhp.hi || !dhp.lo) { set_last_error("workspace too small"); return -1; }
         LinBwdFuse f2; f2.dact_ref = act_ref; f2.lddact = Hd; f2.dact = act; f2.dX_planes = &dhp;
+        if (dY_in.on()) f2.dYp_in = &dY_in;
         TRY(lin_bwd(c, hm.f, Hd, dX, D, rows, fc2, nullptr, Hd, 0.f, true, &hm.p, &f2));
         LinBwdFuse f1; f1.dYp_in = &dhp;
         TRY(lin_bwd(c, t2.f, D, nullptr, Hd, rows, fc1, d_t2, D, 0.f, true, &t2.p, &f1));
     } else {
         ALLOC(d_hm, float, (size_t)rows * Hd);
-        TRY(lin_bwd(c, hm.f, Hd, dX, D, rows, fc2, d_hm, Hd, 0.f, true, &hm.p));
+        LinBwdFuse f2; f2.dYp_in = &dY_in;
+        TRY(lin_bwd(c, hm.f, Hd, dX, D, rows, fc2, d_hm, Hd, 0.f, true, &hm.p, dY_in.on() ? &f2 : nullptr));
         TRY(act_bwd(c, act_ref, d_hm, (long long)rows * Hd, act));
         TRY(lin_bwd(c, t2.f, D, d_hm, Hd, rows, fc1, d_t2, D, 0.f, true, &t2.p));
     }
-    TRY(ln_bwd(c, ln2, n2, d_t2, nullptr, dX, 1));
+    TRY(ln_bwd(c, ln2, n2, d_t2, nullptr, dX, 1, dXp, rows));
     return 0;
 }
 
@@ -191,7 +196,26 @@ int rift_b200_engine::backward_impl(const rift_b200_batch& bt, const float* dlog
     ALLOC(dq, float, (size_t)rowsQ * D);            // running gradient of the decoder residual stream
     ALLOC(deg, float, (size_t)bs * D);
     ZALLOC(dXn, (size_t)rowsE * D);
-    TRY(lin_bwd(c, tp.qlast, D, dqf, D, rowsQ, ca, dq, D, 0.f, false));
+    // dqp: split-bf16 planes of dq whenever its last producer could write them (GEMM epilogue, LayerNorm backward); each
+    // consumer below falls back to packing dq itself when they are off()
+    Planes dqp;
+    {
+        LinBwdFuse fq;
+        if (ln_bwd_fuse_on() && lin_bwd_all_tc(c, rowsQ, ca, true)) {
+            dqp.Kp = tc_pitch(D);
+            dqp.hi = c.alloc<uint16_t>((size_t)rowsQ * dqp.Kp);
+            dqp.lo = c.alloc<uint16_t>((size_t)rowsQ * dqp.Kp);
+            if (!dqp.hi || !dqp.lo) { set_last_error("workspace too small"); return -1; }
+            fq.dX_planes = &dqp;
+        }
+        TRY(lin_bwd(c, tp.qlast, D, dqf, D, rowsQ, ca, dq, D, 0.f, false, nullptr, dqp.on() ? &fq : nullptr));
+    }
+    // dq as pre-packed dY of `L` when both of L's gradient products take the tensor-core route
+    auto with_dq = [&](LinBwdFuse& f, const Lin& L) -> const LinBwdFuse* {
+        if (!dqp.on() || !lin_bwd_all_tc(c, rowsQ, L, true)) return nullptr;
+        f.dYp_in = &dqp;
+        return &f;
+    };
     if (!c.dry) TRY(launch_groupsum(dqf, D, bs, R * Mo, D, deg, D, 0, c.st));
     TRY(lin_bwd(c, tp.Xn.f, (long long)S * D, deg, D, bs, cb, dXn, (long long)S * D, 0.f));
 
@@ -203,62 +227,93 @@ int rift_b200_engine::backward_impl(const rift_b200_batch& bt, const float* dlog
         const Lin cr_q = slice(db.cross.in, 0, D, 0, D, true), cr_kv = slice(db.cross.in, D, 2 * D, 0, D, true);
         // (iv) ReLU FFN
         // ReLU'(.) from the post-activation values, or - after the fused forward, which keeps no fp32 hidden - from the pre-activation
-        TRY(mlp_tail_bwd(c, rowsQ, D, 4 * D, dt.hm, dt.hpre4 ? dt.hpre4 : dt.hm.f, ACT_RELU, dt.t4, dt.ln4, db.n4, db.ffn0, db.ffn3, dq));
+        TRY(mlp_tail_bwd(c, rowsQ, D, 4 * D, dt.hm, dt.hpre4 ? dt.hpre4 : dt.hm.f, ACT_RELU, dt.t4, dt.ln4, db.n4, db.ffn0, db.ffn3, dq, &dqp));
         // (iii) cross-attention
         {
             ALLOC(d_a3, float, (size_t)rowsQ * D);
             ALLOC(d_qc, float, (size_t)rowsQ * D);
             ALLOC(d_kvc, float, (size_t)rowsE * 2 * D);
             ALLOC(d_t3, float, (size_t)rowsQ * D);
-            TRY(lin_bwd(c, dt.a3.f, D, dq, D, rowsQ, db.cross.out, d_a3, D, 0.f, true, &dt.a3.p));
+            LinBwdFuse f3;
+            TRY(lin_bwd(c, dt.a3.f, D, dq, D, rowsQ, db.cross.out, d_a3, D, 0.f, true, &dt.a3.p, with_dq(f3, db.cross.out)));
+            // dQ / dK / dV leave the attention backward as split-bf16 planes when both projections' gradient products run on
+            // the tensor cores: no fp32 copy, no pack
+            const bool ap = attn_planes_on(c) && attention_bwd_planes_ok(R * Mo, S, D / H) && lin_bwd_all_tc(c, rowsQ, cr_q, true) &&
+                            lin_bwd_all_tc(c, rowsE, cr_kv, true);
+            Planes pqc, pkvc;
+            if (ap) { TRY(new_planes(c, rowsQ, D, &pqc)); TRY(new_planes(c, rowsE, 2 * D, &pkvc)); }
             if (!c.dry) {
                 AttnArgs a = attn_cross(dt.qc, dt.kvc, bs, R * Mo, S, D, H, tp.key_pad, att_scale);
                 a.lse = dt.lse3;
-                TRY(launch_attention_bwd(a, d_a3, D, d_qc, D, d_kvc, d_kvc + D, 2 * D, 2 * D, c.st));
+                AttnBwdPlanes pl;
+                if (ap) { pl.q = pqc; pl.k = pkvc; pl.v = plane_cols(pkvc, D); }
+                TRY(launch_attention_bwd(a, d_a3, D, ap ? nullptr : d_qc, D, ap ? nullptr : d_kvc, ap ? nullptr : d_kvc + D, 2 * D, 2 * D, c.st, pl));
             }
-            TRY(lin_bwd(c, dt.t3.f, D, d_qc, D, rowsQ, cr_q, d_t3, D, 0.f, true, &dt.t3.p));
+            LinBwdFuse fqc, fkvc;
+            if (ap) { fqc.dYp_in = &pqc; fkvc.dYp_in = &pkvc; }
+            TRY(lin_bwd(c, dt.t3.f, D, d_qc, D, rowsQ, cr_q, d_t3, D, 0.f, true, &dt.t3.p, ap ? &fqc : nullptr));
             // the K / V projection's gradients feed dXn, which the query chain never reads: branch stream
             // (in order there, so the accumulation into dXn stays sequential)
             TRY(fork_to(c, c.br));
             {
                 OnStream on_br(c, c.br);
-                TRY(lin_bwd(c, tp.Xn.f, D, d_kvc, 2 * D, rowsE, cr_kv, dXn, D, 1.f, true, &tp.Xn.p));
+                TRY(lin_bwd(c, tp.Xn.f, D, d_kvc, 2 * D, rowsE, cr_kv, dXn, D, 1.f, true, &tp.Xn.p, ap ? &fkvc : nullptr));
             }
-            TRY(ln_bwd(c, dt.ln3, db.n3, d_t3, nullptr, dq, 1));
+            // (ii) below starts from dq with the rows of padded reference lines cleared (their forward output was overwritten
+            // with 0 -> no gradient through them): done by this LayerNorm backward on its way out
+            TRY(ln_bwd(c, dt.ln3, db.n3, d_t3, nullptr, dq, 1, &dqp, rowsQ, tp.r_pad, Mo));
         }
-        // (ii) m2m: rows of padded reference lines were overwritten with 0 -> no gradient through them
+        // (ii) m2m
         {
-            if (!c.dry) TRY(launch_zero_rows(dq, tp.r_pad, Mo, rowsQ, D, c.st));
             ALLOC(d_a2, float, (size_t)rowsQ * D);
             ALLOC(dqkv2, float, (size_t)rowsQ * 3 * D);
             ALLOC(d_t2, float, (size_t)rowsQ * D);
             ALLOC(sc, float, (size_t)Mo * D);
-            TRY(lin_bwd(c, dt.a2.f, D, dq, D, rowsQ, db.m2m.out, d_a2, D, 0.f, true, &dt.a2.p));
+            LinBwdFuse f2o;
+            TRY(lin_bwd(c, dt.a2.f, D, dq, D, rowsQ, db.m2m.out, d_a2, D, 0.f, true, &dt.a2.p, with_dq(f2o, db.m2m.out)));
+            const bool ap = attn_planes_on(c) && attention_bwd_planes_ok(Mo, Mo, D / H) && lin_bwd_all_tc(c, rowsQ, m2m_qk, true) &&
+                            lin_bwd_all_tc(c, rowsQ, m2m_v, true);
+            Planes pqk2, pv2;
+            if (ap) { TRY(new_planes(c, rowsQ, 2 * D, &pqk2)); TRY(new_planes(c, rowsQ, D, &pv2)); }
             if (!c.dry) {
                 AttnArgs a = attn_m2m(dt.qkv2, NR, Mo, D, H, att_scale);
                 a.lse = dt.lse2;
-                TRY(launch_attention_bwd(a, d_a2, D, dqkv2, 3 * D, dqkv2 + D, dqkv2 + 2 * D, 3 * D, 3 * D, c.st));
+                AttnBwdPlanes pl;
+                if (ap) { pl.q = pqk2; pl.k = plane_cols(pqk2, D); pl.v = pv2; }
+                TRY(launch_attention_bwd(a, d_a2, D, ap ? nullptr : dqkv2, 3 * D, ap ? nullptr : dqkv2 + D, ap ? nullptr : dqkv2 + 2 * D, 3 * D,
+                                         3 * D, c.st, pl));
             }
-            TRY(lin_bwd(c, dt.t2p.f, D, dqkv2, 3 * D, rowsQ, m2m_qk, d_t2, D, 0.f, true, &dt.t2p.p));            // d(LN2 out + m_pos)
+            LinBwdFuse fqk2, fv2;
+            if (ap) { fqk2.dYp_in = &pqk2; fv2.dYp_in = &pv2; }
+            TRY(lin_bwd(c, dt.t2p.f, D, dqkv2, 3 * D, rowsQ, m2m_qk, d_t2, D, 0.f, true, &dt.t2p.p, ap ? &fqk2 : nullptr));   // d(LN2 out + m_pos)
             if (m.m_pos.train && !c.dry) TRY(launch_modsum(d_t2, D, rowsQ, D, Mo, m.m_pos.d, 1, c.st));
             (void)sc;
-            TRY(lin_bwd(c, dt.t2.f, D, dqkv2 + 2 * D, 3 * D, rowsQ, m2m_v, d_t2, D, 1.f, true, &dt.t2.p));       // + value path
-            TRY(ln_bwd(c, dt.ln2, db.n2, d_t2, nullptr, dq, 1));
+            TRY(lin_bwd(c, dt.t2.f, D, dqkv2 + 2 * D, 3 * D, rowsQ, m2m_v, d_t2, D, 1.f, true, &dt.t2.p, ap ? &fv2 : nullptr));   // + value path
+            TRY(ln_bwd(c, dt.ln2, db.n2, d_t2, nullptr, dq, 1, &dqp, rowsQ));
         }
         // (i) r2r
         {
             ALLOC(d_a1, float, (size_t)rowsQ * D);
             ALLOC(dqkv1, float, (size_t)rowsQ * 3 * D);
             ALLOC(d_t1, float, (size_t)rowsQ * D);
-            TRY(lin_bwd(c, dt.a1.f, D, dq, D, rowsQ, db.r2r.out, d_a1, D, 0.f, true, &dt.a1.p));
+            LinBwdFuse f1o;
+            TRY(lin_bwd(c, dt.a1.f, D, dq, D, rowsQ, db.r2r.out, d_a1, D, 0.f, true, &dt.a1.p, with_dq(f1o, db.r2r.out)));
+            const bool ap = attn_planes_on(c) && attention_bwd_planes_ok(R, R, D / H) && lin_bwd_all_tc(c, rowsQ, db.r2r.in, true);
+            Planes p1;
+            if (ap) TRY(new_planes(c, rowsQ, 3 * D, &p1));
             if (!c.dry) {
                 AttnArgs a = attn_r2r(dt.qkv1, bs, R, Mo, D, H, tp.r_pad_r2r, att_scale);
                 a.kpm_mod = tp.r2r_mod; a.kpm_off = tp.r2r_off;
                 a.lse = dt.lse1;
-                TRY(launch_attention_bwd(a, d_a1, D, dqkv1, 3 * D, dqkv1 + D, dqkv1 + 2 * D, 3 * D, 3 * D, c.st));
+                AttnBwdPlanes pl;
+                if (ap) { pl.q = p1; pl.k = plane_cols(p1, D); pl.v = plane_cols(p1, 2 * D); }
+                TRY(launch_attention_bwd(a, d_a1, D, ap ? nullptr : dqkv1, 3 * D, ap ? nullptr : dqkv1 + D, ap ? nullptr : dqkv1 + 2 * D, 3 * D,
+                                         3 * D, c.st, pl));
             }
-            TRY(lin_bwd(c, dt.t1.f, D, dqkv1, 3 * D, rowsQ, db.r2r.in, d_t1, D, 0.f, true, &dt.t1.p));
-            TRY(ln_bwd(c, dt.ln1, db.n1, d_t1, nullptr, dq, 1));
+            LinBwdFuse f1i;
+            if (ap) f1i.dYp_in = &p1;
+            TRY(lin_bwd(c, dt.t1.f, D, dqkv1, 3 * D, rowsQ, db.r2r.in, d_t1, D, 0.f, true, &dt.t1.p, ap ? &f1i : nullptr));
+            TRY(ln_bwd(c, dt.ln1, db.n1, d_t1, nullptr, dq, 1, &dqp, rowsQ));
         }
     }
 
@@ -291,22 +346,33 @@ int rift_b200_engine::backward_impl(const rift_b200_batch& bt, const float* dlog
     // ---------------- scene encoding: final norm <- encoder blocks
     ALLOC(dX, float, (size_t)rowsE * D);
     if (dxn_done) RIFT_CUDA_OK(cudaStreamWaitEvent(c.st, dxn_done, 0));
-    TRY(ln_bwd(c, tp.ln_final, m.final_norm, dXn, nullptr, dX, 0));
+    Planes dXp;                                      // planes of the encoder stream's gradient, same protocol as dqp
+    TRY(ln_bwd(c, tp.ln_final, m.final_norm, dXn, nullptr, dX, 0, &dXp, rowsE));
     for (int l = (int)m.enc.size() - 1; l >= 0; --l) {
         const EncBlockP& eb = m.enc[l];
         const EncBlockTape& et = tp.enc[l];
-        TRY(mlp_tail_bwd(c, rowsE, D, 4 * D, et.hm, et.hpre, ACT_GELU, et.t2, et.ln2, eb.n2, eb.fc1, eb.fc2, dX));
+        TRY(mlp_tail_bwd(c, rowsE, D, 4 * D, et.hm, et.hpre, ACT_GELU, et.t2, et.ln2, eb.n2, eb.fc1, eb.fc2, dX, &dXp));
         ALLOC(d_att, float, (size_t)rowsE * D);
         ALLOC(dqkv, float, (size_t)rowsE * 3 * D);
         ALLOC(d_t1, float, (size_t)rowsE * D);
-        TRY(lin_bwd(c, et.att.f, D, dX, D, rowsE, eb.attn.out, d_att, D, 0.f, true, &et.att.p));
+        LinBwdFuse fo;
+        if (dXp.on() && lin_bwd_all_tc(c, rowsE, eb.attn.out, true)) fo.dYp_in = &dXp;
+        TRY(lin_bwd(c, et.att.f, D, dX, D, rowsE, eb.attn.out, d_att, D, 0.f, true, &et.att.p, fo.dYp_in ? &fo : nullptr));
+        const bool ap = attn_planes_on(c) && attention_bwd_planes_ok(S, S, D / H) && lin_bwd_all_tc(c, rowsE, eb.attn.in, true);
+        Planes pe;
+        if (ap) TRY(new_planes(c, rowsE, 3 * D, &pe));
         if (!c.dry) {
             AttnArgs a = attn_self(et.qkv, bs, S, D, H, tp.key_pad, att_scale);
             a.lse = et.lse;
-            TRY(launch_attention_bwd(a, d_att, D, dqkv, 3 * D, dqkv + D, dqkv + 2 * D, 3 * D, 3 * D, c.st));
+            AttnBwdPlanes pl;
+            if (ap) { pl.q = pe; pl.k = plane_cols(pe, D); pl.v = plane_cols(pe, 2 * D); }
+            TRY(launch_attention_bwd(a, d_att, D, ap ? nullptr : dqkv, 3 * D, ap ? nullptr : dqkv + D, ap ? nullptr : dqkv + 2 * D, 3 * D, 3 * D,
+                                     c.st, pl));
         }
-        TRY(lin_bwd(c, et.t1.f, D, dqkv, 3 * D, rowsE, eb.attn.in, d_t1, D, 0.f, true, &et.t1.p));
-        TRY(ln_bwd(c, et.ln1, eb.n1, d_t1, nullptr, dX, 1));
+        LinBwdFuse fei;
+        if (ap) fei.dYp_in = &pe;
+        TRY(lin_bwd(c, et.t1.f, D, dqkv, 3 * D, rowsE, eb.attn.in, d_t1, D, 0.f, true, &et.t1.p, ap ? &fei : nullptr));
+        TRY(ln_bwd(c, et.ln1, eb.n1, d_t1, nullptr, dX, 1, &dXp, rowsE));
     }
 
     // ---------------- tokens = [agent tokens ; map tokens] + pos_emb
@@ -410,7 +476,8 @@ int rift_b200_engine::backward_impl(const rift_b200_batch& bt, const float* dlog
                 ALLOC(dx, float, (size_t)rows * d);
                 TRY(lin_bwd(c, nt.colL[i].f, 3 * d, dlat[i], D, rows, m.hist.lateral[i], d_colL, 3 * d, 0.f, true, &nt.colL[i].p));
                 if (!c.dry) TRY(launch_col2im_k3(d_colL, NA, L, d, 1, d_o, 0, c.st));
-                TRY(ln_bwd(c, nt.ln_lev[i], m.hist.norms[i], d_o, nullptr, dx, 0));
+                Planes dxp;                          // planes of dx (valid only while no other kernel has added into dx)
+                TRY(ln_bwd(c, nt.ln_lev[i], m.hist.norms[i], d_o, nullptr, dx, 0, lv.has_down ? nullptr : &dxp, rows));
                 if (lv.has_down) {
                     const int Ln = Ls[i + 1];
                     ALLOC(d_xd, float, (size_t)NA * Ln * 2 * d);
@@ -422,20 +489,28 @@ int rift_b200_engine::backward_impl(const rift_b200_batch& bt, const float* dlog
                 for (int j = 1; j >= 0; --j) {
                     const NatBlockP& nb = lv.blocks[j];
                     const NatBlockTape& bt_ = nt.blocks[i * 2 + j];
-                    TRY(mlp_tail_bwd(c, rows, d, 3 * d, bt_.hm, bt_.hpre, ACT_GELU, bt_.t2, bt_.ln2, nb.n2, nb.fc1, nb.fc2, dx));
+                    TRY(mlp_tail_bwd(c, rows, d, 3 * d, bt_.hm, bt_.hpre, ACT_GELU, bt_.t2, bt_.ln2, nb.n2, nb.fc1, nb.fc2, dx, &dxp));
                     ALLOC(d_att, float, (size_t)rows * d);
                     ALLOC(dqkv, float, (size_t)rows * 3 * d);
                     ALLOC(d_t1, float, (size_t)rows * d);
                     const int nrel = 2 * lv.ksize - 1;
                     ALLOC(drpb, float, (size_t)NA * lv.heads * nrel);
-                    TRY(lin_bwd(c, bt_.att.f, d, dx, d, rows, nb.proj, d_att, d, 0.f, true, &bt_.att.p));
+                    LinBwdFuse fp;
+                    if (dxp.on() && lin_bwd_all_tc(c, rows, nb.proj, true)) fp.dYp_in = &dxp;
+                    TRY(lin_bwd(c, bt_.att.f, d, dx, d, rows, nb.proj, d_att, d, 0.f, true, &bt_.att.p, fp.dYp_in ? &fp : nullptr));
+                    const bool ap = attn_planes_on(c) && nat_attention_bwd_planes_ok(L, lv.ksize) && ((3 * d) % 64) == 0 &&
+                                    lin_bwd_all_tc(c, rows, nb.qkv, true);
+                    Planes pn;
+                    if (ap) TRY(new_planes(c, rows, 3 * d, &pn));
                     if (!c.dry) {
-                        TRY(launch_nat_attention_bwd(bt_.qkv, d_att, NA, L, lv.heads, d / lv.heads, lv.ksize, nb.rpb.p, dqkv,
-                                                     nb.rpb.train ? drpb : nullptr, c.st));
+                        TRY(launch_nat_attention_bwd(bt_.qkv, d_att, NA, L, lv.heads, d / lv.heads, lv.ksize, nb.rpb.p, ap ? nullptr : dqkv,
+                                                     nb.rpb.train ? drpb : nullptr, c.st, pn));
                         if (nb.rpb.train) TRY(launch_colsum(drpb, lv.heads * nrel, NA, lv.heads * nrel, nb.rpb.d, 1, esc, c.st));
                     }
-                    TRY(lin_bwd(c, bt_.t1.f, d, dqkv, 3 * d, rows, nb.qkv, d_t1, d, 0.f, true, &bt_.t1.p));
-                    TRY(ln_bwd(c, bt_.ln1, nb.n1, d_t1, nullptr, dx, 1));
+                    LinBwdFuse fn;
+                    if (ap) fn.dYp_in = &pn;
+                    TRY(lin_bwd(c, bt_.t1.f, d, dqkv, 3 * d, rows, nb.qkv, d_t1, d, 0.f, true, &bt_.t1.p, ap ? &fn : nullptr));
+                    TRY(ln_bwd(c, bt_.ln1, nb.n1, d_t1, nullptr, dx, 1, &dxp, rows));
                 }
                 dxn = dx;
             }

@@ -405,14 +405,53 @@ inline int lin_bwd(Ctx& c, const float* X, long long ldx, const float* dY, long 
     return 0;
 }
 // LayerNorm backward: dx (=|+=) ... ; parameter gradients accumulate
-inline int ln_bwd(Ctx& c, const LNSave& s, const Norm& n, const float* dy, const float* y_relu, float* dx, int accumulate) {
+// dx_planes (optional, tensor-core backward only): the updated dx also leaves as split-bf16 planes for the GEMM that takes
+// it as dY next (LinBwdFuse::dYp_in) - the standalone pack between two sub-blocks disappears; left off() when the shape
+// does not allow it, and the consumer packs as before.  zero_flag: dx rows to clear (replaces a zero_rows launch).
+// RIFT_B200_FUSE_LN_PLANES=0 switches both off.
+inline bool ln_bwd_fuse_on() {
+    static const bool on = [] { const char* e = getenv("RIFT_B200_FUSE_LN_PLANES"); return !(e && atoi(e) == 0); }();
+    return on;
+}
+// planes [rows, tc_pitch(N)] that a backward kernel fills directly (attention backward -> in-projection's dY)
+inline int new_planes(Ctx& c, int rows, int N, Planes* p) {
+    p->Kp = tc_pitch(N);
+    p->hi = c.alloc<uint16_t>((size_t)rows * p->Kp);
+    p->lo = c.alloc<uint16_t>((size_t)rows * p->Kp);
+    if (!p->hi || !p->lo) { set_last_error("workspace too small"); return -1; }
+    return 0;
+}
+inline Planes plane_cols(const Planes& p, int col0) { Planes q = p; q.hi += col0; q.lo += col0; return q; }
+// RIFT_B200_FUSE_ATTN_PLANES=0: attention backward writes fp32 and every in-projection packs its dY again
+inline bool attn_planes_on(const Ctx& c) {
+    static const bool on = [] { const char* e = getenv("RIFT_B200_FUSE_ATTN_PLANES"); return !(e && atoi(e) == 0); }();
+    return on && c.tc_bwd;
+}
+inline int ln_bwd(Ctx& c, const LNSave& s, const Norm& n, const float* dy, const float* y_relu, float* dx, int accumulate,
+                  Planes* dx_planes = nullptr, int plane_rows = 0, const uint8_t* zero_flag = nullptr, int zero_div = 1) {
     ALLOC(sc, float, (size_t)layernorm_bwd_scratch_floats(n.C));
+    const bool fusable = ln_bwd_fuse_on() && c.tc_bwd && (n.C % 64) == 0 && dx != nullptr;
+    Planes out;
+    if (dx_planes) *dx_planes = Planes();
+    if (dx_planes && fusable) {                          // (plane_rows: the dry pass has no tape to read the row count from)
+        out.Kp = n.C;
+        out.hi = c.alloc<uint16_t>((size_t)plane_rows * out.Kp);
+        out.lo = c.alloc<uint16_t>((size_t)plane_rows * out.Kp);
+        if (!out.hi || !out.lo) { set_last_error("workspace too small"); return -1; }
+        *dx_planes = out;
+    }
     if (c.dry) return 0;
+    if (out.on() && plane_rows != s.rows) { set_last_error("internal: ln_bwd plane rows"); return -1; }
     const bool pg = n.train && n.dg;
     SideStream fin;
     if (pg && c.side) { fin.st = c.side; fin.ev = c.next_event(); }       // dgamma / dbeta reduction off the main chain
+    if (zero_flag && !fusable) {                         // generic shapes: the separate kernel, after the update
+        TRY(launch_layernorm_bwd(s.x, n.C, dy, n.C, s.rows, n.C, n.g, s.mean, s.rstd, y_relu, n.C, dx, n.C, accumulate,
+                                 pg ? n.dg : nullptr, pg ? n.db : nullptr, sc, c.st, fin));
+        return launch_zero_rows(dx, zero_flag, zero_div, s.rows, n.C, c.st);
+    }
     return launch_layernorm_bwd(s.x, n.C, dy, n.C, s.rows, n.C, n.g, s.mean, s.rstd, y_relu, n.C, dx, n.C, accumulate,
-                                pg ? n.dg : nullptr, pg ? n.db : nullptr, sc, c.st, fin);
+                                pg ? n.dg : nullptr, pg ? n.db : nullptr, sc, c.st, fin, out, zero_flag, zero_div);
 }
 
 }  // namespace rift

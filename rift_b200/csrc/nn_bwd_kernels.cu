@@ -144,7 +144,8 @@ __host__ __device__ inline size_t attn_bwd2_smem_floats(int Sq, int Sk) {
 template <int G>
 __global__ void __launch_bounds__(512)
 attention_bwd2_kernel(AttnArgs a, const float* __restrict__ d_o, long long lddo, float* __restrict__ dq, long long lddq,
-                      float* __restrict__ dk, float* __restrict__ dv, long long lddk, long long lddv, int PB, int tpp) {
+                      float* __restrict__ dk, float* __restrict__ dv, long long lddk, long long lddv, int PB, int tpp, Planes pq, Planes pk,
+                      Planes pv) {
     pdl_grid_sync();
     constexpr int HD = 32, CPL = HD / G;
     extern __shared__ __align__(16) float sm[];
@@ -236,11 +237,19 @@ attention_bwd2_kernel(AttnArgs a, const float* __restrict__ d_o, long long lddo,
             }
         }
         const long long dr = a.o_custom ? (orow0 + (long long)i * oseq) : (qrow0 + (long long)i * a.q_seq);
-        float* dst = dq + dr * lddq + h * HD + c0;
+        // the gradients leave as fp32 and / or directly as the split-bf16 planes the in-projection's backward GEMMs read
+        if (dq) {
+            float* dst = dq + dr * lddq + h * HD + c0;
 #pragma unroll
-        for (int d = 0; d < CPL; d += 4)
-            *reinterpret_cast<float4*>(dst + d) =
-                make_float4(acc[d] * a.scale, acc[d + 1] * a.scale, acc[d + 2] * a.scale, acc[d + 3] * a.scale);
+            for (int d = 0; d < CPL; d += 4)
+                *reinterpret_cast<float4*>(dst + d) =
+                    make_float4(acc[d] * a.scale, acc[d + 1] * a.scale, acc[d + 2] * a.scale, acc[d + 3] * a.scale);
+        }
+        if (pq.on()) {
+#pragma unroll
+            for (int d = 0; d < CPL; d += 4)
+                split4_store(pq, dr, h * HD + c0 + d, acc[d] * a.scale, acc[d + 1] * a.scale, acc[d + 2] * a.scale, acc[d + 3] * a.scale);
+        }
     }
     __syncthreads();
     // ---- phase B: lane group = key j, lane = channel slice; no reductions
@@ -263,19 +272,39 @@ attention_bwd2_kernel(AttnArgs a, const float* __restrict__ d_o, long long lddo,
             }
         }
         const long long r = krow0 + (long long)j * a.k_seq;
-        float* dkp = dk + r * lddk + h * HD + c0;
-        float* dvp = dv + r * lddv + h * HD + c0;
+        if (dk) {
+            float* dkp = dk + r * lddk + h * HD + c0;
+            float* dvp = dv + r * lddv + h * HD + c0;
 #pragma unroll
-        for (int d = 0; d < CPL; d += 4) {
-            *reinterpret_cast<float4*>(dkp + d) = make_float4(ak[d], ak[d + 1], ak[d + 2], ak[d + 3]);
-            *reinterpret_cast<float4*>(dvp + d) = make_float4(av[d], av[d + 1], av[d + 2], av[d + 3]);
+            for (int d = 0; d < CPL; d += 4) {
+                *reinterpret_cast<float4*>(dkp + d) = make_float4(ak[d], ak[d + 1], ak[d + 2], ak[d + 3]);
+                *reinterpret_cast<float4*>(dvp + d) = make_float4(av[d], av[d + 1], av[d + 2], av[d + 3]);
+            }
+        }
+        if (pk.on()) {
+#pragma unroll
+            for (int d = 0; d < CPL; d += 4) {
+                split4_store(pk, r, h * HD + c0 + d, ak[d], ak[d + 1], ak[d + 2], ak[d + 3]);
+                split4_store(pv, r, h * HD + c0 + d, av[d], av[d + 1], av[d + 2], av[d + 3]);
+            }
         }
     }
 }
 
+// shape-only: will launch_attention_bwd take the kernel above (the one that can write planes)?
+bool attention_bwd_planes_ok(int Sq, int Sk, int hd) {
+    static const bool legacy = getenv("RIFT_B200_ATTN_BWD_LEGACY") != nullptr;
+    const int smax = max(Sq, Sk);
+    return hd == 32 && !legacy && 4 * smax <= 512 && attn_bwd2_smem_floats(Sq, Sk) * sizeof(float) <= 200 * 1024;
+}
+
 int launch_attention_bwd(const AttnArgs& a, const float* d_o, long long lddo, float* dq, long long lddq, float* dk,
-                         float* dv, long long lddk, long long lddv, cudaStream_t st) {
+                         float* dv, long long lddk, long long lddv, cudaStream_t st, const AttnBwdPlanes& pl) {
     if (a.B <= 0 || a.Sq <= 0) return 0;
+    const bool planes = pl.q.on() || pl.k.on() || pl.v.on();
+    RIFT_REQUIRE(pl.k.on() == pl.v.on(), "attention_bwd: dK and dV planes go together");
+    RIFT_REQUIRE((dq != nullptr || pl.q.on()) && (dk != nullptr || pl.k.on()) && ((dk != nullptr) == (dv != nullptr)),
+                 "attention_bwd: every gradient needs an fp32 or a plane destination");
     RIFT_REQUIRE(a.hd == 32 || a.hd == 64, "attention_bwd: head_dim must be 32 or 64");
     RIFT_REQUIRE(a.lse != nullptr, "attention_bwd: forward must have saved the log-sum-exp");
     {
@@ -298,11 +327,12 @@ int launch_attention_bwd(const AttnArgs& a, const float* d_o, long long lddo, fl
                 attr2 = true;
             }
             launch_k(attention_bwd2_kernel<G>, (unsigned)((nprob + PB - 1) / PB), PB * tpp, PB * per, st, a, d_o, lddo, dq, lddq, dk, dv, lddk,
-                                                                                                 lddv, PB, tpp);
+                                                                                                 lddv, PB, tpp, pl.q, pl.k, pl.v);
             RIFT_LAUNCH_OK();
             return 0;
         }
     }
+    RIFT_REQUIRE(!planes, "attention_bwd: plane outputs need the vector kernel (see attention_bwd_planes_ok)");
     const size_t smem = ((size_t)2 * a.Sq * a.hd + (size_t)2 * a.Sk * a.hd + 2 * a.Sq) * sizeof(float);
     RIFT_REQUIRE(smem <= 200 * 1024, "attention_bwd: sequence too long for the shared-memory kernel");
     static bool attr = false;
@@ -407,7 +437,7 @@ nat_attention_bwd_kernel(const float* __restrict__ qkv, const float* __restrict_
 template <int L, int KS>
 __global__ void __launch_bounds__(128)
 nat_attention_bwd_reg_kernel(const float* __restrict__ qkv, const float* __restrict__ d_out, int n_seq, int heads, int hd,
-                             const float* __restrict__ rpb, float* __restrict__ dqkv, float* __restrict__ drpb_partial) {
+                             const float* __restrict__ rpb, float* __restrict__ dqkv, float* __restrict__ drpb_partial, Planes dp_out) {
     pdl_grid_sync();
     const int lane = threadIdx.x & 31;
     const int warp = blockIdx.x * 4 + (threadIdx.x >> 5);
@@ -416,7 +446,7 @@ nat_attention_bwd_reg_kernel(const float* __restrict__ qkv, const float* __restr
     const int dim = heads * hd;
     const float scale = rsqrtf((float)hd);
     const float* base = qkv + (long long)n * L * 3 * dim + h * hd;
-    float* dbase = dqkv + (long long)n * L * 3 * dim + h * hd;
+    float* dbase = dqkv ? dqkv + (long long)n * L * 3 * dim + h * hd : nullptr;
     const bool on = lane < hd;
     float q[L], k[L], v[L], go[L], dk[L], dv[L], rb[2 * KS - 1], drpb[2 * KS - 1];
 #pragma unroll
@@ -456,13 +486,21 @@ nat_attention_bwd_reg_kernel(const float* __restrict__ qkv, const float* __restr
             dv[start + kk] += p[kk] * go[i];
             drpb[start + kk - i + KS - 1] += ds;
         }
-        if (on) dbase[(long long)i * 3 * dim + lane] = dqv * scale;
+        if (on && dbase) dbase[(long long)i * 3 * dim + lane] = dqv * scale;
+        if (on && dp_out.on()) split_store(dp_out, (long long)n * L + i, h * hd + lane, dqv * scale);
     }
-    if (on) {
+    if (on && dbase) {
 #pragma unroll
         for (int j = 0; j < L; ++j) {
             dbase[(long long)j * 3 * dim + dim + lane] = dk[j];
             dbase[(long long)j * 3 * dim + 2 * dim + lane] = dv[j];
+        }
+    }
+    if (on && dp_out.on()) {               // the qkv projection's dY directly as split-bf16 planes [n_seq * L, 3 dim]
+#pragma unroll
+        for (int j = 0; j < L; ++j) {
+            split_store(dp_out, (long long)n * L + j, dim + h * hd + lane, dk[j]);
+            split_store(dp_out, (long long)n * L + j, 2 * dim + h * hd + lane, dv[j]);
         }
     }
     if (drpb_partial && lane == 0) {
@@ -471,14 +509,19 @@ nat_attention_bwd_reg_kernel(const float* __restrict__ qkv, const float* __restr
     }
 }
 
+bool nat_attention_bwd_planes_ok(int L, int ksize) { return (L == 20 && ksize == 3) || (L == 10 && ksize == 3) || (L == 5 && ksize == 5); }
+
 int launch_nat_attention_bwd(const float* qkv, const float* d_out, int n_seq, int L, int heads, int hd, int ksize,
-                             const float* rpb, float* dqkv, float* drpb_partial, cudaStream_t st) {
+                             const float* rpb, float* dqkv, float* drpb_partial, cudaStream_t st, Planes dqkv_planes) {
     if (n_seq <= 0) return 0;
+    RIFT_REQUIRE(dqkv != nullptr || dqkv_planes.on(), "nat_attention_bwd: no destination");
+    RIFT_REQUIRE(!dqkv_planes.on() || (nat_attention_bwd_planes_ok(L, ksize) && dqkv_planes.Kp == 3 * heads * hd),
+                 "nat_attention_bwd: plane output needs the register kernel and pitch 3 * dim");
     RIFT_REQUIRE(hd <= 32 && ksize <= NATB_MAXK && L >= ksize && L <= NATB_MAXL, "nat_attention_bwd: unsupported shape");
 #define RIFT_NATB_REG(LL, KK)                                                                                               \
     if (L == LL && ksize == KK) {                                                                                           \
         launch_k(nat_attention_bwd_reg_kernel<LL, KK>, cdiv((long long)n_seq * heads, 4), 128, 0, st, qkv, d_out, n_seq,    \
-                 heads, hd, rpb, dqkv, drpb_partial);                                                                       \
+                 heads, hd, rpb, dqkv, drpb_partial, dqkv_planes);                                                          \
         RIFT_LAUNCH_OK();                                                                                                   \
         return 0;                                                                                                           \
     }

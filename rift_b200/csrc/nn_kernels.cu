@@ -261,7 +261,7 @@ layernorm_bwd4_kernel(const float* __restrict__ x, long long ldx, const float* _
                       const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
                       const float* __restrict__ y_relu, long long ldy, float* __restrict__ dx, long long lddx,
                       int dx_accumulate, float* __restrict__ partial /*[grid][2][C]*/, float* __restrict__ dgamma_atomic,
-                      float* __restrict__ dbeta_atomic) {
+                      float* __restrict__ dbeta_atomic, Planes dxp, const uint8_t* __restrict__ zero_flag, int zero_div) {
     pdl_grid_sync();
     extern __shared__ float sm[];      // [8 warps][2][C]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -311,7 +311,21 @@ layernorm_bwd4_kernel(const float* __restrict__ x, long long ldx, const float* _
                     v.z = rs * (d[i].z * gm[i].z - s1 - xh[i].z * s2); v.w = rs * (d[i].w * gm[i].w - s1 - xh[i].w * s2);
                     float4* o = reinterpret_cast<float4*>(dx + (long long)row * lddx) + c4;
                     if (dx_accumulate) { const float4 t = *o; v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
+                    // rows whose forward output was overwritten with zero pass no gradient on (decoder: padded reference lines)
+                    if (zero_flag && zero_flag[row / zero_div]) v = make_float4(0.f, 0.f, 0.f, 0.f);
                     *o = v;
+                    if (dxp.on()) {              // the updated residual-stream gradient also leaves as split-bf16 planes (next GEMM's dY)
+                        const __nv_bfloat16 h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y), h2 = __float2bfloat16_rn(v.z),
+                                            h3 = __float2bfloat16_rn(v.w);
+                        const __nv_bfloat162 a = __halves2bfloat162(h0, h1), b = __halves2bfloat162(h2, h3);
+                        const __nv_bfloat162 cc = __floats2bfloat162_rn(v.x - __bfloat162float(h0), v.y - __bfloat162float(h1));
+                        const __nv_bfloat162 dd = __floats2bfloat162_rn(v.z - __bfloat162float(h2), v.w - __bfloat162float(h3));
+                        uint2 uh, ul;
+                        uh.x = *reinterpret_cast<const uint32_t*>(&a); uh.y = *reinterpret_cast<const uint32_t*>(&b);
+                        ul.x = *reinterpret_cast<const uint32_t*>(&cc); ul.y = *reinterpret_cast<const uint32_t*>(&dd);
+                        *reinterpret_cast<uint2*>(dxp.hi + (long long)row * dxp.Kp + 4 * c4) = uh;
+                        *reinterpret_cast<uint2*>(dxp.lo + (long long)row * dxp.Kp + 4 * c4) = ul;
+                    }
                 }
             }
         }
@@ -341,8 +355,17 @@ layernorm_bwd4_kernel(const float* __restrict__ x, long long ldx, const float* _
 int launch_layernorm_bwd(const float* x, long long ldx, const float* dy, long long lddy, int rows, int C,
                          const float* gamma, const float* mean, const float* rstd, const float* y_for_relu, long long ldy,
                          float* dx, long long lddx, int dx_accumulate, float* dgamma, float* dbeta, float* scratch,
-                         cudaStream_t st, SideStream fin) {
+                         cudaStream_t st, SideStream fin, Planes dxp, const uint8_t* zero_flag, int zero_div) {
     if (rows <= 0) return 0;
+    {
+        auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+        const bool vec = (C & 63) == 0 && (ldx & 3) == 0 && (lddy & 3) == 0 && (ldy & 3) == 0 && (lddx & 3) == 0 && al16(x) && al16(dy) &&
+                         al16(y_for_relu) && al16(dx) && al16(gamma);
+        RIFT_REQUIRE(!(dxp.on() || zero_flag) || vec,
+                     "layernorm_bwd: plane output / row zeroing need the vector form (C % 64 == 0, 16-byte aligned rows)");
+    }
+    RIFT_REQUIRE(!dxp.on() || (dxp.Kp == C && dx != nullptr), "layernorm_bwd: plane pitch must equal C");
+    if (zero_div < 1) zero_div = 1;
     RIFT_REQUIRE(C <= LNB_MAXC, "layernorm_bwd: C too large");
     RIFT_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "layernorm_bwd: dgamma/dbeta go together");
     RIFT_REQUIRE(dgamma == nullptr || scratch != nullptr, "layernorm_bwd: scratch required for parameter gradients");
@@ -362,7 +385,7 @@ int launch_layernorm_bwd(const float* x, long long ldx, const float* dy, long lo
             const int nv = cdiv(C, 128);
 #define RIFT_LNB4(NV)                                                                                                       \
     launch_k(layernorm_bwd4_kernel<NV>, nb4, 256, smem4, st, x, ldx, dy, lddy, rows, C, gamma, mean, rstd, y_for_relu, ldy, dx, \
-                                                       lddx, dx_accumulate, part, dga, dba)
+                                                       lddx, dx_accumulate, part, dga, dba, dxp, zero_flag, zero_div)
             static bool attr4 = false;
             if (!attr4) {
                 RIFT_CUDA_OK(cudaFuncSetAttribute(layernorm_bwd4_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * LNB_MAXC * 4));

@@ -83,7 +83,8 @@ int launch_layernorm(const float* x, long long ldx, int rows, int C, const float
 int launch_layernorm_bwd(const float* x, long long ldx, const float* dy, long long lddy, int rows, int C,
                          const float* gamma, const float* mean, const float* rstd, const float* y_for_relu, long long ldy,
                          float* dx, long long lddx, int dx_accumulate, float* dgamma, float* dbeta, float* scratch,
-                         cudaStream_t st, SideStream fin = SideStream());
+                         cudaStream_t st, SideStream fin = SideStream(), Planes dx_planes = Planes(), const uint8_t* zero_flag = nullptr,
+                         int zero_div = 1);      // dx_planes: dx also as split-bf16 planes (pitch C, C % 64 == 0); dx[row] = 0 where zero_flag[row / zero_div]
 int layernorm_bwd_scratch_floats(int C);
 
 struct AttnArgs {
@@ -103,13 +104,18 @@ struct AttnArgs {
     Planes o_planes;                                 // optional split-bf16 copy of the output (o may then be null)
 };
 int launch_attention(const AttnArgs& a, cudaStream_t st);
+// optional plane destinations of dQ / dK / dV (pointers already offset to the gradient's first column inside the
+// in-projection's dY matrix; an fp32 destination may then be null).  Vector kernel only: attention_bwd_planes_ok
+struct AttnBwdPlanes { Planes q, k, v; };
+bool attention_bwd_planes_ok(int Sq, int Sk, int hd);
 int launch_attention_bwd(const AttnArgs& a, const float* d_o, long long lddo, float* dq, long long lddq, float* dk,
-                         float* dv, long long lddk, long long lddv, cudaStream_t st);
+                         float* dv, long long lddk, long long lddv, cudaStream_t st, const AttnBwdPlanes& pl = AttnBwdPlanes());
 
 int launch_nat_attention(const float* qkv, int n_seq, int L, int heads, int hd, int ksize, const float* rpb, float* out,
                          cudaStream_t st, Planes op = Planes());
 int launch_nat_attention_bwd(const float* qkv, const float* d_out, int n_seq, int L, int heads, int hd, int ksize,
-                             const float* rpb, float* dqkv, float* drpb_partial, cudaStream_t st);
+                             const float* rpb, float* dqkv, float* drpb_partial, cudaStream_t st, Planes dqkv_planes = Planes());     // planes: dqkv may be null
+bool nat_attention_bwd_planes_ok(int L, int ksize);
 
 int launch_im2col_k3(const float* x, int n_seq, int L, int C, int stride, float* out, cudaStream_t st,
                      Planes op = Planes());   // -> (n_seq*Lout, C*3)
