@@ -17,9 +17,9 @@ namespace rift {
     ALLOC(var, float, n);                                                                              \
     if (!c.dry) RIFT_CUDA_OK(cudaMemsetAsync(var, 0, (size_t)(n) * sizeof(float), c.st));
 
-static int act_bwd(Ctx& c, const float* ref, float* dy, long long n, int act) {
+static int act_bwd(Ctx& c, const float* ref, float* dy, long long n, int act, Planes flat_planes = Planes()) {
     if (c.dry) return 0;
-    return launch_act_bwd(ref, dy, n, act, c.st);
+    return launch_act_bwd(ref, dy, n, act, c.st, flat_planes);
 }
 static int add_into(Ctx& c, float* dst, const float* src, long long n) {
     if (c.dry || !dst) return 0;
@@ -131,8 +131,12 @@ static int mlp_tail_bwd(Ctx& c, int rows, int D, int Hd, const Act& hm, const fl
         ALLOC(d_hm, float, (size_t)rows * Hd);
         LinBwdFuse f2; f2.dYp_in = &dY_in;
         TRY(lin_bwd(c, hm.f, Hd, dX, D, rows, fc2, d_hm, Hd, 0.f, true, &hm.p, dY_in.on() ? &f2 : nullptr));
-        TRY(act_bwd(c, act_ref, d_hm, (long long)rows * Hd, act));
-        TRY(lin_bwd(c, t2.f, D, d_hm, Hd, rows, fc1, d_t2, D, 0.f, true, &t2.p));
+        // the activation backward writes fc1's dY as split-bf16 planes (and no fp32) when fc1's products take the tensor cores
+        Planes dhp;
+        if (attn_planes_on(c) && (Hd % 64) == 0 && lin_bwd_all_tc(c, rows, fc1, true)) TRY(new_planes(c, rows, Hd, &dhp));
+        TRY(act_bwd(c, act_ref, d_hm, (long long)rows * Hd, act, dhp));
+        LinBwdFuse f1; f1.dYp_in = &dhp;
+        TRY(lin_bwd(c, t2.f, D, d_hm, Hd, rows, fc1, d_t2, D, 0.f, true, &t2.p, dhp.on() ? &f1 : nullptr));
     }
     TRY(ln_bwd(c, ln2, n2, d_t2, nullptr, dX, 1, dXp, rows));
     return 0;

@@ -1411,9 +1411,45 @@ __global__ void act_bwd_kernel(const float* __restrict__ ref, float* __restrict_
         else if (act == ACT_GELU) dy[e] *= gelu_erf_grad(ref[e]);
     }
 }
-int launch_act_bwd(const float* pre_or_post, float* dy, long long n, int act, cudaStream_t st) {
-    if (n <= 0 || act == ACT_NONE) return 0;
-    launch_k(act_bwd_kernel, GRID1D(n, 256), 256, 0, st, pre_or_post, dy, n, act);
+// four elements per thread; with `planes` the product leaves as split-bf16 planes (flat: pitch == row length) INSTEAD of
+// being written back to dy - the consumer is a GEMM that reads planes only
+__global__ void __launch_bounds__(256)
+act_bwd4_kernel(const float4* __restrict__ ref, float4* __restrict__ dy, long long n4, int act, uint2* __restrict__ hi, uint2* __restrict__ lo) {
+    pdl_grid_sync();
+    for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < n4; e += (long long)gridDim.x * 256) {
+        const float4 r = __ldg(ref + e);
+        float4 d = dy[e];
+        if (act == ACT_RELU) {
+            if (!(r.x > 0.f)) d.x = 0.f; if (!(r.y > 0.f)) d.y = 0.f; if (!(r.z > 0.f)) d.z = 0.f; if (!(r.w > 0.f)) d.w = 0.f;
+        } else {
+            d.x *= gelu_erf_grad(r.x); d.y *= gelu_erf_grad(r.y); d.z *= gelu_erf_grad(r.z); d.w *= gelu_erf_grad(r.w);
+        }
+        if (hi) {
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(d.x), h1 = __float2bfloat16_rn(d.y), h2 = __float2bfloat16_rn(d.z), h3 = __float2bfloat16_rn(d.w);
+            const __nv_bfloat162 a = __halves2bfloat162(h0, h1), b = __halves2bfloat162(h2, h3);
+            const __nv_bfloat162 cc = __floats2bfloat162_rn(d.x - __bfloat162float(h0), d.y - __bfloat162float(h1));
+            const __nv_bfloat162 dd = __floats2bfloat162_rn(d.z - __bfloat162float(h2), d.w - __bfloat162float(h3));
+            uint2 uh, ul;
+            uh.x = *reinterpret_cast<const uint32_t*>(&a); uh.y = *reinterpret_cast<const uint32_t*>(&b);
+            ul.x = *reinterpret_cast<const uint32_t*>(&cc); ul.y = *reinterpret_cast<const uint32_t*>(&dd);
+            hi[e] = uh; lo[e] = ul;
+        } else {
+            dy[e] = d;
+        }
+    }
+}
+int launch_act_bwd(const float* pre_or_post, float* dy, long long n, int act, cudaStream_t st, Planes planes) {
+    if (n <= 0) return 0;
+    RIFT_REQUIRE(act == ACT_RELU || act == ACT_GELU || (act == ACT_NONE && !planes.on()), "act_bwd: unknown activation");
+    const bool vec = (n & 3) == 0 && (reinterpret_cast<uintptr_t>(pre_or_post) & 15) == 0 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0;
+    RIFT_REQUIRE(!planes.on() || vec, "act_bwd: plane output needs 16-byte aligned rows of a multiple of 4 elements");
+    if (act == ACT_NONE) return 0;
+    if (vec) {
+        launch_k(act_bwd4_kernel, (int)min((long long)148 * 8, (n / 4 + 255) / 256), 256, 0, st, reinterpret_cast<const float4*>(pre_or_post),
+                 reinterpret_cast<float4*>(dy), n / 4, act, reinterpret_cast<uint2*>(planes.hi), reinterpret_cast<uint2*>(planes.lo));
+    } else {
+        launch_k(act_bwd_kernel, GRID1D(n, 256), 256, 0, st, pre_or_post, dy, n, act);
+    }
     RIFT_LAUNCH_OK();
     return 0;
 }

@@ -171,7 +171,7 @@ int launch_colsum_planes(const Planes& p, int rows, int C, float* out, int accum
 // second stage alone: out[c] (+)= sum over `slabs` partial rows of pitch C
 int launch_colsum_final(const float* partial, int slabs, int C, float* out, int accumulate, cudaStream_t st,
                         SideStream fin = SideStream());
-int launch_act_bwd(const float* pre_or_post, float* dy, long long n, int act, cudaStream_t st);   // in place dy *= act'(.)
+int launch_act_bwd(const float* pre_or_post, float* dy, long long n, int act, cudaStream_t st, Planes flat_planes = Planes());   // dy *= act'(.) in place, or -> planes (pitch == row length) with dy left untouched
 int launch_add_inplace(float* dst, const float* src, long long n, cudaStream_t st);
 int launch_scale_shift_rows_bwd(float* dy, const float* colscale, long long rows, int C, cudaStream_t st);
 int launch_traj_outputs(const float* trajectory, long long n_traj, int T, float* cand, cudaStream_t st);

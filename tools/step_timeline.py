@@ -53,4 +53,31 @@ out = {"steps": args.steps, "wall_span_us_per_step": (t1 - t0) / args.steps, "su
        "any_kernel_busy_us_per_step": busy / args.steps, "kernels_per_step": len(evs) / args.steps,
        "top": [{"kernel": k, "launches_per_step": v[0] / args.steps, "us_per_step": v[1] / args.steps, "avg_us": v[1] / v[0]}
                for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]]}
+# per-stream view and the launch-ordered list of the LAST step, from the chrome trace (kernel events carry their stream id)
+trace_path = os.path.join("gpurun_out", "timeline_trace.json")
+os.makedirs("gpurun_out", exist_ok=True)
+prof.export_chrome_trace(trace_path)
+tr_ev = [e for e in json.load(open(trace_path))["traceEvents"] if e.get("cat") == "kernel"]
+os.remove(trace_path)
+tr_ev.sort(key=lambda e: e["ts"])
+n_last = len(tr_ev) // args.steps
+last = tr_ev[-n_last:]
+base = last[0]["ts"]
+per_stream = collections.defaultdict(lambda: [0, 0.0])
+for e in last:
+    per_stream[e["args"].get("stream", -1)][0] += 1
+    per_stream[e["args"].get("stream", -1)][1] += e["dur"]
+out["last_step_streams"] = {str(k): {"kernels": v[0], "busy_us": v[1]} for k, v in per_stream.items()}
+# concurrency profile of the last step: time spent with n kernels resident
+pts = sorted([(e["ts"], 1) for e in last] + [(e["ts"] + e["dur"], -1) for e in last])
+conc, level, prev = collections.defaultdict(float), 0, pts[0][0]
+for t, d in pts:
+    conc[level] += t - prev
+    prev, level = t, level + d
+out["last_step_concurrency_us"] = {str(k): v for k, v in sorted(conc.items())}
+with open(os.path.join("gpurun_out", "timeline_last_step.csv"), "w") as f:
+    f.write("t_us,dur_us,stream,grid,block,kernel\n")
+    for e in last:
+        a = e["args"]
+        f.write(f"{e['ts'] - base:.1f},{e['dur']:.1f},{a.get('stream', -1)},\"{a.get('grid')}\",\"{a.get('block')}\",\"{e['name'].split('(')[0].replace('void ', '').replace('rift::', '')}\"\n")
 print(json.dumps(out, indent=1))
