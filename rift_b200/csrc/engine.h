@@ -100,6 +100,15 @@ struct Ctx {            // per-call state: stream + bump allocator over the call
         return reinterpret_cast<T*>(base + at);
     }
     bool planes_for(int C) const { return !simt && C >= 32; }
+    // fp32 gradient buffers that the main chain keeps updating in place (residual-stream gradients): kernels moved to
+    // another stream must not read them.  Everything else the backward allocates is written once (bump allocator).
+    const void* inplace_bufs[12] = {}; int n_inplace = 0;
+    void mark_inplace(const void* p) { if (p && n_inplace < 12) inplace_bufs[n_inplace++] = p; }
+    bool updated_inplace(const void* p) const {
+        if (n_inplace >= 12) return true;                 // registry overflow: assume the worst
+        for (int i = 0; i < n_inplace; ++i) if (inplace_bufs[i] == p) return true;
+        return false;
+    }
 };
 
 // ---------------------------------------------------------------- saved activations (forward -> backward)

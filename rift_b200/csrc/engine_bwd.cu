@@ -198,8 +198,11 @@ int rift_b200_engine::backward_impl(const rift_b200_batch& bt, const float* dlog
     // ---------------- cat_x_proj: qf = q Wa^T + (x_ego Wb^T + b)[row / (R*Mo)]
     const Lin ca = slice(m.cat_x_proj, 0, D, 0, D, false), cb = slice(m.cat_x_proj, 0, D, D, D, true);
     ALLOC(dq, float, (size_t)rowsQ * D);            // running gradient of the decoder residual stream
+    c.n_inplace = 0;
+    c.mark_inplace(dq);
     ALLOC(deg, float, (size_t)bs * D);
     ZALLOC(dXn, (size_t)rowsE * D);
+    c.mark_inplace(dXn);
     // dqp: split-bf16 planes of dq whenever its last producer could write them (GEMM epilogue, LayerNorm backward); each
     // consumer below falls back to packing dq itself when they are off()
     Planes dqp;
@@ -349,6 +352,7 @@ int rift_b200_engine::backward_impl(const rift_b200_batch& bt, const float* dlog
 
     // ---------------- scene encoding: final norm <- encoder blocks
     ALLOC(dX, float, (size_t)rowsE * D);
+    c.mark_inplace(dX);
     if (dxn_done) RIFT_CUDA_OK(cudaStreamWaitEvent(c.st, dxn_done, 0));
     Planes dXp;                                      // planes of the encoder stream's gradient, same protocol as dqp
     TRY(ln_bwd(c, tp.ln_final, m.final_norm, dXn, nullptr, dX, 0, &dXp, rowsE));
@@ -478,6 +482,7 @@ int rift_b200_engine::backward_impl(const rift_b200_batch& bt, const float* dlog
                 ALLOC(d_colL, float, (size_t)rows * 3 * d);
                 ALLOC(d_o, float, (size_t)rows * d);
                 ALLOC(dx, float, (size_t)rows * d);
+                c.mark_inplace(dx);
                 TRY(lin_bwd(c, nt.colL[i].f, 3 * d, dlat[i], D, rows, m.hist.lateral[i], d_colL, 3 * d, 0.f, true, &nt.colL[i].p));
                 if (!c.dry) TRY(launch_col2im_k3(d_colL, NA, L, d, 1, d_o, 0, c.st));
                 Planes dxp;                          // planes of dx (valid only while no other kernel has added into dx)

@@ -274,7 +274,9 @@ inline int lin_bwd(Ctx& c, const float* X, long long ldx, const float* dY, long 
     // count padded to 4 (the operand planes are zero there) and stores only the real columns through the reduce
     const int Kpad4 = (L.K + 3) & ~3;
     const bool w_padded = (L.K % 4) != 0 || (L.ldw % 4) != 0;
-    const bool tc_w = tc_on && want_w && gemm_tc_shape_ok(L.N, Kpad4, M) && L.N >= 64 && (Xp && Xp->on() ? Xp->Kp >= Kpad4 : true);
+    // (the weight-gradient product reads activation planes only, so it does not need the layer's W^T planes: first layers
+    // with 16 <= K < 32 - the history encoder's 27-wide im2col - take it too)
+    const bool tc_w = c.tc_bwd && c.tcw && want_w && gemm_tc_shape_ok(L.N, Kpad4, M) && L.N >= 64 && (Xp && Xp->on() ? Xp->Kp >= Kpad4 : true);
     // Parameter gradients go to the side stream: they read only dYp / the saved operand planes (never the fp32 dY, which
     // the main stream may update in place later) and nothing downstream on the main stream depends on them before the
     // final join of backward().  On the tensor-core route the weight-gradient GEMM adds every (tile, split-K part)
@@ -326,6 +328,12 @@ inline int lin_bwd(Ctx& c, const float* X, long long ldx, const float* dY, long 
         if (c.side) { fin.st = c.side; fin.ev = c.next_event(); forked = true; }
         TRY(launch_colsum(dY, lddy, M, L.N, L.db, 1, sc, c.st, fin));
     }
+    // weight-gradient kernels that read the fp32 dY (narrow first layers, shapes the tensor cores do not take) also leave
+    // the main chain, unless dY is one of the buffers the chain updates in place later.  The side stream must then see
+    // everything the main stream has done so far (an earlier fork in this call predates the colsum launches above).
+    static const bool small_side = [] { const char* e = getenv("RIFT_B200_SMALL_WGRAD_SIDE"); return !(e && atoi(e) == 0); }();
+    const bool off_chain = small_side && c.side != nullptr && !c.updated_inplace(dY) && !(fz && fz->dYp_in);
+    if (!tc_w) forked = false;
     if (tc_w) {
         Planes xp;
         if (Xp && Xp->on()) xp = *Xp;
@@ -364,12 +372,20 @@ inline int lin_bwd(Ctx& c, const float* X, long long ldx, const float* dY, long 
     } else if (want_w && L.K <= 32 && L.ldw == L.K && M >= 1024) {
         // narrow first-layer input (raw features / im2col of 9 channels): dedicated kernel instead of the generic SIMT GEMM
         ALLOC(wp, float, (size_t)wgrad_narrow_slabs(M) * L.N * L.K);
-        if (!c.dry) TRY(launch_wgrad_narrow(dY, lddy, X, ldx, M, L.N, L.K, L.dW, wp, c.st));
+        if (!c.dry) {
+            if (off_chain && !forked) { TRY(fork_to(c, c.side)); forked = true; }
+            OnStream on(c, off_chain ? c.side : nullptr);
+            TRY(launch_wgrad_narrow(dY, lddy, X, ldx, M, L.N, L.K, L.dW, wp, c.st));
+        }
     } else if (want_w && L.N == 1 && L.K >= 32 && M >= 1024) {
         // single-output Linear (probability head): dW[1, K] = sum_r dY[r] X[r, :] = the narrow kernel with the roles of
         // dY and X swapped ([K, 1] and [1, K] are the same memory)
         ALLOC(wp, float, (size_t)wgrad_narrow_slabs(M) * L.K);
-        if (!c.dry) TRY(launch_wgrad_narrow(X, ldx, dY, lddy, M, L.K, 1, L.dW, wp, c.st));
+        if (!c.dry) {
+            if (off_chain && !forked) { TRY(fork_to(c, c.side)); forked = true; }
+            OnStream on(c, off_chain ? c.side : nullptr);
+            TRY(launch_wgrad_narrow(X, ldx, dY, lddy, M, L.K, 1, L.dW, wp, c.st));
+        }
     } else if (want_w) {
         const int splits = M >= 2048 ? (M / 512 < 64 ? M / 512 : 64) : 1;
         float* ws = nullptr;
@@ -379,6 +395,8 @@ inline int lin_bwd(Ctx& c, const float* X, long long ldx, const float* dY, long 
         a.B = X; a.sbn = 1; a.sbk = ldx;               // B(n = in feature,  k = row)
         a.C = L.dW; a.ldc = L.ldw; a.M = L.N; a.N = L.K; a.K = M; a.beta = 1.f;
         a.split_k = splits; a.split_ws = ws;
+        if (!c.dry && off_chain && !forked) { TRY(fork_to(c, c.side)); forked = true; }
+        OnStream on(c, (!c.dry && off_chain) ? c.side : nullptr);
         TRY(simt(c, a));
     }
     if (tc_d) {
@@ -443,6 +461,25 @@ inline int ln_bwd(Ctx& c, const LNSave& s, const Norm& n, const float* dy, const
     if (c.dry) return 0;
     if (out.on() && plane_rows != s.rows) { set_last_error("internal: ln_bwd plane rows"); return -1; }
     const bool pg = n.train && n.dg;
+    // The parameter gradients (column sums over all rows, atomics into 2 C addresses) run as a second, dx-less launch of the
+    // same kernel on the side stream: the main chain keeps only the row-wise part.  dy must not be a buffer the chain
+    // updates in place.  Off by default (RIFT_B200_LN_PG_SIDE=1 enables): measured 9.62 vs 9.26 ms per step - the step is
+    // bound by the sum of kernel time over all streams, and the second launch re-reads x and dy.
+    static const bool pg_side = [] { const char* e = getenv("RIFT_B200_LN_PG_SIDE"); return e && atoi(e) != 0; }();
+    if (pg && pg_side && c.side && dx && !c.updated_inplace(dy)) {
+        TRY(fork_to(c, c.side));
+        {
+            OnStream on(c, c.side);
+            TRY(launch_layernorm_bwd(s.x, n.C, dy, n.C, s.rows, n.C, n.g, s.mean, s.rstd, y_relu, n.C, nullptr, n.C, 0, n.dg, n.db, sc, c.st));
+        }
+        if (zero_flag && !fusable) {
+            TRY(launch_layernorm_bwd(s.x, n.C, dy, n.C, s.rows, n.C, n.g, s.mean, s.rstd, y_relu, n.C, dx, n.C, accumulate, nullptr, nullptr,
+                                     sc, c.st));
+            return launch_zero_rows(dx, zero_flag, zero_div, s.rows, n.C, c.st);
+        }
+        return launch_layernorm_bwd(s.x, n.C, dy, n.C, s.rows, n.C, n.g, s.mean, s.rstd, y_relu, n.C, dx, n.C, accumulate, nullptr, nullptr,
+                                    sc, c.st, SideStream(), out, zero_flag, zero_div);
+    }
     SideStream fin;
     if (pg && c.side) { fin.st = c.side; fin.ev = c.next_event(); }       // dgamma / dbeta reduction off the main chain
     if (zero_flag && !fusable) {                         // generic shapes: the separate kernel, after the update

@@ -537,23 +537,39 @@ int launch_nat_attention_bwd(const float* qkv, const float* d_out, int n_seq, in
 // gather / scatter style backward kernels
 // =====================================================================================
 // max-pool: the gradient of a pooled value goes to the arg-max point (nowhere when the winner was a padded zero)
-__global__ void masked_maxpool_bwd_kernel(const float* __restrict__ dout, const int* __restrict__ argmax, int groups, int n,
-                                          int C, float* __restrict__ dx, int accumulate) {
+template <int VEC>
+__global__ void __launch_bounds__(256)
+masked_maxpool_bwd_kernel(const float* __restrict__ dout, const int* __restrict__ argmax, int groups, int n, int C,
+                          float* __restrict__ dx, int accumulate) {
     pdl_grid_sync();
-    FOR_GRID(e, (long long)groups * n * C) {
-        const int c = (int)(e % C);
-        const long long r = e / C;
+    const int CV = C / VEC;
+    FOR_GRID(e, (long long)groups * n * CV) {
+        const int c = (int)(e % CV) * VEC;
+        const long long r = e / CV;
         const int p = (int)(r % n);
         const long long g = r / n;
-        const float v = (argmax[g * C + c] == p) ? dout[g * C + c] : 0.f;
-        dx[e] = accumulate ? dx[e] + v : v;
+        if (VEC == 4) {
+            const int4 am = *reinterpret_cast<const int4*>(argmax + g * C + c);
+            const float4 d = *reinterpret_cast<const float4*>(dout + g * C + c);
+            float4 v = make_float4(am.x == p ? d.x : 0.f, am.y == p ? d.y : 0.f, am.z == p ? d.z : 0.f, am.w == p ? d.w : 0.f);
+            float4* o = reinterpret_cast<float4*>(dx + r * C + c);
+            if (accumulate) { const float4 t = *o; v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
+            *o = v;
+        } else {
+            const float v = (argmax[g * C + c] == p) ? dout[g * C + c] : 0.f;
+            dx[r * C + c] = accumulate ? dx[r * C + c] + v : v;
+        }
     }
 }
 int launch_masked_maxpool_bwd(const float* dout, const int* argmax, int groups, int n, int C, float* dx, int accumulate,
                               cudaStream_t st) {
     const long long total = (long long)groups * n * C;
     if (total <= 0) return 0;
-    launch_k(masked_maxpool_bwd_kernel, GRID1D(total, 256), 256, 0, st, dout, argmax, groups, n, C, dx, accumulate);
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    if ((C & 3) == 0 && al16(dout) && al16(argmax) && al16(dx))
+        launch_k(masked_maxpool_bwd_kernel<4>, GRID1D(total / 4, 256), 256, 0, st, dout, argmax, groups, n, C, dx, accumulate);
+    else
+        launch_k(masked_maxpool_bwd_kernel<1>, GRID1D(total, 256), 256, 0, st, dout, argmax, groups, n, C, dx, accumulate);
     RIFT_LAUNCH_OK();
     return 0;
 }
@@ -608,17 +624,26 @@ int launch_col2im_k3_last(const float* dcols, int n_seq, int L, int C, float* dx
 }
 
 // transpose of fpn_upsample_add: dsrc[n, i, c] += sum_j w(j -> i) ddst[n, j, c]
-__global__ void fpn_upsample_add_bwd_kernel(const float* __restrict__ ddst, float* __restrict__ dsrc, int n_seq, int Ld, int Ls,
-                                            int C) {
+// Only destination positions whose source coordinate sp(j) lies within (i - 1, i + 1) can carry weight: the j loop covers that
+// window (plus one position of slack on both sides; the weight test inside is the exact one, so skipped terms are exact zeros
+// and the sum has the same terms in the same order as the full loop).  VEC = 4 channels per thread.
+template <int VEC>
+__global__ void __launch_bounds__(256)
+fpn_upsample_add_bwd_kernel(const float* __restrict__ ddst, float* __restrict__ dsrc, int n_seq, int Ld, int Ls, int C) {
     pdl_grid_sync();
     const float rscale = (float)Ls / (float)Ld;
-    FOR_GRID(e, (long long)n_seq * Ls * C) {
-        const int c = (int)(e % C);
-        const long long r = e / C;
+    const int CV = C / VEC;
+    FOR_GRID(e, (long long)n_seq * Ls * CV) {
+        const int c = (int)(e % CV) * VEC;
+        const long long r = e / CV;
         const int i = (int)(r % Ls);
         const long long n = r / Ls;
-        float a = 0.f;
-        for (int j = 0; j < Ld; ++j) {
+        const int j_lo = (i == 0) ? 0 : max(0, (int)floorf(((float)i - 0.5f) / rscale - 0.5f) - 1);
+        const int j_hi = (i == Ls - 1) ? Ld - 1 : min(Ld - 1, (int)ceilf(((float)i + 1.5f) / rscale - 0.5f) + 1);
+        float a[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) a[v] = 0.f;
+        for (int j = j_lo; j <= j_hi; ++j) {
             float sp = ((float)j + 0.5f) * rscale - 0.5f;
             sp = fmaxf(sp, 0.f);
             const int i0 = min((int)sp, Ls - 1);
@@ -627,15 +652,32 @@ __global__ void fpn_upsample_add_bwd_kernel(const float* __restrict__ ddst, floa
             float w = 0.f;
             if (i0 == i) w += w0;
             if (i1 == i) w += w1;
-            if (w != 0.f) a += w * ddst[(n * Ld + j) * C + c];
+            if (w != 0.f) {
+                const float* p = ddst + (n * Ld + j) * C + c;
+                if (VEC == 4) {
+                    const float4 x = *reinterpret_cast<const float4*>(p);
+                    a[0] += w * x.x; a[1 % VEC] += w * x.y; a[2 % VEC] += w * x.z; a[3 % VEC] += w * x.w;
+                } else {
+                    a[0] += w * p[0];
+                }
+            }
         }
-        dsrc[e] += a;
+        float* o = dsrc + (n * Ls + i) * C + c;
+        if (VEC == 4) {
+            float4 t = *reinterpret_cast<float4*>(o);
+            t.x += a[0]; t.y += a[1 % VEC]; t.z += a[2 % VEC]; t.w += a[3 % VEC];
+            *reinterpret_cast<float4*>(o) = t;
+        } else {
+            o[0] += a[0];
+        }
     }
 }
 int launch_fpn_upsample_add_bwd(const float* ddst, float* dsrc, int n_seq, int Ld, int Ls, int C, cudaStream_t st) {
     const long long total = (long long)n_seq * Ls * C;
     if (total <= 0) return 0;
-    launch_k(fpn_upsample_add_bwd_kernel, GRID1D(total, 256), 256, 0, st, ddst, dsrc, n_seq, Ld, Ls, C);
+    const bool vec = (C & 3) == 0 && (reinterpret_cast<uintptr_t>(ddst) & 15) == 0 && (reinterpret_cast<uintptr_t>(dsrc) & 15) == 0;
+    if (vec) launch_k(fpn_upsample_add_bwd_kernel<4>, GRID1D(total / 4, 256), 256, 0, st, ddst, dsrc, n_seq, Ld, Ls, C);
+    else launch_k(fpn_upsample_add_bwd_kernel<1>, GRID1D(total, 256), 256, 0, st, ddst, dsrc, n_seq, Ld, Ls, C);
     RIFT_LAUNCH_OK();
     return 0;
 }
@@ -825,10 +867,53 @@ bn_affine_bwd_final_kernel(const float* __restrict__ partial, int nb, int C, flo
         out[c] += s;
     }
 }
+// vector form for C % 4 == 0, C <= 1024: a thread owns one column quad, 1024 / (C / 4) row lanes per block each stream rows
+// with 16-byte loads (four times the bytes in flight of the scalar form); the row lanes are combined in shared memory in a
+// fixed order.  Same partial layout as above.
+__global__ void __launch_bounds__(1024)
+bn_affine_bwd_partial4_kernel(const float* __restrict__ dz, const float* __restrict__ v, long long rows, int C,
+                              const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ partial) {
+    pdl_grid_sync();
+    extern __shared__ float4 sm4[];                        // [lanes][2][C / 4]
+    const int C4 = C >> 2, lanes = 1024 / C4;
+    const int q = threadIdx.x % C4, lane = threadIdx.x / C4;
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f), b = g;
+    if (lane < lanes) {
+        const float4 bt = *reinterpret_cast<const float4*>(beta + 4 * q);
+        for (long long r = (long long)blockIdx.x * lanes + lane; r < rows; r += (long long)gridDim.x * lanes) {
+            const float4 d = *reinterpret_cast<const float4*>(dz + r * C + 4 * q);
+            const float4 x = *reinterpret_cast<const float4*>(v + r * C + 4 * q);
+            g.x = fmaf(d.x, x.x - bt.x, g.x); g.y = fmaf(d.y, x.y - bt.y, g.y); g.z = fmaf(d.z, x.z - bt.z, g.z); g.w = fmaf(d.w, x.w - bt.w, g.w);
+            b.x += d.x; b.y += d.y; b.z += d.z; b.w += d.w;
+        }
+        sm4[(lane * 2 + 0) * C4 + q] = g;
+        sm4[(lane * 2 + 1) * C4 + q] = b;
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * C4) {
+        const int which = threadIdx.x / C4, qq = threadIdx.x % C4;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int l = 0; l < lanes; ++l) { const float4 t = sm4[(l * 2 + which) * C4 + qq]; a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
+        if (which == 0) {
+            const float4 gm = *reinterpret_cast<const float4*>(gamma + 4 * qq);
+            a.x /= gm.x; a.y /= gm.y; a.z /= gm.z; a.w /= gm.w;
+        }
+        *reinterpret_cast<float4*>(partial + ((long long)blockIdx.x * 2 + which) * C + 4 * qq) = a;
+    }
+}
 int launch_bn_affine_bwd(const float* dz, const float* v, long long rows, int C, const float* gamma, const float* beta,
                          float* dgamma, float* dbeta, float* scratch, cudaStream_t st) {
     if (rows <= 0) return 0;
     const int nb = (int)min((long long)148, rows);          // scratch holds 148 x 2 x C partials
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    if ((C & 3) == 0 && C >= 16 && C <= 1024 && al16(dz) && al16(v) && al16(gamma) && al16(beta) && al16(scratch)) {
+        const int lanes = 1024 / (C / 4);
+        launch_k(bn_affine_bwd_partial4_kernel, nb, 1024, (size_t)lanes * 2 * C * sizeof(float), st, dz, v, rows, C, gamma, beta, scratch);
+        RIFT_LAUNCH_OK();
+        launch_k(bn_affine_bwd_final_kernel, dim3(cdiv(C, 32), 2), 256, 0, st, scratch, nb, C, dgamma, dbeta);
+        RIFT_LAUNCH_OK();
+        return 0;
+    }
     launch_k(bn_affine_bwd_partial_kernel, nb, 256, 0, st, dz, v, rows, C, gamma, beta, scratch);
     RIFT_LAUNCH_OK();
     launch_k(bn_affine_bwd_final_kernel, dim3(cdiv(C, 32), 2), 256, 0, st, scratch, nb, C, dgamma, dbeta);

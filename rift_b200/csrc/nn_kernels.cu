@@ -906,10 +906,37 @@ __global__ void im2col_k3_kernel(const float* __restrict__ x, int n_seq, int L, 
         if (op.on()) split_store(op, row, j, v);
     }
 }
+// planes-only form: one thread = four consecutive columns j (8-byte plane stores instead of four 2-byte ones)
+__global__ void __launch_bounds__(256)
+im2col_k3_planes4_kernel(const float* __restrict__ x, int n_seq, int L, int Lout, int C, int stride, Planes op) {
+    pdl_grid_sync();
+    const int W4 = op.Kp >> 2;
+    const long long total = (long long)n_seq * Lout * W4;
+    FOR_GRID(e, total) {
+        const int j0 = (int)(e % W4) << 2;
+        const long long row = e / W4;              // n * Lout + t
+        const int t = (int)(row % Lout);
+        const long long n = row / Lout;
+        float v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int j = j0 + q;
+            const int k = j % 3, c = j / 3;
+            const int ts = t * stride - 1 + k;
+            v[q] = (j < C * 3 && ts >= 0 && ts < L) ? __ldg(x + (n * L + ts) * C + c) : 0.f;
+        }
+        split4_store(op, row, j0, v[0], v[1], v[2], v[3]);
+    }
+}
 int launch_im2col_k3(const float* x, int n_seq, int L, int C, int stride, float* out, cudaStream_t st, Planes op) {
     const int Lout = (L + 2 - 3) / stride + 1;
     const long long total = (long long)n_seq * Lout * (op.on() ? op.Kp : C * 3);
     if (total <= 0) return 0;
+    if (op.on() && out == nullptr) {
+        launch_k(im2col_k3_planes4_kernel, GRID1D(total / 4, 256), 256, 0, st, x, n_seq, L, Lout, C, stride, op);
+        RIFT_LAUNCH_OK();
+        return 0;
+    }
     launch_k(im2col_k3_kernel, GRID1D(total, 256), 256, 0, st, x, n_seq, L, Lout, C, stride, out, op);
     RIFT_LAUNCH_OK();
     return 0;
@@ -960,9 +987,38 @@ __global__ void fpn_upsample_add_kernel(float* __restrict__ dst, const float* __
         dst[e] += w0 * src[(n * Ls + i0) * C + c] + w1 * src[(n * Ls + i1) * C + c];
     }
 }
+__global__ void __launch_bounds__(256)
+fpn_upsample_add4_kernel(float* __restrict__ dst, const float* __restrict__ src, int n_seq, int Ld, int Ls, int C) {
+    pdl_grid_sync();
+    const int C4 = C >> 2;
+    const long long total = (long long)n_seq * Ld * C4;
+    const float rscale = (float)Ls / (float)Ld;
+    FOR_GRID(e, total) {
+        const int c = (int)(e % C4) << 2;
+        const long long r = e / C4;
+        const int j = (int)(r % Ld);
+        const long long n = r / Ld;
+        float sp = ((float)j + 0.5f) * rscale - 0.5f;
+        sp = fmaxf(sp, 0.f);
+        const int i0 = min((int)sp, Ls - 1);
+        const int i1 = min(i0 + 1, Ls - 1);
+        const float w1 = sp - (float)i0, w0 = 1.f - w1;
+        const float4 a = *reinterpret_cast<const float4*>(src + (n * Ls + i0) * C + c);
+        const float4 b = *reinterpret_cast<const float4*>(src + (n * Ls + i1) * C + c);
+        float4* o = reinterpret_cast<float4*>(dst + r * C + c);
+        float4 d = *o;
+        d.x += w0 * a.x + w1 * b.x; d.y += w0 * a.y + w1 * b.y; d.z += w0 * a.z + w1 * b.z; d.w += w0 * a.w + w1 * b.w;
+        *o = d;
+    }
+}
 int launch_fpn_upsample_add(float* dst, const float* src, int n_seq, int Ld, int Ls, int C, cudaStream_t st) {
     const long long total = (long long)n_seq * Ld * C;
     if (total <= 0) return 0;
+    if ((C & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        launch_k(fpn_upsample_add4_kernel, GRID1D(total / 4, 256), 256, 0, st, dst, src, n_seq, Ld, Ls, C);
+        RIFT_LAUNCH_OK();
+        return 0;
+    }
     launch_k(fpn_upsample_add_kernel, GRID1D(total, 256), 256, 0, st, dst, src, n_seq, Ld, Ls, C);
     RIFT_LAUNCH_OK();
     return 0;
@@ -1413,29 +1469,38 @@ __global__ void act_bwd_kernel(const float* __restrict__ ref, float* __restrict_
 }
 // four elements per thread; with `planes` the product leaves as split-bf16 planes (flat: pitch == row length) INSTEAD of
 // being written back to dy - the consumer is a GEMM that reads planes only
+__device__ __forceinline__ float4 act_grad4(float4 d, const float4 r, int act) {
+    if (act == ACT_RELU) {
+        if (!(r.x > 0.f)) d.x = 0.f; if (!(r.y > 0.f)) d.y = 0.f; if (!(r.z > 0.f)) d.z = 0.f; if (!(r.w > 0.f)) d.w = 0.f;
+    } else {
+        d.x *= gelu_erf_grad(r.x); d.y *= gelu_erf_grad(r.y); d.z *= gelu_erf_grad(r.z); d.w *= gelu_erf_grad(r.w);
+    }
+    return d;
+}
+__device__ __forceinline__ void split4_flat(uint2* __restrict__ hi, uint2* __restrict__ lo, long long e, const float4 d) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(d.x), h1 = __float2bfloat16_rn(d.y), h2 = __float2bfloat16_rn(d.z), h3 = __float2bfloat16_rn(d.w);
+    const __nv_bfloat162 a = __halves2bfloat162(h0, h1), b = __halves2bfloat162(h2, h3);
+    const __nv_bfloat162 cc = __floats2bfloat162_rn(d.x - __bfloat162float(h0), d.y - __bfloat162float(h1));
+    const __nv_bfloat162 dd = __floats2bfloat162_rn(d.z - __bfloat162float(h2), d.w - __bfloat162float(h3));
+    uint2 uh, ul;
+    uh.x = *reinterpret_cast<const uint32_t*>(&a); uh.y = *reinterpret_cast<const uint32_t*>(&b);
+    ul.x = *reinterpret_cast<const uint32_t*>(&cc); ul.y = *reinterpret_cast<const uint32_t*>(&dd);
+    hi[e] = uh; lo[e] = ul;
+}
 __global__ void __launch_bounds__(256)
 act_bwd4_kernel(const float4* __restrict__ ref, float4* __restrict__ dy, long long n4, int act, uint2* __restrict__ hi, uint2* __restrict__ lo) {
     pdl_grid_sync();
-    for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < n4; e += (long long)gridDim.x * 256) {
-        const float4 r = __ldg(ref + e);
-        float4 d = dy[e];
-        if (act == ACT_RELU) {
-            if (!(r.x > 0.f)) d.x = 0.f; if (!(r.y > 0.f)) d.y = 0.f; if (!(r.z > 0.f)) d.z = 0.f; if (!(r.w > 0.f)) d.w = 0.f;
-        } else {
-            d.x *= gelu_erf_grad(r.x); d.y *= gelu_erf_grad(r.y); d.z *= gelu_erf_grad(r.z); d.w *= gelu_erf_grad(r.w);
-        }
-        if (hi) {
-            const __nv_bfloat16 h0 = __float2bfloat16_rn(d.x), h1 = __float2bfloat16_rn(d.y), h2 = __float2bfloat16_rn(d.z), h3 = __float2bfloat16_rn(d.w);
-            const __nv_bfloat162 a = __halves2bfloat162(h0, h1), b = __halves2bfloat162(h2, h3);
-            const __nv_bfloat162 cc = __floats2bfloat162_rn(d.x - __bfloat162float(h0), d.y - __bfloat162float(h1));
-            const __nv_bfloat162 dd = __floats2bfloat162_rn(d.z - __bfloat162float(h2), d.w - __bfloat162float(h3));
-            uint2 uh, ul;
-            uh.x = *reinterpret_cast<const uint32_t*>(&a); uh.y = *reinterpret_cast<const uint32_t*>(&b);
-            ul.x = *reinterpret_cast<const uint32_t*>(&cc); ul.y = *reinterpret_cast<const uint32_t*>(&dd);
-            hi[e] = uh; lo[e] = ul;
-        } else {
-            dy[e] = d;
-        }
+    const long long stride = (long long)gridDim.x * 256;
+    long long e = (long long)blockIdx.x * 256 + threadIdx.x;
+    for (; e + stride < n4; e += 2 * stride) {            // two independent 16-byte streams per thread in flight
+        const float4 r0 = __ldg(ref + e), r1 = __ldg(ref + e + stride);
+        const float4 d0 = act_grad4(dy[e], r0, act), d1 = act_grad4(dy[e + stride], r1, act);
+        if (hi) { split4_flat(hi, lo, e, d0); split4_flat(hi, lo, e + stride, d1); }
+        else { dy[e] = d0; dy[e + stride] = d1; }
+    }
+    if (e < n4) {
+        const float4 d0 = act_grad4(dy[e], __ldg(ref + e), act);
+        if (hi) split4_flat(hi, lo, e, d0); else dy[e] = d0;
     }
 }
 int launch_act_bwd(const float* pre_or_post, float* dy, long long n, int act, cudaStream_t st, Planes planes) {
