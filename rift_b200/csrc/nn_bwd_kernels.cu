@@ -291,11 +291,213 @@ attention_bwd2_kernel(AttnArgs a, const float* __restrict__ d_o, long long lddo,
     }
 }
 
+// ---- head_dim 32, register-tiled form (sequences of 24 .. 128 rows: encoder self-attention, decoder cross-attention) -------
+// One (batch, head) problem per CTA of 256 threads.  Every product of the backward is computed in 4 x 4 register tiles, so a
+// 16-byte shared-memory load feeds 16 FMAs instead of 4 and no shuffle is needed (the cooperative form above spends three
+// quarters of its instructions on loads, shuffles and address arithmetic; profiles/r2_attention_ncu.md):
+//   A1  S tile (4 queries x 4 keys over 32 channels) -> P = exp(S - lse), masked keys / dead rows -> 0      -> Ps
+//   A2  dP tile = dO V^T                                                                                     -> dSs
+//   A3  delta_i = sum_j P_ij dP_ij (one thread per query row, ascending j), then dS = P (dP - delta) in place
+//   B   dK / dV tiles (4 keys x 4 channels, loop over queries) and dQ tiles (4 queries x 4 channels, loop over keys)
+// Rows are padded to multiples of 4 (pad rows are zero; pad keys are masked, pad queries are dead rows).
+__host__ __device__ inline int attn_bwd3_skp(int Sk) { const int s4 = (Sk + 3) & ~3; return (s4 & 7) ? s4 : s4 + 4; }   // = 4 (mod 8)
+__host__ __device__ inline size_t attn_bwd3_smem_floats(int Sq, int Sk) {
+    const int Sq4 = (Sq + 3) & ~3, Sk4 = (Sk + 3) & ~3;
+    return (size_t)2 * Sq4 * AB_PITCH + (size_t)2 * Sk4 * AB_PITCH + (size_t)2 * Sq4 * attn_bwd3_skp(Sk) + (size_t)2 * Sq4 + Sk4 / 4;
+}
+__device__ __forceinline__ float dot4(const float4 a, const float4 b, float acc) {
+    acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); return fmaf(a.w, b.w, acc);
+}
+
+__global__ void __launch_bounds__(256, 3)
+attention_bwd3_kernel(AttnArgs a, const float* __restrict__ d_o, long long lddo, float* __restrict__ dq, long long lddq,
+                      float* __restrict__ dk, float* __restrict__ dv, long long lddk, long long lddv, Planes pq, Planes pk, Planes pv) {
+    pdl_grid_sync();
+    constexpr int HD = 32, T = 256;
+    extern __shared__ __align__(16) float sm[];
+    const int Sq = a.Sq, Sk = a.Sk, Sq4 = (Sq + 3) & ~3, Sk4 = (Sk + 3) & ~3, SkP = attn_bwd3_skp(Sk);
+    float* Qs = sm;                                      // [Sq4][36]  (pre-scaled)
+    float* dOs = Qs + (size_t)Sq4 * AB_PITCH;            // [Sq4][36]
+    float* Ks = dOs + (size_t)Sq4 * AB_PITCH;            // [Sk4][36]
+    float* Vs = Ks + (size_t)Sk4 * AB_PITCH;             // [Sk4][36]
+    float* Ps = Vs + (size_t)Sk4 * AB_PITCH;             // [Sq4][SkP]
+    float* dSs = Ps + (size_t)Sq4 * SkP;                 // [Sq4][SkP]  dP, then dS
+    float* lse_s = dSs + (size_t)Sq4 * SkP;              // [Sq4]
+    float* delta = lse_s + Sq4;                          // [Sq4]
+    uint8_t* msk = reinterpret_cast<uint8_t*>(delta + Sq4);   // [Sk4]
+    const int t = threadIdx.x;
+    const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
+    const long long krow0 = attn_row_b(b, a.k_inner_n, a.k_outer, a.k_inner);
+    const long long qrow0 = attn_row_b(b, a.q_inner_n, a.q_outer, a.q_inner);
+    const long long orow0 = a.o_custom ? attn_row_b(b, a.o_inner_n, a.o_outer, a.o_inner) : qrow0;
+    const long long oseq = a.o_custom ? a.o_seq : a.q_seq;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int e = t; e < Sk4 * 8; e += T) {
+        const int j = e >> 3, c = (e & 7) * 4;
+        const long long r = krow0 + (long long)j * a.k_seq;
+        *reinterpret_cast<float4*>(Ks + j * AB_PITCH + c) = j < Sk ? *reinterpret_cast<const float4*>(a.k + r * a.ldk + h * HD + c) : z4;
+        *reinterpret_cast<float4*>(Vs + j * AB_PITCH + c) = j < Sk ? *reinterpret_cast<const float4*>(a.v + r * a.ldv + h * HD + c) : z4;
+    }
+    for (int e = t; e < Sq4 * 8; e += T) {
+        const int i = e >> 3, c = (e & 7) * 4;
+        float4 q = z4, g = z4;
+        if (i < Sq) {
+            q = *reinterpret_cast<const float4*>(a.q + (qrow0 + (long long)i * a.q_seq) * a.ldq + h * HD + c);
+            q.x *= a.scale; q.y *= a.scale; q.z *= a.scale; q.w *= a.scale;
+            g = *reinterpret_cast<const float4*>(d_o + (orow0 + (long long)i * oseq) * lddo + h * HD + c);
+        }
+        *reinterpret_cast<float4*>(Qs + i * AB_PITCH + c) = q;
+        *reinterpret_cast<float4*>(dOs + i * AB_PITCH + c) = g;
+    }
+    for (int i = t; i < Sq4; i += T) lse_s[i] = i < Sq ? a.lse[((long long)b * a.H + h) * Sq + i] : INFINITY;
+    {
+        const uint8_t* kpm = a.kpm ? a.kpm + (long long)(a.kpm_mod > 0 ? (b + a.kpm_off) % a.kpm_mod : b / a.kpm_div) * Sk : nullptr;
+        for (int j = t; j < Sk4; j += T) msk[j] = j < Sk ? (kpm ? kpm[j] : 0) : 1;
+    }
+    __syncthreads();
+    // ---- A1 / A2.  A tile = 4 consecutive queries x the 4 keys {jb, jb + tj, jb + 2 tj, jb + 3 tj}: neighbouring threads then read
+    // neighbouring K / V rows (pitch 36 floats = 4 banks apart, conflict-free), where consecutive keys per thread would put
+    // the rows of a warp 16 banks apart (7-way conflicts on every K / V load)
+    const int tj = Sk4 >> 2, ntile = (Sq4 >> 2) * tj;
+    for (int u = t; u < ntile; u += T) {
+        const int i0 = (u / tj) << 2, jb = u % tj;
+        float s[4][4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int x = 0; x < 4; ++x) s[r][x] = 0.f;
+#pragma unroll
+        for (int c = 0; c < HD; c += 4) {
+            float4 q[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) q[r] = *reinterpret_cast<const float4*>(Qs + (i0 + r) * AB_PITCH + c);
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+                const float4 kk = *reinterpret_cast<const float4*>(Ks + (jb + x * tj) * AB_PITCH + c);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) s[r][x] = dot4(q[r], kk, s[r][x]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const float lse = lse_s[i0 + r];
+            const bool dead = (lse == INFINITY);
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+                Ps[(i0 + r) * SkP + jb + x * tj] = (dead || msk[jb + x * tj]) ? 0.f : __expf(s[r][x] - lse);
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int x = 0; x < 4; ++x) s[r][x] = 0.f;
+#pragma unroll
+        for (int c = 0; c < HD; c += 4) {
+            float4 g[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) g[r] = *reinterpret_cast<const float4*>(dOs + (i0 + r) * AB_PITCH + c);
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+                const float4 vv = *reinterpret_cast<const float4*>(Vs + (jb + x * tj) * AB_PITCH + c);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) s[r][x] = dot4(g[r], vv, s[r][x]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int x = 0; x < 4; ++x) dSs[(i0 + r) * SkP + jb + x * tj] = s[r][x];
+    }
+    __syncthreads();
+    // ---- A3: delta, then dS in place
+    for (int i = t; i < Sq4; i += T) {
+        float dl = 0.f;
+        for (int j = 0; j < Sk; ++j) dl = fmaf(Ps[i * SkP + j], dSs[i * SkP + j], dl);
+        delta[i] = dl;
+    }
+    __syncthreads();
+    for (int e = t; e < Sq4 * tj; e += T) {
+        const int i = e / tj, j0 = (e % tj) << 2;
+        const float dl = delta[i];
+        const float4 pp = *reinterpret_cast<const float4*>(Ps + i * SkP + j0);
+        float4 d = *reinterpret_cast<const float4*>(dSs + i * SkP + j0);
+        d.x = pp.x * (d.x - dl); d.y = pp.y * (d.y - dl); d.z = pp.z * (d.z - dl); d.w = pp.w * (d.w - dl);
+        *reinterpret_cast<float4*>(dSs + i * SkP + j0) = d;
+    }
+    __syncthreads();
+    // ---- B: (key block, channel quad) items produce dK and dV, (query block, channel quad) items produce dQ
+    const int nkv = tj * 8, nq = (Sq4 >> 2) * 8;
+    for (int u = t; u < nkv + nq; u += T) {
+        if (u < nkv) {
+            const int j0 = (u >> 3) << 2, c = (u & 7) << 2;
+            float ak[4][4], av[4][4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int x = 0; x < 4; ++x) { ak[r][x] = 0.f; av[r][x] = 0.f; }
+            for (int i = 0; i < Sq; ++i) {
+                const float4 pp = *reinterpret_cast<const float4*>(Ps + i * SkP + j0);
+                const float4 ds = *reinterpret_cast<const float4*>(dSs + i * SkP + j0);
+                const float4 qq = *reinterpret_cast<const float4*>(Qs + i * AB_PITCH + c);
+                const float4 oo = *reinterpret_cast<const float4*>(dOs + i * AB_PITCH + c);
+#define RIFT_AKV(r, P, D)                                                                                                   \
+    av[r][0] = fmaf(P, oo.x, av[r][0]); av[r][1] = fmaf(P, oo.y, av[r][1]); av[r][2] = fmaf(P, oo.z, av[r][2]);                 \
+    av[r][3] = fmaf(P, oo.w, av[r][3]); ak[r][0] = fmaf(D, qq.x, ak[r][0]); ak[r][1] = fmaf(D, qq.y, ak[r][1]);                 \
+    ak[r][2] = fmaf(D, qq.z, ak[r][2]); ak[r][3] = fmaf(D, qq.w, ak[r][3]);
+                RIFT_AKV(0, pp.x, ds.x) RIFT_AKV(1, pp.y, ds.y) RIFT_AKV(2, pp.z, ds.z) RIFT_AKV(3, pp.w, ds.w)     // Qs is pre-scaled: dK carries `scale`
+#undef RIFT_AKV
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                if (j0 + r >= Sk) continue;
+                const long long row = krow0 + (long long)(j0 + r) * a.k_seq;
+                if (dk) {
+                    *reinterpret_cast<float4*>(dk + row * lddk + h * HD + c) = make_float4(ak[r][0], ak[r][1], ak[r][2], ak[r][3]);
+                    *reinterpret_cast<float4*>(dv + row * lddv + h * HD + c) = make_float4(av[r][0], av[r][1], av[r][2], av[r][3]);
+                }
+                if (pk.on()) {
+                    split4_store(pk, row, h * HD + c, ak[r][0], ak[r][1], ak[r][2], ak[r][3]);
+                    split4_store(pv, row, h * HD + c, av[r][0], av[r][1], av[r][2], av[r][3]);
+                }
+            }
+        } else {
+            const int v = u - nkv;
+            const int i0 = (v >> 3) << 2, c = (v & 7) << 2;
+            float acc[4][4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int x = 0; x < 4; ++x) acc[r][x] = 0.f;
+            for (int j = 0; j < Sk; ++j) {
+                const float4 kk = *reinterpret_cast<const float4*>(Ks + j * AB_PITCH + c);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const float ds = dSs[(i0 + r) * SkP + j];
+                    acc[r][0] = fmaf(ds, kk.x, acc[r][0]); acc[r][1] = fmaf(ds, kk.y, acc[r][1]);
+                    acc[r][2] = fmaf(ds, kk.z, acc[r][2]); acc[r][3] = fmaf(ds, kk.w, acc[r][3]);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                if (i0 + r >= Sq) continue;
+                const long long row = a.o_custom ? (orow0 + (long long)(i0 + r) * oseq) : (qrow0 + (long long)(i0 + r) * a.q_seq);
+                const float x0 = acc[r][0] * a.scale, x1 = acc[r][1] * a.scale, x2 = acc[r][2] * a.scale, x3 = acc[r][3] * a.scale;
+                if (dq) *reinterpret_cast<float4*>(dq + row * lddq + h * HD + c) = make_float4(x0, x1, x2, x3);
+                if (pq.on()) split4_store(pq, row, h * HD + c, x0, x1, x2, x3);
+            }
+        }
+    }
+}
+
 // shape-only: will launch_attention_bwd take the kernel above (the one that can write planes)?
 bool attention_bwd_planes_ok(int Sq, int Sk, int hd) {
     static const bool legacy = getenv("RIFT_B200_ATTN_BWD_LEGACY") != nullptr;
     const int smax = max(Sq, Sk);
     return hd == 32 && !legacy && 4 * smax <= 512 && attn_bwd2_smem_floats(Sq, Sk) * sizeof(float) <= 200 * 1024;
+}
+// register-tiled kernel: sequences long enough to fill a CTA with 4 x 4 tiles (RIFT_B200_ATTN_BWD_TILED=0 switches it off)
+static bool attention_bwd_tiled(int Sq, int Sk, int hd) {
+    static const bool on = [] { const char* e = getenv("RIFT_B200_ATTN_BWD_TILED"); return !(e && atoi(e) == 0); }();
+    return on && hd == 32 && min(Sq, Sk) >= 24 && max(Sq, Sk) <= 128 && attn_bwd3_smem_floats(Sq, Sk) * sizeof(float) <= 160 * 1024;
 }
 
 int launch_attention_bwd(const AttnArgs& a, const float* d_o, long long lddo, float* dq, long long lddq, float* dk,
@@ -312,9 +514,20 @@ int launch_attention_bwd(const AttnArgs& a, const float* d_o, long long lddo, fl
         const bool vec = a.hd == 32 && al16(a.q) && al16(a.k) && al16(a.v) && al16(d_o) && al16(dq) && al16(dk) && al16(dv) &&
                          (a.ldq & 3) == 0 && (a.ldk & 3) == 0 && (a.ldv & 3) == 0 && (lddo & 3) == 0 && (lddq & 3) == 0 &&
                          (lddk & 3) == 0 && (lddv & 3) == 0;
+        static const bool legacy = getenv("RIFT_B200_ATTN_BWD_LEGACY") != nullptr;
+        if (vec && !legacy && attention_bwd_tiled(a.Sq, a.Sk, a.hd)) {
+            const size_t smem3 = attn_bwd3_smem_floats(a.Sq, a.Sk) * sizeof(float);
+            static bool attr3 = false;
+            if (!attr3) {
+                RIFT_CUDA_OK(cudaFuncSetAttribute(attention_bwd3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+                attr3 = true;
+            }
+            launch_k(attention_bwd3_kernel, (unsigned)(a.B * a.H), 256, smem3, st, a, d_o, lddo, dq, lddq, dk, dv, lddk, lddv, pl.q, pl.k, pl.v);
+            RIFT_LAUNCH_OK();
+            return 0;
+        }
         const int smax = max(a.Sq, a.Sk);
         const size_t per = attn_bwd2_smem_floats(a.Sq, a.Sk) * sizeof(float);
-        static const bool legacy = getenv("RIFT_B200_ATTN_BWD_LEGACY") != nullptr;
         if (vec && !legacy && 4 * smax <= 512 && per <= 200 * 1024) {
             constexpr int G = 4;
             const int tpp = (G * smax + 31) / 32 * 32;

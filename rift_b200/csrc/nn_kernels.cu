@@ -721,6 +721,136 @@ attention2_kernel(AttnArgs a, int PB, int tpp) {
     if (a.lse && g == 0) a.lse[((long long)b * a.H + h) * Sq + i] = l > 0.f ? m + logf(l) : INFINITY;
 }
 
+// ---- head_dim 32, register-tiled form (sequences of 24 .. 128 rows; see attention_bwd3_kernel for the tiling) ----------------
+//   A  S tile = 4 consecutive queries x 4 keys strided by Sk4 / 4 (conflict-free K rows) over 32 channels -> Ss (masked: -inf)
+//   B  row softmax, 4 lanes per row: m, l, P = exp(S - m) left unnormalised in Ss, 1 / l and the log-sum-exp per row
+//   C  O tile = 4 queries x 4 channels, loop over keys; scaled by 1 / l on the way out
+__host__ __device__ inline int attn_fwd3_skp(int Sk) { const int s4 = (Sk + 3) & ~3; return (s4 & 7) ? s4 : s4 + 4; }
+__host__ __device__ inline size_t attn_fwd3_smem_floats(int Sq, int Sk) {
+    const int Sq4 = (Sq + 3) & ~3, Sk4 = (Sk + 3) & ~3;
+    return (size_t)Sq4 * AF_PITCH + (size_t)2 * Sk4 * AF_PITCH + (size_t)Sq4 * attn_fwd3_skp(Sk) + Sq4 + Sk4 / 4;
+}
+__global__ void __launch_bounds__(256, 3)
+attention3_kernel(AttnArgs a) {
+    pdl_grid_sync();
+    constexpr int HD = 32, T = 256;
+    extern __shared__ __align__(16) float sm[];
+    const int Sq = a.Sq, Sk = a.Sk, Sq4 = (Sq + 3) & ~3, Sk4 = (Sk + 3) & ~3, SkP = attn_fwd3_skp(Sk);
+    float* Qs = sm;
+    float* Ks = Qs + (size_t)Sq4 * AF_PITCH;
+    float* Vs = Ks + (size_t)Sk4 * AF_PITCH;
+    float* Ss = Vs + (size_t)Sk4 * AF_PITCH;             // [Sq4][SkP]
+    float* inv = Ss + (size_t)Sq4 * SkP;                 // [Sq4]
+    uint8_t* msk = reinterpret_cast<uint8_t*>(inv + Sq4);
+    const int t = threadIdx.x;
+    const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
+    const long long krow0 = attn_row(b, a.k_inner_n, a.k_outer, a.k_inner);
+    const long long qrow0 = attn_row(b, a.q_inner_n, a.q_outer, a.q_inner);
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int e = t; e < Sk4 * 8; e += T) {
+        const int j = e >> 3, c = (e & 7) * 4;
+        const long long r = krow0 + (long long)j * a.k_seq;
+        *reinterpret_cast<float4*>(Ks + j * AF_PITCH + c) = j < Sk ? *reinterpret_cast<const float4*>(a.k + r * a.ldk + h * HD + c) : z4;
+        *reinterpret_cast<float4*>(Vs + j * AF_PITCH + c) = j < Sk ? *reinterpret_cast<const float4*>(a.v + r * a.ldv + h * HD + c) : z4;
+    }
+    for (int e = t; e < Sq4 * 8; e += T) {
+        const int i = e >> 3, c = (e & 7) * 4;
+        float4 q = z4;
+        if (i < Sq) {
+            q = *reinterpret_cast<const float4*>(a.q + (qrow0 + (long long)i * a.q_seq) * a.ldq + h * HD + c);
+            q.x *= a.scale; q.y *= a.scale; q.z *= a.scale; q.w *= a.scale;
+        }
+        *reinterpret_cast<float4*>(Qs + i * AF_PITCH + c) = q;
+    }
+    {
+        const uint8_t* kpm = a.kpm ? a.kpm + (long long)(a.kpm_mod > 0 ? (b + a.kpm_off) % a.kpm_mod : b / a.kpm_div) * Sk : nullptr;
+        for (int j = t; j < Sk4; j += T) msk[j] = j < Sk ? (kpm ? kpm[j] : 0) : 1;
+    }
+    __syncthreads();
+    const int tj = Sk4 >> 2, ntile = (Sq4 >> 2) * tj;
+    for (int u = t; u < ntile; u += T) {
+        const int i0 = (u / tj) << 2, jb = u % tj;
+        float s[4][4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int x = 0; x < 4; ++x) s[r][x] = 0.f;
+#pragma unroll
+        for (int c = 0; c < HD; c += 4) {
+            float4 q[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) q[r] = *reinterpret_cast<const float4*>(Qs + (i0 + r) * AF_PITCH + c);
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+                const float4 kk = *reinterpret_cast<const float4*>(Ks + (jb + x * tj) * AF_PITCH + c);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    s[r][x] = fmaf(q[r].x, kk.x, s[r][x]); s[r][x] = fmaf(q[r].y, kk.y, s[r][x]);
+                    s[r][x] = fmaf(q[r].z, kk.z, s[r][x]); s[r][x] = fmaf(q[r].w, kk.w, s[r][x]);
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int x = 0; x < 4; ++x) Ss[(i0 + r) * SkP + jb + x * tj] = msk[jb + x * tj] ? -INFINITY : s[r][x];
+    }
+    __syncthreads();
+    {
+        const int g = t & 3;
+        const unsigned gmask = 0xfu << ((t & 31) & ~3);
+        for (int row = t >> 2; row < Sq4; row += T / 4) {
+            float* sr = Ss + row * SkP;
+            float m = -INFINITY;
+            for (int j = g; j < Sk; j += 4) m = fmaxf(m, sr[j]);
+            m = fmaxf(m, __shfl_xor_sync(gmask, m, 1));
+            m = fmaxf(m, __shfl_xor_sync(gmask, m, 2));
+            float l = 0.f;
+            if (m > -INFINITY) {
+                for (int j = g; j < Sk; j += 4) { const float p = __expf(sr[j] - m); sr[j] = p; l += p; }
+            } else {
+                for (int j = g; j < Sk; j += 4) sr[j] = 0.f;
+            }
+            l += __shfl_xor_sync(gmask, l, 1);
+            l += __shfl_xor_sync(gmask, l, 2);
+            if (g == 0) {
+                inv[row] = l > 0.f ? 1.f / l : 0.f;
+                if (a.lse && row < Sq) a.lse[((long long)b * a.H + h) * Sq + row] = l > 0.f ? m + logf(l) : INFINITY;
+            }
+        }
+    }
+    __syncthreads();
+    const int nq = (Sq4 >> 2) * 8;
+    for (int u = t; u < nq; u += T) {
+        const int i0 = (u >> 3) << 2, c = (u & 7) << 2;
+        float acc[4][4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int x = 0; x < 4; ++x) acc[r][x] = 0.f;
+        for (int j = 0; j < Sk; ++j) {
+            const float4 vv = *reinterpret_cast<const float4*>(Vs + j * AF_PITCH + c);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const float p = Ss[(i0 + r) * SkP + j];
+                acc[r][0] = fmaf(p, vv.x, acc[r][0]); acc[r][1] = fmaf(p, vv.y, acc[r][1]);
+                acc[r][2] = fmaf(p, vv.z, acc[r][2]); acc[r][3] = fmaf(p, vv.w, acc[r][3]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int i = i0 + r;
+            if (i >= Sq) continue;
+            const float iv = inv[i];
+            const long long qr = qrow0 + (long long)i * a.q_seq;
+            const long long orow = a.o_custom ? attn_row(b, a.o_inner_n, a.o_outer, a.o_inner) + (long long)i * a.o_seq : qr;
+            const float4 o4 = make_float4(acc[r][0] * iv, acc[r][1] * iv, acc[r][2] * iv, acc[r][3] * iv);
+            if (a.o) *reinterpret_cast<float4*>(a.o + orow * a.ldo + h * HD + c) = o4;
+            if (a.o_planes.on()) split4_store(a.o_planes, orow, h * HD + c, o4.x, o4.y, o4.z, o4.w);
+        }
+    }
+}
+
 int launch_attention(const AttnArgs& a, cudaStream_t st) {
     if (a.B <= 0 || a.Sq <= 0) return 0;
     RIFT_REQUIRE(a.hd == 32 || a.hd == 64, "attention: head_dim must be 32 or 64");
@@ -732,6 +862,17 @@ int launch_attention(const AttnArgs& a, cudaStream_t st) {
         const int smax = max(a.Sq, a.Sk);
         const size_t per = attn_fwd2_smem_floats(a.Sq, a.Sk) * sizeof(float);
         static const bool legacy = getenv("RIFT_B200_ATTN_FWD_LEGACY") != nullptr;
+        static const bool tiled = [] { const char* e = getenv("RIFT_B200_ATTN_FWD_TILED"); return !(e && atoi(e) == 0); }();
+        if (vec && !legacy && tiled && min(a.Sq, a.Sk) >= 24 && smax <= 128 && attn_fwd3_smem_floats(a.Sq, a.Sk) * sizeof(float) <= 160 * 1024) {
+            static bool attr3 = false;
+            if (!attr3) {
+                RIFT_CUDA_OK(cudaFuncSetAttribute(attention3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+                attr3 = true;
+            }
+            launch_k(attention3_kernel, (unsigned)(a.B * a.H), 256, attn_fwd3_smem_floats(a.Sq, a.Sk) * sizeof(float), st, a);
+            RIFT_LAUNCH_OK();
+            return 0;
+        }
         if (vec && !legacy && 4 * a.Sq <= 512 && per <= 200 * 1024) {
             constexpr int G = 4;
             const int tpp = (G * max(a.Sq, min(smax, 128 / G)) + 31) / 32 * 32;     // enough threads to stage K / V quickly too

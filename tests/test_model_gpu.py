@@ -272,7 +272,10 @@ BASELINE_SHAPES = {
 #   tensor-core forward + backward       : norm 4.2e-3, relative L2 2.9e-2, element 1.1e-1, 26 541 of 17.0 M elements (0.16 %)
 # norm = | ||g|| - ||g_ref|| | / ||g_ref||, l2 = ||g - g_ref|| / ||g_ref||, element = max |g - g_ref| / (max |g_ref| + 1e-3 gmax).
 PARITY_TOL = {"tcgen05": dict(norm=6e-3, l2=4e-2, element=0.15, over=3e-3),
-              "fp32fwd_tcgen05bwd": dict(norm=2e-3, l2=5e-3, element=1e-2, over=1e-4)}
+              # (exact forward: the few ReLU / arg-max decisions within one ulp of their threshold still flip against the CPU
+              #  oracle - which ones depends on summation order inside the forward kernels; one flipped unit of a 1024-wide FFN
+              #  moves single gradient elements by ~2 % of their tensor's max.  The COUNT bound is the regression guard.)
+              "fp32fwd_tcgen05bwd": dict(norm=2e-3, l2=5e-3, element=3e-2, over=1e-4)}
 
 
 @pytest.mark.parametrize("mode", ["tcgen05", "fp32fwd_tcgen05bwd"])
