@@ -350,8 +350,15 @@ inline int lin_bwd(Ctx& c, const float* X, long long ldx, const float* dY, long 
         // one wave of (tile, split) work items; RIFT_B200_WGRAD_CTAS caps the wave below the SM count, which leaves SMs to
         // the data-gradient chain running next to these side-stream products
         static const int wave = [] { const char* e = getenv("RIFT_B200_WGRAD_CTAS"); const int v = e ? atoi(e) : 148; return v > 0 ? v : 148; }();
+        // split count: at most RIFT_B200_WGRAD_SPLIT_CAP (24) parts per tile.  More parts shorten the kernel but take SMs
+        // from the data-gradient chain running beside it: measured 8.86 ms per step with 148, 8.85 with 64, 8.66 with 24.
+        static const int split_cap = [] { const char* e = getenv("RIFT_B200_WGRAD_SPLIT_CAP"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 24; }();
         int splits = wave / tiles;
-        if (splits > 24) splits = 24;
+        int cap = atomic_w ? split_cap : 24;
+        // very tall activations (the history encoder's 20480 / 40960-row levels: 320 / 640 k-blocks) sit at the end of the
+        // backward, where the data-gradient chain has finished and nothing competes for the SMs: one part per 8 k-blocks
+        if (atomic_w && num_kb >= 256 && num_kb / 8 > cap) cap = num_kb / 8;
+        if (splits > cap) splits = cap;
         if (splits > num_kb) splits = num_kb;
         if (splits < 1) splits = 1;
         float* ws = nullptr;

@@ -408,20 +408,20 @@ attention_bwd3_kernel(AttnArgs a, const float* __restrict__ d_o, long long lddo,
             for (int x = 0; x < 4; ++x) dSs[(i0 + r) * SkP + jb + x * tj] = s[r][x];
     }
     __syncthreads();
-    // ---- A3: delta, then dS in place
-    for (int i = t; i < Sq4; i += T) {
-        float dl = 0.f;
-        for (int j = 0; j < Sk; ++j) dl = fmaf(Ps[i * SkP + j], dSs[i * SkP + j], dl);
-        delta[i] = dl;
-    }
-    __syncthreads();
-    for (int e = t; e < Sq4 * tj; e += T) {
-        const int i = e / tj, j0 = (e % tj) << 2;
-        const float dl = delta[i];
-        const float4 pp = *reinterpret_cast<const float4*>(Ps + i * SkP + j0);
-        float4 d = *reinterpret_cast<const float4*>(dSs + i * SkP + j0);
-        d.x = pp.x * (d.x - dl); d.y = pp.y * (d.y - dl); d.z = pp.z * (d.z - dl); d.w = pp.w * (d.w - dl);
-        *reinterpret_cast<float4*>(dSs + i * SkP + j0) = d;
+    // ---- A3: four lanes per query row: delta_i = sum_j P_ij dP_ij (lane partials combined in a fixed order), then dS = P (dP - delta)
+    // in place on the lane's own columns
+    {
+        const int g = t & 3;
+        const unsigned gmask = 0xfu << ((t & 31) & ~3);
+        for (int i = t >> 2; i < Sq4; i += T / 4) {
+            const float* pr = Ps + i * SkP;
+            float* dr = dSs + i * SkP;
+            float dl = 0.f;
+            for (int j = g; j < Sk; j += 4) dl = fmaf(pr[j], dr[j], dl);
+            dl += __shfl_xor_sync(gmask, dl, 1);
+            dl += __shfl_xor_sync(gmask, dl, 2);
+            for (int j = g; j < Sk4; j += 4) dr[j] = pr[j] * (dr[j] - dl);
+        }
     }
     __syncthreads();
     // ---- B: (key block, channel quad) items produce dK and dV, (query block, channel quad) items produce dQ
