@@ -475,7 +475,27 @@ def run_ours(args):
                           f"(oracle/ restatement of the reference's torch-CPU path, {threads} threads)"}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        shutdown_process_group(tr)
+
+
+def shutdown_process_group(*trainers):
+    """NCCL does not finish destroying a communicator while CUDA graphs that captured its kernels are alive (the step graph
+    holds the all-reduce), so the graphs go first; should the teardown still block, the result line is already out and the
+    process leaves without it."""
+    import gc
+    import threading
+    import torch.distributed as dist
+    for tr in trainers:
+        tr._invalidate_graphs()
+    gc.collect()
+    torch.cuda.synchronize()
+    t = threading.Thread(target=dist.destroy_process_group, daemon=True)
+    t.start()
+    t.join(20.0)
+    if t.is_alive():
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

@@ -2,7 +2,8 @@
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
 import this file.  Each function cites the reference lines it follows.  Pinned against the
-reference's own functions by tests/test_oracle_vs_reference.py (container) and tests/golden/.
+reference's own functions through tests/golden/*.npz (written by oracle/make_golden.py, which imports the unmodified reference)
+and tests/test_oracle_golden.py.
 """
 import math
 from typing import Dict, List, Tuple

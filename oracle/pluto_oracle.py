@@ -6,8 +6,8 @@ import this file; the product path (rift_b200/) never does.
 It restates, in deterministic (eval) mode, `PlanningModel.forward`
 (rift/cbv/planning/pluto/model/pluto_model.py:122-225) and every module it calls, as plain
 functions over a state dict whose keys are the reference's own.  It is pinned against the
-unmodified reference modules by tests/test_oracle_vs_reference.py (container only, via
-oracle/ref_shim.py) and against tests/golden/*.npz (everywhere).
+unmodified reference modules through tests/golden/*.npz (written in the container by oracle/make_golden.py, which
+imports the reference via oracle/ref_shim.py; checked everywhere by tests/test_oracle_golden.py).
 
 Parity status: pinned against the reference's own torch modules run in this container;
 "parity unpinned" only at the NATTEN boundary (natten 0.14.6 is not vendored; see ref_shim.py).

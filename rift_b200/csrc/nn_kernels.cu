@@ -380,7 +380,9 @@ int launch_layernorm_bwd(const float* x, long long ldx, const float* dy, long lo
                          al16(dy) && al16(y_for_relu) && al16(dx) && al16(gamma);
         if (vec) {
             // more, smaller blocks than the partial buffer has slots is not possible: LNB_BLOCKS partial rows
-            const int nb4 = min(cdiv(rows, 8), LNB_BLOCKS);
+            // rows per warp: fewer blocks mean fewer atomics on the 2 C parameter-gradient addresses (RIFT_B200_LNB_RPW)
+            static const int rpw = [] { const char* e = getenv("RIFT_B200_LNB_RPW"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 1; }();
+            const int nb4 = min(cdiv(rows, 8 * rpw), LNB_BLOCKS);
             const size_t smem4 = (size_t)8 * 2 * C * sizeof(float);
             const int nv = cdiv(C, 128);
 #define RIFT_LNB4(NV)                                                                                                       \

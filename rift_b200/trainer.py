@@ -117,6 +117,15 @@ class LightningTrainer:
         self._graphs = {}
         self._graph_seen = {}
 
+    def close(self):
+        """Drop the captured step graphs.  Call before ``torch.distributed.destroy_process_group()`` when world_size > 1: NCCL
+        does not finish destroying a communicator while a CUDA graph that captured its all-reduce is alive."""
+        self._invalidate_graphs()
+        import gc
+        gc.collect()
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+
     def forward(self, features):
         return self.model(features)
 

@@ -1,6 +1,10 @@
 set -x
 N=${1:-2}
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 tools/dp_check.py 2>&1 | tail -6
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --steps 30 --warmup 5 2>gpurun_out/bench_n$N.err | tail -1 | tee gpurun_out/bench_n$N.json
-tail -5 gpurun_out/bench_n$N.err
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus $N --steps 30 --warmup 5 --scaling weak --no-kernels 2>/dev/null | tail -1 | tee gpurun_out/bench_n${N}_weak.json
+date
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --steps 30 --warmup 5 2>gpurun_out/bench_n$N.err | tail -1 > gpurun_out/bench_n$N.json
+echo "rc=$?"; date
+tail -3 gpurun_out/bench_n$N.err | cut -c1-300
+python -c "
+import json; d=json.load(open('gpurun_out/bench_n$N.json')); print('N=$N', d['value'], d['ms_per_step'], d['scaling'], d['e2e']['value'], d.get('weak_scaling'))"
+timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 bench.py --impl reference --gpus $N --steps 2 --warmup 1 2>/dev/null | tail -1 | cut -c1-400
+date
