@@ -5,7 +5,7 @@ import os, sys, json, subprocess, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from rift_b200 import _lib
 
-SHAPES = [(128, 256, 256), (4608, 256, 768), (4608, 1024, 256), (3328, 256, 1024), (40960, 64, 192), (40960, 192, 64),
+SHAPES = [(4608, 256, 256), (128, 256, 256), (4608, 256, 768), (4608, 1024, 256), (3328, 256, 1024), (40960, 64, 192), (40960, 192, 64),
           (46080, 256, 256), (46080, 128, 256)]
 
 
