@@ -258,6 +258,10 @@ int rift_b200_op_fused_mlp(const float* x, int rows, int D, int Hd, int act, con
 size_t rift_b200_op_wgrad_tc_scratch_bytes(int rows, int N, int K);
 int rift_b200_op_wgrad_tc(const float* dY, const float* X, int rows, int N, int K, float* dW, float* db, int splits,
                           void* scratch, size_t scratch_bytes, void* stream);
+/* n <= 12 weight-gradient products (each as rift_b200_op_wgrad_tc) in ONE grouped persistent launch; host arrays of n entries;
+ * every product needs N >= 64, K > 64, K % 4 == 0, rows >= 64; db[i] may be NULL */
+int rift_b200_op_wgrad_group(int n, const float* const* dY, const float* const* X, const int* rows, const int* N, const int* K,
+                             float* const* dW, float* const* db, void* scratch, size_t scratch_bytes, void* stream);
 int rift_b200_op_gemm(const float* A, long long sam, long long sak, const float* B, long long sbn, long long sbk,
                       float* C, long long ldc, int M, int N, int K, float beta, int split_k, float* split_ws,
                       int simt, void* stream);

@@ -106,6 +106,8 @@ _SIGNATURES = {
     "rift_b200_op_fused_mlp_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "rift_b200_op_fused_mlp": (C.c_int, [_V, C.c_int, C.c_int, C.c_int, C.c_int, _V, _V, _V, _V, _V, _V, _V, _V, _V, _V, _V, _V,
                                          _V, _V, _V, C.c_size_t, C.c_int, _V]),
+    "rift_b200_op_wgrad_group": (C.c_int, [C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                           C.POINTER(C.c_int), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _V, C.c_size_t, _V]),
     "rift_b200_op_wgrad_tc_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "rift_b200_op_wgrad_tc": (C.c_int, [_V, _V, C.c_int, C.c_int, C.c_int, _V, _V, C.c_int, _V, C.c_size_t, _V]),
     "rift_b200_op_linear_tc_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),

@@ -345,6 +345,35 @@ int rift_b200_op_wgrad_tc(const float* dY, const float* X, int rows, int N, int 
     return launch_gemm_tc_ex(a, A, B, true, splits, nullptr, S(stream));
 }
 
+// n <= 12 products dW_i[N_i, K_i] += dY_i^T X_i, db_i[N_i] += colsum(dY_i) in ONE grouped launch (wgrad_group_kernel); arrays of
+// n host-side entries; scratch as for n calls of rift_b200_op_wgrad_tc (sum of the per-product sizes)
+int rift_b200_op_wgrad_group(int n, const float* const* dY, const float* const* X, const int* rows, const int* N, const int* K,
+                             float* const* dW, float* const* db, void* scratch, size_t scratch_bytes, void* stream) {
+    RIFT_REQUIRE(n >= 1 && n <= WGRAD_GROUP_MAX && dY && X && rows && N && K && dW && db && scratch, "op_wgrad_group: bad argument");
+    RIFT_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 255) == 0, "op_wgrad_group: scratch must be 256-byte aligned");
+    WgradItem items[WGRAD_GROUP_MAX];
+    char* p = static_cast<char*>(scratch);
+    size_t used = 0;
+    for (int i = 0; i < n; ++i) {
+        RIFT_REQUIRE(wgrad_group_takes(N[i], K[i], rows[i], K[i], dW[i]), "op_wgrad_group: product not eligible (N >= 64, K > 64, K % 4 == 0, rows >= 64)");
+        const int Np = (N[i] + 63) / 64 * 64, Kp = (K[i] + 63) / 64 * 64;
+        const size_t ypl = ((size_t)rows[i] * Np * 2 + 255) & ~(size_t)255, xpl = ((size_t)rows[i] * Kp * 2 + 255) & ~(size_t)255;
+        used += 2 * ypl + 2 * xpl;
+        RIFT_REQUIRE(used <= scratch_bytes, "op_wgrad_group: scratch too small");
+        void *yh = p, *yl = p + ypl, *xh = p + 2 * ypl, *xl = p + 2 * ypl + xpl;
+        p += 2 * ypl + 2 * xpl;
+        int r = launch_pack_split(dY[i], N[i], rows[i], N[i], Np, yh, yl, S(stream));
+        if (r) return r;
+        r = launch_pack_split(X[i], K[i], rows[i], K[i], Kp, xh, xl, S(stream));
+        if (r) return r;
+        items[i].A = PlaneOp{yh, yl, rows[i], Np, 0, 0};
+        items[i].B = PlaneOp{xh, xl, rows[i], Kp, 0, 0};
+        items[i].C = dW[i]; items[i].ldc = K[i]; items[i].colsum = db[i];
+        items[i].M = N[i]; items[i].N = K[i]; items[i].K = rows[i];
+    }
+    return launch_wgrad_group(items, n, 3, S(stream));
+}
+
 int rift_b200_op_gemm(const float* A, long long sam, long long sak, const float* B, long long sbn, long long sbk, float* C,
                       long long ldc, int M, int N, int K, float beta, int split_k, float* split_ws, int simt, void* stream) {
     GemmArgs a;

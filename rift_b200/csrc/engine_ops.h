@@ -39,6 +39,33 @@ inline int join_from(Ctx& c, cudaStream_t from) {
     RIFT_CUDA_OK(cudaStreamWaitEvent(c.st, e, 0));
     return 0;
 }
+// Grouped weight gradients (RIFT_B200_WGRAD_GROUP=0 switches them off): lin_bwd queues eligible products instead of launching
+// them; a group of up to 12 goes out as ONE persistent kernel on the side stream, ordered after everything the stream that
+// produced their operand planes has enqueued so far.  The operands are planes nobody writes again (bump allocator), so the
+// delay between queueing and launching is harmless.
+inline bool wgrad_group_on() {
+    static const bool on = [] { const char* e = getenv("RIFT_B200_WGRAD_GROUP"); return !(e && atoi(e) == 0); }();
+    return on;
+}
+// products per grouped launch (RIFT_B200_WGRAD_GROUP_SIZE, default and maximum 12)
+inline int wgrad_group_size() {
+    static const int n = [] { const char* e = getenv("RIFT_B200_WGRAD_GROUP_SIZE"); const int v = e ? atoi(e) : 0; return (v > 0 && v <= WGRAD_GROUP_MAX) ? v : WGRAD_GROUP_MAX; }();
+    return n;
+}
+inline int bwd_terms();
+inline int flush_wgrads(Ctx& c) {
+    if (c.n_pending == 0) return 0;
+    const int n = c.n_pending;
+    c.n_pending = 0;
+    if (c.dry) return 0;
+    cudaStream_t to = c.side ? c.side : c.pending_stream;
+    if (to != c.pending_stream) {
+        cudaEvent_t e = c.next_event();
+        RIFT_CUDA_OK(cudaEventRecord(e, c.pending_stream));
+        RIFT_CUDA_OK(cudaStreamWaitEvent(to, e, 0));
+    }
+    return launch_wgrad_group(c.pending, n, bwd_terms(), to);
+}
 // launches inside the scope go to `s` (when non-null)
 struct OnStream {
     Ctx& c; cudaStream_t saved;
@@ -363,7 +390,16 @@ inline int lin_bwd(Ctx& c, const float* X, long long ldx, const float* dY, long 
         if (splits < 1) splits = 1;
         float* ws = nullptr;
         if (!atomic_w && (splits > 1 || w_padded)) { ws = c.alloc<float>((size_t)splits * L.N * Kpad4); if (!ws) { set_last_error("workspace too small"); return -1; } }
-        if (!c.dry) {
+        if (!c.dry && wgrad_group_on() && atomic_w && !w_padded && wgrad_group_takes(L.N, L.K, M, L.ldw, L.dW)) {
+            if (c.n_pending && c.pending_stream != c.st) TRY(flush_wgrads(c));
+            c.pending_stream = c.st;
+            WgradItem& w = c.pending[c.n_pending++];
+            w.A = PlaneOp{dYp.hi, dYp.lo, M, dYp.Kp, 0, 0};
+            w.B = PlaneOp{xp.hi, xp.lo, M, xp.Kp, 0, 0};
+            w.C = L.dW; w.ldc = L.ldw; w.colsum = b_in_wgrad ? L.db : nullptr;
+            w.M = L.N; w.N = L.K; w.K = M;
+            if (c.n_pending == wgrad_group_size()) TRY(flush_wgrads(c));
+        } else if (!c.dry) {
             if (!forked) TRY(fork_to(c, c.side));
             OnStream on(c, c.side);
             GemmArgs a;

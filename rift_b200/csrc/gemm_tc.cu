@@ -26,6 +26,7 @@
 #include <cuda_bf16.h>
 
 #include <stdlib.h>
+#include <string.h>
 
 #include <unordered_map>
 
@@ -1232,6 +1233,271 @@ int launch_gemm_tc_ex(const GemmArgs& a, const PlaneOp& A, const PlaneOp& B, boo
     }
     if (narrow) return launch_tc<64, false>(a, A, B, splits, partials, st);
     return launch_tc<128, false>(a, A, B, splits, partials, st);
+}
+
+// ---------------------------------------------------------------------------------- grouped weight gradients
+// Up to WG_MAXP independent products dW_p[M_p, N_p] += dY_p^T X_p (+ bias gradient colsum(dY_p)) in ONE persistent launch.
+// The backward of a transformer block produces ~10 such products, each a grid of 24 .. 96 CTAs that holds 200 KB of shared
+// memory per SM for 3 k-blocks; queued behind each other on the side stream they cost ~20 us apiece (launch, pipeline fill,
+// drain) and compete SM by SM with the data-gradient chain.  Here their (tile, split) work items form one queue: 148 CTAs
+// walk it with the operand ring and the two TMEM accumulators staying busy across items of different products.
+// Same roles / barriers / MMA issue as gemm_tc_kernel<128, true>; the epilogue is the atomic one only.
+// Every product: MN-major operands (planes [rows, features]), N_p % 4 == 0, red.global.add.v4.f32 into dW (zeroed by the caller).
+constexpr int WG_MAXP = 12;                      // 12 x 640 B of descriptors + header = 7.7 KB of kernel parameters (CUDA >= 12.1: 32 KB limit)
+struct alignas(64) WgProblem {
+    CUtensorMap a_hi, a_lo, b_hi, b_lo;
+    float* C; float* colsum; long long ldc;
+    int M, N, K;
+    int tiles_n, tiles_mn, kb_per_split, num_kb, item0;
+    int pad_[3];
+};
+struct alignas(64) WgGroup {
+    WgProblem p[WG_MAXP];
+    int n_problems, n_items, terms, pad_[13];
+};
+static_assert(sizeof(WgGroup) <= 8192, "grouped weight-gradient parameters");
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+wgrad_group_kernel(const __grid_constant__ WgGroup grp) {
+    pdl_trigger();
+    constexpr int BN = 128;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    using SM = TcSmem<BN>;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_STAGES * SM::STAGE);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + TC_STAGES;
+    uint64_t* acc_full = bars + 2 * TC_STAGES;
+    uint64_t* acc_empty = bars + 2 * TC_STAGES + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 4);
+    float* stage_t = reinterpret_cast<float*>(smem + TC_STAGES * SM::STAGE + 256);
+    uint8_t* ones = smem + TC_STAGES * SM::STAGE + 256 + SM::EPI;
+    constexpr uint32_t TMEM_COLS = tmem_cols_pow2(2 * BN + 2 * TC_CS_COLS);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x >= 64 && threadIdx.x < 64 + SM::ONES / 4) reinterpret_cast<uint32_t*>(ones)[threadIdx.x - 64] = 0x3F803F80u;
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], TC_EPI_WARPS); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
+    const int n_items = grp.n_items, np = grp.n_problems;
+    // item -> problem (items of a problem are contiguous; <= WG_MAXP problems: linear scan)
+    auto find = [&](int item) { int pi = 0; while (pi + 1 < np && item >= grp.p[pi + 1].item0) ++pi; return pi; };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int it = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const WgProblem& P = grp.p[find(item)];
+                const int loc = item - P.item0;
+                const int sp = loc / P.tiles_mn, tmn = loc - sp * P.tiles_mn;
+                const int m0 = (tmn / P.tiles_n) * TC_BM, n0 = (tmn % P.tiles_n) * BN;
+                const int kb0 = sp * P.kb_per_split, kb1 = min(P.num_kb, kb0 + P.kb_per_split);
+                const bool lo = grp.terms != 1;
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                    const int s = it % TC_STAGES;
+                    const uint32_t ph = (it / TC_STAGES) & 1;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    uint8_t* a_hi = smem + s * SM::STAGE;
+                    uint8_t* a_lo = a_hi + SM::A_TILE;
+                    uint8_t* b_hi = a_lo + SM::A_TILE;
+                    uint8_t* b_lo = b_hi + SM::B_TILE;
+                    mbar_arrive_expect_tx(&full[s], lo ? SM::STAGE : SM::STAGE / 2);
+                    const int kr = kb * TC_BK;
+#pragma unroll
+                    for (int rb = 0; rb < TC_BM / 64; ++rb) {
+                        tma_load_2d(a_hi + rb * TC_BOX, &P.a_hi, &full[s], m0 + rb * 64, kr);
+                        if (lo) tma_load_2d(a_lo + rb * TC_BOX, &P.a_lo, &full[s], m0 + rb * 64, kr);
+                    }
+#pragma unroll
+                    for (int rb = 0; rb < BN / 64; ++rb) {
+                        tma_load_2d(b_hi + rb * TC_BOX, &P.b_hi, &full[s], n0 + rb * 64, kr);
+                        if (lo) tma_load_2d(b_lo + rb * TC_BOX, &P.b_lo, &full[s], n0 + rb * 64, kr);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BN, true);
+            constexpr uint32_t kstep = 2048u, lbo = (uint32_t)TC_BOX;
+            int it = 0, ti = 0;
+            const uint64_t d_ones = make_sdesc_ones(smem_u32(ones));
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ti) {
+                const WgProblem& P = grp.p[find(item)];
+                const int loc = item - P.item0;
+                const int sp = loc / P.tiles_mn, tmn = loc - sp * P.tiles_mn;
+                const int kb0 = sp * P.kb_per_split, kb1 = min(P.num_kb, kb0 + P.kb_per_split);
+                const int buf = ti & 1;
+                mbar_wait(&acc_empty[buf], ((ti >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t tacc = tmem_base + (uint32_t)(buf * BN);
+                const bool cs_tile = P.colsum != nullptr && (tmn % P.tiles_n) == 0;
+                const uint32_t tcs = tmem_base + (uint32_t)(2 * BN + buf * TC_CS_COLS);
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                    const int s = it % TC_STAGES;
+                    const uint32_t ph = (it / TC_STAGES) & 1;
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    const uint32_t a_hi = smem_u32(smem + s * SM::STAGE);
+                    const uint32_t a_lo = a_hi + SM::A_TILE;
+                    const uint32_t b_hi = a_lo + SM::A_TILE;
+                    const uint32_t b_lo = b_hi + SM::B_TILE;
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 16; ++k) {
+                        const uint64_t dah = make_sdesc(a_hi + k * kstep, lbo), dal = make_sdesc(a_lo + k * kstep, lbo);
+                        const uint64_t dbh = make_sdesc(b_hi + k * kstep, lbo), dbl = make_sdesc(b_lo + k * kstep, lbo);
+                        const uint32_t first = (kb > kb0 || k > 0) ? 1u : 0u;
+                        if (grp.terms != 1) {
+                            umma_bf16(tacc, dal, dbh, idesc, first);
+                            umma_bf16(tacc, dah, dbl, idesc, 1);
+                            umma_bf16(tacc, dah, dbh, idesc, 1);
+                        } else {
+                            umma_bf16(tacc, dah, dbh, idesc, first);
+                        }
+                        if (cs_tile) {
+                            if (grp.terms != 1) {
+                                umma_bf16(tcs, dal, d_ones, make_idesc_colsum(), first);
+                                umma_bf16(tcs, dah, d_ones, make_idesc_colsum(), 1);
+                            } else {
+                                umma_bf16(tcs, dah, d_ones, make_idesc_colsum(), first);
+                            }
+                        }
+                    }
+                    umma_commit(&empty[s]);
+                }
+                umma_commit(&acc_full[buf]);
+            }
+        }
+    } else {
+        const int ew = warp - 2;
+        const int quarter = warp & 3;
+        const int half = ew >> 2;
+        int ti = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ti) {
+            const WgProblem& P = grp.p[find(item)];
+            const int loc = item - P.item0;
+            const int tmn = loc % P.tiles_mn;
+            const int m0 = (tmn / P.tiles_n) * TC_BM, n0 = (tmn % P.tiles_n) * BN;
+            const int buf = ti & 1;
+            mbar_wait(&acc_full[buf], (ti >> 1) & 1);
+            tc_fence_after();
+            const int mrow0 = m0 + quarter * 32;
+            const int m = mrow0 + lane;
+            const bool row_ok = m < P.M;
+            const uint32_t tb = smem_u32(stage_t + ew * (32 * TC_EPI_PITCH));
+            const uint32_t tb_row = tb + (uint32_t)lane * (TC_EPI_PITCH * 4);
+            const uint32_t sw_row = (uint32_t)(lane & 7);
+            const int srow = lane >> 3, sq = (lane & 7) * 4;
+            const uint32_t tb_st0 = tb + (uint32_t)srow * (TC_EPI_PITCH * 4) + ((((uint32_t)lane & 7) ^ ((uint32_t)srow & 7)) << 4);
+            const uint32_t tb_st1 = tb + (uint32_t)srow * (TC_EPI_PITCH * 4) + ((((uint32_t)lane & 7) ^ ((uint32_t)(srow + 4) & 7)) << 4);
+            const int rows_here = min(32, P.M - mrow0);
+            const long long row_step = 4LL * P.ldc;
+            float* c_row = P.C + (long long)(mrow0 + srow) * P.ldc;
+#pragma unroll 1
+            for (int cc = 0; cc < BN / TC_EPI_HALVES; cc += 32) {
+                const int c0 = half * (BN / TC_EPI_HALVES) + cc;
+                if (n0 + c0 >= P.N) break;                       // warp-uniform: nothing of this chunk exists
+                uint32_t r[32];
+                tmem_ld_32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN + c0), r);
+                tmem_ld_wait();
+                const int ncol = n0 + c0 + sq;
+                const bool col_ok = ncol < P.N;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    sts4(tb_row + ((((uint32_t)j >> 2) ^ sw_row) << 4),
+                         make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])));
+                __syncwarp();
+                float4 w[8];
+#pragma unroll
+                for (int it = 0; it < 8; ++it) w[it] = lds4(((it & 1) ? tb_st1 : tb_st0) + it * (4 * TC_EPI_PITCH * 4));
+                if (col_ok) {
+                    float* cp = c_row + ncol;
+#pragma unroll
+                    for (int it = 0; it < 8; ++it)
+                        if (srow + 4 * it < rows_here) red_add_v4(cp + it * row_step, w[it]);
+                }
+                __syncwarp();
+            }
+            if (P.colsum != nullptr && half == 0 && n0 == 0) {
+                const uint32_t v = tmem_ld_1(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(2 * BN + buf * TC_CS_COLS));
+                tmem_ld_wait();
+                if (row_ok) red_add_f32(P.colsum + m, __uint_as_float(v));
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+bool wgrad_group_takes(int M, int N, int K, long long ldc, const void* C) {
+    return M >= 64 && N > 64 && (N % 4) == 0 && K >= 64 && (ldc % 4) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0;
+}
+
+int launch_wgrad_group(const WgradItem* items, int n, int terms, cudaStream_t st) {
+    if (n <= 0) return 0;
+    RIFT_REQUIRE(n <= WG_MAXP, "wgrad_group: too many products for one launch");
+    static bool attr = false;
+    static int sms = 148;
+    if (!attr) {
+        RIFT_CUDA_OK(cudaFuncSetAttribute(wgrad_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<128>::TOTAL));
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        attr = true;
+    }
+    WgGroup g;
+    memset(&g, 0, sizeof(g));
+    long long kb_tiles = 0;
+    for (int i = 0; i < n; ++i) {
+        const WgradItem& w = items[i];
+        RIFT_REQUIRE(wgrad_group_takes(w.M, w.N, w.K, w.ldc, w.C), "wgrad_group: product not eligible");
+        RIFT_REQUIRE(w.A.pitch % 64 == 0 && w.B.pitch % 64 == 0 && w.A.mn0 == 0 && w.A.k0 == 0 && w.B.mn0 == 0 && w.B.k0 == 0,
+                     "wgrad_group: operand planes must start at the origin with a pitch that is a multiple of 64");
+        kb_tiles += (long long)cdiv(w.M, TC_BM) * cdiv(w.N, 128) * cdiv(w.K, TC_BK);
+    }
+    // k-blocks per work item: about two items per CTA over the whole group (measured: 2 -> 8.44, 4 -> 8.46, 8 -> 8.51 ms per step),
+    // at least 2 and at most 16 k-blocks each
+    static const int per_cta = [] { const char* e = getenv("RIFT_B200_WGRAD_GROUP_ITEMS"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 2; }();
+    int kbs = (int)((kb_tiles + (long long)sms * per_cta - 1) / ((long long)sms * per_cta));
+    kbs = kbs < 2 ? 2 : (kbs > 16 ? 16 : kbs);
+    int item0 = 0;
+    for (int i = 0; i < n; ++i) {
+        const WgradItem& w = items[i];
+        WgProblem& P = g.p[i];
+        const CUtensorMap* mp;
+        int r;
+        if ((r = plane_map(w.A.hi, w.A.rows, w.A.pitch, &mp))) return r; P.a_hi = *mp;
+        if ((r = plane_map(w.A.lo, w.A.rows, w.A.pitch, &mp))) return r; P.a_lo = *mp;
+        if ((r = plane_map(w.B.hi, w.B.rows, w.B.pitch, &mp))) return r; P.b_hi = *mp;
+        if ((r = plane_map(w.B.lo, w.B.rows, w.B.pitch, &mp))) return r; P.b_lo = *mp;
+        P.C = w.C; P.colsum = w.colsum; P.ldc = w.ldc;
+        P.M = w.M; P.N = w.N; P.K = w.K;
+        P.tiles_n = cdiv(w.N, 128);
+        P.tiles_mn = P.tiles_n * cdiv(w.M, TC_BM);
+        P.num_kb = cdiv(w.K, TC_BK);
+        P.kb_per_split = min(kbs, P.num_kb);
+        P.item0 = item0;
+        item0 += P.tiles_mn * cdiv(P.num_kb, P.kb_per_split);
+    }
+    g.n_problems = n; g.n_items = item0; g.terms = terms == 1 ? 1 : 3;
+    launch_k(wgrad_group_kernel, min(item0, sms), TC_THREADS, TcSmem<128>::TOTAL, st, g);
+    RIFT_LAUNCH_OK();
+    return 0;
 }
 
 int launch_gemm_tc(const GemmArgs& a, const void* a_hi, const void* a_lo, int Kp, const TcWeight& w, int n0, int k0,

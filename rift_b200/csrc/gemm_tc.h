@@ -19,6 +19,12 @@ struct TcWeight {
 struct PlaneOp { const void* hi; const void* lo; int rows; int pitch; int mn0; int k0; };
 
 inline int tc_pitch(int K) { return (K + 63) / 64 * 64; }
+// One product of a grouped weight-gradient launch: C[M, N] += A^T B over K rows (A = dY planes [K, >= M], B = X planes [K, >= N]),
+// colsum[M] += column sums of A (bias gradient; may be null)
+struct WgradItem { PlaneOp A, B; float* C; long long ldc; float* colsum; int M, N, K; };
+bool wgrad_group_takes(int M, int N, int K, long long ldc, const void* C);
+constexpr int WGRAD_GROUP_MAX = 12;
+int launch_wgrad_group(const WgradItem* items, int n, int terms, cudaStream_t st);      // n <= WGRAD_GROUP_MAX
 bool gemm_tc_shape_ok(int M, int N, int K);
 bool gemm_tc_eligible(const GemmArgs& a);
 // fp32 [M, K] -> bf16 planes hi / lo [M, Kp] (each M * Kp * 2 bytes, 256 B aligned)

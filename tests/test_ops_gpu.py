@@ -97,6 +97,31 @@ def test_wgrad_tcgen05_atomic_accumulate_and_bias(rows, N, K, splits):
     close(db, db0.double() + dY.double().sum(0), 3e-5, "db")
 
 
+@pytest.mark.parametrize("shapes", [[(4608, 256, 256), (4608, 768, 256), (3328, 256, 1024), (4608, 1024, 256), (3328, 512, 256), (4608, 256, 256)],
+                                    [(100, 64, 128)], [(20480, 384, 128), (64, 256, 256), (1000, 100, 132)],
+                                    [(1024 + 64 * i, 128 + 64 * (i % 3), 128 + 128 * (i % 2)) for i in range(12)]])
+def test_wgrad_grouped_launch(shapes):
+    """Up to twelve dW += dY^T X (+ db += colsum(dY)) products of different shapes in ONE persistent launch (wgrad_group_kernel):
+    every product against fp64, on top of non-zero running sums, 3e-5 of the result's scale."""
+    import ctypes as C
+    n = len(shapes)
+    L = _lib.lib()
+    dYs = [rnd(r, N, seed=20 + i) for i, (r, N, K) in enumerate(shapes)]
+    Xs = [rnd(r, K, seed=40 + i) for i, (r, N, K) in enumerate(shapes)]
+    dW0 = [rnd(N, K, seed=60 + i) for i, (r, N, K) in enumerate(shapes)]
+    db0 = [rnd(N, seed=80 + i) for i, (r, N, K) in enumerate(shapes)]
+    dW, db = [t.clone() for t in dW0], [t.clone() for t in db0]
+    total = sum(L.rift_b200_op_wgrad_tc_scratch_bytes(r, N, K) for r, N, K in shapes)
+    scratch = torch.empty(total, dtype=torch.uint8, device="cuda")
+    vp = lambda ts: (C.c_void_p * n)(*[t.data_ptr() for t in ts])
+    ia = lambda xs: (C.c_int * n)(*xs)
+    _lib.check(L.rift_b200_op_wgrad_group(n, vp(dYs), vp(Xs), ia([s_[0] for s_ in shapes]), ia([s_[1] for s_ in shapes]),
+                                          ia([s_[2] for s_ in shapes]), vp(dW), vp(db), P(scratch), scratch.numel(), S()))
+    for i in range(n):
+        close(dW[i], dW0[i].double() + dYs[i].double().t() @ Xs[i].double(), 3e-5, f"dW[{i}]")
+        close(db[i], db0[i].double() + dYs[i].double().sum(0), 3e-5, f"db[{i}]")
+
+
 @pytest.mark.parametrize("layout", ["nt", "nn", "tn", "tt"])
 @pytest.mark.parametrize("M,N,K,split", [(65, 70, 33, 1), (256, 192, 4000, 8), (1, 256, 4608, 9)])
 def test_gemm_strides_and_split_k(layout, M, N, K, split):
