@@ -1069,7 +1069,8 @@ static bool tc2_takes(const GemmArgs& a, int BN, int sms) {
     const int b_bytes = num_kb * 2 * BN * TC_BK * 2;
     const int stages_fit = (227 * 1024 - 1024 - 256 - TC2_EPI_BYTES - b_bytes) / TC2_A_STAGE;
     static const int min_stages = [] { const char* e = getenv("RIFT_B200_GEMM_V2_MIN_STAGES"); return e ? atoi(e) : 3; }();
-    return a.terms != 1 && tiles >= 2LL * sms && stages_fit >= min_stages && a.alpha == 1.f && (a.beta == 0.f || a.beta == 1.f) && !a.dact_ref && a.n_store <= 0 &&
+    static const int min_waves = [] { const char* e = getenv("RIFT_B200_GEMM_V2_MIN_WAVES"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 2; }();
+    return a.terms != 1 && tiles >= (long long)min_waves * sms && stages_fit >= min_stages && a.alpha == 1.f && (a.beta == 0.f || a.beta == 1.f) && !a.dact_ref && a.n_store <= 0 &&
            cdiv(a.N, BN) <= sms;
 }
 
