@@ -58,6 +58,9 @@ inline int flush_wgrads(Ctx& c) {
     const int n = c.n_pending;
     c.n_pending = 0;
     if (c.dry) return 0;
+    // MEASUREMENT ONLY (results are wrong): drop the grouped weight gradients to see what the step costs without them
+    static const bool skip = [] { const char* e = getenv("RIFT_B200_DEBUG_SKIP_WGRAD"); return e && atoi(e) != 0; }();
+    if (skip) return 0;
     cudaStream_t to = c.side ? c.side : c.pending_stream;
     if (to != c.pending_stream) {
         cudaEvent_t e = c.next_event();

@@ -1496,7 +1496,13 @@ int launch_wgrad_group(const WgradItem* items, int n, int terms, cudaStream_t st
         item0 += P.tiles_mn * cdiv(P.num_kb, P.kb_per_split);
     }
     g.n_problems = n; g.n_items = item0; g.terms = terms == 1 ? 1 : 3;
-    launch_k(wgrad_group_kernel, min(item0, sms), TC_THREADS, TcSmem<128>::TOTAL, st, g);
+    // grid: one persistent CTA per SM walking the queue, or (RIFT_B200_WGRAD_GROUP_ONESHOT=1) one CTA per work item - short-lived
+    // CTAs hand their SM back after every item, so a higher-priority stream gets in between
+    static const bool oneshot = [] { const char* e = getenv("RIFT_B200_WGRAD_GROUP_ONESHOT"); return e && atoi(e) != 0; }();
+    static const int grid_cap = [] { const char* e = getenv("RIFT_B200_WGRAD_GROUP_CTAS"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 0; }();
+    int grid = oneshot ? item0 : min(item0, sms);
+    if (grid_cap > 0 && !oneshot) grid = min(grid, grid_cap);
+    launch_k(wgrad_group_kernel, grid, TC_THREADS, TcSmem<128>::TOTAL, st, g);
     RIFT_LAUNCH_OK();
     return 0;
 }

@@ -343,7 +343,10 @@ class LightningTrainer:
             self.configure_optimizers()
         self.model.params_updated(trainable_only=True)   # the re-split of the trainable weight planes is part of the graph
         graph = torch.cuda.CUDAGraph()
-        cap = torch.cuda.Stream(device=dev)
+        # RIFT_B200_STREAM_PRIO=1 (experiment, measured neutral): the capture stream - the step's main chain - gets a high
+        # priority and the engine's side stream (parameter gradients) the lowest, see engine.cu::attach_streams
+        prio = -1 if os.environ.get("RIFT_B200_STREAM_PRIO", "0") == "1" else 0
+        cap = torch.cuda.Stream(device=dev, priority=prio)
         cap.wait_stream(torch.cuda.current_stream(dev))
         count = None
         # thread_local: NCCL's watchdog thread keeps querying events while the data-parallel all-reduce is captured

@@ -191,6 +191,34 @@ def test_three_policy_updates_match_reference_parameters():
                 assert err.size == 0 or err.max() <= 0.05 * 1e-4, (key, err.max())
 
 
+@pytest.mark.parametrize("through", ["trainer", "model"])
+def test_state_dict_load_after_graph_capture_takes_effect(through):
+    """A captured step graph reads frozen weights through pre-split planes: loading a checkpoint AFTER the graph exists must
+    change what the next step computes (trainer.load_state_dict drops the graphs, PlanningModel.load_state_dict re-splits every
+    plane), frozen layers included."""
+    cfg, sd, feats, ex = case_inputs("cfg1_small")
+    model = build(cfg, sd)
+    tr = TRAINERS["grpo"](model, trainable_layers=["planning_decoder.pi_head"], **TRAINER_KW)
+    tr.configure_optimizers()
+    batch = make_batch(feats, ex)
+    for _ in range(3):                                   # the second call captures, the third replays
+        tr.step(batch)
+    sd2 = {k: (v * 1.05 + 0.01).astype(v.dtype) if v.dtype.kind == "f" else v for k, v in sd.items()}
+    t2 = {k: torch.from_numpy(v) for k, v in sd2.items()}
+    if through == "trainer":
+        tr.load_state_dict({"model." + k: v for k, v in t2.items()})
+    else:
+        model.load_state_dict(t2)
+    got = [float(tr.step(batch)) for _ in range(2)][0]   # first step after the load: eager or replay, must use the new weights
+    fresh = build(cfg, sd2)
+    tr2 = TRAINERS["grpo"](fresh, trainable_layers=["planning_decoder.pi_head"], **TRAINER_KW)
+    tr2.configure_optimizers()
+    want = float(tr2.step(batch))
+    stale = float(TRAINERS["grpo"](build(cfg, sd), trainable_layers=["planning_decoder.pi_head"], **TRAINER_KW).training_step(batch))
+    assert abs(got - want) <= 1e-5 * max(abs(want), 1e-3), (got, want)
+    assert abs(want - stale) > 1e-3 * max(abs(want), 1e-3), "the two checkpoints must differ for the test to mean anything"
+
+
 def test_state_dict_roundtrip_and_prefixed_checkpoint():
     cfg, sd, _, _ = case_inputs("cfg1_small")
     model = build(cfg, sd)
