@@ -81,6 +81,7 @@ struct TcKernelArgs {
     float* colsum;           // MN-major (dW = dY^T X) only: colsum[m] += sum_k A[k, m] (bias gradient), from the tensor core
     int terms;               // 3: split-bf16 x3 (A_lo B_hi + A_hi B_lo + A_hi B_hi); 1: plain bf16 (hi planes only: a third of the
                              // MMA work, half the operand bytes) - backward products whose tolerance allows it
+    int late;                // issue griddepcontrol.launch_dependents after the last tile's MMAs (RIFT_B200_PDL_LATE)
     int dbg;                 // bottleneck experiments only (RIFT_B200_TC_DBG)
     unsigned long long* trace;   // profiling aid (rift_b200_debug_gemm_trace): CTA 0 writes %globaltimer stamps
 };
@@ -91,6 +92,18 @@ __device__ __forceinline__ unsigned long long gtimer() {
     return t;
 }
 #define TC_TRACE(slot) do { if (g.trace && blockIdx.x == 0) g.trace[(slot)] = gtimer(); } while (0)
+
+// Late programmatic-launch trigger: once a CTA has ISSUED the MMAs of its last tile only the epilogue of that tile is left, so
+// the stream's next kernel may be scheduled now - its launch latency and set-up then overlap our epilogue and tear-down; it
+// still waits in griddepcontrol.wait for this grid to complete, so memory ordering is unchanged.  (Triggering at kernel START
+// was measured slower: dependents park on SMs the later waves of this grid and the other streams need.)
+__device__ __forceinline__ void pdl_trigger_late(int on) {
+    if (on) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+static int tc_late_trigger() {
+    static const int v = [] { const char* e = getenv("RIFT_B200_PDL_LATE"); return (e && atoi(e) == 0) ? 0 : 1; }();
+    return v;
+}
 
 template <int BN>
 struct TcSmem {
@@ -275,6 +288,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 umma_commit(&acc_full[buf]);
                 if (ti == 0) TC_TRACE(3);
             }
+            pdl_trigger_late(g.late);
         }
     } else {
         // ===================== epilogue (8 warps) =====================
@@ -645,6 +659,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                 }
                 umma_commit(&acc_full[buf]);
             }
+            pdl_trigger_late(g.late);
         }
     } else {
         // ===================== epilogue (8 warps) =====================
@@ -1109,7 +1124,7 @@ static int launch_tc2(const GemmArgs& a, const PlaneOp& A, const PlaneOp& B, cud
     g.M = a.M; g.N = a.N; g.K = a.K;
     g.a_mn0 = A.mn0; g.a_k0 = A.k0; g.b_mn0 = B.mn0; g.b_k0 = B.k0;
     g.out = a.out_planes;
-    g.trace = nullptr; g.dbg = 0; g.atomic = 0; g.n_store = 0; g.colsum = nullptr; g.terms = 3;
+    g.trace = nullptr; g.dbg = 0; g.atomic = 0; g.n_store = 0; g.colsum = nullptr; g.terms = 3; g.late = tc_late_trigger();
     g.splits = 1; g.kb_per_split = num_kb; g.split_stride = 0;
     g.C = a.C; g.ldc = a.ldc;
     g.ep = TcEpilogue{a.bias, a.colscale, a.pre, a.ldpre, a.pre_div, a.res, a.ldres, a.res_div, a.res_mod, a.act, a.beta,
@@ -1155,7 +1170,7 @@ static int launch_tc(const GemmArgs& a, const PlaneOp& A, const PlaneOp& B, int 
     g.M = a.M; g.N = a.N; g.K = a.K;
     g.a_mn0 = A.mn0; g.a_k0 = A.k0; g.b_mn0 = B.mn0; g.b_k0 = B.k0;
     g.out = a.out_planes;
-    g.trace = g_tc_trace;
+    g.trace = g_tc_trace; g.late = tc_late_trigger();
     { static int dbg = -1; if (dbg < 0) { const char* e = getenv("RIFT_B200_TC_DBG"); dbg = e ? atoi(e) : 0; } g.dbg = dbg; }
     const bool via_ws = !a.atomic_out && (splits > 1 || a.n_store > 0);       // raw sums into the partial buffer, epilogue in the reduce
     g.atomic = 0; g.n_store = 0; g.colsum = nullptr; g.terms = a.terms == 1 ? 1 : 3;
@@ -1254,7 +1269,7 @@ struct alignas(64) WgProblem {
 };
 struct alignas(64) WgGroup {
     WgProblem p[WG_MAXP];
-    int n_problems, n_items, terms, pad_[13];
+    int n_problems, n_items, terms, late, pad_[12];
 };
 static_assert(sizeof(WgGroup) <= 8192, "grouped weight-gradient parameters");
 
@@ -1376,6 +1391,7 @@ wgrad_group_kernel(const __grid_constant__ WgGroup grp) {
                 }
                 umma_commit(&acc_full[buf]);
             }
+            pdl_trigger_late(grp.late);
         }
     } else {
         const int ew = warp - 2;
@@ -1495,7 +1511,7 @@ int launch_wgrad_group(const WgradItem* items, int n, int terms, cudaStream_t st
         P.item0 = item0;
         item0 += P.tiles_mn * cdiv(P.num_kb, P.kb_per_split);
     }
-    g.n_problems = n; g.n_items = item0; g.terms = terms == 1 ? 1 : 3;
+    g.n_problems = n; g.n_items = item0; g.terms = terms == 1 ? 1 : 3; g.late = tc_late_trigger();
     // grid: one persistent CTA per SM walking the queue, or (RIFT_B200_WGRAD_GROUP_ONESHOT=1) one CTA per work item - short-lived
     // CTAs hand their SM back after every item, so a higher-priority stream gets in between
     static const bool oneshot = [] { const char* e = getenv("RIFT_B200_WGRAD_GROUP_ONESHOT"); return e && atoi(e) != 0; }();
