@@ -323,8 +323,7 @@ attention_bwd3_kernel(AttnArgs a, const float* __restrict__ d_o, long long lddo,
     float* Ps = Vs + (size_t)Sk4 * AB_PITCH;             // [Sq4][SkP]
     float* dSs = Ps + (size_t)Sq4 * SkP;                 // [Sq4][SkP]  dP, then dS
     float* lse_s = dSs + (size_t)Sq4 * SkP;              // [Sq4]
-    float* delta = lse_s + Sq4;                          // [Sq4]
-    uint8_t* msk = reinterpret_cast<uint8_t*>(delta + Sq4);   // [Sk4]
+    uint8_t* msk = reinterpret_cast<uint8_t*>(lse_s + 2 * Sq4);   // [Sk4]  (one spare row of Sq4 floats in between)
     const int t = threadIdx.x;
     const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
     const long long krow0 = attn_row_b(b, a.k_inner_n, a.k_outer, a.k_inner);
