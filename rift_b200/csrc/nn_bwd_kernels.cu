@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(512)
 attention_bwd2_kernel(AttnArgs a, const float* __restrict__ d_o, long long lddo, float* __restrict__ dq, long long lddq,
                       float* __restrict__ dk, float* __restrict__ dv, long long lddk, long long lddv, int PB, int tpp, Planes pq, Planes pk,
                       Planes pv) {
-    pdl_grid_sync();
+    pdl_grid_sync_sel();
     constexpr int HD = 32, CPL = HD / G;
     extern __shared__ __align__(16) float sm[];
     const int Sq = a.Sq, Sk = a.Sk, Skp = Sk | 1;
@@ -312,7 +312,7 @@ __device__ __forceinline__ float dot4(const float4 a, const float4 b, float acc)
 __global__ void __launch_bounds__(256, 3)
 attention_bwd3_kernel(AttnArgs a, const float* __restrict__ d_o, long long lddo, float* __restrict__ dq, long long lddq,
                       float* __restrict__ dk, float* __restrict__ dv, long long lddk, long long lddv, Planes pq, Planes pk, Planes pv) {
-    pdl_grid_sync();
+    pdl_grid_sync_sel();
     constexpr int HD = 32, T = 256;
     extern __shared__ __align__(16) float sm[];
     const int Sq = a.Sq, Sk = a.Sk, Sq4 = (Sq + 3) & ~3, Sk4 = (Sk + 3) & ~3, SkP = attn_bwd3_skp(Sk);

@@ -63,7 +63,7 @@ layernorm4_kernel(const float* __restrict__ x, long long ldx, int rows, int C, c
                   const float* __restrict__ beta, float* __restrict__ y, long long ldy, int relu,
                   const float* __restrict__ add_rowmod, int rowmod, float* __restrict__ y2, float* __restrict__ mean_out,
                   float* __restrict__ rstd_out, Planes yp, Planes y2p) {
-    pdl_grid_sync();
+    pdl_grid_sync_sel();
     constexpr int RPW = 32 / LPR;                     // rows per warp
     constexpr int NV = LPR == 32 ? 8 : 1;             // float4 groups per lane (narrow rows: C <= 4 * LPR)
     const int lane = threadIdx.x & 31;
@@ -262,7 +262,7 @@ layernorm_bwd4_kernel(const float* __restrict__ x, long long ldx, const float* _
                       const float* __restrict__ y_relu, long long ldy, float* __restrict__ dx, long long lddx,
                       int dx_accumulate, float* __restrict__ partial /*[grid][2][C]*/, float* __restrict__ dgamma_atomic,
                       float* __restrict__ dbeta_atomic, Planes dxp, const uint8_t* __restrict__ zero_flag, int zero_div) {
-    pdl_grid_sync();
+    pdl_grid_sync_sel();
     extern __shared__ float sm[];      // [8 warps][2][C]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int C4 = C >> 2;
@@ -645,7 +645,7 @@ __host__ __device__ inline size_t attn_fwd2_smem_floats(int Sq, int Sk) {
 template <int G>
 __global__ void __launch_bounds__(512)
 attention2_kernel(AttnArgs a, int PB, int tpp) {
-    pdl_grid_sync();
+    pdl_grid_sync_sel();
     constexpr int HD = 32, CPL = HD / G;
     extern __shared__ __align__(16) float sm[];
     const int Sq = a.Sq, Sk = a.Sk;
@@ -734,7 +734,7 @@ __host__ __device__ inline size_t attn_fwd3_smem_floats(int Sq, int Sk) {
 }
 __global__ void __launch_bounds__(256, 3)
 attention3_kernel(AttnArgs a) {
-    pdl_grid_sync();
+    pdl_grid_sync_sel();
     constexpr int HD = 32, T = 256;
     extern __shared__ __align__(16) float sm[];
     const int Sq = a.Sq, Sk = a.Sk, Sq4 = (Sq + 3) & ~3, Sk4 = (Sk + 3) & ~3, SkP = attn_fwd3_skp(Sk);
@@ -1632,7 +1632,7 @@ __device__ __forceinline__ void split4_flat(uint2* __restrict__ hi, uint2* __res
 }
 __global__ void __launch_bounds__(256)
 act_bwd4_kernel(const float4* __restrict__ ref, float4* __restrict__ dy, long long n4, int act, uint2* __restrict__ hi, uint2* __restrict__ lo) {
-    pdl_grid_sync();
+    pdl_grid_sync_sel();
     const long long stride = (long long)gridDim.x * 256;
     long long e = (long long)blockIdx.x * 256 + threadIdx.x;
     for (; e + stride < n4; e += 2 * stride) {            // two independent 16-byte streams per thread in flight
