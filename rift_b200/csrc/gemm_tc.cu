@@ -795,7 +795,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
 __global__ void __launch_bounds__(256)
 pack_split_kernel(const float* __restrict__ src, long long ld, int M, int K, int Kp, __nv_bfloat16* __restrict__ hi,
                   __nv_bfloat16* __restrict__ lo, int vec) {
-    pdl_grid_sync();
+    pdl_grid_sync_sel();
     const int kq = Kp >> 2;
     const long long total = (long long)M * kq;
     for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
