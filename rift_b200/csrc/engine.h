@@ -101,7 +101,9 @@ struct Ctx {            // per-call state: stream + bump allocator over the call
     }
     bool planes_for(int C) const { return !simt && C >= 32; }
     // weight-gradient products waiting for a grouped launch (engine_ops.h::flush_wgrads); `pending_stream` produced their operands
-    WgradItem pending[WGRAD_GROUP_MAX]; int n_pending = 0; cudaStream_t pending_stream = nullptr;
+    // (two queues: products whose operands were produced on the caller's stream / on the branch stream - a queue is ordered
+    //  after ONE stream, and alternating between the two would cut the groups short)
+    WgradItem pending[2][WGRAD_GROUP_MAX]; int n_pending[2] = {0, 0}; cudaStream_t pending_stream[2] = {nullptr, nullptr};
     // fp32 gradient buffers that the main chain keeps updating in place (residual-stream gradients): kernels moved to
     // another stream must not read them.  Everything else the backward allocates is written once (bump allocator).
     const void* inplace_bufs[12] = {}; int n_inplace = 0;

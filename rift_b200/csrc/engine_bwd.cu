@@ -147,7 +147,7 @@ static int mlp_tail_bwd(Ctx& c, int rows, int D, int Hd, const Act& hm, const fl
 int rift_b200_engine::backward(const rift_b200_batch& bt, const float* dlogits, Ctx& c) {
     TRY(attach_streams(c));
     int r = backward_impl(bt, dlogits, c);
-    if (r) { c.n_pending = 0; return r; }
+    if (r) { c.n_pending[0] = c.n_pending[1] = 0; return r; }
     TRY(flush_wgrads(c));                        // the last queued weight-gradient products
     // parameter-gradient work (side stream) and the parameter-only branches rejoin the caller's stream here
     TRY(join_from(c, c.br));

@@ -53,21 +53,26 @@ inline int wgrad_group_size() {
     return n;
 }
 inline int bwd_terms();
-inline int flush_wgrads(Ctx& c) {
-    if (c.n_pending == 0) return 0;
-    const int n = c.n_pending;
-    c.n_pending = 0;
+inline int flush_wgrads(Ctx& c, int q) {
+    if (c.n_pending[q] == 0) return 0;
+    const int n = c.n_pending[q];
+    c.n_pending[q] = 0;
     if (c.dry) return 0;
     // MEASUREMENT ONLY (results are wrong): drop the grouped weight gradients to see what the step costs without them
     static const bool skip = [] { const char* e = getenv("RIFT_B200_DEBUG_SKIP_WGRAD"); return e && atoi(e) != 0; }();
     if (skip) return 0;
-    cudaStream_t to = c.side ? c.side : c.pending_stream;
-    if (to != c.pending_stream) {
+    cudaStream_t from = c.pending_stream[q];
+    cudaStream_t to = c.side ? c.side : from;
+    if (to != from) {
         cudaEvent_t e = c.next_event();
-        RIFT_CUDA_OK(cudaEventRecord(e, c.pending_stream));
+        RIFT_CUDA_OK(cudaEventRecord(e, from));
         RIFT_CUDA_OK(cudaStreamWaitEvent(to, e, 0));
     }
-    return launch_wgrad_group(c.pending, n, bwd_terms(), to);
+    return launch_wgrad_group(c.pending[q], n, bwd_terms(), to);
+}
+inline int flush_wgrads(Ctx& c) {
+    TRY(flush_wgrads(c, 0));
+    return flush_wgrads(c, 1);
 }
 // launches inside the scope go to `s` (when non-null)
 struct OnStream {
@@ -394,14 +399,15 @@ inline int lin_bwd(Ctx& c, const float* X, long long ldx, const float* dY, long 
         float* ws = nullptr;
         if (!atomic_w && (splits > 1 || w_padded)) { ws = c.alloc<float>((size_t)splits * L.N * Kpad4); if (!ws) { set_last_error("workspace too small"); return -1; } }
         if (!c.dry && wgrad_group_on() && atomic_w && !w_padded && wgrad_group_takes(L.N, L.K, M, L.ldw, L.dW)) {
-            if (c.n_pending && c.pending_stream != c.st) TRY(flush_wgrads(c));
-            c.pending_stream = c.st;
-            WgradItem& w = c.pending[c.n_pending++];
+            const int q = (c.br != nullptr && c.st == c.br) ? 1 : 0;
+            if (c.n_pending[q] && c.pending_stream[q] != c.st) TRY(flush_wgrads(c, q));
+            c.pending_stream[q] = c.st;
+            WgradItem& w = c.pending[q][c.n_pending[q]++];
             w.A = PlaneOp{dYp.hi, dYp.lo, M, dYp.Kp, 0, 0};
             w.B = PlaneOp{xp.hi, xp.lo, M, xp.Kp, 0, 0};
             w.C = L.dW; w.ldc = L.ldw; w.colsum = b_in_wgrad ? L.db : nullptr;
             w.M = L.N; w.N = L.K; w.K = M;
-            if (c.n_pending == wgrad_group_size()) TRY(flush_wgrads(c));
+            if (c.n_pending[q] == wgrad_group_size()) TRY(flush_wgrads(c, q));
         } else if (!c.dry) {
             if (!forked) TRY(fork_to(c, c.side));
             OnStream on(c, c.side);
