@@ -150,6 +150,51 @@ def make_batch_dict(feats_t, ex_t):
     return b
 
 
+def device_buffer_leg(tr, feats, ex, wl, args, sync):
+    """Fills a DeviceRolloutBuffer with 2 x bs transitions cut from the workload's scenes (one CBV trajectory, stored through the
+    reference's store() protocol) and times sample-indices -> collate_device -> step -> loss."""
+    from rift_b200.buffer import DeviceRolloutBuffer
+    from rift_b200.feature import PlutoFeature
+    bs = wl["bs"]
+    keys = ["CBVs_actions", "CBVs_actions_old_group_logits", "CBVs_actions_ref_group_logits", "CBVs_group_advantage", "CBVs_obs",
+            "CBVs_next_obs", "CBVs_reward", "CBVs_terminated", "CBVs_done"]
+    cap = 2 * bs
+    buf = DeviceRolloutBuffer(1, "train_cbv", {"buffer_capacity": cap, "data_keys": keys})
+    dd = {k: [] for k in keys}
+    dd["CBV_ids"] = []
+    n = cap + 1
+    for t in range(n):
+        i = t % bs
+        d = {k: ({kk: vv[i] for kk, vv in v.items()} if isinstance(v, dict) else v[i]) for k, v in feats.items()}
+        f = PlutoFeature(data=d)
+        vm = np.asarray(ex["group_advantage_mask"][i], bool)
+        tr_ = {"CBVs_actions": (0.1, 0.0, False), "CBVs_obs": {"raw_pluto_feature": f}, "CBVs_next_obs": {"raw_pluto_feature": f},
+               "CBVs_group_advantage": {"advantage": ex["group_advantage"][i], "valid_mask": vm},
+               "CBVs_actions_old_group_logits": {"logits": ex["old_group_logits"][i], "valid_mask": vm},
+               "CBVs_actions_ref_group_logits": {"logits": ex["ref_group_logits"][i], "valid_mask": vm},
+               "CBVs_reward": np.float32(0.0), "CBVs_terminated": np.float32(0.0), "CBVs_done": t == n - 1}
+        dd["CBV_ids"].append([0])
+        for k in keys:
+            dd[k].append({0: tr_[k]})
+    buf.store(dd)
+    assert buf.buffer_full and len(buf) == cap
+    rng = np.random.Generator(np.random.PCG64(3))
+
+    def one():
+        idx = rng.permutation(cap)[:bs]
+        return float(tr.step(buf.collate_device(idx.tolist(), "grpo")))
+    for _ in range(max(min(args.warmup, 5), 3)):
+        one()
+    sync()
+    ts = []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        one()
+        ts.append((time.perf_counter() - t0) * 1e3)
+    sync()
+    return float(np.median(ts)), bs * 8
+
+
 def pick_workload(args):
     """BASELINE.json configs by GPU count (see the module docstring)."""
     name = args.workload
@@ -413,6 +458,17 @@ def run_ours(args):
     sync()
     e2e_ms = float(np.median(e2e_t))
 
+    # ---- end to end from the device-resident replay buffer: the scenes live in the buffer's device arenas
+    # (as they would after a rollout), a step = draw 64 slot indices on the host -> ONE gather launch builds the batch -> step ->
+    # loss on the host.  Host-to-device traffic: the index vector.
+    devbuf_ms, devbuf_h2d = 0.0, 0
+    if world == 1 and not args.no_devbuf:
+        try:
+            feats_np, ex_np = host_batch(cfg, wl, seed=1)
+            devbuf_ms, devbuf_h2d = device_buffer_leg(tr, feats_np, ex_np, wl, args, sync)
+        except Exception as e:                                   # a secondary record must not cost the headline line
+            print(f"device-buffer leg failed: {e!r}", file=sys.stderr)
+
     # ---- secondary leg at N > 1: weak scaling (every rank its own full batch)
     weak = None
     if world > 1 and scaling == "strong" and not args.no_weak:
@@ -461,6 +517,10 @@ def run_ours(args):
                               "mma_work_factor": 3, "peak_source": src},
             "kernels": kern,
         }
+        if devbuf_ms > 0:
+            line["e2e_device_buffer"] = {"value": (wl["bs"] / 64.0) * 1e3 / devbuf_ms, "unit": UNIT, "ms_per_step": devbuf_ms,
+                                         "h2d_bytes_per_step": devbuf_h2d, "d2h_bytes_per_step": 8,
+                                         "path": "DeviceRolloutBuffer.collate_device (rift_b200_gather_fields) -> trainer.step"}
         if weak_ms > 0:
             line["weak_scaling"] = {"value": world * (wl["bs"] / 64.0) * 1e3 / weak_ms, "unit": UNIT, "ms_per_step": weak_ms,
                                     "global_batch": wl["bs"] * world}
@@ -513,6 +573,7 @@ def main():
     ap.add_argument("--no-cpu", dest="no_cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-weak", dest="no_weak", action="store_true", help="skip the secondary weak-scaling leg at N > 1")
     ap.add_argument("--no-kernels", dest="no_kernels", action="store_true", help="skip the per-kernel roofline legs")
+    ap.add_argument("--no-devbuf", dest="no_devbuf", action="store_true", help="skip the device-resident replay-buffer end-to-end leg")
     ap.add_argument("--no-graph", dest="no_graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     args = ap.parse_args()
     if args.impl == "reference":
