@@ -81,6 +81,11 @@ class DeviceRolloutBuffer:
         self._arena: Dict[str, torch.Tensor] = {}     # device mirror, allocated at the first store
         self._extent = {k: np.zeros(self.buffer_capacity, np.int32) for k in ("A", "Mp", "R")}
         self._extra_dev: Dict[str, torch.Tensor] = {}
+        self._collate_cache: Dict[tuple, dict] = {}   # staged outputs of collate_device per (algo, bs, extents)
+        self._arena_gen = 0                           # bumped whenever an arena tensor is (re)allocated: cached field tables hold its pointers
+
+    def _arena_generation(self):
+        return self._arena_gen
 
     def __len__(self):
         return self.buffer_capacity if self.buffer_full else self.buffer_pos
@@ -145,6 +150,7 @@ class DeviceRolloutBuffer:
     # ------------------------------------------------------------------ device mirror
     def _alloc(self, name, cap, trailing, dtype):
         self._arena[name] = torch.zeros((self.buffer_capacity, cap) + tuple(trailing), dtype=dtype, device=self.device)
+        self._arena_gen += 1
 
     def _grow(self, dim, need):
         new = self.caps[dim]
@@ -157,6 +163,7 @@ class DeviceRolloutBuffer:
                 big._ragged = dim
                 self._arena[name] = big
         self.caps[dim] = new
+        self._arena_gen += 1
 
     def _put(self, name, dim, first, arrays, dtype):
         """arrays: one (n_i, ...) array per item -> slots [first, first + len) of arena `name`, zero padded."""
@@ -188,6 +195,7 @@ class DeviceRolloutBuffer:
             cs = np.stack([_np(f["current_state"]).astype(np.float32) for f in feats], 0)
             if "current_state" not in self._arena:
                 self._arena["current_state"] = torch.zeros((self.buffer_capacity, 1, cs.shape[1]), dtype=torch.float32, device=self.device)
+                self._arena_gen += 1
             self._arena["current_state"][first:first + len(feats), 0] = torch.from_numpy(cs).to(self.device)
         for bkey, terms in _GROUP_TERMS.items():
             if bkey in items:
@@ -195,38 +203,54 @@ class DeviceRolloutBuffer:
                     self._put(name, "R", first, [_np(d[sub]) for d in items[bkey]], dtype)
 
     # ------------------------------------------------------------------ GPU collate
-    def collate_device(self, indices, algo: str = "rift") -> Dict:
+    def collate_device(self, indices, algo: str = "rift", reuse: bool = True) -> Dict:
         """The mini-batch the trainer reads, built on the device from slot indices: equals
-        ``{RIFT,GRPO,PPO,Reinforce}Collate()([buffer.sample(i) for i in indices])`` value for value."""
+        ``{RIFT,GRPO,PPO,Reinforce}Collate()([buffer.sample(i) for i in indices])`` value for value.
+
+        With ``reuse`` (default) the output tensors - and the ``PackedBatch`` object around them - are cached per
+        (algo, batch size, padded extents) and OVERWRITTEN by the next call of the same shape, like a loader's staging
+        buffer: the trainer's step graph then takes the batch in place as its static input (no per-step copies, one graph
+        per shape).  ``reuse=False`` returns fresh tensors."""
         idx_host = np.asarray(indices, np.int64)
         bs = len(idx_host)
-        idx = torch.from_numpy(idx_host).to(self.device, non_blocking=True)
         n_b = {d: int(self._extent[d][idx_host].max()) for d in ("A", "Mp", "R")}
-        fields, outs = [], {}
+        key = (algo, bs, n_b["A"], n_b["Mp"], n_b["R"], self._arena_generation())
+        slot = self._collate_cache.get(key) if reuse else None
+        if slot is None:
+            fields, outs = [], {}
 
-        def add(name, n_rows):
-            src = self._arena[name]
-            row_bytes = src[0, 0].numel() * src.element_size()
-            dst = torch.empty((bs, n_rows) + tuple(src.shape[2:]), dtype=src.dtype, device=self.device)
-            outs[name] = dst
-            if n_rows > 0:
-                fields.append(_lib.GatherField(src.data_ptr(), dst.data_ptr(), src.shape[1] * row_bytes, n_rows * row_bytes, n_rows * row_bytes))
+            def add(name, n_rows):
+                src = self._arena[name]
+                row_bytes = src[0, 0].numel() * src.element_size()
+                dst = torch.empty((bs, n_rows) + tuple(src.shape[2:]), dtype=src.dtype, device=self.device)
+                outs[name] = dst
+                if n_rows > 0:
+                    fields.append(_lib.GatherField(src.data_ptr(), dst.data_ptr(), src.shape[1] * row_bytes, n_rows * row_bytes, n_rows * row_bytes))
 
-        for _, _, name, dim, _ in _FEATURE_FIELDS:
-            add(name, n_b[dim])
-        add("current_state", 1)
-        for bkey in _ALGO_GROUP_KEYS[algo]:
-            for _, name, _ in _GROUP_TERMS[bkey]:
-                add(name, n_b["R"])
-        arr = (_lib.GatherField * len(fields))(*fields)
-        _lib.check(_lib.lib().rift_b200_gather_fields(arr, len(fields), _lib.ptr(idx), bs, _lib.stream_ptr()), "gather_fields")
-        data = {"agent": {}, "map": {}, "reference_line": {}, "current_state": outs["current_state"][:, 0]}
-        for grp, key, name, _, _ in _FEATURE_FIELDS:
-            data[grp][key] = outs[name]
-        batch = {"cur_pluto_feature_torch": PackedBatch(data, self.device)}
-        for bkey in _ALGO_GROUP_KEYS[algo]:
-            for _, name, dtype in _GROUP_TERMS[bkey]:
-                batch[name] = outs[name].view(torch.bool) if dtype == torch.uint8 else outs[name]
+            for _, _, name, dim, _ in _FEATURE_FIELDS:
+                add(name, n_b[dim])
+            add("current_state", 1)
+            for bkey in _ALGO_GROUP_KEYS[algo]:
+                for _, name, _ in _GROUP_TERMS[bkey]:
+                    add(name, n_b["R"])
+            data = {"agent": {}, "map": {}, "reference_line": {}, "current_state": outs["current_state"][:, 0]}
+            for grp, k, name, _, _ in _FEATURE_FIELDS:
+                data[grp][k] = outs[name]
+            batch = {"cur_pluto_feature_torch": PackedBatch(data, self.device)}
+            for bkey in _ALGO_GROUP_KEYS[algo]:
+                for _, name, dtype in _GROUP_TERMS[bkey]:
+                    batch[name] = outs[name].view(torch.bool) if dtype == torch.uint8 else outs[name]
+            slot = {"arr": (_lib.GatherField * len(fields))(*fields), "n": len(fields), "outs": outs, "batch": batch,
+                    "idx": torch.empty(bs, dtype=torch.int64, device=self.device),
+                    "idx_host": torch.empty(bs, dtype=torch.int64).pin_memory() if self.device.type == "cuda" else torch.empty(bs, dtype=torch.int64)}
+            if reuse:
+                if len(self._collate_cache) >= 16:
+                    self._collate_cache.clear()
+                self._collate_cache[key] = slot
+        slot["idx_host"].copy_(torch.from_numpy(idx_host))
+        slot["idx"].copy_(slot["idx_host"], non_blocking=True)
+        _lib.check(_lib.lib().rift_b200_gather_fields(slot["arr"], slot["n"], _lib.ptr(slot["idx"]), bs, _lib.stream_ptr()), "gather_fields")
+        batch = dict(slot["batch"])
         for bkey, name in _ALGO_EXTRA[algo]:
-            batch[name] = self._extra_dev[bkey].index_select(0, idx)
+            batch[name] = self._extra_dev[bkey].index_select(0, slot["idx"])
         return batch

@@ -68,10 +68,7 @@ inline int flush_wgrads(Ctx& c, int q) {
         RIFT_CUDA_OK(cudaEventRecord(e, from));
         RIFT_CUDA_OK(cudaStreamWaitEvent(to, e, 0));
     }
-    // RIFT_B200_WGRAD_TERMS = 1 | 2 | 3 (experiment; default: what the data-gradient products use).  Weight gradients are leaves of
-    // the backward - a rounding error in them does not propagate - so they tolerate fewer terms than the data gradients.
-    static const int wt = [] { const char* e = getenv("RIFT_B200_WGRAD_TERMS"); const int v = e ? atoi(e) : 0; return (v >= 1 && v <= 3) ? v : 0; }();
-    return launch_wgrad_group(c.pending[q], n, wt ? wt : bwd_terms(), to);
+    return launch_wgrad_group(c.pending[q], n, bwd_terms(), to);
 }
 inline int flush_wgrads(Ctx& c) {
     TRY(flush_wgrads(c, 0));

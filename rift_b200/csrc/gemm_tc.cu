@@ -1316,8 +1316,7 @@ wgrad_group_kernel(const __grid_constant__ WgGroup grp) {
                 const int sp = loc / P.tiles_mn, tmn = loc - sp * P.tiles_mn;
                 const int m0 = (tmn / P.tiles_n) * TC_BM, n0 = (tmn % P.tiles_n) * BN;
                 const int kb0 = sp * P.kb_per_split, kb1 = min(P.num_kb, kb0 + P.kb_per_split);
-                // terms: 3 = A_lo B_hi + A_hi B_lo + A_hi B_hi ; 2 = A_hi (B_lo + B_hi): dY rounded to bf16, X exact to 16 bits ; 1 = A_hi B_hi
-                const bool alo = grp.terms == 3, blo = grp.terms != 1;
+                const bool lo = grp.terms != 1;
                 for (int kb = kb0; kb < kb1; ++kb, ++it) {
                     const int s = it % TC_STAGES;
                     const uint32_t ph = (it / TC_STAGES) & 1;
@@ -1326,17 +1325,17 @@ wgrad_group_kernel(const __grid_constant__ WgGroup grp) {
                     uint8_t* a_lo = a_hi + SM::A_TILE;
                     uint8_t* b_hi = a_lo + SM::A_TILE;
                     uint8_t* b_lo = b_hi + SM::B_TILE;
-                    mbar_arrive_expect_tx(&full[s], (alo ? 2 : 1) * SM::A_TILE + (blo ? 2 : 1) * SM::B_TILE);
+                    mbar_arrive_expect_tx(&full[s], lo ? SM::STAGE : SM::STAGE / 2);
                     const int kr = kb * TC_BK;
 #pragma unroll
                     for (int rb = 0; rb < TC_BM / 64; ++rb) {
                         tma_load_2d(a_hi + rb * TC_BOX, &P.a_hi, &full[s], m0 + rb * 64, kr);
-                        if (alo) tma_load_2d(a_lo + rb * TC_BOX, &P.a_lo, &full[s], m0 + rb * 64, kr);
+                        if (lo) tma_load_2d(a_lo + rb * TC_BOX, &P.a_lo, &full[s], m0 + rb * 64, kr);
                     }
 #pragma unroll
                     for (int rb = 0; rb < BN / 64; ++rb) {
                         tma_load_2d(b_hi + rb * TC_BOX, &P.b_hi, &full[s], n0 + rb * 64, kr);
-                        if (blo) tma_load_2d(b_lo + rb * TC_BOX, &P.b_lo, &full[s], n0 + rb * 64, kr);
+                        if (lo) tma_load_2d(b_lo + rb * TC_BOX, &P.b_lo, &full[s], n0 + rb * 64, kr);
                     }
                 }
             }
@@ -1372,18 +1371,15 @@ wgrad_group_kernel(const __grid_constant__ WgGroup grp) {
                         const uint64_t dah = make_sdesc(a_hi + k * kstep, lbo), dal = make_sdesc(a_lo + k * kstep, lbo);
                         const uint64_t dbh = make_sdesc(b_hi + k * kstep, lbo), dbl = make_sdesc(b_lo + k * kstep, lbo);
                         const uint32_t first = (kb > kb0 || k > 0) ? 1u : 0u;
-                        if (grp.terms == 3) {
+                        if (grp.terms != 1) {
                             umma_bf16(tacc, dal, dbh, idesc, first);
                             umma_bf16(tacc, dah, dbl, idesc, 1);
-                            umma_bf16(tacc, dah, dbh, idesc, 1);
-                        } else if (grp.terms == 2) {
-                            umma_bf16(tacc, dah, dbl, idesc, first);
                             umma_bf16(tacc, dah, dbh, idesc, 1);
                         } else {
                             umma_bf16(tacc, dah, dbh, idesc, first);
                         }
                         if (cs_tile) {
-                            if (grp.terms == 3) {
+                            if (grp.terms != 1) {
                                 umma_bf16(tcs, dal, d_ones, make_idesc_colsum(), first);
                                 umma_bf16(tcs, dah, d_ones, make_idesc_colsum(), 1);
                             } else {
@@ -1515,7 +1511,7 @@ int launch_wgrad_group(const WgradItem* items, int n, int terms, cudaStream_t st
         P.item0 = item0;
         item0 += P.tiles_mn * cdiv(P.num_kb, P.kb_per_split);
     }
-    g.n_problems = n; g.n_items = item0; g.terms = (terms == 1 || terms == 2) ? terms : 3; g.late = tc_late_trigger();
+    g.n_problems = n; g.n_items = item0; g.terms = terms == 1 ? 1 : 3; g.late = tc_late_trigger();
     // grid: one persistent CTA per SM walking the queue, or (RIFT_B200_WGRAD_GROUP_ONESHOT=1) one CTA per work item - short-lived
     // CTAs hand their SM back after every item, so a higher-priority stream gets in between
     static const bool oneshot = [] { const char* e = getenv("RIFT_B200_WGRAD_GROUP_ONESHOT"); return e && atoi(e) != 0; }();
