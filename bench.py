@@ -17,6 +17,10 @@ One "step" = one policy update on one pre-collated synthetic rollout batch: Plan
            inputs resident in HBM, CUDA events around each step, L2 flushed between steps, max over ranks.
 `e2e`    : the same step through LightningTrainer.step() starting from pinned HOST buffers (H2D of the
            rank's batch inside the timed region) and ending with the loss read back to the host.
+`e2e_device_buffer` (N = 1): the same step fed from the device-resident replay buffer - slot indices drawn on the host,
+           one gather launch (DeviceRolloutBuffer.collate_device) into the batch the step graph reads in place, loss read back.
+`roofline` / `roofline_step` / `kernels` : the dominant kernel family replayed alone against the measured HBM copy bandwidth,
+           the whole step against the measured bf16 rate, and the reference-line GEMM + cfg5 advantage kernels.
 `--impl reference` : the CPU oracle port of the reference step on the host cores (torch CPU threads).
 """
 import argparse
