@@ -487,6 +487,72 @@ attention_bwd3_kernel(AttnArgs a, const float* __restrict__ d_o, long long lddo,
     }
 }
 
+// ---- head_dim 32, tiny sequences (S = 6 / 12): one warp per (batch, head) problem, lane = channel; q, k, v, dO and the dK / dV
+// accumulators of the whole problem live in registers (see attention_small_kernel)
+template <int S>
+__global__ void __launch_bounds__(128, 3)
+attention_small_bwd_kernel(AttnArgs a, const float* __restrict__ d_o, long long lddo, float* __restrict__ dq, long long lddq,
+                           float* __restrict__ dk, float* __restrict__ dv, long long lddk, long long lddv, Planes pq, Planes pk, Planes pv) {
+    pdl_grid_sync_sel();
+    constexpr int HD = 32;
+    const int lane = threadIdx.x & 31;
+    const long long prob = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (prob >= (long long)a.B * a.H) return;
+    const int b = (int)(prob / a.H), h = (int)(prob % a.H);
+    const long long krow0 = attn_row_b(b, a.k_inner_n, a.k_outer, a.k_inner);
+    const long long qrow0 = attn_row_b(b, a.q_inner_n, a.q_outer, a.q_inner);
+    const long long orow0 = a.o_custom ? attn_row_b(b, a.o_inner_n, a.o_outer, a.o_inner) : qrow0;
+    const long long oseq = a.o_custom ? a.o_seq : a.q_seq;
+    const uint8_t* kpm = a.kpm ? a.kpm + (long long)(a.kpm_mod > 0 ? (b + a.kpm_off) % a.kpm_mod : b / a.kpm_div) * S : nullptr;
+    float q[S], k[S], v[S], go[S], ak[S], av[S], lse[S];
+    unsigned masked = 0;
+#pragma unroll
+    for (int i = 0; i < S; ++i) {
+        q[i] = a.q[(qrow0 + (long long)i * a.q_seq) * a.ldq + h * HD + lane] * a.scale;
+        const long long r = krow0 + (long long)i * a.k_seq;
+        k[i] = a.k[r * a.ldk + h * HD + lane];
+        v[i] = a.v[r * a.ldv + h * HD + lane];
+        go[i] = d_o[(orow0 + (long long)i * oseq) * lddo + h * HD + lane];
+        lse[i] = a.lse[((long long)b * a.H + h) * S + i];
+        ak[i] = 0.f; av[i] = 0.f;
+        if (kpm && kpm[i]) masked |= 1u << i;
+    }
+#pragma unroll
+    for (int i = 0; i < S; ++i) {
+        const bool dead = (lse[i] == INFINITY);
+        float p[S], dp[S];
+        float dl = 0.f;
+#pragma unroll
+        for (int j = 0; j < S; ++j) {
+            const float sc = warp_sum(q[i] * k[j]);
+            dp[j] = warp_sum(go[i] * v[j]);
+            p[j] = (dead || ((masked >> j) & 1u)) ? 0.f : __expf(sc - lse[i]);
+            dl = fmaf(p[j], dp[j], dl);
+        }
+        float dqv = 0.f;
+#pragma unroll
+        for (int j = 0; j < S; ++j) {
+            const float ds = p[j] * (dp[j] - dl);
+            dqv = fmaf(ds, k[j], dqv);
+            ak[j] = fmaf(ds, q[i], ak[j]);                  // q is pre-scaled: dK carries `scale`
+            av[j] = fmaf(p[j], go[i], av[j]);
+        }
+        const long long dr = a.o_custom ? (orow0 + (long long)i * oseq) : (qrow0 + (long long)i * a.q_seq);
+        if (dq) dq[dr * lddq + h * HD + lane] = dqv * a.scale;
+        if (pq.on()) split_store(pq, dr, h * HD + lane, dqv * a.scale);
+    }
+#pragma unroll
+    for (int j = 0; j < S; ++j) {
+        const long long r = krow0 + (long long)j * a.k_seq;
+        if (dk) { dk[r * lddk + h * HD + lane] = ak[j]; dv[r * lddv + h * HD + lane] = av[j]; }
+        if (pk.on()) { split_store(pk, r, h * HD + lane, ak[j]); split_store(pv, r, h * HD + lane, av[j]); }
+    }
+}
+static bool attention_small_bwd_on() {
+    static const bool on = [] { const char* e = getenv("RIFT_B200_ATTN_SMALL"); return e && atoi(e) != 0; }();   // measured slower: off
+    return on;
+}
+
 // shape-only: will launch_attention_bwd take the kernel above (the one that can write planes)?
 bool attention_bwd_planes_ok(int Sq, int Sk, int hd) {
     static const bool legacy = getenv("RIFT_B200_ATTN_BWD_LEGACY") != nullptr;
@@ -514,6 +580,13 @@ int launch_attention_bwd(const AttnArgs& a, const float* d_o, long long lddo, fl
                          (a.ldq & 3) == 0 && (a.ldk & 3) == 0 && (a.ldv & 3) == 0 && (lddo & 3) == 0 && (lddq & 3) == 0 &&
                          (lddk & 3) == 0 && (lddv & 3) == 0;
         static const bool legacy = getenv("RIFT_B200_ATTN_BWD_LEGACY") != nullptr;
+        if (a.hd == 32 && !legacy && attention_small_bwd_on() && a.Sq == a.Sk && (a.Sq == 6 || a.Sq == 12)) {
+            const unsigned nb = (unsigned)(((long long)a.B * a.H + 3) / 4);
+            if (a.Sq == 6) launch_k(attention_small_bwd_kernel<6>, nb, 128, 0, st, a, d_o, lddo, dq, lddq, dk, dv, lddk, lddv, pl.q, pl.k, pl.v);
+            else launch_k(attention_small_bwd_kernel<12>, nb, 128, 0, st, a, d_o, lddo, dq, lddq, dk, dv, lddk, lddv, pl.q, pl.k, pl.v);
+            RIFT_LAUNCH_OK();
+            return 0;
+        }
         if (vec && !legacy && attention_bwd_tiled(a.Sq, a.Sk, a.hd)) {
             const size_t smem3 = attn_bwd3_smem_floats(a.Sq, a.Sk) * sizeof(float);
             static bool attr3 = false;

@@ -853,6 +853,64 @@ attention3_kernel(AttnArgs a) {
     }
 }
 
+// ---- head_dim 32, tiny sequences (decoder r2r: 6 reference lines, m2m: 12 modes): ONE WARP per (batch, head) problem, lane =
+// channel.  q, k, v of the whole problem live in registers (3 S values per lane, every index a compile-time constant), a score
+// is one warp reduction, soft-max and the P V product are replicated / per-lane: no shared memory, no block barrier.
+// S = compile-time sequence length (Sq == Sk == S).  Same conventions as the kernels above: masked keys are skipped, a row
+// without keys yields 0 and lse = +inf.  EXPERIMENT, off by default (RIFT_B200_ATTN_SMALL=1): the S^2 five-step warp reductions
+// make it slower than the cooperative kernels - forward + backward 89 vs 37 us at 3072 problems of 12 x 12, 36 vs 27 us at 6144
+// of 6 x 6, 8.65 vs 8.23 ms per step.
+template <int S>
+__global__ void __launch_bounds__(128)
+attention_small_kernel(AttnArgs a) {
+    pdl_grid_sync_sel();
+    constexpr int HD = 32;
+    const int lane = threadIdx.x & 31;
+    const long long prob = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (prob >= (long long)a.B * a.H) return;
+    const int b = (int)(prob / a.H), h = (int)(prob % a.H);
+    const long long krow0 = attn_row(b, a.k_inner_n, a.k_outer, a.k_inner);
+    const long long qrow0 = attn_row(b, a.q_inner_n, a.q_outer, a.q_inner);
+    const uint8_t* kpm = a.kpm ? a.kpm + (long long)(a.kpm_mod > 0 ? (b + a.kpm_off) % a.kpm_mod : b / a.kpm_div) * S : nullptr;
+    float q[S], k[S], v[S];
+    unsigned masked = 0;
+#pragma unroll
+    for (int i = 0; i < S; ++i) {
+        q[i] = a.q[(qrow0 + (long long)i * a.q_seq) * a.ldq + h * HD + lane] * a.scale;
+        const long long r = krow0 + (long long)i * a.k_seq;
+        k[i] = a.k[r * a.ldk + h * HD + lane];
+        v[i] = a.v[r * a.ldv + h * HD + lane];
+        if (kpm && kpm[i]) masked |= 1u << i;
+    }
+#pragma unroll
+    for (int i = 0; i < S; ++i) {
+        float sc[S];
+        float m = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < S; ++j) {
+            sc[j] = warp_sum(q[i] * k[j]);
+            if (!((masked >> j) & 1u)) m = fmaxf(m, sc[j]);
+        }
+        float l = 0.f, o = 0.f;
+#pragma unroll
+        for (int j = 0; j < S; ++j) {
+            const float p = ((masked >> j) & 1u) ? 0.f : __expf(sc[j] - m);
+            l += p;
+            o = fmaf(p, v[j], o);
+        }
+        const float inv = l > 0.f ? 1.f / l : 0.f;
+        const long long qr = qrow0 + (long long)i * a.q_seq;
+        const long long orow = a.o_custom ? attn_row(b, a.o_inner_n, a.o_outer, a.o_inner) + (long long)i * a.o_seq : qr;
+        if (a.o) a.o[orow * a.ldo + h * HD + lane] = o * inv;
+        if (a.o_planes.on()) split_store(a.o_planes, orow, h * HD + lane, o * inv);
+        if (a.lse && lane == 0) a.lse[((long long)b * a.H + h) * S + i] = l > 0.f ? m + logf(l) : INFINITY;
+    }
+}
+static bool attention_small_on() {
+    static const bool on = [] { const char* e = getenv("RIFT_B200_ATTN_SMALL"); return e && atoi(e) != 0; }();   // measured slower: off
+    return on;
+}
+
 int launch_attention(const AttnArgs& a, cudaStream_t st) {
     if (a.B <= 0 || a.Sq <= 0) return 0;
     RIFT_REQUIRE(a.hd == 32 || a.hd == 64, "attention: head_dim must be 32 or 64");
@@ -864,6 +922,13 @@ int launch_attention(const AttnArgs& a, cudaStream_t st) {
         const int smax = max(a.Sq, a.Sk);
         const size_t per = attn_fwd2_smem_floats(a.Sq, a.Sk) * sizeof(float);
         static const bool legacy = getenv("RIFT_B200_ATTN_FWD_LEGACY") != nullptr;
+        if (a.hd == 32 && !legacy && attention_small_on() && a.Sq == a.Sk && (a.Sq == 6 || a.Sq == 12)) {
+            const unsigned nb = (unsigned)(((long long)a.B * a.H + 3) / 4);
+            if (a.Sq == 6) launch_k(attention_small_kernel<6>, nb, 128, 0, st, a);
+            else launch_k(attention_small_kernel<12>, nb, 128, 0, st, a);
+            RIFT_LAUNCH_OK();
+            return 0;
+        }
         static const bool tiled = [] { const char* e = getenv("RIFT_B200_ATTN_FWD_TILED"); return !(e && atoi(e) == 0); }();
         if (vec && !legacy && tiled && min(a.Sq, a.Sk) >= 24 && smax <= 128 && attn_fwd3_smem_floats(a.Sq, a.Sk) * sizeof(float) <= 160 * 1024) {
             static bool attr3 = false;

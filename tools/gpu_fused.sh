@@ -1,6 +1,12 @@
 #!/bin/bash
-# scratch script for one gpurun call: the documented runtime switches still give a correct step
+# scratch script for one gpurun call (rewritten per experiment)
 set -x
-for e in RIFT_B200_STREAMS=0 RIFT_B200_PDL=0 RIFT_B200_CUDA_GRAPH=0 RIFT_B200_WGRAD_GROUP=0 RIFT_B200_FUSE_LN_PLANES=0 RIFT_B200_FUSE_ATTN_PLANES=0 RIFT_B200_ATTN_BWD_TILED=0 RIFT_B200_ATTN_FWD_TILED=0 RIFT_B200_WGRAD_ATOMIC=0 RIFT_B200_SMALL_WGRAD_SIDE=0 RIFT_B200_FUSED=1 RIFT_B200_PDL_LATE=0; do
-  echo "== $e"; env $e timeout 300 python -m pytest tests/test_model_gpu.py -m gpu -q -x -k "full_backward_matches_reference_golden or three_policy or baseline_shape_parity_vs_oracle and cfg2-" 2>&1 | tail -1
-done
+timeout 900 python -m pytest tests/test_ops_gpu.py tests/test_model_gpu.py -m gpu -q 2>&1 | grep -E "FAILED|passed|failed" | tail -6
+python tools/attn_probe.py
+RIFT_B200_ATTN_SMALL=0 python tools/attn_probe.py 384 12 8 32
+RIFT_B200_ATTN_SMALL=0 python tools/attn_probe.py 768 6 8 32
+b() { timeout 300 python bench.py --steps 40 --warmup 5 --no-kernels --no-weak --no-cpu --no-devbuf 2>/dev/null | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('$1', d['ms_per_step'], d['e2e']['value'], d['gpu_launches'])"; }
+b SMALL
+RIFT_B200_ATTN_SMALL=0 b NOSMALL
+b SMALL_again
+RIFT_B200_ATTN_SMALL=0 b NOSMALL_again
